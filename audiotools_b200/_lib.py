@@ -1,0 +1,74 @@
+"""ctypes binding of ``libb2a.so`` (C ABI declared in ``include/b2a.h``).
+
+The library is built in-tree by ``audiotools_b200/_build.py`` (nvcc, sm_100a) and
+lives next to the sources in ``audiotools_b200/csrc/``.  There is no fallback: if
+the shared object is missing or does not load, importing the engine raises.
+"""
+import ctypes
+import os
+from ctypes import POINTER, c_char_p, c_double, c_float, c_int, c_int32, c_int64, c_size_t, c_void_p
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "csrc", "libb2a.so")
+
+B2A_OK = 0
+PAD_MODES = {"reflect": 0, "constant": 1, "replicate": 2}
+POST_NONE, POST_LOG10, POST_LN = 0, 1, 2
+
+# name -> (restype, argtypes); must list every symbol include/b2a.h declares
+SIGNATURES = {
+    "b2a_version": (c_int, []),
+    "b2a_last_error": (c_char_p, []),
+    "b2a_stft_num_frames": (c_int64, [c_int64, c_int, c_int, c_int, c_int, c_int]),
+    "b2a_spectral_f32": (c_int, [c_void_p, c_int64, c_int64, c_int, c_int, c_void_p,
+                                 c_int, c_int, c_int, c_int,
+                                 c_void_p, c_int, c_void_p,
+                                 c_void_p, c_void_p, c_void_p, c_int,
+                                 c_int, c_float, c_float,
+                                 c_void_p, c_void_p, c_void_p]),
+    "b2a_lufs_num_blocks": (c_int64, [c_int64, c_double, c_double]),
+    "b2a_lufs_workspace_bytes": (c_size_t, [c_int64, c_int, c_int64, c_double, c_double]),
+    "b2a_lufs_f32": (c_int, [c_void_p, c_int64, c_int, c_int64, c_int64, c_double,
+                             POINTER(c_double), POINTER(c_double), c_int, c_double,
+                             POINTER(c_double), c_void_p, c_void_p, c_void_p,
+                             c_void_p, c_int, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "b2a_gain_f32": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_void_p, c_void_p]),
+}
+
+
+class B2AError(RuntimeError):
+    pass
+
+
+class B2ALibrary:
+    """A loaded ``libb2a`` with typed entry points.  ``check(rc)`` raises ``B2AError``
+    carrying ``b2a_last_error()``; error codes map to the reference's exception types
+    at the AudioSignal layer."""
+
+    def __init__(self, path: str = LIB_PATH):
+        if not os.path.exists(path):
+            raise ImportError(
+                f"{path} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                "(nvcc, sm_100a).  audiotools_b200 has no CPU fallback.")
+        self.path = path
+        self.cdll = ctypes.CDLL(path)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(self.cdll, name)  # AttributeError if the symbol is not exported
+            fn.restype = res
+            fn.argtypes = args
+            setattr(self, name, fn)
+
+    def check(self, rc: int):
+        if rc != B2A_OK:
+            msg = self.b2a_last_error()
+            raise B2AError(f"libb2a error {rc}: {msg.decode() if msg else '?'}")
+
+
+_LIB = None
+
+
+def get_lib() -> B2ALibrary:
+    global _LIB
+    if _LIB is None:
+        _LIB = B2ALibrary(LIB_PATH)
+    return _LIB

@@ -1,0 +1,183 @@
+"""``EffectMixin`` / ``ImpulseResponseMixin``: loudness normalisation, gain, mixing, mel-band
+equaliser, impulse-response convolution and pitch shift with the method surface of
+ref:audiotools/core/effects.py, on the sm_100a engine."""
+import numpy as np
+import torch
+
+from . import util
+
+
+def _engine():
+    from ..engine import get_engine
+
+    return get_engine()
+
+
+class EffectMixin:
+    GAIN_FACTOR = np.log(10) / 20
+    """Gain factor for converting between amplitude and decibels."""
+
+    def mix(self, other, snr=10, other_eq=None):
+        """Add ``other`` at the given signal-to-noise ratio (dB), optionally equalised first (ref :27-64)."""
+        snr = util.ensure_tensor(snr).to(self.device)
+        other.zero_pad(0, max(0, self.signal_length - other.signal_length))
+        other.truncate_samples(self.signal_length)
+        if other_eq is not None:
+            other = other.equalizer(other_eq)
+        other = other.normalize(self.loudness() - snr)
+        self.audio_data = self.audio_data + other.audio_data
+        return self
+
+    def convolve(self, other, start_at_max: bool = True):
+        """CIRCULAR convolution with ``other`` (period = signal length), the IR rolled so that its
+        peak sits at t=0 and scaled by 1/max|IR| (ref :66-123)."""
+        self.audio_data = _engine().circular_convolve(self._materialized(), other.audio_data,
+                                                      roll_to_peak=start_at_max)
+        return self
+
+    def __matmul__(self, other):
+        return self.convolve(other)
+
+    def apply_ir(self, ir, drr=None, ir_eq=None, use_original_phase: bool = False):
+        """Equalise / DRR-alter the impulse response, convolve, restore the input's peak (ref :125-179)."""
+        if ir_eq is not None:
+            ir = ir.equalizer(ir_eq)
+        if drr is not None:
+            ir = ir.alter_drr(drr)
+        max_spk = self.audio_data.abs().max(dim=-1, keepdims=True).values
+        phase = self.phase if use_original_phase else None
+        self.convolve(ir)
+        if use_original_phase:
+            self.stft()
+            self.stft_data = self.magnitude * torch.exp(1j * phase)
+            self.istft()
+        max_transformed = self.audio_data.abs().max(dim=-1, keepdims=True).values
+        scale = max_spk.clamp(1e-8) / max_transformed.clamp(1e-8)
+        self.audio_data = self.audio_data * scale
+        return self
+
+    def ensure_max_of_audio(self, max: float = 1.0):
+        peak = self.audio_data.abs().max(dim=-1, keepdims=True)[0]
+        peak_gain = torch.ones_like(peak)
+        peak_gain[peak > max] = max / peak[peak > max]
+        self.audio_data = self.audio_data * peak_gain
+        return self
+
+    def normalize(self, db=-24.0):
+        """Scale every item to ``db`` LUFS (scalar or [B]) (ref :200-220).  The per-item gain comes
+        out of the loudness kernel; the multiply is deferred and fused into the next kernel that
+        reads the samples (``stft`` / ``mel_spectrogram``) or materialised on first access."""
+        db = util.ensure_tensor(db).to(self.device).float().reshape(-1)
+        if self._loudness is None and self._pending_gain is None:
+            T = self.signal_length
+            padded = T
+            if self.signal_duration < 0.5:
+                padded = T + int((0.5 - self.signal_duration) * self.sample_rate)
+            out = _engine().lufs(self._audio_data, self.sample_rate, padded_length=padded, target_db=db)
+            gain = out["gain"]
+        else:
+            gain = torch.exp((db - self.loudness()) * float(np.float32(self.GAIN_FACTOR)))
+        self._defer_gain(gain)
+        return self
+
+    def volume_change(self, db):
+        """Multiply every item by ``10**(db/20)`` (ref :222-238)."""
+        db = util.ensure_tensor(db, ndim=1).to(self.device).float()
+        gain = torch.exp(db * float(np.float32(self.GAIN_FACTOR)))
+        self._defer_gain(util.ensure_tensor(gain, 1, self.batch_size))
+        return self
+
+    def pitch_shift(self, n_semitones: int, quick: bool = True):
+        """Shift the pitch of every item by ``n_semitones`` keeping the length (ref :247-277, SoX there)."""
+        self.audio_data = _engine().pitch_shift(self._materialized(), self.sample_rate, float(n_semitones),
+                                                quick=quick)
+        return self
+
+    def time_stretch(self, factor: float, quick: bool = True):
+        raise NotImplementedError("time_stretch is outside the accelerated hot path (SURVEY.md §8a a14)")
+
+    def apply_codec(self, *args, **kwargs):
+        raise NotImplementedError("apply_codec calls external lossy codecs: out of scope (SURVEY.md §2 row 3)")
+
+    def mel_filterbank(self, n_bands: int):
+        """Split into ``n_bands`` mel-spaced bands -> [B, C, T, n_bands] (ref :386-403)."""
+        return _engine().mel_filterbank(self._materialized(), self.sample_rate, n_bands)
+
+    def equalizer(self, db):
+        """Mel-spaced band equaliser; band weights are ``10**db`` exactly as in the reference (ref :405-433).
+        The band split and the weighted sum collapse into ONE FIR per item."""
+        db = util.ensure_tensor(db)
+        if db.ndim == 2:
+            if db.shape[0] != 1:
+                assert db.shape[0] == self.batch_size
+        else:
+            db = db.unsqueeze(0)
+        self.audio_data = _engine().equalizer(self._materialized(), self.sample_rate, db.to(self.device))
+        return self
+
+    def clip_distortion(self, clip_percentile):
+        clip_percentile = util.ensure_tensor(clip_percentile, ndim=1)
+        min_thresh = torch.quantile(self.audio_data, clip_percentile / 2, dim=-1)
+        max_thresh = torch.quantile(self.audio_data, 1 - (clip_percentile / 2), dim=-1)
+        nc = self.audio_data.shape[1]
+        self.audio_data = self.audio_data.clamp(min_thresh[:, :nc, :], max_thresh[:, :nc, :])
+        return self
+
+    def quantization(self, quantization_channels):
+        q = util.ensure_tensor(quantization_channels, ndim=3).to(self.device)
+        x = self.audio_data
+        x = (x + 1) / 2
+        x = (x * q).floor() / q
+        self.audio_data = 2 * x - 1
+        return self
+
+    def mulaw_quantization(self, quantization_channels):
+        mu = util.ensure_tensor(quantization_channels, ndim=3).to(self.device) - 1.0
+        x = self.audio_data
+        x = torch.sign(x) * torch.log1p(mu * torch.abs(x)) / torch.log1p(mu)
+        x = ((x + 1) / 2 * mu + 0.5).to(torch.int64)
+        x = (x / mu) * 2 - 1.0
+        self.audio_data = torch.sign(x) * (torch.exp(torch.abs(x) * torch.log1p(mu)) - 1.0) / mu
+        return self
+
+
+class ImpulseResponseMixin:
+    """Impulse-response augmentation of Bryan (ICASSP 2020): early/late split around the direct
+    path, DRR measurement and alteration (ref :529-647)."""
+
+    def decompose_ir(self):
+        x = self.audio_data
+        td = torch.argmax(x, dim=-1, keepdim=True)
+        t0 = int(self.sample_rate * 0.0025)
+        idx = torch.arange(x.shape[-1], device=self.device)[None, None, :].expand(self.batch_size, -1, -1)
+        early_idx = (idx >= td - t0) * (idx <= td + t0)
+        early = torch.where(early_idx, x, torch.zeros_like(x))
+        late = torch.where(early_idx, torch.zeros_like(x), x)
+        window = torch.zeros_like(x)
+        for b in range(self.batch_size):
+            widx = early_idx[b, 0].nonzero()
+            window[b, ..., widx] = self.get_window("hann", widx.shape[-1], self.device)
+        return early, late, window
+
+    def measure_drr(self):
+        early, late, _ = self.decompose_ir()
+        return 10 * torch.log10((early ** 2).sum(dim=-1) / (late ** 2).sum(dim=-1))
+
+    @staticmethod
+    def solve_alpha(early_response, late_field, wd, target_drr):
+        e_sq = early_response ** 2
+        a = ((wd ** 2) * e_sq).sum(dim=-1)
+        b = (2 * (1 - wd) * wd * e_sq).sum(dim=-1)
+        c = (((1 - wd) ** 2) * e_sq).sum(dim=-1) - torch.pow(10, target_drr / 10) * (late_field ** 2).sum(dim=-1)
+        expr = ((b ** 2) - 4 * a * c).sqrt()
+        return torch.maximum((-b - expr) / (2 * a), (-b + expr) / (2 * a))
+
+    def alter_drr(self, drr):
+        drr = util.ensure_tensor(drr, 2, self.batch_size).to(self.device)
+        early, late, window = self.decompose_ir()
+        alpha = self.solve_alpha(early, late, window, drr)
+        min_alpha = late.abs().max(dim=-1)[0] / early.abs().max(dim=-1)[0]
+        alpha = torch.maximum(alpha, min_alpha)[..., None]
+        self.audio_data = alpha * window * early + ((1 - window) * early) + late
+        self.ensure_max_of_audio()
+        return self

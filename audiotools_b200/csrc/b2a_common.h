@@ -1,0 +1,111 @@
+// b2a_common.h -- shared helpers of the sm_100a kernels behind include/b2a.h.
+//
+// The same sources compile two ways:
+//   nvcc -gencode arch=compute_100a,code=sm_100a   -> libb2a.so (the product)
+//   g++ -x c++ -DB2A_SIM -include tests/cusim/cusim.h -> test-only CPU execution of the
+//     identical kernel bodies (tests/cusim); inline PTX is compiled out there.
+#pragma once
+#ifndef B2A_SIM
+#include <cuda_runtime.h>
+#endif
+#include <math.h>
+#include <stdarg.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "../../include/b2a.h"
+
+#define B2A_NUM_SMS 148  // B200: 2 dies x 74 SMs
+
+// ---------------------------------------------------------------------------------------
+// error plumbing (thread-local message, integer codes; nothing throws)
+// ---------------------------------------------------------------------------------------
+namespace b2a {
+char* err_buf();
+int fail(int code, const char* fmt, ...);
+}  // namespace b2a
+
+#define B2A_REQUIRE(cond, code, ...) \
+  do {                               \
+    if (!(cond)) return b2a::fail((code), __VA_ARGS__); \
+  } while (0)
+
+#define B2A_CUDA_OK(expr)                                                                   \
+  do {                                                                                      \
+    cudaError_t e__ = (expr);                                                               \
+    if (e__ != cudaSuccess)                                                                 \
+      return b2a::fail(B2A_E_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e__), \
+                       __FILE__, __LINE__);                                                 \
+  } while (0)
+
+// ---------------------------------------------------------------------------------------
+// launch + dynamic shared memory, CUDA vs sim
+// ---------------------------------------------------------------------------------------
+#ifdef B2A_SIM
+#define B2A_LAUNCH(kernel, grid, block, smem, stream, ...) \
+  cusim::launch((grid), (block), (smem), [&] { kernel(__VA_ARGS__); })
+#define B2A_DYN_SMEM(name) unsigned char* name = cusim::ctx()->dyn_smem
+#define B2A_BAR_SYNC(id, nthreads) cusim::named_bar((id), (nthreads))
+#else
+#define B2A_LAUNCH(kernel, grid, block, smem, stream, ...) \
+  kernel<<<(grid), (block), (smem), (cudaStream_t)(stream)>>>(__VA_ARGS__)
+#define B2A_DYN_SMEM(name) extern __shared__ __align__(1024) unsigned char name[]
+// named barrier over a sub-set of the CTA's warps (ids 1..15; 0 is __syncthreads)
+#define B2A_BAR_SYNC(id, nthreads) asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory")
+#endif
+
+namespace b2a {
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// acquire / release on a 32-bit flag in global memory (decoupled look-back)
+__device__ __forceinline__ void st_release(int* p, int v) {
+#ifdef B2A_SIM
+  __atomic_store_n(p, v, __ATOMIC_RELEASE);
+#else
+  asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+#endif
+}
+__device__ __forceinline__ int ld_acquire(const int* p) {
+#ifdef B2A_SIM
+  return __atomic_load_n(p, __ATOMIC_ACQUIRE);
+#else
+  int v;
+  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+#endif
+}
+
+// streaming (evict-first) 128-bit global accesses for data touched exactly once
+__device__ __forceinline__ float4 ld_stream4(const float* p) {
+#ifdef B2A_SIM
+  return *reinterpret_cast<const float4*>(p);
+#else
+  float4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+               : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w)
+               : "l"(p));
+  return r;
+#endif
+}
+__device__ __forceinline__ void st_stream4(float* p, float4 v) {
+#ifdef B2A_SIM
+  *reinterpret_cast<float4*>(p) = v;
+#else
+  asm volatile("st.global.L1::no_allocate.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v.x), "f"(v.y),
+               "f"(v.z), "f"(v.w)
+               : "memory");
+#endif
+}
+
+}  // namespace b2a

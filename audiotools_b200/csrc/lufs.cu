@@ -1,0 +1,594 @@
+// lufs.cu -- integrated loudness (ITU-R BS.1770) for [B, C, T] float32 waveforms on sm_100a.
+//
+// Replaces the device work of Meter.integrated_loudness with the exact-IIR semantics of
+// Meter.apply_filter_cpu (ref:audiotools/core/loudness.py:102-126) -- NOT the 512-tap FIR
+// approximation the reference falls back to on CUDA (:69-100) -- followed by the 400 ms / 75 %
+// block energies (:164-174, 214) and the two-pass gating (:208-247).
+//
+// Kernel 1  kweight_energy_kernel   (HBM-bound: reads x exactly once, 4 B/sample)
+//   The cascade of NS biquads is a linear recurrence with a 2*NS-dim state.  Each row is cut
+//   into tiles of 256 threads x 32 samples.  Every thread runs the float32 direct-form-I
+//   recursion over its 32 samples from a ZERO state (phase A); the per-chunk end states are
+//   combined with an affine scan (state' = A^32 state + e): warp shuffles, then warp totals,
+//   then a decoupled look-back across the tiles of the row (exact carry, no truncation of the
+//   38 Hz high-pass tail whose pole radius is 0.9946 @44.1k).  With its true start state each
+//   thread re-runs the recursion (phase B) and accumulates y^2 into "elementary interval" bins:
+//   with K = q*stride + r, interval A_j = [j*stride, j*stride+r), B_j = [j*stride+r, (j+1)*stride),
+//   so that block i = sum_{j=i}^{i+q-1}(A_j + B_j) + A_{i+q} -- bit-exact block indexing for any
+//   rate (K is not always 4*stride, e.g. 11025 Hz).  Warp partials are added into float64 bins.
+// Kernel 2  lufs_gate_kernel        (tiny: one CTA per item)
+//   z -> l -> absolute gate -> relative gate -> LUFS, with the reference's dtypes (float32 z,
+//   float64 logs) and its NaN / inf scrubbing; optionally max(.,-70) and normalize()'s gain.
+#include "b2a_common.h"
+
+namespace b2a {
+namespace lufs {
+
+constexpr int L = 32;              // samples per thread chunk
+constexpr int THREADS = 256;       // threads per CTA
+constexpr int NW = THREADS / 32;   // warps per CTA
+constexpr int TILE = L * THREADS;  // samples per tile (8192)
+constexpr int MAX_STAGES = 2;
+
+template <int NS>
+struct Coef {  // float32-rounded, a0-normalised, stage gain folded into b
+  float b0[NS], b1[NS], b2[NS], a1[NS], a2[NS];
+};
+
+template <int NS>
+struct Tables {
+  static constexpr int D = 2 * NS;
+  float Mlane[32][D * D];  // A^(L*l), l = 0..31   (chunk-start state from the warp carry)
+  float Mscan[5][D * D];   // A^(L*2^k)            (warp shuffle scan)
+  double Mwarp[D * D];     // A^(L*32)
+  double Mtile[D * D];     // A^(TILE)
+};
+
+__host__ __device__ inline size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
+
+struct WsLayout {
+  size_t ticket, flags, bins, zeroed_bytes, agg, incl, tables, zws, total;
+};
+__host__ inline WsLayout ws_layout(int64_t rows, int64_t ntile, int64_t nbins, int64_t nblk, int D) {
+  WsLayout w;
+  size_t o = 0;
+  w.ticket = o; o += 256;
+  w.flags = o; o = align256(o + sizeof(int) * rows * ntile);
+  w.bins = o; o = align256(o + sizeof(double) * rows * nbins);
+  w.zeroed_bytes = o;
+  w.agg = o; o = align256(o + sizeof(double) * D * rows * ntile);
+  w.incl = o; o = align256(o + sizeof(double) * D * rows * ntile);
+  w.tables = o; o = align256(o + sizeof(Tables<MAX_STAGES>));
+  w.zws = o; o = align256(o + sizeof(float) * rows * nblk);
+  w.total = o;
+  return w;
+}
+
+// one step of the cascade (float32 DF-I, the arithmetic torchaudio.lfilter performs per stage)
+template <int NS, class F>
+__host__ __device__ __forceinline__ F cascade_step(const F (&b0)[NS], const F (&b1)[NS], const F (&b2)[NS],
+                                                    const F (&a1)[NS], const F (&a2)[NS], F in0, F in1, F in2,
+                                                    F (&y1)[NS], F (&y2)[NS]) {
+#pragma unroll
+  for (int s = 0; s < NS; ++s) {
+    F f = b0[s] * in0 + (b1[s] * in1 + b2[s] * in2);
+    F y0 = f - a2[s] * y2[s] - a1[s] * y1[s];
+    in0 = y0; in1 = y1[s]; in2 = y2[s];
+    y2[s] = y1[s]; y1[s] = y0;
+  }
+  return in0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// setup: state-transition matrix powers, float64, one thread
+// ---------------------------------------------------------------------------------------------
+template <int D>
+__device__ void matmul(const double* a, const double* b, double* c) {
+  double t[D * D];
+  for (int i = 0; i < D; ++i)
+    for (int j = 0; j < D; ++j) {
+      double s = 0;
+      for (int k = 0; k < D; ++k) s += a[i * D + k] * b[k * D + j];
+      t[i * D + j] = s;
+    }
+  for (int i = 0; i < D * D; ++i) c[i] = t[i];
+}
+
+template <int NS>
+__global__ void lufs_setup_kernel(Coef<NS> cf, Tables<NS>* tb) {
+  constexpr int D = 2 * NS;
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  double b0[NS], b1[NS], b2[NS], a1[NS], a2[NS];
+  for (int s = 0; s < NS; ++s) {
+    b0[s] = cf.b0[s]; b1[s] = cf.b1[s]; b2[s] = cf.b2[s]; a1[s] = cf.a1[s]; a2[s] = cf.a2[s];
+  }
+  double A[D * D];
+  for (int k = 0; k < D; ++k) {  // column k = one zero-input step applied to basis vector e_k
+    double y1[NS], y2[NS];
+    for (int s = 0; s < NS; ++s) { y1[s] = (k == 2 * s) ? 1.0 : 0.0; y2[s] = (k == 2 * s + 1) ? 1.0 : 0.0; }
+    cascade_step<NS, double>(b0, b1, b2, a1, a2, 0.0, 0.0, 0.0, y1, y2);
+    for (int s = 0; s < NS; ++s) { A[(2 * s) * D + k] = y1[s]; A[(2 * s + 1) * D + k] = y2[s]; }
+  }
+  double P[D * D];  // A^L
+  for (int i = 0; i < D * D; ++i) P[i] = A[i];
+  for (int l = 1; l < L; l <<= 1) matmul<D>(P, P, P);
+  double Q[D * D];
+  for (int i = 0; i < D * D; ++i) Q[i] = (i / D == i % D) ? 1.0 : 0.0;
+  for (int l = 0; l < 32; ++l) {
+    for (int i = 0; i < D * D; ++i) tb->Mlane[l][i] = (float)Q[i];
+    matmul<D>(P, Q, Q);
+  }
+  for (int i = 0; i < D * D; ++i) tb->Mwarp[i] = Q[i];  // P^32
+  double S[D * D];
+  for (int i = 0; i < D * D; ++i) S[i] = P[i];
+  for (int k = 0; k < 5; ++k) {
+    for (int i = 0; i < D * D; ++i) tb->Mscan[k][i] = (float)S[i];
+    matmul<D>(S, S, S);
+  }
+  for (int i = 0; i < D * D; ++i) S[i] = Q[i];
+  for (int w = 1; w < NW; w <<= 1) matmul<D>(S, S, S);  // (P^32)^NW, NW is a power of two
+  for (int i = 0; i < D * D; ++i) tb->Mtile[i] = S[i];
+}
+
+// ---------------------------------------------------------------------------------------------
+// main streaming kernel
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ int sx_phys(int p) { return p + (p >> 5); }  // +1 word per 32: conflict-free
+
+template <int NS>
+__global__ void __launch_bounds__(THREADS)
+kweight_energy_kernel(const float* __restrict__ x, int rows, int T, int Tp, int ntile, Coef<NS> cf,
+                      const Tables<NS>* __restrict__ tb, int* __restrict__ ticket, int* __restrict__ flags,
+                      double* __restrict__ agg, double* __restrict__ incl, double* __restrict__ bins,
+                      int stride, int r, int nbins) {
+  constexpr int D = 2 * NS;
+  __shared__ float sx[TILE + 2 + (TILE + 2) / 32 + 1];
+  __shared__ float s_mlane[32][D * D];
+  __shared__ float s_mscan[5][D * D];
+  __shared__ float s_tot[NW][D];
+  __shared__ float s_carry[NW][D];
+  __shared__ double s_c0[NW][D];
+  __shared__ double s_mw[D * D], s_mt[D * D], s_P[D * D], s_v[D];
+  __shared__ int s_ticket;
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid == 0) s_ticket = atomicAdd(ticket, 1);
+  for (int i = tid; i < 32 * D * D; i += THREADS) (&s_mlane[0][0])[i] = (&tb->Mlane[0][0])[i];
+  for (int i = tid; i < 5 * D * D; i += THREADS) (&s_mscan[0][0])[i] = (&tb->Mscan[0][0])[i];
+  if (tid < D * D) { s_mw[tid] = tb->Mwarp[tid]; s_mt[tid] = tb->Mtile[tid]; }
+  __syncthreads();
+  const int tk = s_ticket;
+  const int tile = tk / rows, row = tk - tile * rows;  // tile-major: predecessors hold smaller tickets
+  const int t0 = tile * TILE;
+  const float* xr = x + (size_t)row * (size_t)T;
+
+  // stage x[t0-2 .. t0+TILE) into shared memory (coalesced 128 B per warp-load, zero beyond [0,T))
+#pragma unroll 8
+  for (int p = tid; p < TILE + 2; p += THREADS) {
+    int n = t0 - 2 + p;
+    float v = 0.f;
+    if (n >= 0 && n < T) v = __ldg(xr + n);
+    sx[sx_phys(p)] = v;
+  }
+  __syncthreads();
+
+  float xs[L + 2];
+#pragma unroll
+  for (int i = 0; i < L + 2; ++i) xs[i] = sx[sx_phys(tid * L + i)];
+
+  // ---- phase A: zero-state response of this thread's chunk -> end state e
+  float g[D];
+  {
+    float y1[NS], y2[NS];
+#pragma unroll
+    for (int s = 0; s < NS; ++s) { y1[s] = 0.f; y2[s] = 0.f; }
+#pragma unroll
+    for (int i = 0; i < L; ++i)
+      cascade_step<NS, float>(cf.b0, cf.b1, cf.b2, cf.a1, cf.a2, xs[i + 2], xs[i + 1], xs[i], y1, y2);
+#pragma unroll
+    for (int s = 0; s < NS; ++s) { g[2 * s] = y1[s]; g[2 * s + 1] = y2[s]; }
+  }
+  // ---- inclusive affine scan over the warp's 32 chunks
+#pragma unroll
+  for (int k = 0; k < 5; ++k) {
+    float o[D];
+#pragma unroll
+    for (int j = 0; j < D; ++j) o[j] = __shfl_up_sync(0xffffffffu, g[j], 1u << k);
+    if (lane >= (1 << k)) {
+#pragma unroll
+      for (int i = 0; i < D; ++i) {
+        float acc = g[i];
+#pragma unroll
+        for (int j = 0; j < D; ++j) acc = fmaf(s_mscan[k][i * D + j], o[j], acc);
+        g[i] = acc;
+      }
+    }
+  }
+  float ex[D];  // exclusive prefix within the warp
+#pragma unroll
+  for (int j = 0; j < D; ++j) {
+    ex[j] = __shfl_up_sync(0xffffffffu, g[j], 1);
+    if (lane == 0) ex[j] = 0.f;
+  }
+  if (lane == 31) {
+#pragma unroll
+    for (int j = 0; j < D; ++j) s_tot[warp][j] = g[j];
+  }
+  __syncthreads();
+
+  // ---- tile carry: warp totals -> tile aggregate -> decoupled look-back -> carry into each warp.
+  // Warp 0 does this in float64; lane i owns row i of every mat-vec, vectors live in shared memory.
+  if (warp == 0) {
+    const size_t me = ((size_t)tile * rows + row);
+    const bool rl = lane < D;  // "row lane"
+    double c = 0.0;            // carry for a ZERO incoming state, component `lane`
+    for (int w = 0; w < NW; ++w) {
+      if (rl) s_c0[w][lane] = c;
+      __syncwarp();
+      if (rl) {
+        double a = (double)s_tot[w][lane];
+        for (int j = 0; j < D; ++j) a += s_mw[lane * D + j] * s_c0[w][j];
+        c = a;
+      }
+    }
+    // c == tile aggregate E (end state of the tile for a zero incoming state)
+    double sin_i = 0.0;  // incoming state S_in, component `lane`
+    if (tile > 0) {
+      if (rl) agg[me * D + lane] = c;
+      __threadfence();
+      __syncwarp();
+      if (lane == 0) st_release(&flags[me], 1);
+      if (lane < D * D) s_P[lane] = (lane / D == lane % D) ? 1.0 : 0.0;
+      __syncwarp();
+      for (int tj = tile - 1; tj >= 0; --tj) {
+        const size_t pj = ((size_t)tj * rows + row);
+        int f = 0;
+        if (lane == 0) {
+          do { f = ld_acquire(&flags[pj]); } while (f == 0);
+        }
+        f = __shfl_sync(0xffffffffu, f, 0);
+        if (rl) s_v[lane] = ((f == 2) ? (const volatile double*)incl : (const volatile double*)agg)[pj * D + lane];
+        __syncwarp();
+        if (rl) {
+          double a = sin_i;
+          for (int j = 0; j < D; ++j) a += s_P[lane * D + j] * s_v[j];
+          sin_i = a;
+        }
+        if (f == 2) break;
+        double pn = 0.0;
+        if (lane < D * D) {
+          const int pi = lane / D, pjx = lane % D;
+          for (int k = 0; k < D; ++k) pn += s_P[pi * D + k] * s_mt[k * D + pjx];
+        }
+        __syncwarp();
+        if (lane < D * D) s_P[lane] = pn;
+        __syncwarp();
+      }
+    }
+    if (rl) s_v[lane] = sin_i;
+    __syncwarp();
+    if (rl) {
+      double so = c;
+      for (int j = 0; j < D; ++j) so += s_mt[lane * D + j] * s_v[j];
+      incl[me * D + lane] = so;
+    }
+    __threadfence();
+    __syncwarp();
+    if (lane == 0) st_release(&flags[me], 2);
+    // carry into warp w = c0[w] + Mwarp^w * S_in
+    double cur = sin_i;
+    for (int w = 0; w < NW; ++w) {
+      if (rl) {
+        s_carry[w][lane] = (float)(s_c0[w][lane] + cur);
+        s_v[lane] = cur;
+      }
+      __syncwarp();
+      double nx = 0.0;
+      if (rl)
+        for (int j = 0; j < D; ++j) nx += s_mw[lane * D + j] * s_v[j];
+      __syncwarp();
+      cur = nx;
+    }
+  }
+  __syncthreads();
+
+  // ---- phase B: true start state, recursion again, energies into bins
+  float y1[NS], y2[NS];
+  {
+    float st[D];
+#pragma unroll
+    for (int i = 0; i < D; ++i) {
+      float acc = ex[i];
+#pragma unroll
+      for (int j = 0; j < D; ++j) acc = fmaf(s_mlane[lane][i * D + j], s_carry[warp][j], acc);
+      st[i] = acc;
+    }
+#pragma unroll
+    for (int s = 0; s < NS; ++s) { y1[s] = st[2 * s]; y2[s] = st[2 * s + 1]; }
+  }
+  const int n0 = t0 + tid * L;
+  const int nv = min(L, max(0, Tp - n0));  // samples of this chunk that exist in the padded signal
+  // bin of a sample n: j = n / stride, rem = n - j*stride -> 2j + (rem >= r); A_j is empty when r == 0
+  int j0 = n0 / stride, rem0 = n0 - j0 * stride;
+  int b0 = 2 * j0 + (rem0 >= r ? 1 : 0);
+  int end0 = (b0 & 1) ? (j0 + 1) * stride : j0 * stride + r;  // first sample after bin b0
+  int s1 = min(end0 - n0, L);
+  const bool simple = (s1 >= L) && (nv == L);
+  const int b0_first = __shfl_sync(0xffffffffu, b0, 0), b0_last = __shfl_sync(0xffffffffu, b0, 31);
+  const bool fast = __all_sync(0xffffffffu, simple) && (b0_first == b0_last);
+  double* rb = bins + (size_t)row * (size_t)nbins;
+  if (fast) {
+    float acc = 0.f;
+#pragma unroll
+    for (int i = 0; i < L; ++i) {
+      float y = cascade_step<NS, float>(cf.b0, cf.b1, cf.b2, cf.a1, cf.a2, xs[i + 2], xs[i + 1], xs[i], y1, y2);
+      acc = fmaf(y, y, acc);
+    }
+    acc = warp_sum(acc);
+    if (lane == 0) atomicAdd(rb + b0, (double)acc);
+  } else {
+    int s2 = L, b1 = b0, b2 = b0;
+    if (s1 < L) {
+      int n1 = n0 + s1, j1 = n1 / stride, rem1 = n1 - j1 * stride;
+      b1 = 2 * j1 + (rem1 >= r ? 1 : 0);
+      int end1 = (b1 & 1) ? (j1 + 1) * stride : j1 * stride + r;
+      s2 = min(end1 - n0, L);
+      if (s2 < L) {
+        int n2 = n0 + s2, j2 = n2 / stride, rem2 = n2 - j2 * stride;
+        b2 = 2 * j2 + (rem2 >= r ? 1 : 0);
+      }
+    }
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < L; ++i) {
+      float y = cascade_step<NS, float>(cf.b0, cf.b1, cf.b2, cf.a1, cf.a2, xs[i + 2], xs[i + 1], xs[i], y1, y2);
+      float e = (i < nv) ? y * y : 0.f;
+      a0 += (i < s1) ? e : 0.f;
+      a1 += (i >= s1 && i < s2) ? e : 0.f;
+      a2 += (i >= s2) ? e : 0.f;
+    }
+    if (nv > 0) {
+      atomicAdd(rb + b0, (double)a0);
+      if (s1 < nv) atomicAdd(rb + b1, (double)a1);
+      if (s2 < nv) atomicAdd(rb + b2, (double)a2);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// gating: ref:audiotools/core/loudness.py:208-247 (+ :315-320 clamp, effects.py:214-217 gain)
+// ---------------------------------------------------------------------------------------------
+constexpr int GT = 128;
+
+template <class T>
+__device__ T block_sum(T v, T* scratch) {
+  __syncthreads();
+  scratch[threadIdx.x] = v;
+  __syncthreads();
+  for (int s = GT / 2; s > 0; s >>= 1) {
+    if ((int)threadIdx.x < s) scratch[threadIdx.x] += scratch[threadIdx.x + s];
+    __syncthreads();
+  }
+  return scratch[0];
+}
+
+struct GateParams {
+  double G[8];
+  float scale;  // float32(1 / (block_s * rate))
+  int C, nblk, nbins, q;
+};
+
+__global__ void __launch_bounds__(GT)
+lufs_gate_kernel(const double* __restrict__ bins, GateParams gp, float* __restrict__ zws,
+                 float* __restrict__ z_out, float* __restrict__ lufs_out, float* __restrict__ loud_out,
+                 const float* __restrict__ target_db, int n_target, float* __restrict__ gain_out) {
+  __shared__ double sd[GT];
+  __shared__ int si[GT];
+  const int b = blockIdx.x, C = gp.C, nblk = gp.nblk, q = gp.q;
+  const int tid = threadIdx.x;
+  float* z = zws + (size_t)b * C * nblk;
+  // z[c][i] = float32(sum of the block's interval energies) * float32(1/(T_g*rate))   (:214)
+  for (int idx = tid; idx < C * nblk; idx += GT) {
+    int c = idx / nblk, i = idx - c * nblk;
+    const double* rb = bins + ((size_t)b * C + c) * gp.nbins;
+    double s = 0.0;
+    for (int j = i; j < i + q; ++j) s += rb[2 * j] + rb[2 * j + 1];
+    s += rb[2 * (i + q)];
+    float zf = (float)s * gp.scale;
+    z[idx] = zf;
+    if (z_out) z_out[(size_t)b * C * nblk + idx] = zf;
+  }
+  __syncthreads();
+  const double Gamma_a = -70.0;
+  // pass 1: absolute gate
+  double sum1[8];
+  for (int c = 0; c < C; ++c) sum1[c] = 0.0;
+  int n1 = 0;
+  for (int i = tid; i < nblk; i += GT) {
+    double acc = 0.0;
+    for (int c = 0; c < C; ++c) acc += gp.G[c] * (double)z[c * nblk + i];
+    double l = -0.691 + 10.0 * log10(acc);
+    // z[l <= Ga] = 0 (a NaN l is NOT zeroed), masked = l > Ga (a NaN l is NOT counted)
+    if (!(l <= Gamma_a))
+      for (int c = 0; c < C; ++c) sum1[c] += (double)z[c * nblk + i];
+    if (l > Gamma_a) n1++;
+  }
+  int n1t = block_sum<int>(n1, si);
+  double gr_acc = 0.0;
+  for (int c = 0; c < C; ++c) {
+    float zs = (float)block_sum<double>(sum1[c], sd);  // float32 sum in the reference
+    float zavg = zs / (float)n1t;                      // 0/0 -> NaN as in the reference
+    gr_acc += (double)zavg * gp.G[c];
+  }
+  const double Gamma_r = -0.691 + 10.0 * log10(gr_acc) - 10.0;
+  // pass 2: absolute + relative gate (comparisons with NaN are false, as in torch)
+  double sum2[8];
+  for (int c = 0; c < C; ++c) sum2[c] = 0.0;
+  int n2 = 0;
+  for (int i = tid; i < nblk; i += GT) {
+    double acc = 0.0;
+    for (int c = 0; c < C; ++c) acc += gp.G[c] * (double)z[c * nblk + i];
+    double l = -0.691 + 10.0 * log10(acc);
+    // z[l <= Ga] = 0; z[l <= Gr] = 0  ->  a block survives iff !(l <= Ga) && !(l <= Gr)
+    bool zeroed = (l <= Gamma_a) || (l <= Gamma_r);
+    if (!zeroed)
+      for (int c = 0; c < C; ++c) sum2[c] += (double)z[c * nblk + i];
+    if ((l > Gamma_a) && (l > Gamma_r)) n2++;
+  }
+  int n2t = block_sum<int>(n2, si);
+  double lacc = 0.0;
+  for (int c = 0; c < C; ++c) {
+    float zs = (float)block_sum<double>(sum2[c], sd);
+    float zavg = zs / (float)n2t;
+    if (zavg != zavg) zavg = 0.f;                              // nan -> 0          (:240-242)
+    if (zavg == INFINITY) zavg = 3.4028234663852886e38f;       // +inf -> f32 max   (:243)
+    if (zavg == -INFINITY) zavg = -3.4028234663852886e38f;     // -inf -> f32 min   (:244)
+    lacc += gp.G[c] * (double)zavg;
+  }
+  if (tid == 0) {
+    float lufs = (float)(-0.691 + 10.0 * log10(lacc));
+    lufs_out[b] = lufs;
+    float loud = fmaxf(lufs, -70.0f);  // MIN_LOUDNESS (:265, :315-320)
+    if (loud_out) loud_out[b] = loud;
+    if (gain_out) {
+      float db = target_db[n_target == 1 ? 0 : b];
+      float gdb = db - loud;
+      gain_out[b] = expf(gdb * 0.11512925464970229f);  // GAIN_FACTOR = ln(10)/20 (effects.py:12)
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// per-item gain
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+gain_kernel(const float* __restrict__ x, float* __restrict__ out, int64_t per_item, const float* __restrict__ gain,
+            int vec_ok) {
+  const int b = blockIdx.y;
+  const float g = __ldg(gain + b);
+  const float* xi = x + (size_t)b * per_item;
+  float* oi = out + (size_t)b * per_item;
+  const int64_t nthreads = (int64_t)gridDim.x * blockDim.x;
+  const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (vec_ok) {
+    const int64_t n4 = per_item >> 2;
+    for (int64_t i = gid; i < n4; i += nthreads) {
+      float4 v = ld_stream4(xi + 4 * i);
+      v.x *= g; v.y *= g; v.z *= g; v.w *= g;
+      st_stream4(oi + 4 * i, v);
+    }
+    for (int64_t i = (n4 << 2) + gid; i < per_item; i += nthreads) oi[i] = xi[i] * g;
+  } else {
+    for (int64_t i = gid; i < per_item; i += nthreads) oi[i] = xi[i] * g;
+  }
+}
+
+struct Geometry {
+  int K, stride, q, r, nblk, nbins, ntile;
+};
+static int geometry(int64_t Tp, double rate, double block_s, Geometry* g) {
+  double kf = block_s * rate;
+  int64_t K = (int64_t)kf;                 // int(T_g * rate)            (:168)
+  int64_t stride = (int64_t)(kf * 0.25);   // int(T_g * rate * step)     (:169)
+  if (K < 1 || stride < 64) return -1;
+  int64_t d = (Tp > K ? Tp : K) - K;
+  int64_t nblk = (d + stride - 1) / stride + 1;  // julius.core.unfold
+  g->K = (int)K; g->stride = (int)stride; g->q = (int)(K / stride); g->r = (int)(K % stride);
+  g->nblk = (int)nblk;
+  g->nbins = 2 * (int)(nblk + g->q);
+  g->ntile = (int)((Tp + TILE - 1) / TILE);
+  return 0;
+}
+
+template <int NS>
+static int run(const float* x, int64_t B, int C, int64_t T, int64_t Tp, const Geometry& g, const double* sos_h,
+               const double* stage_gain_h, double rate, double block_s, const double* chan_gain_h,
+               float* z_blocks, float* lufs_out, float* loud_out, const float* target_db, int n_target,
+               float* gain_out, void* ws, size_t ws_bytes, void* stream) {
+  const int64_t rows = B * C;
+  WsLayout w = ws_layout(rows, g.ntile, g.nbins, g.nblk, 2 * MAX_STAGES);
+  B2A_REQUIRE(ws_bytes >= w.total, B2A_E_INVALID, "lufs: workspace too small (%zu < %zu)", ws_bytes, w.total);
+  Coef<NS> cf;
+  for (int s = 0; s < NS; ++s) {
+    const double* c = sos_h + 6 * s;
+    B2A_REQUIRE(c[3] != 0.0, B2A_E_INVALID, "lufs: a0 == 0 in stage %d", s);
+    // the reference casts b and a to float32 (:118-119); lfilter then divides by a0 (== 1.0 for pyloudnorm)
+    float a0 = (float)c[3];
+    float sg = (float)stage_gain_h[s];
+    cf.b0[s] = (float)c[0] / a0 * sg; cf.b1[s] = (float)c[1] / a0 * sg; cf.b2[s] = (float)c[2] / a0 * sg;
+    cf.a1[s] = (float)c[4] / a0; cf.a2[s] = (float)c[5] / a0;
+  }
+  char* base = (char*)ws;
+  Tables<NS>* tb = (Tables<NS>*)(base + w.tables);
+  B2A_CUDA_OK(cudaMemsetAsync(base, 0, w.zeroed_bytes, (cudaStream_t)stream));
+  B2A_LAUNCH(lufs_setup_kernel<NS>, dim3(1), dim3(32), 0, stream, cf, tb);
+  B2A_LAUNCH(kweight_energy_kernel<NS>, dim3((unsigned)(rows * g.ntile)), dim3(THREADS), 0, stream, x, (int)rows,
+             (int)T, (int)Tp, g.ntile, cf, (const Tables<NS>*)tb, (int*)(base + w.ticket), (int*)(base + w.flags),
+             (double*)(base + w.agg), (double*)(base + w.incl), (double*)(base + w.bins), g.stride, g.r, g.nbins);
+  GateParams gp;
+  for (int c = 0; c < 8; ++c) gp.G[c] = c < C ? chan_gain_h[c] : 0.0;
+  gp.scale = (float)(1.0 / (block_s * rate));
+  gp.C = C; gp.nblk = g.nblk; gp.nbins = g.nbins; gp.q = g.q;
+  B2A_LAUNCH(lufs_gate_kernel, dim3((unsigned)B), dim3(GT), 0, stream, (const double*)(base + w.bins), gp,
+             (float*)(base + w.zws), z_blocks, lufs_out, loud_out, target_db, n_target, gain_out);
+  B2A_CUDA_OK(cudaGetLastError());
+  return B2A_OK;
+}
+
+}  // namespace lufs
+}  // namespace b2a
+
+using namespace b2a::lufs;
+
+extern "C" int64_t b2a_lufs_num_blocks(int64_t T_padded, double rate, double block_s) {
+  Geometry g;
+  if (T_padded < 1 || geometry(T_padded, rate, block_s, &g) != 0) return -1;
+  return g.nblk;
+}
+
+extern "C" size_t b2a_lufs_workspace_bytes(int64_t B, int C, int64_t T_padded, double rate, double block_s) {
+  Geometry g;
+  if (B < 1 || C < 1 || T_padded < 1 || geometry(T_padded, rate, block_s, &g) != 0) return 0;
+  return ws_layout(B * C, g.ntile, g.nbins, g.nblk, 2 * MAX_STAGES).total;
+}
+
+extern "C" int b2a_lufs_f32(const float* x, int64_t B, int C, int64_t T, int64_t T_padded, double rate,
+                            const double* sos_h, const double* stage_gain_h, int n_stage, double block_s,
+                            const double* chan_gain_h, float* z_blocks, float* lufs_out, float* loud_out,
+                            const float* target_db, int n_target, float* gain_out, void* ws, size_t ws_bytes,
+                            void* stream) {
+  B2A_REQUIRE(x && lufs_out && ws && sos_h && stage_gain_h && chan_gain_h, B2A_E_INVALID, "lufs: null pointer");
+  B2A_REQUIRE(B >= 1 && C >= 1 && T >= 1, B2A_E_INVALID, "lufs: empty input (B=%lld C=%d T=%lld)", (long long)B, C,
+              (long long)T);
+  B2A_REQUIRE(C <= 5, B2A_E_INVALID, "lufs: at most 5 channels have BS.1770 gains (got %d)", C);
+  B2A_REQUIRE(T_padded >= T, B2A_E_INVALID, "lufs: T_padded < T");
+  B2A_REQUIRE(T_padded < (int64_t)2147483647 - 2 * TILE, B2A_E_UNSUPPORTED, "lufs: rows longer than 2^31 samples");
+  B2A_REQUIRE(B * C * ((T_padded + TILE - 1) / TILE) < (int64_t)2147483647, B2A_E_UNSUPPORTED, "lufs: too many tiles");
+  B2A_REQUIRE(n_stage >= 1 && n_stage <= MAX_STAGES, B2A_E_UNSUPPORTED,
+              "lufs: %d biquad stages (1..%d supported: K-weighting has 2)", n_stage, MAX_STAGES);
+  B2A_REQUIRE(!gain_out || (target_db && (n_target == 1 || n_target == B)), B2A_E_INVALID,
+              "lufs: gain_out needs target_db with 1 or B entries");
+  Geometry g;
+  B2A_REQUIRE(geometry(T_padded, rate, block_s, &g) == 0, B2A_E_UNSUPPORTED,
+              "lufs: gating stride int(block_s*rate/4) must be >= 64 samples (rate=%g block_s=%g)", rate, block_s);
+  if (n_stage == 1)
+    return run<1>(x, B, C, T, T_padded, g, sos_h, stage_gain_h, rate, block_s, chan_gain_h, z_blocks, lufs_out,
+                  loud_out, target_db, n_target, gain_out, ws, ws_bytes, stream);
+  return run<2>(x, B, C, T, T_padded, g, sos_h, stage_gain_h, rate, block_s, chan_gain_h, z_blocks, lufs_out,
+                loud_out, target_db, n_target, gain_out, ws, ws_bytes, stream);
+}
+
+extern "C" int b2a_gain_f32(const float* x, float* out, int64_t B, int64_t per_item, const float* gain,
+                            void* stream) {
+  B2A_REQUIRE(x && out && gain, B2A_E_INVALID, "gain: null pointer");
+  B2A_REQUIRE(B >= 1 && per_item >= 1 && B <= 65535, B2A_E_INVALID, "gain: bad shape");
+  int vec_ok = (((uintptr_t)x | (uintptr_t)out) % 16 == 0) && (per_item % 4 == 0);
+  int64_t work = vec_ok ? per_item / 4 : per_item;
+  int64_t want = (work + 255) / 256;
+  // ~8 resident CTAs per SM in total across the batch; grid-stride inside
+  int64_t cap = (int64_t)B2A_NUM_SMS * 8 / B + 1;
+  unsigned gx = (unsigned)(want < cap ? want : cap);
+  B2A_LAUNCH(gain_kernel, dim3(gx, (unsigned)B), dim3(256), 0, stream, x, out, per_item, gain, vec_ok);
+  B2A_CUDA_OK(cudaGetLastError());
+  return B2A_OK;
+}

@@ -1,0 +1,478 @@
+// spectral.cu -- fused framing -> window -> real FFT -> |.| -> banded mel -> post-op on sm_100a.
+//
+// Replaces the device work of AudioSignal.stft (ref:audiotools/core/audio_signal.py:1123-1212),
+// AudioSignal.mel_spectrogram (:1333-1369), the log-mel of ref:audiotools/metrics/spectral.py:187-190
+// and -- optionally, in the same pass over x -- the x*gain of EffectMixin.normalize
+// (ref:audiotools/core/effects.py:219).  The reference materialises the complex STFT
+// ([64,2,1025,862] c64 = 905 MB at BASELINE cfg2), |.|, a transpose and a matmul; here the
+// spectrum of a frame never leaves the SM.
+//
+// One CTA (256 threads) owns FR consecutive frames of one row:
+//   1. the contiguous sample span those frames cover ((FR-1)*hop + n_fft samples) is loaded ONCE
+//      into shared memory (coalesced 128-bit loads; optional *gain and write-back of the scaled
+//      waveform for the samples the CTA owns); edge tiles resolve torch's two nested paddings
+//      (F.pad(pad, pad+right_pad, mode) then stft(center=True) reflect) per sample, bit-exact in
+//      the frame/sample indexing;
+//   2. G = 256/(N/16) frames are transformed concurrently, N = n_fft/2: the real frame is packed
+//      as N complex points, each thread keeps 16 of them in registers, and a Stockham
+//      auto-sort FFT runs as 2-3 radix-16/8/4/2 passes with one shared-memory exchange between
+//      passes (reads are always lane-consecutive; the strided pass-0 write is padded 17/16).
+//      Twiddles depend only on the thread's role, so they are computed once per CTA (sincospif)
+//      and kept in shared memory in [slot][thread] order (conflict-free);
+//   3. the N-point spectrum is untangled into the n_fft/2+1 real-FFT bins; optional stft_out;
+//   4. |X| -> banded mel projection in FP32 (each Slaney filter touches 2..63 of the 1025 bins:
+//      2013 non-zeros of 131200 at 44.1k/2048/128, so the banded FP32 sum costs 64x fewer FLOPs
+//      than a dense tensor-core GEMM and is exact to FP32 rounding) -> post-op -> tile in shared
+//      memory -> coalesced store along the frame axis.
+#include "b2a_common.h"
+
+namespace b2a {
+namespace spectral {
+
+constexpr int THREADS = 256;
+constexpr int E = 16;  // complex points per thread
+
+// ---------------------------------------------------------------------------------------------
+// small DFTs in registers
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
+__device__ __forceinline__ float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
+__device__ __forceinline__ float2 cmul(float2 a, float2 b) {
+  return make_float2(fmaf(a.x, b.x, -a.y * b.y), fmaf(a.x, b.y, a.y * b.x));
+}
+
+// cos(pi*j/8), j = 0..8
+__device__ __forceinline__ constexpr float cos_pi8(int j) {
+  return j == 0 ? 1.0f
+       : j == 1 ? 0.92387953251128674f
+       : j == 2 ? 0.70710678118654752f
+       : j == 3 ? 0.38268343236508977f
+       : j == 4 ? 0.0f
+       : j == 5 ? -0.38268343236508977f
+       : j == 6 ? -0.70710678118654752f
+       : j == 7 ? -0.92387953251128674f
+                : -1.0f;
+}
+
+// o * W_R^k, W = exp(-2 pi i / R), 0 <= k < R/2, R in {2,4,8,16}
+template <int R, int K>
+__device__ __forceinline__ float2 mul_wr(float2 o) {
+  constexpr int j = 16 * K / R;  // angle = pi*j/8
+  if constexpr (j == 0) {
+    return o;
+  } else if constexpr (j == 4) {  // -i
+    return make_float2(o.y, -o.x);
+  } else if constexpr (j == 2) {  // (1 - i)/sqrt2
+    constexpr float h = 0.70710678118654752f;
+    return make_float2(h * (o.x + o.y), h * (o.y - o.x));
+  } else if constexpr (j == 6) {  // (-1 - i)/sqrt2
+    constexpr float h = 0.70710678118654752f;
+    return make_float2(h * (o.y - o.x), -h * (o.x + o.y));
+  } else {
+    constexpr float c = cos_pi8(j);
+    constexpr float s = cos_pi8(j <= 4 ? 4 - j : j - 4);  // sin(pi j/8)
+    return make_float2(fmaf(o.x, c, o.y * s), fmaf(o.y, c, -o.x * s));  // o * (c - i s)
+  }
+}
+
+template <int R, int S>
+struct DFT {
+  template <int K>
+  static __device__ __forceinline__ void comb(const float2 (&e)[R / 2], const float2 (&o)[R / 2], float2* out) {
+    float2 t = mul_wr<R, K>(o[K]);
+    out[K] = cadd(e[K], t);
+    out[K + R / 2] = csub(e[K], t);
+    if constexpr (K + 1 < R / 2) comb<K + 1>(e, o, out);
+  }
+  // in: R values at in[0], in[S], ...; out: R values, natural frequency order
+  static __device__ __forceinline__ void run(const float2* in, float2* out) {
+    float2 e[R / 2], o[R / 2];
+    DFT<R / 2, 2 * S>::run(in, e);
+    DFT<R / 2, 2 * S>::run(in + S, o);
+    comb<0>(e, o, out);
+  }
+};
+template <int S>
+struct DFT<1, S> {
+  static __device__ __forceinline__ void run(const float2* in, float2* out) { out[0] = in[0]; }
+};
+
+// ---------------------------------------------------------------------------------------------
+// compile-time FFT plan for N = 2^LOG2N complex points, 16 points per thread
+// ---------------------------------------------------------------------------------------------
+template <int LOG2N>
+struct Plan {
+  static constexpr int N = 1 << LOG2N;
+  static constexpr int TPF = N / E;          // threads per frame
+  static constexpr int G = THREADS / TPF;    // frames in flight per CTA
+  static constexpr int P = (LOG2N + 3) / 4;  // passes
+  static constexpr int radix(int p) {        // 16,16,...,rest
+    return (p < LOG2N / 4) ? 16 : (1 << (LOG2N % 4));
+  }
+  static constexpr int ns(int p) { return 1 << (4 * p); }  // product of earlier radices
+  // twiddle slots of pass p (p >= 1): (16/R) butterflies x (R-1) factors
+  static constexpr int slots(int p) { return p == 0 ? 0 : (E / radix(p)) * (radix(p) - 1); }
+  static constexpr int slot_off(int p) {
+    int o = 0;
+    for (int i = 1; i < p; ++i) o += slots(i);
+    return o;
+  }
+  static constexpr int NSLOT = slot_off(P);
+  static constexpr int BUF = N + N / 16 + 1;  // padded complex work buffer per frame
+  static constexpr int MAG = N + 4;           // floats per frame (N+1 used)
+  // frames per CTA: enough rounds to amortise the span load, bounded shared memory
+  static constexpr int FR = (G >= 16) ? G : ((LOG2N >= 11) ? 2 * G : ((LOG2N == 10) ? 4 * G : 16));
+};
+
+struct Params {
+  const float* x;
+  const float* window;
+  const float* gain;
+  float* y_out;
+  const float* mel_fb;
+  const int32_t* mel_lo;
+  const int32_t* mel_hi;
+  float* mel_out;
+  float2* stft_out;
+  int rows, T, n_fft, hop, pad, right_pad, pad_mode, drop_edge;
+  int n_frames, n_tiles, n_mels, rows_per_gain, post;
+  float post_eps, post_power;
+  int span;  // (FR-1)*hop + n_fft
+  // shared memory offsets (bytes)
+  int off_win, off_tw, off_ut, off_buf, off_mag, off_mel, smem_bytes;
+};
+
+// index of sample `w` (in un-padded x coordinates, may be outside [0,T)) after torch's two
+// paddings; -1 => zero.   ref:audiotools/core/audio_signal.py:1192-1202
+__device__ __forceinline__ int src_index(int w, int T, int pad, int right_pad, int pad_mode) {
+  const int Lp = T + 2 * pad + right_pad;
+  int v = w + pad;  // position in the F.pad-ed signal
+  if (v < 0) v = -v;                       // torch.stft(center=True): reflect, no edge repeat
+  else if (v >= Lp) v = 2 * (Lp - 1) - v;
+  if (v < 0 || v >= Lp) return -1;         // only reachable from frames past the end (never stored)
+  int u = v - pad;
+  if (u >= 0 && u < T) return u;
+  if (pad_mode == B2A_PAD_REFLECT) u = u < 0 ? -u : 2 * (T - 1) - u;
+  else if (pad_mode == B2A_PAD_REPLICATE) u = u < 0 ? 0 : T - 1;
+  else return -1;
+  return (u >= 0 && u < T) ? u : -1;
+}
+
+template <int TPF>
+__device__ __forceinline__ void group_sync(int g) {
+  if constexpr (TPF >= 64) {
+    B2A_BAR_SYNC(1 + g, TPF);
+  } else {
+    __syncwarp();
+  }
+}
+
+template <int LOG2N>
+__device__ __forceinline__ int buf_phys(int i) { return i + (i >> 4); }
+
+// one Stockham pass p >= 1 on the 16 register-resident points of this thread
+template <int LOG2N, int PASS>
+__device__ __forceinline__ void fft_pass(float2 (&v)[E], float2* buf, const float2* tw, int q) {
+  using PL = Plan<LOG2N>;
+  constexpr int R = PL::radix(PASS), NS = PL::ns(PASS), B = E / R, TPF = PL::TPF;
+#pragma unroll
+  for (int b = 0; b < B; ++b) {
+    // twiddle: v[b + B t] *= W_{NS*R}^{k t}
+#pragma unroll
+    for (int t = 1; t < R; ++t) {
+      float2 w = tw[(PL::slot_off(PASS) + b * (R - 1) + (t - 1)) * TPF + q];
+      v[b + B * t] = cmul(v[b + B * t], w);
+    }
+    float2 out[R];
+    DFT<R, B>::run(&v[b], out);
+    const int j = q + TPF * b;
+    const int k = j & (NS - 1);
+    const int base = (j - k) * R + k;
+#pragma unroll
+    for (int t = 0; t < R; ++t) buf[buf_phys<LOG2N>(base + t * NS)] = out[t];
+  }
+}
+
+template <int LOG2N>
+__global__ void __launch_bounds__(THREADS) spectral_kernel(Params p) {
+  using PL = Plan<LOG2N>;
+  constexpr int N = PL::N, TPF = PL::TPF, G = PL::G, FR = PL::FR, P = PL::P;
+  B2A_DYN_SMEM(smem);
+  float* sp = reinterpret_cast<float*>(smem);                        // sample span
+  float* win = reinterpret_cast<float*>(smem + p.off_win);           // [n_fft]
+  float2* tw = reinterpret_cast<float2*>(smem + p.off_tw);           // [NSLOT][TPF]
+  float2* ut = reinterpret_cast<float2*>(smem + p.off_ut);           // [N/2+1]  exp(-i pi k / N)
+  float2* bufs = reinterpret_cast<float2*>(smem + p.off_buf);        // [G][BUF]
+  float* mags = reinterpret_cast<float*>(smem + p.off_mag);          // [G][MAG]
+  float* melt = reinterpret_cast<float*>(smem + p.off_mel);          // [n_mels][FR+1]
+
+  const int tid = threadIdx.x;
+  const int row = blockIdx.x / p.n_tiles;
+  const int tile = blockIdx.x - row * p.n_tiles;
+  const int n0 = tile * FR;  // first output frame of this CTA
+  const int T = p.T, hop = p.hop, n_fft = 2 * N;
+  const float* xr = p.x + (size_t)row * (size_t)T;
+  const float g = p.gain ? __ldg(p.gain + row / p.rows_per_gain) : 1.0f;
+  const int ws = (n0 + p.drop_edge) * hop - N - p.pad;  // x-coordinate of span[0]
+  const int span = p.span;
+
+  // ---- tables (role-dependent only)
+  for (int i = tid; i < n_fft; i += THREADS) win[i] = __ldg(p.window + i);
+  for (int i = tid; i < PL::NSLOT * TPF; i += THREADS) {
+    const int slot = i / TPF, q = i - slot * TPF;
+    int pass = 1;
+#pragma unroll
+    for (int pp = 1; pp < P; ++pp)
+      if (slot >= PL::slot_off(pp)) pass = pp;
+    const int R = PL::radix(pass), NS = PL::ns(pass);
+    const int s = slot - PL::slot_off(pass);
+    const int b = s / (R - 1), t = s - b * (R - 1) + 1;
+    const int k = (q + TPF * b) & (NS - 1);
+    float sn, cs;
+    sincospif(-2.0f * (float)(k * t) / (float)(NS * R), &sn, &cs);
+    tw[i] = make_float2(cs, sn);
+  }
+  for (int i = tid; i <= N / 2; i += THREADS) {
+    float sn, cs;
+    sincospif(-(float)i / (float)N, &sn, &cs);
+    ut[i] = make_float2(cs, sn);
+  }
+
+  // ---- stage the sample span (x * gain), write back the owned part of the scaled waveform
+  const int own_lo = n0 * hop;  // only used when y_out (pad == 0, drop_edge == 0)
+  const int own_hi = (tile == p.n_tiles - 1) ? T : min(T, (n0 + FR) * hop);
+  const bool interior = (ws >= 0) && (ws + span <= T);
+  if (interior) {
+    const float* src = xr + ws;
+    const bool vec = ((((uintptr_t)src) & 15) == 0) && ((span & 3) == 0) &&
+                     (!p.y_out || (((uintptr_t)(p.y_out + (size_t)row * T + ws)) & 15) == 0);
+    if (vec) {
+      for (int i = tid * 4; i < span; i += THREADS * 4) {
+        float4 v = *reinterpret_cast<const float4*>(src + i);
+        if (p.gain) { v.x *= g; v.y *= g; v.z *= g; v.w *= g; }
+        *reinterpret_cast<float4*>(sp + i) = v;
+        if (p.y_out) {
+          const int w = ws + i;
+          if (w >= own_lo && w + 3 < own_hi) {
+            *reinterpret_cast<float4*>(p.y_out + (size_t)row * T + w) = v;
+          } else {
+            float vv[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e)
+              if (w + e >= own_lo && w + e < own_hi) p.y_out[(size_t)row * T + w + e] = vv[e];
+          }
+        }
+      }
+    } else {
+      for (int i = tid; i < span; i += THREADS) {
+        float v = __ldg(src + i);
+        if (p.gain) v *= g;
+        sp[i] = v;
+        const int w = ws + i;
+        if (p.y_out && w >= own_lo && w < own_hi) p.y_out[(size_t)row * T + w] = v;
+      }
+    }
+  } else {
+    for (int i = tid; i < span; i += THREADS) {
+      const int w = ws + i;
+      const int u = src_index(w, T, p.pad, p.right_pad, p.pad_mode);
+      float v = (u >= 0) ? __ldg(xr + u) : 0.f;
+      if (p.gain) v *= g;
+      sp[i] = v;
+      if (p.y_out && w >= own_lo && w < own_hi) p.y_out[(size_t)row * T + w] = v;  // w in [0,T) => u == w
+    }
+  }
+  if (p.y_out) {  // owned samples the span does not cover (only when hop > n_fft/2)
+    for (int w = max(own_lo, ws + span) + tid; w < own_hi; w += THREADS) {
+      float v = __ldg(xr + w);
+      if (p.gain) v *= g;
+      p.y_out[(size_t)row * T + w] = v;
+    }
+  }
+  __syncthreads();
+
+  const int grp = tid / TPF, q = tid - grp * TPF;
+  float2* buf = bufs + grp * PL::BUF;
+  float* mag = mags + grp * PL::MAG;
+  const int F = N + 1;
+
+  for (int rd = 0; rd < FR / G; ++rd) {
+    const int f = rd * G + grp;  // frame within the tile
+    const int n = n0 + f;        // output frame index
+    const bool live = n < p.n_frames;
+    const float* fs = sp + f * hop;
+
+    // ---- pass 0: windowed real frame packed as N complex points, radix-16, no twiddles
+    float2 v[E];
+    if ((hop & 1) == 0) {
+#pragma unroll
+      for (int m = 0; m < E; ++m) {
+        const int e = q + TPF * m;
+        const float2 s2 = *reinterpret_cast<const float2*>(fs + 2 * e);
+        const float2 w2 = *reinterpret_cast<const float2*>(win + 2 * e);
+        v[m] = make_float2(s2.x * w2.x, s2.y * w2.y);
+      }
+    } else {
+#pragma unroll
+      for (int m = 0; m < E; ++m) {
+        const int e = q + TPF * m;
+        v[m] = make_float2(fs[2 * e] * win[2 * e], fs[2 * e + 1] * win[2 * e + 1]);
+      }
+    }
+    {
+      float2 out[E];
+      DFT<E, 1>::run(v, out);
+#pragma unroll
+      for (int t = 0; t < E; ++t) buf[buf_phys<LOG2N>(q * E + t)] = out[t];
+    }
+    group_sync<TPF>(grp);
+    // ---- passes 1..P-1
+    if constexpr (P >= 2) {
+#pragma unroll
+      for (int m = 0; m < E; ++m) v[m] = buf[buf_phys<LOG2N>(q + TPF * m)];
+      group_sync<TPF>(grp);
+      fft_pass<LOG2N, 1>(v, buf, tw, q);
+      group_sync<TPF>(grp);
+    }
+    if constexpr (P >= 3) {
+#pragma unroll
+      for (int m = 0; m < E; ++m) v[m] = buf[buf_phys<LOG2N>(q + TPF * m)];
+      group_sync<TPF>(grp);
+      fft_pass<LOG2N, 2>(v, buf, tw, q);
+      group_sync<TPF>(grp);
+    }
+
+    // ---- untangle the packed transform into the real-FFT bins k and N-k
+    for (int k = q; k <= N / 2; k += TPF) {
+      const float2 zk = buf[buf_phys<LOG2N>(k)];
+      const float2 zn = buf[buf_phys<LOG2N>((N - k) & (N - 1))];
+      const float2 xe = make_float2(0.5f * (zk.x + zn.x), 0.5f * (zk.y - zn.y));  // (Zk + conj Zn)/2
+      const float2 xo = make_float2(0.5f * (zk.y + zn.y), 0.5f * (zn.x - zk.x));  // (Zk - conj Zn)/(2i)
+      const float2 tt = cmul(ut[k], xo);
+      const float2 xk = cadd(xe, tt);
+      const float2 d = csub(xe, tt);
+      const float2 xnk = make_float2(d.x, -d.y);  // conj(Xe - T)
+      if (p.stft_out && live) {
+        float2* o = p.stft_out + (size_t)row * F * p.n_frames + n;
+        o[(size_t)k * p.n_frames] = xk;
+        o[(size_t)(N - k) * p.n_frames] = xnk;
+      }
+      mag[k] = sqrtf(fmaf(xk.x, xk.x, xk.y * xk.y));
+      mag[N - k] = sqrtf(fmaf(xnk.x, xnk.x, xnk.y * xnk.y));
+    }
+    group_sync<TPF>(grp);
+
+    // ---- banded mel projection + post-op for this frame
+    if (p.mel_out) {
+      for (int m = q; m < p.n_mels; m += TPF) {
+        const int lo = __ldg(p.mel_lo + m), hi = __ldg(p.mel_hi + m);
+        const float* wrow = p.mel_fb + (size_t)m * F;
+        float acc = 0.f;
+        for (int k = lo; k < hi; ++k) acc = fmaf(__ldg(wrow + k), mag[k], acc);
+        if (p.post == B2A_POST_LOG10) {
+          float c = fmaxf(acc, p.post_eps);
+          c = (p.post_power == 2.0f) ? c * c : powf(c, p.post_power);
+          acc = log10f(c);
+        } else if (p.post == B2A_POST_LN) {
+          acc = logf(acc + p.post_eps);
+        }
+        melt[m * (FR + 1) + f] = acc;
+      }
+    }
+    group_sync<TPF>(grp);
+  }
+
+  if (p.mel_out) {
+    __syncthreads();
+    const int nf = min(FR, p.n_frames - n0);
+    float* o = p.mel_out + (size_t)row * p.n_mels * p.n_frames + n0;
+    for (int i = tid; i < p.n_mels * FR; i += THREADS) {
+      const int m = i / FR, f = i - m * FR;
+      if (f < nf) o[(size_t)m * p.n_frames + f] = melt[m * (FR + 1) + f];
+    }
+  }
+}
+
+static inline int align16(int v) { return (v + 15) & ~15; }
+
+template <int LOG2N>
+static int launch(Params& p, void* stream) {
+  using PL = Plan<LOG2N>;
+  p.span = (PL::FR - 1) * p.hop + p.n_fft;
+  p.n_tiles = (p.n_frames + PL::FR - 1) / PL::FR;
+  int o = align16(p.span * 4);
+  p.off_win = o; o = align16(o + p.n_fft * 4);
+  p.off_tw = o; o = align16(o + PL::NSLOT * PL::TPF * 8 + 16);
+  p.off_ut = o; o = align16(o + (PL::N / 2 + 1) * 8);
+  p.off_buf = o; o = align16(o + PL::G * PL::BUF * 8);
+  p.off_mag = o; o = align16(o + PL::G * PL::MAG * 4);
+  p.off_mel = o; o = align16(o + (p.mel_out ? p.n_mels * (PL::FR + 1) * 4 : 0));
+  p.smem_bytes = o;
+  B2A_REQUIRE(o <= 227 * 1024, B2A_E_UNSUPPORTED,
+              "spectral: n_fft=%d hop=%d n_mels=%d needs %d bytes of shared memory (> 227 KB)", p.n_fft, p.hop,
+              p.n_mels, o);
+  B2A_REQUIRE((int64_t)p.rows * p.n_tiles < (int64_t)2147483647, B2A_E_UNSUPPORTED, "spectral: grid too large");
+  B2A_CUDA_OK(cudaFuncSetAttribute(spectral_kernel<LOG2N>, cudaFuncAttributeMaxDynamicSharedMemorySize, o));
+  B2A_LAUNCH(spectral_kernel<LOG2N>, dim3((unsigned)(p.rows * p.n_tiles)), dim3(THREADS), (size_t)o, stream, p);
+  B2A_CUDA_OK(cudaGetLastError());
+  return B2A_OK;
+}
+
+}  // namespace spectral
+}  // namespace b2a
+
+extern "C" int64_t b2a_stft_num_frames(int64_t T, int n_fft, int hop, int pad, int right_pad, int drop_edge) {
+  if (T < 1 || n_fft < 2 || hop < 1 || pad < 0 || right_pad < 0 || drop_edge < 0) return -1;
+  // torch.stft(center=True): 1 + (len + 2*(n_fft/2) - n_fft) / hop  with len = T + 2 pad + right_pad
+  int64_t n = 1 + (T + 2 * (int64_t)pad + right_pad) / hop - 2 * (int64_t)drop_edge;
+  return n;
+}
+
+extern "C" int b2a_spectral_f32(const float* x, int64_t rows, int64_t T, int n_fft, int hop, const float* window,
+                                int pad, int right_pad, int pad_mode, int drop_edge, const float* gain,
+                                int rows_per_gain, float* y_out, const float* mel_fb, const int32_t* mel_lo,
+                                const int32_t* mel_hi, int n_mels, int post, float post_eps, float post_power,
+                                float* mel_out, float* stft_out, void* stream) {
+  using namespace b2a::spectral;
+  B2A_REQUIRE(x && window, B2A_E_INVALID, "spectral: null x/window");
+  B2A_REQUIRE(mel_out || stft_out, B2A_E_INVALID, "spectral: neither mel_out nor stft_out requested");
+  B2A_REQUIRE(rows >= 1 && T >= 1, B2A_E_INVALID, "spectral: empty input");
+  B2A_REQUIRE(T < (int64_t)1 << 30, B2A_E_UNSUPPORTED, "spectral: rows longer than 2^30 samples");
+  B2A_REQUIRE(n_fft >= 32 && n_fft <= 4096 && (n_fft & (n_fft - 1)) == 0, B2A_E_UNSUPPORTED,
+              "spectral: window_length must be a power of two in [32, 4096] (got %d)", n_fft);
+  B2A_REQUIRE(hop >= 1, B2A_E_INVALID, "spectral: hop_length must be >= 1");
+  B2A_REQUIRE(pad >= 0 && right_pad >= 0 && drop_edge >= 0, B2A_E_INVALID, "spectral: negative padding");
+  B2A_REQUIRE(pad_mode >= 0 && pad_mode <= 2, B2A_E_UNSUPPORTED, "spectral: pad mode %d", pad_mode);
+  const int64_t Lp = T + 2 * (int64_t)pad + right_pad;
+  // torch raises for these (reflect padding wider than the signal)
+  B2A_REQUIRE(n_fft / 2 < Lp, B2A_E_INVALID, "spectral: n_fft/2 (%d) must be < padded length (%lld)", n_fft / 2,
+              (long long)Lp);
+  B2A_REQUIRE(pad_mode != B2A_PAD_REFLECT || (pad + right_pad) < T || (pad + right_pad) == 0, B2A_E_INVALID,
+              "spectral: reflect padding (%d) must be < signal length (%lld)", pad + right_pad, (long long)T);
+  const int64_t nfr = b2a_stft_num_frames(T, n_fft, hop, pad, right_pad, drop_edge);
+  B2A_REQUIRE(nfr >= 1, B2A_E_INVALID, "spectral: no frames");
+  B2A_REQUIRE(!y_out || (pad == 0 && right_pad == 0 && drop_edge == 0), B2A_E_UNSUPPORTED,
+              "spectral: y_out needs pad == right_pad == drop_edge == 0");
+  B2A_REQUIRE(!gain || rows_per_gain >= 1, B2A_E_INVALID, "spectral: rows_per_gain");
+  B2A_REQUIRE(!mel_out || (mel_fb && mel_lo && mel_hi && n_mels >= 1), B2A_E_INVALID, "spectral: mel arguments");
+  B2A_REQUIRE(post >= 0 && post <= 2, B2A_E_INVALID, "spectral: post-op %d", post);
+  Params p;
+  memset(&p, 0, sizeof(p));
+  p.x = x; p.window = window; p.gain = gain; p.y_out = y_out;
+  p.mel_fb = mel_fb; p.mel_lo = mel_lo; p.mel_hi = mel_hi; p.mel_out = mel_out;
+  p.stft_out = reinterpret_cast<float2*>(stft_out);
+  p.rows = (int)rows; p.T = (int)T; p.n_fft = n_fft; p.hop = hop; p.pad = pad; p.right_pad = right_pad;
+  p.pad_mode = pad_mode; p.drop_edge = drop_edge; p.n_frames = (int)nfr; p.n_mels = n_mels;
+  p.rows_per_gain = gain ? rows_per_gain : 1; p.post = post; p.post_eps = post_eps; p.post_power = post_power;
+  switch (n_fft) {
+    case 32: return launch<4>(p, stream);
+    case 64: return launch<5>(p, stream);
+    case 128: return launch<6>(p, stream);
+    case 256: return launch<7>(p, stream);
+    case 512: return launch<8>(p, stream);
+    case 1024: return launch<9>(p, stream);
+    case 2048: return launch<10>(p, stream);
+    case 4096: return launch<11>(p, stream);
+  }
+  return b2a::fail(B2A_E_UNSUPPORTED, "spectral: n_fft %d", n_fft);
+}

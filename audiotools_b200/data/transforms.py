@@ -1,0 +1,396 @@
+"""Batched, seed-reproducible transforms with the API of ref:audiotools/data/transforms.py.
+
+A transform has two halves.  ``instantiate(state, signal)`` draws its parameters on the host from
+distribution tuples with a ``numpy.random.RandomState`` (so a seed reproduces them) and returns a
+nested dict keyed by the transform's name; ``transform(signal, **kwargs)`` applies it to a whole
+batch on the device, gated per item by the boolean ``mask`` drawn with probability ``prob``.
+``Compose`` names its children ``"{position}.{Name}"`` and threads the same nested dict through
+them; ``Choose`` turns the children's masks into a one-hot choice.
+
+Every concrete transform is one ``AudioSignal`` method, i.e. one or two launches of ``libb2a``.
+Transforms of the reference that need file-backed loaders (``BackgroundNoise``, ``CrossTalk``,
+file-based ``RoomImpulseResponse``) take in-memory ``AudioSignal`` pools here instead: decoding
+audio files is outside the accelerated hot path.
+"""
+import copy
+from contextlib import contextmanager
+from inspect import signature
+from typing import List
+
+import numpy as np
+import torch
+from numpy.random import RandomState
+
+from ..core import AudioSignal
+from ..core import util
+
+tt = torch.tensor
+"""Shorthand for converting things to torch.tensor."""
+
+
+class BaseTransform:
+    def __init__(self, keys: list = [], name: str = None, prob: float = 1.0):
+        # parameter names come from the _transform signature (everything but signal / kwargs)
+        tfm_keys = [k for k in signature(self._transform).parameters.keys() if k not in ("signal", "kwargs")]
+        self.keys = keys + tfm_keys + ["mask"]
+        self.prob = prob
+        self.name = self.__class__.__name__ if name is None else name
+
+    def _prepare(self, batch: dict):
+        sub_batch = batch[self.name]
+        for k in self.keys:
+            assert k in sub_batch.keys(), f"{k} not in batch"
+        return sub_batch
+
+    def _transform(self, signal):
+        return signal
+
+    def _instantiate(self, state: RandomState, signal: AudioSignal = None):
+        return {}
+
+    @staticmethod
+    def apply_mask(batch: dict, mask: torch.Tensor):
+        return util.unflatten({k: v[mask] for k, v in util.flatten(batch).items()})
+
+    def transform(self, signal: AudioSignal, **kwargs):
+        tfm_kwargs = self._prepare(kwargs)
+        mask = tfm_kwargs["mask"]
+        if torch.any(mask):
+            tfm_kwargs = self.apply_mask(tfm_kwargs, mask)
+            tfm_kwargs = {k: v for k, v in tfm_kwargs.items() if k != "mask"}
+            signal[mask] = self._transform(signal[mask], **tfm_kwargs)
+        return signal
+
+    def __call__(self, *args, **kwargs):
+        return self.transform(*args, **kwargs)
+
+    def instantiate(self, state: RandomState = None, signal: AudioSignal = None):
+        state = util.random_state(state)
+        needs_signal = "signal" in set(signature(self._instantiate).parameters.keys())
+        params = self._instantiate(state, **({"signal": signal} if needs_signal else {}))
+        for k in list(params.keys()):
+            v = params[k]
+            if not isinstance(v, (AudioSignal, torch.Tensor, dict)):
+                params[k] = tt(v)
+        params["mask"] = tt(state.rand() <= self.prob)
+        return {self.name: params}
+
+    def batch_instantiate(self, states: list = None, signal: AudioSignal = None):
+        return util.collate([self.instantiate(state, signal) for state in states])
+
+
+class Identity(BaseTransform):
+    pass
+
+
+class SpectralTransform(BaseTransform):
+    """stft -> transform -> istft."""
+
+    def transform(self, signal, **kwargs):
+        signal.stft()
+        super().transform(signal, **kwargs)
+        signal.istft()
+        return signal
+
+
+class Compose(BaseTransform):
+    def __init__(self, *transforms: list, name: str = None, prob: float = 1.0):
+        if isinstance(transforms[0], list):
+            transforms = transforms[0]
+        for i, tfm in enumerate(transforms):
+            tfm.name = f"{i}.{tfm.name}"
+        keys = [tfm.name for tfm in transforms]
+        super().__init__(keys=keys, name=name, prob=prob)
+        self.transforms = transforms
+        self.transforms_to_apply = keys
+
+    @contextmanager
+    def filter(self, *names: list):
+        old = self.transforms_to_apply
+        self.transforms_to_apply = names
+        yield
+        self.transforms_to_apply = old
+
+    def _transform(self, signal, **kwargs):
+        for transform in self.transforms:
+            if any([x in transform.name for x in self.transforms_to_apply]):
+                signal = transform(signal, **kwargs)
+        return signal
+
+    def _instantiate(self, state: RandomState, signal: AudioSignal = None):
+        parameters = {}
+        for transform in self.transforms:
+            parameters.update(transform.instantiate(state, signal=signal))
+        return parameters
+
+    def __getitem__(self, idx):
+        return self.transforms[idx]
+
+    def __len__(self):
+        return len(self.transforms)
+
+    def __iter__(self):
+        for transform in self.transforms:
+            yield transform
+
+
+class Choose(Compose):
+    def __init__(self, *transforms: list, weights: list = None, name: str = None, prob: float = 1.0):
+        super().__init__(*transforms, name=name, prob=prob)
+        if weights is None:
+            n = len(self.transforms)
+            weights = [1 / n for _ in range(n)]
+        self.weights = np.array(weights)
+
+    def _instantiate(self, state: RandomState, signal: AudioSignal = None):
+        kwargs = super()._instantiate(state, signal)
+        tfm_idx = state.choice(list(range(len(self.transforms))), p=self.weights)
+        one_hot = []
+        for i, t in enumerate(self.transforms):
+            mask = kwargs[t.name]["mask"]
+            if mask.item():
+                kwargs[t.name]["mask"] = tt(i == tfm_idx)
+            one_hot.append(kwargs[t.name]["mask"])
+        kwargs["one_hot"] = one_hot
+        return kwargs
+
+
+class Repeat(Compose):
+    def __init__(self, transform, n_repeat: int = 1, name: str = None, prob: float = 1.0):
+        super().__init__([copy.copy(transform) for _ in range(n_repeat)], name=name, prob=prob)
+        self.n_repeat = n_repeat
+
+
+class RepeatUpTo(Choose):
+    def __init__(self, transform, max_repeat: int = 5, weights: list = None, name: str = None, prob: float = 1.0):
+        transforms = [Repeat(transform, n_repeat=n) for n in range(1, max_repeat)]
+        super().__init__(transforms, name=name, prob=prob, weights=weights)
+        self.max_repeat = max_repeat
+
+
+# ------------------------------------------------------------------------------------------
+# concrete transforms (one AudioSignal method each)
+# ------------------------------------------------------------------------------------------
+class VolumeChange(BaseTransform):
+    """``signal.volume_change(db)`` (ref :941-970)."""
+
+    def __init__(self, db: tuple = ("uniform", -12.0, 0.0), name: str = None, prob: float = 1.0):
+        super().__init__(name=name, prob=prob)
+        self.db = db
+
+    def _instantiate(self, state: RandomState):
+        return {"db": util.sample_from_dist(self.db, state)}
+
+    def _transform(self, signal, db):
+        return signal.volume_change(db)
+
+
+class VolumeNorm(BaseTransform):
+    """``signal.normalize(db)`` -- LUFS normalisation (ref :973-1003)."""
+
+    def __init__(self, db: tuple = ("const", -24), name: str = None, prob: float = 1.0):
+        super().__init__(name=name, prob=prob)
+        self.db = db
+
+    def _instantiate(self, state: RandomState):
+        return {"db": util.sample_from_dist(self.db, state)}
+
+    def _transform(self, signal, db):
+        return signal.normalize(db)
+
+
+class GlobalVolumeNorm(BaseTransform):
+    """Normalise using the loudness of the whole source file, read from
+    ``signal.metadata["loudness"]`` (ref :1006-1050)."""
+
+    def __init__(self, db: tuple = ("const", -24), name: str = None, prob: float = 1.0):
+        super().__init__(name=name, prob=prob)
+        self.db = db
+
+    def _instantiate(self, state: RandomState, signal: AudioSignal):
+        if "loudness" not in signal.metadata:
+            db_change = 0.0
+        elif float(signal.metadata["loudness"]) == float("-inf"):
+            db_change = 0.0
+        else:
+            db_change = util.sample_from_dist(self.db, state) - float(signal.metadata["loudness"])
+        return {"db": db_change}
+
+    def _transform(self, signal, db):
+        return signal.volume_change(db)
+
+
+class Equalizer(BaseTransform):
+    """``signal.equalizer(eq)`` with ``eq = -eq_amount * rand(n_bands)`` (ref :564-600)."""
+
+    def __init__(self, eq_amount: tuple = ("const", 1.0), n_bands: int = 6, name: str = None, prob: float = 1.0):
+        super().__init__(name=name, prob=prob)
+        self.eq_amount = eq_amount
+        self.n_bands = n_bands
+
+    def _instantiate(self, state: RandomState):
+        eq_amount = util.sample_from_dist(self.eq_amount, state)
+        return {"eq": -eq_amount * state.rand(self.n_bands)}
+
+    def _transform(self, signal, eq):
+        return signal.equalizer(eq)
+
+
+class LowPass(BaseTransform):
+    """``signal.low_pass(cutoff, zeros)`` (ref :1095-1131)."""
+
+    def __init__(self, cutoff: tuple = ("choice", [4000, 8000, 16000]), zeros: int = 51, name: str = None,
+                 prob: float = 1):
+        super().__init__(name=name, prob=prob)
+        self.cutoff = cutoff
+        self.zeros = zeros
+
+    def _instantiate(self, state: RandomState):
+        return {"cutoff": util.sample_from_dist(self.cutoff, state)}
+
+    def _transform(self, signal, cutoff):
+        return signal.low_pass(cutoff, zeros=self.zeros)
+
+
+class HighPass(BaseTransform):
+    """``signal.high_pass(cutoff, zeros)`` (ref :1134-1170)."""
+
+    def __init__(self, cutoff: tuple = ("choice", [50, 100, 250, 500, 1000]), zeros: int = 51, name: str = None,
+                 prob: float = 1):
+        super().__init__(name=name, prob=prob)
+        self.cutoff = cutoff
+        self.zeros = zeros
+
+    def _instantiate(self, state: RandomState):
+        return {"cutoff": util.sample_from_dist(self.cutoff, state)}
+
+    def _transform(self, signal, cutoff):
+        return signal.high_pass(cutoff, zeros=self.zeros)
+
+
+class RoomImpulseResponse(BaseTransform):
+    """``signal.apply_ir(ir, drr, eq)`` (ref :857-938).  ``sources`` is an in-memory pool: a list of
+    single-item ``AudioSignal`` impulse responses (or a callable ``(state, signal) -> AudioSignal``);
+    one is drawn per item with ``state.choice`` and zero-padded to one second like the reference."""
+
+    def __init__(self, drr: tuple = ("uniform", 0.0, 30.0), sources: List[AudioSignal] = None,
+                 weights: List[float] = None, eq_amount: tuple = ("const", 1.0), n_bands: int = 6,
+                 name: str = None, prob: float = 1.0, use_original_phase: bool = False):
+        super().__init__(name=name, prob=prob)
+        self.drr = drr
+        self.eq_amount = eq_amount
+        self.n_bands = n_bands
+        self.use_original_phase = use_original_phase
+        self.sources = sources
+        self.weights = weights
+
+    def _draw(self, state, signal):
+        if callable(self.sources):
+            return self.sources(state, signal)
+        if not self.sources:
+            raise ValueError("RoomImpulseResponse needs `sources`: a list of AudioSignal impulse responses")
+        idx = state.choice(len(self.sources), p=self.weights)
+        return self.sources[idx].clone()
+
+    def _instantiate(self, state: RandomState, signal: AudioSignal = None):
+        eq_amount = util.sample_from_dist(self.eq_amount, state)
+        eq = -eq_amount * state.rand(self.n_bands)
+        drr = util.sample_from_dist(self.drr, state)
+        ir_signal = self._draw(state, signal)
+        ir_signal.zero_pad_to(signal.sample_rate)
+        return {"eq": eq, "ir_signal": ir_signal, "drr": drr}
+
+    def _transform(self, signal, ir_signal, drr, eq):
+        return signal.apply_ir(ir_signal.clone(), drr, eq, use_original_phase=self.use_original_phase)
+
+
+class PitchShift(BaseTransform):
+    """``signal.pitch_shift(n_semitones)``.  NEW: the reference has no PitchShift transform (only the
+    ``AudioSignal.pitch_shift`` method, ref:audiotools/core/effects.py:247-277, which takes ONE shift
+    for the whole batch); BASELINE.json config 4 needs it.  Items are grouped by their drawn shift."""
+
+    def __init__(self, n_semitones: tuple = ("choice", [-2, -1, 0, 1, 2]), quick: bool = True, name: str = None,
+                 prob: float = 1.0):
+        super().__init__(name=name, prob=prob)
+        self.n_semitones = n_semitones
+        self.quick = quick
+
+    def _instantiate(self, state: RandomState):
+        return {"n_semitones": util.sample_from_dist(self.n_semitones, state)}
+
+    def _transform(self, signal, n_semitones):
+        shifts = util.ensure_tensor(n_semitones, 1, signal.batch_size).reshape(-1)
+        for s in torch.unique(shifts).tolist():
+            if s == 0:
+                continue
+            sel = shifts == s
+            signal[sel] = signal[sel].pitch_shift(s, quick=self.quick)
+        return signal
+
+
+class ClippingDistortion(BaseTransform):
+    def __init__(self, perc: tuple = ("uniform", 0.0, 0.1), name: str = None, prob: float = 1.0):
+        super().__init__(name=name, prob=prob)
+        self.perc = perc
+
+    def _instantiate(self, state: RandomState):
+        return {"perc": util.sample_from_dist(self.perc, state)}
+
+    def _transform(self, signal, perc):
+        return signal.clip_distortion(perc)
+
+
+class Quantization(BaseTransform):
+    def __init__(self, channels: tuple = ("choice", [8, 32, 128, 256, 1024]), name: str = None, prob: float = 1.0):
+        super().__init__(name=name, prob=prob)
+        self.channels = channels
+
+    def _instantiate(self, state: RandomState):
+        return {"channels": util.sample_from_dist(self.channels, state)}
+
+    def _transform(self, signal, channels):
+        return signal.quantization(channels)
+
+
+class MuLawQuantization(BaseTransform):
+    def __init__(self, channels: tuple = ("choice", [8, 32, 128, 256, 1024]), name: str = None, prob: float = 1.0):
+        super().__init__(name=name, prob=prob)
+        self.channels = channels
+
+    def _instantiate(self, state: RandomState):
+        return {"channels": util.sample_from_dist(self.channels, state)}
+
+    def _transform(self, signal, channels):
+        return signal.mulaw_quantization(channels)
+
+
+class RescaleAudio(BaseTransform):
+    def __init__(self, val: float = 1.0, name: str = None, prob: float = 1):
+        super().__init__(name=name, prob=prob)
+        self.val = val
+
+    def _transform(self, signal):
+        return signal.ensure_max_of_audio(self.val)
+
+
+class InvertPhase(BaseTransform):
+    def __init__(self, name: str = None, prob: float = 1):
+        super().__init__(name=name, prob=prob)
+
+    def _transform(self, signal):
+        signal.audio_data = -signal.audio_data
+        return signal
+
+
+class Silence(BaseTransform):
+    """Replace the item by silence while KEEPING its cached loudness (ref :1053-1092)."""
+
+    def __init__(self, name: str = None, prob: float = 0.1):
+        super().__init__(name=name, prob=prob)
+
+    def _transform(self, signal):
+        _loudness = signal._loudness
+        signal = AudioSignal(torch.zeros_like(signal.audio_data), sample_rate=signal.sample_rate,
+                             stft_params=signal.stft_params)
+        signal._loudness = _loudness  # so that the target still can be normalised relative to it
+        return signal

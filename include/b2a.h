@@ -1,0 +1,112 @@
+/* b2a.h -- C ABI of libb2a.so, the B200-native (sm_100a) engine behind the
+ * AudioSignal transform/augment hot path of descriptinc/audiotools.
+ *
+ * The reference is 100% Python and has NO plugin/FFI interface: the
+ * "API for this path" is the AudioSignal method surface.  Each entry point below
+ * therefore names the reference *method* (file:line under /root/reference) whose
+ * device-side work it replaces; audiotools_b200/ (Python, ctypes) keeps the
+ * method-level names and semantics on top of it.  INTEGRATION.md shows the binding.
+ *
+ * Conventions
+ *  - plain C types only; every pointer is a DEVICE pointer unless suffixed _h (host);
+ *  - the caller owns every buffer (inputs, outputs, workspaces);
+ *  - every call is asynchronous on `stream` (a cudaStream_t passed as void*);
+ *  - returns 0 on success, <0 on error (B2A_E_*); b2a_last_error() gives the
+ *    thread-local message.  Nothing throws, nothing falls back to the CPU.
+ *  - waveforms are float32, contiguous [rows, T] with rows = B*C (row = b*C + c).
+ */
+#ifndef B2A_H_
+#define B2A_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B2A_VERSION 100 /* 0.1.0 */
+
+#define B2A_OK 0
+#define B2A_E_INVALID -1     /* bad argument (the message says which)               */
+#define B2A_E_UNSUPPORTED -2 /* valid in the reference, not implemented on device   */
+#define B2A_E_CUDA -3        /* a CUDA runtime call / launch failed                 */
+
+/* pad modes of torch.nn.functional.pad used by AudioSignal.stft (padding_type) */
+#define B2A_PAD_REFLECT 0
+#define B2A_PAD_CONSTANT 1
+#define B2A_PAD_REPLICATE 2
+
+/* post-ops fused behind the mel projection */
+#define B2A_POST_NONE 0   /* mel                                      audio_signal.py:1367-1368 */
+#define B2A_POST_LOG10 1  /* log10(clamp(mel, eps)^power)             metrics/spectral.py:187-190 */
+#define B2A_POST_LN 2     /* ln(mel + eps)                            audio_signal.py:1421 (mfcc) */
+
+int b2a_version(void);
+const char* b2a_last_error(void);
+
+/* ---- STFT / mel ---------------------------------------------------------------------
+ * Replaces the device work of AudioSignal.stft (audiotools/core/audio_signal.py:1123-1212:
+ * F.pad(pad, pad+right_pad, padding_type) -> torch.stft(center=True, reflect) -> optional
+ * drop of 2+2 edge frames) and AudioSignal.mel_spectrogram (:1333-1369: |X| @ mel_basis.T),
+ * fused: framing -> window -> real FFT -> |.| -> banded mel -> post-op, one pass over x.
+ *
+ *   x        [rows, T]
+ *   window   [n_fft]              (AudioSignal.get_window, :1009-1039)
+ *   n_fft    power of two in [64, 4096]; hop >= 1
+ *   pad/right_pad/pad_mode        compute_stft_padding (:1089-1121); 0/0 when !match_stride
+ *   drop_edge                     frames dropped at each end (2 when match_stride, else 0)
+ *   gain     nullable [rows/rows_per_gain]: x is multiplied by gain[row / rows_per_gain] first
+ *            (EffectMixin.normalize's x*gain, effects.py:219) and, if y_out != NULL, the scaled
+ *            waveform is written there ([rows, T]) by the same pass.
+ *   mel_fb   nullable [n_mels, F] row-major dense filterbank (get_mel_filters, :1298-1331);
+ *   mel_lo/mel_hi  [n_mels] int32: mel_fb[m, k] == 0 outside mel_lo[m] <= k < mel_hi[m]
+ *            (the caller derives them from the actual non-zeros, so the banded sum equals the
+ *            dense matmul exactly for ANY matrix).
+ *   mel_out  nullable [rows, n_mels, n_frames]    stft_out  nullable [rows, F, n_frames] (re,im)
+ *   n_frames = 1 + (T + 2*pad + right_pad)/hop - 2*drop_edge,  F = n_fft/2 + 1
+ */
+int64_t b2a_stft_num_frames(int64_t T, int n_fft, int hop, int pad, int right_pad, int drop_edge);
+int b2a_spectral_f32(const float* x, int64_t rows, int64_t T, int n_fft, int hop, const float* window,
+                     int pad, int right_pad, int pad_mode, int drop_edge,
+                     const float* gain, int rows_per_gain, float* y_out,
+                     const float* mel_fb, const int32_t* mel_lo, const int32_t* mel_hi, int n_mels,
+                     int post, float post_eps, float post_power,
+                     float* mel_out, float* stft_out, void* stream);
+
+/* ---- integrated loudness (ITU-R BS.1770 / LUFS) ----------------------------------------
+ * Replaces Meter.integrated_loudness with the IIR semantics of apply_filter_cpu
+ * (audiotools/core/loudness.py:102-126, 164-247) and the pad / clamp shell of
+ * LoudnessMixin.loudness (:268-320); optionally also produces normalize()'s gain
+ * (audiotools/core/effects.py:214-217).
+ *
+ *   x [B, C, T];  T_padded >= T is the zero-extended length (loudness.py:302-305)
+ *   sos_h   [n_stage][6] float64 host: b0 b1 b2 a0 a1 a2 per biquad stage, in application order
+ *           (pyloudnorm K-weighting: high-shelf then high-pass); coefficients are rounded to
+ *           float32 exactly as the reference does (:118-119); stage_gain_h [n_stage] passband gains
+ *   chan_gain_h [C] float64 host (G = [1,1,1,1.41,1.41], :49-50)
+ *   block_s  gating block in seconds (0.4): K = int(block_s*rate), stride = int(block_s*rate*0.25)
+ *   z_blocks nullable [B, C, nblk] float32 block energies before gating (:214)
+ *   lufs_out [B] float32: integrated loudness, NOT clamped (may be -inf for silence)
+ *   loud_out nullable [B]: max(lufs, -70)            (:315-320)
+ *   target_db nullable [n_target] (n_target 1 or B), gain_out nullable [B]:
+ *            gain = exp((target_db - loud) * ln(10)/20)
+ *   ws: b2a_lufs_workspace_bytes(...) bytes of scratch, contents irrelevant on entry.
+ */
+int64_t b2a_lufs_num_blocks(int64_t T_padded, double rate, double block_s);
+size_t b2a_lufs_workspace_bytes(int64_t B, int C, int64_t T_padded, double rate, double block_s);
+int b2a_lufs_f32(const float* x, int64_t B, int C, int64_t T, int64_t T_padded, double rate,
+                 const double* sos_h, const double* stage_gain_h, int n_stage, double block_s,
+                 const double* chan_gain_h, float* z_blocks, float* lufs_out, float* loud_out,
+                 const float* target_db, int n_target, float* gain_out,
+                 void* ws, size_t ws_bytes, void* stream);
+
+/* ---- per-item gain ---------------------------------------------------------------------
+ * x[b, :, :] * gain[b]  (EffectMixin.normalize / volume_change, effects.py:219,237).
+ * out may alias x.  per_item = C*T. */
+int b2a_gain_f32(const float* x, float* out, int64_t B, int64_t per_item, const float* gain, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B2A_H_ */

@@ -1,0 +1,246 @@
+"""GPU parity tests proper (run with ``-m gpu`` on a B200): the product path -- AudioSignal API ->
+ctypes -> C ABI of libb2a.so -> sm_100a kernels -- against (a) the golden vectors produced by the
+REAL reference, (b) the oracle on the same seeded inputs, and (c) at BASELINE.json's full sizes,
+size-independent properties (linearity, batch == per-item, normalise-then-measure, round trips).
+
+Tolerance: BASELINE.json asks for 1e-4 relative FP32 and bit-exact frame/block indexing.
+"relative" = max|a-b| / max|b| (``rel_err``); LUFS values are compared in dB with atol 2e-3
+(1e-4 of a ~-20 LUFS value).  Shapes (frame counts, block counts) are compared exactly.
+"""
+import numpy as np
+import pytest
+import torch
+
+from tests.conftest import rel_err
+from tests.golden import cases
+
+pytestmark = pytest.mark.gpu
+
+DEV = "cuda:0"
+TOL = 1e-4
+LUFS_ATOL = 2e-3
+
+
+@pytest.fixture(scope="module")
+def at():
+    import __graft_entry__ as graft
+
+    graft.build()
+    import audiotools_b200
+
+    return audiotools_b200
+
+
+@pytest.fixture(scope="module")
+def sp():
+    from oracle import signal_path
+
+    return signal_path
+
+
+def G(golden, key):
+    return torch.from_numpy(golden[key])
+
+
+def sig_of(at, name, sl=slice(None), **kw):
+    return at.AudioSignal(cases.make_input(name)[sl].clone(), cases.sample_rate(name), **kw).to(DEV)
+
+
+# ------------------------------------------------------------------------------------------
+# BASELINE configs[0]: batch=4 mono 1s@16kHz stft(n_fft=512, hop=128) -- reference parity
+# ------------------------------------------------------------------------------------------
+def test_cfg1_stft_matches_reference(at, golden):
+    sig = sig_of(at, "cfg1")
+    s = sig.stft(window_length=512, hop_length=128)
+    ref = G(golden, "cfg1_stft")
+    assert s.shape == ref.shape == (4, 1, 257, 126)  # frame indexing bit-exact
+    assert s.dtype == torch.complex64 and sig.stft_data is s
+    assert rel_err(torch.view_as_real(s.cpu()), torch.view_as_real(ref)) < TOL
+    assert rel_err(torch.view_as_real(sig_of(at, "cfg1").stft().cpu()), torch.view_as_real(ref)) < TOL  # defaults
+
+
+def test_stft_variants_match_reference(at, golden):
+    p = at.STFTParams(256, 64, "sqrt_hann", True, "reflect")
+    s = sig_of(at, "cfg1", slice(0, 2), stft_params=p).stft()
+    ref = G(golden, "cfg1_stft_match_stride")
+    assert s.shape == ref.shape and s.shape[-1] == 16000 // 64
+    assert rel_err(torch.view_as_real(s.cpu()), torch.view_as_real(ref)) < TOL
+    x = cases.make_input("cfg1")[:2, :, :15999]
+    s = at.AudioSignal(x, 16000, stft_params=at.STFTParams(256, 64, "hann", True, "reflect")).to(DEV).stft()
+    ref = G(golden, "cfg1_stft_match_stride_odd")
+    assert s.shape == ref.shape and rel_err(torch.view_as_real(s.cpu()), torch.view_as_real(ref)) < TOL
+    s = sig_of(at, "cfg1", slice(0, 2)).stft(window_length=256, hop_length=100, window_type="average")
+    ref = G(golden, "cfg1_stft_average_hop100")
+    assert s.shape == ref.shape and rel_err(torch.view_as_real(s.cpu()), torch.view_as_real(ref)) < TOL
+
+
+@pytest.mark.parametrize("n_fft,hop", [(32, 8), (64, 16), (128, 32), (256, 77), (1024, 256), (4096, 1024)])
+def test_stft_all_sizes_vs_oracle(at, sp, n_fft, hop):
+    x = cases.make_input("cfg1")[:2]
+    s = at.AudioSignal(x.clone(), 16000).to(DEV).stft(window_length=n_fft, hop_length=hop)
+    ref = sp.stft(x, 16000, n_fft, hop)
+    assert s.shape == ref.shape
+    assert rel_err(torch.view_as_real(s.cpu()), torch.view_as_real(ref)) < TOL
+
+
+def test_mel_mfcc_logmag_match_reference(at, golden):
+    assert rel_err(sig_of(at, "cfg1").mel_spectrogram(n_mels=80).cpu(), G(golden, "cfg1_mel80")) < TOL
+    m = sig_of(at, "cfg1", slice(0, 2)).mel_spectrogram(n_mels=40, mel_fmin=100.0, mel_fmax=6000.0,
+                                                        window_length=1024, hop_length=256)
+    assert rel_err(m.cpu(), G(golden, "cfg1_mel40_fmin_fmax")) < TOL
+    assert rel_err(sig_of(at, "cfg1").mfcc().cpu(), G(golden, "cfg1_mfcc")) < TOL
+    sig = sig_of(at, "cfg1", slice(0, 2))
+    sig.stft()
+    assert rel_err(sig.log_magnitude().cpu(), G(golden, "cfg1_logmag")) < TOL
+
+
+def test_stft_istft_round_trip(at):
+    """ref:tests/core/test_audio_signal.py:400-456."""
+    sig = sig_of(at, "cfg1")
+    x = sig.audio_data.clone()
+    sig.stft()
+    sig.istft()
+    assert torch.allclose(sig.audio_data, x, atol=1e-5)
+    sig = sig_of(at, "cfg1", stft_params=at.STFTParams(256, 64, "sqrt_hann", True, "reflect"))
+    assert sig.stft().shape[-1] == sig.signal_length // 64
+    sig.istft()
+    assert torch.allclose(sig.audio_data, x, atol=1e-5)
+
+
+# ------------------------------------------------------------------------------------------
+# loudness
+# ------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name,key", [("cfg2", "cfg2_lufs"), ("lufs16k", "lufs16k"), ("short", "lufs_short"),
+                                      ("lufs48k", "lufs48k"), ("lufs11k", "lufs11k")])
+def test_loudness_matches_reference(at, golden, name, key):
+    sig = sig_of(at, name)
+    l = sig.loudness()
+    assert l.dtype == torch.float32 and l.shape == (sig.batch_size,)
+    assert torch.allclose(l.cpu(), G(golden, key), atol=LUFS_ATOL)
+    assert sig._loudness is l or torch.equal(sig._loudness, l)  # cached
+    if name == "cfg2":
+        assert l[1].item() == -70.0  # silent item: NaN scrub -> -inf -> clamp
+
+
+def test_block_energies_bit_exact_indexing(at, golden):
+    from audiotools_b200.engine import get_engine
+
+    x = cases.make_input("cfg2").to(DEV)
+    out = get_engine().lufs(x, 44100, want_blocks=True)
+    ref = G(golden, "cfg2_z")
+    assert out["blocks"].shape == ref.shape
+    assert rel_err(out["blocks"].cpu(), ref) < TOL
+    m = at.Meter(44100)
+    assert torch.allclose(m.integrated_loudness(x.permute(0, 2, 1)).cpu()[[0, 2]], G(golden, "cfg2_lufs")[[0, 2]],
+                          atol=LUFS_ATOL)
+
+
+def test_loudness_batch_equals_per_item(at):
+    """ref:tests/core/test_loudness.py:31-52."""
+    sig = sig_of(at, "lufs16k")
+    batch = sig.loudness().cpu()
+    for i in range(0, 16, 5):
+        one = sig_of(at, "lufs16k", slice(i, i + 1)).loudness().cpu()
+        assert torch.allclose(one, batch[i: i + 1], atol=1e-5)
+
+
+def test_normalize_and_volume_change_match_reference(at, golden):
+    sig = sig_of(at, "cfg2")
+    sig.normalize(-24.0)
+    assert sig._pending_gain is not None and sig._loudness is None  # deferred; cache dropped like the reference
+    y = sig.audio_data
+    assert sig._pending_gain is None
+    assert rel_err(y.cpu(), G(golden, "cfg2_norm")) < TOL
+    db = G(golden, "norm16k_db")
+    sig = sig_of(at, "lufs16k", slice(0, 4)).normalize(db)
+    assert rel_err(sig.audio_data.cpu(), G(golden, "norm16k")) < TOL
+    sig = sig_of(at, "lufs16k", slice(0, 4)).volume_change(db)
+    assert rel_err(sig.audio_data.cpu(), G(golden, "volchange16k")) < TOL
+
+
+def test_normalize_then_measure(at):
+    """ref:tests/core/test_effects.py:15-33."""
+    x = torch.randn(16, 2, 32000, generator=torch.Generator().manual_seed(0))
+    for db in (-70.0, -50.0, -30.0, -10.0):
+        sig = at.AudioSignal(x.clone(), 16000).to(DEV).normalize(db)
+        assert torch.allclose(sig.loudness().cpu(), torch.full((16,), db), atol=0.1)
+
+
+# ------------------------------------------------------------------------------------------
+# BASELINE configs[1]: LUFS normalise + log-mel, fused
+# ------------------------------------------------------------------------------------------
+def test_cfg2_fused_pipeline_matches_reference(at, golden):
+    sig = sig_of(at, "cfg2")
+    sig.normalize(-24.0)
+    logmel = sig.mel_spectrogram(n_mels=128, window_length=2048, hop_length=512, window_type="hann", log=True)
+    assert sig._pending_gain is None and sig.stft_data is None  # gain rode along; no STFT materialised
+    assert logmel.shape == golden["cfg2_logmel"].shape
+    assert rel_err(logmel.cpu(), G(golden, "cfg2_logmel")) < TOL
+    assert rel_err(sig.audio_data.cpu(), G(golden, "cfg2_norm")) < TOL
+    mel = sig.mel_spectrogram(n_mels=128, window_length=2048, hop_length=512, window_type="hann")
+    assert rel_err(mel.cpu(), G(golden, "cfg2_mel")) < TOL
+    # unfused order gives the same thing
+    sig2 = sig_of(at, "cfg2").normalize(-24.0)
+    _ = sig2.audio_data
+    lm2 = sig2.mel_spectrogram(n_mels=128, window_length=2048, hop_length=512, log=True)
+    assert torch.allclose(lm2, logmel, atol=1e-5)
+
+
+def _full_batch(B=64, seed=0):
+    g = torch.Generator().manual_seed(seed)
+    x = (0.1 * torch.randn(B, 2, 441000, generator=g)).clamp(-1, 1)
+    return (x * (0.05 + 0.95 * torch.rand(B, 1, 1, generator=g))).float()
+
+
+def test_cfg2_full_size_properties_and_oracle_subset(at, sp):
+    """64 x 2ch x 10 s @ 44.1 kHz: shapes, oracle on a subset of items, linearity, batch == per-item."""
+    x = _full_batch()
+    sig = at.AudioSignal(x.clone(), 44100).to(DEV)
+    lufs = sig.loudness().clone()
+    sig.normalize(-24.0)
+    logmel = sig.mel_spectrogram(n_mels=128, window_length=2048, hop_length=512, window_type="hann", log=True)
+    y = sig.audio_data
+    assert logmel.shape == (64, 2, 128, 862) and y.shape == (64, 2, 441000)  # 1 + T//hop frames
+    sub = [0, 31, 63]
+    y_ref, l_ref = sp.normalize(x[sub], 44100, -24.0)
+    lm_ref = sp.log_mel(sp.mel_spectrogram(y_ref, 44100, 128, window_length=2048, hop_length=512, window_type="hann"))
+    assert torch.allclose(lufs[sub].cpu(), l_ref, atol=LUFS_ATOL)
+    assert rel_err(y[sub].cpu(), y_ref) < TOL
+    assert rel_err(logmel[sub].cpu(), lm_ref) < TOL
+    # after normalisation every item measures -24 LUFS
+    assert torch.allclose(sig.loudness().cpu(), torch.full((64,), -24.0), atol=1e-2)
+    # loudness(a*x) = loudness(x) + 20 log10 a ; mel(a*x) = a*mel(x)
+    a = 0.37
+    l2 = at.AudioSignal((a * x).clone(), 44100).to(DEV).loudness()
+    assert torch.allclose(l2, lufs + 20 * np.log10(a), atol=2e-3)
+    m1 = at.AudioSignal(x[:8].clone(), 44100).to(DEV).mel_spectrogram(128, window_length=2048, hop_length=512)
+    m2 = at.AudioSignal((a * x[:8]).clone(), 44100).to(DEV).mel_spectrogram(128, window_length=2048, hop_length=512)
+    assert rel_err(m2, a * m1) < 1e-5
+    # batch == per-item
+    one = at.AudioSignal(x[5:6].clone(), 44100).to(DEV)
+    assert torch.allclose(one.loudness(), lufs[5:6], atol=1e-4)
+    one.normalize(-24.0)
+    assert torch.allclose(one.mel_spectrogram(128, window_length=2048, hop_length=512, log=True), logmel[5:6], atol=1e-4)
+
+
+def test_full_size_stft_parseval(at):
+    """cfg2-size STFT: with a rectangular window and hop = n_fft, sum|X|^2 recovers the signal energy."""
+    x = _full_batch(4, 3)[:, :1, : 2048 * 200]
+    sig = at.AudioSignal(x.clone(), 44100).to(DEV)
+    s = sig.stft(window_length=2048, hop_length=2048, window_type="boxcar")
+    # interior frames (centre padding shifts frames by n_fft/2): energy per frame via Parseval
+    frames = torch.nn.functional.pad(x.to(DEV), (1024, 1024), mode="reflect").unfold(-1, 2048, 2048)
+    e_time = (frames ** 2).sum(-1)
+    mag2 = s.abs() ** 2
+    e_freq = (mag2[..., 0, :] + mag2[..., -1, :] + 2 * mag2[..., 1:-1, :].sum(-2)) / 2048
+    assert rel_err(e_freq, e_time) < 1e-4
+
+
+def test_cpu_tensor_raises_and_errors_map(at):
+    sig = at.AudioSignal(torch.zeros(1, 1, 16000), 16000)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        sig.loudness()
+    with pytest.raises(Exception, match="power of two"):
+        at.AudioSignal(torch.zeros(1, 1, 16000), 16000).to(DEV).stft(window_length=400, hop_length=100)
+    with pytest.raises(RuntimeError, match="without self.stft_data"):
+        at.AudioSignal(torch.zeros(1, 1, 16000), 16000).to(DEV).istft()

@@ -1,0 +1,119 @@
+"""The product's kernel SOURCES, compiled for the CPU by tests/cusim (CUDA threads -> host
+threads), against the oracle.  This checks indexing and arithmetic of the exact code that ships
+before it ever reaches a GPU; the GPU parity tests proper are tests/test_gpu_parity.py.
+Sizes are small: every CUDA thread is a host thread here."""
+import numpy as np
+import pytest
+import torch
+
+from audiotools_b200 import _lib
+from audiotools_b200.core import mel as melmod
+from oracle import signal_path as sp
+from tests.conftest import rel_err
+from tests.cusim.sim_engine import sim_engine
+from tests.golden import cases
+
+
+@pytest.fixture(scope="module")
+def eng():
+    return sim_engine()
+
+
+def padded_len(T, sr):
+    return T + int((0.5 - T / sr) * sr) if T / sr < 0.5 else T
+
+
+@pytest.mark.parametrize("name", ["short", "lufs48k", "lufs11k", "cfg2"])
+def test_lufs_blocks_and_gating(eng, golden, name):
+    x, sr = cases.make_input(name), cases.sample_rate(name)
+    T = x.shape[-1]
+    out = eng.lufs(x, sr, padded_length=padded_len(T, sr), target_db=torch.tensor([-24.0]), want_blocks=True)
+    z_ref = sp.Meter(sr).block_energies(torch.nn.functional.pad(x, (0, padded_len(T, sr) - T)).permute(0, 2, 1))
+    assert out["blocks"].shape == z_ref.shape  # block indexing is bit-exact
+    assert rel_err(out["blocks"], z_ref) < 1e-4
+    ref = torch.from_numpy(golden["cfg2_lufs" if name == "cfg2" else {"short": "lufs_short"}.get(name, name)])
+    assert torch.allclose(out["loud"], ref, atol=1e-3)  # dB; 1e-4 relative of a ~-20 LUFS value is 2e-3
+    if name == "cfg2":
+        assert out["lufs"][1].item() == float("-inf") and out["loud"][1].item() == -70.0
+        assert rel_err(z_ref * 0 + torch.from_numpy(golden["cfg2_z"]), z_ref) < 1e-6
+    gain_ref = torch.exp((torch.tensor(-24.0) - ref) * sp.GAIN_FACTOR)
+    assert torch.allclose(out["gain"], gain_ref, rtol=1e-4)
+
+
+def test_lufs_single_stage_and_errors(eng):
+    x = cases.make_input("short")
+    with pytest.raises(NotImplementedError):
+        eng.lufs(x, 16000, filter_class="Fenton/Lee 1")
+    with pytest.raises(_lib.B2AError, match="unsupported geometry"):
+        eng.lufs(x, 500)  # gating stride would be < 64 samples
+
+
+@pytest.mark.parametrize("n_fft,hop,wtype,match_stride,T", [
+    (512, 128, "hann", False, 16000),        # BASELINE cfg1
+    (256, 64, "sqrt_hann", True, 16000),     # match_stride, T % hop == 0
+    (256, 64, "hann", True, 15999),          # match_stride with right_pad
+    (2048, 512, "hann", False, 16000),       # cfg2 transform size
+    (64, 16, "hann", False, 3000),
+    (1024, 256, "hann", False, 9000),
+    (256, 77, "average", False, 5000),       # odd hop, non-hann window
+    (4096, 1024, "hann", False, 16000),
+])
+def test_stft_vs_torch_stft(eng, n_fft, hop, wtype, match_stride, T):
+    x = cases.make_input("cfg1")[:2, :, :T]
+    right_pad, pad = sp.compute_stft_padding(T, n_fft, hop, match_stride)
+    out = eng.spectral(x, n_fft, hop, sp.get_window(wtype, n_fft), pad=pad, right_pad=right_pad,
+                       drop_edge=2 if match_stride else 0)["stft"]
+    ref = sp.stft(x, 16000, n_fft, hop, wtype, match_stride, "reflect")
+    assert out.shape == ref.shape  # frame indexing is bit-exact
+    assert rel_err(torch.view_as_real(out), torch.view_as_real(ref)) < 1e-5
+
+
+def test_cfg1_against_reference_golden(eng, golden):
+    x = cases.make_input("cfg1")
+    out = eng.spectral(x, 512, 128, sp.get_window("hann", 512))["stft"]
+    ref = torch.from_numpy(golden["cfg1_stft"])
+    assert out.shape == ref.shape == (4, 1, 257, 126)
+    assert rel_err(torch.view_as_real(out), torch.view_as_real(ref)) < 1e-5
+
+
+@pytest.mark.parametrize("mode", ["constant", "replicate"])
+def test_stft_other_padding_types(eng, mode):
+    x = cases.make_input("cfg1")[:1, :, :4000]
+    right_pad, pad = sp.compute_stft_padding(4000, 256, 64, True)
+    out = eng.spectral(x, 256, 64, sp.get_window("hann", 256), pad=pad, right_pad=right_pad, pad_mode=mode,
+                       drop_edge=2)["stft"]
+    ref = sp.stft(x, 16000, 256, 64, "hann", True, mode)
+    assert out.shape == ref.shape and rel_err(torch.view_as_real(out), torch.view_as_real(ref)) < 1e-5
+
+
+def _mel_tables(sr, n_fft, n_mels, fmin=0.0, fmax=None):
+    fb = melmod.mel_filters(sr, n_fft, n_mels, fmin, fmax)
+    lo, hi = melmod.band_table(fb)
+    return torch.from_numpy(np.ascontiguousarray(fb)), torch.from_numpy(lo), torch.from_numpy(hi)
+
+
+def test_fused_normalize_logmel_cfg2_golden(eng, golden):
+    """normalize(-24) -> log-mel(2048/512/128) in two launches, against the real reference."""
+    x, sr = cases.make_input("cfg2"), 44100
+    lu = eng.lufs(x, sr, target_db=torch.tensor([-24.0]))
+    fb, lo, hi = _mel_tables(sr, 2048, 128)
+    out = eng.spectral(x, 2048, 512, sp.get_window("hann", 2048), gain=lu["gain"], want_scaled=True, mel_fb=fb,
+                       mel_lo=lo, mel_hi=hi, post=_lib.POST_LOG10, post_eps=1e-5, post_power=2.0, want_stft=False)
+    assert rel_err(out["scaled"], torch.from_numpy(golden["cfg2_norm"])) < 1e-4
+    assert out["mel"].shape == golden["cfg2_logmel"].shape
+    assert rel_err(out["mel"], torch.from_numpy(golden["cfg2_logmel"])) < 1e-4
+    plain = eng.spectral(x, 2048, 512, sp.get_window("hann", 2048), mel_fb=fb, mel_lo=lo, mel_hi=hi, want_stft=False)
+    ref = sp.mel_spectrogram(x, sr, 128, window_length=2048, hop_length=512, window_type="hann")
+    assert rel_err(plain["mel"], ref) < 1e-5
+    assert eng.gain(x, lu["gain"]).equal(out["scaled"])
+
+
+def test_mel_variants_golden(eng, golden):
+    x = cases.make_input("cfg1")
+    fb, lo, hi = _mel_tables(16000, 512, 80)
+    mel = eng.spectral(x, 512, 128, sp.get_window("hann", 512), mel_fb=fb, mel_lo=lo, mel_hi=hi, want_stft=False)["mel"]
+    assert rel_err(mel, torch.from_numpy(golden["cfg1_mel80"])) < 1e-5
+    fb, lo, hi = _mel_tables(16000, 1024, 40, 100.0, 6000.0)
+    mel = eng.spectral(x[:2], 1024, 256, sp.get_window("hann", 1024), mel_fb=fb, mel_lo=lo, mel_hi=hi,
+                       want_stft=False)["mel"]
+    assert rel_err(mel, torch.from_numpy(golden["cfg1_mel40_fmin_fmax"])) < 1e-5

@@ -104,7 +104,10 @@ def test_stft_istft_round_trip(at):
     sig = sig_of(at, "cfg1", stft_params=at.STFTParams(256, 64, "sqrt_hann", True, "reflect"))
     assert sig.stft().shape[-1] == sig.signal_length // 64
     sig.istft()
-    assert torch.allclose(sig.audio_data, x, atol=1e-5)
+    # with match_stride the 2+2 dropped edge frames are not recoverable: the reference's own test
+    # compares the interior only (discard = 2 * window_length)
+    assert sig.signal_length == x.shape[-1]
+    assert torch.allclose(sig.audio_data[..., 512:-512], x[..., 512:-512], atol=1e-5)
 
 
 # ------------------------------------------------------------------------------------------

@@ -1,0 +1,189 @@
+"""Host-side logic of the drop-in layer on CPU tensors (no kernels involved): the container
+semantics of AudioSignal and the Compose / Choose / Repeat / mask algebra of the transforms,
+modelled on ref:tests/data/test_transforms.py:114-330 and ref:tests/core/test_audio_signal.py
+(synthetic signals instead of the LFS audio)."""
+import numpy as np
+import pytest
+import torch
+
+from audiotools_b200 import AudioSignal, STFTParams, util
+from audiotools_b200.data import transforms as tfm
+
+
+def noise(B=1, C=1, T=2000, seed=0, sr=44100):
+    return AudioSignal(torch.randn(B, C, T, generator=torch.Generator().manual_seed(seed)), sr)
+
+
+class MulTransform(tfm.BaseTransform):
+    def __init__(self, num, name=None):
+        self.num = num
+        super().__init__(name=name, keys=["num"])
+
+    def _transform(self, signal, num):
+        signal.audio_data = signal.audio_data * num[:, None, None]
+        return signal
+
+    def _instantiate(self, state):
+        return {"num": self.num}
+
+
+MULS = [0.5, 0.25, 0.125]
+
+
+@pytest.mark.parametrize("build", [
+    lambda: tfm.Compose([MulTransform(x) for x in MULS]),
+    lambda: tfm.Compose([MulTransform(MULS[0]),
+                         tfm.Compose([MulTransform(MULS[1]), tfm.Compose([MulTransform(MULS[2])])])]),
+    lambda: tfm.Compose([tfm.Compose([MulTransform(MULS[0])]),
+                         tfm.Compose([MulTransform(MULS[1]), MulTransform(MULS[2])])]),
+])
+def test_compose_products(build):
+    transform = build()
+    signal = noise()
+    out = transform(signal.clone(), **transform.instantiate(0))
+    assert torch.allclose(out.audio_data, signal.audio_data * np.prod(MULS))
+
+
+def test_compose_naming_indexing_and_filter():
+    transform = tfm.Compose([MulTransform(x, name=str(x)) for x in MULS])
+    assert [t.name for t in transform] == ["0.0.5", "1.0.25", "2.0.125"]
+    assert len(transform) == 3 and isinstance(transform[1], MulTransform)
+    kwargs = transform.instantiate(0)
+    assert set(kwargs["Compose"]) == {"0.0.5", "1.0.25", "2.0.125", "mask"}
+    signal = noise()
+    rng = np.random.RandomState(0)
+    for size in range(len(MULS)):
+        for _ in range(5):
+            chosen = rng.choice(MULS, size=size, replace=False).tolist()
+            with transform.filter(*[str(x) for x in chosen]):
+                out = transform(signal.clone(), **kwargs)
+            assert torch.allclose(out.audio_data, signal.audio_data * np.prod(chosen))
+    assert transform.transforms_to_apply == ["0.0.5", "1.0.25", "2.0.125"]  # restored
+
+
+def test_choose_one_hot_and_batch():
+    signal = noise()
+    transform = tfm.Choose([MulTransform(0.0), MulTransform(2.0)])
+    targets = [signal.clone() * 0.0, signal.clone() * 2.0]
+    for seed in range(10):
+        kwargs = transform.instantiate(seed, signal)
+        assert sum(int(m.item()) for m in kwargs["Choose"]["one_hot"]) == 1
+        out = transform(signal.clone(), **kwargs)
+        assert any(out == t for t in targets)
+    batch = AudioSignal.batch([signal.clone() for _ in range(4)])
+    kwargs = transform.batch_instantiate([0, 1, 2, 3], batch)
+    out = transform(batch, **kwargs)
+    for nb in range(4):
+        assert any(out[nb] == t for t in targets)
+    weighted = tfm.Choose([MulTransform(0.0), MulTransform(2.0)], weights=[0.0, 1.0])
+    out = weighted(AudioSignal.batch([signal.clone() for _ in range(4)]), **weighted.batch_instantiate([0, 1, 2, 3], batch))
+    for nb in range(4):
+        assert out[nb] == targets[1]
+    nested = tfm.Choose([tfm.Compose([MulTransform(0.0)]), tfm.Compose([MulTransform(2.0)])])
+    for seed in range(6):
+        assert any(nested(signal.clone(), **nested.instantiate(seed, signal)) == t for t in targets)
+
+
+def test_repeat_and_repeat_up_to():
+    signal = AudioSignal(torch.randn(1, 1, 100).clamp(1e-5), 44100)
+    transform = tfm.Repeat(MulTransform(0.5), n_repeat=3)
+    out = transform(signal.clone(), **transform.instantiate(0, signal))
+    assert (out.audio_data / signal.audio_data).mean() == 0.5 ** 3
+    up = tfm.RepeatUpTo(MulTransform(0.5), max_repeat=4)
+    out = up(signal.clone(), **up.instantiate(3, signal))
+    ratio = (out.audio_data / signal.audio_data).mean().item()
+    assert any(abs(ratio - 0.5 ** n) < 1e-7 for n in (1, 2, 3))
+
+
+def test_masks_gate_items_and_instantiate_is_seed_reproducible():
+    transform = tfm.Compose([MulTransform(3.0), tfm.VolumeChange(prob=0.5)], prob=0.7)
+    a, b = transform.instantiate(5), transform.instantiate(5)
+    fa, fb = util.flatten(a), util.flatten(b)
+    assert fa.keys() == fb.keys() and all(torch.equal(fa[k], fb[k]) for k in fa)
+    batch = noise(B=6)
+    kwargs = MulTransform(3.0).batch_instantiate(list(range(6)), batch)
+    kwargs["MulTransform"]["mask"] = torch.tensor([True, False, True, False, False, True])
+    out = MulTransform(3.0)(batch.clone(), **kwargs)
+    for i, m in enumerate(kwargs["MulTransform"]["mask"].tolist()):
+        assert torch.allclose(out.audio_data[i], batch.audio_data[i] * (3.0 if m else 1.0))
+    kwargs["MulTransform"]["mask"][:] = False
+    assert MulTransform(3.0)(batch.clone(), **kwargs) == batch
+
+
+def test_keys_come_from_transform_signature():
+    assert tfm.LowPass().keys == ["cutoff", "mask"]
+    assert tfm.RoomImpulseResponse(sources=[noise()]).keys == ["ir_signal", "drr", "eq", "mask"]
+    p = tfm.Equalizer(n_bands=6).instantiate(0)["Equalizer"]
+    assert p["eq"].shape == (6,) and (p["eq"] <= 0).all() and p["mask"].item() is True
+    expected = -1.0 * np.random.RandomState(0).rand(6)
+    assert np.allclose(p["eq"].numpy(), expected)  # same draw order as the reference (ref :594-597)
+
+
+def test_sample_from_dist_and_ensure_tensor():
+    assert util.sample_from_dist(("const", 3)) == 3
+    v = util.sample_from_dist(("uniform", 1.0, 2.0), 0)
+    assert v == np.random.RandomState(0).uniform(1.0, 2.0)
+    assert util.sample_from_dist(("choice", [4, 8]), 1) in (4, 8)
+    t = util.ensure_tensor(2.0, 2, 3)
+    assert t.shape == (3, 1)
+    assert util.ensure_tensor(np.arange(3), 2, 3).shape == (3, 1)
+    with pytest.raises(ValueError):
+        util.random_state("nope")
+
+
+def test_audio_signal_container_semantics():
+    with pytest.raises(ValueError):
+        AudioSignal(object(), 16000)
+    with pytest.raises(AssertionError):
+        AudioSignal(torch.zeros(10))
+    s = AudioSignal(np.zeros(100), 16000)  # float64 numpy -> float32 [1,1,T]
+    assert s.audio_data.dtype == torch.float32 and s.shape == (1, 1, 100)
+    assert s.stft_params == STFTParams(512, 128, "hann", False, "reflect")  # 2**ceil(log2(0.032*sr))
+    assert AudioSignal(torch.zeros(44100), 44100).stft_params.window_length == 2048
+    with pytest.raises(AssertionError):
+        s.audio_data = torch.zeros(5)
+    s._loudness = torch.tensor([-20.0])
+    s.audio_data = s.audio_data * 2  # the setter drops the loudness cache ...
+    assert s._loudness is None
+    b = noise(B=3)
+    b._loudness = torch.tensor([-1.0, -2.0, -3.0])
+    sub = b[torch.tensor([True, False, True])]
+    assert sub.batch_size == 2 and torch.equal(sub._loudness, torch.tensor([-1.0, -3.0]))
+    sub.audio_data = sub.audio_data * 0  # (clears sub's cache)
+    b[torch.tensor([True, False, True])] = sub  # ... but __setitem__ keeps the parent's (Silence relies on it)
+    assert torch.equal(b._loudness, torch.tensor([-1.0, -2.0, -3.0]))
+    assert b.audio_data[0].abs().sum() == 0 and b.audio_data[1].abs().sum() > 0
+    c = b.clone()
+    assert c == b and c.audio_data.data_ptr() != b.audio_data.data_ptr()
+    c += 1.0
+    assert c != b and torch.allclose((c - 1.0).audio_data, b.audio_data, atol=1e-6)
+    assert torch.equal((2 * b).audio_data, (b * 2).audio_data)
+    s = noise(T=100)
+    assert s.zero_pad(5, 7).signal_length == 112 and s.trim(5, 7).signal_length == 100
+    assert s.zero_pad_to(150).signal_length == 150 and s.truncate_samples(60).signal_length == 60
+    assert noise(C=2).to_mono().num_channels == 1
+    assert s.compute_stft_padding(512, 128, False) == (0, 0)
+    assert noise(T=1000).compute_stft_padding(256, 64, True) == (24, 96)
+    with pytest.raises(AssertionError):
+        s.compute_stft_padding(512, 100, True)
+
+
+def test_batching_rules():
+    a, b = noise(T=100), noise(T=80, seed=1)
+    with pytest.raises(RuntimeError, match="same length"):
+        AudioSignal.batch([a.clone(), b.clone()])
+    assert AudioSignal.batch([a.clone(), b.clone()], pad_signals=True).shape == (2, 1, 100)
+    assert AudioSignal.batch([a.clone(), b.clone()], truncate_signals=True).shape == (2, 1, 80)
+    with pytest.raises(RuntimeError, match="same sample rate"):
+        AudioSignal.batch([a.clone(), noise(T=100, sr=16000)])
+    d = util.collate([{"signal": a.clone(), "x": {"y": torch.tensor(1.0)}}, {"signal": b.clone(), "x": {"y": torch.tensor(2.0)}}])
+    assert d["signal"].shape == (2, 1, 100) and torch.equal(d["x"]["y"], torch.tensor([1.0, 2.0]))
+    assert util.unflatten(util.flatten({"a": {"b": 1, "c": {"d": 2}}, "e": 3})) == {"a": {"b": 1, "c": {"d": 2}}, "e": 3}
+
+
+def test_deferred_gain_on_cpu_is_plain_arithmetic():
+    s = noise(B=2)
+    x = s.audio_data.clone()
+    s.volume_change(torch.tensor([-6.0, 0.0]))
+    assert s._pending_gain is None
+    assert torch.allclose(s.audio_data[0], x[0] * 10 ** (-6 / 20), rtol=1e-6) and torch.equal(s.audio_data[1], x[1])

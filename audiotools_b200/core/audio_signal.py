@@ -389,7 +389,7 @@ class AudioSignal(EffectMixin, LoudnessMixin, ImpulseResponseMixin, DSPMixin):
     def _mel_tables(sr, n_fft, n_mels, fmin, fmax, device):
         fb = _mel.mel_filters(sr, n_fft, n_mels, fmin, fmax)
         lo, hi = _mel.band_table(fb)
-        return (torch.from_numpy(np.ascontiguousarray(fb)).to(device), torch.from_numpy(lo).to(device),
+        return (torch.from_numpy(np.array(fb)).to(device), torch.from_numpy(lo).to(device),
                 torch.from_numpy(hi).to(device))
 
     def mel_spectrogram(self, n_mels: int = 80, mel_fmin: float = 0.0, mel_fmax: float = None,

@@ -11,7 +11,9 @@
 //   recursion over its 32 samples from a ZERO state (phase A); the per-chunk end states are
 //   combined with an affine scan (state' = A^32 state + e): warp shuffles, then warp totals,
 //   then a decoupled look-back across the tiles of the row (exact carry, no truncation of the
-//   38 Hz high-pass tail whose pole radius is 0.9946 @44.1k).  With its true start state each
+//   38 Hz high-pass tail whose pole radius is 0.9946 @44.1k).  The look-back runs in a ninth
+//   "carry" warp concurrently with phase A; tile records are 8-byte {value, tag} words, so one
+//   round trip fetches and validates a predecessor's state.  With its true start state each
 //   thread re-runs the recursion (phase B) and accumulates y^2 into "elementary interval" bins:
 //   with K = q*stride + r, interval A_j = [j*stride, j*stride+r), B_j = [j*stride+r, (j+1)*stride),
 //   so that block i = sum_{j=i}^{i+q-1}(A_j + B_j) + A_{i+q} -- bit-exact block indexing for any
@@ -25,9 +27,11 @@ namespace b2a {
 namespace lufs {
 
 constexpr int L = 32;              // samples per thread chunk
-constexpr int THREADS = 256;       // threads per CTA
-constexpr int NW = THREADS / 32;   // warps per CTA
-constexpr int TILE = L * THREADS;  // samples per tile (8192)
+constexpr int WORKERS = 256;       // filter threads per CTA
+constexpr int THREADS = WORKERS + 32;  // + one carry warp (decoupled look-back)
+constexpr int NW = WORKERS / 32;   // worker warps per CTA
+constexpr int TILE = L * WORKERS;  // samples per tile (8192)
+constexpr int CH = 36;             // shared-memory words per 32-sample chunk: 16 B aligned, conflict-free LDS.128
 constexpr int MAX_STAGES = 2;
 
 template <int NS>
@@ -38,26 +42,25 @@ struct Coef {  // float32-rounded, a0-normalised, stage gain folded into b
 template <int NS>
 struct Tables {
   static constexpr int D = 2 * NS;
-  float Mlane[32][D * D];  // A^(L*l), l = 0..31   (chunk-start state from the warp carry)
-  float Mscan[5][D * D];   // A^(L*2^k)            (warp shuffle scan)
-  double Mwarp[D * D];     // A^(L*32)
-  double Mtile[D * D];     // A^(TILE)
+  float Mlane[32][D * D];     // A^(L*l), l = 0..31   (chunk-start state from the warp carry)
+  float Mscan[5][D * D];      // A^(L*2^k)            (warp shuffle scan)
+  float MwPow[NW + 1][D * D]; // A^(L*32*v), v = 0..NW (carry of warp v's total into later warps)
+  float Mtile[D * D];         // A^(TILE)             (look-back across tiles)
 };
 
 __host__ __device__ inline size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
 
 struct WsLayout {
-  size_t ticket, flags, bins, zeroed_bytes, agg, incl, tables, zws, total;
+  size_t ticket, recs, bins, zeroed_bytes, tables, zws, total;
 };
+// tile records: per (tile,row) 2*D 8-byte words {float value, uint tag}: [0,D) aggregate, [D,2D) inclusive
 __host__ inline WsLayout ws_layout(int64_t rows, int64_t ntile, int64_t nbins, int64_t nblk, int D) {
   WsLayout w;
   size_t o = 0;
   w.ticket = o; o += 256;
-  w.flags = o; o = align256(o + sizeof(int) * rows * ntile);
+  w.recs = o; o = align256(o + sizeof(unsigned long long) * 2 * D * rows * ntile);
   w.bins = o; o = align256(o + sizeof(double) * rows * nbins);
   w.zeroed_bytes = o;
-  w.agg = o; o = align256(o + sizeof(double) * D * rows * ntile);
-  w.incl = o; o = align256(o + sizeof(double) * D * rows * ntile);
   w.tables = o; o = align256(o + sizeof(Tables<MAX_STAGES>));
   w.zws = o; o = align256(o + sizeof(float) * rows * nblk);
   w.total = o;
@@ -118,63 +121,166 @@ __global__ void lufs_setup_kernel(Coef<NS> cf, Tables<NS>* tb) {
     for (int i = 0; i < D * D; ++i) tb->Mlane[l][i] = (float)Q[i];
     matmul<D>(P, Q, Q);
   }
-  for (int i = 0; i < D * D; ++i) tb->Mwarp[i] = Q[i];  // P^32
+  // Q == P^32 == transition over one warp (1024 samples)
   double S[D * D];
   for (int i = 0; i < D * D; ++i) S[i] = P[i];
   for (int k = 0; k < 5; ++k) {
     for (int i = 0; i < D * D; ++i) tb->Mscan[k][i] = (float)S[i];
     matmul<D>(S, S, S);
   }
-  for (int i = 0; i < D * D; ++i) S[i] = Q[i];
-  for (int w = 1; w < NW; w <<= 1) matmul<D>(S, S, S);  // (P^32)^NW, NW is a power of two
-  for (int i = 0; i < D * D; ++i) tb->Mtile[i] = S[i];
+  double W[D * D];
+  for (int i = 0; i < D * D; ++i) W[i] = (i / D == i % D) ? 1.0 : 0.0;
+  for (int v = 0; v <= NW; ++v) {
+    for (int i = 0; i < D * D; ++i) tb->MwPow[v][i] = (float)W[i];
+    matmul<D>(Q, W, W);
+  }
+  for (int i = 0; i < D * D; ++i) tb->Mtile[i] = tb->MwPow[NW][i];
 }
 
 // ---------------------------------------------------------------------------------------------
 // main streaming kernel
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ int sx_phys(int p) { return p + (p >> 5); }  // +1 word per 32: conflict-free
+// 8-byte tile-record words {float value, uint32 tag}: one relaxed 64-bit access is atomic, so a
+// word is either absent (tag 0, the workspace is zeroed per call) or complete.
+__device__ __forceinline__ void rec_store(unsigned long long* p, float v) {
+  const unsigned long long w = ((unsigned long long)1u << 32) | (unsigned long long)(unsigned)__float_as_int(v);
+#ifdef B2A_SIM
+  __atomic_store_n(p, w, __ATOMIC_RELEASE);
+#else
+  asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(w) : "memory");
+#endif
+}
+__device__ __forceinline__ unsigned long long rec_load(const unsigned long long* p) {
+#ifdef B2A_SIM
+  return __atomic_load_n(p, __ATOMIC_ACQUIRE);
+#else
+  unsigned long long w;
+  asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(w) : "l"(p) : "memory");
+  return w;
+#endif
+}
+
+template <int D>
+__device__ __forceinline__ float row_dot(const float* M, int i, const float* v) {
+  float a = 0.f;
+#pragma unroll
+  for (int j = 0; j < D; ++j) a = fmaf(M[i * D + j], v[j], a);
+  return a;
+}
 
 template <int NS>
-__global__ void __launch_bounds__(THREADS)
+__global__ void __launch_bounds__(THREADS, 3)
 kweight_energy_kernel(const float* __restrict__ x, int rows, int T, int Tp, int ntile, Coef<NS> cf,
-                      const Tables<NS>* __restrict__ tb, int* __restrict__ ticket, int* __restrict__ flags,
-                      double* __restrict__ agg, double* __restrict__ incl, double* __restrict__ bins,
-                      int stride, int r, int nbins) {
+                      const Tables<NS>* __restrict__ tb, int* __restrict__ ticket,
+                      unsigned long long* __restrict__ recs, double* __restrict__ bins, int stride, int r,
+                      int nbins) {
   constexpr int D = 2 * NS;
-  __shared__ float sx[TILE + 2 + (TILE + 2) / 32 + 1];
+  __shared__ __align__(16) float sx[WORKERS * CH];
+  __shared__ float s_hist[2];
   __shared__ float s_mlane[32][D * D];
   __shared__ float s_mscan[5][D * D];
+  __shared__ float s_mwpow[NW + 1][D * D];
+  __shared__ float s_mt[D * D];
   __shared__ float s_tot[NW][D];
-  __shared__ float s_carry[NW][D];
-  __shared__ double s_c0[NW][D];
-  __shared__ double s_mw[D * D], s_mt[D * D], s_P[D * D], s_v[D];
+  __shared__ float s_c0[NW + 1][D];  // carry into warp w for a ZERO incoming tile state; [NW] = tile aggregate
+  __shared__ float s_sin[D];         // incoming tile state (from the look-back)
   __shared__ int s_ticket;
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   if (tid == 0) s_ticket = atomicAdd(ticket, 1);
   for (int i = tid; i < 32 * D * D; i += THREADS) (&s_mlane[0][0])[i] = (&tb->Mlane[0][0])[i];
   for (int i = tid; i < 5 * D * D; i += THREADS) (&s_mscan[0][0])[i] = (&tb->Mscan[0][0])[i];
-  if (tid < D * D) { s_mw[tid] = tb->Mwarp[tid]; s_mt[tid] = tb->Mtile[tid]; }
+  for (int i = tid; i < (NW + 1) * D * D; i += THREADS) (&s_mwpow[0][0])[i] = (&tb->MwPow[0][0])[i];
+  if (tid < D * D) s_mt[tid] = tb->Mtile[tid];
   __syncthreads();
   const int tk = s_ticket;
   const int tile = tk / rows, row = tk - tile * rows;  // tile-major: predecessors hold smaller tickets
   const int t0 = tile * TILE;
   const float* xr = x + (size_t)row * (size_t)T;
+  unsigned long long* myrec = recs + ((size_t)tile * rows + row) * (2 * D);
 
-  // stage x[t0-2 .. t0+TILE) into shared memory (coalesced 128 B per warp-load, zero beyond [0,T))
-#pragma unroll 8
-  for (int p = tid; p < TILE + 2; p += THREADS) {
-    int n = t0 - 2 + p;
-    float v = 0.f;
-    if (n >= 0 && n < T) v = __ldg(xr + n);
-    sx[sx_phys(p)] = v;
+  if (warp == NW) {
+    // ================= carry warp: decoupled look-back, concurrent with phase A of the workers
+    // lanes [0,D): inclusive words of the predecessor, lanes [D,2D): its aggregate words
+    float sin_i = 0.f;  // lane i < D: component i of the incoming state
+    if (tile > 0) {
+      float prow[D];  // lane i < D: row i of P = Mtile^j
+#pragma unroll
+      for (int j = 0; j < D; ++j) prow[j] = (lane == j) ? 1.f : 0.f;
+      for (int tj = tile - 1; tj >= 0; --tj) {
+        const unsigned long long* rec = recs + ((size_t)tj * rows + row) * (2 * D);
+        unsigned incl_ok, agg_ok;
+        unsigned long long w = 0;
+        do {
+          if (lane < 2 * D) w = rec_load(rec + (lane < D ? D + lane : lane - D));
+          const unsigned ok = __ballot_sync(0xffffffffu, (lane < 2 * D) && (w >> 32) != 0);
+          incl_ok = (ok & ((1u << D) - 1)) == ((1u << D) - 1);
+          agg_ok = ((ok >> D) & ((1u << D) - 1)) == ((1u << D) - 1);
+        } while (!incl_ok && !agg_ok);
+        const float val = __int_as_float((int)(unsigned)(w & 0xffffffffu));
+        float v[D];  // the predecessor's inclusive state if present, else its aggregate
+#pragma unroll
+        for (int j = 0; j < D; ++j) v[j] = __shfl_sync(0xffffffffu, val, incl_ok ? j : D + j);
+        if (lane < D) {
+#pragma unroll
+          for (int j = 0; j < D; ++j) sin_i = fmaf(prow[j], v[j], sin_i);
+        }
+        if (incl_ok) break;
+        float pn[D];  // P <- P * Mtile (row-wise)
+#pragma unroll
+        for (int j = 0; j < D; ++j) {
+          float a = 0.f;
+#pragma unroll
+          for (int k = 0; k < D; ++k) a = fmaf(prow[k], s_mt[k * D + j], a);
+          pn[j] = a;
+        }
+#pragma unroll
+        for (int j = 0; j < D; ++j) prow[j] = pn[j];
+      }
+    }
+    if (lane < D) s_sin[lane] = sin_i;
+    B2A_BAR_SYNC(2, THREADS);  // S_in is ready
+    return;
   }
-  __syncthreads();
+
+  // ================= worker warps
+  // stage x[t0 .. t0+TILE) as 32-sample chunks of CH words (+2 samples of history)
+  const bool fast_stage = (t0 + TILE <= T) && ((((uintptr_t)(xr + t0)) & 15) == 0);
+  if (fast_stage) {
+#pragma unroll
+    for (int i = 0; i < L / 4; ++i) {
+      const int v = tid + WORKERS * i;  // float4 index within the tile
+      const float4 q = ld_stream4(xr + t0 + 4 * v);
+      *reinterpret_cast<float4*>(&sx[CH * (v >> 3) + 4 * (v & 7)]) = q;
+    }
+  } else {
+#pragma unroll 4
+    for (int pp = tid; pp < TILE; pp += WORKERS) {
+      const int n = t0 + pp;
+      sx[CH * (pp >> 5) + (pp & 31)] = (n < T) ? __ldg(xr + n) : 0.f;
+    }
+  }
+  if (tid < 2) {
+    const int n = t0 - 2 + tid;
+    s_hist[tid] = (n >= 0 && n < T) ? __ldg(xr + n) : 0.f;
+  }
+  B2A_BAR_SYNC(1, WORKERS);
 
   float xs[L + 2];
+  {
+    const float4* c4 = reinterpret_cast<const float4*>(&sx[CH * tid]);
 #pragma unroll
-  for (int i = 0; i < L + 2; ++i) xs[i] = sx[sx_phys(tid * L + i)];
+    for (int i = 0; i < L / 4; ++i) {
+      const float4 q = c4[i];
+      xs[2 + 4 * i] = q.x; xs[3 + 4 * i] = q.y; xs[4 + 4 * i] = q.z; xs[5 + 4 * i] = q.w;
+    }
+    if (tid == 0) {
+      xs[0] = s_hist[0]; xs[1] = s_hist[1];
+    } else {
+      const float2 h = *reinterpret_cast<const float2*>(&sx[CH * (tid - 1) + 30]);
+      xs[0] = h.x; xs[1] = h.y;
+    }
+  }
 
   // ---- phase A: zero-state response of this thread's chunk -> end state e
   float g[D];
@@ -196,12 +302,7 @@ kweight_energy_kernel(const float* __restrict__ x, int rows, int T, int Tp, int 
     for (int j = 0; j < D; ++j) o[j] = __shfl_up_sync(0xffffffffu, g[j], 1u << k);
     if (lane >= (1 << k)) {
 #pragma unroll
-      for (int i = 0; i < D; ++i) {
-        float acc = g[i];
-#pragma unroll
-        for (int j = 0; j < D; ++j) acc = fmaf(s_mscan[k][i * D + j], o[j], acc);
-        g[i] = acc;
-      }
+      for (int i = 0; i < D; ++i) g[i] += row_dot<D>(s_mscan[k], i, o);
     }
   }
   float ex[D];  // exclusive prefix within the warp
@@ -214,95 +315,32 @@ kweight_energy_kernel(const float* __restrict__ x, int rows, int T, int Tp, int 
 #pragma unroll
     for (int j = 0; j < D; ++j) s_tot[warp][j] = g[j];
   }
-  __syncthreads();
+  B2A_BAR_SYNC(1, WORKERS);
 
-  // ---- tile carry: warp totals -> tile aggregate -> decoupled look-back -> carry into each warp.
-  // Warp 0 does this in float64; lane i owns row i of every mat-vec, vectors live in shared memory.
-  if (warp == 0) {
-    const size_t me = ((size_t)tile * rows + row);
-    const bool rl = lane < D;  // "row lane"
-    double c = 0.0;            // carry for a ZERO incoming state, component `lane`
-    for (int w = 0; w < NW; ++w) {
-      if (rl) s_c0[w][lane] = c;
-      __syncwarp();
-      if (rl) {
-        double a = (double)s_tot[w][lane];
-        for (int j = 0; j < D; ++j) a += s_mw[lane * D + j] * s_c0[w][j];
-        c = a;
-      }
-    }
-    // c == tile aggregate E (end state of the tile for a zero incoming state)
-    double sin_i = 0.0;  // incoming state S_in, component `lane`
-    if (tile > 0) {
-      if (rl) agg[me * D + lane] = c;
-      __threadfence();
-      __syncwarp();
-      if (lane == 0) st_release(&flags[me], 1);
-      if (lane < D * D) s_P[lane] = (lane / D == lane % D) ? 1.0 : 0.0;
-      __syncwarp();
-      for (int tj = tile - 1; tj >= 0; --tj) {
-        const size_t pj = ((size_t)tj * rows + row);
-        int f = 0;
-        if (lane == 0) {
-          do { f = ld_acquire(&flags[pj]); } while (f == 0);
-        }
-        f = __shfl_sync(0xffffffffu, f, 0);
-        if (rl) s_v[lane] = ((f == 2) ? (const volatile double*)incl : (const volatile double*)agg)[pj * D + lane];
-        __syncwarp();
-        if (rl) {
-          double a = sin_i;
-          for (int j = 0; j < D; ++j) a += s_P[lane * D + j] * s_v[j];
-          sin_i = a;
-        }
-        if (f == 2) break;
-        double pn = 0.0;
-        if (lane < D * D) {
-          const int pi = lane / D, pjx = lane % D;
-          for (int k = 0; k < D; ++k) pn += s_P[pi * D + k] * s_mt[k * D + pjx];
-        }
-        __syncwarp();
-        if (lane < D * D) s_P[lane] = pn;
-        __syncwarp();
-      }
-    }
-    if (rl) s_v[lane] = sin_i;
-    __syncwarp();
-    if (rl) {
-      double so = c;
-      for (int j = 0; j < D; ++j) so += s_mt[lane * D + j] * s_v[j];
-      incl[me * D + lane] = so;
-    }
-    __threadfence();
-    __syncwarp();
-    if (lane == 0) st_release(&flags[me], 2);
-    // carry into warp w = c0[w] + Mwarp^w * S_in
-    double cur = sin_i;
-    for (int w = 0; w < NW; ++w) {
-      if (rl) {
-        s_carry[w][lane] = (float)(s_c0[w][lane] + cur);
-        s_v[lane] = cur;
-      }
-      __syncwarp();
-      double nx = 0.0;
-      if (rl)
-        for (int j = 0; j < D; ++j) nx += s_mw[lane * D + j] * s_v[j];
-      __syncwarp();
-      cur = nx;
+  // ---- carries for a zero incoming state: c0[w] = sum_{v<w} MwPow[w-1-v] tot[v]  (each warp its own)
+  if (lane < D) {
+    float c = 0.f;
+    for (int v = 0; v < warp; ++v) c += row_dot<D>(s_mwpow[warp - 1 - v], lane, s_tot[v]);
+    s_c0[warp][lane] = c;
+    if (warp == 0) {  // tile aggregate = c0[NW]; publish it at once so successors need not wait for our look-back
+      float e = 0.f;
+      for (int v = 0; v < NW; ++v) e += row_dot<D>(s_mwpow[NW - 1 - v], lane, s_tot[v]);
+      s_c0[NW][lane] = e;
+      if (tile > 0) rec_store(myrec + lane, e);
     }
   }
-  __syncthreads();
+  B2A_BAR_SYNC(2, THREADS);  // S_in from the carry warp (also orders s_c0 within each warp: same lanes)
+  if (warp == 0 && lane < D)  // inclusive tile state = Mtile S_in + aggregate
+    rec_store(myrec + D + lane, s_c0[NW][lane] + row_dot<D>(s_mt, lane, s_sin));
 
   // ---- phase B: true start state, recursion again, energies into bins
   float y1[NS], y2[NS];
   {
-    float st[D];
+    float cw[D], st[D];
 #pragma unroll
-    for (int i = 0; i < D; ++i) {
-      float acc = ex[i];
+    for (int i = 0; i < D; ++i) cw[i] = s_c0[warp][i] + row_dot<D>(s_mwpow[warp], i, s_sin);
 #pragma unroll
-      for (int j = 0; j < D; ++j) acc = fmaf(s_mlane[lane][i * D + j], s_carry[warp][j], acc);
-      st[i] = acc;
-    }
+    for (int i = 0; i < D; ++i) st[i] = ex[i] + row_dot<D>(s_mlane[lane], i, cw);
 #pragma unroll
     for (int s = 0; s < NS; ++s) { y1[s] = st[2 * s]; y2[s] = st[2 * s + 1]; }
   }
@@ -523,8 +561,8 @@ static int run(const float* x, int64_t B, int C, int64_t T, int64_t Tp, const Ge
   B2A_CUDA_OK(cudaMemsetAsync(base, 0, w.zeroed_bytes, (cudaStream_t)stream));
   B2A_LAUNCH(lufs_setup_kernel<NS>, dim3(1), dim3(32), 0, stream, cf, tb);
   B2A_LAUNCH(kweight_energy_kernel<NS>, dim3((unsigned)(rows * g.ntile)), dim3(THREADS), 0, stream, x, (int)rows,
-             (int)T, (int)Tp, g.ntile, cf, (const Tables<NS>*)tb, (int*)(base + w.ticket), (int*)(base + w.flags),
-             (double*)(base + w.agg), (double*)(base + w.incl), (double*)(base + w.bins), g.stride, g.r, g.nbins);
+             (int)T, (int)Tp, g.ntile, cf, (const Tables<NS>*)tb, (int*)(base + w.ticket),
+             (unsigned long long*)(base + w.recs), (double*)(base + w.bins), g.stride, g.r, g.nbins);
   GateParams gp;
   for (int c = 0; c < 8; ++c) gp.G[c] = c < C ? chan_gain_h[c] : 0.0;
   gp.scale = (float)(1.0 / (block_s * rate));

@@ -41,37 +41,38 @@ __device__ __forceinline__ float2 cmul(float2 a, float2 b) {
   return make_float2(fmaf(a.x, b.x, -a.y * b.y), fmaf(a.x, b.y, a.y * b.x));
 }
 
-// cos(pi*j/8), j = 0..8
-__device__ __forceinline__ constexpr float cos_pi8(int j) {
+// cos(pi*j/16), j = 0..16
+__device__ __forceinline__ constexpr float cos_pi16(int j) {
   return j == 0 ? 1.0f
-       : j == 1 ? 0.92387953251128674f
-       : j == 2 ? 0.70710678118654752f
-       : j == 3 ? 0.38268343236508977f
-       : j == 4 ? 0.0f
-       : j == 5 ? -0.38268343236508977f
-       : j == 6 ? -0.70710678118654752f
-       : j == 7 ? -0.92387953251128674f
-                : -1.0f;
+       : j == 1 ? 0.98078528040323043f
+       : j == 2 ? 0.92387953251128674f
+       : j == 3 ? 0.83146961230254524f
+       : j == 4 ? 0.70710678118654752f
+       : j == 5 ? 0.55557023301960222f
+       : j == 6 ? 0.38268343236508977f
+       : j == 7 ? 0.19509032201612827f
+       : j == 8 ? 0.0f
+                : -cos_pi16(16 - j);
 }
 
-// o * W_R^k, W = exp(-2 pi i / R), 0 <= k < R/2, R in {2,4,8,16}
+// o * W_R^k, W = exp(-2 pi i / R), 0 <= k < R/2, R in {2,4,8,16,32}
 template <int R, int K>
 __device__ __forceinline__ float2 mul_wr(float2 o) {
-  constexpr int j = 16 * K / R;  // angle = pi*j/8
+  constexpr int j = 32 * K / R;  // angle = pi*j/16, 0 <= j < 16
   if constexpr (j == 0) {
     return o;
-  } else if constexpr (j == 4) {  // -i
+  } else if constexpr (j == 8) {  // -i
     return make_float2(o.y, -o.x);
-  } else if constexpr (j == 2) {  // (1 - i)/sqrt2
+  } else if constexpr (j == 4) {  // (1 - i)/sqrt2
     constexpr float h = 0.70710678118654752f;
     return make_float2(h * (o.x + o.y), h * (o.y - o.x));
-  } else if constexpr (j == 6) {  // (-1 - i)/sqrt2
+  } else if constexpr (j == 12) {  // (-1 - i)/sqrt2
     constexpr float h = 0.70710678118654752f;
     return make_float2(h * (o.y - o.x), -h * (o.x + o.y));
   } else {
-    constexpr float c = cos_pi8(j);
-    constexpr float s = cos_pi8(j <= 4 ? 4 - j : j - 4);  // sin(pi j/8)
-    return make_float2(fmaf(o.x, c, o.y * s), fmaf(o.y, c, -o.x * s));  // o * (c - i s)
+    constexpr float c = cos_pi16(j);
+    constexpr float sn = cos_pi16(j <= 8 ? 8 - j : j - 8);  // sin(pi j/16)
+    return make_float2(fmaf(o.x, c, o.y * sn), fmaf(o.y, c, -o.x * sn));  // o * (c - i sn)
   }
 }
 
@@ -158,6 +159,65 @@ __device__ __forceinline__ int src_index(int w, int T, int pad, int right_pad, i
   return (u >= 0 && u < T) ? u : -1;
 }
 
+// Stage the contiguous sample span of a tile into shared memory (x * gain) and write back the part
+// of the scaled waveform this CTA owns ([n0*hop, (n0+FR)*hop) -- the last tile up to T).
+__device__ __forceinline__ void stage_span(const Params& p, float* sp, int row, int tile, int n0, int FR, int ws,
+                                           float g) {
+  const int tid = threadIdx.x, T = p.T, hop = p.hop, span = p.span;
+  const float* xr = p.x + (size_t)row * (size_t)T;
+  // ---- stage the sample span (x * gain), write back the owned part of the scaled waveform
+  const int own_lo = n0 * hop;  // only used when y_out (pad == 0, drop_edge == 0)
+  const int own_hi = (tile == p.n_tiles - 1) ? T : min(T, (n0 + FR) * hop);
+  const bool interior = (ws >= 0) && (ws + span <= T);
+  if (interior) {
+    const float* src = xr + ws;
+    const bool vec = ((((uintptr_t)src) & 15) == 0) && ((span & 3) == 0) &&
+                     (!p.y_out || (((uintptr_t)(p.y_out + (size_t)row * T + ws)) & 15) == 0);
+    if (vec) {
+      for (int i = tid * 4; i < span; i += (int)blockDim.x * 4) {
+        float4 v = *reinterpret_cast<const float4*>(src + i);
+        if (p.gain) { v.x *= g; v.y *= g; v.z *= g; v.w *= g; }
+        *reinterpret_cast<float4*>(sp + i) = v;
+        if (p.y_out) {
+          const int w = ws + i;
+          if (w >= own_lo && w + 3 < own_hi) {
+            *reinterpret_cast<float4*>(p.y_out + (size_t)row * T + w) = v;
+          } else {
+            float vv[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e)
+              if (w + e >= own_lo && w + e < own_hi) p.y_out[(size_t)row * T + w + e] = vv[e];
+          }
+        }
+      }
+    } else {
+      for (int i = tid; i < span; i += (int)blockDim.x) {
+        float v = __ldg(src + i);
+        if (p.gain) v *= g;
+        sp[i] = v;
+        const int w = ws + i;
+        if (p.y_out && w >= own_lo && w < own_hi) p.y_out[(size_t)row * T + w] = v;
+      }
+    }
+  } else {
+    for (int i = tid; i < span; i += (int)blockDim.x) {
+      const int w = ws + i;
+      const int u = src_index(w, T, p.pad, p.right_pad, p.pad_mode);
+      float v = (u >= 0) ? __ldg(xr + u) : 0.f;
+      if (p.gain) v *= g;
+      sp[i] = v;
+      if (p.y_out && w >= own_lo && w < own_hi) p.y_out[(size_t)row * T + w] = v;  // w in [0,T) => u == w
+    }
+  }
+  if (p.y_out) {  // owned samples the span does not cover (only when hop > n_fft/2)
+    for (int w = max(own_lo, ws + span) + tid; w < own_hi; w += (int)blockDim.x) {
+      float v = __ldg(xr + w);
+      if (p.gain) v *= g;
+      p.y_out[(size_t)row * T + w] = v;
+    }
+  }
+}
+
 template <int TPF>
 __device__ __forceinline__ void group_sync(int g) {
   if constexpr (TPF >= 64) {
@@ -210,11 +270,9 @@ __global__ void __launch_bounds__(THREADS) spectral_kernel(Params p) {
   const int row = blockIdx.x / p.n_tiles;
   const int tile = blockIdx.x - row * p.n_tiles;
   const int n0 = tile * FR;  // first output frame of this CTA
-  const int T = p.T, hop = p.hop, n_fft = 2 * N;
-  const float* xr = p.x + (size_t)row * (size_t)T;
+  const int hop = p.hop, n_fft = 2 * N;
   const float g = p.gain ? __ldg(p.gain + row / p.rows_per_gain) : 1.0f;
   const int ws = (n0 + p.drop_edge) * hop - N - p.pad;  // x-coordinate of span[0]
-  const int span = p.span;
 
   // ---- tables (role-dependent only)
   for (int i = tid; i < n_fft; i += THREADS) win[i] = __ldg(p.window + i);
@@ -238,57 +296,7 @@ __global__ void __launch_bounds__(THREADS) spectral_kernel(Params p) {
     ut[i] = make_float2(cs, sn);
   }
 
-  // ---- stage the sample span (x * gain), write back the owned part of the scaled waveform
-  const int own_lo = n0 * hop;  // only used when y_out (pad == 0, drop_edge == 0)
-  const int own_hi = (tile == p.n_tiles - 1) ? T : min(T, (n0 + FR) * hop);
-  const bool interior = (ws >= 0) && (ws + span <= T);
-  if (interior) {
-    const float* src = xr + ws;
-    const bool vec = ((((uintptr_t)src) & 15) == 0) && ((span & 3) == 0) &&
-                     (!p.y_out || (((uintptr_t)(p.y_out + (size_t)row * T + ws)) & 15) == 0);
-    if (vec) {
-      for (int i = tid * 4; i < span; i += THREADS * 4) {
-        float4 v = *reinterpret_cast<const float4*>(src + i);
-        if (p.gain) { v.x *= g; v.y *= g; v.z *= g; v.w *= g; }
-        *reinterpret_cast<float4*>(sp + i) = v;
-        if (p.y_out) {
-          const int w = ws + i;
-          if (w >= own_lo && w + 3 < own_hi) {
-            *reinterpret_cast<float4*>(p.y_out + (size_t)row * T + w) = v;
-          } else {
-            float vv[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-            for (int e = 0; e < 4; ++e)
-              if (w + e >= own_lo && w + e < own_hi) p.y_out[(size_t)row * T + w + e] = vv[e];
-          }
-        }
-      }
-    } else {
-      for (int i = tid; i < span; i += THREADS) {
-        float v = __ldg(src + i);
-        if (p.gain) v *= g;
-        sp[i] = v;
-        const int w = ws + i;
-        if (p.y_out && w >= own_lo && w < own_hi) p.y_out[(size_t)row * T + w] = v;
-      }
-    }
-  } else {
-    for (int i = tid; i < span; i += THREADS) {
-      const int w = ws + i;
-      const int u = src_index(w, T, p.pad, p.right_pad, p.pad_mode);
-      float v = (u >= 0) ? __ldg(xr + u) : 0.f;
-      if (p.gain) v *= g;
-      sp[i] = v;
-      if (p.y_out && w >= own_lo && w < own_hi) p.y_out[(size_t)row * T + w] = v;  // w in [0,T) => u == w
-    }
-  }
-  if (p.y_out) {  // owned samples the span does not cover (only when hop > n_fft/2)
-    for (int w = max(own_lo, ws + span) + tid; w < own_hi; w += THREADS) {
-      float v = __ldg(xr + w);
-      if (p.gain) v *= g;
-      p.y_out[(size_t)row * T + w] = v;
-    }
-  }
+  stage_span(p, sp, row, tile, n0, FR, ws, g);
   __syncthreads();
 
   const int grp = tid / TPF, q = tid - grp * TPF;
@@ -418,6 +426,227 @@ static int launch(Params& p, void* stream) {
   return B2A_OK;
 }
 
+
+// =============================================================================================
+// Warp-per-frame kernel (n_fft 64 .. 2048): the fast path.
+//
+// A frame of N = n_fft/2 packed complex points is owned by LPF = N/32 lanes of ONE warp, 32 points
+// per lane, and transformed with two Stockham passes: radix 32, then radix LPF.  Nothing in the
+// FFT crosses a warp, so there is no CTA barrier between the span load and the final tile store:
+//   pass 0   32 points/lane straight from the staged span (x window), radix-32 DFT in registers
+//   exchange one warp-private 32 x 32 transpose through shared memory (two float planes, stride 33:
+//            conflict-free), __syncwarp only
+//   pass 1   role-constant twiddles (shared memory, [slot][lane]), radix-LPF DFTs in registers;
+//            the lane ends up with Z[l + LPF m], m = 0..31, in natural order
+//   untangle Z[N-k] lives in lane LPF-l, register 31-m: one warp shuffle per pair, each lane
+//            produces the real-FFT bins k and N-k for its 16 k < N/2
+//   mel      |X| -> the (dead) exchange plane -> banded FP32 gather, post-op, tile in smem
+// =============================================================================================
+template <int LOG2N>
+struct WPlan {
+  static constexpr int N = 1 << LOG2N;
+  static constexpr int LPF = N / 32;   // lanes per frame
+  static constexpr int FPW = 32 / LPF; // frames per warp in flight
+  static constexpr int R1 = LPF;       // radix of pass 1 (1 => single pass)
+  static constexpr int B1 = 32 / R1;   // pass-1 butterflies per lane
+  static constexpr int NWARP = 8;
+  static constexpr int G = NWARP * FPW;            // frames in flight per CTA
+  static constexpr int FR = (G >= 16) ? G : 16;    // frames per CTA
+  static constexpr int NTW = (R1 >= 2) ? B1 * (R1 - 1) : 0;
+  static constexpr int XB = N + N / 32 + 1;        // floats per frame: padded exchange plane, >= N + 1 (mags)
+};
+
+__device__ __forceinline__ float fast_sqrt(float v) {
+#ifdef B2A_SIM
+  return sqrtf(v);
+#else
+  float r;
+  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(v));  // <= 2 ulp; |X| feeds a 1e-4 tolerance
+  return r;
+#endif
+}
+
+template <int LOG2N>
+__global__ void __launch_bounds__(256, 2) spectral_warp_kernel(Params p) {
+  using PL = WPlan<LOG2N>;
+  constexpr int N = PL::N, LPF = PL::LPF, FPW = PL::FPW, R1 = PL::R1, B1 = PL::B1, G = PL::G, FR = PL::FR;
+  B2A_DYN_SMEM(smem);
+  float* sp = reinterpret_cast<float*>(smem);
+  float* win = reinterpret_cast<float*>(smem + p.off_win);   // [n_fft]
+  float2* tw = reinterpret_cast<float2*>(smem + p.off_tw);   // [NTW][LPF]
+  float2* ut = reinterpret_cast<float2*>(smem + p.off_ut);   // [16][LPF]  exp(-i pi (l + LPF m) / N)
+  float* xbs = reinterpret_cast<float*>(smem + p.off_buf);   // [G][XB]
+  float* melt = reinterpret_cast<float*>(smem + p.off_mel);  // [n_mels][FR+1]
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int row = blockIdx.x / p.n_tiles;
+  const int tile = blockIdx.x - row * p.n_tiles;
+  const int n0 = tile * FR;
+  const int hop = p.hop, n_fft = 2 * N, F = N + 1;
+  const float g = p.gain ? __ldg(p.gain + row / p.rows_per_gain) : 1.0f;
+  const int ws = (n0 + p.drop_edge) * hop - N - p.pad;
+  const int l = lane & (LPF - 1);  // lane within the frame
+  const int fw = lane / LPF;       // frame within the warp
+
+  for (int i = tid; i < n_fft; i += 256) win[i] = __ldg(p.window + i);
+  for (int i = tid; i < PL::NTW * LPF; i += 256) {
+    const int slot = i / LPF, ll = i - slot * LPF;
+    const int b = slot / (R1 > 1 ? R1 - 1 : 1), t = slot - b * (R1 > 1 ? R1 - 1 : 1) + 1;
+    float sn, cs;  // W_N^{(ll + LPF b) t}
+    sincospif(-2.0f * (float)((ll + LPF * b) * t) / (float)N, &sn, &cs);
+    tw[i] = make_float2(cs, sn);
+  }
+  for (int i = tid; i < 16 * LPF; i += 256) {
+    const int m = i / LPF, ll = i - m * LPF;
+    float sn, cs;
+    sincospif(-(float)(ll + LPF * m) / (float)N, &sn, &cs);
+    ut[i] = make_float2(cs, sn);
+  }
+  stage_span(p, sp, row, tile, n0, FR, ws, g);
+  __syncthreads();
+
+  float* xb = xbs + (warp * FPW + fw) * PL::XB;
+  const int src_lane = (lane & ~(LPF - 1)) | ((LPF - l) & (LPF - 1));  // holder of Z[N - k]
+
+#pragma unroll 1
+  for (int rd = 0; rd < FR / G; ++rd) {
+    const int f = rd * G + warp * FPW + fw;
+    const int n = n0 + f;
+    const bool live = n < p.n_frames;
+    const float* fs = sp + f * hop;
+
+    // ---- pass 0: radix 32 over the windowed frame, element e = l + LPF m
+    float2 z[32];
+    {
+      float2 v[32];
+      if ((hop & 1) == 0) {
+#pragma unroll
+        for (int m = 0; m < 32; ++m) {
+          const int e = l + LPF * m;
+          const float2 s2 = *reinterpret_cast<const float2*>(fs + 2 * e);
+          const float2 w2 = *reinterpret_cast<const float2*>(win + 2 * e);
+          v[m] = make_float2(s2.x * w2.x, s2.y * w2.y);
+        }
+      } else {
+#pragma unroll
+        for (int m = 0; m < 32; ++m) {
+          const int e = l + LPF * m;
+          v[m] = make_float2(fs[2 * e] * win[2 * e], fs[2 * e + 1] * win[2 * e + 1]);
+        }
+      }
+      DFT<32, 1>::run(v, z);
+    }
+    if constexpr (R1 >= 2) {
+      // ---- exchange (transpose within the frame's lanes): write i = l*32 + t, read e = l + LPF m
+#pragma unroll
+      for (int t = 0; t < 32; ++t) xb[l * 33 + t] = z[t].x;
+      __syncwarp();
+#pragma unroll
+      for (int m = 0; m < 32; ++m) { const int e = l + LPF * m; z[m].x = xb[e + (e >> 5)]; }
+      __syncwarp();
+#pragma unroll
+      for (int t = 0; t < 32; ++t) xb[l * 33 + t] = z[t].y;
+      __syncwarp();
+#pragma unroll
+      for (int m = 0; m < 32; ++m) { const int e = l + LPF * m; z[m].y = xb[e + (e >> 5)]; }
+      __syncwarp();
+      // ---- pass 1: radix LPF, NS = 32
+#pragma unroll
+      for (int b = 0; b < B1; ++b) {
+#pragma unroll
+        for (int t = 1; t < R1; ++t)
+          z[b + B1 * t] = cmul(z[b + B1 * t], tw[(b * (R1 - 1) + (t - 1)) * LPF + l]);
+        float2 o[R1];
+        DFT<R1, B1>::run(&z[b], o);
+#pragma unroll
+        for (int t = 0; t < R1; ++t) z[b + B1 * t] = o[t];
+      }
+    }
+    // now z[m] = Z[l + LPF m]
+
+    // ---- untangle -> real-FFT bins k = l + LPF m (m < 16) and N - k ; magnitudes into xb
+    float2* so = p.stft_out ? p.stft_out + (size_t)row * F * p.n_frames + n : nullptr;
+#pragma unroll
+    for (int m = 0; m < 16; ++m) {
+      const float2 zk = z[m];
+      float2 zn;
+      zn.x = __shfl_sync(0xffffffffu, z[31 - m].x, src_lane);
+      zn.y = __shfl_sync(0xffffffffu, z[31 - m].y, src_lane);
+      if (l == 0) zn = z[(32 - m) & 31];
+      const int k = l + LPF * m;
+      const float2 xe = make_float2(0.5f * (zk.x + zn.x), 0.5f * (zk.y - zn.y));
+      const float2 xo = make_float2(0.5f * (zk.y + zn.y), 0.5f * (zn.x - zk.x));
+      const float2 tt = cmul(ut[m * LPF + l], xo);
+      const float2 xk = cadd(xe, tt);
+      const float2 d = csub(xe, tt);
+      if (so && live) {
+        so[(size_t)k * p.n_frames] = xk;
+        so[(size_t)(N - k) * p.n_frames] = make_float2(d.x, -d.y);
+      }
+      xb[k] = fast_sqrt(fmaf(xk.x, xk.x, xk.y * xk.y));
+      xb[N - k] = fast_sqrt(fmaf(d.x, d.x, d.y * d.y));
+    }
+    if (l == 0) {  // k = N/2 pairs with itself: X = conj(Z[N/2])
+      const float2 zh = z[16];
+      if (so && live) so[(size_t)(N / 2) * p.n_frames] = make_float2(zh.x, -zh.y);
+      xb[N / 2] = fast_sqrt(fmaf(zh.x, zh.x, zh.y * zh.y));
+    }
+    __syncwarp();
+
+    // ---- banded mel projection + post-op
+    if (p.mel_out) {
+      for (int mm = l; mm < p.n_mels; mm += LPF) {
+        const int lo = __ldg(p.mel_lo + mm), hi = __ldg(p.mel_hi + mm);
+        const float* wrow = p.mel_fb + (size_t)mm * F;
+        float acc = 0.f;
+        for (int k = lo; k < hi; ++k) acc = fmaf(__ldg(wrow + k), xb[k], acc);
+        if (p.post == B2A_POST_LOG10) {
+          float c = fmaxf(acc, p.post_eps);
+          c = (p.post_power == 2.0f) ? c * c : powf(c, p.post_power);
+          acc = log10f(c);
+        } else if (p.post == B2A_POST_LN) {
+          acc = logf(acc + p.post_eps);
+        }
+        melt[mm * (FR + 1) + f] = acc;
+      }
+    }
+    __syncwarp();
+  }
+
+  if (p.mel_out) {
+    __syncthreads();
+    const int nf = min(FR, p.n_frames - n0);
+    float* o = p.mel_out + (size_t)row * p.n_mels * p.n_frames + n0;
+    for (int i = tid; i < p.n_mels * FR; i += 256) {
+      const int m = i / FR, f = i - m * FR;
+      if (f < nf) o[(size_t)m * p.n_frames + f] = melt[m * (FR + 1) + f];
+    }
+  }
+}
+
+template <int LOG2N>
+static int launch_warp(Params& p, void* stream) {
+  using PL = WPlan<LOG2N>;
+  p.span = (PL::FR - 1) * p.hop + p.n_fft;
+  p.n_tiles = (p.n_frames + PL::FR - 1) / PL::FR;
+  int o = align16(p.span * 4);
+  p.off_win = o; o = align16(o + p.n_fft * 4);
+  p.off_tw = o; o = align16(o + PL::NTW * PL::LPF * 8 + 16);
+  p.off_ut = o; o = align16(o + 16 * PL::LPF * 8);
+  p.off_buf = o; o = align16(o + PL::G * PL::XB * 4);
+  p.off_mag = o;
+  p.off_mel = o; o = align16(o + (p.mel_out ? p.n_mels * (PL::FR + 1) * 4 : 0));
+  p.smem_bytes = o;
+  B2A_REQUIRE(o <= 227 * 1024, B2A_E_UNSUPPORTED,
+              "spectral: n_fft=%d hop=%d n_mels=%d needs %d bytes of shared memory (> 227 KB)", p.n_fft, p.hop,
+              p.n_mels, o);
+  B2A_REQUIRE((int64_t)p.rows * p.n_tiles < (int64_t)2147483647, B2A_E_UNSUPPORTED, "spectral: grid too large");
+  B2A_CUDA_OK(cudaFuncSetAttribute(spectral_warp_kernel<LOG2N>, cudaFuncAttributeMaxDynamicSharedMemorySize, o));
+  B2A_LAUNCH(spectral_warp_kernel<LOG2N>, dim3((unsigned)(p.rows * p.n_tiles)), dim3(256), (size_t)o, stream, p);
+  B2A_CUDA_OK(cudaGetLastError());
+  return B2A_OK;
+}
+
 }  // namespace spectral
 }  // namespace b2a
 
@@ -466,13 +695,13 @@ extern "C" int b2a_spectral_f32(const float* x, int64_t rows, int64_t T, int n_f
   p.rows_per_gain = gain ? rows_per_gain : 1; p.post = post; p.post_eps = post_eps; p.post_power = post_power;
   switch (n_fft) {
     case 32: return launch<4>(p, stream);
-    case 64: return launch<5>(p, stream);
-    case 128: return launch<6>(p, stream);
-    case 256: return launch<7>(p, stream);
-    case 512: return launch<8>(p, stream);
-    case 1024: return launch<9>(p, stream);
-    case 2048: return launch<10>(p, stream);
-    case 4096: return launch<11>(p, stream);
+    case 64: return launch_warp<5>(p, stream);
+    case 128: return launch_warp<6>(p, stream);
+    case 256: return launch_warp<7>(p, stream);
+    case 512: return launch_warp<8>(p, stream);
+    case 1024: return launch_warp<9>(p, stream);
+    case 2048: return launch_warp<10>(p, stream);
+    case 4096: return launch<11>(p, stream);  // 64 lanes per frame: CTA-cooperative kernel
   }
   return b2a::fail(B2A_E_UNSUPPORTED, "spectral: n_fft %d", n_fft);
 }

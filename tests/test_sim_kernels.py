@@ -89,7 +89,7 @@ def test_stft_other_padding_types(eng, mode):
 def _mel_tables(sr, n_fft, n_mels, fmin=0.0, fmax=None):
     fb = melmod.mel_filters(sr, n_fft, n_mels, fmin, fmax)
     lo, hi = melmod.band_table(fb)
-    return torch.from_numpy(np.ascontiguousarray(fb)), torch.from_numpy(lo), torch.from_numpy(hi)
+    return torch.from_numpy(np.array(fb)), torch.from_numpy(lo), torch.from_numpy(hi)
 
 
 def test_fused_normalize_logmel_cfg2_golden(eng, golden):

@@ -23,7 +23,7 @@ SIGNATURES = {
     "b2a_spectral_f32": (c_int, [c_void_p, c_int64, c_int64, c_int, c_int, c_void_p,
                                  c_int, c_int, c_int, c_int,
                                  c_void_p, c_int, c_void_p,
-                                 c_void_p, c_void_p, c_void_p, c_int,
+                                 c_void_p, c_void_p, c_void_p, c_int, c_int,
                                  c_int, c_float, c_float,
                                  c_void_p, c_void_p, c_void_p]),
     "b2a_lufs_num_blocks": (c_int64, [c_int64, c_double, c_double]),

@@ -137,6 +137,8 @@ struct Params {
   float2* stft_out;
   int rows, T, n_fft, hop, pad, right_pad, pad_mode, drop_edge;
   int n_frames, n_tiles, n_mels, rows_per_gain, post;
+  int mel_packed_len;  // sum over filters of the 4-aligned band widths (0: read weights from global)
+  int off_mpk, off_mseg;
   float post_eps, post_power;
   int span;  // (FR-1)*hop + n_fft
   // shared memory offsets (bytes)
@@ -216,6 +218,63 @@ __device__ __forceinline__ void stage_span(const Params& p, float* sp, int row, 
       p.y_out[(size_t)row * T + w] = v;
     }
   }
+}
+
+// ---- asynchronous staging (warp kernel): raw x -> shared memory with cp.async, so that the copy
+// overlaps the per-CTA table set-up; the gain is folded into the window (x*(w*g)) and the scaled
+// waveform x*g is written back from shared memory afterwards.
+__device__ __forceinline__ void cp_async16(float* smem_dst, const float* gmem_src) {
+#ifdef B2A_SIM
+  *reinterpret_cast<float4*>(smem_dst) = *reinterpret_cast<const float4*>(gmem_src);
+#else
+  const unsigned sa = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(gmem_src) : "memory");
+#endif
+}
+__device__ __forceinline__ void cp_async_wait_all() {
+#ifndef B2A_SIM
+  asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
+#endif
+}
+
+__device__ __forceinline__ void stage_span_async(const Params& p, float* sp, int row, int ws) {
+  const int tid = threadIdx.x, T = p.T, span = p.span;
+  const float* xr = p.x + (size_t)row * (size_t)T;
+  const bool interior = (ws >= 0) && (ws + span <= T);
+  if (interior && ((((uintptr_t)(xr + ws)) & 15) == 0) && ((span & 3) == 0)) {
+    for (int i = tid * 4; i < span; i += (int)blockDim.x * 4) cp_async16(sp + i, xr + ws + i);
+  } else if (interior) {
+    for (int i = tid; i < span; i += (int)blockDim.x) sp[i] = __ldg(xr + ws + i);
+  } else {
+    for (int i = tid; i < span; i += (int)blockDim.x) {
+      const int u = src_index(ws + i, T, p.pad, p.right_pad, p.pad_mode);
+      sp[i] = (u >= 0) ? __ldg(xr + u) : 0.f;
+    }
+  }
+}
+
+// y_out[w] = x[w] * g for the samples this CTA owns (requires pad == drop_edge == 0, so span[i] = x[ws+i])
+__device__ __forceinline__ void writeback_scaled(const Params& p, const float* sp, int row, int tile, int n0, int FR,
+                                                 int ws, float g) {
+  const int tid = threadIdx.x, T = p.T, hop = p.hop, span = p.span;
+  const int own_lo = n0 * hop;
+  const int own_hi = (tile == p.n_tiles - 1) ? T : min(T, (n0 + FR) * hop);
+  float* yr = p.y_out + (size_t)row * (size_t)T;
+  const int lo = max(own_lo, ws), hi = min(own_hi, ws + span);  // part covered by the span
+  const bool vec = (((lo - ws) & 3) == 0) && ((((uintptr_t)(yr + lo)) & 15) == 0);
+  if (vec) {
+    const int n4 = (hi - lo) >> 2;
+    for (int i = tid; i < n4; i += (int)blockDim.x) {
+      float4 v = *reinterpret_cast<const float4*>(sp + (lo - ws) + 4 * i);
+      v.x *= g; v.y *= g; v.z *= g; v.w *= g;
+      st_stream4(yr + lo + 4 * i, v);
+    }
+    for (int w = lo + 4 * n4 + tid; w < hi; w += (int)blockDim.x) yr[w] = sp[w - ws] * g;
+  } else {
+    for (int w = lo + tid; w < hi; w += (int)blockDim.x) yr[w] = sp[w - ws] * g;
+  }
+  const float* xr = p.x + (size_t)row * (size_t)T;
+  for (int w = max(own_lo, ws + span) + tid; w < own_hi; w += (int)blockDim.x) yr[w] = __ldg(xr + w) * g;
 }
 
 template <int TPF>
@@ -453,7 +512,7 @@ struct WPlan {
   static constexpr int G = NWARP * FPW;            // frames in flight per CTA
   static constexpr int FR = (G >= 16) ? G : 16;    // frames per CTA
   static constexpr int NTW = (R1 >= 2) ? B1 * (R1 - 1) : 0;
-  static constexpr int XB = N + N / 32 + 1;        // floats per frame: padded exchange plane, >= N + 1 (mags)
+  static constexpr int XB = ((N + N / 32 + 4 + 3) / 4) * 4;  // floats per frame: padded exchange plane / |X| + 3 zeros, 16 B multiple
 };
 
 __device__ __forceinline__ float fast_sqrt(float v) {
@@ -488,7 +547,9 @@ __global__ void __launch_bounds__(256, 2) spectral_warp_kernel(Params p) {
   const int l = lane & (LPF - 1);  // lane within the frame
   const int fw = lane / LPF;       // frame within the warp
 
-  for (int i = tid; i < n_fft; i += 256) win[i] = __ldg(p.window + i);
+  stage_span_async(p, sp, row, ws);  // in flight while the tables below are computed
+
+  for (int i = tid; i < n_fft; i += 256) win[i] = __ldg(p.window + i) * g;  // gain folded into the window
   for (int i = tid; i < PL::NTW * LPF; i += 256) {
     const int slot = i / LPF, ll = i - slot * LPF;
     const int b = slot / (R1 > 1 ? R1 - 1 : 1), t = slot - b * (R1 > 1 ? R1 - 1 : 1) + 1;
@@ -502,8 +563,44 @@ __global__ void __launch_bounds__(256, 2) spectral_warp_kernel(Params p) {
     sincospif(-(float)(ll + LPF * m) / (float)N, &sn, &cs);
     ut[i] = make_float2(cs, sn);
   }
-  stage_span(p, sp, row, tile, n0, FR, ws, g);
+  // banded mel weights packed into shared memory: filter m -> 4-aligned band [lo4, lo4 + 4 n4), zero padded
+  float* mpk = reinterpret_cast<float*>(smem + p.off_mpk);
+  int4* mseg = reinterpret_cast<int4*>(smem + p.off_mseg);  // (offset, lo4, n4, -)
+  const bool packed = p.mel_out && p.mel_packed_len > 0;
+  if (packed) {
+    if (warp == 0) {  // exclusive scan of the padded widths
+      int run = 0;
+      for (int m0 = 0; m0 < p.n_mels; m0 += 32) {
+        const int m = m0 + lane;
+        int lo4 = 0, n4 = 0;
+        if (m < p.n_mels) {
+          lo4 = __ldg(p.mel_lo + m) & ~3;
+          n4 = (((__ldg(p.mel_hi + m) + 3) & ~3) - lo4) >> 2;
+          if (n4 < 0) n4 = 0;
+        }
+        int inc = n4;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const int up = __shfl_up_sync(0xffffffffu, inc, o);
+          if (lane >= o) inc += up;
+        }
+        if (m < p.n_mels) mseg[m] = make_int4(run + inc - n4, lo4, n4, 0);
+        run += __shfl_sync(0xffffffffu, inc, 31);
+      }
+    }
+    __syncthreads();
+    for (int m = warp; m < p.n_mels; m += 8) {
+      const int4 sg = mseg[m];
+      const float* wrow = p.mel_fb + (size_t)m * F;
+      for (int i = lane; i < 4 * sg.z; i += 32) {
+        const int k = sg.y + i;
+        mpk[4 * sg.x + i] = (k < F) ? __ldg(wrow + k) : 0.f;
+      }
+    }
+  }
+  cp_async_wait_all();
   __syncthreads();
+  if (p.y_out) writeback_scaled(p, sp, row, tile, n0, FR, ws, g);
 
   float* xb = xbs + (warp * FPW + fw) * PL::XB;
   const int src_lane = (lane & ~(LPF - 1)) | ((LPF - l) & (LPF - 1));  // holder of Z[N - k]
@@ -590,16 +687,30 @@ __global__ void __launch_bounds__(256, 2) spectral_warp_kernel(Params p) {
       const float2 zh = z[16];
       if (so && live) so[(size_t)(N / 2) * p.n_frames] = make_float2(zh.x, -zh.y);
       xb[N / 2] = fast_sqrt(fmaf(zh.x, zh.x, zh.y * zh.y));
+      xb[N + 1] = 0.f; xb[N + 2] = 0.f; xb[N + 3] = 0.f;  // read (x 0 weight) by 4-wide band loads
     }
     __syncwarp();
 
     // ---- banded mel projection + post-op
     if (p.mel_out) {
       for (int mm = l; mm < p.n_mels; mm += LPF) {
-        const int lo = __ldg(p.mel_lo + mm), hi = __ldg(p.mel_hi + mm);
-        const float* wrow = p.mel_fb + (size_t)mm * F;
         float acc = 0.f;
-        for (int k = lo; k < hi; ++k) acc = fmaf(__ldg(wrow + k), xb[k], acc);
+        if (packed) {
+          const int4 sg = mseg[mm];
+          const float4* w4 = reinterpret_cast<const float4*>(mpk) + sg.x;
+          const float4* m4 = reinterpret_cast<const float4*>(xb + sg.y);
+          float a0 = 0.f, a1 = 0.f;
+          for (int i = 0; i < sg.z; ++i) {
+            const float4 w = w4[i], v = m4[i];
+            a0 = fmaf(w.x, v.x, a0); a1 = fmaf(w.y, v.y, a1);
+            a0 = fmaf(w.z, v.z, a0); a1 = fmaf(w.w, v.w, a1);
+          }
+          acc = a0 + a1;
+        } else {
+          const int lo = __ldg(p.mel_lo + mm), hi = __ldg(p.mel_hi + mm);
+          const float* wrow = p.mel_fb + (size_t)mm * F;
+          for (int k = lo; k < hi; ++k) acc = fmaf(__ldg(wrow + k), xb[k], acc);
+        }
         if (p.post == B2A_POST_LOG10) {
           float c = fmaxf(acc, p.post_eps);
           c = (p.post_power == 2.0f) ? c * c : powf(c, p.post_power);
@@ -636,6 +747,12 @@ static int launch_warp(Params& p, void* stream) {
   p.off_buf = o; o = align16(o + PL::G * PL::XB * 4);
   p.off_mag = o;
   p.off_mel = o; o = align16(o + (p.mel_out ? p.n_mels * (PL::FR + 1) * 4 : 0));
+  const int base = o;
+  if (p.mel_out && p.mel_packed_len > 0) {
+    p.off_mpk = o; o = align16(o + p.mel_packed_len * 4);
+    p.off_mseg = o; o = align16(o + p.n_mels * 16);
+    if (o > 227 * 1024) { o = base; p.mel_packed_len = 0; }  // does not fit: read the weights from global
+  }
   p.smem_bytes = o;
   B2A_REQUIRE(o <= 227 * 1024, B2A_E_UNSUPPORTED,
               "spectral: n_fft=%d hop=%d n_mels=%d needs %d bytes of shared memory (> 227 KB)", p.n_fft, p.hop,
@@ -660,8 +777,8 @@ extern "C" int64_t b2a_stft_num_frames(int64_t T, int n_fft, int hop, int pad, i
 extern "C" int b2a_spectral_f32(const float* x, int64_t rows, int64_t T, int n_fft, int hop, const float* window,
                                 int pad, int right_pad, int pad_mode, int drop_edge, const float* gain,
                                 int rows_per_gain, float* y_out, const float* mel_fb, const int32_t* mel_lo,
-                                const int32_t* mel_hi, int n_mels, int post, float post_eps, float post_power,
-                                float* mel_out, float* stft_out, void* stream) {
+                                const int32_t* mel_hi, int n_mels, int mel_packed_len, int post, float post_eps,
+                                float post_power, float* mel_out, float* stft_out, void* stream) {
   using namespace b2a::spectral;
   B2A_REQUIRE(x && window, B2A_E_INVALID, "spectral: null x/window");
   B2A_REQUIRE(mel_out || stft_out, B2A_E_INVALID, "spectral: neither mel_out nor stft_out requested");
@@ -692,6 +809,7 @@ extern "C" int b2a_spectral_f32(const float* x, int64_t rows, int64_t T, int n_f
   p.stft_out = reinterpret_cast<float2*>(stft_out);
   p.rows = (int)rows; p.T = (int)T; p.n_fft = n_fft; p.hop = hop; p.pad = pad; p.right_pad = right_pad;
   p.pad_mode = pad_mode; p.drop_edge = drop_edge; p.n_frames = (int)nfr; p.n_mels = n_mels;
+  p.mel_packed_len = (mel_out && mel_packed_len > 0) ? mel_packed_len : 0;
   p.rows_per_gain = gain ? rows_per_gain : 1; p.post = post; p.post_eps = post_eps; p.post_power = post_power;
   switch (n_fft) {
     case 32: return launch<4>(p, stream);

@@ -27,6 +27,7 @@ class Engine:
         self.lib = lib
         self.require_cuda = require_cuda
         self.launches = 0  # kernels of libb2a launched through this engine (bench.py reports it)
+        self._packed_cache = {}
 
     # ------------------------------------------------------------------ helpers
     def _prep(self, t: torch.Tensor, name: str, dtype=torch.float32) -> torch.Tensor:
@@ -103,6 +104,14 @@ class Engine:
         return out
 
     # ------------------------------------------------------------------ STFT / mel
+    def _packed_len(self, mel_lo: torch.Tensor, mel_hi: torch.Tensor) -> int:
+        """Sum of the 4-aligned band widths (host int; cached per band table)."""
+        key = (mel_lo.data_ptr(), mel_hi.data_ptr(), mel_lo.numel())
+        if key not in self._packed_cache:
+            lo, hi = mel_lo.cpu().numpy().astype("int64"), mel_hi.cpu().numpy().astype("int64")
+            self._packed_cache[key] = int((((hi + 3) & ~3) - (lo & ~3)).clip(min=0).sum())
+        return self._packed_cache[key]
+
     def num_frames(self, T: int, n_fft: int, hop: int, pad: int = 0, right_pad: int = 0, drop_edge: int = 0) -> int:
         return int(self.lib.b2a_stft_num_frames(T, n_fft, hop, pad, right_pad, drop_edge))
 
@@ -132,6 +141,7 @@ class Engine:
         stft = torch.empty(B, C, F, N, dtype=torch.complex64, device=dev) if want_stft else None
         mel = None
         n_mels = 0
+        packed_len = 0
         if mel_fb is not None:
             mel_fb = self._prep(mel_fb, "mel_fb")
             n_mels = mel_fb.shape[0]
@@ -139,6 +149,7 @@ class Engine:
             mel_lo = self._prep(mel_lo, "mel_lo", torch.int32)
             mel_hi = self._prep(mel_hi, "mel_hi", torch.int32)
             mel = torch.empty(B, C, n_mels, N, dtype=torch.float32, device=dev)
+            packed_len = self._packed_len(mel_lo, mel_hi)
         scaled = None
         rows_per_gain = 1
         if gain is not None:
@@ -150,7 +161,8 @@ class Engine:
         rc = self.lib.b2a_spectral_f32(
             _dptr(x), rows, T, n_fft, hop, _dptr(window), pad, right_pad, _lib.PAD_MODES[pad_mode], drop_edge,
             _dptr(gain), rows_per_gain, _dptr(scaled),
-            _dptr(mel_fb), _dptr(mel_lo), _dptr(mel_hi), n_mels, post, float(post_eps), float(post_power),
+            _dptr(mel_fb), _dptr(mel_lo), _dptr(mel_hi), n_mels, packed_len, post, float(post_eps),
+            float(post_power),
             _dptr(mel), _dptr(torch.view_as_real(stft)) if stft is not None else None, self._stream(x))
         self.lib.check(rc)
         self.launches += 1

@@ -63,6 +63,8 @@ const char* b2a_last_error(void);
  *   mel_lo/mel_hi  [n_mels] int32: mel_fb[m, k] == 0 outside mel_lo[m] <= k < mel_hi[m]
  *            (the caller derives them from the actual non-zeros, so the banded sum equals the
  *            dense matmul exactly for ANY matrix).
+ *   mel_packed_len  sum over m of (ceil4(mel_hi[m]) - floor4(mel_lo[m])): when > 0 the kernel packs
+ *            the bands into shared memory once per CTA (128-bit loads); 0 reads them from global.
  *   mel_out  nullable [rows, n_mels, n_frames]    stft_out  nullable [rows, F, n_frames] (re,im)
  *   n_frames = 1 + (T + 2*pad + right_pad)/hop - 2*drop_edge,  F = n_fft/2 + 1
  */
@@ -71,7 +73,7 @@ int b2a_spectral_f32(const float* x, int64_t rows, int64_t T, int n_fft, int hop
                      int pad, int right_pad, int pad_mode, int drop_edge,
                      const float* gain, int rows_per_gain, float* y_out,
                      const float* mel_fb, const int32_t* mel_lo, const int32_t* mel_hi, int n_mels,
-                     int post, float post_eps, float post_power,
+                     int mel_packed_len, int post, float post_eps, float post_power,
                      float* mel_out, float* stft_out, void* stream);
 
 /* ---- integrated loudness (ITU-R BS.1770 / LUFS) ----------------------------------------

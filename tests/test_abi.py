@@ -48,15 +48,15 @@ def test_version_and_pure_host_queries(lib):
 
 def test_bad_arguments_return_codes_not_crashes(lib):
     # null pointers / unsupported sizes are rejected before any CUDA call is made
-    rc = lib.b2a_spectral_f32(None, 1, 100, 512, 128, None, 0, 0, 0, 0, None, 1, None, None, None, None, 0, 0, 0.0,
+    rc = lib.b2a_spectral_f32(None, 1, 100, 512, 128, None, 0, 0, 0, 0, None, 1, None, None, None, None, 0, 0, 0, 0.0,
                               1.0, None, None, None)
     assert rc == -1 and b"null" in lib.b2a_last_error()
     buf = (ctypes.c_float * 1024)()
     p = ctypes.cast(buf, ctypes.c_void_p)
-    rc = lib.b2a_spectral_f32(p, 1, 1024, 500, 128, p, 0, 0, 0, 0, None, 1, None, None, None, None, 0, 0, 0.0, 1.0,
+    rc = lib.b2a_spectral_f32(p, 1, 1024, 500, 128, p, 0, 0, 0, 0, None, 1, None, None, None, None, 0, 0, 0, 0.0, 1.0,
                               None, p, None)
     assert rc == -2 and b"power of two" in lib.b2a_last_error()
-    rc = lib.b2a_spectral_f32(p, 1, 100, 512, 128, p, 0, 0, 0, 0, None, 1, None, None, None, None, 0, 0, 0.0, 1.0,
+    rc = lib.b2a_spectral_f32(p, 1, 100, 512, 128, p, 0, 0, 0, 0, None, 1, None, None, None, None, 0, 0, 0, 0.0, 1.0,
                               None, p, None)
     assert rc == -1 and b"n_fft/2" in lib.b2a_last_error()
     with pytest.raises(_lib.B2AError):

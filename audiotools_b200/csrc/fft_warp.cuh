@@ -1,0 +1,165 @@
+// fft_warp.cuh -- register/warp-level FFT building blocks shared by spectral.cu and fftconv.cu.
+//
+//   DFT<R,S>           radix-R (2..32) DFT of register-resident complex values, natural order out
+//   WPlan<LOG2N>       geometry of the warp-per-frame FFT: N = 2^LOG2N complex points, LPF = N/32 lanes
+//                      per frame, 32 points per lane, passes = radix 32 then radix LPF
+//   warp_fft           the forward N-point transform of a frame held by LPF lanes of one warp
+//   warp_fft_tables    its role-constant twiddle tables (shared memory, [slot][lane])
+#pragma once
+#include "b2a_common.h"
+
+namespace b2a {
+namespace spectral {
+
+// ---------------------------------------------------------------------------------------------
+// small DFTs in registers
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
+__device__ __forceinline__ float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
+__device__ __forceinline__ float2 cmul(float2 a, float2 b) {
+  return make_float2(fmaf(a.x, b.x, -a.y * b.y), fmaf(a.x, b.y, a.y * b.x));
+}
+
+// cos(pi*j/16), j = 0..16
+__device__ __forceinline__ constexpr float cos_pi16(int j) {
+  return j == 0 ? 1.0f
+       : j == 1 ? 0.98078528040323043f
+       : j == 2 ? 0.92387953251128674f
+       : j == 3 ? 0.83146961230254524f
+       : j == 4 ? 0.70710678118654752f
+       : j == 5 ? 0.55557023301960222f
+       : j == 6 ? 0.38268343236508977f
+       : j == 7 ? 0.19509032201612827f
+       : j == 8 ? 0.0f
+                : -cos_pi16(16 - j);
+}
+
+// o * W_R^k, W = exp(-2 pi i / R), 0 <= k < R/2, R in {2,4,8,16,32}
+template <int R, int K>
+__device__ __forceinline__ float2 mul_wr(float2 o) {
+  constexpr int j = 32 * K / R;  // angle = pi*j/16, 0 <= j < 16
+  if constexpr (j == 0) {
+    return o;
+  } else if constexpr (j == 8) {  // -i
+    return make_float2(o.y, -o.x);
+  } else if constexpr (j == 4) {  // (1 - i)/sqrt2
+    constexpr float h = 0.70710678118654752f;
+    return make_float2(h * (o.x + o.y), h * (o.y - o.x));
+  } else if constexpr (j == 12) {  // (-1 - i)/sqrt2
+    constexpr float h = 0.70710678118654752f;
+    return make_float2(h * (o.y - o.x), -h * (o.x + o.y));
+  } else {
+    constexpr float c = cos_pi16(j);
+    constexpr float sn = cos_pi16(j <= 8 ? 8 - j : j - 8);  // sin(pi j/16)
+    return make_float2(fmaf(o.x, c, o.y * sn), fmaf(o.y, c, -o.x * sn));  // o * (c - i sn)
+  }
+}
+
+template <int R, int S>
+struct DFT {
+  template <int K>
+  static __device__ __forceinline__ void comb(const float2 (&e)[R / 2], const float2 (&o)[R / 2], float2* out) {
+    float2 t = mul_wr<R, K>(o[K]);
+    out[K] = cadd(e[K], t);
+    out[K + R / 2] = csub(e[K], t);
+    if constexpr (K + 1 < R / 2) comb<K + 1>(e, o, out);
+  }
+  // in: R values at in[0], in[S], ...; out: R values, natural frequency order
+  static __device__ __forceinline__ void run(const float2* in, float2* out) {
+    float2 e[R / 2], o[R / 2];
+    DFT<R / 2, 2 * S>::run(in, e);
+    DFT<R / 2, 2 * S>::run(in + S, o);
+    comb<0>(e, o, out);
+  }
+};
+template <int S>
+struct DFT<1, S> {
+  static __device__ __forceinline__ void run(const float2* in, float2* out) { out[0] = in[0]; }
+};
+
+template <int LOG2N>
+struct WPlan {
+  static constexpr int N = 1 << LOG2N;
+  static constexpr int LPF = N / 32;   // lanes per frame
+  static constexpr int FPW = 32 / LPF; // frames per warp in flight
+  static constexpr int R1 = LPF;       // radix of pass 1 (1 => single pass)
+  static constexpr int B1 = 32 / R1;   // pass-1 butterflies per lane
+  static constexpr int NWARP = 8;
+  static constexpr int G = NWARP * FPW;            // frames in flight per CTA
+  static constexpr int FR = (G >= 16) ? G : 16;    // frames per CTA
+  static constexpr int NTW = (R1 >= 2) ? B1 * (R1 - 1) : 0;
+  static constexpr int XB = ((N + N / 32 + 4 + 3) / 4) * 4;  // floats per frame: padded exchange plane / |X| + 3 zeros, 16 B multiple
+};
+
+__device__ __forceinline__ float fast_sqrt(float v) {
+#ifdef B2A_SIM
+  return sqrtf(v);
+#else
+  float r;
+  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(v));  // <= 2 ulp; |X| feeds a 1e-4 tolerance
+  return r;
+#endif
+}
+
+// Forward N-point FFT of the 32 register-resident points of a lane (element e = l + LPF m, natural
+// order in and out): radix 32, warp-private transpose through `xb`, radix LPF.
+template <int LOG2N>
+__device__ __forceinline__ void warp_fft(float2 (&z)[32], float* xb, const float2* tw, int l) {
+  using PL = WPlan<LOG2N>;
+  constexpr int LPF = PL::LPF, R1 = PL::R1, B1 = PL::B1;
+  {
+    float2 o[32];
+    DFT<32, 1>::run(z, o);
+#pragma unroll
+    for (int t = 0; t < 32; ++t) z[t] = o[t];
+  }
+  if constexpr (R1 >= 2) {
+    // exchange (transpose within the frame's lanes): write i = l*32 + t, read e = l + LPF m
+#pragma unroll
+    for (int t = 0; t < 32; ++t) xb[l * 33 + t] = z[t].x;
+    __syncwarp();
+#pragma unroll
+    for (int m = 0; m < 32; ++m) { const int e = l + LPF * m; z[m].x = xb[e + (e >> 5)]; }
+    __syncwarp();
+#pragma unroll
+    for (int t = 0; t < 32; ++t) xb[l * 33 + t] = z[t].y;
+    __syncwarp();
+#pragma unroll
+    for (int m = 0; m < 32; ++m) { const int e = l + LPF * m; z[m].y = xb[e + (e >> 5)]; }
+    __syncwarp();
+#pragma unroll
+    for (int b = 0; b < B1; ++b) {  // pass 1: radix LPF, NS = 32
+#pragma unroll
+      for (int t = 1; t < R1; ++t)
+        z[b + B1 * t] = cmul(z[b + B1 * t], tw[(b * (R1 - 1) + (t - 1)) * LPF + l]);
+      float2 o[R1];
+      DFT<R1, B1>::run(&z[b], o);
+#pragma unroll
+      for (int t = 0; t < R1; ++t) z[b + B1 * t] = o[t];
+    }
+  }
+}
+
+// role-constant tables of the warp FFT: pass-1 twiddles [NTW][LPF] and untangle twiddles [16][LPF]
+template <int LOG2N>
+__device__ __forceinline__ void warp_fft_tables(float2* tw, float2* ut) {
+  using PL = WPlan<LOG2N>;
+  constexpr int N = PL::N, LPF = PL::LPF, R1 = PL::R1;
+  const int tid = threadIdx.x, nt = blockDim.x;
+  for (int i = tid; i < PL::NTW * LPF; i += nt) {
+    const int slot = i / LPF, ll = i - slot * LPF;
+    const int b = slot / (R1 > 1 ? R1 - 1 : 1), t = slot - b * (R1 > 1 ? R1 - 1 : 1) + 1;
+    float sn, cs;  // W_N^{(ll + LPF b) t}
+    sincospif(-2.0f * (float)((ll + LPF * b) * t) / (float)N, &sn, &cs);
+    tw[i] = make_float2(cs, sn);
+  }
+  for (int i = tid; i < 16 * LPF; i += nt) {
+    const int m = i / LPF, ll = i - m * LPF;
+    float sn, cs;  // exp(-i pi (ll + LPF m) / N)
+    sincospif(-(float)(ll + LPF * m) / (float)N, &sn, &cs);
+    ut[i] = make_float2(cs, sn);
+  }
+}
+
+}  // namespace spectral
+}  // namespace b2a

@@ -1,0 +1,308 @@
+// fftconv.cu -- per-row FIR / circular convolution of [rows, T] waveforms by uniformly partitioned
+// overlap-save FFT convolution on sm_100a.
+//
+// One engine serves every "long filter" of the hot path:
+//   * DSPMixin.low_pass / high_pass   (ref:audiotools/core/dsp.py:153-215 -> julius.LowPassFilter:
+//                                      windowed-sinc, 103 .. 44983 taps, replicate padding)
+//   * EffectMixin.equalizer / mel_filterbank (ref:audiotools/core/effects.py:386-433 -> julius.SplitBands,
+//                                      641 taps @44.1k/6 bands; the band split + weighted sum collapses
+//                                      into ONE FIR per item)
+//   * EffectMixin.convolve            (ref:audiotools/core/effects.py:66-123: CIRCULAR convolution with
+//                                      period T, IR rolled to its peak, scaled by 1/max|IR|)
+// The reference does these with torch.fft.rfft of the whole (non power of two) signal or with julius'
+// block FFT; here:   out[row][n] = post * sum_k g[filt][k] * xv[row][n - k + c[filt]],   n in [0, T)
+// where xv extends x by zero / replicate / circular (period T) indexing.
+//
+//   1. H[filt][f][p]   = rFFT_2048([g_p, 0])            p-th 1024-tap partition   (spectral.cu kernel)
+//   2. X[row][f][b]    = rFFT_2048(xv[(b-1)*1024 .. (b+1)*1024))                   (spectral.cu kernel)
+//   3. Y[row][f][b]    = sum_p H[f][p] * X[f][b-p]       a complex FIR along the block index, per bin
+//   4. out[b*1024 ..]  = irFFT_2048(Y[.][b])[1024:]      warp-per-block inverse FFT + epilogue
+// Rows are processed in chunks so that X and Y stay L2-friendly (<= 256 MB of workspace).
+#include "b2a_common.h"
+#include "fft_warp.cuh"
+#include "spectral_internal.h"
+
+namespace b2a {
+namespace fftconv {
+
+using namespace b2a::spectral;
+
+constexpr int LP = 1024;    // partition length == new samples per block
+constexpr int NFFT = 2048;  // block size
+constexpr int NF = 1025;    // bins
+constexpr int LOG2N = 10;   // 1024 complex points per block FFT
+
+__global__ void fill_windows_kernel(float* ones, float* half) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < NFFT) {
+    ones[i] = 1.0f;
+    half[i] = i < LP ? 1.0f : 0.0f;
+  }
+}
+
+__global__ void row_origin_kernel(const int32_t* __restrict__ offset, int offset0, int rows_per_filt, int rows,
+                                  int row0, int32_t* __restrict__ row_origin) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r < rows) row_origin[r] = offset0 + (offset ? offset[(row0 + r) / rows_per_filt] : 0);
+}
+
+// Y[row][f][b] = sum_p H[filt][f][p] * X[row][f][b + P-1 - p]
+__global__ void __launch_bounds__(128)
+freq_fir_kernel(const float2* __restrict__ X, const float2* __restrict__ H, float2* __restrict__ Y, int NB,
+                int NBX, int P, int rows_per_filt, int row0) {
+  const int f = blockIdx.y, row = blockIdx.z;
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= NB) return;
+  const float2* xr = X + ((size_t)row * NF + f) * NBX + b + (P - 1);
+  const float2* hr = H + ((size_t)((row0 + row) / rows_per_filt) * NF + f) * P;
+  float ar = 0.f, ai = 0.f;
+  for (int p = 0; p < P; ++p) {
+    const float2 h = __ldg(hr + p);
+    const float2 x = __ldg(xr - p);
+    ar = fmaf(h.x, x.x, ar); ar = fmaf(-h.y, x.y, ar);
+    ai = fmaf(h.x, x.y, ai); ai = fmaf(h.y, x.x, ai);
+  }
+  Y[((size_t)row * NF + f) * NB + b] = make_float2(ar, ai);
+}
+
+struct InvParams {
+  const float2* Y;       // [rows, NF, NB]
+  const float* x;        // [rows_total, T] (for subtract_from_input)
+  const float* post;     // [n_filt] nullable
+  float* out;            // [rows_total, T]
+  int rows, row0, T, NB, rows_per_filt, subtract;
+  int off_tw, off_ut, off_buf;
+};
+
+// inverse real FFT of block spectra, one warp per block, keeping the last LP samples (overlap-save)
+__global__ void __launch_bounds__(256, 2) ifft_blocks_kernel(InvParams p) {
+  using PL = WPlan<LOG2N>;
+  constexpr int N = PL::N;
+  B2A_DYN_SMEM(smem);
+  float2* tw = reinterpret_cast<float2*>(smem + p.off_tw);
+  float2* ut = reinterpret_cast<float2*>(smem + p.off_ut);
+  float* xbs = reinterpret_cast<float*>(smem + p.off_buf);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  warp_fft_tables<LOG2N>(tw, ut);
+  __syncthreads();
+  float* xb = xbs + warp * PL::XB;
+  const int l = lane;
+  const int groups = (p.NB + 7) / 8;
+  const int total = p.rows * groups;
+  const float inv_n = 1.0f / (float)N;
+#pragma unroll 1
+  for (int t = blockIdx.x; t < total; t += gridDim.x) {
+    const int row = t / groups, b = (t - row * groups) * 8 + warp;
+    if (b >= p.NB) continue;  // warp-uniform
+    const float2* yr = p.Y + (size_t)row * NF * p.NB + b;
+    // Z[e] = Xe[e] + i Xo[e] from the real-FFT bins X[e], X[N-e]; the inverse transform is
+    // conj(FFT(conj(Z)))/N, so feed conj(Z).   e = l + 32 m
+    float2 z[32];
+#pragma unroll
+    for (int m = 0; m < 32; ++m) {
+      const int e = l + 32 * m;
+      // for e > N/2 use the pair (k = N-e): Z[e] = conj(Xe[k]) + i conj(Xo[k])
+      const int k = (m < 16) ? e : N - e;
+      const float2 xk = __ldg(yr + (size_t)k * p.NB);
+      const float2 xn = __ldg(yr + (size_t)(N - k) * p.NB);
+      // Xe = (X[k] + conj X[N-k])/2 ; T = (X[k] - conj X[N-k])/2 ; Xo = conj(W_k) T, W_k = exp(-i pi k/N)
+      const float2 xe = make_float2(0.5f * (xk.x + xn.x), 0.5f * (xk.y - xn.y));
+      const float2 tt = make_float2(0.5f * (xk.x - xn.x), 0.5f * (xk.y + xn.y));
+      float2 w;
+      if (k == N / 2) w = make_float2(0.f, -1.f);
+      else w = ut[(k >> 5) * 32 + (k & 31)];  // table index m' * LPF + l' with k = l' + 32 m'
+      const float2 xo = make_float2(fmaf(w.x, tt.x, w.y * tt.y), fmaf(w.x, tt.y, -w.y * tt.x));  // conj(w) * tt
+      float2 zz = make_float2(xe.x - xo.y, xe.y + xo.x);  // Xe + i Xo
+      if (m >= 16 && e != N / 2) zz = make_float2(xe.x + xo.y, -xe.y + xo.x);  // conj(Xe) + i conj(Xo)
+      z[m] = make_float2(zz.x, -zz.y);  // conj for the inverse-by-forward trick
+    }
+    warp_fft<LOG2N>(z, xb, tw, l);
+    // z[m] = conj(N * zt[n]), n = l + 32 m; samples x[2n] = Re zt, x[2n+1] = Im zt; keep n >= N/2
+    const int grow = p.row0 + row;
+    const float post = p.post ? __ldg(p.post + grow / p.rows_per_filt) : 1.0f;
+    float* orow = p.out + (size_t)grow * p.T;
+    const float* xrow = p.x + (size_t)grow * p.T;
+#pragma unroll
+    for (int m = 16; m < 32; ++m) {
+      const int n = l + 32 * m;
+      const int s0 = b * LP + 2 * n - LP;
+      float v0 = z[m].x * inv_n * post, v1 = -z[m].y * inv_n * post;
+      if (s0 < p.T) {
+        if (p.subtract) v0 = __ldg(xrow + s0) - v0;
+        orow[s0] = v0;
+      }
+      if (s0 + 1 < p.T) {
+        if (p.subtract) v1 = __ldg(xrow + s0 + 1) - v1;
+        orow[s0 + 1] = v1;
+      }
+    }
+    __syncwarp();
+  }
+}
+
+// per item: first index of max|h| over the first Leff samples, and 1 / max(max|h|, 1e-5)
+__global__ void __launch_bounds__(256)
+ir_peak_kernel(const float* __restrict__ ir, int L, int Leff, int32_t* __restrict__ idx_out,
+               float* __restrict__ scale_out, int roll) {
+  __shared__ float sv[256];
+  __shared__ int si[256];
+  const float* h = ir + (size_t)blockIdx.x * L;
+  float best = -1.f;
+  int bi = 0;
+  for (int i = threadIdx.x; i < Leff; i += 256) {
+    const float a = fabsf(h[i]);
+    if (a > best) { best = a; bi = i; }  // strictly greater: keeps the first maximum of this thread's stride
+  }
+  sv[threadIdx.x] = best;
+  si[threadIdx.x] = bi;
+  __syncthreads();
+  for (int s = 128; s > 0; s >>= 1) {
+    if ((int)threadIdx.x < s) {
+      const float o = sv[threadIdx.x + s];
+      const int oi = si[threadIdx.x + s];
+      if (o > sv[threadIdx.x] || (o == sv[threadIdx.x] && oi < si[threadIdx.x])) {
+        sv[threadIdx.x] = o;
+        si[threadIdx.x] = oi;
+      }
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    idx_out[blockIdx.x] = roll ? si[0] : 0;
+    scale_out[blockIdx.x] = 1.0f / fmaxf(sv[0], 1e-5f);
+  }
+}
+
+struct Layout {
+  size_t ones, half, H, X, Y, rorg, peak_idx, peak_scale, total;
+  int P, NB, NBX, chunk;
+};
+static inline size_t al(size_t v) { return (v + 255) & ~(size_t)255; }
+static Layout layout(int64_t rows, int64_t T, int64_t n_filt, int64_t L) {
+  Layout w;
+  w.P = (int)((L + LP - 1) / LP);
+  w.NB = (int)((T + LP - 1) / LP);
+  w.NBX = w.NB + w.P - 1;
+  const size_t per_row = (size_t)NF * (w.NBX + w.NB) * 8;
+  int64_t chunk = (int64_t)(((size_t)256 << 20) / per_row);
+  if (chunk < 1) chunk = 1;
+  if (chunk > rows) chunk = rows;
+  if (chunk > 65535) chunk = 65535;
+  w.chunk = (int)chunk;
+  size_t o = 0;
+  w.ones = o; o = al(o + NFFT * 4);
+  w.half = o; o = al(o + NFFT * 4);
+  w.H = o; o = al(o + (size_t)n_filt * NF * w.P * 8);
+  w.X = o; o = al(o + (size_t)w.chunk * NF * w.NBX * 8);
+  w.Y = o; o = al(o + (size_t)w.chunk * NF * w.NB * 8);
+  w.rorg = o; o = al(o + (size_t)w.chunk * 4);
+  w.peak_idx = o; o = al(o + (size_t)n_filt * 4);
+  w.peak_scale = o; o = al(o + (size_t)n_filt * 4);
+  w.total = o;
+  return w;
+}
+
+static int num_sms() {
+  int dev = 0, n = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0)
+    n = B2A_NUM_SMS;
+  return n;
+}
+
+static int run(const float* x, int64_t rows, int64_t T, const float* g, int64_t n_filt, int64_t L, int rows_per_filt,
+               const int32_t* offset, int offset0, int pad_mode, const float* post_scale, int subtract, float* out,
+               char* ws, const Layout& w, void* stream) {
+  float* ones = (float*)(ws + w.ones);
+  float* half = (float*)(ws + w.half);
+  float2* H = (float2*)(ws + w.H);
+  float2* X = (float2*)(ws + w.X);
+  float2* Y = (float2*)(ws + w.Y);
+  int32_t* rorg = (int32_t*)(ws + w.rorg);
+  B2A_LAUNCH(fill_windows_kernel, dim3(NFFT / 256), dim3(256), 0, stream, ones, half);
+  // 1. filter partitions: frame p = g[p*LP, p*LP + 2048) x [1..1 0..0], zero beyond L
+  int rc = frames_fft(g, (int)n_filt, (int)L, NFFT, LP, half, 0, nullptr, B2A_PAD_CONSTANT, w.P, H, stream);
+  if (rc != B2A_OK) return rc;
+  using PL = WPlan<LOG2N>;
+  InvParams ip;
+  memset(&ip, 0, sizeof(ip));
+  int o = 0;
+  ip.off_tw = o; o += (PL::NTW * PL::LPF * 8 + 31) & ~15;
+  ip.off_ut = o; o += (16 * PL::LPF * 8 + 15) & ~15;
+  ip.off_buf = o; o += 8 * PL::XB * 4;
+  B2A_CUDA_OK(cudaFuncSetAttribute(ifft_blocks_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, o));
+  for (int64_t r0 = 0; r0 < rows; r0 += w.chunk) {
+    const int nr = (int)((rows - r0 < w.chunk) ? rows - r0 : w.chunk);
+    B2A_LAUNCH(row_origin_kernel, dim3((nr + 255) / 256), dim3(256), 0, stream, offset, offset0, rows_per_filt, nr,
+               (int)r0, rorg);
+    // 2. block b' covers xv[(b' - P)*LP + c, +2048)
+    rc = frames_fft(x + (size_t)r0 * T, nr, (int)T, NFFT, LP, ones, -w.P * LP, rorg, pad_mode, w.NBX, X, stream);
+    if (rc != B2A_OK) return rc;
+    // 3. complex FIR along the block index
+    B2A_LAUNCH(freq_fir_kernel, dim3((w.NB + 127) / 128, NF, nr), dim3(128), 0, stream, (const float2*)X,
+               (const float2*)H, Y, w.NB, w.NBX, w.P, rows_per_filt, (int)r0);
+    // 4. inverse FFT + overlap-save + epilogue
+    ip.Y = Y; ip.x = x; ip.post = post_scale; ip.out = out;
+    ip.rows = nr; ip.row0 = (int)r0; ip.T = (int)T; ip.NB = w.NB; ip.rows_per_filt = rows_per_filt;
+    ip.subtract = subtract;
+    const int64_t total = (int64_t)nr * ((w.NB + 7) / 8);
+    const int64_t cap = (int64_t)num_sms() * 2;
+    B2A_LAUNCH(ifft_blocks_kernel, dim3((unsigned)(total < cap ? total : cap)), dim3(256), (size_t)o, stream, ip);
+  }
+  B2A_CUDA_OK(cudaGetLastError());
+  return B2A_OK;
+}
+
+}  // namespace fftconv
+}  // namespace b2a
+
+using namespace b2a::fftconv;
+
+extern "C" size_t b2a_fftconv_workspace_bytes(int64_t rows, int64_t T, int64_t n_filt, int64_t L) {
+  if (rows < 1 || T < 1 || n_filt < 1 || L < 1) return 0;
+  return layout(rows, T, n_filt, L).total;
+}
+
+extern "C" int b2a_fftconv_f32(const float* x, int64_t rows, int64_t T, const float* g, int64_t n_filt, int64_t L,
+                               int rows_per_filt, const int32_t* offset, int offset0, int pad_mode,
+                               const float* post_scale, int subtract_from_input, float* out, void* ws,
+                               size_t ws_bytes, void* stream) {
+  B2A_REQUIRE(x && g && out && ws, B2A_E_INVALID, "fftconv: null pointer");
+  B2A_REQUIRE(rows >= 1 && T >= 1 && n_filt >= 1 && L >= 1 && rows_per_filt >= 1, B2A_E_INVALID, "fftconv: bad shape");
+  B2A_REQUIRE((rows + rows_per_filt - 1) / rows_per_filt <= n_filt, B2A_E_INVALID,
+              "fftconv: %lld rows / %d per filter need more than %lld filters", (long long)rows, rows_per_filt,
+              (long long)n_filt);
+  B2A_REQUIRE(T < ((int64_t)1 << 30) && L < ((int64_t)1 << 30), B2A_E_UNSUPPORTED, "fftconv: too long");
+  B2A_REQUIRE(pad_mode == B2A_PAD_CONSTANT || pad_mode == B2A_PAD_REPLICATE || pad_mode == 3, B2A_E_INVALID,
+              "fftconv: pad_mode %d (1 zero, 2 replicate, 3 circular)", pad_mode);
+  B2A_REQUIRE(out != x, B2A_E_INVALID, "fftconv: in-place is not supported");
+  const Layout w = layout(rows, T, n_filt, L);
+  B2A_REQUIRE(ws_bytes >= w.total, B2A_E_INVALID, "fftconv: workspace too small (%zu < %zu)", ws_bytes, w.total);
+  return run(x, rows, T, g, n_filt, L, rows_per_filt, offset, offset0, pad_mode, post_scale, subtract_from_input, out,
+             (char*)ws, w, stream);
+}
+
+/* EffectMixin.convolve (ref:audiotools/core/effects.py:66-123): out = (x (*) roll(ir, -argmax|ir|)) / max(max|ir|, 1e-5),
+ * circular with period T.  ir: [n_ir, L] (mono IRs, one per rows_per_ir rows); only its first min(L, T) samples count. */
+extern "C" size_t b2a_circconv_workspace_bytes(int64_t rows, int64_t T, int64_t n_ir, int64_t L) {
+  if (rows < 1 || T < 1 || n_ir < 1 || L < 1) return 0;
+  return layout(rows, T, n_ir, L < T ? L : T).total;
+}
+
+extern "C" int b2a_circconv_f32(const float* x, int64_t rows, int64_t T, const float* ir, int64_t n_ir, int64_t L,
+                                int rows_per_ir, int roll_to_peak, float* out, void* ws, size_t ws_bytes,
+                                void* stream) {
+  B2A_REQUIRE(x && ir && out && ws, B2A_E_INVALID, "circconv: null pointer");
+  B2A_REQUIRE(rows >= 1 && T >= 1 && n_ir >= 1 && L >= 1 && rows_per_ir >= 1, B2A_E_INVALID, "circconv: bad shape");
+  const int64_t Leff = L < T ? L : T;  // the reference truncates the IR to the signal length
+  const Layout w = layout(rows, T, n_ir, Leff);
+  B2A_REQUIRE(ws_bytes >= w.total, B2A_E_INVALID, "circconv: workspace too small (%zu < %zu)", ws_bytes, w.total);
+  char* base = (char*)ws;
+  int32_t* pidx = (int32_t*)(base + w.peak_idx);
+  float* pscale = (float*)(base + w.peak_scale);
+  B2A_LAUNCH(ir_peak_kernel, dim3((unsigned)n_ir), dim3(256), 0, stream, ir, (int)L, (int)Leff, pidx, pscale,
+             roll_to_peak);
+  // y[n] = sum_j h[j] x[(n - (j - idx)) mod T]  ==  causal conv with offset c = idx, circular indexing
+  B2A_REQUIRE(L == Leff, B2A_E_INVALID, "circconv: pass the IR already truncated to the signal length (L=%lld > T=%lld)",
+              (long long)L, (long long)T);
+  return run(x, rows, T, ir, n_ir, Leff, rows_per_ir, pidx, 0, 3, pscale, 0, out, base, w, stream);
+}

@@ -25,78 +25,14 @@
 //      than a dense tensor-core GEMM and is exact to FP32 rounding) -> post-op -> tile in shared
 //      memory -> coalesced store along the frame axis.
 #include "b2a_common.h"
+#include "fft_warp.cuh"
+#include "spectral_internal.h"
 
 namespace b2a {
 namespace spectral {
 
 constexpr int THREADS = 256;
 constexpr int E = 16;  // complex points per thread
-
-// ---------------------------------------------------------------------------------------------
-// small DFTs in registers
-// ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
-__device__ __forceinline__ float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
-__device__ __forceinline__ float2 cmul(float2 a, float2 b) {
-  return make_float2(fmaf(a.x, b.x, -a.y * b.y), fmaf(a.x, b.y, a.y * b.x));
-}
-
-// cos(pi*j/16), j = 0..16
-__device__ __forceinline__ constexpr float cos_pi16(int j) {
-  return j == 0 ? 1.0f
-       : j == 1 ? 0.98078528040323043f
-       : j == 2 ? 0.92387953251128674f
-       : j == 3 ? 0.83146961230254524f
-       : j == 4 ? 0.70710678118654752f
-       : j == 5 ? 0.55557023301960222f
-       : j == 6 ? 0.38268343236508977f
-       : j == 7 ? 0.19509032201612827f
-       : j == 8 ? 0.0f
-                : -cos_pi16(16 - j);
-}
-
-// o * W_R^k, W = exp(-2 pi i / R), 0 <= k < R/2, R in {2,4,8,16,32}
-template <int R, int K>
-__device__ __forceinline__ float2 mul_wr(float2 o) {
-  constexpr int j = 32 * K / R;  // angle = pi*j/16, 0 <= j < 16
-  if constexpr (j == 0) {
-    return o;
-  } else if constexpr (j == 8) {  // -i
-    return make_float2(o.y, -o.x);
-  } else if constexpr (j == 4) {  // (1 - i)/sqrt2
-    constexpr float h = 0.70710678118654752f;
-    return make_float2(h * (o.x + o.y), h * (o.y - o.x));
-  } else if constexpr (j == 12) {  // (-1 - i)/sqrt2
-    constexpr float h = 0.70710678118654752f;
-    return make_float2(h * (o.y - o.x), -h * (o.x + o.y));
-  } else {
-    constexpr float c = cos_pi16(j);
-    constexpr float sn = cos_pi16(j <= 8 ? 8 - j : j - 8);  // sin(pi j/16)
-    return make_float2(fmaf(o.x, c, o.y * sn), fmaf(o.y, c, -o.x * sn));  // o * (c - i sn)
-  }
-}
-
-template <int R, int S>
-struct DFT {
-  template <int K>
-  static __device__ __forceinline__ void comb(const float2 (&e)[R / 2], const float2 (&o)[R / 2], float2* out) {
-    float2 t = mul_wr<R, K>(o[K]);
-    out[K] = cadd(e[K], t);
-    out[K + R / 2] = csub(e[K], t);
-    if constexpr (K + 1 < R / 2) comb<K + 1>(e, o, out);
-  }
-  // in: R values at in[0], in[S], ...; out: R values, natural frequency order
-  static __device__ __forceinline__ void run(const float2* in, float2* out) {
-    float2 e[R / 2], o[R / 2];
-    DFT<R / 2, 2 * S>::run(in, e);
-    DFT<R / 2, 2 * S>::run(in + S, o);
-    comb<0>(e, o, out);
-  }
-};
-template <int S>
-struct DFT<1, S> {
-  static __device__ __forceinline__ void run(const float2* in, float2* out) { out[0] = in[0]; }
-};
 
 // ---------------------------------------------------------------------------------------------
 // compile-time FFT plan for N = 2^LOG2N complex points, 16 points per thread
@@ -139,6 +75,10 @@ struct Params {
   int n_frames, n_tiles, n_mels, rows_per_gain, post;
   int mel_packed_len;  // sum over filters of the 4-aligned band widths (0: read weights from global)
   int off_mpk, off_mseg;
+  // framing: frame n of a row starts at x-coordinate (n + drop_edge)*hop + origin (+ row_origin[row]);
+  // center = 1: torch.stft(center=True) semantics (reflect about the F.pad-ed signal), 0: raw
+  int center, origin;
+  const int32_t* row_origin;
   float post_eps, post_power;
   int span;  // (FR-1)*hop + n_fft
   // shared memory offsets (bytes)
@@ -147,16 +87,22 @@ struct Params {
 
 // index of sample `w` (in un-padded x coordinates, may be outside [0,T)) after torch's two
 // paddings; -1 => zero.   ref:audiotools/core/audio_signal.py:1192-1202
-__device__ __forceinline__ int src_index(int w, int T, int pad, int right_pad, int pad_mode) {
-  const int Lp = T + 2 * pad + right_pad;
-  int v = w + pad;  // position in the F.pad-ed signal
-  if (v < 0) v = -v;                       // torch.stft(center=True): reflect, no edge repeat
-  else if (v >= Lp) v = 2 * (Lp - 1) - v;
-  if (v < 0 || v >= Lp) return -1;         // only reachable from frames past the end (never stored)
-  int u = v - pad;
+#define B2A_PAD_CIRCULAR 3  // internal (FFT convolution): index modulo T
+
+__device__ __forceinline__ int src_index(int w, int T, int pad, int right_pad, int pad_mode, int center = 1) {
+  int u = w;
+  if (center) {
+    const int Lp = T + 2 * pad + right_pad;
+    int v = w + pad;  // position in the F.pad-ed signal
+    if (v < 0) v = -v;                       // torch.stft(center=True): reflect, no edge repeat
+    else if (v >= Lp) v = 2 * (Lp - 1) - v;
+    if (v < 0 || v >= Lp) return -1;         // only reachable from frames past the end (never stored)
+    u = v - pad;
+  }
   if (u >= 0 && u < T) return u;
   if (pad_mode == B2A_PAD_REFLECT) u = u < 0 ? -u : 2 * (T - 1) - u;
   else if (pad_mode == B2A_PAD_REPLICATE) u = u < 0 ? 0 : T - 1;
+  else if (pad_mode == B2A_PAD_CIRCULAR) { u %= T; if (u < 0) u += T; }
   else return -1;
   return (u >= 0 && u < T) ? u : -1;
 }
@@ -247,7 +193,7 @@ __device__ __forceinline__ void stage_span_async(const Params& p, float* sp, int
     for (int i = tid; i < span; i += (int)blockDim.x) sp[i] = __ldg(xr + ws + i);
   } else {
     for (int i = tid; i < span; i += (int)blockDim.x) {
-      const int u = src_index(ws + i, T, p.pad, p.right_pad, p.pad_mode);
+      const int u = src_index(ws + i, T, p.pad, p.right_pad, p.pad_mode, p.center);
       sp[i] = (u >= 0) ? __ldg(xr + u) : 0.f;
     }
   }
@@ -502,70 +448,34 @@ static int launch(Params& p, void* stream) {
 //   mel      |X| -> the (dead) exchange plane -> banded FP32 gather, post-op, tile in smem
 // =============================================================================================
 template <int LOG2N>
-struct WPlan {
-  static constexpr int N = 1 << LOG2N;
-  static constexpr int LPF = N / 32;   // lanes per frame
-  static constexpr int FPW = 32 / LPF; // frames per warp in flight
-  static constexpr int R1 = LPF;       // radix of pass 1 (1 => single pass)
-  static constexpr int B1 = 32 / R1;   // pass-1 butterflies per lane
-  static constexpr int NWARP = 8;
-  static constexpr int G = NWARP * FPW;            // frames in flight per CTA
-  static constexpr int FR = (G >= 16) ? G : 16;    // frames per CTA
-  static constexpr int NTW = (R1 >= 2) ? B1 * (R1 - 1) : 0;
-  static constexpr int XB = ((N + N / 32 + 4 + 3) / 4) * 4;  // floats per frame: padded exchange plane / |X| + 3 zeros, 16 B multiple
-};
-
-__device__ __forceinline__ float fast_sqrt(float v) {
-#ifdef B2A_SIM
-  return sqrtf(v);
-#else
-  float r;
-  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(v));  // <= 2 ulp; |X| feeds a 1e-4 tolerance
-  return r;
-#endif
-}
-
-template <int LOG2N>
 __global__ void __launch_bounds__(256, 2) spectral_warp_kernel(Params p) {
   using PL = WPlan<LOG2N>;
-  constexpr int N = PL::N, LPF = PL::LPF, FPW = PL::FPW, R1 = PL::R1, B1 = PL::B1, G = PL::G, FR = PL::FR;
+  constexpr int N = PL::N, LPF = PL::LPF, FPW = PL::FPW, G = PL::G, FR = PL::FR;
   B2A_DYN_SMEM(smem);
   float* sp = reinterpret_cast<float*>(smem);
   float* win = reinterpret_cast<float*>(smem + p.off_win);   // [n_fft]
   float2* tw = reinterpret_cast<float2*>(smem + p.off_tw);   // [NTW][LPF]
-  float2* ut = reinterpret_cast<float2*>(smem + p.off_ut);   // [16][LPF]  exp(-i pi (l + LPF m) / N)
+  float2* ut = reinterpret_cast<float2*>(smem + p.off_ut);   // [16][LPF]
   float* xbs = reinterpret_cast<float*>(smem + p.off_buf);   // [G][XB]
   float* melt = reinterpret_cast<float*>(smem + p.off_mel);  // [n_mels][FR+1]
+  float* mpk = reinterpret_cast<float*>(smem + p.off_mpk);
+  int4* mseg = reinterpret_cast<int4*>(smem + p.off_mseg);   // (offset, lo4, n4, -)
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int row = blockIdx.x / p.n_tiles;
-  const int tile = blockIdx.x - row * p.n_tiles;
-  const int n0 = tile * FR;
   const int hop = p.hop, n_fft = 2 * N, F = N + 1;
-  const float g = p.gain ? __ldg(p.gain + row / p.rows_per_gain) : 1.0f;
-  const int ws = (n0 + p.drop_edge) * hop - N - p.pad;
   const int l = lane & (LPF - 1);  // lane within the frame
   const int fw = lane / LPF;       // frame within the warp
+  const int total_tiles = p.rows * p.n_tiles;
 
-  stage_span_async(p, sp, row, ws);  // in flight while the tables below are computed
-
-  for (int i = tid; i < n_fft; i += 256) win[i] = __ldg(p.window + i) * g;  // gain folded into the window
-  for (int i = tid; i < PL::NTW * LPF; i += 256) {
-    const int slot = i / LPF, ll = i - slot * LPF;
-    const int b = slot / (R1 > 1 ? R1 - 1 : 1), t = slot - b * (R1 > 1 ? R1 - 1 : 1) + 1;
-    float sn, cs;  // W_N^{(ll + LPF b) t}
-    sincospif(-2.0f * (float)((ll + LPF * b) * t) / (float)N, &sn, &cs);
-    tw[i] = make_float2(cs, sn);
+  // ---- first tile's samples in flight while the (row-independent) tables are built ONCE per CTA
+  int t = blockIdx.x;
+  {
+    const int row = t / p.n_tiles, tile = t - row * p.n_tiles;
+    stage_span_async(p, sp, row, (tile * FR + p.drop_edge) * hop + p.origin + (p.row_origin ? __ldg(p.row_origin + row) : 0));
   }
-  for (int i = tid; i < 16 * LPF; i += 256) {
-    const int m = i / LPF, ll = i - m * LPF;
-    float sn, cs;
-    sincospif(-(float)(ll + LPF * m) / (float)N, &sn, &cs);
-    ut[i] = make_float2(cs, sn);
-  }
+  for (int i = tid; i < n_fft; i += 256) win[i] = __ldg(p.window + i);
+  warp_fft_tables<LOG2N>(tw, ut);
   // banded mel weights packed into shared memory: filter m -> 4-aligned band [lo4, lo4 + 4 n4), zero padded
-  float* mpk = reinterpret_cast<float*>(smem + p.off_mpk);
-  int4* mseg = reinterpret_cast<int4*>(smem + p.off_mseg);  // (offset, lo4, n4, -)
   const bool packed = p.mel_out && p.mel_packed_len > 0;
   if (packed) {
     if (warp == 0) {  // exclusive scan of the padded widths
@@ -598,141 +508,134 @@ __global__ void __launch_bounds__(256, 2) spectral_warp_kernel(Params p) {
       }
     }
   }
-  cp_async_wait_all();
-  __syncthreads();
-  if (p.y_out) writeback_scaled(p, sp, row, tile, n0, FR, ws, g);
 
   float* xb = xbs + (warp * FPW + fw) * PL::XB;
   const int src_lane = (lane & ~(LPF - 1)) | ((LPF - l) & (LPF - 1));  // holder of Z[N - k]
 
 #pragma unroll 1
-  for (int rd = 0; rd < FR / G; ++rd) {
-    const int f = rd * G + warp * FPW + fw;
-    const int n = n0 + f;
-    const bool live = n < p.n_frames;
-    const float* fs = sp + f * hop;
+  for (; t < total_tiles; t += gridDim.x) {
+    const int row = t / p.n_tiles, tile = t - row * p.n_tiles;
+    const int n0 = tile * FR;
+    const int ws = (n0 + p.drop_edge) * hop + p.origin + (p.row_origin ? __ldg(p.row_origin + row) : 0);
+    const float g = p.gain ? __ldg(p.gain + row / p.rows_per_gain) : 1.0f;
+    const float ga = fabsf(g);
+    if (t != (int)blockIdx.x) stage_span_async(p, sp, row, ws);
+    cp_async_wait_all();
+    __syncthreads();
+    if (p.y_out) writeback_scaled(p, sp, row, tile, n0, FR, ws, g);
 
-    // ---- pass 0: radix 32 over the windowed frame, element e = l + LPF m
-    float2 z[32];
-    {
-      float2 v[32];
+#pragma unroll 1
+    for (int rd = 0; rd < FR / G; ++rd) {
+      const int f = rd * G + warp * FPW + fw;
+      const int n = n0 + f;
+      const bool live = n < p.n_frames;
+      const float* fs = sp + f * hop;
+
+      // ---- windowed frame, element e = l + LPF m
+      float2 z[32];
       if ((hop & 1) == 0) {
 #pragma unroll
         for (int m = 0; m < 32; ++m) {
           const int e = l + LPF * m;
           const float2 s2 = *reinterpret_cast<const float2*>(fs + 2 * e);
           const float2 w2 = *reinterpret_cast<const float2*>(win + 2 * e);
-          v[m] = make_float2(s2.x * w2.x, s2.y * w2.y);
+          z[m] = make_float2(s2.x * w2.x, s2.y * w2.y);
         }
       } else {
 #pragma unroll
         for (int m = 0; m < 32; ++m) {
           const int e = l + LPF * m;
-          v[m] = make_float2(fs[2 * e] * win[2 * e], fs[2 * e + 1] * win[2 * e + 1]);
+          z[m] = make_float2(fs[2 * e] * win[2 * e], fs[2 * e + 1] * win[2 * e + 1]);
         }
       }
-      DFT<32, 1>::run(v, z);
-    }
-    if constexpr (R1 >= 2) {
-      // ---- exchange (transpose within the frame's lanes): write i = l*32 + t, read e = l + LPF m
-#pragma unroll
-      for (int t = 0; t < 32; ++t) xb[l * 33 + t] = z[t].x;
-      __syncwarp();
-#pragma unroll
-      for (int m = 0; m < 32; ++m) { const int e = l + LPF * m; z[m].x = xb[e + (e >> 5)]; }
-      __syncwarp();
-#pragma unroll
-      for (int t = 0; t < 32; ++t) xb[l * 33 + t] = z[t].y;
-      __syncwarp();
-#pragma unroll
-      for (int m = 0; m < 32; ++m) { const int e = l + LPF * m; z[m].y = xb[e + (e >> 5)]; }
-      __syncwarp();
-      // ---- pass 1: radix LPF, NS = 32
-#pragma unroll
-      for (int b = 0; b < B1; ++b) {
-#pragma unroll
-        for (int t = 1; t < R1; ++t)
-          z[b + B1 * t] = cmul(z[b + B1 * t], tw[(b * (R1 - 1) + (t - 1)) * LPF + l]);
-        float2 o[R1];
-        DFT<R1, B1>::run(&z[b], o);
-#pragma unroll
-        for (int t = 0; t < R1; ++t) z[b + B1 * t] = o[t];
-      }
-    }
-    // now z[m] = Z[l + LPF m]
+      warp_fft<LOG2N>(z, xb, tw, l);  // z[m] = Z[l + LPF m]
 
-    // ---- untangle -> real-FFT bins k = l + LPF m (m < 16) and N - k ; magnitudes into xb
-    float2* so = p.stft_out ? p.stft_out + (size_t)row * F * p.n_frames + n : nullptr;
+      // ---- untangle -> real-FFT bins k = l + LPF m (m < 16) and N - k ; magnitudes into xb
+      float2* so = p.stft_out ? p.stft_out + (size_t)row * F * p.n_frames + n : nullptr;
 #pragma unroll
-    for (int m = 0; m < 16; ++m) {
-      const float2 zk = z[m];
-      float2 zn;
-      zn.x = __shfl_sync(0xffffffffu, z[31 - m].x, src_lane);
-      zn.y = __shfl_sync(0xffffffffu, z[31 - m].y, src_lane);
-      if (l == 0) zn = z[(32 - m) & 31];
-      const int k = l + LPF * m;
-      const float2 xe = make_float2(0.5f * (zk.x + zn.x), 0.5f * (zk.y - zn.y));
-      const float2 xo = make_float2(0.5f * (zk.y + zn.y), 0.5f * (zn.x - zk.x));
-      const float2 tt = cmul(ut[m * LPF + l], xo);
-      const float2 xk = cadd(xe, tt);
-      const float2 d = csub(xe, tt);
-      if (so && live) {
-        so[(size_t)k * p.n_frames] = xk;
-        so[(size_t)(N - k) * p.n_frames] = make_float2(d.x, -d.y);
+      for (int m = 0; m < 16; ++m) {
+        const float2 zk = z[m];
+        float2 zn;
+        zn.x = __shfl_sync(0xffffffffu, z[31 - m].x, src_lane);
+        zn.y = __shfl_sync(0xffffffffu, z[31 - m].y, src_lane);
+        if (l == 0) zn = z[(32 - m) & 31];
+        const int k = l + LPF * m;
+        const float2 xe = make_float2(0.5f * (zk.x + zn.x), 0.5f * (zk.y - zn.y));
+        const float2 xo = make_float2(0.5f * (zk.y + zn.y), 0.5f * (zn.x - zk.x));
+        const float2 tt = cmul(ut[m * LPF + l], xo);
+        const float2 xk = cadd(xe, tt);
+        const float2 d = csub(xe, tt);
+        if (so && live) {
+          so[(size_t)k * p.n_frames] = make_float2(g * xk.x, g * xk.y);
+          so[(size_t)(N - k) * p.n_frames] = make_float2(g * d.x, -g * d.y);
+        }
+        xb[k] = fast_sqrt(fmaf(xk.x, xk.x, xk.y * xk.y));
+        xb[N - k] = fast_sqrt(fmaf(d.x, d.x, d.y * d.y));
       }
-      xb[k] = fast_sqrt(fmaf(xk.x, xk.x, xk.y * xk.y));
-      xb[N - k] = fast_sqrt(fmaf(d.x, d.x, d.y * d.y));
-    }
-    if (l == 0) {  // k = N/2 pairs with itself: X = conj(Z[N/2])
-      const float2 zh = z[16];
-      if (so && live) so[(size_t)(N / 2) * p.n_frames] = make_float2(zh.x, -zh.y);
-      xb[N / 2] = fast_sqrt(fmaf(zh.x, zh.x, zh.y * zh.y));
-      xb[N + 1] = 0.f; xb[N + 2] = 0.f; xb[N + 3] = 0.f;  // read (x 0 weight) by 4-wide band loads
-    }
-    __syncwarp();
+      if (l == 0) {  // k = N/2 pairs with itself: X = conj(Z[N/2])
+        const float2 zh = z[16];
+        if (so && live) so[(size_t)(N / 2) * p.n_frames] = make_float2(g * zh.x, -g * zh.y);
+        xb[N / 2] = fast_sqrt(fmaf(zh.x, zh.x, zh.y * zh.y));
+        xb[N + 1] = 0.f; xb[N + 2] = 0.f; xb[N + 3] = 0.f;  // read (x 0 weight) by 4-wide band loads
+      }
+      __syncwarp();
 
-    // ---- banded mel projection + post-op
-    if (p.mel_out) {
-      for (int mm = l; mm < p.n_mels; mm += LPF) {
-        float acc = 0.f;
-        if (packed) {
-          const int4 sg = mseg[mm];
-          const float4* w4 = reinterpret_cast<const float4*>(mpk) + sg.x;
-          const float4* m4 = reinterpret_cast<const float4*>(xb + sg.y);
-          float a0 = 0.f, a1 = 0.f;
-          for (int i = 0; i < sg.z; ++i) {
-            const float4 w = w4[i], v = m4[i];
-            a0 = fmaf(w.x, v.x, a0); a1 = fmaf(w.y, v.y, a1);
-            a0 = fmaf(w.z, v.z, a0); a1 = fmaf(w.w, v.w, a1);
+      // ---- banded mel projection (x |gain|: the projection is linear) + post-op
+      if (p.mel_out) {
+        for (int mm = l; mm < p.n_mels; mm += LPF) {
+          float acc = 0.f;
+          if (packed) {
+            const int4 sg = mseg[mm];
+            const float4* w4 = reinterpret_cast<const float4*>(mpk) + sg.x;
+            const float4* m4 = reinterpret_cast<const float4*>(xb + sg.y);
+            float a0 = 0.f, a1 = 0.f;
+            for (int i = 0; i < sg.z; ++i) {
+              const float4 w = w4[i], v = m4[i];
+              a0 = fmaf(w.x, v.x, a0); a1 = fmaf(w.y, v.y, a1);
+              a0 = fmaf(w.z, v.z, a0); a1 = fmaf(w.w, v.w, a1);
+            }
+            acc = a0 + a1;
+          } else {
+            const int lo = __ldg(p.mel_lo + mm), hi = __ldg(p.mel_hi + mm);
+            const float* wrow = p.mel_fb + (size_t)mm * F;
+            for (int k = lo; k < hi; ++k) acc = fmaf(__ldg(wrow + k), xb[k], acc);
           }
-          acc = a0 + a1;
-        } else {
-          const int lo = __ldg(p.mel_lo + mm), hi = __ldg(p.mel_hi + mm);
-          const float* wrow = p.mel_fb + (size_t)mm * F;
-          for (int k = lo; k < hi; ++k) acc = fmaf(__ldg(wrow + k), xb[k], acc);
+          acc *= ga;
+          if (p.post == B2A_POST_LOG10) {
+            float c = fmaxf(acc, p.post_eps);
+            c = (p.post_power == 2.0f) ? c * c : powf(c, p.post_power);
+            acc = log10f(c);
+          } else if (p.post == B2A_POST_LN) {
+            acc = logf(acc + p.post_eps);
+          }
+          melt[mm * (FR + 1) + f] = acc;
         }
-        if (p.post == B2A_POST_LOG10) {
-          float c = fmaxf(acc, p.post_eps);
-          c = (p.post_power == 2.0f) ? c * c : powf(c, p.post_power);
-          acc = log10f(c);
-        } else if (p.post == B2A_POST_LN) {
-          acc = logf(acc + p.post_eps);
-        }
-        melt[mm * (FR + 1) + f] = acc;
       }
+      __syncwarp();
     }
-    __syncwarp();
-  }
 
-  if (p.mel_out) {
-    __syncthreads();
-    const int nf = min(FR, p.n_frames - n0);
-    float* o = p.mel_out + (size_t)row * p.n_mels * p.n_frames + n0;
-    for (int i = tid; i < p.n_mels * FR; i += 256) {
-      const int m = i / FR, f = i - m * FR;
-      if (f < nf) o[(size_t)m * p.n_frames + f] = melt[m * (FR + 1) + f];
+    __syncthreads();  // all frames of the tile are done: melt complete, sp free for the next tile
+    if (p.mel_out) {
+      const int nf = min(FR, p.n_frames - n0);
+      float* o = p.mel_out + (size_t)row * p.n_mels * p.n_frames + n0;
+      for (int i = tid; i < p.n_mels * FR; i += 256) {
+        const int m = i / FR, f = i - m * FR;
+        if (f < nf) o[(size_t)m * p.n_frames + f] = melt[m * (FR + 1) + f];
+      }
+      __syncthreads();  // melt is rewritten by the next tile
     }
   }
+  cp_async_wait_all();
+}
+
+static int num_sms() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0)
+      n = B2A_NUM_SMS;
+  }
+  return n;
 }
 
 template <int LOG2N>
@@ -748,6 +651,7 @@ static int launch_warp(Params& p, void* stream) {
   p.off_mag = o;
   p.off_mel = o; o = align16(o + (p.mel_out ? p.n_mels * (PL::FR + 1) * 4 : 0));
   const int base = o;
+  p.off_mpk = o; p.off_mseg = o;
   if (p.mel_out && p.mel_packed_len > 0) {
     p.off_mpk = o; o = align16(o + p.mel_packed_len * 4);
     p.off_mseg = o; o = align16(o + p.n_mels * 16);
@@ -757,11 +661,28 @@ static int launch_warp(Params& p, void* stream) {
   B2A_REQUIRE(o <= 227 * 1024, B2A_E_UNSUPPORTED,
               "spectral: n_fft=%d hop=%d n_mels=%d needs %d bytes of shared memory (> 227 KB)", p.n_fft, p.hop,
               p.n_mels, o);
-  B2A_REQUIRE((int64_t)p.rows * p.n_tiles < (int64_t)2147483647, B2A_E_UNSUPPORTED, "spectral: grid too large");
+  const int64_t total = (int64_t)p.rows * p.n_tiles;
+  B2A_REQUIRE(total < (int64_t)2147483647, B2A_E_UNSUPPORTED, "spectral: too many tiles");
   B2A_CUDA_OK(cudaFuncSetAttribute(spectral_warp_kernel<LOG2N>, cudaFuncAttributeMaxDynamicSharedMemorySize, o));
-  B2A_LAUNCH(spectral_warp_kernel<LOG2N>, dim3((unsigned)(p.rows * p.n_tiles)), dim3(256), (size_t)o, stream, p);
+  // persistent: as many CTAs as fit (2 per SM by registers; 1 when the shared memory is large), each loops over tiles
+  const int per_sm = (o <= 110 * 1024) ? 2 : 1;
+  const int64_t cap = (int64_t)num_sms() * per_sm;
+  const unsigned grid = (unsigned)(total < cap ? total : cap);
+  B2A_LAUNCH(spectral_warp_kernel<LOG2N>, dim3(grid), dim3(256), (size_t)o, stream, p);
   B2A_CUDA_OK(cudaGetLastError());
   return B2A_OK;
+}
+
+// raw-framing forward FFT of blocks (used by the FFT convolution): out[rows, F, n_frames]
+int frames_fft(const float* x, int rows, int T, int n_fft, int hop, const float* window, int origin,
+               const int32_t* row_origin, int pad_mode, int n_frames, float2* out, void* stream) {
+  Params p;
+  memset(&p, 0, sizeof(p));
+  p.x = x; p.window = window; p.stft_out = out;
+  p.rows = rows; p.T = T; p.n_fft = n_fft; p.hop = hop; p.pad_mode = pad_mode; p.n_frames = n_frames;
+  p.rows_per_gain = 1; p.center = 0; p.origin = origin; p.row_origin = row_origin;
+  B2A_REQUIRE(n_fft == 2048, B2A_E_UNSUPPORTED, "frames_fft: block size %d", n_fft);
+  return launch_warp<10>(p, stream);
 }
 
 }  // namespace spectral
@@ -810,6 +731,7 @@ extern "C" int b2a_spectral_f32(const float* x, int64_t rows, int64_t T, int n_f
   p.rows = (int)rows; p.T = (int)T; p.n_fft = n_fft; p.hop = hop; p.pad = pad; p.right_pad = right_pad;
   p.pad_mode = pad_mode; p.drop_edge = drop_edge; p.n_frames = (int)nfr; p.n_mels = n_mels;
   p.mel_packed_len = (mel_out && mel_packed_len > 0) ? mel_packed_len : 0;
+  p.center = 1; p.origin = -(n_fft / 2) - pad; p.row_origin = nullptr;
   p.rows_per_gain = gain ? rows_per_gain : 1; p.post = post; p.post_eps = post_eps; p.post_power = post_power;
   switch (n_fft) {
     case 32: return launch<4>(p, stream);

@@ -169,6 +169,249 @@ class Engine:
         return {"stft": stft, "mel": mel, "scaled": scaled}
 
 
+    # ------------------------------------------------------------------ FIR / convolution
+    def fftconv(self, x: torch.Tensor, taps: torch.Tensor, rows_per_filt: int, offset: Optional[torch.Tensor] = None,
+                offset0: int = 0, pad_mode: str = "replicate", post_scale: Optional[torch.Tensor] = None,
+                subtract_from_input: bool = False) -> torch.Tensor:
+        """``out[row, n] = post * sum_k taps[f, k] * xv[row, n - k + offset0 + offset[f]]`` with
+        ``f = row // rows_per_filt`` and ``xv`` = ``x`` extended by ``pad_mode`` ("constant" zeros,
+        "replicate", "circular").  x: [..., T] (leading dims are flattened to rows); taps: [n_filt, L]."""
+        x = self._prep(x, "x")
+        shape = x.shape
+        T = shape[-1]
+        rows = x.numel() // T
+        taps = self._prep(taps, "taps")
+        assert taps.ndim == 2
+        n_filt, L = taps.shape
+        if offset is not None:
+            offset = self._prep(offset.reshape(-1), "offset", torch.int32)
+            assert offset.numel() == n_filt
+        if post_scale is not None:
+            post_scale = self._prep(post_scale.reshape(-1), "post_scale")
+            assert post_scale.numel() == n_filt
+        mode = {"constant": 1, "replicate": 2, "circular": 3}[pad_mode]
+        ws_bytes = self.lib.b2a_fftconv_workspace_bytes(rows, T, n_filt, L)
+        if ws_bytes == 0:
+            raise _lib.B2AError("fftconv: bad shape")
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=x.device)
+        out = torch.empty_like(x)
+        rc = self.lib.b2a_fftconv_f32(_dptr(x), rows, T, _dptr(taps), n_filt, L, int(rows_per_filt), _dptr(offset),
+                                      int(offset0), mode, _dptr(post_scale), int(bool(subtract_from_input)),
+                                      _dptr(out), _dptr(ws), ws_bytes, self._stream(x))
+        self.lib.check(rc)
+        nchunk = 1  # kernels: fill, filter FFT, then per row-chunk: origins, block FFT, bin FIR, inverse FFT
+        self.launches += 2 + 4 * nchunk
+        return out
+
+    @staticmethod
+    def _sinc(x: torch.Tensor) -> torch.Tensor:
+        return torch.where(x == 0, torch.ones_like(x), torch.sin(x) / x)
+
+    def _lowpass_bank(self, cutoffs: torch.Tensor, half: torch.Tensor, device) -> torch.Tensor:
+        """Windowed-sinc low-pass taps (julius.LowPassFilters arithmetic, float32) for per-filter
+        normalised cutoffs [n] and half sizes [n]; filter i occupies taps[i, :2*half[i]+1], rest 0."""
+        n = cutoffs.numel()
+        hmax = int(half.max().item())
+        c = cutoffs.to(device=device, dtype=torch.float32).reshape(n, 1)
+        h = half.to(device=device).reshape(n, 1)
+        j = torch.arange(2 * hmax + 1, device=device).reshape(1, -1)
+        valid = j <= 2 * h
+        t = (j - h).to(torch.float32)
+        # torch.hann_window(2*half+1, periodic=False)[j] = 0.5 - 0.5 cos(2 pi j / (2 half))
+        win = 0.5 - 0.5 * torch.cos(2 * math.pi * j.to(torch.float32) / (2 * h).clamp(min=1).to(torch.float32))
+        f = 2 * c * win * self._sinc(2 * c * math.pi * t)
+        f = torch.where(valid & (c > 0), f, torch.zeros_like(f))
+        s = f.sum(dim=1, keepdim=True)
+        return torch.where(s != 0, f / s, f)
+
+    @staticmethod
+    def _reverse_rows(f: torch.Tensor, lengths: torch.Tensor) -> torch.Tensor:
+        """g[i, k] = f[i, lengths[i]-1-k] for k < lengths[i] (correlation taps -> convolution taps)."""
+        n, L = f.shape
+        k = torch.arange(L, device=f.device).reshape(1, -1)
+        idx = (lengths.to(f.device).reshape(n, 1) - 1 - k)
+        g = torch.gather(f, 1, idx.clamp(min=0))
+        return torch.where(idx >= 0, g, torch.zeros_like(g))
+
+    def sinc_filter(self, x: torch.Tensor, cutoffs_hz: torch.Tensor, sample_rate: int, zeros: int = 51,
+                    highpass: bool = False) -> torch.Tensor:
+        """Per-item windowed-sinc low-pass (or ``x - lowpass(x)``) of x [B, C, T]
+        (ref:audiotools/core/dsp.py:153-215 -> julius.LowPassFilter(cutoff / sr, zeros), replicate padding)."""
+        x = self._prep(x, "x")
+        B, C, T = x.shape
+        cut = torch.as_tensor(cutoffs_hz).reshape(-1).cpu()
+        if cut.numel() == 1:
+            cut = cut.expand(B)
+        assert cut.numel() == B
+        # the reference divides a [B,1] tensor by the (python int) sample rate: float32 unless the input is float64
+        cn = (cut / sample_rate)
+        if cn.dtype not in (torch.float32, torch.float64):
+            cn = cn.float()
+        if (cn < 0).any():
+            raise ValueError("Minimum cutoff must be larger than zero.")
+        if (cn > 0.5).any():
+            raise ValueError("A cutoff above 0.5 does not make sense.")
+        if (cn == 0).any():
+            raise ValueError("cutoff 0: julius.LowPassFilter has no positive cutoff to size the filter from")
+        half = (zeros / cn / 2).to(torch.int64)  # int(zeros / cutoff / 2), in the tensor's own precision
+        f = self._lowpass_bank(cn, half, x.device)
+        g = self._reverse_rows(f, 2 * half + 1)
+        return self.fftconv(x, g, rows_per_filt=C, offset=half.to(torch.int32), pad_mode="replicate",
+                            subtract_from_input=highpass)
+
+    @staticmethod
+    def _split_band_cutoffs(sample_rate: float, n_bands: int):
+        """julius.SplitBands cutoffs: HTK-mel spaced, normalised by the sample rate (float64)."""
+        import numpy as _np
+
+        lo, hi = 2595 * math.log10(1 + 0.0 / 700), 2595 * math.log10(1 + (sample_rate / 2) / 700)
+        mels = _np.linspace(lo, hi, n_bands + 1)
+        hz = 700 * (10 ** (mels / 2595) - 1)
+        return hz[1:-1] / sample_rate
+
+    def _band_lowpasses(self, sample_rate: float, n_bands: int, device):
+        """(lp [n_bands-1, 2*half+1] float32 correlation taps, half) of julius.SplitBands(zeros=8)."""
+        c = self._split_band_cutoffs(sample_rate, n_bands)
+        half = int(8 / min(c) / 2)
+        cn = torch.from_numpy(c)  # float64 scalars multiply float32 tensors as python scalars in julius
+        lp = self._lowpass_bank(cn.float(), torch.full((len(c),), half, dtype=torch.int64), device)
+        return lp, half
+
+    def equalizer(self, x: torch.Tensor, sample_rate: int, db: torch.Tensor) -> torch.Tensor:
+        """Mel-band equaliser of x [B, C, T] (ref:audiotools/core/effects.py:405-433): band weights
+        10**db [B or 1, n_bands]; split + weighted sum == one FIR per item,
+        h = w_last * delta + sum_k (w_k - w_{k+1}) * lowpass_k."""
+        x = self._prep(x, "x")
+        B, C, T = x.shape
+        db = torch.as_tensor(db)
+        if db.ndim == 1:
+            db = db.unsqueeze(0)
+        n_bands = db.shape[-1]
+        w = (10 ** db).to(x.device).float()
+        if w.shape[0] == 1:
+            w = w.expand(B, n_bands)
+        assert w.shape[0] == B
+        if n_bands == 1:
+            return self.gain(x, w[:, 0].contiguous())
+        lp, half = self._band_lowpasses(sample_rate, n_bands, x.device)
+        h = (w[:, :-1] - w[:, 1:]) @ lp  # [B, 2*half+1]
+        h[:, half] += w[:, -1]
+        g = torch.flip(h, dims=[1]).contiguous()
+        return self.fftconv(x, g, rows_per_filt=C, offset0=half, pad_mode="replicate")
+
+    def mel_filterbank(self, x: torch.Tensor, sample_rate: int, n_bands: int) -> torch.Tensor:
+        """julius.SplitBands(sample_rate, n_bands)(x).permute(1, 2, 3, 0) -> [B, C, T, n_bands]
+        (ref:audiotools/core/effects.py:386-403)."""
+        x = self._prep(x, "x")
+        B, C, T = x.shape
+        if n_bands == 1:
+            return x.unsqueeze(-1).clone()
+        lp, half = self._band_lowpasses(sample_rate, n_bands, x.device)
+        h = torch.zeros(n_bands, 2 * half + 1, device=x.device)
+        h[0] = lp[0]
+        h[1:-1] = lp[1:] - lp[:-1]
+        h[-1] = -lp[-1]
+        h[-1, half] += 1.0
+        g = torch.flip(h, dims=[1]).contiguous()
+        bands = [self.fftconv(x, g[k:k + 1], rows_per_filt=B * C, offset0=half, pad_mode="replicate")
+                 for k in range(n_bands)]
+        return torch.stack(bands, dim=-1)
+
+    def circular_convolve(self, x: torch.Tensor, ir: torch.Tensor, roll_to_peak: bool = True) -> torch.Tensor:
+        """``EffectMixin.convolve`` (ref:audiotools/core/effects.py:66-123): circular convolution with period T,
+        the IR rolled to its peak, scaled by 1/max(max|ir|, 1e-5).  x: [B, C, T]; ir: [B, 1 or C, L]."""
+        x = self._prep(x, "x")
+        B, C, T = x.shape
+        ir = self._prep(ir, "ir")
+        assert ir.ndim == 3 and ir.shape[0] == B and ir.shape[1] in (1, C), ir.shape
+        if ir.shape[-1] > T:
+            ir = ir[..., :T].contiguous()
+        L = ir.shape[-1]
+        n_ir = B * ir.shape[1]
+        rows_per_ir = C if ir.shape[1] == 1 else 1
+        ws_bytes = self.lib.b2a_circconv_workspace_bytes(B * C, T, n_ir, L)
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=x.device)
+        out = torch.empty_like(x)
+        rc = self.lib.b2a_circconv_f32(_dptr(x), B * C, T, _dptr(ir), n_ir, L, rows_per_ir, int(bool(roll_to_peak)),
+                                       _dptr(out), _dptr(ws), ws_bytes, self._stream(x))
+        self.lib.check(rc)
+        self.launches += 7
+        return out
+
+
+    # ------------------------------------------------------------------ resample
+    def _resample_kernel(self, old_sr: int, new_sr: int, device, zeros: int = 24, rolloff: float = 0.945):
+        """julius.ResampleFrac._init_kernels (float32 arithmetic), transposed to [K, new]; cached."""
+        key = (old_sr, new_sr, str(device), zeros, rolloff)
+        if key not in self._packed_cache:
+            gcd = math.gcd(old_sr, new_sr)
+            old, new = old_sr // gcd, new_sr // gcd
+            sr = min(new, old) * rolloff
+            width = math.ceil(zeros * old / sr)
+            idx = torch.arange(-width, width + old, device=device).float()
+            i = torch.arange(new, device=device).float().reshape(-1, 1)
+            t = (-i / new + idx.reshape(1, -1) / old) * sr
+            t = t.clamp(-zeros, zeros) * math.pi
+            window = torch.cos(t / zeros / 2) ** 2
+            kernel = self._sinc(t) * window
+            kernel = kernel / kernel.sum(dim=1, keepdim=True)
+            self._packed_cache[key] = (kernel.t().contiguous(), width, old, new)
+        return self._packed_cache[key]
+
+    def resample(self, x: torch.Tensor, old_sr: int, new_sr: int) -> torch.Tensor:
+        """julius.resample_frac(x, old_sr, new_sr) for x [..., T] (ref:audiotools/core/audio_signal.py:732-734)."""
+        x = self._prep(x, "x")
+        if int(old_sr) == int(new_sr):
+            return x
+        kt, width, old, new = self._resample_kernel(int(old_sr), int(new_sr), x.device)
+        T = x.shape[-1]
+        rows = x.numel() // T
+        out_len = int(self.lib.b2a_resample_out_len(T, old, new))
+        out = torch.empty(*x.shape[:-1], out_len, dtype=torch.float32, device=x.device)
+        rc = self.lib.b2a_resample_f32(_dptr(x), rows, T, old, new, width, _dptr(kt), _dptr(out), self._stream(x))
+        self.lib.check(rc)
+        self.launches += 1
+        return out
+
+
+    # ------------------------------------------------------------------ pitch shift
+    def _interp_table(self, ratio: float, device, Q: int = 256, zero_crossings: int = 8):
+        """[Q+1, NT] windowed-sinc interpolation weights, cutoff 0.95*min(1, 1/ratio), rows sum to 1."""
+        c = 0.95 * min(1.0, 1.0 / ratio)
+        half = int(math.ceil(zero_crossings / c))
+        NT = 2 * half
+        key = ("interp", round(c, 9), str(device), Q)
+        if key not in self._packed_cache:
+            q = torch.arange(Q + 1, device=device, dtype=torch.float64).reshape(-1, 1) / Q
+            k = torch.arange(NT, device=device, dtype=torch.float64).reshape(1, -1)
+            t = (k - half + 1) - q  # tap position relative to the read position
+            a = math.pi * c * t
+            sinc = torch.where(t == 0, torch.ones_like(a), torch.sin(a) / a)
+            win = torch.where(t.abs() < half, 0.5 + 0.5 * torch.cos(math.pi * t / half), torch.zeros_like(t))
+            w = c * sinc * win
+            w = w / w.sum(dim=1, keepdim=True)
+            self._packed_cache[key] = (w.float().contiguous(), NT)
+        return self._packed_cache[key] + (Q,)
+
+    def pitch_shift(self, x: torch.Tensor, sample_rate: int, n_semitones: float, quick: bool = True) -> torch.Tensor:
+        """Shift the pitch of x [..., T] by ``n_semitones`` keeping T (ref:audiotools/core/effects.py:247-277)."""
+        x = self._prep(x, "x")
+        if float(n_semitones) == 0.0:
+            return x.clone()
+        T = x.shape[-1]
+        rows = x.numel() // T
+        ratio = 2.0 ** (float(n_semitones) / 12.0)
+        table, NT, Q = self._interp_table(ratio, x.device)
+        ws_bytes = self.lib.b2a_pitch_shift_workspace_bytes(rows, T, int(sample_rate), float(n_semitones))
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=x.device)
+        out = torch.empty_like(x)
+        rc = self.lib.b2a_pitch_shift_f32(_dptr(x), rows, T, int(sample_rate), float(n_semitones), _dptr(table), Q, NT,
+                                          _dptr(out), _dptr(ws), ws_bytes, self._stream(x))
+        self.lib.check(rc)
+        self.launches += 2
+        return out
+
+
 _ENGINE = None
 
 

@@ -108,6 +108,43 @@ int b2a_lufs_f32(const float* x, int64_t B, int C, int64_t T, int64_t T_padded, 
  * out may alias x.  per_item = C*T. */
 int b2a_gain_f32(const float* x, float* out, int64_t B, int64_t per_item, const float* gain, void* stream);
 
+/* ---- FIR / circular convolution by partitioned overlap-save FFT convolution -------------------
+ * out[row][n] = post_scale[f] * sum_{k<L} g[f][k] * xv[row][n - k + offset0 + offset[f]],  f = row / rows_per_filt,
+ * n in [0, T), where xv extends x[row] by pad_mode: 1 zeros, 2 replicate (edge), 3 circular (period T).
+ * With subtract_from_input != 0 the result is x - (that).   g: [n_filt, L] row-major taps (zero-pad
+ * shorter filters); offset / post_scale: nullable [n_filt].   out must not alias x.
+ * Replaces julius.LowPassFilter / HighPassFilter (audiotools/core/dsp.py:153-215), julius.SplitBands +
+ * the weighted band sum (audiotools/core/effects.py:386-433) -- each collapsed to one FIR per item. */
+size_t b2a_fftconv_workspace_bytes(int64_t rows, int64_t T, int64_t n_filt, int64_t L);
+int b2a_fftconv_f32(const float* x, int64_t rows, int64_t T, const float* g, int64_t n_filt, int64_t L,
+                    int rows_per_filt, const int32_t* offset, int offset0, int pad_mode,
+                    const float* post_scale, int subtract_from_input, float* out, void* ws, size_t ws_bytes,
+                    void* stream);
+
+/* EffectMixin.convolve (audiotools/core/effects.py:66-123): CIRCULAR convolution (period T) of each row with
+ * its item's impulse response, the IR rolled so that max|ir| sits at t = 0 (roll_to_peak) and the result
+ * scaled by 1 / max(max|ir|, 1e-5).   ir: [n_ir, L] with L <= T (truncate first, as the reference does). */
+size_t b2a_circconv_workspace_bytes(int64_t rows, int64_t T, int64_t n_ir, int64_t L);
+int b2a_circconv_f32(const float* x, int64_t rows, int64_t T, const float* ir, int64_t n_ir, int64_t L,
+                     int rows_per_ir, int roll_to_peak, float* out, void* ws, size_t ws_bytes, void* stream);
+
+/* ---- windowed-sinc polyphase resampling ------------------------------------------------------
+ * AudioSignal.resample (audiotools/core/audio_signal.py:716-736 -> julius.resample_frac): old_r/new_r are
+ * the gcd-reduced rates, kernel_t the per-phase kernels transposed to [K = 2*width + old_r][new_r]
+ * (julius.ResampleFrac._init_kernels: zeros 24, rolloff 0.945, each phase renormalised to sum 1).
+ * out: [rows, b2a_resample_out_len(T, old_r, new_r)] = floor(new_r*T/old_r) samples per row. */
+int64_t b2a_resample_out_len(int64_t T, int old_r, int new_r);
+int b2a_resample_f32(const float* x, int64_t rows, int64_t T, int old_r, int new_r, int width,
+                     const float* kernel_t, float* out, void* stream);
+
+/* ---- pitch shift ---------------------------------------------------------------------------------
+ * EffectMixin.pitch_shift (audiotools/core/effects.py:247-277; SoX `pitch -q` + `rate` there): WSOLA
+ * time-scale modification by r = 2^(semitones/12) + band-limited resampling by 1/r, output length == T.
+ * table: [Q+1][NT] windowed-sinc interpolation weights (phase q/Q, tap k at floor(pos)+k-NT/2+1). */
+size_t b2a_pitch_shift_workspace_bytes(int64_t rows, int64_t T, int sr, float semitones);
+int b2a_pitch_shift_f32(const float* x, int64_t rows, int64_t T, int sr, float semitones, const float* table,
+                        int Q, int NT, float* out, void* ws, size_t ws_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -247,3 +247,176 @@ def test_cpu_tensor_raises_and_errors_map(at):
         at.AudioSignal(torch.zeros(1, 1, 16000), 16000).to(DEV).stft(window_length=400, hop_length=100)
     with pytest.raises(RuntimeError, match="without self.stft_data"):
         at.AudioSignal(torch.zeros(1, 1, 16000), 16000).to(DEV).istft()
+
+
+# ------------------------------------------------------------------------------------------
+# resample / FIR filters / equaliser / IR convolution / pitch shift / transforms
+# ------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("key,sl,old,new", [("rs_48k_16k", 24000, 48000, 16000), ("rs_44k_16k", 22050, 44100, 16000),
+                                            ("rs_16k_44k", 8000, 16000, 44100), ("rs_16k_48k", 8001, 16000, 48000),
+                                            ("rs_44k_48k", 4410, 44100, 48000)])
+def test_resample_matches_reference(at, golden, key, sl, old, new):
+    x = cases.make_input("rs")[..., :sl]
+    sig = at.AudioSignal(x.clone(), old).to(DEV).resample(new)
+    ref = G(golden, key)
+    assert sig.sample_rate == new and sig.audio_data.shape == ref.shape  # floor(new*T/old)
+    assert rel_err(sig.audio_data.cpu(), ref) < TOL
+
+
+def test_cfg3_shape_resample_lowpass(at, golden, sp):
+    """BASELINE configs[2] shape (48k -> 16k + low_pass(8k)), small: vs the reference golden; and one
+    30 s row of the full-size config vs the oracle."""
+    sig = sig_of(at, "rs").resample(16000).low_pass(8000)
+    assert rel_err(sig.audio_data.cpu(), G(golden, "rs_48k_16k_lp8k")) < TOL
+    x = 0.1 * torch.randn(2, 1, 1440000, generator=torch.Generator().manual_seed(0))
+    y = at.AudioSignal(x.clone(), 48000).to(DEV).resample(16000).low_pass(8000).audio_data
+    assert y.shape == (2, 1, 480000)
+    ref = sp.low_pass(sp.resample(x, 48000, 16000), 16000, 8000)
+    assert rel_err(y.cpu(), ref) < TOL
+
+
+def test_low_high_pass_match_reference(at, golden):
+    cut = G(golden, "fir_cut")
+    assert rel_err(sig_of(at, "fir").low_pass(cut).audio_data.cpu(), G(golden, "lp_peritem")) < TOL
+    assert rel_err(sig_of(at, "fir").high_pass(cut / 8).audio_data.cpu(), G(golden, "hp_peritem")) < TOL
+    assert rel_err(sig_of(at, "fir").low_pass(4000).audio_data.cpu(), G(golden, "lp_scalar")) < TOL
+    sig = sig_of(at, "fir")
+    sig.stft()
+    assert sig.low_pass(4000).stft_data is None  # filters drop the STFT cache (ref dsp.py:182)
+
+
+def test_low_high_pass_sine_thresholds(at):
+    """ref:tests/core/test_dsp.py:76-109 (fully synthetic in the reference too)."""
+    sr, f = 44100, 440
+    t = torch.arange(sr) / sr
+    x = (torch.sin(2 * np.pi * f * t) * torch.hann_window(sr))[None, None]
+    mk = lambda: at.AudioSignal(x.clone(), sr).to(DEV)
+    assert mk().low_pass(220).audio_data.abs().max() < 1e-4
+    assert (mk().low_pass(880).audio_data.cpu() - x).abs().max() < 1e-3
+    assert (mk().high_pass(220).audio_data.cpu() - x).abs().max() < 1e-4
+    both = at.AudioSignal(x.repeat(2, 1, 1), sr).to(DEV).low_pass(torch.tensor([220.0, 880.0])).audio_data.cpu()
+    assert both[0].abs().max() < 1e-4 and (both[1] - x[0]).abs().max() < 1e-3
+    # the default HighPass cutoff 50 Hz @44.1k is a 44983-tap filter (44 partitions)
+    y = mk().high_pass(50).audio_data.cpu()
+    assert (y - x).abs().max() < 1e-3
+
+
+def test_equalizer_and_filterbank_match_reference(at, golden):
+    eq = golden["eq_db"]
+    assert rel_err(sig_of(at, "fir").equalizer(eq).audio_data.cpu(), G(golden, "eq_out")) < TOL
+    assert rel_err(sig_of(at, "fir").equalizer(eq[0]).audio_data.cpu(), G(golden, "eq_out_1d")) < TOL
+    assert rel_err(sig_of(at, "fir", slice(0, 1)).mel_filterbank(4)[:, :1].cpu(), G(golden, "fbank4")) < TOL
+    x = cases.make_input("fir")[:1]
+    for n_bands in (1, 2, 4, 8, 12, 16):  # ref:tests/core/test_effects.py:184-231
+        sig = at.AudioSignal(x.clone(), 44100).to(DEV)
+        fb = sig.mel_filterbank(n_bands)
+        assert fb.shape[-1] == n_bands and torch.allclose(fb.sum(-1).cpu(), x, atol=1e-6)
+        assert torch.allclose(sig.equalizer(np.zeros(n_bands)).audio_data.cpu(), x, atol=1e-6)
+
+
+def test_convolve_and_apply_ir_match_reference(at, golden):
+    ir = cases.make_ir()
+    mk_ir = lambda: at.AudioSignal(ir.clone(), 44100).to(DEV)
+    assert rel_err(sig_of(at, "fir").convolve(mk_ir()).audio_data.cpu(), G(golden, "conv_out")) < TOL
+    assert rel_err(sig_of(at, "fir").convolve(mk_ir(), start_at_max=False).audio_data.cpu(),
+                   G(golden, "conv_out_nomax")) < TOL
+    assert rel_err(sig_of(at, "fir").apply_ir(mk_ir()).audio_data.cpu(), G(golden, "applyir_plain")) < TOL
+    drr = G(golden, "drr")
+    assert rel_err(mk_ir().alter_drr(drr).audio_data.cpu(), G(golden, "alter_drr")) < TOL
+    assert torch.allclose(mk_ir().measure_drr().cpu(), G(golden, "measure_drr"), atol=1e-3)
+    out = sig_of(at, "fir").apply_ir(mk_ir(), drr=drr, ir_eq=golden["eq_db"]).audio_data.cpu()
+    assert rel_err(out, G(golden, "applyir_full")) < TOL
+    x = cases.make_input("fir")
+    for delay in (0, 1, 777):  # delta IR == identity, ref:tests/core/test_effects.py:86-121
+        d = torch.zeros(3, 1, 1000)
+        d[..., delay] = 1.0
+        y = at.AudioSignal(x.clone(), 44100).to(DEV).convolve(at.AudioSignal(d, 44100).to(DEV)).audio_data.cpu()
+        assert torch.allclose(y, x, atol=1e-6)
+
+
+def test_circular_convolution_full_size_vs_fft(at):
+    """cfg4-size rows (10 s @44.1k, 1 s IR): against a float64 FFT circular convolution."""
+    g = torch.Generator().manual_seed(5)
+    x = 0.1 * torch.randn(4, 1, 441000, generator=g)
+    t = torch.arange(44100) / 44100
+    ir = torch.randn(4, 1, 44100, generator=g) * torch.exp(-t / 0.3)
+    ir[..., 100] = 3.0
+    y = at.AudioSignal(x.clone(), 44100).to(DEV).convolve(at.AudioSignal(ir.clone(), 44100).to(DEV)).audio_data.cpu()
+    h = torch.nn.functional.pad(ir, (0, 441000 - 44100)).double()
+    idx = h.abs().argmax(-1)
+    h = torch.stack([torch.roll(h[i], -idx[i].item(), -1) for i in range(4)])
+    ref = torch.fft.irfft(torch.fft.rfft(x.double(), 441000) * torch.fft.rfft(h, 441000), 441000)
+    ref = ref / h.abs().amax(-1, keepdim=True).clamp(1e-5)
+    assert rel_err(y, ref.float()) < TOL
+
+
+def test_pitch_shift_properties(at):
+    """SoX's output is pinned nowhere in the reference; parity = properties (ref:tests/core/test_effects.py:156-181)."""
+    sr, T = 44100, 88200
+    t = torch.arange(T) / sr
+    x = torch.stack([0.5 * torch.sin(2 * np.pi * 440 * t), 0.3 * torch.sin(2 * np.pi * 1000 * t)])[:, None, :]
+    x = x.repeat(1, 2, 1)
+    for st in (2, -2, 7):
+        sig = at.AudioSignal(x.clone(), sr).to(DEV).pitch_shift(st)
+        y = sig.audio_data.cpu()
+        assert y.shape == x.shape and sig.sample_rate == sr
+        for i, f0 in enumerate((440.0, 1000.0)):
+            spec = torch.fft.rfft(y[i, 0] * torch.hann_window(T)).abs()
+            assert abs(spec.argmax().item() * sr / T - f0 * 2 ** (st / 12)) < 2.0
+        single = at.AudioSignal(x[:1].clone(), sr).to(DEV).pitch_shift(st).audio_data.cpu()
+        assert torch.equal(single, y[:1])  # batch[0] == single
+        again = at.AudioSignal(x.clone(), sr).to(DEV).pitch_shift(st).audio_data.cpu()
+        assert torch.equal(again, y)  # deterministic
+
+
+def test_transforms_compose_matches_reference(at, golden):
+    """Compose[VolumeNorm, Equalizer, LowPass, HighPass, VolumeChange] with masks, instantiated with the
+    same seeds as the real reference (tests/golden/make_golden.py): parameters and output must agree."""
+    from audiotools_b200.data import transforms as tfm
+
+    transform = tfm.Compose(
+        [tfm.VolumeNorm(db=("uniform", -30, -16)), tfm.Equalizer(prob=0.5), tfm.LowPass(prob=0.7),
+         tfm.HighPass(prob=0.6), tfm.VolumeChange()],
+    )
+    sig = sig_of(at, "tfm")
+    kwargs = transform.batch_instantiate([10, 11, 12, 13], sig)
+    flat = at.util.flatten(kwargs)
+    ref_keys = {k[len("tfm_kw/"):] for k in golden.files if k.startswith("tfm_kw/")}
+    assert {"/".join(k) for k in flat} == ref_keys
+    for k, v in flat.items():
+        ref = golden["tfm_kw/" + "/".join(k)]
+        assert np.allclose(v.cpu().numpy(), ref), k  # seeded draws identical to the reference's
+    kwargs = at.util.prepare_batch(kwargs, DEV)
+    out = transform(sig.clone(), **kwargs)
+    assert rel_err(out.audio_data.cpu(), G(golden, "tfm_out")) < TOL
+    # same kwargs twice => same output; batch[0] == single (ref:tests/data/test_transforms.py:21-85)
+    out2 = transform(sig.clone(), **kwargs)
+    assert torch.equal(out2.audio_data, out.audio_data)
+
+
+def test_cfg4_augment_pipeline(at):
+    """BASELINE configs[3] shape: Compose[Equalizer + RoomImpulseResponse + PitchShift(+-2)] on a batch."""
+    from audiotools_b200.data import transforms as tfm
+
+    g = torch.Generator().manual_seed(9)
+    B, T, sr = 8, 88200, 44100
+    x = 0.1 * torch.randn(B, 1, T, generator=g)
+    t = torch.arange(sr) / sr
+    irs = []
+    for i in range(3):
+        h = torch.randn(1, 1, sr, generator=g) * torch.exp(-t / 0.3) * 0.1
+        h[..., 50 + i] = 1.0
+        irs.append(at.AudioSignal(h, sr))
+    transform = tfm.Compose([tfm.Equalizer(), tfm.RoomImpulseResponse(sources=irs),
+                             tfm.PitchShift(("choice", [-2, -1, 1, 2]))])
+    sig = at.AudioSignal(x.clone(), sr)
+    kwargs = transform.batch_instantiate(list(range(B)), sig)
+    sig = sig.to(DEV)
+    kwargs = at.util.prepare_batch(kwargs, DEV)
+    out = transform(sig.clone(), **kwargs)
+    assert out.audio_data.shape == (B, 1, T) and torch.isfinite(out.audio_data).all()
+    # apply_ir restores the input peak; EQ(<=0 dB cuts) + pitch shift keep the level in the same range
+    peak_in, peak_out = sig.audio_data.abs().amax(-1), out.audio_data.abs().amax(-1)
+    assert ((peak_out / peak_in) < 1.5).all() and ((peak_out / peak_in) > 0.2).all()
+    one = transform(sig[2:3].clone(), **at.util.prepare_batch(transform.batch_instantiate([2], sig[2:3].cpu()), DEV))
+    assert torch.allclose(one.audio_data, out.audio_data[2:3], atol=1e-5)

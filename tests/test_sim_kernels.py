@@ -117,3 +117,55 @@ def test_mel_variants_golden(eng, golden):
     mel = eng.spectral(x[:2], 1024, 256, sp.get_window("hann", 1024), mel_fb=fb, mel_lo=lo, mel_hi=hi,
                        want_stft=False)["mel"]
     assert rel_err(mel, torch.from_numpy(golden["cfg1_mel40_fmin_fmax"])) < 1e-5
+
+
+# ------------------------------------------------------------------------------------------
+# FIR / convolution / resample / pitch (csrc/fftconv.cu, resample.cu, pitch.cu)
+# ------------------------------------------------------------------------------------------
+def test_sinc_filters_and_equalizer_golden(eng, golden):
+    x, sr = cases.make_input("fir"), 44100
+    cut = torch.from_numpy(golden["fir_cut"])
+    assert rel_err(eng.sinc_filter(x, cut, sr, 51, False), torch.from_numpy(golden["lp_peritem"])) < 1e-5
+    assert rel_err(eng.sinc_filter(x, cut / 8, sr, 51, True), torch.from_numpy(golden["hp_peritem"])) < 1e-5
+    assert rel_err(eng.sinc_filter(x, torch.tensor(4000), sr, 51, False), torch.from_numpy(golden["lp_scalar"])) < 1e-5
+    assert rel_err(eng.equalizer(x, sr, golden["eq_db"]), torch.from_numpy(golden["eq_out"])) < 1e-5
+    assert rel_err(eng.equalizer(x, sr, golden["eq_db"][0]), torch.from_numpy(golden["eq_out_1d"])) < 1e-5
+    fb = eng.mel_filterbank(x[:1, :1], sr, 4)
+    assert fb.shape == (1, 1, 12000, 4) and rel_err(fb, torch.from_numpy(golden["fbank4"])) < 1e-5
+    with pytest.raises(ValueError):
+        eng.sinc_filter(x, torch.tensor(30000.0), sr)
+
+
+def test_circular_convolution_golden(eng, golden):
+    x, ir = cases.make_input("fir"), cases.make_ir()
+    assert rel_err(eng.circular_convolve(x, ir, True), torch.from_numpy(golden["conv_out"])) < 1e-5
+    assert rel_err(eng.circular_convolve(x, ir, False), torch.from_numpy(golden["conv_out_nomax"])) < 1e-5
+    for delay in (0, 777):  # ref:tests/core/test_effects.py:86-121: a delta IR is the identity
+        d = torch.zeros(3, 1, 1000)
+        d[..., delay] = 1.0
+        assert torch.allclose(eng.circular_convolve(x, d, True), x, atol=1e-6)
+
+
+@pytest.mark.parametrize("key,sl,old,new", [("rs_48k_16k", 24000, 48000, 16000), ("rs_44k_16k", 22050, 44100, 16000),
+                                            ("rs_16k_44k", 8000, 16000, 44100), ("rs_16k_48k", 8001, 16000, 48000),
+                                            ("rs_44k_48k", 4410, 44100, 48000)])
+def test_resample_golden(eng, golden, key, sl, old, new):
+    x = cases.make_input("rs")[..., :sl]
+    y = eng.resample(x, old, new)
+    ref = torch.from_numpy(golden[key])
+    assert y.shape == ref.shape  # floor(new*T/old), bit-exact
+    assert rel_err(y, ref) < 1e-5
+
+
+def test_pitch_shift_properties(eng):
+    sr, T = 16000, 12000
+    t = torch.arange(T) / sr
+    x = torch.stack([0.5 * torch.sin(2 * np.pi * 440 * t), 0.3 * torch.sin(2 * np.pi * 1000 * t)])[:, None, :]
+    for st in (3, -2, 12):
+        y = eng.pitch_shift(x, sr, st)
+        assert y.shape == x.shape  # length preserved exactly
+        for i, f0 in enumerate((440.0, 1000.0)):
+            spec = torch.fft.rfft(y[i, 0] * torch.hann_window(T)).abs()
+            assert abs(spec.argmax().item() * sr / T - f0 * 2 ** (st / 12)) < 4.0  # pitch ratio 2^(n/12)
+        assert torch.equal(eng.pitch_shift(x[:1], sr, st), y[:1])  # batch == per-item
+    assert torch.equal(eng.pitch_shift(x, sr, 0), x)

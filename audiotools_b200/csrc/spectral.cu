@@ -519,10 +519,10 @@ __global__ void __launch_bounds__(256, 2) spectral_warp_kernel(Params p) {
     const int ws = (n0 + p.drop_edge) * hop + p.origin + (p.row_origin ? __ldg(p.row_origin + row) : 0);
     const float g = p.gain ? __ldg(p.gain + row / p.rows_per_gain) : 1.0f;
     const float ga = fabsf(g);
-    if (t != (int)blockIdx.x) stage_span_async(p, sp, row, ws);
-    cp_async_wait_all();
+    cp_async_wait_all();  // this tile's span was issued by the previous iteration (or the prologue)
     __syncthreads();
-    if (p.y_out) writeback_scaled(p, sp, row, tile, n0, FR, ws, g);
+    if (p.y_out) writeback_scaled(p, sp, row, tile, n0, FR, ws, g);  // (sp is re-filled only after the barrier
+                                                                      //  inside the last round, below)
 
 #pragma unroll 1
     for (int rd = 0; rd < FR / G; ++rd) {
@@ -546,6 +546,17 @@ __global__ void __launch_bounds__(256, 2) spectral_warp_kernel(Params p) {
         for (int m = 0; m < 32; ++m) {
           const int e = l + LPF * m;
           z[m] = make_float2(fs[2 * e] * win[2 * e], fs[2 * e + 1] * win[2 * e + 1]);
+        }
+      }
+      if (rd == FR / G - 1) {
+        // every warp holds its last frame in registers: the span buffer is dead, so the next tile's
+        // samples stream in (cp.async) underneath this round's FFTs and mel projection
+        __syncthreads();
+        const int tn = t + gridDim.x;
+        if (tn < total_tiles) {
+          const int rown = tn / p.n_tiles, tilen = tn - rown * p.n_tiles;
+          stage_span_async(p, sp, rown,
+                           (tilen * FR + p.drop_edge) * hop + p.origin + (p.row_origin ? __ldg(p.row_origin + rown) : 0));
         }
       }
       warp_fft<LOG2N>(z, xb, tw, l);  // z[m] = Z[l + LPF m]
@@ -664,8 +675,10 @@ static int launch_warp(Params& p, void* stream) {
   const int64_t total = (int64_t)p.rows * p.n_tiles;
   B2A_REQUIRE(total < (int64_t)2147483647, B2A_E_UNSUPPORTED, "spectral: too many tiles");
   B2A_CUDA_OK(cudaFuncSetAttribute(spectral_warp_kernel<LOG2N>, cudaFuncAttributeMaxDynamicSharedMemorySize, o));
-  // persistent: as many CTAs as fit (2 per SM by registers; 1 when the shared memory is large), each loops over tiles
-  const int per_sm = (o <= 110 * 1024) ? 2 : 1;
+  // persistent: as many CTAs as are resident at once (2 per SM by registers / shared memory), each loops over tiles
+  int per_sm = 1;
+  B2A_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, spectral_warp_kernel<LOG2N>, 256, (size_t)o));
+  if (per_sm < 1) per_sm = 1;
   const int64_t cap = (int64_t)num_sms() * per_sm;
   const unsigned grid = (unsigned)(total < cap ? total : cap);
   B2A_LAUNCH(spectral_warp_kernel<LOG2N>, dim3(grid), dim3(256), (size_t)o, stream, p);

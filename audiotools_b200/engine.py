@@ -180,14 +180,14 @@ class Engine:
         shape = x.shape
         T = shape[-1]
         rows = x.numel() // T
-        taps = self._prep(taps, "taps")
+        taps = self._prep(taps.to(x.device), "taps")
         assert taps.ndim == 2
         n_filt, L = taps.shape
         if offset is not None:
-            offset = self._prep(offset.reshape(-1), "offset", torch.int32)
+            offset = self._prep(offset.reshape(-1).to(x.device), "offset", torch.int32)
             assert offset.numel() == n_filt
         if post_scale is not None:
-            post_scale = self._prep(post_scale.reshape(-1), "post_scale")
+            post_scale = self._prep(post_scale.reshape(-1).to(x.device), "post_scale")
             assert post_scale.numel() == n_filt
         mode = {"constant": 1, "replicate": 2, "circular": 3}[pad_mode]
         ws_bytes = self.lib.b2a_fftconv_workspace_bytes(rows, T, n_filt, L)

@@ -184,17 +184,16 @@ def run_ours(args):
     db = torch.tensor([TARGET_DB], device=dev)
     win = AudioSignal.get_window("hann", N_FFT, dev)
     fb, lo, hi = AudioSignal._mel_tables(SR, N_FFT, N_MELS, 0.0, None, dev)
-    gathered = torch.empty(world * B, device=dev) if world > 1 else None
-    side = torch.cuda.Stream(device=dev)
+    from audiotools_b200.parallel import LoudnessGather
+
+    gather = LoudnessGather(side_stream=torch.cuda.Stream(device=dev))  # NCCL all-gather on a side stream
     spec_events = []
 
     def step(i, timed=False):
         x = xs[i % NBUF]
         lu = eng.lufs(x, SR, target_db=db)
-        if world > 1:  # whole-batch loudness statistics: 256 B/rank all-gather on a side stream,
-            side.wait_stream(torch.cuda.current_stream())  # overlapping the spectral kernel
-            with torch.cuda.stream(side):
-                dist.all_gather_into_tensor(gathered, lu["loud"])
+        if world > 1:  # whole-batch loudness statistics: 256 B/rank all-gather, overlapping the spectral kernel
+            lu["loud_all"] = gather(lu["loud"])
         if timed:
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
@@ -204,7 +203,7 @@ def run_ours(args):
             e1.record()
             spec_events.append((e0, e1))
         if world > 1:
-            torch.cuda.current_stream().wait_stream(side)
+            gather.wait()
         return out, lu
 
     def barrier():

@@ -103,6 +103,16 @@ __device__ __forceinline__ float fast_sqrt(float v) {
 
 // Forward N-point FFT of the 32 register-resident points of a lane (element e = l + LPF m, natural
 // order in and out): radix 32, warp-private transpose through `xb`, radix LPF.
+__device__ __forceinline__ float fast_log2(float v) {
+#ifdef B2A_SIM
+  return log2f(v);
+#else
+  float r;
+  asm("lg2.approx.f32 %0, %1;" : "=f"(r) : "f"(v));  // abs error <= 2^-22: 1.4e-7 in log10 units
+  return r;
+#endif
+}
+
 template <int LOG2N>
 __device__ __forceinline__ void warp_fft(float2 (&z)[32], float* xb, const float2* tw, int l) {
   using PL = WPlan<LOG2N>;

@@ -46,6 +46,7 @@ struct Tables {
   float Mscan[5][D * D];      // A^(L*2^k)            (warp shuffle scan)
   float MwPow[NW + 1][D * D]; // A^(L*32*v), v = 0..NW (carry of warp v's total into later warps)
   float Mtile[D * D];         // A^(TILE)             (look-back across tiles)
+  float Wa[L + 2][D];         // zero-state end state of a chunk as a linear map of its 34 inputs (phase A)
 };
 
 __host__ __device__ inline size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
@@ -135,6 +136,16 @@ __global__ void lufs_setup_kernel(Coef<NS> cf, Tables<NS>* tb) {
     matmul<D>(Q, W, W);
   }
   for (int i = 0; i < D * D; ++i) tb->Mtile[i] = tb->MwPow[NW][i];
+  // Wa[j] = end state after the chunk when the only non-zero input is xs[j] = 1 (xs[0], xs[1] = history)
+  for (int j = 0; j < L + 2; ++j) {
+    double y1[NS], y2[NS];
+    for (int s = 0; s < NS; ++s) { y1[s] = 0.0; y2[s] = 0.0; }
+    for (int i = 0; i < L; ++i) {
+      const double in0 = (i + 2 == j) ? 1.0 : 0.0, in1 = (i + 1 == j) ? 1.0 : 0.0, in2 = (i == j) ? 1.0 : 0.0;
+      cascade_step<NS, double>(b0, b1, b2, a1, a2, in0, in1, in2, y1, y2);
+    }
+    for (int s = 0; s < NS; ++s) { tb->Wa[j][2 * s] = (float)y1[s]; tb->Wa[j][2 * s + 1] = (float)y2[s]; }
+  }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -184,16 +195,25 @@ kweight_energy_kernel(const float* __restrict__ x, int rows, int T, int Tp, int 
   __shared__ float s_tot[NW][D];
   __shared__ float s_c0[NW + 1][D];  // carry into warp w for a ZERO incoming tile state; [NW] = tile aggregate
   __shared__ float s_sin[D];         // incoming tile state (from the look-back)
+  __shared__ __align__(16) float s_wa[L + 2][D];
   __shared__ int s_ticket;
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  if (tid == 0) s_ticket = atomicAdd(ticket, 1);
   for (int i = tid; i < 32 * D * D; i += THREADS) (&s_mlane[0][0])[i] = (&tb->Mlane[0][0])[i];
   for (int i = tid; i < 5 * D * D; i += THREADS) (&s_mscan[0][0])[i] = (&tb->Mscan[0][0])[i];
   for (int i = tid; i < (NW + 1) * D * D; i += THREADS) (&s_mwpow[0][0])[i] = (&tb->MwPow[0][0])[i];
+  for (int i = tid; i < (L + 2) * D; i += THREADS) (&s_wa[0][0])[i] = (&tb->Wa[0][0])[i];
   if (tid < D * D) s_mt[tid] = tb->Mtile[tid];
+  const int total_tiles = rows * ntile;
+
+  // persistent CTA: tables are loaded once; tiles are claimed through a global ticket so that the tile a
+  // look-back waits for always belongs to a CTA that is already running (tile-major order)
+#pragma unroll 1
+  for (;;) {
+  if (tid == 0) s_ticket = atomicAdd(ticket, 1);
   __syncthreads();
   const int tk = s_ticket;
+  if (tk >= total_tiles) return;
   const int tile = tk / rows, row = tk - tile * rows;  // tile-major: predecessors hold smaller tickets
   const int t0 = tile * TILE;
   const float* xr = x + (size_t)row * (size_t)T;
@@ -240,7 +260,7 @@ kweight_energy_kernel(const float* __restrict__ x, int rows, int T, int Tp, int 
     }
     if (lane < D) s_sin[lane] = sin_i;
     B2A_BAR_SYNC(2, THREADS);  // S_in is ready
-    return;
+    continue;
   }
 
   // ================= worker warps
@@ -282,17 +302,15 @@ kweight_energy_kernel(const float* __restrict__ x, int rows, int T, int Tp, int 
     }
   }
 
-  // ---- phase A: zero-state response of this thread's chunk -> end state e
+  // ---- phase A: zero-state end state of this thread's chunk, e = Wa^T xs (a 34-tap linear map per state
+  //      component: the same numbers the recursion would produce, without its serial dependency)
   float g[D];
-  {
-    float y1[NS], y2[NS];
 #pragma unroll
-    for (int s = 0; s < NS; ++s) { y1[s] = 0.f; y2[s] = 0.f; }
+  for (int i = 0; i < D; ++i) g[i] = 0.f;
 #pragma unroll
-    for (int i = 0; i < L; ++i)
-      cascade_step<NS, float>(cf.b0, cf.b1, cf.b2, cf.a1, cf.a2, xs[i + 2], xs[i + 1], xs[i], y1, y2);
+  for (int j = 0; j < L + 2; ++j) {
 #pragma unroll
-    for (int s = 0; s < NS; ++s) { g[2 * s] = y1[s]; g[2 * s + 1] = y2[s]; }
+    for (int i = 0; i < D; ++i) g[i] = fmaf(s_wa[j][i], xs[j], g[i]);
   }
   // ---- inclusive affine scan over the warp's 32 chunks
 #pragma unroll
@@ -391,6 +409,7 @@ kweight_energy_kernel(const float* __restrict__ x, int rows, int T, int Tp, int 
       if (s2 < nv) atomicAdd(rb + b2, (double)a2);
     }
   }
+  }  // persistent tile loop
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -560,7 +579,12 @@ static int run(const float* x, int64_t B, int C, int64_t T, int64_t Tp, const Ge
   Tables<NS>* tb = (Tables<NS>*)(base + w.tables);
   B2A_CUDA_OK(cudaMemsetAsync(base, 0, w.zeroed_bytes, (cudaStream_t)stream));
   B2A_LAUNCH(lufs_setup_kernel<NS>, dim3(1), dim3(32), 0, stream, cf, tb);
-  B2A_LAUNCH(kweight_energy_kernel<NS>, dim3((unsigned)(rows * g.ntile)), dim3(THREADS), 0, stream, x, (int)rows,
+  int per_sm = 1, sms = B2A_NUM_SMS, dev = 0;
+  B2A_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kweight_energy_kernel<NS>, THREADS, 0));
+  if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess)
+    sms = B2A_NUM_SMS;
+  const int64_t resident = (int64_t)sms * (per_sm < 1 ? 1 : per_sm), tiles_all = rows * g.ntile;
+  B2A_LAUNCH(kweight_energy_kernel<NS>, dim3((unsigned)(tiles_all < resident ? tiles_all : resident)), dim3(THREADS), 0, stream, x, (int)rows,
              (int)T, (int)Tp, g.ntile, cf, (const Tables<NS>*)tb, (int*)(base + w.ticket),
              (unsigned long long*)(base + w.recs), (double*)(base + w.bins), g.stride, g.r, g.nbins);
   GateParams gp;

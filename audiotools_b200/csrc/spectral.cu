@@ -475,36 +475,36 @@ __global__ void __launch_bounds__(256, 2) spectral_warp_kernel(Params p) {
   }
   for (int i = tid; i < n_fft; i += 256) win[i] = __ldg(p.window + i);
   warp_fft_tables<LOG2N>(tw, ut);
-  // banded mel weights packed into shared memory: filter m -> 4-aligned band [lo4, lo4 + 4 n4), zero padded
+  // banded mel weights, lane-interleaved: lane l of a frame projects filters m = l + LPF*i (group i).  Group i
+  // stores float4 W[i][it][l], it < n4max_i (the widest 4-aligned band of the group, narrower ones zero
+  // padded): every lane of a warp reads consecutive 16 B (conflict-free) and runs the same trip count.
   const bool packed = p.mel_out && p.mel_packed_len > 0;
+  const int n_groups = (p.n_mels + LPF - 1) / LPF;
   if (packed) {
-    if (warp == 0) {  // exclusive scan of the padded widths
+    for (int m = tid; m < p.n_mels; m += 256) {
+      const int lo4 = __ldg(p.mel_lo + m) & ~3;
+      int n4 = (((__ldg(p.mel_hi + m) + 3) & ~3) - lo4) >> 2;
+      mseg[m] = make_int4(0, lo4, n4 < 0 ? 0 : n4, 0);
+    }
+    __syncthreads();
+    if (tid == 0) {  // group offsets (float4 units) and widths: a few dozen groups at most
       int run = 0;
-      for (int m0 = 0; m0 < p.n_mels; m0 += 32) {
-        const int m = m0 + lane;
-        int lo4 = 0, n4 = 0;
-        if (m < p.n_mels) {
-          lo4 = __ldg(p.mel_lo + m) & ~3;
-          n4 = (((__ldg(p.mel_hi + m) + 3) & ~3) - lo4) >> 2;
-          if (n4 < 0) n4 = 0;
-        }
-        int inc = n4;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-          const int up = __shfl_up_sync(0xffffffffu, inc, o);
-          if (lane >= o) inc += up;
-        }
-        if (m < p.n_mels) mseg[m] = make_int4(run + inc - n4, lo4, n4, 0);
-        run += __shfl_sync(0xffffffffu, inc, 31);
+      for (int i = 0; i < n_groups; ++i) {
+        int mx = 0;
+        for (int m = i * LPF; m < min((i + 1) * LPF, p.n_mels); ++m) mx = max(mx, mseg[m].z);
+        for (int m = i * LPF; m < min((i + 1) * LPF, p.n_mels); ++m) { mseg[m].x = run; mseg[m].w = mx; }
+        run += mx * LPF;
       }
     }
     __syncthreads();
     for (int m = warp; m < p.n_mels; m += 8) {
       const int4 sg = mseg[m];
+      const int lm = m % LPF;
       const float* wrow = p.mel_fb + (size_t)m * F;
-      for (int i = lane; i < 4 * sg.z; i += 32) {
+      for (int i = lane; i < 4 * sg.w; i += 32) {  // element i of the (padded) band of filter m
         const int k = sg.y + i;
-        mpk[4 * sg.x + i] = (k < F) ? __ldg(wrow + k) : 0.f;
+        const float v = (i < 4 * sg.z && k < F) ? __ldg(wrow + k) : 0.f;
+        mpk[4 * (sg.x + (i >> 2) * LPF + lm) + (i & 3)] = v;
       }
     }
   }
@@ -596,12 +596,13 @@ __global__ void __launch_bounds__(256, 2) spectral_warp_kernel(Params p) {
         for (int mm = l; mm < p.n_mels; mm += LPF) {
           float acc = 0.f;
           if (packed) {
-            const int4 sg = mseg[mm];
-            const float4* w4 = reinterpret_cast<const float4*>(mpk) + sg.x;
-            const float4* m4 = reinterpret_cast<const float4*>(xb + sg.y);
+            const int4 sg = mseg[mm];  // (group offset, lo4, n4, n4max of the group)
+            const float4* w4 = reinterpret_cast<const float4*>(mpk) + sg.x + l;
+            const int lim = PL::XB - 4;
             float a0 = 0.f, a1 = 0.f;
-            for (int i = 0; i < sg.z; ++i) {
-              const float4 w = w4[i], v = m4[i];
+            for (int i = 0; i < sg.w; ++i) {
+              const float4 w = w4[i * LPF];
+              const float4 v = *reinterpret_cast<const float4*>(xb + min(sg.y + 4 * i, lim));
               a0 = fmaf(w.x, v.x, a0); a1 = fmaf(w.y, v.y, a1);
               a0 = fmaf(w.z, v.z, a0); a1 = fmaf(w.w, v.w, a1);
             }
@@ -612,10 +613,8 @@ __global__ void __launch_bounds__(256, 2) spectral_warp_kernel(Params p) {
             for (int k = lo; k < hi; ++k) acc = fmaf(__ldg(wrow + k), xb[k], acc);
           }
           acc *= ga;
-          if (p.post == B2A_POST_LOG10) {
-            float c = fmaxf(acc, p.post_eps);
-            c = (p.post_power == 2.0f) ? c * c : powf(c, p.post_power);
-            acc = log10f(c);
+          if (p.post == B2A_POST_LOG10) {  // log10(clamp(x, eps)^power) = power * log10(2) * log2(clamp(x, eps))
+            acc = p.post_power * 0.30102999566398120f * fast_log2(fmaxf(acc, p.post_eps));
           } else if (p.post == B2A_POST_LN) {
             acc = logf(acc + p.post_eps);
           }

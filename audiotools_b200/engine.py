@@ -104,12 +104,18 @@ class Engine:
         return out
 
     # ------------------------------------------------------------------ STFT / mel
-    def _packed_len(self, mel_lo: torch.Tensor, mel_hi: torch.Tensor) -> int:
-        """Sum of the 4-aligned band widths (host int; cached per band table)."""
-        key = (mel_lo.data_ptr(), mel_hi.data_ptr(), mel_lo.numel())
+    def _packed_len(self, mel_lo: torch.Tensor, mel_hi: torch.Tensor, n_fft: int) -> int:
+        """Floats of the lane-interleaved band table of csrc/spectral.cu: filters are grouped by the LPF =
+        n_fft/64 lanes that own a frame; a group stores LPF * (widest 4-aligned band of the group) float4."""
+        key = (mel_lo.data_ptr(), mel_hi.data_ptr(), mel_lo.numel(), n_fft)
         if key not in self._packed_cache:
             lo, hi = mel_lo.cpu().numpy().astype("int64"), mel_hi.cpu().numpy().astype("int64")
-            self._packed_cache[key] = int((((hi + 3) & ~3) - (lo & ~3)).clip(min=0).sum())
+            n4 = ((((hi + 3) & ~3) - (lo & ~3)) >> 2).clip(min=0)
+            lpf = max(1, min(32, n_fft // 64))
+            total = 0
+            for i in range(0, len(n4), lpf):
+                total += int(n4[i:i + lpf].max()) * lpf
+            self._packed_cache[key] = 4 * total
         return self._packed_cache[key]
 
     def num_frames(self, T: int, n_fft: int, hop: int, pad: int = 0, right_pad: int = 0, drop_edge: int = 0) -> int:
@@ -149,7 +155,7 @@ class Engine:
             mel_lo = self._prep(mel_lo, "mel_lo", torch.int32)
             mel_hi = self._prep(mel_hi, "mel_hi", torch.int32)
             mel = torch.empty(B, C, n_mels, N, dtype=torch.float32, device=dev)
-            packed_len = self._packed_len(mel_lo, mel_hi)
+            packed_len = self._packed_len(mel_lo, mel_hi, n_fft)
         scaled = None
         rows_per_gain = 1
         if gain is not None:

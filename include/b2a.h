@@ -63,8 +63,9 @@ const char* b2a_last_error(void);
  *   mel_lo/mel_hi  [n_mels] int32: mel_fb[m, k] == 0 outside mel_lo[m] <= k < mel_hi[m]
  *            (the caller derives them from the actual non-zeros, so the banded sum equals the
  *            dense matmul exactly for ANY matrix).
- *   mel_packed_len  sum over m of (ceil4(mel_hi[m]) - floor4(mel_lo[m])): when > 0 the kernel packs
- *            the bands into shared memory once per CTA (128-bit loads); 0 reads them from global.
+ *   mel_packed_len  floats of the kernel's shared-memory band table (0: read the weights from global):
+ *            with LPF = min(32, n_fft/64) and n4[m] = (ceil4(mel_hi[m]) - floor4(mel_lo[m]))/4,
+ *            4 * LPF * sum over groups g of max(n4[g*LPF .. g*LPF+LPF-1]).
  *   mel_out  nullable [rows, n_mels, n_frames]    stft_out  nullable [rows, F, n_frames] (re,im)
  *   n_frames = 1 + (T + 2*pad + right_pad)/hop - 2*drop_edge,  F = n_fft/2 + 1
  */

@@ -43,6 +43,12 @@ int fail(int code, const char* fmt, ...);
 // launch + dynamic shared memory, CUDA vs sim
 // ---------------------------------------------------------------------------------------
 #ifdef B2A_SIM
+#define B2A_GRID_CONSTANT
+#else
+#define B2A_GRID_CONSTANT __grid_constant__
+#endif
+
+#ifdef B2A_SIM
 #define B2A_LAUNCH(kernel, grid, block, smem, stream, ...) \
   cusim::launch((grid), (block), (smem), [&] { kernel(__VA_ARGS__); })
 #define B2A_DYN_SMEM(name) unsigned char* name = cusim::ctx()->dyn_smem

@@ -86,7 +86,8 @@ struct WPlan {
   static constexpr int B1 = 32 / R1;   // pass-1 butterflies per lane
   static constexpr int NWARP = 8;
   static constexpr int G = NWARP * FPW;            // frames in flight per CTA
-  static constexpr int FR = (G >= 16) ? G : 16;    // frames per CTA
+  // frames per tile: 16, except n_fft = 2048 where 8 keeps two CTAs per SM resident (97 KB of shared memory)
+  static constexpr int FR = (G >= 16) ? G : (LOG2N == 10 ? 8 : 16);
   static constexpr int NTW = (R1 >= 2) ? B1 * (R1 - 1) : 0;
   static constexpr int XB = ((N + N / 32 + 4 + 3) / 4) * 4;  // floats per frame: padded exchange plane / |X| + 3 zeros, 16 B multiple
 };

@@ -84,10 +84,11 @@ __host__ __device__ __forceinline__ F cascade_step(const F (&b0)[NS], const F (&
 }
 
 // ---------------------------------------------------------------------------------------------
-// setup: state-transition matrix powers, float64, one thread
+// tables: state-transition matrix powers and the phase-A map, float64 on the host (a few microseconds),
+// handed to the kernel as a __grid_constant__ parameter -- no set-up launch, no device buffer
 // ---------------------------------------------------------------------------------------------
 template <int D>
-__device__ void matmul(const double* a, const double* b, double* c) {
+static void matmul(const double* a, const double* b, double* c) {
   double t[D * D];
   for (int i = 0; i < D; ++i)
     for (int j = 0; j < D; ++j) {
@@ -99,9 +100,8 @@ __device__ void matmul(const double* a, const double* b, double* c) {
 }
 
 template <int NS>
-__global__ void lufs_setup_kernel(Coef<NS> cf, Tables<NS>* tb) {
+static void build_tables(const Coef<NS>& cf, Tables<NS>* tb) {
   constexpr int D = 2 * NS;
-  if (threadIdx.x != 0 || blockIdx.x != 0) return;
   double b0[NS], b1[NS], b2[NS], a1[NS], a2[NS];
   for (int s = 0; s < NS; ++s) {
     b0[s] = cf.b0[s]; b1[s] = cf.b1[s]; b2[s] = cf.b2[s]; a1[s] = cf.a1[s]; a2[s] = cf.a2[s];
@@ -182,7 +182,7 @@ __device__ __forceinline__ float row_dot(const float* M, int i, const float* v) 
 template <int NS>
 __global__ void __launch_bounds__(THREADS, 3)
 kweight_energy_kernel(const float* __restrict__ x, int rows, int T, int Tp, int ntile, Coef<NS> cf,
-                      const Tables<NS>* __restrict__ tb, int* __restrict__ ticket,
+                      const B2A_GRID_CONSTANT Tables<NS> tbv, int* __restrict__ ticket,
                       unsigned long long* __restrict__ recs, double* __restrict__ bins, int stride, int r,
                       int nbins) {
   constexpr int D = 2 * NS;
@@ -199,6 +199,7 @@ kweight_energy_kernel(const float* __restrict__ x, int rows, int T, int Tp, int 
   __shared__ int s_ticket;
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const Tables<NS>* tb = &tbv;
   for (int i = tid; i < 32 * D * D; i += THREADS) (&s_mlane[0][0])[i] = (&tb->Mlane[0][0])[i];
   for (int i = tid; i < 5 * D * D; i += THREADS) (&s_mscan[0][0])[i] = (&tb->Mscan[0][0])[i];
   for (int i = tid; i < (NW + 1) * D * D; i += THREADS) (&s_mwpow[0][0])[i] = (&tb->MwPow[0][0])[i];
@@ -576,16 +577,16 @@ static int run(const float* x, int64_t B, int C, int64_t T, int64_t Tp, const Ge
     cf.a1[s] = (float)c[4] / a0; cf.a2[s] = (float)c[5] / a0;
   }
   char* base = (char*)ws;
-  Tables<NS>* tb = (Tables<NS>*)(base + w.tables);
+  Tables<NS> tbh;
+  build_tables<NS>(cf, &tbh);
   B2A_CUDA_OK(cudaMemsetAsync(base, 0, w.zeroed_bytes, (cudaStream_t)stream));
-  B2A_LAUNCH(lufs_setup_kernel<NS>, dim3(1), dim3(32), 0, stream, cf, tb);
   int per_sm = 1, sms = B2A_NUM_SMS, dev = 0;
   B2A_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kweight_energy_kernel<NS>, THREADS, 0));
   if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess)
     sms = B2A_NUM_SMS;
   const int64_t resident = (int64_t)sms * (per_sm < 1 ? 1 : per_sm), tiles_all = rows * g.ntile;
   B2A_LAUNCH(kweight_energy_kernel<NS>, dim3((unsigned)(tiles_all < resident ? tiles_all : resident)), dim3(THREADS), 0, stream, x, (int)rows,
-             (int)T, (int)Tp, g.ntile, cf, (const Tables<NS>*)tb, (int*)(base + w.ticket),
+             (int)T, (int)Tp, g.ntile, cf, tbh, (int*)(base + w.ticket),
              (unsigned long long*)(base + w.recs), (double*)(base + w.bins), g.stride, g.r, g.nbins);
   GateParams gp;
   for (int c = 0; c < 8; ++c) gp.G[c] = c < C ? chan_gain_h[c] : 0.0;

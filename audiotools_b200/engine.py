@@ -87,7 +87,7 @@ class Engine:
                             G.ctypes.data_as(dp), _dptr(blocks), _dptr(lufs), _dptr(loud),
                             _dptr(target_db), n_target, _dptr(gain), _dptr(ws), ws_bytes, self._stream(x))
         L.check(rc)
-        self.launches += 3  # lufs_setup, kweight_energy, lufs_gate (+ one memset node)
+        self.launches += 2  # kweight_energy, lufs_gate (+ one memset node)
         return {"lufs": lufs, "loud": loud, "gain": gain, "blocks": blocks}
 
     def gain(self, x: torch.Tensor, gain: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:

@@ -209,9 +209,11 @@ kweight_energy_kernel(const float* __restrict__ x, int rows, int T, int Tp, int 
 
   // persistent CTA: tables are loaded once; tiles are claimed through a global ticket so that the tile a
   // look-back waits for always belongs to a CTA that is already running (tile-major order)
+  // tickets 0 .. gridDim.x-1 are the CTAs' first tiles; later ones come from the global counter, fetched by
+  // the carry warp one tile ahead so that the atomic's round trip is never waited for
+  if (tid == 0) s_ticket = blockIdx.x;
 #pragma unroll 1
   for (;;) {
-  if (tid == 0) s_ticket = atomicAdd(ticket, 1);
   __syncthreads();
   const int tk = s_ticket;
   if (tk >= total_tiles) return;
@@ -223,6 +225,8 @@ kweight_energy_kernel(const float* __restrict__ x, int rows, int T, int Tp, int 
   if (warp == NW) {
     // ================= carry warp: decoupled look-back, concurrent with phase A of the workers
     // lanes [0,D): inclusive words of the predecessor, lanes [D,2D): its aggregate words
+    int next_ticket = 0;
+    if (lane == 0) next_ticket = (int)gridDim.x + atomicAdd(ticket, 1);
     float sin_i = 0.f;  // lane i < D: component i of the incoming state
     if (tile > 0) {
       float prow[D];  // lane i < D: row i of P = Mtile^j
@@ -260,7 +264,8 @@ kweight_energy_kernel(const float* __restrict__ x, int rows, int T, int Tp, int 
       }
     }
     if (lane < D) s_sin[lane] = sin_i;
-    B2A_BAR_SYNC(2, THREADS);  // S_in is ready
+    B2A_BAR_SYNC(2, THREADS);  // S_in is ready (every thread has read s_ticket long ago)
+    if (lane == 0) s_ticket = next_ticket;
     continue;
   }
 
@@ -584,7 +589,12 @@ static int run(const float* x, int64_t B, int C, int64_t T, int64_t Tp, const Ge
   B2A_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kweight_energy_kernel<NS>, THREADS, 0));
   if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess)
     sms = B2A_NUM_SMS;
-  const int64_t resident = (int64_t)sms * (per_sm < 1 ? 1 : per_sm), tiles_all = rows * g.ntile;
+#ifdef B2A_SIM
+  const int64_t resident = 1;  // the CPU simulator runs CTAs one after another: no co-resident predecessors
+#else
+  const int64_t resident = (int64_t)sms * (per_sm < 1 ? 1 : per_sm);
+#endif
+  const int64_t tiles_all = rows * g.ntile;
   B2A_LAUNCH(kweight_energy_kernel<NS>, dim3((unsigned)(tiles_all < resident ? tiles_all : resident)), dim3(THREADS), 0, stream, x, (int)rows,
              (int)T, (int)Tp, g.ntile, cf, tbh, (int*)(base + w.ticket),
              (unsigned long long*)(base + w.recs), (double*)(base + w.bins), g.stride, g.r, g.nbins);

@@ -492,6 +492,7 @@ __global__ void __launch_bounds__(256, 2) spectral_warp_kernel(Params p) {
       for (int i = 0; i < n_groups; ++i) {
         int mx = 0;
         for (int m = i * LPF; m < min((i + 1) * LPF, p.n_mels); ++m) mx = max(mx, mseg[m].z);
+        mx = (mx + 3) & ~3;  // whole groups of 4 iterations: the gather issues 8 loads, then 16 FMAs
         for (int m = i * LPF; m < min((i + 1) * LPF, p.n_mels); ++m) { mseg[m].x = run; mseg[m].w = mx; }
         run += mx * LPF;
       }
@@ -600,11 +601,18 @@ __global__ void __launch_bounds__(256, 2) spectral_warp_kernel(Params p) {
             const float4* w4 = reinterpret_cast<const float4*>(mpk) + sg.x + l;
             const int lim = PL::XB - 4;
             float a0 = 0.f, a1 = 0.f;
-            for (int i = 0; i < sg.w; ++i) {
-              const float4 w = w4[i * LPF];
-              const float4 v = *reinterpret_cast<const float4*>(xb + min(sg.y + 4 * i, lim));
-              a0 = fmaf(w.x, v.x, a0); a1 = fmaf(w.y, v.y, a1);
-              a0 = fmaf(w.z, v.z, a0); a1 = fmaf(w.w, v.w, a1);
+            for (int i = 0; i < sg.w; i += 4) {
+              float4 w[4], v[4];
+#pragma unroll
+              for (int u = 0; u < 4; ++u) {
+                w[u] = w4[(i + u) * LPF];
+                v[u] = *reinterpret_cast<const float4*>(xb + min(sg.y + 4 * (i + u), lim));
+              }
+#pragma unroll
+              for (int u = 0; u < 4; ++u) {
+                a0 = fmaf(w[u].x, v[u].x, a0); a1 = fmaf(w[u].y, v[u].y, a1);
+                a0 = fmaf(w[u].z, v[u].z, a0); a1 = fmaf(w[u].w, v[u].w, a1);
+              }
             }
             acc = a0 + a1;
           } else {

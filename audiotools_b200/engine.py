@@ -114,7 +114,7 @@ class Engine:
             lpf = max(1, min(32, n_fft // 64))
             total = 0
             for i in range(0, len(n4), lpf):
-                total += int(n4[i:i + lpf].max()) * lpf
+                total += ((int(n4[i:i + lpf].max()) + 3) & ~3) * lpf
             self._packed_cache[key] = 4 * total
         return self._packed_cache[key]
 

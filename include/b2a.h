@@ -65,7 +65,7 @@ const char* b2a_last_error(void);
  *            dense matmul exactly for ANY matrix).
  *   mel_packed_len  floats of the kernel's shared-memory band table (0: read the weights from global):
  *            with LPF = min(32, n_fft/64) and n4[m] = (ceil4(mel_hi[m]) - floor4(mel_lo[m]))/4,
- *            4 * LPF * sum over groups g of max(n4[g*LPF .. g*LPF+LPF-1]).
+ *            4 * LPF * sum over groups g of ceil4(max(n4[g*LPF .. g*LPF+LPF-1])).
  *   mel_out  nullable [rows, n_mels, n_frames]    stft_out  nullable [rows, F, n_frames] (re,im)
  *   n_frames = 1 + (T + 2*pad + right_pad)/hop - 2*drop_edge,  F = n_fft/2 + 1
  */

@@ -451,6 +451,7 @@ template <int LOG2N>
 __global__ void __launch_bounds__(256, 2) spectral_warp_kernel(Params p) {
   using PL = WPlan<LOG2N>;
   constexpr int N = PL::N, LPF = PL::LPF, FPW = PL::FPW, G = PL::G, FR = PL::FR;
+  static_assert(FR == G && FR % 8 == 0, "one round per tile: the |X| slot of a frame is its index in the tile");
   B2A_DYN_SMEM(smem);
   float* sp = reinterpret_cast<float*>(smem);
   float* win = reinterpret_cast<float*>(smem + p.off_win);   // [n_fft]
@@ -475,11 +476,12 @@ __global__ void __launch_bounds__(256, 2) spectral_warp_kernel(Params p) {
   }
   for (int i = tid; i < n_fft; i += 256) win[i] = __ldg(p.window + i);
   warp_fft_tables<LOG2N>(tw, ut);
-  // banded mel weights, lane-interleaved: lane l of a frame projects filters m = l + LPF*i (group i).  Group i
-  // stores float4 W[i][it][l], it < n4max_i (the widest 4-aligned band of the group, narrower ones zero
-  // padded): every lane of a warp reads consecutive 16 B (conflict-free) and runs the same trip count.
+  // banded mel weights in shared memory.  The projection runs once per tile, AFTER the tile's FFTs, with the
+  // work transposed: lane (f, j) of warp w handles frame f (8 at a time) and filter m = w + 8*(4*i + j) in
+  // step i, so one 128-bit weight load is broadcast to 8 frames and the |X| loads of the 8 frames interleave
+  // conflict-free.  Row m = its 4-aligned band [lo4, lo4 + 4*n4), zero padded to the widest of the 4 filters
+  // of its (warp, step) so that all lanes of a warp run the same trip count.
   const bool packed = p.mel_out && p.mel_packed_len > 0;
-  const int n_groups = (p.n_mels + LPF - 1) / LPF;
   if (packed) {
     for (int m = tid; m < p.n_mels; m += 256) {
       const int lo4 = __ldg(p.mel_lo + m) & ~3;
@@ -487,25 +489,25 @@ __global__ void __launch_bounds__(256, 2) spectral_warp_kernel(Params p) {
       mseg[m] = make_int4(0, lo4, n4 < 0 ? 0 : n4, 0);
     }
     __syncthreads();
-    if (tid == 0) {  // group offsets (float4 units) and widths: a few dozen groups at most
+    if (tid == 0) {  // offsets (float4 units) and padded widths
       int run = 0;
-      for (int i = 0; i < n_groups; ++i) {
-        int mx = 0;
-        for (int m = i * LPF; m < min((i + 1) * LPF, p.n_mels); ++m) mx = max(mx, mseg[m].z);
-        mx = (mx + 3) & ~3;  // whole groups of 4 iterations: the gather issues 8 loads, then 16 FMAs
-        for (int m = i * LPF; m < min((i + 1) * LPF, p.n_mels); ++m) { mseg[m].x = run; mseg[m].w = mx; }
-        run += mx * LPF;
-      }
+      for (int w = 0; w < 8; ++w)
+        for (int i = 0; w + 32 * i < p.n_mels; ++i) {
+          int mx = 0;
+          for (int j = 0; j < 4; ++j) { const int m = w + 8 * (4 * i + j); if (m < p.n_mels) mx = max(mx, mseg[m].z); }
+          for (int j = 0; j < 4; ++j) {
+            const int m = w + 8 * (4 * i + j);
+            if (m < p.n_mels) { mseg[m].x = run; mseg[m].w = mx; run += mx; }
+          }
+        }
     }
     __syncthreads();
     for (int m = warp; m < p.n_mels; m += 8) {
       const int4 sg = mseg[m];
-      const int lm = m % LPF;
       const float* wrow = p.mel_fb + (size_t)m * F;
-      for (int i = lane; i < 4 * sg.w; i += 32) {  // element i of the (padded) band of filter m
+      for (int i = lane; i < 4 * sg.w; i += 32) {
         const int k = sg.y + i;
-        const float v = (i < 4 * sg.z && k < F) ? __ldg(wrow + k) : 0.f;
-        mpk[4 * (sg.x + (i >> 2) * LPF + lm) + (i & 3)] = v;
+        mpk[4 * sg.x + i] = (i < 4 * sg.z && k < F) ? __ldg(wrow + k) : 0.f;
       }
     }
   }
@@ -592,44 +594,47 @@ __global__ void __launch_bounds__(256, 2) spectral_warp_kernel(Params p) {
       }
       __syncwarp();
 
-      // ---- banded mel projection (x |gain|: the projection is linear) + post-op
-      if (p.mel_out) {
-        for (int mm = l; mm < p.n_mels; mm += LPF) {
-          float acc = 0.f;
-          if (packed) {
-            const int4 sg = mseg[mm];  // (group offset, lo4, n4, n4max of the group)
-            const float4* w4 = reinterpret_cast<const float4*>(mpk) + sg.x + l;
-            const int lim = PL::XB - 4;
-            float a0 = 0.f, a1 = 0.f;
-            for (int i = 0; i < sg.w; i += 4) {
-              float4 w[4], v[4];
-#pragma unroll
-              for (int u = 0; u < 4; ++u) {
-                w[u] = w4[(i + u) * LPF];
-                v[u] = *reinterpret_cast<const float4*>(xb + min(sg.y + 4 * (i + u), lim));
+    }
+
+    // ---- mel phase of the tile: |X| of all FR frames sit in the xb slots (slot = frame within the tile)
+    if (p.mel_out) {
+      __syncthreads();
+      const int fl = lane & 7, jq = lane >> 3;
+      const int lim = PL::XB - 4;
+      for (int fc = 0; fc < FR; fc += 8) {
+        const int f = fc + fl;
+        const float* xf = xbs + f * PL::XB;
+        for (int i = 0; warp + 32 * i < p.n_mels; ++i) {
+          const int mm = warp + 8 * (4 * i + jq);
+          if (mm < p.n_mels) {
+            float acc = 0.f;
+            if (packed) {
+              const int4 sg = mseg[mm];  // (row offset, lo4, own n4, padded n4)
+              const float4* w4 = reinterpret_cast<const float4*>(mpk) + sg.x;
+              float a0 = 0.f, a1 = 0.f;
+#pragma unroll 2
+              for (int it = 0; it < sg.w; ++it) {
+                const float4 w = w4[it];
+                const float4 v = *reinterpret_cast<const float4*>(xf + min(sg.y + 4 * it, lim));
+                a0 = fmaf(w.x, v.x, a0); a1 = fmaf(w.y, v.y, a1);
+                a0 = fmaf(w.z, v.z, a0); a1 = fmaf(w.w, v.w, a1);
               }
-#pragma unroll
-              for (int u = 0; u < 4; ++u) {
-                a0 = fmaf(w[u].x, v[u].x, a0); a1 = fmaf(w[u].y, v[u].y, a1);
-                a0 = fmaf(w[u].z, v[u].z, a0); a1 = fmaf(w[u].w, v[u].w, a1);
-              }
+              acc = a0 + a1;
+            } else {
+              const int lo = __ldg(p.mel_lo + mm), hi = __ldg(p.mel_hi + mm);
+              const float* wrow = p.mel_fb + (size_t)mm * F;
+              for (int k = lo; k < hi; ++k) acc = fmaf(__ldg(wrow + k), xf[k], acc);
             }
-            acc = a0 + a1;
-          } else {
-            const int lo = __ldg(p.mel_lo + mm), hi = __ldg(p.mel_hi + mm);
-            const float* wrow = p.mel_fb + (size_t)mm * F;
-            for (int k = lo; k < hi; ++k) acc = fmaf(__ldg(wrow + k), xb[k], acc);
+            acc *= ga;
+            if (p.post == B2A_POST_LOG10) {  // log10(clamp(x, eps)^power) = power * log10(2) * log2(clamp(x, eps))
+              acc = p.post_power * 0.30102999566398120f * fast_log2(fmaxf(acc, p.post_eps));
+            } else if (p.post == B2A_POST_LN) {
+              acc = logf(acc + p.post_eps);
+            }
+            melt[mm * (FR + 1) + f] = acc;
           }
-          acc *= ga;
-          if (p.post == B2A_POST_LOG10) {  // log10(clamp(x, eps)^power) = power * log10(2) * log2(clamp(x, eps))
-            acc = p.post_power * 0.30102999566398120f * fast_log2(fmaxf(acc, p.post_eps));
-          } else if (p.post == B2A_POST_LN) {
-            acc = logf(acc + p.post_eps);
-          }
-          melt[mm * (FR + 1) + f] = acc;
         }
       }
-      __syncwarp();
     }
 
     __syncthreads();  // all frames of the tile are done: melt complete, sp free for the next tile

@@ -105,16 +105,19 @@ class Engine:
 
     # ------------------------------------------------------------------ STFT / mel
     def _packed_len(self, mel_lo: torch.Tensor, mel_hi: torch.Tensor, n_fft: int) -> int:
-        """Floats of the lane-interleaved band table of csrc/spectral.cu: filters are grouped by the LPF =
-        n_fft/64 lanes that own a frame; a group stores LPF * (widest 4-aligned band of the group) float4."""
-        key = (mel_lo.data_ptr(), mel_hi.data_ptr(), mel_lo.numel(), n_fft)
+        """Floats of the shared-memory band table of csrc/spectral.cu: row m is filter m's 4-aligned band, padded
+        to the widest of the (up to) 4 filters {w + 8*(4i + j), j < 4} that warp w = m % 8 projects in step i."""
+        key = (mel_lo.data_ptr(), mel_hi.data_ptr(), mel_lo.numel())
         if key not in self._packed_cache:
             lo, hi = mel_lo.cpu().numpy().astype("int64"), mel_hi.cpu().numpy().astype("int64")
             n4 = ((((hi + 3) & ~3) - (lo & ~3)) >> 2).clip(min=0)
-            lpf = max(1, min(32, n_fft // 64))
-            total = 0
-            for i in range(0, len(n4), lpf):
-                total += ((int(n4[i:i + lpf].max()) + 3) & ~3) * lpf
+            n, total = len(n4), 0
+            for w in range(8):
+                i = 0
+                while w + 32 * i < n:
+                    grp = [w + 8 * (4 * i + j) for j in range(4) if w + 8 * (4 * i + j) < n]
+                    total += int(max(n4[m] for m in grp)) * len(grp)
+                    i += 1
             self._packed_cache[key] = 4 * total
         return self._packed_cache[key]
 

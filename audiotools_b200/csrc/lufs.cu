@@ -171,6 +171,48 @@ __device__ __forceinline__ unsigned long long rec_load(const unsigned long long*
 #endif
 }
 
+// cp.async (16 B) global -> shared; plain copy under the CPU simulator
+__device__ __forceinline__ void cp_async16(float* smem_dst, const float* gmem_src) {
+#ifdef B2A_SIM
+  *reinterpret_cast<float4*>(smem_dst) = *reinterpret_cast<const float4*>(gmem_src);
+#else
+  const unsigned sa = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(gmem_src) : "memory");
+#endif
+}
+__device__ __forceinline__ void cp_async_wait_all() {
+#ifndef B2A_SIM
+  asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
+#endif
+}
+
+// Stage tile `tk` of the ticket order into sx (32-sample chunks of CH words) and its 2 history samples into
+// hist.  Called by the WORKERS threads only.  Interior, 16 B aligned tiles go through cp.async (no registers,
+// completes in the background); the others (row tails, unaligned rows) through plain loads.
+__device__ __forceinline__ void stage_tile(const float* __restrict__ x, int tk, int rows, int T, float* sx,
+                                           float* hist, int tid) {
+  const int tile = tk / rows, row = tk - tile * rows;
+  const int t0 = tile * TILE;
+  const float* xr = x + (size_t)row * (size_t)T;
+  if ((t0 + TILE <= T) && ((((uintptr_t)(xr + t0)) & 15) == 0)) {
+#pragma unroll
+    for (int i = 0; i < L / 4; ++i) {
+      const int v = tid + WORKERS * i;  // float4 index within the tile
+      cp_async16(&sx[CH * (v >> 3) + 4 * (v & 7)], xr + t0 + 4 * v);
+    }
+  } else {
+#pragma unroll 4
+    for (int pp = tid; pp < TILE; pp += WORKERS) {
+      const int n = t0 + pp;
+      sx[CH * (pp >> 5) + (pp & 31)] = (n < T) ? __ldg(xr + n) : 0.f;
+    }
+  }
+  if (tid < 2) {
+    const int n = t0 - 2 + tid;
+    hist[tid] = (n >= 0 && n < T) ? __ldg(xr + n) : 0.f;
+  }
+}
+
 template <int D>
 __device__ __forceinline__ float row_dot(const float* M, int i, const float* v) {
   float a = 0.f;
@@ -187,7 +229,7 @@ kweight_energy_kernel(const float* __restrict__ x, int rows, int T, int Tp, int 
                       int nbins) {
   constexpr int D = 2 * NS;
   __shared__ __align__(16) float sx[WORKERS * CH];
-  __shared__ float s_hist[2];
+  __shared__ float s_hist[2][2];   // history samples of the current / prefetched tile
   __shared__ float s_mlane[32][D * D];
   __shared__ float s_mscan[5][D * D];
   __shared__ float s_mwpow[NW + 1][D * D];
@@ -196,7 +238,7 @@ kweight_energy_kernel(const float* __restrict__ x, int rows, int T, int Tp, int 
   __shared__ float s_c0[NW + 1][D];  // carry into warp w for a ZERO incoming tile state; [NW] = tile aggregate
   __shared__ float s_sin[D];         // incoming tile state (from the look-back)
   __shared__ __align__(16) float s_wa[L + 2][D];
-  __shared__ int s_ticket;
+  __shared__ int s_cur, s_next;    // ticket of this tile and of the next one (its samples are prefetched)
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const Tables<NS>* tb = &tbv;
@@ -208,25 +250,32 @@ kweight_energy_kernel(const float* __restrict__ x, int rows, int T, int Tp, int 
   const int total_tiles = rows * ntile;
 
   // persistent CTA: tables are loaded once; tiles are claimed through a global ticket so that the tile a
-  // look-back waits for always belongs to a CTA that is already running (tile-major order)
-  // tickets 0 .. gridDim.x-1 are the CTAs' first tiles; later ones come from the global counter, fetched by
-  // the carry warp one tile ahead so that the atomic's round trip is never waited for
-  if (tid == 0) s_ticket = blockIdx.x;
-#pragma unroll 1
-  for (;;) {
+  // look-back waits for always belongs to a CTA that is already running (tile-major order).  Tickets
+  // 0 .. gridDim.x-1 are the CTAs' first tiles; later ones come from the global counter.  The carry warp fetches
+  // tickets TWO tiles ahead, so the next tile is always known and its samples stream in (cp.async) underneath
+  // the current tile's phases A/B -- the staging buffer is dead once every worker holds its chunk in registers.
+  if (tid == 0) {
+    s_cur = blockIdx.x;
+    s_next = (int)gridDim.x + atomicAdd(ticket, 1);
+  }
   __syncthreads();
-  const int tk = s_ticket;
+  if (warp < NW && s_cur < total_tiles) stage_tile(x, s_cur, rows, T, sx, s_hist[0], tid);
+  int par = 0;  // which history slot belongs to the current tile
+#pragma unroll 1
+  for (;; par ^= 1) {
+  cp_async_wait_all();
+  __syncthreads();
+  const int tk = s_cur, nxt = s_next;
   if (tk >= total_tiles) return;
   const int tile = tk / rows, row = tk - tile * rows;  // tile-major: predecessors hold smaller tickets
   const int t0 = tile * TILE;
-  const float* xr = x + (size_t)row * (size_t)T;
   unsigned long long* myrec = recs + ((size_t)tile * rows + row) * (2 * D);
 
   if (warp == NW) {
     // ================= carry warp: decoupled look-back, concurrent with phase A of the workers
     // lanes [0,D): inclusive words of the predecessor, lanes [D,2D): its aggregate words
-    int next_ticket = 0;
-    if (lane == 0) next_ticket = (int)gridDim.x + atomicAdd(ticket, 1);
+    int ticket2 = 0;  // two tiles ahead; its round trip overlaps the look-back
+    if (lane == 0) ticket2 = (int)gridDim.x + atomicAdd(ticket, 1);
     float sin_i = 0.f;  // lane i < D: component i of the incoming state
     if (tile > 0) {
       float prow[D];  // lane i < D: row i of P = Mtile^j
@@ -264,34 +313,12 @@ kweight_energy_kernel(const float* __restrict__ x, int rows, int T, int Tp, int 
       }
     }
     if (lane < D) s_sin[lane] = sin_i;
-    B2A_BAR_SYNC(2, THREADS);  // S_in is ready (every thread has read s_ticket long ago)
-    if (lane == 0) s_ticket = next_ticket;
+    B2A_BAR_SYNC(2, THREADS);  // S_in is ready (every thread has read s_cur / s_next long ago)
+    if (lane == 0) { s_cur = nxt; s_next = ticket2; }
     continue;
   }
 
-  // ================= worker warps
-  // stage x[t0 .. t0+TILE) as 32-sample chunks of CH words (+2 samples of history)
-  const bool fast_stage = (t0 + TILE <= T) && ((((uintptr_t)(xr + t0)) & 15) == 0);
-  if (fast_stage) {
-#pragma unroll
-    for (int i = 0; i < L / 4; ++i) {
-      const int v = tid + WORKERS * i;  // float4 index within the tile
-      const float4 q = ld_stream4(xr + t0 + 4 * v);
-      *reinterpret_cast<float4*>(&sx[CH * (v >> 3) + 4 * (v & 7)]) = q;
-    }
-  } else {
-#pragma unroll 4
-    for (int pp = tid; pp < TILE; pp += WORKERS) {
-      const int n = t0 + pp;
-      sx[CH * (pp >> 5) + (pp & 31)] = (n < T) ? __ldg(xr + n) : 0.f;
-    }
-  }
-  if (tid < 2) {
-    const int n = t0 - 2 + tid;
-    s_hist[tid] = (n >= 0 && n < T) ? __ldg(xr + n) : 0.f;
-  }
-  B2A_BAR_SYNC(1, WORKERS);
-
+  // ================= worker warps: this tile's samples are already in sx (prologue / previous iteration)
   float xs[L + 2];
   {
     const float4* c4 = reinterpret_cast<const float4*>(&sx[CH * tid]);
@@ -301,12 +328,14 @@ kweight_energy_kernel(const float* __restrict__ x, int rows, int T, int Tp, int 
       xs[2 + 4 * i] = q.x; xs[3 + 4 * i] = q.y; xs[4 + 4 * i] = q.z; xs[5 + 4 * i] = q.w;
     }
     if (tid == 0) {
-      xs[0] = s_hist[0]; xs[1] = s_hist[1];
+      xs[0] = s_hist[par][0]; xs[1] = s_hist[par][1];
     } else {
       const float2 h = *reinterpret_cast<const float2*>(&sx[CH * (tid - 1) + 30]);
       xs[0] = h.x; xs[1] = h.y;
     }
   }
+  B2A_BAR_SYNC(1, WORKERS);  // every worker holds its chunk: sx is free
+  if (nxt < total_tiles) stage_tile(x, nxt, rows, T, sx, s_hist[par ^ 1], tid);  // lands under phases A / B
 
   // ---- phase A: zero-state end state of this thread's chunk, e = Wa^T xs (a 34-tap linear map per state
   //      component: the same numbers the recursion would produce, without its serial dependency)

@@ -89,7 +89,9 @@ struct WPlan {
   // frames per tile: 16, except n_fft = 2048 where 8 keeps two CTAs per SM resident (97 KB of shared memory)
   static constexpr int FR = (G >= 16) ? G : (LOG2N == 10 ? 8 : 16);
   static constexpr int NTW = (R1 >= 2) ? B1 * (R1 - 1) : 0;
-  static constexpr int XB = ((N + N / 32 + 4 + 3) / 4) * 4;  // floats per frame: padded exchange plane / |X| + 3 zeros, 16 B multiple
+  // floats per frame slot (16 B multiple): the padded exchange plane, later |X| (N+1 values + 3 zeros) plus
+  // slack that the zero-weight tail of a padded mel band may read
+  static constexpr int XB = ((N + N / 32 + 4 + 3) / 4) * 4 + (N >= 256 ? 128 : 32);
 };
 
 __device__ __forceinline__ float fast_sqrt(float v) {

@@ -475,6 +475,7 @@ __global__ void __launch_bounds__(256, 2) spectral_warp_kernel(Params p) {
     stage_span_async(p, sp, row, (tile * FR + p.drop_edge) * hop + p.origin + (p.row_origin ? __ldg(p.row_origin + row) : 0));
   }
   for (int i = tid; i < n_fft; i += 256) win[i] = __ldg(p.window + i);
+  for (int i = tid; i < G * PL::XB; i += 256) xbs[i] = 0.f;  // the slack behind each |X| slot must stay finite (0 x w)
   warp_fft_tables<LOG2N>(tw, ut);
   // banded mel weights in shared memory.  The projection runs once per tile, AFTER the tile's FFTs, with the
   // work transposed: lane (f, j) of warp w handles frame f (8 at a time) and filter m = w + 8*(4*i + j) in
@@ -482,6 +483,7 @@ __global__ void __launch_bounds__(256, 2) spectral_warp_kernel(Params p) {
   // conflict-free.  Row m = its 4-aligned band [lo4, lo4 + 4*n4), zero padded to the widest of the 4 filters
   // of its (warp, step) so that all lanes of a warp run the same trip count.
   const bool packed = p.mel_out && p.mel_packed_len > 0;
+  __shared__ int s_clamp;
   if (packed) {
     for (int m = tid; m < p.n_mels; m += 256) {
       const int lo4 = __ldg(p.mel_lo + m) & ~3;
@@ -490,16 +492,17 @@ __global__ void __launch_bounds__(256, 2) spectral_warp_kernel(Params p) {
     }
     __syncthreads();
     if (tid == 0) {  // offsets (float4 units) and padded widths
-      int run = 0;
+      int run = 0, reach = 0;
       for (int w = 0; w < 8; ++w)
         for (int i = 0; w + 32 * i < p.n_mels; ++i) {
           int mx = 0;
           for (int j = 0; j < 4; ++j) { const int m = w + 8 * (4 * i + j); if (m < p.n_mels) mx = max(mx, mseg[m].z); }
           for (int j = 0; j < 4; ++j) {
             const int m = w + 8 * (4 * i + j);
-            if (m < p.n_mels) { mseg[m].x = run; mseg[m].w = mx; run += mx; }
+            if (m < p.n_mels) { mseg[m].x = run; mseg[m].w = mx; run += mx; reach = max(reach, mseg[m].y + 4 * mx); }
           }
         }
+      s_clamp = reach > PL::XB;  // a zero-padded row would read past its frame's |X| slot: clamp the index
     }
     __syncthreads();
     for (int m = warp; m < p.n_mels; m += 8) {
@@ -600,37 +603,61 @@ __global__ void __launch_bounds__(256, 2) spectral_warp_kernel(Params p) {
     if (p.mel_out) {
       __syncthreads();
       const int fl = lane & 7, jq = lane >> 3;
-      const int lim = PL::XB - 4;
-      for (int fc = 0; fc < FR; fc += 8) {
-        const int f = fc + fl;
-        const float* xf = xbs + f * PL::XB;
-        for (int i = 0; warp + 32 * i < p.n_mels; ++i) {
-          const int mm = warp + 8 * (4 * i + jq);
-          if (mm < p.n_mels) {
-            float acc = 0.f;
-            if (packed) {
-              const int4 sg = mseg[mm];  // (row offset, lo4, own n4, padded n4)
-              const float4* w4 = reinterpret_cast<const float4*>(mpk) + sg.x;
-              float a0 = 0.f, a1 = 0.f;
-#pragma unroll 2
+      const float lscale = p.post_power * 0.30102999566398120f;  // log10(c^power) = power * log10(2) * log2(c)
+      if (packed) {
+        const float4* mpk4 = reinterpret_cast<const float4*>(mpk);
+        for (int fc = 0; fc < FR; fc += 8) {
+          const int f = fc + fl;
+          const float* xf = xbs + f * PL::XB;
+          for (int mm = warp + 8 * jq; mm < p.n_mels; mm += 32) {
+            const int4 sg = mseg[mm];  // (row offset, lo4, own n4, padded n4: the same for the 4 filters of a step)
+            const float4* w4 = mpk4 + sg.x;
+            float a0 = 0.f, a1 = 0.f;
+            if (!s_clamp) {  // the padded rows stay inside the frame's |X| slot: straight-line 4-wide groups
+              const float4* v4 = reinterpret_cast<const float4*>(xf + sg.y);
+              int it = 0;
+              for (; it + 4 <= sg.w; it += 4) {
+                float4 w[4], v[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) { w[u] = w4[it + u]; v[u] = v4[it + u]; }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                  a0 = fmaf(w[u].x, v[u].x, a0); a1 = fmaf(w[u].y, v[u].y, a1);
+                  a0 = fmaf(w[u].z, v[u].z, a0); a1 = fmaf(w[u].w, v[u].w, a1);
+                }
+              }
+              for (; it < sg.w; ++it) {
+                const float4 w = w4[it], v = v4[it];
+                a0 = fmaf(w.x, v.x, a0); a1 = fmaf(w.y, v.y, a1);
+                a0 = fmaf(w.z, v.z, a0); a1 = fmaf(w.w, v.w, a1);
+              }
+            } else {
+              const int lim = PL::XB - 4;
               for (int it = 0; it < sg.w; ++it) {
                 const float4 w = w4[it];
                 const float4 v = *reinterpret_cast<const float4*>(xf + min(sg.y + 4 * it, lim));
                 a0 = fmaf(w.x, v.x, a0); a1 = fmaf(w.y, v.y, a1);
                 a0 = fmaf(w.z, v.z, a0); a1 = fmaf(w.w, v.w, a1);
               }
-              acc = a0 + a1;
-            } else {
-              const int lo = __ldg(p.mel_lo + mm), hi = __ldg(p.mel_hi + mm);
-              const float* wrow = p.mel_fb + (size_t)mm * F;
-              for (int k = lo; k < hi; ++k) acc = fmaf(__ldg(wrow + k), xf[k], acc);
             }
+            float acc = (a0 + a1) * ga;
+            if (p.post == B2A_POST_LOG10) acc = lscale * fast_log2(fmaxf(acc, p.post_eps));
+            else if (p.post == B2A_POST_LN) acc = logf(acc + p.post_eps);
+            melt[mm * (FR + 1) + f] = acc;
+          }
+        }
+      } else {  // band table does not fit in shared memory: weights from global
+        for (int fc = 0; fc < FR; fc += 8) {
+          const int f = fc + fl;
+          const float* xf = xbs + f * PL::XB;
+          for (int mm = warp + 8 * jq; mm < p.n_mels; mm += 32) {
+            const int lo = __ldg(p.mel_lo + mm), hi = __ldg(p.mel_hi + mm);
+            const float* wrow = p.mel_fb + (size_t)mm * F;
+            float acc = 0.f;
+            for (int k = lo; k < hi; ++k) acc = fmaf(__ldg(wrow + k), xf[k], acc);
             acc *= ga;
-            if (p.post == B2A_POST_LOG10) {  // log10(clamp(x, eps)^power) = power * log10(2) * log2(clamp(x, eps))
-              acc = p.post_power * 0.30102999566398120f * fast_log2(fmaxf(acc, p.post_eps));
-            } else if (p.post == B2A_POST_LN) {
-              acc = logf(acc + p.post_eps);
-            }
+            if (p.post == B2A_POST_LOG10) acc = lscale * fast_log2(fmaxf(acc, p.post_eps));
+            else if (p.post == B2A_POST_LN) acc = logf(acc + p.post_eps);
             melt[mm * (FR + 1) + f] = acc;
           }
         }

@@ -1,0 +1,128 @@
+#!/usr/bin/env python
+"""bench_configs.py -- auxiliary measurements of the OTHER BASELINE.json configs (the contract bench is
+bench.py, which measures configs[1]).  One JSON line per config: device-resident throughput (CUDA events,
+>= 3 warm-ups, inputs larger than L2 or rotated), algorithmic bytes, and the CPU oracle on a bounded sample.
+
+    python bench_configs.py [--only cfg1,cfg3,cfg4] [--no-cpu]
+"""
+import argparse
+import json
+import os
+import sys
+import time
+
+import numpy as np
+import torch
+
+REPO = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, REPO)
+
+
+def timed(fn, warmup=3, steps=10):
+    for _ in range(warmup):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / steps  # ms
+
+
+def cpu_time(fn, reps=2):
+    fn()
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        fn()
+    return (time.perf_counter() - t0) / reps
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--only", default="cfg1,cfg3,cfg4")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    import __graft_entry__ as graft
+
+    graft.build()
+    from audiotools_b200 import AudioSignal
+    from audiotools_b200.data import transforms as tfm
+    from oracle import signal_path as sp
+
+    dev = "cuda:0"
+    peak = 6576.1
+    pp = os.path.join(REPO, "MEASURED_PEAKS.json")
+    if os.path.exists(pp):
+        peak = float(json.load(open(pp))["hbm_gbs"])
+    torch.set_num_threads(os.cpu_count() or 1)
+    only = set(args.only.split(","))
+
+    if "cfg1" in only:  # batch=4 mono 1s@16kHz stft(512,128): launch-latency bound
+        x = torch.randn(4, 1, 16000, generator=torch.Generator().manual_seed(0))
+        sig = AudioSignal(x.clone(), 16000).to(dev)
+        ms = timed(lambda: sig.stft(window_length=512, hop_length=128), steps=50)
+        line = {"config": "cfg1 batch=4 mono 1s@16k stft(512,128)", "ms": ms, "clips_per_s": 4 / ms * 1e3,
+                "alg_bytes": 64000 + 1036224}
+        if not args.no_cpu:
+            line["cpu_ms"] = 1e3 * cpu_time(lambda: sp.stft(x, 16000, 512, 128), reps=20)
+        print(json.dumps(line))
+
+    if "cfg3" in only:  # batch=256 mono 30s@48k -> 16k polyphase resample + low_pass(8k)
+        B = 256
+        g = torch.Generator().manual_seed(0)
+        x = (0.1 * torch.randn(B, 1, 1440000, generator=g)).to(dev)  # 1.47 GB > L2
+
+        def run():
+            s = AudioSignal(x, 48000)
+            s.resample(16000)
+            s.low_pass(8000)
+            return s
+
+        ms_rs = timed(lambda: AudioSignal(x, 48000).resample(16000), steps=5)
+        ms = timed(run, steps=5)
+        alg = B * (5760000 + 1920000) + B * 2 * 1920000
+        line = {"config": "cfg3 batch=256 mono 30s@48k resample->16k + low_pass(8k)", "ms": ms, "ms_resample": ms_rs,
+                "clips_per_s": B / ms * 1e3, "alg_bytes": alg, "achieved_GBps": alg / ms / 1e6,
+                "frac_of_hbm_peak": alg / ms / 1e6 / peak}
+        if not args.no_cpu:
+            xc = x[:8].cpu()
+            t = cpu_time(lambda: sp.low_pass(sp.resample(xc, 48000, 16000), 16000, 8000), reps=1)
+            line["cpu_clips_per_s"] = 8 / t
+        print(json.dumps(line))
+        del x
+
+    if "cfg4" in only:  # batch=512 Compose[EQ + IR-convolve + pitch_shift +-2], mono 10s@44.1k (one GPU's share: 128)
+        B, T, sr = 128, 441000, 44100
+        g = torch.Generator().manual_seed(0)
+        x = 0.1 * torch.randn(B, 1, T, generator=g)
+        t = torch.arange(sr) / sr
+        irs = []
+        for i in range(8):
+            h = torch.randn(1, 1, sr, generator=g) * torch.exp(-t / 0.3) * 0.1
+            h[..., 40 + i] = 1.0
+            irs.append(AudioSignal(h, sr))
+        transform = tfm.Compose([tfm.Equalizer(), tfm.RoomImpulseResponse(sources=irs),
+                                 tfm.PitchShift(("choice", [-2, 2]))])
+        sig = AudioSignal(x, sr)
+        kwargs = transform.batch_instantiate(list(range(B)), sig)
+        sig = sig.to(dev)
+        from audiotools_b200 import util
+
+        kwargs = util.prepare_batch(kwargs, dev)
+        ms = timed(lambda: transform(sig.clone(), **kwargs), warmup=2, steps=3)
+        per = {}
+        for name, fn in [("equalizer", lambda: sig.clone().equalizer(kwargs["Compose"]["0.Equalizer"]["eq"])),
+                         ("apply_ir", lambda: sig.clone().apply_ir(kwargs["Compose"]["1.RoomImpulseResponse"]["ir_signal"].clone(),
+                                                                   kwargs["Compose"]["1.RoomImpulseResponse"]["drr"],
+                                                                   kwargs["Compose"]["1.RoomImpulseResponse"]["eq"])),
+                         ("pitch_shift", lambda: sig.clone().pitch_shift(2))]:
+            per[name] = timed(fn, warmup=1, steps=3)
+        line = {"config": f"cfg4 per-GPU share batch={B} mono 10s@44.1k Compose[EQ+RoomIR+PitchShift+-2]", "ms": ms,
+                "clips_per_s": B / ms * 1e3, "ms_parts": per}
+        print(json.dumps(line))
+
+
+if __name__ == "__main__":
+    main()

@@ -212,6 +212,28 @@ class Engine:
         self.launches += 2 + 4 * nchunk
         return out
 
+    DIRECT_FIR_MAX_TAPS = 320  # longer filters are cheaper through the FFT engine
+
+    def fir_direct(self, x: torch.Tensor, taps: torch.Tensor, rows_per_filt: int, left: Optional[torch.Tensor] = None,
+                   left0: int = 0, stride: int = 1, out_len: Optional[int] = None, pad_mode: str = "replicate",
+                   subtract_from_input: bool = False) -> torch.Tensor:
+        """``out[row, m] = sum_k taps[f, k] * xv[row, m*stride + k - left0 - left[f]]`` (correlation form)."""
+        x = self._prep(x, "x")
+        T = x.shape[-1]
+        rows = x.numel() // T
+        taps = self._prep(taps.to(x.device), "taps")
+        n_filt, K = taps.shape
+        if left is not None:
+            left = self._prep(left.reshape(-1).to(x.device), "left", torch.int32)
+        out_len = T if out_len is None else int(out_len)
+        out = torch.empty(*x.shape[:-1], out_len, dtype=torch.float32, device=x.device)
+        rc = self.lib.b2a_fir_direct_f32(_dptr(x), rows, T, _dptr(taps), n_filt, K, int(rows_per_filt), _dptr(left),
+                                         int(left0), int(stride), out_len, {"constant": 1, "replicate": 2}[pad_mode],
+                                         int(bool(subtract_from_input)), _dptr(out), self._stream(x))
+        self.lib.check(rc)
+        self.launches += 1
+        return out
+
     @staticmethod
     def _sinc(x: torch.Tensor) -> torch.Tensor:
         return torch.where(x == 0, torch.ones_like(x), torch.sin(x) / x)
@@ -264,6 +286,11 @@ class Engine:
             raise ValueError("cutoff 0: julius.LowPassFilter has no positive cutoff to size the filter from")
         half = (zeros / cn / 2).to(torch.int64)  # int(zeros / cutoff / 2), in the tensor's own precision
         f = self._lowpass_bank(cn, half, x.device)
+        K = f.shape[1]
+        if K <= self.DIRECT_FIR_MAX_TAPS and self.lib.b2a_fir_direct_supported(T, K, 1):
+            # short filters: time-domain kernel, correlation taps as designed (filter b is centred at half[b])
+            return self.fir_direct(x, f, rows_per_filt=C, left=half.to(torch.int32), pad_mode="replicate",
+                                   subtract_from_input=highpass)
         g = self._reverse_rows(f, 2 * half + 1)
         return self.fftconv(x, g, rows_per_filt=C, offset=half.to(torch.int32), pad_mode="replicate",
                             subtract_from_input=highpass)
@@ -376,6 +403,10 @@ class Engine:
         T = x.shape[-1]
         rows = x.numel() // T
         out_len = int(self.lib.b2a_resample_out_len(T, old, new))
+        if new == 1 and self.lib.b2a_fir_direct_supported(T, kt.shape[0], old):
+            # single output phase (48k -> 16k, ...): a decimating FIR, register-tiled direct kernel
+            return self.fir_direct(x, kt.reshape(1, -1), rows_per_filt=rows, left0=width, stride=old, out_len=out_len,
+                                   pad_mode="replicate")
         out = torch.empty(*x.shape[:-1], out_len, dtype=torch.float32, device=x.device)
         rc = self.lib.b2a_resample_f32(_dptr(x), rows, T, old, new, width, _dptr(kt), _dptr(out), self._stream(x))
         self.lib.check(rc)

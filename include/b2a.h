@@ -123,6 +123,17 @@ int b2a_fftconv_f32(const float* x, int64_t rows, int64_t T, const float* g, int
                     const float* post_scale, int subtract_from_input, float* out, void* ws, size_t ws_bytes,
                     void* stream);
 
+/* Direct (time-domain) strided FIR for short filters, correlation form:
+ *   out[row][m] = sum_{k<K} taps[f][k] * xv[row][m*stride + k - left0 - left[f]],  f = row / rows_per_filt, m < out_len
+ * xv = x extended by zeros (pad_mode 1) or edge replication (2).  Used for short julius.LowPassFilter /
+ * HighPassFilter taps (stride 1, left = half; subtract_from_input gives x - y) and for julius.resample_frac when
+ * the reduced new rate is 1 (stride = old rate, left = width).  b2a_fir_direct_supported tells whether
+ * (K, stride) fits the kernel's shared memory; longer filters go through b2a_fftconv_f32. */
+int b2a_fir_direct_supported(int64_t T, int K, int stride);
+int b2a_fir_direct_f32(const float* x, int64_t rows, int64_t T, const float* taps, int64_t n_filt, int K,
+                       int rows_per_filt, const int32_t* left, int left0, int stride, int64_t out_len,
+                       int pad_mode, int subtract_from_input, float* out, void* stream);
+
 /* EffectMixin.convolve (audiotools/core/effects.py:66-123): CIRCULAR convolution (period T) of each row with
  * its item's impulse response, the IR rolled so that max|ir| sits at t = 0 (roll_to_peak) and the result
  * scaled by 1 / max(max|ir|, 1e-5).   ir: [n_ir, L] with L <= T (truncate first, as the reference does). */

@@ -169,3 +169,23 @@ def test_pitch_shift_properties(eng):
             assert abs(spec.argmax().item() * sr / T - f0 * 2 ** (st / 12)) < 4.0  # pitch ratio 2^(n/12)
         assert torch.equal(eng.pitch_shift(x[:1], sr, st), y[:1])  # batch == per-item
     assert torch.equal(eng.pitch_shift(x, sr, 0), x)
+
+
+def test_direct_fir_paths(eng, golden):
+    """Short filters take the time-domain kernel (csrc/fir.cu): cfg3's low_pass(8k)@16k (103 taps) after the
+    single-phase 48k->16k resample (also fir.cu), per-item high-pass (x - y), zero vs replicate padding."""
+    x = cases.make_input("rs")
+    y = eng.resample(x, 48000, 16000)
+    assert rel_err(y, torch.from_numpy(golden["rs_48k_16k"])) < 1e-5
+    z = eng.sinc_filter(y, torch.tensor(8000.0), 16000, 51, False)
+    assert rel_err(z, torch.from_numpy(golden["rs_48k_16k_lp8k"])) < 1e-5
+    xs = cases.make_input("short")  # [2,1,4000] @16k
+    cut = torch.tensor([4000.0, 2500.0])
+    hp = eng.sinc_filter(xs, cut, 16000, 51, True)
+    assert rel_err(hp, sp.high_pass(xs, 16000, cut)) < 1e-5
+    lp = eng.sinc_filter(xs, cut, 16000, 51, False)
+    assert rel_err(lp, sp.low_pass(xs, 16000, cut)) < 1e-5
+    taps = torch.randn(1, 37)
+    out = eng.fir_direct(xs, taps, rows_per_filt=2, left0=5, stride=2, out_len=1990, pad_mode="constant")
+    ref = torch.nn.functional.conv1d(torch.nn.functional.pad(xs.reshape(2, 1, -1), (5, 40)), taps[None], stride=2)[..., :1990]
+    assert rel_err(out, ref.reshape(2, 1, -1)) < 1e-5

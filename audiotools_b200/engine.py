@@ -415,24 +415,6 @@ class Engine:
 
 
     # ------------------------------------------------------------------ pitch shift
-    def _interp_table(self, ratio: float, device, Q: int = 256, zero_crossings: int = 8):
-        """[Q+1, NT] windowed-sinc interpolation weights, cutoff 0.95*min(1, 1/ratio), rows sum to 1."""
-        c = 0.95 * min(1.0, 1.0 / ratio)
-        half = int(math.ceil(zero_crossings / c))
-        NT = 2 * half
-        key = ("interp", round(c, 9), str(device), Q)
-        if key not in self._packed_cache:
-            q = torch.arange(Q + 1, device=device, dtype=torch.float64).reshape(-1, 1) / Q
-            k = torch.arange(NT, device=device, dtype=torch.float64).reshape(1, -1)
-            t = (k - half + 1) - q  # tap position relative to the read position
-            a = math.pi * c * t
-            sinc = torch.where(t == 0, torch.ones_like(a), torch.sin(a) / a)
-            win = torch.where(t.abs() < half, 0.5 + 0.5 * torch.cos(math.pi * t / half), torch.zeros_like(t))
-            w = c * sinc * win
-            w = w / w.sum(dim=1, keepdim=True)
-            self._packed_cache[key] = (w.float().contiguous(), NT)
-        return self._packed_cache[key] + (Q,)
-
     def pitch_shift(self, x: torch.Tensor, sample_rate: int, n_semitones: float, quick: bool = True) -> torch.Tensor:
         """Shift the pitch of x [..., T] by ``n_semitones`` keeping T (ref:audiotools/core/effects.py:247-277)."""
         x = self._prep(x, "x")
@@ -440,15 +422,13 @@ class Engine:
             return x.clone()
         T = x.shape[-1]
         rows = x.numel() // T
-        ratio = 2.0 ** (float(n_semitones) / 12.0)
-        table, NT, Q = self._interp_table(ratio, x.device)
         ws_bytes = self.lib.b2a_pitch_shift_workspace_bytes(rows, T, int(sample_rate), float(n_semitones))
         ws = torch.empty(ws_bytes, dtype=torch.uint8, device=x.device)
         out = torch.empty_like(x)
-        rc = self.lib.b2a_pitch_shift_f32(_dptr(x), rows, T, int(sample_rate), float(n_semitones), _dptr(table), Q, NT,
-                                          _dptr(out), _dptr(ws), ws_bytes, self._stream(x))
+        rc = self.lib.b2a_pitch_shift_f32(_dptr(x), rows, T, int(sample_rate), float(n_semitones), _dptr(out), _dptr(ws),
+                                          ws_bytes, self._stream(x))
         self.lib.check(rc)
-        self.launches += 2
+        self.launches += 3
         return out
 
 

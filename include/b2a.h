@@ -152,11 +152,12 @@ int b2a_resample_f32(const float* x, int64_t rows, int64_t T, int old_r, int new
 
 /* ---- pitch shift ---------------------------------------------------------------------------------
  * EffectMixin.pitch_shift (audiotools/core/effects.py:247-277; SoX `pitch -q` + `rate` there): WSOLA
- * time-scale modification by r = 2^(semitones/12) + band-limited resampling by 1/r, output length == T.
- * table: [Q+1][NT] windowed-sinc interpolation weights (phase q/Q, tap k at floor(pos)+k-NT/2+1). */
+ * time-scale modification by r = 2^(semitones/12) (search -> overlap-add into the workspace) + band-limited
+ * rate change by 1/r (windowed sinc, cutoff 0.95*min(1,1/r), 8 zero crossings), output length == T.
+ * ws: 16-byte aligned, b2a_pitch_shift_workspace_bytes() bytes (frame positions + the stretched rows). */
 size_t b2a_pitch_shift_workspace_bytes(int64_t rows, int64_t T, int sr, float semitones);
-int b2a_pitch_shift_f32(const float* x, int64_t rows, int64_t T, int sr, float semitones, const float* table,
-                        int Q, int NT, float* out, void* ws, size_t ws_bytes, void* stream);
+int b2a_pitch_shift_f32(const float* x, int64_t rows, int64_t T, int sr, float semitones, float* out, void* ws,
+                        size_t ws_bytes, void* stream);
 
 #ifdef __cplusplus
 }

@@ -241,6 +241,7 @@ static inline void sincospif(float x, float* s, float* c) {
   *c = (float)cos(M_PI * (double)x);
 }
 static inline void sincospi(double x, double* s, double* c) { *s = sin(M_PI * x); *c = cos(M_PI * x); }
+static inline float __fdividef(float a, float b) { return a / b; }
 static inline float cospif(float x) { return (float)cos(M_PI * (double)x); }
 static inline float sinpif(float x) { return (float)sin(M_PI * (double)x); }
 static inline float __int_as_float(int i) { float f; memcpy(&f, &i, 4); return f; }

@@ -367,6 +367,16 @@ def test_pitch_shift_properties(at):
         assert torch.equal(single, y[:1])  # batch[0] == single
         again = at.AudioSignal(x.clone(), sr).to(DEV).pitch_shift(st).audio_data.cpu()
         assert torch.equal(again, y)  # deterministic
+        n = np.arange(T) / sr  # amplitude preserved; residual = WSOLA splice jitter only
+        f = 440.0 * 2 ** (st / 12)
+        A = np.stack([np.sin(2 * np.pi * f * n), np.cos(2 * np.pi * f * n)], 1)[4000:-4000]
+        coef = np.linalg.lstsq(A, y[0, 0, 4000:-4000].double().numpy(), rcond=None)[0]
+        assert abs(np.hypot(*coef) - 0.5) < 0.01
+        assert (y[0, 0, 4000:-4000].double().numpy() - A @ coef).std() < 0.03 * 0.5
+    dc = torch.full((2, 1, 60000), 0.25)  # windows and interpolation weights sum to one
+    for st in (2, -5):
+        y = at.AudioSignal(dc.clone(), sr).to(DEV).pitch_shift(st).audio_data.cpu()
+        assert torch.allclose(y[..., 3000:-6000], dc[..., 3000:-6000], atol=2e-6)
 
 
 def test_transforms_compose_matches_reference(at, golden):

@@ -168,7 +168,19 @@ def test_pitch_shift_properties(eng):
             spec = torch.fft.rfft(y[i, 0] * torch.hann_window(T)).abs()
             assert abs(spec.argmax().item() * sr / T - f0 * 2 ** (st / 12)) < 4.0  # pitch ratio 2^(n/12)
         assert torch.equal(eng.pitch_shift(x[:1], sr, st), y[:1])  # batch == per-item
+        # amplitude is preserved and the output is (up to WSOLA's splice jitter) the shifted sinusoid
+        n = np.arange(T) / sr
+        f = 440.0 * 2 ** (st / 12)
+        A = np.stack([np.sin(2 * np.pi * f * n), np.cos(2 * np.pi * f * n)], 1)[1500:-1500]
+        coef = np.linalg.lstsq(A, y[0, 0, 1500:-1500].double().numpy(), rcond=None)[0]
+        assert abs(np.hypot(*coef) - 0.5) < 0.01
+        assert (y[0, 0, 1500:-1500].double().numpy() - A @ coef).std() < 0.06 * 0.5
     assert torch.equal(eng.pitch_shift(x, sr, 0), x)
+    # overlap-add windows and interpolation weights both sum to one: a constant stays that constant
+    dc = torch.full((1, 1, 9000), 0.25)
+    for st in (2, -5):
+        y = eng.pitch_shift(dc, 8000, st)
+        assert torch.allclose(y[..., 600:-1200], dc[..., 600:-1200], atol=2e-6)
 
 
 def test_direct_fir_paths(eng, golden):

@@ -58,8 +58,7 @@ class EffectMixin:
 
     def ensure_max_of_audio(self, max: float = 1.0):
         peak = self.audio_data.abs().max(dim=-1, keepdims=True)[0]
-        peak_gain = torch.ones_like(peak)
-        peak_gain[peak > max] = max / peak[peak > max]
+        peak_gain = torch.where(peak > max, max / peak, torch.ones_like(peak))  # no boolean-mask host sync
         self.audio_data = self.audio_data * peak_gain
         return self
 
@@ -153,10 +152,11 @@ class ImpulseResponseMixin:
         early_idx = (idx >= td - t0) * (idx <= td + t0)
         early = torch.where(early_idx, x, torch.zeros_like(x))
         late = torch.where(early_idx, torch.zeros_like(x), x)
-        window = torch.zeros_like(x)
-        for b in range(self.batch_size):
-            widx = early_idx[b, 0].nonzero()
-            window[b, ..., widx] = self.get_window("hann", widx.shape[-1], self.device)
+        # ref :569-573 fills window[b, ..., widx] with get_window("hann", widx.shape[-1]) where widx =
+        # early_idx[b, 0].nonzero() has shape [n, 1]: the window length is always 1 (scipy's hann(1) == [1.0])
+        # and channel 0's early region is used for every channel.  Same values without the per-item loop, its
+        # nonzero() host synchronisations and the per-item host->device window copies:
+        window = early_idx[:, :1].to(x.dtype).expand_as(x)
         return early, late, window
 
     def measure_drr(self):

@@ -46,23 +46,55 @@ __global__ void row_origin_kernel(const int32_t* __restrict__ offset, int offset
   if (r < rows) row_origin[r] = offset0 + (offset ? offset[(row0 + r) / rows_per_filt] : 0);
 }
 
-// Y[row][f][b] = sum_p H[filt][f][p] * X[row][f][b + P-1 - p]
+// Y[row][f][b] = sum_p H[filt][f][p] * X[row][f][b + P-1 - p]   (complex FIR along the block index)
+//
+// Register-tiled: a thread owns 4 consecutive blocks b and slides an 8-element complex window over
+// q = P-1-p, so 4 new X values and 4 taps are loaded for 16 complex MACs (64 FMAs).  The (row, f) line of X
+// is staged in shared memory de-interleaved by (index mod 4): the 4 new window elements of all lanes are then
+// unit-stride 64-bit loads (conflict-free); the reversed taps g[q] = H[P-1-q] are broadcast loads.
+constexpr int FIR_R = 4;
+
+__device__ __forceinline__ void cmac(float2& a, const float2 g, const float2 x) {
+  a.x = fmaf(g.x, x.x, a.x); a.x = fmaf(-g.y, x.y, a.x);
+  a.y = fmaf(g.x, x.y, a.y); a.y = fmaf(g.y, x.x, a.y);
+}
+
 __global__ void __launch_bounds__(128)
 freq_fir_kernel(const float2* __restrict__ X, const float2* __restrict__ H, float2* __restrict__ Y, int NB,
-                int NBX, int P, int rows_per_filt, int row0) {
+                int NBX, int P, int rows_per_filt, int row0, int SP) {
+  B2A_DYN_SMEM(smem);
+  float2* xs = reinterpret_cast<float2*>(smem);  // [4][SP]: xs[i & 3][i >> 2] = X[b0 + i]
+  float2* gs = xs + 4 * SP;                      // [P4]
   const int f = blockIdx.y, row = blockIdx.z;
-  const int b = blockIdx.x * blockDim.x + threadIdx.x;
-  if (b >= NB) return;
-  const float2* xr = X + ((size_t)row * NF + f) * NBX + b + (P - 1);
+  const int tid = threadIdx.x, nt = blockDim.x;
+  const int P4 = (P + 3) & ~3;
+  const int b0 = blockIdx.x * nt * FIR_R;
+  const float2* xr = X + ((size_t)row * NF + f) * NBX + b0;
   const float2* hr = H + ((size_t)((row0 + row) / rows_per_filt) * NF + f) * P;
-  float ar = 0.f, ai = 0.f;
-  for (int p = 0; p < P; ++p) {
-    const float2 h = __ldg(hr + p);
-    const float2 x = __ldg(xr - p);
-    ar = fmaf(h.x, x.x, ar); ar = fmaf(-h.y, x.y, ar);
-    ai = fmaf(h.x, x.y, ai); ai = fmaf(h.y, x.x, ai);
+  const int avail = NBX - b0;
+  for (int i = tid; i < 4 * SP; i += nt)
+    xs[(i & 3) * SP + (i >> 2)] = i < avail ? __ldg(xr + i) : make_float2(0.f, 0.f);
+  for (int q = tid; q < P4; q += nt) gs[q] = q < P ? __ldg(hr + (P - 1 - q)) : make_float2(0.f, 0.f);
+  __syncthreads();
+  float2 w0 = xs[tid], w1 = xs[SP + tid], w2 = xs[2 * SP + tid], w3 = xs[3 * SP + tid];
+  float2 a0 = make_float2(0.f, 0.f), a1 = a0, a2 = a0, a3 = a0;
+#pragma unroll 2
+  for (int q = 0; q < P4; q += 4) {
+    const int n = tid + (q >> 2) + 1;
+    const float2 v0 = xs[n], v1 = xs[SP + n], v2 = xs[2 * SP + n], v3 = xs[3 * SP + n];
+    const float2 g0 = gs[q], g1 = gs[q + 1], g2 = gs[q + 2], g3 = gs[q + 3];
+    cmac(a0, g0, w0); cmac(a0, g1, w1); cmac(a0, g2, w2); cmac(a0, g3, w3);
+    cmac(a1, g0, w1); cmac(a1, g1, w2); cmac(a1, g2, w3); cmac(a1, g3, v0);
+    cmac(a2, g0, w2); cmac(a2, g1, w3); cmac(a2, g2, v0); cmac(a2, g3, v1);
+    cmac(a3, g0, w3); cmac(a3, g1, v0); cmac(a3, g2, v1); cmac(a3, g3, v2);
+    w0 = v0; w1 = v1; w2 = v2; w3 = v3;
   }
-  Y[((size_t)row * NF + f) * NB + b] = make_float2(ar, ai);
+  const int b = b0 + FIR_R * tid;
+  float2* yr = Y + ((size_t)row * NF + f) * NB + b;
+  if (b < NB) yr[0] = a0;
+  if (b + 1 < NB) yr[1] = a1;
+  if (b + 2 < NB) yr[2] = a2;
+  if (b + 3 < NB) yr[3] = a3;
 }
 
 struct InvParams {
@@ -238,8 +270,17 @@ static int run(const float* x, int64_t rows, int64_t T, const float* g, int64_t 
     rc = frames_fft(x + (size_t)r0 * T, nr, (int)T, NFFT, LP, ones, -w.P * LP, rorg, pad_mode, w.NBX, X, stream);
     if (rc != B2A_OK) return rc;
     // 3. complex FIR along the block index
-    B2A_LAUNCH(freq_fir_kernel, dim3((w.NB + 127) / 128, NF, nr), dim3(128), 0, stream, (const float2*)X,
-               (const float2*)H, Y, w.NB, w.NBX, w.P, rows_per_filt, (int)r0);
+    {
+      int nt = ((w.NB + FIR_R - 1) / FIR_R + 31) / 32 * 32;
+      if (nt > 128) nt = 128;
+      const int P4 = (w.P + 3) & ~3;
+      int SP = nt + P4 / 4 + 1;
+      SP += (8 - (SP & 15)) & 15;  // SP = 8 mod 16: the 4 phase rows of a staging store hit distinct banks
+      const size_t fir_smem = (size_t)(4 * SP + P4) * sizeof(float2);
+      B2A_REQUIRE(fir_smem <= 48 * 1024, B2A_E_UNSUPPORTED, "fftconv: %d partitions do not fit", w.P);
+      B2A_LAUNCH(freq_fir_kernel, dim3((w.NB + nt * FIR_R - 1) / (nt * FIR_R), NF, nr), dim3(nt), fir_smem, stream,
+                 (const float2*)X, (const float2*)H, Y, w.NB, w.NBX, w.P, rows_per_filt, (int)r0, SP);
+    }
     // 4. inverse FFT + overlap-save + epilogue
     ip.Y = Y; ip.x = x; ip.post = post_scale; ip.out = out;
     ip.rows = nr; ip.row0 = (int)r0; ip.T = (int)T; ip.NB = w.NB; ip.rows_per_filt = rows_per_filt;

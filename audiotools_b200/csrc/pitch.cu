@@ -46,6 +46,8 @@ struct Geo {
   float cb, sb;      // cos, sin of pi*c        (sinc numerator recurrence)
   float cw, sw;      // cos, sin of pi/half     (window recurrence)
   float inv_half;
+  float inv_Hs;       // 1 / Hs (the Hann argument is 2 t / W = t / Hs)
+  int log2Hs;
 };
 
 __device__ __forceinline__ void cp_async4(float* smem_dst, const float* gmem_src) {
@@ -62,8 +64,10 @@ __device__ __forceinline__ void cp_async_wait_all() {
 #endif
 }
 
-__device__ __forceinline__ int nominal(int j, const Geo& g) {  // nominal analysis position of frame j
-  return (int)floor((double)j * (double)g.Hs / g.r + 0.5);
+// nominal analysis position of frame j (double arithmetic, once per call; every row shares the table)
+__global__ void nominal_kernel(int* __restrict__ nom, Geo g) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j < g.J) nom[j] = (int)floor((double)j * (double)g.Hs / g.r + 0.5);
 }
 
 // prefer the larger correlation; ties go to the smaller |offset|, then the smaller offset (deterministic)
@@ -74,9 +78,8 @@ __device__ __forceinline__ bool better(float o, int od, float v, int d) {
 // Region of frame j: covers its candidate window [a_j - D, a_j + D + span) and every possible continuation
 // of frame j-1, [a_{j-1} - D + Hs, a_{j-1} + D + Hs + span).  lo is chosen so that a_j - D - lo is a multiple
 // of 8: the parity streams of the candidate window then start float4-aligned.
-__device__ __forceinline__ void region_of(int j, const Geo& g, int& lo, int& rn) {
+__device__ __forceinline__ void region_of(int aj, int ap, const Geo& g, int& lo, int& rn) {
   const int span = 2 * g.Lc;
-  const int aj = nominal(j, g), ap = nominal(j - 1, g);
   const int mn = min(aj - g.D, ap - g.D + g.Hs);
   const int mx = max(aj + g.D + span, ap + g.D + g.Hs + span);
   lo = aj - g.D - 8 * ((aj - g.D - mn + 7) >> 3);
@@ -84,7 +87,8 @@ __device__ __forceinline__ void region_of(int j, const Geo& g, int& lo, int& rn)
 }
 
 __global__ void __launch_bounds__(ST)
-wsola_search_kernel(const float* __restrict__ x, int T, Geo g, int* __restrict__ pos /*[rows, J]*/) {
+wsola_search_kernel(const float* __restrict__ x, int T, Geo g, const int* __restrict__ nom /*[J]*/,
+                    int* __restrict__ pos /*[rows, J]*/) {
   B2A_DYN_SMEM(smem);
   // layout (floats): [2 buffers][E: RH][O: RH] | part[8*ST] | tfb[Lc] ; RH = rcap/2 + 16 rounded to 16 mod 32
   const int RH = (((g.rcap >> 1) + 16 + 31) & ~31) + 16;
@@ -108,7 +112,7 @@ wsola_search_kernel(const float* __restrict__ x, int T, Geo g, int* __restrict__
   if (tid == 0) { pr[0] = 0; s_prev[0] = 0; }
   if (g.J > 1) {
     int lo, rn;
-    region_of(1, g, lo, rn);
+    region_of(__ldg(nom + 1), __ldg(nom), g, lo, rn);
     float* E = reg + 2 * RH;  // buffer 1
     for (int i = tid; i < rn; i += ST) {
       const int u = lo + i;
@@ -120,15 +124,15 @@ wsola_search_kernel(const float* __restrict__ x, int T, Geo g, int* __restrict__
     cp_async_wait_all();
     __syncthreads();  // region j landed; s_prev[(j-1)&1] visible; buffer (j+1)&1 and part[] are free again
     const int prev = s_prev[(j - 1) & 1];
-    const int a = nominal(j, g);
+    const int a = __ldg(nom + j);
     const int cont = prev + g.Hs;  // natural continuation of frame j-1
     int lo, rn;
-    region_of(j, g, lo, rn);
+    region_of(a, __ldg(nom + j - 1), g, lo, rn);
     const float* E = reg + (j & 1) * 2 * RH;
     const float* O = E + RH;
     if (j + 1 < g.J) {  // stream the next region in underneath this frame's correlations
       int lo2, rn2;
-      region_of(j + 1, g, lo2, rn2);
+      region_of(__ldg(nom + j + 1), a, g, lo2, rn2);
       float* E2 = reg + ((j + 1) & 1) * 2 * RH;
       for (int i = tid; i < rn2; i += ST) {
         const int u = lo2 + i;
@@ -213,18 +217,17 @@ wsola_search_kernel(const float* __restrict__ x, int T, Geo g, int* __restrict__
 
 // stretched row: sbuf[row][H + u] = s[u]; the H-sample halo in front is zero
 __global__ void __launch_bounds__(256)
-wsola_ola_kernel(const float* __restrict__ x, const int* __restrict__ pos, float* __restrict__ sbuf, int T, Geo g,
-                 int64_t total) {
-  const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (gid >= total) return;
-  const int row = (int)(gid / g.SL);
-  const int u = (int)(gid - (int64_t)row * g.SL) - g.H;
+wsola_ola_kernel(const float* __restrict__ x, const int* __restrict__ pos, float* __restrict__ sbuf, int T, Geo g) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= g.SL) return;
+  const int row = blockIdx.y;
+  const int u = i - g.H;
   float v = 0.f;
   if (u >= 0) {
     const float* xr = x + (size_t)row * (size_t)T;
     const int* pr = pos + (size_t)row * g.J;
-    const int J0 = u / g.Hs, t0 = u - J0 * g.Hs;
-    const float h0 = 0.5f - 0.5f * cospif(2.0f * (float)t0 / (float)g.W);
+    const int J0 = u >> g.log2Hs, t0 = u - (J0 << g.log2Hs);
+    const float h0 = 0.5f - 0.5f * cospif((float)t0 * g.inv_Hs);
     if (J0 < g.J) {
       const int idx = __ldg(pr + J0) + t0;
       if (idx >= 0 && idx < T) v = h0 * __ldg(xr + idx);
@@ -234,14 +237,14 @@ wsola_ola_kernel(const float* __restrict__ x, const int* __restrict__ pos, float
       if (idx >= 0 && idx < T) v = fmaf(1.0f - h0, __ldg(xr + idx), v);
     }
   }
-  sbuf[gid] = v;
+  sbuf[(size_t)row * (size_t)g.SL + i] = v;
 }
 
 __global__ void __launch_bounds__(256)
-rate_kernel(const float* __restrict__ sbuf, float* __restrict__ y, int T, Geo g, int64_t total) {
-  const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (gid >= total) return;
-  const int row = (int)(gid / T), n = (int)(gid - (int64_t)row * T);
+rate_kernel(const float* __restrict__ sbuf, float* __restrict__ y, int T, Geo g) {
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= T) return;
+  const int row = blockIdx.y;
   const double P = (double)n * g.r;  // read position in the stretched signal
   const int ip = (int)P;
   const float f = (float)(P - (double)ip);
@@ -256,21 +259,42 @@ rate_kernel(const float* __restrict__ sbuf, float* __restrict__ y, int T, Geo g,
   float sk = s0, ck = wc0;
   const float two_cb = 2.0f * g.cb, two_cw = 2.0f * g.cw;
   float acc = 0.f, wsum = 0.f;
-  const int NT = 2 * g.half;
+  const int half = g.half;
+  // taps 0 .. half-2 and half+1 .. 2 half-1 have |t| >= 1: sin(pi c t)/t straight from the recurrence
+#define B2A_RATE_STEP()                                          \
+  {                                                              \
+    const float sn = fmaf(two_cb, sk, -sm), cn = fmaf(two_cw, ck, -cm); \
+    sm = sk; sk = sn; cm = ck; ck = cn;                          \
+  }
 #pragma unroll 4
-  for (int k = 0; k < NT; ++k) {
-    const float t = t0 + (float)k;
-    // near the centre the recurrence's absolute error would be amplified by 1/t: use the series there
+  for (int k = 0; k < half - 1; ++k) {
+    const float w = fmaf(0.5f, ck, 0.5f) * __fdividef(sk, t0 + (float)k);
+    wsum += w;
+    acc = fmaf(w, __ldg(sp + k), acc);
+    B2A_RATE_STEP();
+  }
+  // the two taps around the read position (t = -f and 1 - f): where |t| is small the recurrence's absolute
+  // error would be amplified by 1/t, so use the series of sin(z)/z there
+#pragma unroll
+  for (int k2 = 0; k2 < 2; ++k2) {
+    const int k = half - 1 + k2;
+    const float t = (float)k2 - f;
     const float z2 = (g.pic * t) * (g.pic * t);
     const float sinc = fabsf(t) < 0.1f ? g.pic * fmaf(z2, fmaf(z2, 1.0f / 120.0f, -1.0f / 6.0f), 1.0f) : __fdividef(sk, t);
     const float w = fmaf(0.5f, ck, 0.5f) * sinc;
     wsum += w;
     acc = fmaf(w, __ldg(sp + k), acc);
-    const float sn = fmaf(two_cb, sk, -sm), cn = fmaf(two_cw, ck, -cm);
-    sm = sk; sk = sn;
-    cm = ck; ck = cn;
+    B2A_RATE_STEP();
   }
-  y[gid] = __fdividef(acc, wsum);
+#pragma unroll 4
+  for (int k = half + 1; k < 2 * half; ++k) {
+    const float w = fmaf(0.5f, ck, 0.5f) * __fdividef(sk, t0 + (float)k);
+    wsum += w;
+    acc = fmaf(w, __ldg(sp + k), acc);
+    B2A_RATE_STEP();
+  }
+#undef B2A_RATE_STEP
+  y[(size_t)row * (size_t)T + n] = __fdividef(acc, wsum);
 }
 
 static int geometry(int64_t rows, int64_t T, int sr, float semitones, Geo* g) {
@@ -296,10 +320,13 @@ static int geometry(int64_t rows, int64_t T, int sr, float semitones, Geo* g) {
   g->cb = (float)cos(PI * c); g->sb = (float)sin(PI * c);
   g->cw = (float)cos(PI / g->half); g->sw = (float)sin(PI / g->half);
   g->inv_half = (float)(1.0 / g->half);
+  g->inv_Hs = 1.0f / (float)g->Hs;
+  g->log2Hs = 0;
+  while ((1 << g->log2Hs) < g->Hs) ++g->log2Hs;
   return 0;
 }
 
-static size_t pos_bytes(int64_t rows, const Geo& g) { return ((size_t)rows * g.J * 4 + 255) / 256 * 256; }
+static size_t pos_bytes(int64_t rows, const Geo& g) { return ((size_t)(rows + 1) * g.J * 4 + 255) / 256 * 256; }  // + nominal[J]
 
 }  // namespace pitch
 }  // namespace b2a
@@ -318,7 +345,7 @@ extern "C" int b2a_pitch_shift_f32(const float* x, int64_t rows, int64_t T, int 
   B2A_REQUIRE(x && out && ws, B2A_E_INVALID, "pitch_shift: null pointer");
   B2A_REQUIRE(rows >= 1 && T >= 1 && sr >= 1, B2A_E_INVALID, "pitch_shift: bad argument");
   B2A_REQUIRE(fabsf(semitones) <= 24.f, B2A_E_UNSUPPORTED, "pitch_shift: |semitones| > 24");
-  B2A_REQUIRE(rows * T < ((int64_t)1 << 40) && T < ((int64_t)1 << 28) && rows < ((int64_t)1 << 31), B2A_E_UNSUPPORTED,
+  B2A_REQUIRE(rows * T < ((int64_t)1 << 40) && T < ((int64_t)1 << 28) && rows <= 65535, B2A_E_UNSUPPORTED,
               "pitch_shift: too large");
   B2A_REQUIRE(((uintptr_t)ws & 15) == 0, B2A_E_INVALID, "pitch_shift: workspace must be 16-byte aligned");
   Geo g;
@@ -326,17 +353,17 @@ extern "C" int b2a_pitch_shift_f32(const float* x, int64_t rows, int64_t T, int 
   const size_t pb = pos_bytes(rows, g);
   B2A_REQUIRE(ws_bytes >= pb + (size_t)rows * (size_t)g.SL * 4, B2A_E_INVALID, "pitch_shift: workspace too small");
   int* pos = (int*)ws;
+  int* nom = pos + (size_t)rows * g.J;
   float* sbuf = (float*)((char*)ws + pb);
   const int RH = (((g.rcap >> 1) + 16 + 31) & ~31) + 16;
   const size_t smem = (size_t)(4 * RH + 8 * ST + g.Lc) * 4;
   B2A_CUDA_OK(cudaFuncSetAttribute(wsola_search_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  B2A_LAUNCH(wsola_search_kernel, dim3((unsigned)rows), dim3(ST), smem, stream, x, (int)T, g, pos);
-  const int64_t tot_s = rows * g.SL;
-  B2A_LAUNCH(wsola_ola_kernel, dim3((unsigned)((tot_s + 255) / 256)), dim3(256), 0, stream, x, (const int*)pos, sbuf,
-             (int)T, g, tot_s);
-  const int64_t total = rows * T;
-  B2A_LAUNCH(rate_kernel, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, stream, (const float*)sbuf, out, (int)T, g,
-             total);
+  B2A_LAUNCH(nominal_kernel, dim3((unsigned)((g.J + 255) / 256)), dim3(256), 0, stream, nom, g);
+  B2A_LAUNCH(wsola_search_kernel, dim3((unsigned)rows), dim3(ST), smem, stream, x, (int)T, g, (const int*)nom, pos);
+  B2A_LAUNCH(wsola_ola_kernel, dim3((unsigned)((g.SL + 255) / 256), (unsigned)rows), dim3(256), 0, stream, x,
+             (const int*)pos, sbuf, (int)T, g);
+  B2A_LAUNCH(rate_kernel, dim3((unsigned)((T + 255) / 256), (unsigned)rows), dim3(256), 0, stream, (const float*)sbuf,
+             out, (int)T, g);
   B2A_CUDA_OK(cudaGetLastError());
   return B2A_OK;
 }

@@ -428,7 +428,7 @@ class Engine:
         rc = self.lib.b2a_pitch_shift_f32(_dptr(x), rows, T, int(sample_rate), float(n_semitones), _dptr(out), _dptr(ws),
                                           ws_bytes, self._stream(x))
         self.lib.check(rc)
-        self.launches += 3
+        self.launches += 4
         return out
 
 

@@ -187,3 +187,19 @@ def test_deferred_gain_on_cpu_is_plain_arithmetic():
     s.volume_change(torch.tensor([-6.0, 0.0]))
     assert s._pending_gain is None
     assert torch.allclose(s.audio_data[0], x[0] * 10 ** (-6 / 20), rtol=1e-6) and torch.equal(s.audio_data[1], x[1])
+
+
+def test_drr_algebra_matches_reference_on_cpu(golden):
+    """decompose_ir / measure_drr / alter_drr are host-side tensor algebra (no kernel): the vectorised early/late
+    split must reproduce the real reference's outputs (tests/golden/make_golden.py) without its per-item loop."""
+    from tests.conftest import rel_err
+    from tests.golden import cases
+
+    ir = cases.make_ir()
+    drr = torch.from_numpy(golden["drr"])
+    assert rel_err(AudioSignal(ir.clone(), 44100).alter_drr(drr).audio_data, torch.from_numpy(golden["alter_drr"])) < 1e-5
+    assert torch.allclose(AudioSignal(ir.clone(), 44100).measure_drr(), torch.from_numpy(golden["measure_drr"]), atol=1e-3)
+    stereo = AudioSignal(torch.cat([ir, 0.5 * ir.roll(7, -1)], dim=1), 44100)
+    early, late, window = stereo.decompose_ir()
+    assert torch.equal(window[:, 0], window[:, 1])  # channel 0's early region serves every channel (ref :569-573)
+    assert torch.equal(early + late, stereo.audio_data)

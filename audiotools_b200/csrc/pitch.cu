@@ -19,9 +19,10 @@
 // Kernel 1  wsola_search_kernel  one CTA (512 threads) per row.  Frames are sequential (each depends on the
 //           previous choice); inside a frame the 2D x (W/4) correlation table is a register-tiled FIR: the
 //           candidate window is staged in shared memory split by sample parity (the stride-2 correlation
-//           then reads unit-stride streams), a thread owns 8 candidates x a slice of the taps with a sliding
-//           float4 window (6 shared loads per 32 FMAs), slices are summed through shared memory and the
-//           arg-max is a shuffle tree.  The NEXT frame's window only depends on the nominal positions, so it
+//           then reads unit-stride streams) and by (index mod 8), a thread owns 8 consecutive candidates x a
+//           slice of the taps with a sliding 16-sample register window (8 conflict-free loads + 2 broadcast
+//           float4 tap loads per 64 FMAs), slices are summed through shared memory and the arg-max is a
+//           shuffle tree.  The NEXT frame's window only depends on the nominal positions, so it
 //           streams in with cp.async underneath the current frame's arithmetic.
 // Kernel 2  wsola_ola_kernel     one thread per stretched sample (coalesced reads of x, write s once).
 // Kernel 3  rate_kernel          one thread per output; the 2*half weights are generated in registers with
@@ -38,7 +39,7 @@ struct Geo {
   int W, Hs, D, Lc;  // frame, synthesis hop, search radius, correlation taps (every 2nd sample)
   int J;             // frames
   int half;          // interpolation taps each side
-  int H;             // left halo of the stretched row (== half)
+  int H;             // left halo of the stretched row (half rounded up to 4)
   int rcap;          // capacity (samples) of one staged search region
   int64_t SL;        // floats per stretched row (halo + samples, multiple of 4)
   double r;          // pitch ratio = stretch factor
@@ -70,6 +71,18 @@ __global__ void nominal_kernel(int* __restrict__ nom, Geo g) {
   if (j < g.J) nom[j] = (int)floor((double)j * (double)g.Hs / g.r + 0.5);
 }
 
+__device__ __forceinline__ float fast_rcp(float v) {
+#ifdef B2A_SIM
+  return 1.0f / v;
+#else
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(v));
+  return r;
+#endif
+}
+
+__host__ __device__ inline int search_row_stride(int rcap) { return (((rcap >> 4) + 3 + 31) & ~31) + 2; }
+
 // prefer the larger correlation; ties go to the smaller |offset|, then the smaller offset (deterministic)
 __device__ __forceinline__ bool better(float o, int od, float v, int d) {
   return (o > v) || (o == v && (abs(od) < abs(d) || (abs(od) == abs(d) && od < d)));
@@ -77,23 +90,36 @@ __device__ __forceinline__ bool better(float o, int od, float v, int d) {
 
 // Region of frame j: covers its candidate window [a_j - D, a_j + D + span) and every possible continuation
 // of frame j-1, [a_{j-1} - D + Hs, a_{j-1} + D + Hs + span).  lo is chosen so that a_j - D - lo is a multiple
-// of 8: the parity streams of the candidate window then start float4-aligned.
+// of 16: each parity stream of the candidate window then starts on a multiple of 8.
 __device__ __forceinline__ void region_of(int aj, int ap, const Geo& g, int& lo, int& rn) {
   const int span = 2 * g.Lc;
   const int mn = min(aj - g.D, ap - g.D + g.Hs);
   const int mx = max(aj + g.D + span, ap + g.D + g.Hs + span);
-  lo = aj - g.D - 8 * ((aj - g.D - mn + 7) >> 3);
-  rn = min((mx - lo + 7) & ~7, g.rcap);
+  lo = aj - g.D - 16 * ((aj - g.D - mn + 15) >> 4);
+  rn = min((mx - lo + 15) & ~15, g.rcap);
+}
+
+// Shared-memory image of a region: sample x[lo + i] has parity p = i & 1 and index m = i >> 1 in its parity
+// stream; it is stored in row p*8 + (m & 7), column m >> 3.  A thread that owns 8 consecutive candidates of
+// one parity then reads every window element as a unit-stride (conflict-free) 32-bit load across the warp.
+__device__ __forceinline__ void stage_region(const float* __restrict__ xr, int T, int lo, int rn, float* buf, int RS,
+                                             int tid) {
+  for (int i = tid; i < rn; i += ST) {
+    const int u = lo + i;
+    float* dst = buf + (((i & 1) << 3) + ((i >> 1) & 7)) * RS + (i >> 4);
+    if (u >= 0 && u < T) cp_async4(dst, xr + u); else *dst = 0.f;
+  }
 }
 
 __global__ void __launch_bounds__(ST)
 wsola_search_kernel(const float* __restrict__ x, int T, Geo g, const int* __restrict__ nom /*[J]*/,
                     int* __restrict__ pos /*[rows, J]*/) {
   B2A_DYN_SMEM(smem);
-  // layout (floats): [2 buffers][E: RH][O: RH] | part[8*ST] | tfb[Lc] ; RH = rcap/2 + 16 rounded to 16 mod 32
-  const int RH = (((g.rcap >> 1) + 16 + 31) & ~31) + 16;
+  // layout (floats): [2 buffers][16 rows][RS] | part[8*ST] | tfb[Lc];  RS = 2 mod 32 (staging stores of 32
+  // consecutive samples touch 16 rows x 2 columns: distinct banks)
+  const int RS = search_row_stride(g.rcap);
   float* reg = reinterpret_cast<float*>(smem);
-  float* part = reg + 4 * RH;
+  float* part = reg + 32 * RS;
   float* tfb = part + 8 * ST;
   __shared__ float wv[ST / 32];
   __shared__ int wd[ST / 32];
@@ -103,83 +129,72 @@ wsola_search_kernel(const float* __restrict__ x, int T, Geo g, const int* __rest
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int span = 2 * g.Lc;
   const int ne = g.D;       // candidates per parity
-  const int G = ne >> 3;    // 8-candidate groups per parity
+  const int G = ne >> 3;    // groups of 8 consecutive candidates per parity
   const int og = tid % (2 * G), kq = tid / (2 * G);
   const int parity = og / G, gi = og - parity * G;
-  const int KS = min(ST / (2 * G), g.Lc >> 2);  // tap slices
-  const int TS = g.Lc / KS;                     // taps per slice (multiple of 4)
+  const int KS = min(ST / (2 * G), g.Lc >> 3);  // tap slices
+  const int TS = g.Lc / KS;                     // taps per slice (multiple of 8)
   const bool active = kq < KS;
   if (tid == 0) { pr[0] = 0; s_prev[0] = 0; }
   if (g.J > 1) {
     int lo, rn;
     region_of(__ldg(nom + 1), __ldg(nom), g, lo, rn);
-    float* E = reg + 2 * RH;  // buffer 1
-    for (int i = tid; i < rn; i += ST) {
-      const int u = lo + i;
-      float* dst = E + ((i & 1) ? RH : 0) + (i >> 1);
-      if (u >= 0 && u < T) cp_async4(dst, xr + u); else *dst = 0.f;
-    }
+    stage_region(xr, T, lo, rn, reg + 16 * RS, RS, tid);  // buffer 1
   }
   for (int j = 1; j < g.J; ++j) {
     cp_async_wait_all();
-    __syncthreads();  // region j landed; s_prev[(j-1)&1] visible; buffer (j+1)&1 and part[] are free again
+    __syncthreads();  // region j landed; s_prev[(j-1)&1] visible; buffer (j+1)&1, part[] and tfb[] are free again
     const int prev = s_prev[(j - 1) & 1];
     const int a = __ldg(nom + j);
     const int cont = prev + g.Hs;  // natural continuation of frame j-1
     int lo, rn;
     region_of(a, __ldg(nom + j - 1), g, lo, rn);
-    const float* E = reg + (j & 1) * 2 * RH;
-    const float* O = E + RH;
+    const float* buf = reg + (j & 1) * 16 * RS;
+    int best = min(max(a, 0), max(T - g.W, 0));
+    const bool search = cont + span <= T && a - g.D >= 0 && a + g.D + span <= T;  // uniform over the CTA
+    if (search) {  // the template: tfb[i] = x[cont + 2 i]
+      const int c = cont - lo;
+      if (c >= 0 && c + span <= rn) {
+        for (int i = tid; i < g.Lc; i += ST) {
+          const int m = (c >> 1) + i;
+          tfb[i] = buf[(((c & 1) << 3) + (m & 7)) * RS + (m >> 3)];
+        }
+      } else {  // continuation outside the staged region (only after a clamped frame)
+        for (int i = tid; i < g.Lc; i += ST) tfb[i] = __ldg(xr + cont + 2 * i);
+      }
+    }
     if (j + 1 < g.J) {  // stream the next region in underneath this frame's correlations
       int lo2, rn2;
       region_of(__ldg(nom + j + 1), a, g, lo2, rn2);
-      float* E2 = reg + ((j + 1) & 1) * 2 * RH;
-      for (int i = tid; i < rn2; i += ST) {
-        const int u = lo2 + i;
-        float* dst = E2 + ((i & 1) ? RH : 0) + (i >> 1);
-        if (u >= 0 && u < T) cp_async4(dst, xr + u); else *dst = 0.f;
-      }
+      stage_region(xr, T, lo2, rn2, reg + ((j + 1) & 1) * 16 * RS, RS, tid);
     }
-    int best = min(max(a, 0), max(T - g.W, 0));
-    if (cont + span <= T && a - g.D >= 0 && a + g.D + span <= T) {  // uniform over the CTA
-      const int s = a - g.D - lo;  // multiple of 8, >= 0
-      const int c = cont - lo;
-      const float* Tp;
-      if (c >= 0 && c + span <= rn && s + 2 * g.D + span <= rn) {
-        Tp = ((c & 1) ? O : E) + (c >> 1);
-      } else {  // continuation outside the staged region (only after a clamped frame): fetch it
-        for (int i = tid; i < g.Lc; i += ST) tfb[i] = __ldg(xr + cont + 2 * i);
-        __syncthreads();
-        Tp = tfb;
-      }
+    if (search) {
+      __syncthreads();  // tfb complete
       if (active) {
-        const float* S = (parity ? O : E) + (s >> 1) + TS * kq;
-        const float* tq = Tp + TS * kq;
-        const int b0 = 4 * gi, b1 = b0 + (ne >> 1);
-        float4 wa0 = *reinterpret_cast<const float4*>(S + b0);
-        float4 wa1 = *reinterpret_cast<const float4*>(S + b1);
-        float acc[8];
+        const int s8 = (a - g.D - lo) >> 4;  // window start in units of 8 stream samples
+        const float* rowp = buf + (parity << 3) * RS + s8 + gi + ((TS * kq) >> 3);
+        const float4* tq = reinterpret_cast<const float4*>(tfb + TS * kq);
+        float w[8], acc[8];
 #pragma unroll
-        for (int q = 0; q < 8; ++q) acc[q] = 0.f;
-#pragma unroll 2
-        for (int i = 0; i < TS; i += 4) {
-          const float4 wb0 = *reinterpret_cast<const float4*>(S + b0 + i + 4);
-          const float4 wb1 = *reinterpret_cast<const float4*>(S + b1 + i + 4);
-          const float t0 = tq[i], t1 = tq[i + 1], t2 = tq[i + 2], t3 = tq[i + 3];
-          acc[0] = fmaf(t0, wa0.x, fmaf(t1, wa0.y, fmaf(t2, wa0.z, fmaf(t3, wa0.w, acc[0]))));
-          acc[1] = fmaf(t0, wa0.y, fmaf(t1, wa0.z, fmaf(t2, wa0.w, fmaf(t3, wb0.x, acc[1]))));
-          acc[2] = fmaf(t0, wa0.z, fmaf(t1, wa0.w, fmaf(t2, wb0.x, fmaf(t3, wb0.y, acc[2]))));
-          acc[3] = fmaf(t0, wa0.w, fmaf(t1, wb0.x, fmaf(t2, wb0.y, fmaf(t3, wb0.z, acc[3]))));
-          acc[4] = fmaf(t0, wa1.x, fmaf(t1, wa1.y, fmaf(t2, wa1.z, fmaf(t3, wa1.w, acc[4]))));
-          acc[5] = fmaf(t0, wa1.y, fmaf(t1, wa1.z, fmaf(t2, wa1.w, fmaf(t3, wb1.x, acc[5]))));
-          acc[6] = fmaf(t0, wa1.z, fmaf(t1, wa1.w, fmaf(t2, wb1.x, fmaf(t3, wb1.y, acc[6]))));
-          acc[7] = fmaf(t0, wa1.w, fmaf(t1, wb1.x, fmaf(t2, wb1.y, fmaf(t3, wb1.z, acc[7]))));
-          wa0 = wb0;
-          wa1 = wb1;
+        for (int q = 0; q < 8; ++q) { w[q] = rowp[q * RS]; acc[q] = 0.f; }
+#pragma unroll 1
+        for (int i8 = 0; i8 < (TS >> 3); ++i8) {
+          float v[8];
+#pragma unroll
+          for (int q = 0; q < 8; ++q) v[q] = rowp[q * RS + i8 + 1];
+          const float4 ta = tq[2 * i8], tb = tq[2 * i8 + 1];
+          const float t[8] = {ta.x, ta.y, ta.z, ta.w, tb.x, tb.y, tb.z, tb.w};
+#pragma unroll
+          for (int r = 0; r < 8; ++r) {
+#pragma unroll
+            for (int u = 0; u < 8; ++u) acc[r] = fmaf(t[u], (r + u < 8) ? w[r + u] : v[r + u - 8], acc[r]);
+          }
+#pragma unroll
+          for (int q = 0; q < 8; ++q) w[q] = v[q];
         }
-        float* pq = part + kq * (2 * ne) + parity * ne;
-        *reinterpret_cast<float4*>(pq + b0) = make_float4(acc[0], acc[1], acc[2], acc[3]);
-        *reinterpret_cast<float4*>(pq + b1) = make_float4(acc[4], acc[5], acc[6], acc[7]);
+        float* pq = part + kq * (2 * ne) + parity * ne + 8 * gi;
+        *reinterpret_cast<float4*>(pq) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+        *reinterpret_cast<float4*>(pq + 4) = make_float4(acc[4], acc[5], acc[6], acc[7]);
       }
       __syncthreads();
       float bv = -3.4e38f;
@@ -215,29 +230,30 @@ wsola_search_kernel(const float* __restrict__ x, int T, Geo g, const int* __rest
   }
 }
 
-// stretched row: sbuf[row][H + u] = s[u]; the H-sample halo in front is zero
+// stretched row: sbuf[row][H + u] = s[u]; the H-sample halo in front is zero.  4 samples per thread (H, Hs and SL
+// are multiples of 4, so the 4 samples share their two frames and the store is one aligned float4).
 __global__ void __launch_bounds__(256)
 wsola_ola_kernel(const float* __restrict__ x, const int* __restrict__ pos, float* __restrict__ sbuf, int T, Geo g) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int i = 4 * (blockIdx.x * blockDim.x + threadIdx.x);
   if (i >= g.SL) return;
   const int row = blockIdx.y;
   const int u = i - g.H;
-  float v = 0.f;
+  float v[4] = {0.f, 0.f, 0.f, 0.f};
   if (u >= 0) {
     const float* xr = x + (size_t)row * (size_t)T;
     const int* pr = pos + (size_t)row * g.J;
     const int J0 = u >> g.log2Hs, t0 = u - (J0 << g.log2Hs);
-    const float h0 = 0.5f - 0.5f * cospif((float)t0 * g.inv_Hs);
-    if (J0 < g.J) {
-      const int idx = __ldg(pr + J0) + t0;
-      if (idx >= 0 && idx < T) v = h0 * __ldg(xr + idx);
-    }
-    if (J0 >= 1 && J0 - 1 < g.J) {
-      const int idx = __ldg(pr + J0 - 1) + t0 + g.Hs;
-      if (idx >= 0 && idx < T) v = fmaf(1.0f - h0, __ldg(xr + idx), v);
+    const int i0 = J0 < g.J ? __ldg(pr + J0) + t0 : -8;                 // frame J0 reads x[i0 + q]
+    const int i1 = J0 >= 1 ? __ldg(pr + J0 - 1) + t0 + g.Hs : -8;      // frame J0-1
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const float h0 = 0.5f - 0.5f * cospif((float)(t0 + q) * g.inv_Hs);
+      const float a = (J0 < g.J && i0 + q >= 0 && i0 + q < T) ? __ldg(xr + i0 + q) : 0.f;
+      const float b = (J0 >= 1 && i1 + q >= 0 && i1 + q < T) ? __ldg(xr + i1 + q) : 0.f;
+      v[q] = fmaf(1.0f - h0, b, h0 * a);
     }
   }
-  sbuf[(size_t)row * (size_t)g.SL + i] = v;
+  *reinterpret_cast<float4*>(sbuf + (size_t)row * (size_t)g.SL + i) = make_float4(v[0], v[1], v[2], v[3]);
 }
 
 __global__ void __launch_bounds__(256)
@@ -248,8 +264,8 @@ rate_kernel(const float* __restrict__ sbuf, float* __restrict__ y, int T, Geo g)
   const double P = (double)n * g.r;  // read position in the stretched signal
   const int ip = (int)P;
   const float f = (float)(P - (double)ip);
-  // tap k reads s[ip + k - half + 1] = sbuf[H + ...] = sbuf[ip + k + 1]; its distance to P is t_k = t0 + k
-  const float* sp = sbuf + (size_t)row * (size_t)g.SL + ip + 1;
+  // tap k reads s[ip + k - half + 1] = sbuf[H + ip + k - half + 1]; its distance to P is t_k = t0 + k
+  const float* sp = sbuf + (size_t)row * (size_t)g.SL + ip + 1 + (g.H - g.half);
   const float t0 = (float)(1 - g.half) - f;
   float s0, c0, ws0, wc0;
   sincospif(g.c * t0, &s0, &c0);            // sin, cos(pi c t0)
@@ -266,35 +282,38 @@ rate_kernel(const float* __restrict__ sbuf, float* __restrict__ y, int T, Geo g)
     const float sn = fmaf(two_cb, sk, -sm), cn = fmaf(two_cw, ck, -cm); \
     sm = sk; sk = sn; cm = ck; ck = cn;                          \
   }
+  float t = t0;
 #pragma unroll 4
   for (int k = 0; k < half - 1; ++k) {
-    const float w = fmaf(0.5f, ck, 0.5f) * __fdividef(sk, t0 + (float)k);
+    const float w = fmaf(0.5f, ck, 0.5f) * (sk * fast_rcp(t));
     wsum += w;
     acc = fmaf(w, __ldg(sp + k), acc);
+    t += 1.0f;
     B2A_RATE_STEP();
   }
   // the two taps around the read position (t = -f and 1 - f): where |t| is small the recurrence's absolute
   // error would be amplified by 1/t, so use the series of sin(z)/z there
 #pragma unroll
   for (int k2 = 0; k2 < 2; ++k2) {
-    const int k = half - 1 + k2;
-    const float t = (float)k2 - f;
-    const float z2 = (g.pic * t) * (g.pic * t);
-    const float sinc = fabsf(t) < 0.1f ? g.pic * fmaf(z2, fmaf(z2, 1.0f / 120.0f, -1.0f / 6.0f), 1.0f) : __fdividef(sk, t);
+    const float tc = (float)k2 - f;
+    const float z2 = (g.pic * tc) * (g.pic * tc);
+    const float sinc = fabsf(tc) < 0.1f ? g.pic * fmaf(z2, fmaf(z2, 1.0f / 120.0f, -1.0f / 6.0f), 1.0f) : sk * fast_rcp(tc);
     const float w = fmaf(0.5f, ck, 0.5f) * sinc;
     wsum += w;
-    acc = fmaf(w, __ldg(sp + k), acc);
+    acc = fmaf(w, __ldg(sp + half - 1 + k2), acc);
     B2A_RATE_STEP();
   }
+  t = 2.0f - f;
 #pragma unroll 4
   for (int k = half + 1; k < 2 * half; ++k) {
-    const float w = fmaf(0.5f, ck, 0.5f) * __fdividef(sk, t0 + (float)k);
+    const float w = fmaf(0.5f, ck, 0.5f) * (sk * fast_rcp(t));
     wsum += w;
     acc = fmaf(w, __ldg(sp + k), acc);
+    t += 1.0f;
     B2A_RATE_STEP();
   }
 #undef B2A_RATE_STEP
-  y[(size_t)row * (size_t)T + n] = __fdividef(acc, wsum);
+  y[(size_t)row * (size_t)T + n] = acc * fast_rcp(wsum);
 }
 
 static int geometry(int64_t rows, int64_t T, int sr, float semitones, Geo* g) {
@@ -310,11 +329,11 @@ static int geometry(int64_t rows, int64_t T, int sr, float semitones, Geo* g) {
   g->J = (int)((double)T * r / g->Hs) + 2;
   const double c = 0.95 * (r > 1.0 ? 1.0 / r : 1.0);
   g->half = (int)ceil(8.0 / c);
-  g->H = g->half;
-  const int64_t Ls = (int64_t)ceil((double)T * r) + g->half + 2;
+  g->H = (g->half + 3) & ~3;
+  const int64_t Ls = (int64_t)ceil((double)T * r) + g->half + 2;  // samples s[0 .. Ls)
   g->SL = (g->H + Ls + 3) / 4 * 4;
   const int drift = (int)ceil(fabs((double)g->Hs / r - (double)g->Hs)) + 1;
-  g->rcap = (2 * g->D + 2 * g->Lc + drift + 16 + 63) / 64 * 64;
+  g->rcap = (2 * g->D + 2 * g->Lc + drift + 48 + 63) / 64 * 64;
   const double PI = 3.14159265358979323846;
   g->c = (float)c; g->pic = (float)(PI * c);
   g->cb = (float)cos(PI * c); g->sb = (float)sin(PI * c);
@@ -355,12 +374,11 @@ extern "C" int b2a_pitch_shift_f32(const float* x, int64_t rows, int64_t T, int 
   int* pos = (int*)ws;
   int* nom = pos + (size_t)rows * g.J;
   float* sbuf = (float*)((char*)ws + pb);
-  const int RH = (((g.rcap >> 1) + 16 + 31) & ~31) + 16;
-  const size_t smem = (size_t)(4 * RH + 8 * ST + g.Lc) * 4;
+  const size_t smem = (size_t)(32 * search_row_stride(g.rcap) + 8 * ST + g.Lc) * 4;
   B2A_CUDA_OK(cudaFuncSetAttribute(wsola_search_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   B2A_LAUNCH(nominal_kernel, dim3((unsigned)((g.J + 255) / 256)), dim3(256), 0, stream, nom, g);
   B2A_LAUNCH(wsola_search_kernel, dim3((unsigned)rows), dim3(ST), smem, stream, x, (int)T, g, (const int*)nom, pos);
-  B2A_LAUNCH(wsola_ola_kernel, dim3((unsigned)((g.SL + 255) / 256), (unsigned)rows), dim3(256), 0, stream, x,
+  B2A_LAUNCH(wsola_ola_kernel, dim3((unsigned)((g.SL / 4 + 255) / 256), (unsigned)rows), dim3(256), 0, stream, x,
              (const int*)pos, sbuf, (int)T, g);
   B2A_LAUNCH(rate_kernel, dim3((unsigned)((T + 255) / 256), (unsigned)rows), dim3(256), 0, stream, (const float*)sbuf,
              out, (int)T, g);

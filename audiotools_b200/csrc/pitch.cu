@@ -83,9 +83,26 @@ __device__ __forceinline__ float fast_rcp(float v) {
 
 __host__ __device__ inline int search_row_stride(int rcap) { return (((rcap >> 4) + 3 + 31) & ~31) + 2; }
 
-// prefer the larger correlation; ties go to the smaller |offset|, then the smaller offset (deterministic)
-__device__ __forceinline__ bool better(float o, int od, float v, int d) {
-  return (o > v) || (o == v && (abs(od) < abs(d) || (abs(od) == abs(d) && od < d)));
+// Arg-max key: high word = the correlation as an order-preserving unsigned, low word = the tie-break (ties go to
+// the smaller |offset|, then the smaller offset), so the larger 64-bit key wins and the result is deterministic.
+__device__ __forceinline__ unsigned long long corr_key(float v, int d) {
+  const unsigned b = __float_as_uint(v);
+  const unsigned ord = (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+  const unsigned tie = 0xffffffffu - (unsigned)(2 * abs(d) + (d > 0 ? 1 : 0));
+  return ((unsigned long long)ord << 32) | tie;
+}
+__device__ __forceinline__ int key_offset(unsigned long long k) {
+  const unsigned c = 0xffffffffu - (unsigned)(k & 0xffffffffu);
+  const int m = (int)(c >> 1);
+  return (c & 1) ? m : -m;
+}
+__device__ __forceinline__ unsigned long long warp_max_key(unsigned long long k) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const unsigned long long other = __shfl_xor_sync(0xffffffffu, k, o);
+    k = other > k ? other : k;
+  }
+  return k;
 }
 
 // Region of frame j: covers its candidate window [a_j - D, a_j + D + span) and every possible continuation
@@ -104,10 +121,12 @@ __device__ __forceinline__ void region_of(int aj, int ap, const Geo& g, int& lo,
 // one parity then reads every window element as a unit-stride (conflict-free) 32-bit load across the warp.
 __device__ __forceinline__ void stage_region(const float* __restrict__ xr, int T, int lo, int rn, float* buf, int RS,
                                              int tid) {
-  for (int i = tid; i < rn; i += ST) {
-    const int u = lo + i;
-    float* dst = buf + (((i & 1) << 3) + ((i >> 1) & 7)) * RS + (i >> 4);
-    if (u >= 0 && u < T) cp_async4(dst, xr + u); else *dst = 0.f;
+  // ST is a multiple of 16: a thread always writes the same row, 32 columns further each time
+  float* dst = buf + (((tid & 1) << 3) + ((tid >> 1) & 7)) * RS + (tid >> 4);
+  const float* src = xr + lo + tid;
+  int u = lo + tid;
+  for (int i = tid; i < rn; i += ST, dst += ST / 16, src += ST, u += ST) {
+    if ((unsigned)u < (unsigned)T) cp_async4(dst, src); else *dst = 0.f;
   }
 }
 
@@ -121,8 +140,7 @@ wsola_search_kernel(const float* __restrict__ x, int T, Geo g, const int* __rest
   float* reg = reinterpret_cast<float*>(smem);
   float* part = reg + 32 * RS;
   float* tfb = part + 8 * ST;
-  __shared__ float wv[ST / 32];
-  __shared__ int wd[ST / 32];
+  __shared__ unsigned long long wk[ST / 32];
   __shared__ int s_prev[2];
   const float* xr = x + (size_t)blockIdx.x * (size_t)T;
   int* pr = pos + (size_t)blockIdx.x * g.J;
@@ -174,56 +192,50 @@ wsola_search_kernel(const float* __restrict__ x, int T, Geo g, const int* __rest
         const int s8 = (a - g.D - lo) >> 4;  // window start in units of 8 stream samples
         const float* rowp = buf + (parity << 3) * RS + s8 + gi + ((TS * kq) >> 3);
         const float4* tq = reinterpret_cast<const float4*>(tfb + TS * kq);
-        float w[8], acc[8];
+        const float* r0 = rowp, *r1 = r0 + RS, *r2 = r1 + RS, *r3 = r2 + RS;
+        const float* r4 = r3 + RS, *r5 = r4 + RS, *r6 = r5 + RS, *r7 = r6 + RS;
+        float w[8], v[8], acc[8];
 #pragma unroll
-        for (int q = 0; q < 8; ++q) { w[q] = rowp[q * RS]; acc[q] = 0.f; }
+        for (int q = 0; q < 8; ++q) acc[q] = 0.f;
+        w[0] = r0[0]; w[1] = r1[0]; w[2] = r2[0]; w[3] = r3[0]; w[4] = r4[0]; w[5] = r5[0]; w[6] = r6[0]; w[7] = r7[0];
+#define B2A_CORR_STEP(WIN, NXT, I8)                                                                          \
+  {                                                                                                          \
+    NXT[0] = r0[(I8) + 1]; NXT[1] = r1[(I8) + 1]; NXT[2] = r2[(I8) + 1]; NXT[3] = r3[(I8) + 1];              \
+    NXT[4] = r4[(I8) + 1]; NXT[5] = r5[(I8) + 1]; NXT[6] = r6[(I8) + 1]; NXT[7] = r7[(I8) + 1];              \
+    const float4 ta = tq[2 * (I8)], tb = tq[2 * (I8) + 1];                                                   \
+    const float t[8] = {ta.x, ta.y, ta.z, ta.w, tb.x, tb.y, tb.z, tb.w};                                     \
+    _Pragma("unroll") for (int r = 0; r < 8; ++r) {                                                          \
+      _Pragma("unroll") for (int u = 0; u < 8; ++u)                                                          \
+          acc[r] = fmaf(t[u], (r + u < 8) ? WIN[r + u] : NXT[r + u - 8], acc[r]);                            \
+    }                                                                                                        \
+  }
+        const int steps = TS >> 3;
+        int i8 = 0;
 #pragma unroll 1
-        for (int i8 = 0; i8 < (TS >> 3); ++i8) {
-          float v[8];
-#pragma unroll
-          for (int q = 0; q < 8; ++q) v[q] = rowp[q * RS + i8 + 1];
-          const float4 ta = tq[2 * i8], tb = tq[2 * i8 + 1];
-          const float t[8] = {ta.x, ta.y, ta.z, ta.w, tb.x, tb.y, tb.z, tb.w};
-#pragma unroll
-          for (int r = 0; r < 8; ++r) {
-#pragma unroll
-            for (int u = 0; u < 8; ++u) acc[r] = fmaf(t[u], (r + u < 8) ? w[r + u] : v[r + u - 8], acc[r]);
-          }
-#pragma unroll
-          for (int q = 0; q < 8; ++q) w[q] = v[q];
+        for (; i8 + 2 <= steps; i8 += 2) {  // ping-pong the two window halves: no register moves
+          B2A_CORR_STEP(w, v, i8);
+          B2A_CORR_STEP(v, w, i8 + 1);
         }
+        if (i8 < steps) B2A_CORR_STEP(w, v, i8);
+#undef B2A_CORR_STEP
         float* pq = part + kq * (2 * ne) + parity * ne + 8 * gi;
         *reinterpret_cast<float4*>(pq) = make_float4(acc[0], acc[1], acc[2], acc[3]);
         *reinterpret_cast<float4*>(pq + 4) = make_float4(acc[4], acc[5], acc[6], acc[7]);
       }
       __syncthreads();
-      float bv = -3.4e38f;
-      int bd = 0;
+      unsigned long long key = 0ull;  // below every real key (NaN correlations never win: offset 0)
       if (tid < 2 * ne) {
         float v = 0.f;
         for (int q = 0; q < KS; ++q) v += part[q * (2 * ne) + tid];
         const int par = tid >= ne, e = tid - par * ne;
-        bv = v;
-        bd = 2 * e + par - g.D;
+        if (v == v) key = corr_key(v, 2 * e + par - g.D);
       }
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) {
-        const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
-        const int od = __shfl_xor_sync(0xffffffffu, bd, o);
-        if (better(ov, od, bv, bd)) { bv = ov; bd = od; }
-      }
-      if (lane == 0) { wv[warp] = bv; wd[warp] = bd; }
+      key = warp_max_key(key);
+      if (lane == 0) wk[warp] = key;
       __syncthreads();
       if (warp == 0) {
-        bv = lane < ST / 32 ? wv[lane] : -3.4e38f;
-        bd = lane < ST / 32 ? wd[lane] : 0;
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-          const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
-          const int od = __shfl_xor_sync(0xffffffffu, bd, o);
-          if (better(ov, od, bv, bd)) { bv = ov; bd = od; }
-        }
-        best = a + bd;
+        key = warp_max_key(lane < ST / 32 ? wk[lane] : 0ull);
+        best = a + (key ? key_offset(key) : 0);
       }
     }
     if (tid == 0) { pr[j] = best; s_prev[j & 1] = best; }

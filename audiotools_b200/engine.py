@@ -45,6 +45,64 @@ class Engine:
             return ctypes.c_void_p(torch.cuda.current_stream(t.device).cuda_stream)
         return None
 
+    # ------------------------------------------------------------------ inverse STFT
+    @staticmethod
+    def _envelope_min(window: torch.Tensor, n_fft: int, hop: int, n_frames: int, start: int, end: int) -> float:
+        """min over [start, end) of sum_n w^2[t - n*hop] (host, float64): the quantity torch.istft checks.  The
+        envelope is hop-periodic away from the first / last n_fft samples, so edges + one period suffice."""
+        w2 = window.detach().double().cpu().numpy() ** 2
+        total = (n_frames - 1) * hop + n_fft
+        end = min(end, total)
+        if end <= start:
+            return float("inf")
+
+        def env_at(ts):
+            ts = np.asarray(ts, dtype=np.int64)
+            out = np.zeros(len(ts))
+            n_hi = np.minimum(ts // hop, n_frames - 1)
+            for d in range((n_fft + hop - 1) // hop + 1):
+                n = n_hi - d
+                off = ts - n * hop
+                ok = (n >= 0) & (off >= 0) & (off < n_fft)
+                out[ok] += w2[off[ok]]
+            return out
+
+        edge = 2 * n_fft + hop
+        if end - start <= 2 * edge + hop:
+            ts = np.arange(start, end)
+        else:
+            ts = np.concatenate([np.arange(start, start + edge), np.arange(end - edge, end)])
+        return float(env_at(ts).min())
+
+    def istft(self, spec: torch.Tensor, n_fft: int, hop: int, window: torch.Tensor, length: int,
+              pad_frames: int = 0, trim: int = 0) -> torch.Tensor:
+        """``torch.istft(spec, n_fft, hop, window=window, length=..., center=True)`` for spec [B, C, F, N] complex64
+        (ref:audiotools/core/audio_signal.py:1214-1296) -> [B, C, length].  ``pad_frames`` zero frames are put back
+        on either side and ``trim`` extra leading samples are dropped (the reference's match_stride handling)."""
+        if not torch.is_complex(spec):
+            raise TypeError("istft: spec must be complex")
+        if self.require_cuda and not spec.is_cuda:
+            raise RuntimeError(f"stft_data is on {spec.device}: audiotools_b200 runs on CUDA (sm_100a) only and has "
+                               "no CPU fallback")
+        if spec.dtype != torch.complex64:
+            spec = spec.to(torch.complex64)
+        spec = spec.contiguous()
+        B, C, F, N = spec.shape
+        assert F == n_fft // 2 + 1, (F, n_fft)
+        if not self.lib.b2a_istft_supported(int(n_fft), int(hop)):
+            raise NotImplementedError(f"istft: n_fft={n_fft} hop={hop} (power-of-two n_fft in [64, 2048])")
+        window = self._prep(window, "window")
+        assert window.numel() == n_fft
+        start = n_fft // 2 + int(trim)
+        if self._envelope_min(window, n_fft, hop, N + 2 * pad_frames, start, start + int(length)) < 1e-11:
+            raise RuntimeError("istft: window overlap add min: 1 (the window envelope vanishes inside the output)")
+        out = torch.empty(B, C, int(length), dtype=torch.float32, device=spec.device)
+        rc = self.lib.b2a_istft_f32(_dptr(torch.view_as_real(spec)), B * C, N, int(n_fft), int(hop), _dptr(window),
+                                    int(pad_frames), start, int(length), _dptr(out), self._stream(spec))
+        self.lib.check(rc)
+        self.launches += 1
+        return out
+
     # ------------------------------------------------------------------ loudness
     def lufs(self, x: torch.Tensor, sample_rate: float, filter_class: str = "K-weighting",
              block_size: float = 0.400, padded_length: Optional[int] = None,

@@ -3,7 +3,7 @@
 bench.py, which measures configs[1]).  One JSON line per config: device-resident throughput (CUDA events,
 >= 3 warm-ups, inputs larger than L2 or rotated), algorithmic bytes, and the CPU oracle on a bounded sample.
 
-    python bench_configs.py [--only cfg1,cfg3,cfg4] [--no-cpu]
+    python bench_configs.py [--only cfg1,cfg3,cfg4,istft] [--no-cpu]
 """
 import argparse
 import json
@@ -41,7 +41,7 @@ def cpu_time(fn, reps=2):
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--only", default="cfg1,cfg3,cfg4")
+    ap.add_argument("--only", default="cfg1,cfg3,cfg4,istft")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
     import __graft_entry__ as graft
@@ -122,6 +122,21 @@ def main():
         line = {"config": f"cfg4 per-GPU share batch={B} mono 10s@44.1k Compose[EQ+RoomIR+PitchShift+-2]", "ms": ms,
                 "clips_per_s": B / ms * 1e3, "ms_parts": per}
         print(json.dumps(line))
+
+    if "istft" in only:  # inverse STFT at cfg2's shape (64 x 2ch x 10 s @ 44.1 kHz, 2048/512)
+        g = torch.Generator().manual_seed(0)
+        x = (0.1 * torch.randn(64, 2, 441000, generator=g)).to(dev)
+        sig = AudioSignal(x, 44100)
+        sig.stft(window_length=2048, hop_length=512)
+        X = sig.stft_data  # 905 MB > L2
+        ms = timed(lambda: sig.istft(window_length=2048, hop_length=512), steps=10)
+        w = torch.hann_window(2048, periodic=True, device=dev)
+        Xr = X.reshape(128, 1025, -1)
+        ms_torch = timed(lambda: torch.istft(Xr, 2048, 512, window=w, center=True, length=441000), steps=5)
+        alg = X.numel() * 8 + x.numel() * 4
+        print(json.dumps({"config": "istft 64x2ch 10s@44.1k n_fft=2048 hop=512", "ms": ms, "ms_torch_istft_cufft": ms_torch,
+                          "clips_per_s": 64 / ms * 1e3, "alg_bytes": alg, "achieved_GBps": alg / ms / 1e6,
+                          "frac_of_hbm_peak": alg / ms / 1e6 / peak}))
 
 
 if __name__ == "__main__":

@@ -78,6 +78,20 @@ int b2a_spectral_f32(const float* x, int64_t rows, int64_t T, int n_fft, int hop
                      int mel_packed_len, int post, float post_eps, float post_power,
                      float* mel_out, float* stft_out, void* stream);
 
+/* ---- inverse STFT ---------------------------------------------------------------------------------
+ * Replaces AudioSignal.istft (audiotools/core/audio_signal.py:1214-1296 -> torch.istft(center=True, onesided,
+ * window of n_fft samples)): inverse real FFT of every frame, window, overlap-add, division by the window
+ * envelope, all in one pass.
+ *   spec   [rows, n_fft/2+1, n_frames] complex64 (re,im), 8-byte aligned (the layout b2a_spectral_f32 writes)
+ *   pad_frames  zero frames put back on either side (match_stride: 2, :1276-1279); they count in the envelope
+ *   start  overlap-add coordinate of out[0]: n_fft/2 (+ the match_stride trim `pad`, :1291-1292)
+ *   out    [rows, out_len]; samples at or beyond (n_frames + 2*pad_frames - 1)*hop + n_fft are zero, as torch pads
+ * The caller checks the envelope (torch raises when its minimum over the kept range is < 1e-11).
+ * Supported: power-of-two n_fft in [64, 2048], 1 <= hop <= n_fft (b2a_istft_supported). */
+int b2a_istft_supported(int n_fft, int hop);
+int b2a_istft_f32(const float* spec, int64_t rows, int64_t n_frames, int n_fft, int hop, const float* window,
+                  int pad_frames, int64_t start, int64_t out_len, float* out, void* stream);
+
 /* ---- integrated loudness (ITU-R BS.1770 / LUFS) ----------------------------------------
  * Replaces Meter.integrated_loudness with the IIR semantics of apply_filter_cpu
  * (audiotools/core/loudness.py:102-126, 164-247) and the pad / clamp shell of

@@ -110,6 +110,39 @@ def test_stft_istft_round_trip(at):
     assert torch.allclose(sig.audio_data[..., 512:-512], x[..., 512:-512], atol=1e-5)
 
 
+def test_istft_matches_reference(at, golden):
+    """The fused inverse kernel (csrc/istft.cu) against the real reference's istft outputs, and against torch.istft
+    on spectra that are not consistent STFTs (so the overlap-add and the envelope are exercised on their own)."""
+    sig = sig_of(at, "cfg1", slice(0, 2))
+    sig.stft()
+    assert rel_err(sig.istft().audio_data.cpu(), G(golden, "cfg1_istft")) < TOL
+    sig = sig_of(at, "cfg1", slice(0, 2), stft_params=at.STFTParams(256, 64, "sqrt_hann", True, "reflect"))
+    sig.stft()
+    assert rel_err(sig.istft().audio_data.cpu(), G(golden, "cfg1_istft_match_stride")) < TOL
+    g = torch.Generator().manual_seed(5)
+    for n_fft, hop, T in ((2048, 512, 100000), (1024, 256, 50000), (512, 100, 20000), (128, 32, 8000), (64, 64, 4000)):
+        w = torch.hann_window(n_fft) + 0.1
+        X = torch.stft(torch.randn(4, T, generator=g), n_fft, hop, window=w, center=True, return_complex=True)
+        X = X * (1 + 0.3 * torch.randn(X.shape, generator=g))
+        ref = torch.istft(X, n_fft, hop, window=w, center=True, length=T - 13)
+        from audiotools_b200.engine import get_engine
+
+        out = get_engine().istft(X.reshape(2, 2, *X.shape[1:]).to(DEV), n_fft, hop, w.to(DEV), T - 13)
+        assert rel_err(out.reshape(4, -1).cpu(), ref) < TOL, (n_fft, hop)
+
+
+def test_istft_full_size_round_trip(at):
+    """cfg2's full shape (64 x 2ch x 10 s @ 44.1 kHz, 2048/512): istft(stft(x)) == x to 1e-5 (size-independent
+    property; the reference's own round-trip tolerance is atol 1e-6 on [-1, 1] audio, ref:tests/core/test_audio_signal.py:400-456)."""
+    g = torch.Generator().manual_seed(11)
+    x = (0.2 * torch.randn(64, 2, 441000, generator=g)).to(DEV)
+    sig = at.AudioSignal(x, 44100)
+    sig.stft(window_length=2048, hop_length=512)
+    sig.istft(window_length=2048, hop_length=512)
+    assert sig.audio_data.shape == x.shape
+    assert (sig.audio_data - x).abs().max().item() < 1e-5
+
+
 # ------------------------------------------------------------------------------------------
 # loudness
 # ------------------------------------------------------------------------------------------

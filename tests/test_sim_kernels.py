@@ -201,3 +201,55 @@ def test_direct_fir_paths(eng, golden):
     out = eng.fir_direct(xs, taps, rows_per_filt=2, left0=5, stride=2, out_len=1990, pad_mode="constant")
     ref = torch.nn.functional.conv1d(torch.nn.functional.pad(xs.reshape(2, 1, -1), (5, 40)), taps[None], stride=2)[..., :1990]
     assert rel_err(out, ref.reshape(2, 1, -1)) < 1e-5
+
+
+# ------------------------------------------------------------------------------------------
+# inverse STFT (csrc/istft.cu) against torch.istft
+# ------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("n_fft,hop,T,wtype", [(2048, 512, 30000, "hann"), (512, 128, 9000, "sqrt_hann"),
+                                               (256, 64, 5000, "sqrt_hann"), (64, 16, 3000, "hann"),
+                                               (1024, 300, 12000, "hann"), (128, 128, 4000, "boxcar"),
+                                               (512, 37, 3000, "hann")])
+def test_istft_matches_torch(eng, n_fft, hop, T, wtype):
+    from scipy import signal as ss
+
+    g = torch.Generator().manual_seed(n_fft + hop)
+    x = torch.randn(3, T, generator=g)
+    w = ss.get_window("hann" if wtype == "sqrt_hann" else wtype, n_fft)
+    w = torch.from_numpy(np.sqrt(w) if wtype == "sqrt_hann" else w).float()
+    X = torch.stft(x, n_fft, hop, window=w, center=True, return_complex=True)
+    X = X + 0.01 * torch.randn(X.shape, generator=g)  # not a consistent STFT any more: exercises the plain OLA
+    X[:, 0] = X[:, 0] + 0.5j  # imaginary parts of DC / Nyquist must be ignored (C2R semantics)
+    X[:, -1] = X[:, -1] - 0.25j
+    for length in (T, T - 77, (X.shape[-1] - 1) * hop):
+        ref = torch.istft(X, n_fft, hop, window=w, center=True, length=length)
+        out = eng.istft(X.reshape(3, 1, *X.shape[1:]), n_fft, hop, w, length)
+        assert out.shape == (3, 1, length)
+        assert rel_err(out[:, 0], ref) < 2e-5, (n_fft, hop, length)
+    # match_stride handling of the reference: 2 zero frames back on either side, trim `pad` samples in front
+    Xp = torch.nn.functional.pad(X, (2, 2))
+    pad, length = (n_fft - hop) // 2, T - 100
+    if (Xp.shape[-1] - 1) * hop + n_fft >= n_fft // 2 + pad + length:
+        ref = torch.istft(Xp, n_fft, hop, window=w, center=True, length=length + 2 * pad)[..., pad:pad + length]
+        out = eng.istft(X.reshape(3, 1, *X.shape[1:]), n_fft, hop, w, length, pad_frames=2, trim=pad)
+        assert rel_err(out[:, 0], ref) < 2e-5
+
+
+def test_istft_zero_tail_and_envelope_check(eng):
+    n_fft, hop = 256, 64
+    w = torch.hann_window(n_fft)
+    X = torch.stft(torch.randn(1, 2000, generator=torch.Generator().manual_seed(3)), n_fft, hop, window=w,
+                   center=True, return_complex=True)
+    expected = (X.shape[-1] - 1) * hop + n_fft
+    length = expected - n_fft // 2 + 333  # torch pads with zeros beyond the overlap-add's support
+    out = eng.istft(X[:, None], n_fft, hop, w, length)
+    assert torch.count_nonzero(out[..., expected - n_fft // 2:]) == 0
+    ref = torch.istft(X, n_fft, hop, window=w, center=True, length=expected - n_fft // 2 - 1)
+    assert rel_err(out[0, :, : ref.shape[-1] - 16], ref[..., :-16]) < 2e-5
+    assert rel_err(out[0, :, : ref.shape[-1]], ref) < 1e-4  # the envelope -> 0 at the very end amplifies rounding
+    with pytest.raises(RuntimeError):  # a window that vanishes inside the kept range (torch: "window overlap add min")
+        wz = w.clone()
+        wz[: n_fft // 2 + 10] = 0
+        eng.istft(X[:, None], n_fft, n_fft, wz, 1500)
+    with pytest.raises(NotImplementedError):
+        eng.istft(torch.zeros(1, 1, 2049, 5, dtype=torch.complex64), 4096, 1024, torch.ones(4096), 4096)

@@ -37,6 +37,19 @@ def _engine():
     return get_engine()
 
 
+@functools.lru_cache(None)
+def _cached_window(window_type: str, window_length: int, device: str) -> torch.Tensor:
+    from scipy import signal
+
+    if window_type == "average":
+        w = np.ones(window_length) / window_length
+    elif window_type == "sqrt_hann":
+        w = np.sqrt(signal.get_window("hann", window_length))
+    else:
+        w = signal.get_window(window_type, window_length)
+    return torch.from_numpy(w).to(device).float()
+
+
 class AudioSignal(EffectMixin, LoudnessMixin, ImpulseResponseMixin, DSPMixin):
     def __init__(self, audio_path_or_array, sample_rate: int = None, stft_params: STFTParams = None,
                  offset: float = 0, duration: float = None, device: str = None):
@@ -290,16 +303,9 @@ class AudioSignal(EffectMixin, LoudnessMixin, ImpulseResponseMixin, DSPMixin):
     @staticmethod
     @functools.lru_cache(None)
     def get_window(window_type: str, window_length: int, device: str):
-        """scipy window (periodic), float64 -> float32; ``sqrt_hann`` and ``average`` specials (ref :1009-1039)."""
-        from scipy import signal
-
-        if window_type == "average":
-            w = np.ones(window_length) / window_length
-        elif window_type == "sqrt_hann":
-            w = np.sqrt(signal.get_window("hann", window_length))
-        else:
-            w = signal.get_window(window_type, window_length)
-        return torch.from_numpy(w).to(device).float()
+        """scipy window (periodic), float64 -> float32; ``sqrt_hann`` and ``average`` specials (ref :1009-1039).
+        Cached per (type, length, device): the reference rebuilds and re-uploads it on every stft/istft call."""
+        return _cached_window(str(window_type), int(window_length), str(device))
 
     @property
     def stft_params(self):

@@ -130,6 +130,10 @@ __global__ void __launch_bounds__(256, 2) istft_kernel(const Params p) {
       for (int r = r_first; r < hop; r += RL) {
         const int dmax = (NFFT - 1 - r) / hop;  // frames n with (q - n) in [0, dmax] cover residue r of hop q
         const int qn = G + dmax;                // hops of this group's span that hold residue r
+        // envelope of residue r where all dmax+1 covering frames exist (everywhere but the signal's two ends)
+        float env_full = 0.f;
+        for (int d = 0; d <= dmax; ++d) { const float wv = win[d * hop + r]; env_full = fmaf(wv, wv, env_full); }
+        const float inv_env_full = 1.0f / env_full;
         for (int q = q_first; q < qn; q += QL) {
           const int trel = q * hop + r;
           float acc = trel < tail ? cin[trel] : 0.f;
@@ -144,9 +148,13 @@ __global__ void __launch_bounds__(256, 2) istft_kernel(const Params p) {
                 if (t < p.expected) {
                   // env[t] = sum over frames n' = g0 + q - d, d in [0, dmax], 0 <= n' < NP
                   const int dlo = max(g0 + q - (NP - 1), 0), dhi = min(dmax, g0 + q);
-                  float env = 0.f;
-                  for (int d = dlo; d <= dhi; ++d) { const float wv = win[d * hop + r]; env = fmaf(wv, wv, env); }
-                  v = acc / env;
+                  if (dlo == 0 && dhi == dmax) {
+                    v = acc * inv_env_full;
+                  } else {
+                    float env = 0.f;
+                    for (int d = dlo; d <= dhi; ++d) { const float wv = win[d * hop + r]; env = fmaf(wv, wv, env); }
+                    v = acc / env;
+                  }
                 }
                 orow[i] = v;
               }

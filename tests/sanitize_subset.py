@@ -25,6 +25,14 @@ y = AudioSignal(x.clone(), 44100).to(dev).low_pass(4000).high_pass(100).equalize
 ir = torch.randn(3, 1, 4000, generator=g) * torch.exp(-torch.arange(4000) / 800.0)
 ir[..., 10] = 2.0
 y = y.convolve(AudioSignal(ir, 44100).to(dev))
-y = y.resample(16000).pitch_shift(2)
+y = y.resample(16000).pitch_shift(2)          # 44.1k -> 16k: general polyphase kernel; WSOLA search / OLA / rate kernels
+z = AudioSignal(x.clone(), 48000).to(dev).resample(16000).low_pass(7000)  # fir.cu: single-phase decimator + 103-tap FIR
+for wl, hop in ((2048, 512), (512, 100), (64, 16)):  # istft.cu: inverse FFT + gather overlap-add, three plans
+    s2 = AudioSignal(x.clone(), 44100).to(dev)
+    s2.stft(window_length=wl, hop_length=hop)
+    s2.istft(window_length=wl, hop_length=hop)
+s3 = AudioSignal(x.clone(), 44100, stft_params=None).to(dev)
+s3.stft(window_length=256, hop_length=64, window_type="sqrt_hann", match_stride=True)
+s3.istft(window_length=256, hop_length=64, window_type="sqrt_hann", match_stride=True)
 torch.cuda.synchronize()
 print("ok", float(lm.mean()), float(y.audio_data.abs().mean()))

@@ -293,7 +293,7 @@ def run_ours(args):
     alg_bytes = B * (2 * BYTES_X + BYTES_MEL)  # read x + write y + write log-mel, each once
     achieved = alg_bytes / (spec_ms * 1e-3) / 1e9
     lufs_ms = ms / args.steps - spec_ms
-    roof = {"kernel": "spectral_kernel<10> (gain + STFT + |.| + mel + log10, fused)", "bound": "hbm",
+    roof = {"kernel": "spectral_warp_kernel<10> (gain + STFT + |.| + mel + log10, fused)", "bound": "hbm",
             "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
             # dram__bytes_read.sum + dram__bytes_write.sum of one launch at B=64 from the ncu --set full capture
             # profiles/r01h_prof_spectral_v7_ncu_full_summary.csv (226.0 + 229.2 MB), scaled to this batch

@@ -92,6 +92,57 @@ __device__ __forceinline__ int ld_acquire(const int* p) {
 #endif
 }
 
+// ---------------------------------------------------------------------------------------
+// TMA bulk copy (1-D, global -> shared) completing on an mbarrier: one elected thread arms the barrier with
+// the byte count and issues ONE copy for a whole contiguous span (SASS: UBLKCP); the consumers spin on the
+// barrier's phase parity.  16-byte aligned source, destination and size.  Under the CPU simulator the issuing
+// thread copies synchronously and the wait is a no-op (a __syncthreads always follows it in the kernels).
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
+#ifdef B2A_SIM
+  *bar = 0;
+  (void)count;
+#else
+  const unsigned a = (unsigned)__cvta_generic_to_shared(bar);
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(a), "r"(count) : "memory");
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+#endif
+}
+__device__ __forceinline__ void tma_load_1d(void* smem_dst, const void* gmem_src, unsigned bytes, unsigned long long* bar) {
+#ifdef B2A_SIM
+  memcpy(smem_dst, gmem_src, bytes);
+  (void)bar;
+#else
+  const unsigned b = (unsigned)__cvta_generic_to_shared(bar);
+  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+  // order the CTA's earlier generic-proxy accesses of the destination (made visible to this thread by the
+  // preceding barrier) before the async-proxy write
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(b), "r"(bytes) : "memory");
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(d),
+               "l"(gmem_src), "r"(bytes), "r"(b)
+               : "memory");
+#endif
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+#ifdef B2A_SIM
+  (void)bar; (void)parity;
+#else
+  const unsigned b = (unsigned)__cvta_generic_to_shared(bar);
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "B2A_MBAR_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra B2A_MBAR_DONE;\n"
+      "bra B2A_MBAR_WAIT;\n"
+      "B2A_MBAR_DONE:\n"
+      "}\n" ::"r"(b),
+      "r"(parity)
+      : "memory");
+#endif
+}
+
 // streaming (evict-first) 128-bit global accesses for data touched exactly once
 __device__ __forceinline__ float4 ld_stream4(const float* p) {
 #ifdef B2A_SIM

@@ -166,29 +166,19 @@ __device__ __forceinline__ void stage_span(const Params& p, float* sp, int row, 
   }
 }
 
-// ---- asynchronous staging (warp kernel): raw x -> shared memory with cp.async, so that the copy
-// overlaps the per-CTA table set-up; the gain is folded into the window (x*(w*g)) and the scaled
-// waveform x*g is written back from shared memory afterwards.
-__device__ __forceinline__ void cp_async16(float* smem_dst, const float* gmem_src) {
-#ifdef B2A_SIM
-  *reinterpret_cast<float4*>(smem_dst) = *reinterpret_cast<const float4*>(gmem_src);
-#else
-  const unsigned sa = (unsigned)__cvta_generic_to_shared(smem_dst);
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(gmem_src) : "memory");
-#endif
-}
-__device__ __forceinline__ void cp_async_wait_all() {
-#ifndef B2A_SIM
-  asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
-#endif
-}
-
-__device__ __forceinline__ void stage_span_async(const Params& p, float* sp, int row, int ws) {
+// ---- asynchronous staging (warp kernel): raw x -> shared memory by the TMA engine, so that the copy overlaps
+// the per-CTA table set-up and, later, the previous tile's FFTs; the gain is applied after the (linear) mel
+// projection and the scaled waveform x*g is written back from shared memory.
+// Returns true when the span was handed to the TMA engine (completion on `bar`), false when it was staged with
+// cp.async / plain stores (completion by cp_async_wait_all + the CTA barrier).  The choice is CTA-uniform.
+__device__ __forceinline__ bool stage_span_async(const Params& p, float* sp, int row, int ws, unsigned long long* bar) {
   const int tid = threadIdx.x, T = p.T, span = p.span;
   const float* xr = p.x + (size_t)row * (size_t)T;
   const bool interior = (ws >= 0) && (ws + span <= T);
   if (interior && ((((uintptr_t)(xr + ws)) & 15) == 0) && ((span & 3) == 0)) {
-    for (int i = tid * 4; i < span; i += (int)blockDim.x * 4) cp_async16(sp + i, xr + ws + i);
+    // interior tile: its (FR-1)*hop + n_fft samples are one contiguous, 16 B aligned run of the row -> ONE bulk copy
+    if (tid == 0) tma_load_1d(sp, xr + ws, (unsigned)span * 4u, bar);
+    return true;
   } else if (interior) {
     for (int i = tid; i < span; i += (int)blockDim.x) sp[i] = __ldg(xr + ws + i);
   } else {
@@ -197,6 +187,7 @@ __device__ __forceinline__ void stage_span_async(const Params& p, float* sp, int
       sp[i] = (u >= 0) ? __ldg(xr + u) : 0.f;
     }
   }
+  return false;
 }
 
 // y_out[w] = x[w] * g for the samples this CTA owns (requires pad == drop_edge == 0, so span[i] = x[ws+i])
@@ -470,9 +461,16 @@ __global__ void __launch_bounds__(256, 2) spectral_warp_kernel(Params p) {
 
   // ---- first tile's samples in flight while the (row-independent) tables are built ONCE per CTA
   int t = blockIdx.x;
+  __shared__ __align__(8) unsigned long long s_bar;  // mbarrier the TMA span copies complete on
+  if (tid == 0) mbar_init(&s_bar, 1);
+  __syncthreads();
+  bool by_tma;
+  unsigned tma_parity = 0;
   {
     const int row = t / p.n_tiles, tile = t - row * p.n_tiles;
-    stage_span_async(p, sp, row, (tile * FR + p.drop_edge) * hop + p.origin + (p.row_origin ? __ldg(p.row_origin + row) : 0));
+    by_tma = stage_span_async(p, sp, row,
+                              (tile * FR + p.drop_edge) * hop + p.origin + (p.row_origin ? __ldg(p.row_origin + row) : 0),
+                              &s_bar);
   }
   for (int i = tid; i < n_fft; i += 256) win[i] = __ldg(p.window + i);
   for (int i = tid; i < G * PL::XB; i += 256) xbs[i] = 0.f;  // the slack behind each |X| slot must stay finite (0 x w)
@@ -525,7 +523,8 @@ __global__ void __launch_bounds__(256, 2) spectral_warp_kernel(Params p) {
     const int ws = (n0 + p.drop_edge) * hop + p.origin + (p.row_origin ? __ldg(p.row_origin + row) : 0);
     const float g = p.gain ? __ldg(p.gain + row / p.rows_per_gain) : 1.0f;
     const float ga = fabsf(g);
-    cp_async_wait_all();  // this tile's span was issued by the previous iteration (or the prologue)
+    // this tile's span was issued by the previous iteration (or the prologue)
+    if (by_tma) { mbar_wait(&s_bar, tma_parity); tma_parity ^= 1u; }
     __syncthreads();
     if (p.y_out) writeback_scaled(p, sp, row, tile, n0, FR, ws, g);  // (sp is re-filled only after the barrier
                                                                       //  inside the last round, below)
@@ -556,13 +555,15 @@ __global__ void __launch_bounds__(256, 2) spectral_warp_kernel(Params p) {
       }
       if (rd == FR / G - 1) {
         // every warp holds its last frame in registers: the span buffer is dead, so the next tile's
-        // samples stream in (cp.async) underneath this round's FFTs and mel projection
+        // samples stream in (one TMA bulk copy) underneath this round's FFTs and mel projection
         __syncthreads();
         const int tn = t + gridDim.x;
+        by_tma = false;
         if (tn < total_tiles) {
           const int rown = tn / p.n_tiles, tilen = tn - rown * p.n_tiles;
-          stage_span_async(p, sp, rown,
-                           (tilen * FR + p.drop_edge) * hop + p.origin + (p.row_origin ? __ldg(p.row_origin + rown) : 0));
+          by_tma = stage_span_async(
+              p, sp, rown, (tilen * FR + p.drop_edge) * hop + p.origin + (p.row_origin ? __ldg(p.row_origin + rown) : 0),
+              &s_bar);
         }
       }
       warp_fft<LOG2N>(z, xb, tw, l);  // z[m] = Z[l + LPF m]
@@ -675,7 +676,6 @@ __global__ void __launch_bounds__(256, 2) spectral_warp_kernel(Params p) {
       __syncthreads();  // melt is rewritten by the next tile
     }
   }
-  cp_async_wait_all();
 }
 
 static int num_sms() {

@@ -82,6 +82,30 @@ def sample_from_dist(dist_tuple: tuple, state: np.random.RandomState = None):
     return getattr(state, dist_tuple[0])(*dist_tuple[1:])
 
 
+_HOST_MIRROR_MAX = 1 << 16
+
+
+def _to_device(v, device):
+    """``v.to(device)``; a small CPU parameter tensor moved to an accelerator keeps a reference to its host
+    original (``_b2a_host``), so that host-side decisions on it (mask all-true?, which pitch shifts?, cutoff
+    range checks) need no device->host synchronisation later (see :func:`host_view`)."""
+    out = v.to(device)
+    if torch.is_tensor(v) and out is not v and not v.is_cuda and out.is_cuda and v.numel() <= _HOST_MIRROR_MAX:
+        out._b2a_host = v
+    return out
+
+
+def host_view(t):
+    """The values of tensor ``t`` on the host: ``t`` itself on CPU, the mirror recorded by :func:`prepare_batch`
+    when there is one, else a (synchronising) copy."""
+    if not torch.is_tensor(t) or not t.is_cuda:
+        return t
+    h = getattr(t, "_b2a_host", None)
+    if h is not None and h.shape == t.shape:
+        return h
+    return t.cpu()
+
+
 def prepare_batch(batch, device="cpu"):
     """Move every tensor / AudioSignal of a (nested) batch to ``device`` -- the
     host->device boundary of the training loop."""
@@ -89,16 +113,16 @@ def prepare_batch(batch, device="cpu"):
         flat = flatten(batch)
         for k, v in flat.items():
             try:
-                flat[k] = v.to(device)
+                flat[k] = _to_device(v, device)
             except Exception:
                 pass
         return unflatten(flat)
     if torch.is_tensor(batch):
-        return batch.to(device)
+        return _to_device(batch, device)
     if isinstance(batch, list):
         for i in range(len(batch)):
             try:
-                batch[i] = batch[i].to(device)
+                batch[i] = _to_device(batch[i], device)
             except Exception:
                 pass
     return batch

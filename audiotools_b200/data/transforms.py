@@ -53,12 +53,31 @@ class BaseTransform:
         return util.unflatten({k: v[mask] for k, v in util.flatten(batch).items()})
 
     def transform(self, signal: AudioSignal, **kwargs):
+        """``signal[mask] = self._transform(signal[mask], **kwargs[mask])`` (ref :133-166).  When every item is
+        selected the gather / scatter copies of the whole batch are skipped and the transform runs on ``signal``
+        itself, leaving the same state the masked round trip leaves (samples replaced; a loudness / STFT cache is
+        only overwritten when both sides hold one, :1658-1679).  The mask is read from its host mirror
+        (``util.prepare_batch``) when there is one: no device synchronisation."""
         tfm_kwargs = self._prepare(kwargs)
         mask = tfm_kwargs["mask"]
-        if torch.any(mask):
-            tfm_kwargs = self.apply_mask(tfm_kwargs, mask)
+        host_mask = util.host_view(mask)
+        n_sel = int(host_mask.sum())
+        if n_sel == 0:
+            return signal
+        if host_mask.ndim == 1 and n_sel == host_mask.numel() == signal.batch_size:
             tfm_kwargs = {k: v for k, v in tfm_kwargs.items() if k != "mask"}
-            signal[mask] = self._transform(signal[mask], **tfm_kwargs)
+            pre_loud, pre_stft = signal._loudness, signal.stft_data
+            out = self._transform(signal, **tfm_kwargs)
+            if out is signal:
+                new_loud, new_stft = signal._loudness, signal.stft_data
+                signal._loudness = new_loud if (pre_loud is not None and new_loud is not None) else pre_loud
+                signal.stft_data = new_stft if (pre_stft is not None and new_stft is not None) else pre_stft
+                return signal
+            signal[mask] = out
+            return signal
+        tfm_kwargs = self.apply_mask(tfm_kwargs, mask)
+        tfm_kwargs = {k: v for k, v in tfm_kwargs.items() if k != "mask"}
+        signal[mask] = self._transform(signal[mask], **tfm_kwargs)
         return signal
 
     def __call__(self, *args, **kwargs):
@@ -319,11 +338,16 @@ class PitchShift(BaseTransform):
         return {"n_semitones": util.sample_from_dist(self.n_semitones, state)}
 
     def _transform(self, signal, n_semitones):
-        shifts = util.ensure_tensor(n_semitones, 1, signal.batch_size).reshape(-1)
-        for s in torch.unique(shifts).tolist():
+        shifts = util.host_view(n_semitones)  # grouping is a host decision: use the host mirror, no sync
+        shifts = util.ensure_tensor(shifts, 1, signal.batch_size).reshape(-1)
+        values = sorted(set(shifts.tolist()))
+        for s in values:
             if s == 0:
                 continue
-            sel = shifts == s
+            if len(values) == 1:
+                signal.pitch_shift(s, quick=self.quick)
+                break
+            sel = torch.nonzero(shifts == s).reshape(-1).to(signal.device)
             signal[sel] = signal[sel].pitch_shift(s, quick=self.quick)
         return signal
 

@@ -432,6 +432,10 @@ def test_transforms_compose_matches_reference(at, golden):
     kwargs = at.util.prepare_batch(kwargs, DEV)
     out = transform(sig.clone(), **kwargs)
     assert rel_err(out.audio_data.cpu(), G(golden, "tfm_out")) < TOL
+    # the host mirrors recorded by prepare_batch spare the mask / cutoff synchronisations; values are unchanged
+    lp = kwargs["Compose"]["2.LowPass"]
+    assert torch.equal(at.util.host_view(lp["mask"]), lp["mask"].cpu())
+    assert torch.equal(at.util.host_view(lp["cutoff"]), lp["cutoff"].cpu())
     # same kwargs twice => same output; batch[0] == single (ref:tests/data/test_transforms.py:21-85)
     out2 = transform(sig.clone(), **kwargs)
     assert torch.equal(out2.audio_data, out.audio_data)

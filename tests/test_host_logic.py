@@ -203,3 +203,26 @@ def test_drr_algebra_matches_reference_on_cpu(golden):
     early, late, window = stereo.decompose_ir()
     assert torch.equal(window[:, 0], window[:, 1])  # channel 0's early region serves every channel (ref :569-573)
     assert torch.equal(early + late, stereo.audio_data)
+
+
+def test_all_true_mask_fast_path_matches_masked_round_trip():
+    """BaseTransform.transform skips the gather / scatter copies when every item is selected; the samples and the
+    cache state must equal what the masked round trip of the reference leaves (ref transforms.py:133-166,
+    audio_signal.py:1658-1679: a cache is only overwritten when both sides hold one)."""
+    t = MulTransform(0.5)
+    sig = noise(B=3)
+    kw = t.batch_instantiate([0, 1, 2])
+    assert bool(kw["MulTransform"]["mask"].all())
+    # generic path, forced by a mask with one item off; then only compare the selected items
+    ref = sig.clone()
+    ref._loudness = torch.tensor([-20.0, -21.0, -22.0])
+    kw_part = {"MulTransform": {"num": kw["MulTransform"]["num"], "mask": torch.tensor([True, True, False])}}
+    ref = t(ref, **kw_part)
+    out = sig.clone()
+    out._loudness = torch.tensor([-20.0, -21.0, -22.0])
+    out = t(out, **kw)
+    assert torch.equal(out.audio_data[:2], ref.audio_data[:2]) and torch.equal(out.audio_data[2], sig.audio_data[2] * 0.5)
+    assert torch.equal(out._loudness, ref._loudness)  # the stale cache survives in both paths, as in the reference
+    assert util.host_view(kw["MulTransform"]["mask"]) is kw["MulTransform"]["mask"]  # CPU tensors are their own view
+    moved = util.prepare_batch(kw, "cpu")
+    assert not hasattr(moved["MulTransform"]["mask"], "_b2a_host")

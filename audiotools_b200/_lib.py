@@ -40,6 +40,9 @@ SIGNATURES = {
     "b2a_resample_f32": (c_int, [c_void_p, c_int64, c_int64, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "b2a_pitch_shift_workspace_bytes": (c_size_t, [c_int64, c_int64, c_int, c_float]),
     "b2a_pitch_shift_f32": (c_int, [c_void_p, c_int64, c_int64, c_int, c_float, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "b2a_pitch_shift_multi_workspace_bytes": (c_size_t, [c_int64, c_int64, c_int, c_void_p, c_int]),
+    "b2a_pitch_shift_multi_f32": (c_int, [c_void_p, c_int64, c_int64, c_int, c_void_p, c_int, c_void_p, c_void_p, c_void_p,
+                                          c_size_t, c_void_p]),
     "b2a_istft_supported": (c_int, [c_int, c_int]),
     "b2a_istft_f32": (c_int, [c_void_p, c_int64, c_int64, c_int, c_int, c_void_p, c_int, c_int64, c_int64, c_void_p,
                               c_void_p]),

@@ -86,10 +86,13 @@ class EffectMixin:
         self._defer_gain(util.ensure_tensor(gain, 1, self.batch_size))
         return self
 
-    def pitch_shift(self, n_semitones: int, quick: bool = True):
-        """Shift the pitch of every item by ``n_semitones`` keeping the length (ref :247-277, SoX there)."""
-        self.audio_data = _engine().pitch_shift(self._materialized(), self.sample_rate, float(n_semitones),
-                                                quick=quick)
+    def pitch_shift(self, n_semitones, quick: bool = True):
+        """Shift the pitch of every item by ``n_semitones`` keeping the length (ref :247-277, SoX there).  Extension:
+        ``n_semitones`` may also hold one shift per item (list / tensor of batch_size values, read on the host)."""
+        shifts = util.host_view(n_semitones) if torch.is_tensor(n_semitones) else n_semitones
+        if not torch.is_tensor(shifts) and np.ndim(shifts) == 0:
+            shifts = float(shifts)
+        self.audio_data = _engine().pitch_shift(self._materialized(), self.sample_rate, shifts, quick=quick)
         return self
 
     def time_stretch(self, factor: float, quick: bool = True):

@@ -49,7 +49,21 @@ struct Geo {
   float inv_half;
   float inv_Hs;       // 1 / Hs (the Hann argument is 2 t / W = t / Hs)
   int log2Hs;
+  int identity;       // semitones == 0: the row is copied
 };
+
+// One launch serves rows with different shifts: every row belongs to a group (<= MAXG distinct shifts) and reads
+// its group's geometry; buffers are laid out with the largest group's strides.
+constexpr int MAXG = 8;
+struct GeoTable {
+  Geo g[MAXG];
+  int n;
+  int Jmax;            // stride of the nominal / position tables
+  long long SLmax;     // stride of the stretched rows
+};
+__device__ __forceinline__ int group_of(const int* __restrict__ row_group, int row) {
+  return row_group ? __ldg(row_group + row) : 0;
+}
 
 __device__ __forceinline__ void cp_async4(float* smem_dst, const float* gmem_src) {
 #ifdef B2A_SIM
@@ -66,9 +80,10 @@ __device__ __forceinline__ void cp_async_wait_all() {
 }
 
 // nominal analysis position of frame j (double arithmetic, once per call; every row shares the table)
-__global__ void nominal_kernel(int* __restrict__ nom, Geo g) {
+__global__ void nominal_kernel(int* __restrict__ nom, const B2A_GRID_CONSTANT GeoTable tab) {
+  const Geo& g = tab.g[blockIdx.y];
   const int j = blockIdx.x * blockDim.x + threadIdx.x;
-  if (j < g.J) nom[j] = (int)floor((double)j * (double)g.Hs / g.r + 0.5);
+  if (j < g.J) nom[(size_t)blockIdx.y * tab.Jmax + j] = (int)floor((double)j * (double)g.Hs / g.r + 0.5);
 }
 
 __device__ __forceinline__ float fast_rcp(float v) {
@@ -131,9 +146,14 @@ __device__ __forceinline__ void stage_region(const float* __restrict__ xr, int T
 }
 
 __global__ void __launch_bounds__(ST)
-wsola_search_kernel(const float* __restrict__ x, int T, Geo g, const int* __restrict__ nom /*[J]*/,
-                    int* __restrict__ pos /*[rows, J]*/) {
+wsola_search_kernel(const float* __restrict__ x, int T, const B2A_GRID_CONSTANT GeoTable tab,
+                    const int* __restrict__ row_group, const int* __restrict__ nom_all /*[n, Jmax]*/,
+                    int* __restrict__ pos /*[rows, Jmax]*/) {
   B2A_DYN_SMEM(smem);
+  const int grp = group_of(row_group, blockIdx.x);
+  const Geo g = tab.g[grp];
+  if (g.identity) return;
+  const int* nom = nom_all + (size_t)grp * tab.Jmax;
   // layout (floats): [2 buffers][16 rows][RS] | part[8*ST] | tfb[Lc];  RS = 2 mod 32 (staging stores of 32
   // consecutive samples touch 16 rows x 2 columns: distinct banks)
   const int RS = search_row_stride(g.rcap);
@@ -143,7 +163,7 @@ wsola_search_kernel(const float* __restrict__ x, int T, Geo g, const int* __rest
   __shared__ unsigned long long wk[ST / 32];
   __shared__ int s_prev[2];
   const float* xr = x + (size_t)blockIdx.x * (size_t)T;
-  int* pr = pos + (size_t)blockIdx.x * g.J;
+  int* pr = pos + (size_t)blockIdx.x * tab.Jmax;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int span = 2 * g.Lc;
   const int ne = g.D;       // candidates per parity
@@ -245,15 +265,17 @@ wsola_search_kernel(const float* __restrict__ x, int T, Geo g, const int* __rest
 // stretched row: sbuf[row][H + u] = s[u]; the H-sample halo in front is zero.  4 samples per thread (H, Hs and SL
 // are multiples of 4, so the 4 samples share their two frames and the store is one aligned float4).
 __global__ void __launch_bounds__(256)
-wsola_ola_kernel(const float* __restrict__ x, const int* __restrict__ pos, float* __restrict__ sbuf, int T, Geo g) {
-  const int i = 4 * (blockIdx.x * blockDim.x + threadIdx.x);
-  if (i >= g.SL) return;
+wsola_ola_kernel(const float* __restrict__ x, const int* __restrict__ pos, float* __restrict__ sbuf, int T,
+                 const B2A_GRID_CONSTANT GeoTable tab, const int* __restrict__ row_group) {
   const int row = blockIdx.y;
+  const Geo g = tab.g[group_of(row_group, row)];
+  const int i = 4 * (blockIdx.x * blockDim.x + threadIdx.x);
+  if (g.identity || i >= g.SL) return;
   const int u = i - g.H;
   float v[4] = {0.f, 0.f, 0.f, 0.f};
   if (u >= 0) {
     const float* xr = x + (size_t)row * (size_t)T;
-    const int* pr = pos + (size_t)row * g.J;
+    const int* pr = pos + (size_t)row * tab.Jmax;
     const int J0 = u >> g.log2Hs, t0 = u - (J0 << g.log2Hs);
     const int i0 = J0 < g.J ? __ldg(pr + J0) + t0 : -8;                 // frame J0 reads x[i0 + q]
     const int i1 = J0 >= 1 ? __ldg(pr + J0 - 1) + t0 + g.Hs : -8;      // frame J0-1
@@ -265,19 +287,25 @@ wsola_ola_kernel(const float* __restrict__ x, const int* __restrict__ pos, float
       v[q] = fmaf(1.0f - h0, b, h0 * a);
     }
   }
-  *reinterpret_cast<float4*>(sbuf + (size_t)row * (size_t)g.SL + i) = make_float4(v[0], v[1], v[2], v[3]);
+  *reinterpret_cast<float4*>(sbuf + (size_t)row * (size_t)tab.SLmax + i) = make_float4(v[0], v[1], v[2], v[3]);
 }
 
 __global__ void __launch_bounds__(256)
-rate_kernel(const float* __restrict__ sbuf, float* __restrict__ y, int T, Geo g) {
+rate_kernel(const float* __restrict__ sbuf, const float* __restrict__ x, float* __restrict__ y, int T,
+            const B2A_GRID_CONSTANT GeoTable tab, const int* __restrict__ row_group) {
   const int n = blockIdx.x * blockDim.x + threadIdx.x;
   if (n >= T) return;
   const int row = blockIdx.y;
+  const Geo g = tab.g[group_of(row_group, row)];
+  if (g.identity) {
+    y[(size_t)row * (size_t)T + n] = __ldg(x + (size_t)row * (size_t)T + n);
+    return;
+  }
   const double P = (double)n * g.r;  // read position in the stretched signal
   const int ip = (int)P;
   const float f = (float)(P - (double)ip);
   // tap k reads s[ip + k - half + 1] = sbuf[H + ip + k - half + 1]; its distance to P is t_k = t0 + k
-  const float* sp = sbuf + (size_t)row * (size_t)g.SL + ip + 1 + (g.H - g.half);
+  const float* sp = sbuf + (size_t)row * (size_t)tab.SLmax + ip + 1 + (g.H - g.half);
   const float t0 = (float)(1 - g.half) - f;
   float s0, c0, ws0, wc0;
   sincospif(g.c * t0, &s0, &c0);            // sin, cos(pi c t0)
@@ -354,46 +382,87 @@ static int geometry(int64_t rows, int64_t T, int sr, float semitones, Geo* g) {
   g->inv_Hs = 1.0f / (float)g->Hs;
   g->log2Hs = 0;
   while ((1 << g->log2Hs) < g->Hs) ++g->log2Hs;
+  g->identity = (semitones == 0.0f);
   return 0;
 }
 
-static size_t pos_bytes(int64_t rows, const Geo& g) { return ((size_t)(rows + 1) * g.J * 4 + 255) / 256 * 256; }  // + nominal[J]
+static int build_table(int64_t rows, int64_t T, int sr, const float* semitones_h, int n_groups, GeoTable* tab) {
+  memset(tab, 0, sizeof(*tab));
+  tab->n = n_groups;
+  for (int i = 0; i < n_groups; ++i) {
+    geometry(rows, T, sr, semitones_h[i], &tab->g[i]);
+    if (tab->g[i].J > tab->Jmax) tab->Jmax = tab->g[i].J;
+    if (tab->g[i].SL > tab->SLmax) tab->SLmax = tab->g[i].SL;
+  }
+  return 0;
+}
+// workspace: positions [rows, Jmax] | nominal [n, Jmax] | (256 B aligned) stretched rows [rows, SLmax]
+static size_t pos_bytes(int64_t rows, const GeoTable& t) {
+  return ((size_t)(rows + t.n) * t.Jmax * 4 + 255) / 256 * 256;
+}
+static bool groups_ok(const float* semitones_h, int n_groups) {
+  if (!semitones_h || n_groups < 1 || n_groups > MAXG) return false;
+  for (int i = 0; i < n_groups; ++i)
+    if (!(fabsf(semitones_h[i]) <= 24.f)) return false;
+  return true;
+}
 
 }  // namespace pitch
 }  // namespace b2a
 
 using namespace b2a::pitch;
 
+extern "C" size_t b2a_pitch_shift_multi_workspace_bytes(int64_t rows, int64_t T, int sr, const float* semitones_h,
+                                                        int n_groups) {
+  if (rows < 1 || T < 1 || sr < 1 || !groups_ok(semitones_h, n_groups)) return 0;
+  GeoTable tab;
+  build_table(rows, T, sr, semitones_h, n_groups, &tab);
+  return pos_bytes(rows, tab) + (size_t)rows * (size_t)tab.SLmax * 4;
+}
+
+extern "C" int b2a_pitch_shift_multi_f32(const float* x, int64_t rows, int64_t T, int sr, const float* semitones_h,
+                                         int n_groups, const int32_t* row_group, float* out, void* ws, size_t ws_bytes,
+                                         void* stream) {
+  B2A_REQUIRE(x && out && ws && semitones_h, B2A_E_INVALID, "pitch_shift: null pointer");
+  B2A_REQUIRE(rows >= 1 && T >= 1 && sr >= 1, B2A_E_INVALID, "pitch_shift: bad argument");
+  B2A_REQUIRE(n_groups >= 1 && n_groups <= MAXG, B2A_E_UNSUPPORTED, "pitch_shift: %d distinct shifts (max %d per call)",
+              n_groups, MAXG);
+  B2A_REQUIRE(groups_ok(semitones_h, n_groups), B2A_E_UNSUPPORTED, "pitch_shift: |semitones| > 24");
+  B2A_REQUIRE(row_group || n_groups == 1, B2A_E_INVALID, "pitch_shift: row_group is required with several shifts");
+  B2A_REQUIRE(rows * T < ((int64_t)1 << 40) && T < ((int64_t)1 << 28) && rows <= 65535, B2A_E_UNSUPPORTED,
+              "pitch_shift: too large");
+  B2A_REQUIRE(((uintptr_t)ws & 15) == 0, B2A_E_INVALID, "pitch_shift: workspace must be 16-byte aligned");
+  B2A_REQUIRE(out != x, B2A_E_INVALID, "pitch_shift: in-place is not supported");
+  GeoTable tab;
+  build_table(rows, T, sr, semitones_h, n_groups, &tab);
+  const size_t pb = pos_bytes(rows, tab);
+  B2A_REQUIRE(ws_bytes >= pb + (size_t)rows * (size_t)tab.SLmax * 4, B2A_E_INVALID, "pitch_shift: workspace too small");
+  int* pos = (int*)ws;
+  int* nom = pos + (size_t)rows * tab.Jmax;
+  float* sbuf = (float*)((char*)ws + pb);
+  size_t smem = 0;
+  for (int i = 0; i < n_groups; ++i) {
+    const Geo& g = tab.g[i];
+    const size_t b = (size_t)(32 * search_row_stride(g.rcap) + 8 * ST + g.Lc) * 4;
+    if (b > smem) smem = b;
+  }
+  B2A_CUDA_OK(cudaFuncSetAttribute(wsola_search_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  B2A_LAUNCH(nominal_kernel, dim3((unsigned)((tab.Jmax + 255) / 256), (unsigned)n_groups), dim3(256), 0, stream, nom, tab);
+  B2A_LAUNCH(wsola_search_kernel, dim3((unsigned)rows), dim3(ST), smem, stream, x, (int)T, tab, row_group,
+             (const int*)nom, pos);
+  B2A_LAUNCH(wsola_ola_kernel, dim3((unsigned)((tab.SLmax / 4 + 255) / 256), (unsigned)rows), dim3(256), 0, stream, x,
+             (const int*)pos, sbuf, (int)T, tab, row_group);
+  B2A_LAUNCH(rate_kernel, dim3((unsigned)((T + 255) / 256), (unsigned)rows), dim3(256), 0, stream, (const float*)sbuf, x,
+             out, (int)T, tab, row_group);
+  B2A_CUDA_OK(cudaGetLastError());
+  return B2A_OK;
+}
+
 extern "C" size_t b2a_pitch_shift_workspace_bytes(int64_t rows, int64_t T, int sr, float semitones) {
-  if (rows < 1 || T < 1 || sr < 1 || !(fabsf(semitones) <= 24.f)) return 0;
-  Geo g;
-  geometry(rows, T, sr, semitones, &g);
-  return pos_bytes(rows, g) + (size_t)rows * (size_t)g.SL * 4;
+  return b2a_pitch_shift_multi_workspace_bytes(rows, T, sr, &semitones, 1);
 }
 
 extern "C" int b2a_pitch_shift_f32(const float* x, int64_t rows, int64_t T, int sr, float semitones, float* out,
                                    void* ws, size_t ws_bytes, void* stream) {
-  B2A_REQUIRE(x && out && ws, B2A_E_INVALID, "pitch_shift: null pointer");
-  B2A_REQUIRE(rows >= 1 && T >= 1 && sr >= 1, B2A_E_INVALID, "pitch_shift: bad argument");
-  B2A_REQUIRE(fabsf(semitones) <= 24.f, B2A_E_UNSUPPORTED, "pitch_shift: |semitones| > 24");
-  B2A_REQUIRE(rows * T < ((int64_t)1 << 40) && T < ((int64_t)1 << 28) && rows <= 65535, B2A_E_UNSUPPORTED,
-              "pitch_shift: too large");
-  B2A_REQUIRE(((uintptr_t)ws & 15) == 0, B2A_E_INVALID, "pitch_shift: workspace must be 16-byte aligned");
-  Geo g;
-  geometry(rows, T, sr, semitones, &g);
-  const size_t pb = pos_bytes(rows, g);
-  B2A_REQUIRE(ws_bytes >= pb + (size_t)rows * (size_t)g.SL * 4, B2A_E_INVALID, "pitch_shift: workspace too small");
-  int* pos = (int*)ws;
-  int* nom = pos + (size_t)rows * g.J;
-  float* sbuf = (float*)((char*)ws + pb);
-  const size_t smem = (size_t)(32 * search_row_stride(g.rcap) + 8 * ST + g.Lc) * 4;
-  B2A_CUDA_OK(cudaFuncSetAttribute(wsola_search_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  B2A_LAUNCH(nominal_kernel, dim3((unsigned)((g.J + 255) / 256)), dim3(256), 0, stream, nom, g);
-  B2A_LAUNCH(wsola_search_kernel, dim3((unsigned)rows), dim3(ST), smem, stream, x, (int)T, g, (const int*)nom, pos);
-  B2A_LAUNCH(wsola_ola_kernel, dim3((unsigned)((g.SL / 4 + 255) / 256), (unsigned)rows), dim3(256), 0, stream, x,
-             (const int*)pos, sbuf, (int)T, g);
-  B2A_LAUNCH(rate_kernel, dim3((unsigned)((T + 255) / 256), (unsigned)rows), dim3(256), 0, stream, (const float*)sbuf,
-             out, (int)T, g);
-  B2A_CUDA_OK(cudaGetLastError());
-  return B2A_OK;
+  return b2a_pitch_shift_multi_f32(x, rows, T, sr, &semitones, 1, nullptr, out, ws, ws_bytes, stream);
 }

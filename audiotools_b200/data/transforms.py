@@ -326,7 +326,8 @@ class RoomImpulseResponse(BaseTransform):
 class PitchShift(BaseTransform):
     """``signal.pitch_shift(n_semitones)``.  NEW: the reference has no PitchShift transform (only the
     ``AudioSignal.pitch_shift`` method, ref:audiotools/core/effects.py:247-277, which takes ONE shift
-    for the whole batch); BASELINE.json config 4 needs it.  Items are grouped by their drawn shift."""
+    for the whole batch); BASELINE.json config 4 needs it.  Items are grouped by their drawn shift inside the
+    engine (one set of launches for the whole batch)."""
 
     def __init__(self, n_semitones: tuple = ("choice", [-2, -1, 0, 1, 2]), quick: bool = True, name: str = None,
                  prob: float = 1.0):
@@ -338,18 +339,9 @@ class PitchShift(BaseTransform):
         return {"n_semitones": util.sample_from_dist(self.n_semitones, state)}
 
     def _transform(self, signal, n_semitones):
-        shifts = util.host_view(n_semitones)  # grouping is a host decision: use the host mirror, no sync
-        shifts = util.ensure_tensor(shifts, 1, signal.batch_size).reshape(-1)
-        values = sorted(set(shifts.tolist()))
-        for s in values:
-            if s == 0:
-                continue
-            if len(values) == 1:
-                signal.pitch_shift(s, quick=self.quick)
-                break
-            sel = torch.nonzero(shifts == s).reshape(-1).to(signal.device)
-            signal[sel] = signal[sel].pitch_shift(s, quick=self.quick)
-        return signal
+        # the grouping by shift is a host decision (host mirror: no sync); all groups share the kernel launches
+        shifts = util.ensure_tensor(util.host_view(n_semitones), 1, signal.batch_size).reshape(-1)
+        return signal.pitch_shift(shifts, quick=self.quick)
 
 
 class ClippingDistortion(BaseTransform):

@@ -480,18 +480,44 @@ class Engine:
 
 
     # ------------------------------------------------------------------ pitch shift
-    def pitch_shift(self, x: torch.Tensor, sample_rate: int, n_semitones: float, quick: bool = True) -> torch.Tensor:
-        """Shift the pitch of x [..., T] by ``n_semitones`` keeping T (ref:audiotools/core/effects.py:247-277)."""
+    MAX_PITCH_GROUPS = 8
+
+    def pitch_shift(self, x: torch.Tensor, sample_rate: int, n_semitones, quick: bool = True) -> torch.Tensor:
+        """Shift the pitch of x [B, C, T] keeping T (ref:audiotools/core/effects.py:247-277).  ``n_semitones`` is one
+        value for the batch (the reference's API) or one value per item (host list / tensor with B entries): all
+        items go through the same launches, grouped by their shift; a shift of 0 copies the item."""
         x = self._prep(x, "x")
-        if float(n_semitones) == 0.0:
-            return x.clone()
         T = x.shape[-1]
         rows = x.numel() // T
-        ws_bytes = self.lib.b2a_pitch_shift_workspace_bytes(rows, T, int(sample_rate), float(n_semitones))
+        vals = np.asarray(torch.as_tensor(n_semitones).detach().cpu().reshape(-1).numpy(), dtype=np.float32)
+        if vals.size == 1:
+            if float(vals[0]) == 0.0:
+                return x.clone()
+            uniq, row_group = vals, None
+        else:
+            B = x.shape[0]
+            assert vals.size == B, f"{vals.size} shifts for a batch of {B}"
+            uniq, inv = np.unique(vals, return_inverse=True)
+            if uniq.size == 1:
+                return self.pitch_shift(x, sample_rate, float(uniq[0]), quick)
+            if uniq.size > self.MAX_PITCH_GROUPS:  # more distinct shifts than one launch takes: split the batch
+                out = torch.empty_like(x)
+                for i in range(0, uniq.size, self.MAX_PITCH_GROUPS):
+                    sel = np.nonzero(np.isin(vals, uniq[i:i + self.MAX_PITCH_GROUPS]))[0]
+                    idx = torch.as_tensor(sel, device=x.device)
+                    out[idx] = self.pitch_shift(x[idx], sample_rate, vals[sel], quick)
+                return out
+            per_row = np.repeat(inv.astype(np.int32), rows // B)
+            row_group = torch.from_numpy(per_row).to(x.device, non_blocking=True)
+        sem = np.ascontiguousarray(uniq, dtype=np.float32)
+        sem_p = sem.ctypes.data_as(ctypes.c_void_p)
+        ws_bytes = self.lib.b2a_pitch_shift_multi_workspace_bytes(rows, T, int(sample_rate), sem_p, int(sem.size))
+        if ws_bytes == 0:
+            raise NotImplementedError(f"pitch_shift: unsupported shifts {sem.tolist()} (|semitones| <= 24)")
         ws = torch.empty(ws_bytes, dtype=torch.uint8, device=x.device)
         out = torch.empty_like(x)
-        rc = self.lib.b2a_pitch_shift_f32(_dptr(x), rows, T, int(sample_rate), float(n_semitones), _dptr(out), _dptr(ws),
-                                          ws_bytes, self._stream(x))
+        rc = self.lib.b2a_pitch_shift_multi_f32(_dptr(x), rows, T, int(sample_rate), sem_p, int(sem.size),
+                                                _dptr(row_group), _dptr(out), _dptr(ws), ws_bytes, self._stream(x))
         self.lib.check(rc)
         self.launches += 4
         return out

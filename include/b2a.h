@@ -172,6 +172,13 @@ int b2a_resample_f32(const float* x, int64_t rows, int64_t T, int old_r, int new
 size_t b2a_pitch_shift_workspace_bytes(int64_t rows, int64_t T, int sr, float semitones);
 int b2a_pitch_shift_f32(const float* x, int64_t rows, int64_t T, int sr, float semitones, float* out, void* ws,
                         size_t ws_bytes, void* stream);
+/* Several shifts in one launch (a batch whose items drew different shifts, e.g. a PitchShift transform):
+ * semitones_h HOST [n_groups] (n_groups <= 8 distinct values, 0 = copy the row), row_group DEVICE [rows] int32
+ * in [0, n_groups) (nullable when n_groups == 1).  Rows of all groups share every launch, so the one-CTA-per-row
+ * search fills the GPU with the whole batch instead of one group at a time. */
+size_t b2a_pitch_shift_multi_workspace_bytes(int64_t rows, int64_t T, int sr, const float* semitones_h, int n_groups);
+int b2a_pitch_shift_multi_f32(const float* x, int64_t rows, int64_t T, int sr, const float* semitones_h, int n_groups,
+                              const int32_t* row_group, float* out, void* ws, size_t ws_bytes, void* stream);
 
 #ifdef __cplusplus
 }

@@ -406,6 +406,20 @@ def test_pitch_shift_properties(at):
         coef = np.linalg.lstsq(A, y[0, 0, 4000:-4000].double().numpy(), rcond=None)[0]
         assert abs(np.hypot(*coef) - 0.5) < 0.01
         assert (y[0, 0, 4000:-4000].double().numpy() - A @ coef).std() < 0.03 * 0.5
+    # per-item shifts share one set of launches and equal the per-group calls; 0 copies the item
+    xm = torch.cat([x, x.flip(0)], 0)
+    ym = at.AudioSignal(xm.clone(), sr).to(DEV).pitch_shift([2, 0, -2, 2]).audio_data.cpu()
+    y2 = at.AudioSignal(xm[[0, 3]].clone(), sr).to(DEV).pitch_shift(2).audio_data.cpu()
+    assert torch.equal(ym[[0, 3]], y2) and torch.equal(ym[1], xm[1])
+    assert torch.equal(ym[2:3], at.AudioSignal(xm[2:3].clone(), sr).to(DEV).pitch_shift(-2).audio_data.cpu())
+    from audiotools_b200.data import transforms as tfm
+
+    t = tfm.PitchShift(("choice", [-2, 2]))
+    sig4 = at.AudioSignal(xm.clone(), sr)
+    kw = at.util.prepare_batch(t.batch_instantiate([0, 1, 2, 3], sig4), DEV)
+    shifts = at.util.host_view(kw["PitchShift"]["n_semitones"]).tolist()
+    out = t(sig4.to(DEV), **kw).audio_data.cpu()
+    assert torch.equal(out, at.AudioSignal(xm.clone(), sr).to(DEV).pitch_shift(shifts).audio_data.cpu())
     dc = torch.full((2, 1, 60000), 0.25)  # windows and interpolation weights sum to one
     for st in (2, -5):
         y = at.AudioSignal(dc.clone(), sr).to(DEV).pitch_shift(st).audio_data.cpu()

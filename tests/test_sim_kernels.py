@@ -176,6 +176,15 @@ def test_pitch_shift_properties(eng):
         assert abs(np.hypot(*coef) - 0.5) < 0.01
         assert (y[0, 0, 1500:-1500].double().numpy() - A @ coef).std() < 0.06 * 0.5
     assert torch.equal(eng.pitch_shift(x, sr, 0), x)
+    # several shifts in one launch == each group on its own; a shift of 0 copies the item bit for bit
+    xm = torch.cat([x, x.flip(0)], 0)  # 4 items
+    ym = eng.pitch_shift(xm, sr, [3.0, 0.0, -2.0, 3.0])
+    assert torch.equal(ym[[0, 3]], eng.pitch_shift(xm[[0, 3]], sr, 3.0))
+    assert torch.equal(ym[2:3], eng.pitch_shift(xm[2:3], sr, -2.0))
+    assert torch.equal(ym[1], xm[1])
+    stereo = eng.pitch_shift(xm.reshape(2, 2, -1), sr, [3.0, -2.0])  # group per item, both channels of an item together
+    assert torch.equal(stereo[0], eng.pitch_shift(xm[:2].reshape(1, 2, -1), sr, 3.0)[0])
+    assert torch.equal(stereo[1], eng.pitch_shift(xm[2:].reshape(1, 2, -1), sr, -2.0)[0])
     # overlap-add windows and interpolation weights both sum to one: a constant stays that constant
     dc = torch.full((1, 1, 9000), 0.25)
     for st in (2, -5):

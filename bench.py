@@ -186,16 +186,41 @@ def run_ours(args):
     fb, lo, hi = AudioSignal._mel_tables(SR, N_FFT, N_MELS, 0.0, None, dev)
     from audiotools_b200.parallel import LoudnessGather
 
-    gather = LoudnessGather(side_stream=torch.cuda.Stream(device=dev))  # NCCL all-gather on a side stream
+    # Whole-batch loudness statistics (the path's only exchange: 256 B per rank and step).  Preferred: one-sided
+    # stores into every peer's buffer over NVLink (csrc/peer.cu) -- no rendezvous, no NCCL kernel next to the
+    # persistent spectral kernel.  Fallback if the peer mapping cannot be set up: NCCL all-gather on a side stream.
+    exchange, gather, exchange_kind = None, None, "none"
+    if world > 1 and not os.environ.get("B2A_BENCH_NO_GATHER"):
+        try:
+            if os.environ.get("B2A_BENCH_NCCL_GATHER"):
+                raise RuntimeError("NCCL all-gather requested")
+            from audiotools_b200.parallel import PeerLoudnessExchange
+
+            exchange = PeerLoudnessExchange(n_max=B)
+            exchange_kind = "peer-store (cudaIpc + NVLink P2P stores, csrc/peer.cu)"
+        except Exception as e:  # noqa: BLE001
+            gather = LoudnessGather(side_stream=torch.cuda.Stream(device=dev))
+            exchange_kind = f"nccl all_gather on a side stream ({type(e).__name__}: {e})"
     spec_events = []
+    pending = []  # statistics are logging data: they are consumed one step late, never inside the step that made them
+
+    def drain():
+        while pending:
+            kind, h = pending.pop(0)
+            if kind == "peer":
+                exchange.collect(h)
+            else:
+                gather.wait()
 
     def step(i, timed=False):
         x = xs[i % NBUF]
-        if world > 1:
-            gather.wait()  # previous step's all-gather (long finished) before its output buffer is reused
+        drain()  # previous step's statistics (long complete)
         lu = eng.lufs(x, SR, target_db=db)
-        if world > 1:  # whole-batch loudness statistics: 256 B/rank all-gather, overlapping the spectral kernel
+        if exchange is not None:
+            pending.append(("peer", exchange.put(lu["loud"])))
+        elif gather is not None:
             lu["loud_all"] = gather(lu["loud"])
+            pending.append(("nccl", None))
         if timed:
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
@@ -204,9 +229,6 @@ def run_ours(args):
         if timed:
             e1.record()
             spec_events.append((e0, e1))
-        # The gathered statistics are logging data, not an input of the data path: they are consumed one step late
-        # (`gather.wait()` of step i runs at the top of step i+1 and once after the loop), so a rank never stalls
-        # on its peers inside a step.
         return out, lu
 
     def barrier():
@@ -220,17 +242,17 @@ def run_ours(args):
         step(i)
     barrier()
     launches0 = eng.launches
+    xl0 = exchange.launches if exchange is not None else 0
     t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     with ClockSampler(local) as clocks:
         t0.record()
         for i in range(args.steps):
             step(args.warmup + i, timed=True)
-        if world > 1:
-            gather.wait()  # the last step's statistics are inside the timed region too
+        drain()  # the last step's statistics are inside the timed region too
         t1.record()
         barrier()
     ms = t0.elapsed_time(t1)
-    launches = eng.launches - launches0
+    launches = eng.launches - launches0 + (exchange.launches - xl0 if exchange is not None else 0)
     spec_ms = sum(a.elapsed_time(b) for a, b in spec_events) / max(1, len(spec_events))
     tms = torch.tensor([ms], device=dev, dtype=torch.float64)
     if world > 1:
@@ -283,6 +305,8 @@ def run_ours(args):
     if world > 1:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e_value = world * B * e2e_steps / float(te.item())
+    if exchange is not None:
+        exchange.close()  # collective (barrier inside): all ranks, before the non-zero ranks leave
 
     if rank != 0:
         if world > 1:
@@ -321,7 +345,7 @@ def run_ours(args):
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": WORKLOAD, "global_batch": world * B, "per_gpu_batch": B,
                    "parallelism": f"batch-sharded x{world}, no data-path collective"
-                                  + (" (+ all-gather of per-item LUFS)" if world > 1 else ""),
+                                  + (f" (+ per-item LUFS exchange: {exchange_kind})" if world > 1 else ""),
                    "l2": f"inputs rotate over {NBUF} distinct {B * BYTES_X / 1e6:.0f} MB batches (> 126 MB L2)"},
         "roofline": roof, "cpu_baseline": cpu,
         "e2e": {"value": e2e_value, "unit": "clips/s", "h2d_bytes_per_step": B * BYTES_X,

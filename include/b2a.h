@@ -180,6 +180,25 @@ size_t b2a_pitch_shift_multi_workspace_bytes(int64_t rows, int64_t T, int sr, co
 int b2a_pitch_shift_multi_f32(const float* x, int64_t rows, int64_t T, int sr, const float* semitones_h, int n_groups,
                               const int32_t* row_group, float* out, void* ws, size_t ws_bytes, void* stream);
 
+/* ---- one-sided statistics exchange between the GPUs of a node (NVLink peer memory) --------------------
+ * The path shards by batch item with no data-path collective; the one exchange is the per-item loudness vector for
+ * whole-batch statistics (the reference has no multi-GPU code of its own: SURVEY.md 8e).  Every rank owns a small
+ * buffer (b2a_peer_buffer_create: cudaMalloc + cudaIpc handle), maps its peers' buffers (b2a_peer_buffer_open on
+ * the 64-byte handles, exchanged by the host side), then per step
+ *   b2a_peer_put_f32      stores src[0..n) into its slot of EVERY rank's buffer and publishes `seq` (system-scope
+ *                         release); no rendezvous, no NCCL kernel;
+ *   b2a_peer_collect_f32  waits (bounded) until all ranks published `seq` in the LOCAL buffer, gathers [world, n].
+ * seq >= 1 grows by one per step; slots are double buffered by seq parity: a put of seq may only be issued after
+ * the local collect of seq-1 (stream order) -- then no slot is overwritten before every reader has read it. */
+size_t b2a_peer_buffer_bytes(int world, int n_max);
+int b2a_peer_buffer_create(int world, int n_max, void** dev_ptr, unsigned char* handle_out /*[64]*/);
+int b2a_peer_buffer_open(const unsigned char* handle /*[64]*/, void** peer_ptr);
+int b2a_peer_buffer_close(void* peer_ptr);
+int b2a_peer_buffer_destroy(void* dev_ptr);
+int b2a_peer_put_f32(const float* src, int n, void* const* peer_bufs_h /*host [world]*/, int world, int rank,
+                     int n_max, int seq, void* stream);
+int b2a_peer_collect_f32(const void* local_buf, int world, int n, int n_max, int seq, float* out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

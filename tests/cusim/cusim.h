@@ -242,6 +242,7 @@ static inline void sincospif(float x, float* s, float* c) {
 }
 static inline void sincospi(double x, double* s, double* c) { *s = sin(M_PI * x); *c = cos(M_PI * x); }
 static inline float __fdividef(float a, float b) { return a / b; }
+static inline void __threadfence_system() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
 static inline unsigned __float_as_uint(float v) { unsigned u; memcpy(&u, &v, 4); return u; }
 static inline float cospif(float x) { return (float)cos(M_PI * (double)x); }
 static inline float sinpif(float x) { return (float)sin(M_PI * (double)x); }

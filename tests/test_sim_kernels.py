@@ -262,3 +262,36 @@ def test_istft_zero_tail_and_envelope_check(eng):
         eng.istft(X[:, None], n_fft, n_fft, wz, 1500)
     with pytest.raises(NotImplementedError):
         eng.istft(torch.zeros(1, 1, 2049, 5, dtype=torch.complex64), 4096, 1024, torch.ones(4096), 4096)
+
+
+# ------------------------------------------------------------------------------------------
+# one-sided peer exchange (csrc/peer.cu): two "ranks" in one process, buffers in host memory
+# ------------------------------------------------------------------------------------------
+def test_peer_put_collect_two_ranks(eng):
+    import ctypes
+
+    lib, world, n_max = eng.lib, 2, 8
+    assert lib.b2a_peer_buffer_bytes(world, n_max) == (2 * world * n_max + 2 * world + 4) * 4
+    assert lib.b2a_peer_buffer_bytes(17, 8) == 0
+    bufs, peers = [], (ctypes.c_void_p * world)()
+    for r in range(world):
+        p, h = ctypes.c_void_p(), (ctypes.c_ubyte * 64)()
+        lib.check(lib.b2a_peer_buffer_create(world, n_max, ctypes.byref(p), h))
+        q = ctypes.c_void_p()
+        lib.check(lib.b2a_peer_buffer_open(h, ctypes.byref(q)))
+        assert q.value == p.value
+        bufs.append(p.value)
+        peers[r] = p.value
+    vals = {r: [torch.arange(5, dtype=torch.float32) + 10 * r + 100 * s for s in (1, 2, 3)] for r in range(world)}
+    for s in (1, 2, 3):  # three steps: both parities and a reuse of the first slot
+        for r in range(world):
+            v = vals[r][s - 1]
+            lib.check(lib.b2a_peer_put_f32(ctypes.c_void_p(v.data_ptr()), 5, peers, world, r, n_max, s, None))
+        for r in range(world):
+            out = torch.empty(world * 5)
+            lib.check(lib.b2a_peer_collect_f32(ctypes.c_void_p(bufs[r]), world, 5, n_max, s,
+                                               ctypes.c_void_p(out.data_ptr()), None))
+            assert torch.equal(out, torch.cat([vals[0][s - 1], vals[1][s - 1]]))
+    assert lib.b2a_peer_put_f32(None, 5, peers, world, 0, n_max, 1, None) != 0  # null source is refused
+    for b in bufs:
+        lib.check(lib.b2a_peer_buffer_destroy(ctypes.c_void_p(b)))

@@ -50,6 +50,8 @@ SIGNATURES = {
     "b2a_peer_buffer_destroy": (c_int, [c_void_p]),
     "b2a_peer_put_f32": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
     "b2a_peer_collect_f32": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
+    "b2a_peer_exchange_f32": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_int, c_int, c_void_p,
+                                      c_void_p]),
     "b2a_istft_supported": (c_int, [c_int, c_int]),
     "b2a_istft_f32": (c_int, [c_void_p, c_int64, c_int64, c_int, c_int, c_void_p, c_int, c_int64, c_int64, c_void_p,
                               c_void_p]),

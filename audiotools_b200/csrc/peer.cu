@@ -79,6 +79,44 @@ peer_collect_kernel(const float* __restrict__ local, int world, int n, int n_max
   if (threadIdx.x == 0 && !s_ok) *status = seq;
 }
 
+// One launch per step: CTAs 0..world-1 put sequence `seq_put`, CTA `world` collects sequence `seq_col` (the
+// previous step's, already published by every rank long ago) -- the steady state of a pipelined consumer.
+__global__ void __launch_bounds__(256)
+peer_exchange_kernel(const float* __restrict__ src, int n, const B2A_GRID_CONSTANT Peers peers, int world, int rank,
+                     int n_max, int seq_put, const float* __restrict__ local, int n_col, int seq_col,
+                     float* __restrict__ out, long long max_spins) {
+  if ((int)blockIdx.x < world) {
+    float* base = peers.buf[blockIdx.x];
+    float* dst = base + ((size_t)(seq_put & 1) * world + rank) * n_max;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) dst[i] = src[i];
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      int* flags = reinterpret_cast<int*>(base + flag_offset_floats(world, n_max));
+      st_release_sys(flags + (seq_put & 1) * world + rank, seq_put);
+    }
+    return;
+  }
+  const int* flags = reinterpret_cast<const int*>(local + flag_offset_floats(world, n_max)) + (seq_col & 1) * world;
+  int* status = const_cast<int*>(reinterpret_cast<const int*>(local + flag_offset_floats(world, n_max))) + 2 * world;
+  __shared__ int s_ok;
+  if (threadIdx.x == 0) s_ok = 1;
+  __syncthreads();
+  if ((int)threadIdx.x < world) {
+    long long spins = 0;
+    while (ld_acquire_sys(flags + threadIdx.x) - seq_col < 0) {
+      if (++spins > max_spins) { s_ok = 0; break; }
+    }
+  }
+  __syncthreads();
+  const float* data = local + (size_t)(seq_col & 1) * world * n_max;
+  for (int i = threadIdx.x; i < world * n_col; i += blockDim.x) {
+    const int r = i / n_col, k = i - r * n_col;
+    out[i] = s_ok ? data[(size_t)r * n_max + k] : __int_as_float(0x7fc00000);
+  }
+  if (threadIdx.x == 0 && !s_ok) *status = seq_col;
+}
+
 }  // namespace peer
 }  // namespace b2a
 
@@ -163,6 +201,25 @@ extern "C" int b2a_peer_collect_f32(const void* local_buf, int world, int n, int
   const long long max_spins = 20000000LL;  // a few seconds of polling local memory, then give up (NaN + status)
   B2A_LAUNCH(peer_collect_kernel, dim3(1), dim3(256), 0, stream, (const float*)local_buf, world, n, n_max, seq, out,
              max_spins);
+  B2A_CUDA_OK(cudaGetLastError());
+  return B2A_OK;
+}
+
+extern "C" int b2a_peer_exchange_f32(const float* src, int n, void* const* peer_bufs_h, int world, int rank, int n_max,
+                                     int seq_put, const void* local_buf, int n_collect, int seq_collect, float* out,
+                                     void* stream) {
+  B2A_REQUIRE(src && peer_bufs_h && local_buf && out, B2A_E_INVALID, "peer_exchange: null pointer");
+  B2A_REQUIRE(world >= 1 && world <= MAX_WORLD && rank >= 0 && rank < world && n >= 1 && n <= n_max &&
+                  n_collect >= 1 && n_collect <= n_max && seq_put >= 2 && seq_collect == seq_put - 1,
+              B2A_E_INVALID, "peer_exchange: bad argument (collects seq_put - 1)");
+  Peers peers;
+  memset(&peers, 0, sizeof(peers));
+  for (int i = 0; i < world; ++i) {
+    B2A_REQUIRE(peer_bufs_h[i], B2A_E_INVALID, "peer_exchange: buffer of rank %d is not mapped", i);
+    peers.buf[i] = (float*)peer_bufs_h[i];
+  }
+  B2A_LAUNCH(peer_exchange_kernel, dim3((unsigned)world + 1), dim3(256), 0, stream, src, n, peers, world, rank, n_max,
+             seq_put, (const float*)local_buf, n_collect, seq_collect, out, 20000000LL);
   B2A_CUDA_OK(cudaGetLastError());
   return B2A_OK;
 }

@@ -141,6 +141,26 @@ class PeerLoudnessExchange:
         self.launches += 1
         return out
 
+    def put_collect(self, loud_local: torch.Tensor):
+        """Steady state of a one-step-late consumer, ONE launch: publish ``loud_local`` as the next sequence number and
+        return ``(seq, statistics of seq - 1)`` (``None`` on the very first call)."""
+        if self._collected == self.seq:  # nothing outstanding (first call, or already drained): plain put
+            return self.put(loud_local), None
+        assert loud_local.is_cuda and loud_local.dtype == torch.float32 and loud_local.is_contiguous()
+        n = loud_local.numel()
+        prev = self.seq
+        n_prev = self._n.pop(prev)
+        self.seq += 1
+        self._n[self.seq] = n
+        out = torch.empty(self.world * n_prev, dtype=torch.float32, device=self.device)
+        stream = self._ct.c_void_p(torch.cuda.current_stream(loud_local.device).cuda_stream)
+        self.lib.check(self.lib.b2a_peer_exchange_f32(
+            self._ct.c_void_p(loud_local.data_ptr()), n, self.peers, self.world, self.rank, self.n_max, self.seq,
+            self._ct.c_void_p(self.local), n_prev, prev, self._ct.c_void_p(out.data_ptr()), stream))
+        self._collected = prev
+        self.launches += 1
+        return self.seq, out
+
     def close(self):
         if getattr(self, "local", None) is None:
             return

@@ -214,10 +214,12 @@ def run_ours(args):
 
     def step(i, timed=False):
         x = xs[i % NBUF]
-        drain()  # previous step's statistics (long complete)
+        if exchange is None:
+            drain()  # previous step's statistics (long complete)
         lu = eng.lufs(x, SR, target_db=db)
-        if exchange is not None:
-            pending.append(("peer", exchange.put(lu["loud"])))
+        if exchange is not None:  # ONE launch: publish this step's vector, read the previous step's statistics
+            seq, lu["loud_all_prev"] = exchange.put_collect(lu["loud"])
+            pending[:] = [("peer", seq)]
         elif gather is not None:
             lu["loud_all"] = gather(lu["loud"])
             pending.append(("nccl", None))

@@ -198,6 +198,10 @@ int b2a_peer_buffer_destroy(void* dev_ptr);
 int b2a_peer_put_f32(const float* src, int n, void* const* peer_bufs_h /*host [world]*/, int world, int rank,
                      int n_max, int seq, void* stream);
 int b2a_peer_collect_f32(const void* local_buf, int world, int n, int n_max, int seq, float* out, void* stream);
+/* steady state of a consumer that reads the statistics one step late: put(seq_put) and collect(seq_put - 1) in ONE
+ * launch (the collect CTA never waits in practice: that sequence was published a whole step ago). */
+int b2a_peer_exchange_f32(const float* src, int n, void* const* peer_bufs_h, int world, int rank, int n_max,
+                          int seq_put, const void* local_buf, int n_collect, int seq_collect, float* out, void* stream);
 
 #ifdef __cplusplus
 }

@@ -37,6 +37,17 @@ def _worker(rank, world, port, q):
             ok &= torch.equal(ex.collect(seq_prev), ref_prev)
         pending = (ex.put(loud), ref)
     ok &= torch.equal(ex.collect(pending[0]), pending[1])
+    refs = []
+    for step in range(5):  # the fused one-launch form: put(seq) + collect(seq - 1)
+        loud = AudioSignal(x * (1 + 0.05 * step), 44100).loudness().contiguous()
+        ref = torch.empty(world * loud.numel(), device=loud.device)
+        dist.all_gather_into_tensor(ref, loud)
+        refs.append(ref)
+        seq, prev = ex.put_collect(loud)
+        ok &= (prev is None) == (step == 0)
+        if prev is not None:
+            ok &= torch.equal(prev, refs[step - 1])
+    ok &= torch.equal(ex.collect(seq), refs[-1])
     torch.cuda.synchronize()
     ex.close()
     dist.destroy_process_group()

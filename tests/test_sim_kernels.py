@@ -292,6 +292,16 @@ def test_peer_put_collect_two_ranks(eng):
             lib.check(lib.b2a_peer_collect_f32(ctypes.c_void_p(bufs[r]), world, 5, n_max, s,
                                                ctypes.c_void_p(out.data_ptr()), None))
             assert torch.equal(out, torch.cat([vals[0][s - 1], vals[1][s - 1]]))
+    # fused form: put(4) + collect(3) in one launch per rank (sequence 3 was published above)
+    nxt = {r: torch.arange(5, dtype=torch.float32) - 7 * r for r in range(world)}
+    for r in range(world):
+        out = torch.empty(world * 5)
+        lib.check(lib.b2a_peer_exchange_f32(ctypes.c_void_p(nxt[r].data_ptr()), 5, peers, world, r, n_max, 4,
+                                            ctypes.c_void_p(bufs[r]), 5, 3, ctypes.c_void_p(out.data_ptr()), None))
+        assert torch.equal(out, torch.cat([vals[0][2], vals[1][2]]))
+    out = torch.empty(world * 5)
+    lib.check(lib.b2a_peer_collect_f32(ctypes.c_void_p(bufs[0]), world, 5, n_max, 4, ctypes.c_void_p(out.data_ptr()), None))
+    assert torch.equal(out, torch.cat([nxt[0], nxt[1]]))
     assert lib.b2a_peer_put_f32(None, 5, peers, world, 0, n_max, 1, None) != 0  # null source is refused
     for b in bufs:
         lib.check(lib.b2a_peer_buffer_destroy(ctypes.c_void_p(b)))

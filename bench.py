@@ -345,7 +345,7 @@ def run_ours(args):
             "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
             # dram__bytes_read.sum + dram__bytes_write.sum of one launch at B=64 from the ncu --set full capture
             # profiles/r01h_prof_spectral_v7_ncu_full_summary.csv (226.0 + 229.2 MB), scaled to this batch
-            "traffic": (226.0e6 + 229.2e6) * B / 64,
+            "traffic": (226.3e6 + 229.2e6) * B / 64,  # dram__bytes_read + write of one launch: profiles/r01r_prof_spectral_final_ncu_full_summary.csv
             "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes, "ms_per_launch": spec_ms,
             "rest_of_step_ms": lufs_ms,
             "rest_of_step": "lufs kernels (read x once: %.0f GB/s algorithmic)" % (B * BYTES_X / max(lufs_ms, 1e-9) / 1e6)}

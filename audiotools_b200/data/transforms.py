@@ -389,13 +389,153 @@ class RescaleAudio(BaseTransform):
         return signal.ensure_max_of_audio(self.val)
 
 
-class InvertPhase(BaseTransform):
-    def __init__(self, name: str = None, prob: float = 1):
-        super().__init__(name=name, prob=prob)
+class ShiftPhase(SpectralTransform):
+    """stft -> ``phase += shift`` -> istft (ref :1200-1229)."""
 
-    def _transform(self, signal):
-        signal.audio_data = -signal.audio_data
-        return signal
+    def __init__(self, shift: tuple = ("uniform", -np.pi, np.pi), name: str = None, prob: float = 1):
+        super().__init__(name=name, prob=prob)
+        self.shift = shift
+
+    def _instantiate(self, state: RandomState):
+        return {"shift": util.sample_from_dist(self.shift, state)}
+
+    def _transform(self, signal, shift):
+        return signal.shift_phase(shift)
+
+
+class InvertPhase(ShiftPhase):
+    """Phase shift by pi (ref :1232-1247)."""
+
+    def __init__(self, name: str = None, prob: float = 1):
+        super().__init__(shift=("const", np.pi), name=name, prob=prob)
+
+
+class CorruptPhase(SpectralTransform):
+    """Adds host-drawn (seeded) Gaussian noise to the phase (ref :1250-1278)."""
+
+    def __init__(self, scale: tuple = ("uniform", 0, np.pi), name: str = None, prob: float = 1):
+        super().__init__(name=name, prob=prob)
+        self.scale = scale
+
+    def _instantiate(self, state: RandomState, signal: AudioSignal = None):
+        scale = util.sample_from_dist(self.scale, state)
+        # the shape of one item's phase, without touching the device: [C, F, N]
+        wl, hop, _, match_stride, _ = signal._resolve_stft(None, None, None, None, None)
+        right_pad, pad = signal.compute_stft_padding(wl, hop, match_stride)
+        if signal.stft_data is not None:
+            n_frames = signal.stft_data.shape[-1]
+        else:
+            from ..engine import get_engine
+
+            n_frames = get_engine().num_frames(signal.signal_length, wl, hop, pad, right_pad, 2 if match_stride else 0)
+        shape = (signal.num_channels, wl // 2 + 1, n_frames)
+        corruption = state.normal(scale=scale, size=shape)
+        return {"corruption": corruption.astype("float32")}
+
+    def _transform(self, signal, corruption):
+        return signal.shift_phase(shift=corruption)
+
+
+class FrequencyMask(SpectralTransform):
+    """Zeroes a frequency band around a drawn centre (SpecAugment; ref :1281-1324)."""
+
+    def __init__(self, f_center: tuple = ("uniform", 0.0, 1.0), f_width: tuple = ("const", 0.1), name: str = None,
+                 prob: float = 1):
+        super().__init__(name=name, prob=prob)
+        self.f_center = f_center
+        self.f_width = f_width
+
+    def _instantiate(self, state: RandomState, signal: AudioSignal):
+        f_center = util.sample_from_dist(self.f_center, state)
+        f_width = util.sample_from_dist(self.f_width, state)
+        fmin = max(f_center - (f_width / 2), 0.0)
+        fmax = min(f_center + (f_width / 2), 1.0)
+        return {"fmin_hz": (signal.sample_rate / 2) * fmin, "fmax_hz": (signal.sample_rate / 2) * fmax}
+
+    def _transform(self, signal, fmin_hz: float, fmax_hz: float):
+        return signal.mask_frequencies(fmin_hz=fmin_hz, fmax_hz=fmax_hz)
+
+
+class TimeMask(SpectralTransform):
+    """Zeroes a span of frames around a drawn centre (SpecAugment; ref :1327-1369)."""
+
+    def __init__(self, t_center: tuple = ("uniform", 0.0, 1.0), t_width: tuple = ("const", 0.025), name: str = None,
+                 prob: float = 1):
+        super().__init__(name=name, prob=prob)
+        self.t_center = t_center
+        self.t_width = t_width
+
+    def _instantiate(self, state: RandomState, signal: AudioSignal):
+        t_center = util.sample_from_dist(self.t_center, state)
+        t_width = util.sample_from_dist(self.t_width, state)
+        tmin = max(t_center - (t_width / 2), 0.0)
+        tmax = min(t_center + (t_width / 2), 1.0)
+        return {"tmin_s": signal.signal_duration * tmin, "tmax_s": signal.signal_duration * tmax}
+
+    def _transform(self, signal, tmin_s: float, tmax_s: float):
+        return signal.mask_timesteps(tmin_s=tmin_s, tmax_s=tmax_s)
+
+
+class MaskLowMagnitudes(SpectralTransform):
+    """Zeroes STFT cells below a drawn dB threshold (ref :1372-1402)."""
+
+    def __init__(self, db_cutoff: tuple = ("uniform", -10, 10), name: str = None, prob: float = 1):
+        super().__init__(name=name, prob=prob)
+        self.db_cutoff = db_cutoff
+
+    def _instantiate(self, state: RandomState, signal: AudioSignal = None):
+        return {"db_cutoff": util.sample_from_dist(self.db_cutoff, state)}
+
+    def _transform(self, signal, db_cutoff: float):
+        return signal.mask_low_magnitudes(db_cutoff)
+
+
+class Smoothing(BaseTransform):
+    """Convolves the signal with a drawn window and restores its peak (ref :1405-1453)."""
+
+    def __init__(self, window_type: tuple = ("const", "average"),
+                 window_length: tuple = ("choice", [8, 16, 32, 64, 128, 256, 512]), name: str = None, prob: float = 1):
+        super().__init__(name=name, prob=prob)
+        self.window_type = window_type
+        self.window_length = window_length
+
+    def _instantiate(self, state: RandomState, signal: AudioSignal = None):
+        window_type = util.sample_from_dist(self.window_type, state)
+        window_length = util.sample_from_dist(self.window_length, state)
+        window = signal.get_window(window_type=window_type, window_length=window_length, device="cpu")
+        return {"window": AudioSignal(window.clone(), signal.sample_rate)}
+
+    def _transform(self, signal, window):
+        sscale = signal.audio_data.abs().max(dim=-1, keepdim=True).values
+        sscale = torch.where(sscale == 0.0, torch.ones_like(sscale), sscale)
+        out = signal.convolve(window)
+        oscale = out.audio_data.abs().max(dim=-1, keepdim=True).values
+        oscale = torch.where(oscale == 0.0, torch.ones_like(oscale), oscale)
+        return out * (sscale / oscale)
+
+
+def _refill_masked_cells(signal):
+    """Replace the cells a band mask zeroed (|X| == 0 and angle == 0) by N(0,1) magnitude / phase noise drawn on
+    the device (ref :1485-1495 / :1526-1536)."""
+    mag, phase = signal.magnitude, signal.phase
+    mag_r, phase_r = torch.randn_like(mag), torch.randn_like(phase)
+    mask = (mag == 0.0) & (phase == 0.0)
+    signal.stft_data = torch.where(mask, mag_r, mag) * torch.exp(1j * torch.where(mask, phase_r, phase))
+    return signal
+
+
+class TimeNoise(TimeMask):
+    """TimeMask, then the masked frames are filled with noise (ref :1456-1495)."""
+
+    def _transform(self, signal, tmin_s: float, tmax_s: float):
+        return _refill_masked_cells(signal.mask_timesteps(tmin_s=tmin_s, tmax_s=tmax_s, val=0.0))
+
+
+class FrequencyNoise(FrequencyMask):
+    """FrequencyMask, then the masked band is filled with noise (ref :1498-1536)."""
+
+    def _transform(self, signal, fmin_hz: float, fmax_hz: float):
+        return _refill_masked_cells(signal.mask_frequencies(fmin_hz=fmin_hz, fmax_hz=fmax_hz))
 
 
 class Silence(BaseTransform):

@@ -109,6 +109,32 @@ class Engine:
         self.launches += 1
         return out
 
+    # ------------------------------------------------------------------ spectral masks
+    def spec_band_mask(self, spec: torch.Tensor, axis_vals: torch.Tensor, lo: torch.Tensor, hi: torch.Tensor,
+                       axis: int, val: float = 0.0) -> torch.Tensor:
+        """In place: ``spec[b, c, f, n] = val * exp(1j * val)`` where ``lo[b] <= axis_vals[f or n] < hi[b]``
+        (ref:audiotools/core/dsp.py:217-306).  spec [B, C, F, N] complex64, contiguous; returns it."""
+        if not torch.is_complex(spec) or spec.dtype != torch.complex64 or not spec.is_contiguous():
+            raise TypeError("spec_band_mask: spec must be a contiguous complex64 tensor")
+        if self.require_cuda and not spec.is_cuda:
+            raise RuntimeError(f"stft_data is on {spec.device}: audiotools_b200 runs on CUDA (sm_100a) only and has "
+                               "no CPU fallback")
+        B, C, F, N = spec.shape
+        axis_vals = self._prep(axis_vals.to(spec.device), "axis_vals")
+        lo = self._prep(lo.to(spec.device).reshape(-1), "lo")
+        hi = self._prep(hi.to(spec.device).reshape(-1), "hi")
+        if lo.numel() == 1:
+            lo, hi = lo.expand(B).contiguous(), hi.expand(B).contiguous()
+        assert lo.numel() == B and hi.numel() == B and axis_vals.numel() == (F if axis == 0 else N)
+        v = torch.tensor(float(val), dtype=torch.float32)
+        fill = v * torch.exp(1j * v)  # the reference's own arithmetic for a filled cell (complex64)
+        rc = self.lib.b2a_spec_band_mask_f32(_dptr(torch.view_as_real(spec)), B * C, F, N, _dptr(axis_vals), _dptr(lo),
+                                             _dptr(hi), C, int(axis), float(fill.real), float(fill.imag),
+                                             self._stream(spec))
+        self.lib.check(rc)
+        self.launches += 1
+        return spec
+
     # ------------------------------------------------------------------ loudness
     def lufs(self, x: torch.Tensor, sample_rate: float, filter_class: str = "K-weighting",
              block_size: float = 0.400, padded_length: Optional[int] = None,

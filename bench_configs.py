@@ -3,7 +3,7 @@
 bench.py, which measures configs[1]).  One JSON line per config: device-resident throughput (CUDA events,
 >= 3 warm-ups, inputs larger than L2 or rotated), algorithmic bytes, and the CPU oracle on a bounded sample.
 
-    python bench_configs.py [--only cfg1,cfg3,cfg4,istft] [--no-cpu]
+    python bench_configs.py [--only cfg1,cfg3,cfg4,istft,specaug] [--no-cpu]
 """
 import argparse
 import json
@@ -41,7 +41,7 @@ def cpu_time(fn, reps=2):
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--only", default="cfg1,cfg3,cfg4,istft")
+    ap.add_argument("--only", default="cfg1,cfg3,cfg4,istft,specaug")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
     import __graft_entry__ as graft
@@ -137,6 +137,42 @@ def main():
         print(json.dumps({"config": "istft 64x2ch 10s@44.1k n_fft=2048 hop=512", "ms": ms, "ms_torch_istft_cufft": ms_torch,
                           "clips_per_s": 64 / ms * 1e3, "alg_bytes": alg, "achieved_GBps": alg / ms / 1e6,
                           "frac_of_hbm_peak": alg / ms / 1e6 / peak}))
+
+    if "specaug" in only:  # SpectralTransform chain stft -> FrequencyMask -> TimeMask -> istft at cfg2's shape
+        g = torch.Generator().manual_seed(0)
+        B = 64
+        x = (0.1 * torch.randn(B, 2, 441000, generator=g)).to(dev)
+        fmin, fmax = (torch.rand(B, generator=g) * 8000).to(dev), None
+        fmax = fmin + 2000.0
+        tmin = (torch.rand(B, generator=g) * 9.0).to(dev)
+        tmax = tmin + 0.25
+
+        def ours():
+            s = AudioSignal(x, 44100)
+            s.stft(window_length=2048, hop_length=512)
+            s.mask_frequencies(fmin, fmax)
+            s.mask_timesteps(tmin, tmax)
+            return s.istft(window_length=2048, hop_length=512)
+
+        w = torch.hann_window(2048, periodic=True, device=dev)
+
+        def stock_ops():  # the reference's own tensor ops (torch.stft / polar masks / torch.istft), run on the GPU
+            X = torch.stft(x.reshape(-1, 441000), 2048, 512, window=w, center=True, return_complex=True)
+            X = X.reshape(B, 2, 1025, -1)
+            mag, ph = torch.abs(X), torch.angle(X)
+            bins = torch.linspace(0, 22050, 1025, device=dev)[None, None, :, None].repeat(B, 1, 1, X.shape[-1])
+            m = (fmin[:, None, None, None] <= bins) & (bins < fmax[:, None, None, None])
+            X = mag.masked_fill(m, 0.0) * torch.exp(1j * ph.masked_fill(m, 0.0))
+            mag, ph = torch.abs(X), torch.angle(X)
+            bt = torch.linspace(0, 10.0, X.shape[-1], device=dev)[None, None, None, :].repeat(B, 1, 1025, 1)
+            m = (tmin[:, None, None, None] <= bt) & (bt < tmax[:, None, None, None])
+            X = mag.masked_fill(m, 0.0) * torch.exp(1j * ph.masked_fill(m, 0.0))
+            return torch.istft(X.reshape(-1, 1025, X.shape[-1]), 2048, 512, window=w, center=True, length=441000)
+
+        ms = timed(ours, warmup=2, steps=5)
+        ms_stock = timed(stock_ops, warmup=1, steps=3)
+        print(json.dumps({"config": "specaug 64x2ch 10s@44.1k stft->mask_frequencies->mask_timesteps->istft (2048/512)",
+                          "ms": ms, "ms_reference_tensor_ops_on_gpu": ms_stock, "clips_per_s": B / ms * 1e3}))
 
 
 if __name__ == "__main__":

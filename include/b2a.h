@@ -92,6 +92,14 @@ int b2a_istft_supported(int n_fft, int hop);
 int b2a_istft_f32(const float* spec, int64_t rows, int64_t n_frames, int n_fft, int hop, const float* window,
                   int pad_frames, int64_t start, int64_t out_len, float* out, void* stream);
 
+/* ---- SpecAugment band masks on a complex STFT, in place -------------------------------------------------
+ * DSPMixin.mask_frequencies / mask_timesteps (audiotools/core/dsp.py:217-306): cells whose axis value v satisfies
+ * lo[item] <= v < hi[item] (float32, as the reference compares) become fill = val * exp(1j * val); all other
+ * cells are left as they are.  spec [rows, F, N] complex64; axis 0 = frequency (axis_vals [F] = the reference's
+ * linspace(0, sr/2, F)), 1 = time (axis_vals [N] = linspace(0, duration, N)); lo, hi [rows / rows_per_item]. */
+int b2a_spec_band_mask_f32(float* spec, int64_t rows, int F, int N, const float* axis_vals, const float* lo,
+                           const float* hi, int rows_per_item, int axis, float fill_re, float fill_im, void* stream);
+
 /* ---- integrated loudness (ITU-R BS.1770 / LUFS) ----------------------------------------
  * Replaces Meter.integrated_loudness with the IIR semantics of apply_filter_cpu
  * (audiotools/core/loudness.py:102-126, 164-247) and the pad / clamp shell of

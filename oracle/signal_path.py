@@ -167,6 +167,51 @@ def log_magnitude(stft_data, ref_value=1.0, amin=1e-5, top_db=80.0):
 
 
 # ----------------------------------------------------------------------------
+# Spectral masks  (ref:audiotools/core/dsp.py:217-370) -- all on the complex STFT [B, C, F, N]
+# ----------------------------------------------------------------------------
+def _band_mask(stft_data, bins, lo, hi, val):
+    """mag/phase masked_fill + recombination, ref:audiotools/core/dsp.py:241-264 (frequency) / :290-306 (time)."""
+    mag, phase = torch.abs(stft_data), torch.angle(stft_data)
+    lo = ensure_tensor(lo, ndim=mag.ndim)
+    hi = ensure_tensor(hi, ndim=mag.ndim)
+    assert torch.all(lo < hi)
+    mask = (lo <= bins) & (bins < hi)
+    mag = mag.masked_fill(mask, val)
+    phase = phase.masked_fill(mask, val)
+    return mag * torch.exp(1j * phase)
+
+
+def mask_frequencies(stft_data, sample_rate, fmin_hz, fmax_hz, val=0.0):
+    """ref:audiotools/core/dsp.py:217-264."""
+    B, _, F, N = stft_data.shape
+    bins_hz = torch.linspace(0, sample_rate / 2, F)[None, None, :, None].repeat(B, 1, 1, N)
+    return _band_mask(stft_data, bins_hz, fmin_hz, fmax_hz, val)
+
+
+def mask_timesteps(stft_data, signal_duration, tmin_s, tmax_s, val=0.0):
+    """ref:audiotools/core/dsp.py:266-306."""
+    B, _, F, N = stft_data.shape
+    bins_t = torch.linspace(0, signal_duration, N)[None, None, None, :].repeat(B, 1, F, 1)
+    return _band_mask(stft_data, bins_t, tmin_s, tmax_s, val)
+
+
+def mask_low_magnitudes(stft_data, db_cutoff, val=0.0):
+    """ref:audiotools/core/dsp.py:308-333 (+ the magnitude setter, ref:audiotools/core/audio_signal.py:1452-1455)."""
+    mag = torch.abs(stft_data)
+    log_mag = log_magnitude(stft_data)
+    db_cutoff = ensure_tensor(db_cutoff, ndim=mag.ndim)
+    mag = mag.masked_fill(log_mag < db_cutoff, val)
+    return mag * torch.exp(1j * torch.angle(stft_data))
+
+
+def shift_phase(stft_data, shift):
+    """ref:audiotools/core/dsp.py:335-351 (+ the phase setter, ref:audiotools/core/audio_signal.py:1512-1516)."""
+    phase = torch.angle(stft_data)
+    shift = ensure_tensor(shift, ndim=phase.ndim)
+    return torch.abs(stft_data) * torch.exp(1j * (phase + shift))
+
+
+# ----------------------------------------------------------------------------
 # Loudness  (ref:audiotools/core/loudness.py)
 # ----------------------------------------------------------------------------
 class Meter:

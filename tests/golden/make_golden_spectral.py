@@ -1,0 +1,79 @@
+"""Golden vectors of the SpectralTransform family, produced by the REAL reference exactly like
+``make_golden.py`` (same shims; run here only):  ``python tests/golden/make_golden_spectral.py``
+-> ``reference_golden_spectral.npz`` (ref:audiotools/core/dsp.py:217-370, ref:audiotools/data/transforms.py:1200-1453)."""
+import os
+import sys
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+REPO = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, REPO)
+
+from tests.golden.make_golden import _flatten, import_reference  # noqa: E402
+from tests.golden.cases import make_input  # noqa: E402
+
+# per-item parameters shared with the tests
+FMIN = torch.tensor([500.0, 0.0, 3000.0, 7000.0])
+FMAX = torch.tensor([1500.0, 250.0, 3100.0, 8000.0])
+TMIN = torch.tensor([0.10, 0.0, 0.50, 0.90])
+TMAX = torch.tensor([0.20, 0.05, 0.51, 1.00])
+DBCUT = torch.tensor([-10.0, 0.0, 5.0, -40.0])
+SHIFT = torch.tensor([0.5, -1.0, float(np.pi), 0.0])
+SEEDS = [20, 21, 22, 23]
+
+
+def main():
+    at = import_reference()
+    AudioSignal = at.AudioSignal
+    from audiotools.data import transforms as tfm
+
+    out = {}
+    x = make_input("cfg1")  # [4, 1, 16000] @ 16 kHz, default STFT 512/128 hann
+
+    def fresh():
+        s = AudioSignal(x.clone(), 16000)
+        s.stft()
+        return s
+
+    s = fresh().mask_frequencies(FMIN, FMAX)
+    out["maskfreq_stft"] = s.stft_data.numpy()
+    out["maskfreq_audio"] = s.istft().audio_data.numpy()
+    s = fresh().mask_frequencies(FMIN, FMAX, val=0.25)
+    out["maskfreq_val_stft"] = s.stft_data[:1].numpy()
+    s = fresh().mask_timesteps(TMIN, TMAX)
+    out["masktime_stft"] = s.stft_data.numpy()
+    out["masktime_audio"] = s.istft().audio_data.numpy()
+    s = fresh().mask_low_magnitudes(DBCUT)
+    out["masklow_stft"] = s.stft_data[:2].numpy()
+    out["masklow_audio"] = s.istft().audio_data.numpy()
+    s = fresh().shift_phase(SHIFT)
+    out["shift_stft"] = s.stft_data[2:].numpy()
+    out["shift_audio"] = s.istft().audio_data.numpy()
+    g = torch.Generator().manual_seed(77)
+    corr = 0.3 * torch.randn(4, 1, 257, 126, generator=g)
+    out["corrupt_in"] = corr.numpy()
+    out["corrupt_audio"] = fresh().shift_phase(corr).istft().audio_data.numpy()
+
+    # transforms (seeded instantiate; TimeNoise / FrequencyNoise draw device noise: properties only, not pinned here)
+    transform = tfm.Compose([tfm.FrequencyMask(), tfm.TimeMask(prob=0.7), tfm.ShiftPhase(), tfm.MaskLowMagnitudes(prob=0.6),
+                             tfm.CorruptPhase(prob=0.5), tfm.InvertPhase(prob=0.5)])
+    sig = AudioSignal(x.clone(), 16000)
+    kwargs = transform.batch_instantiate(SEEDS, sig)
+    for k, v in _flatten(kwargs).items():
+        out["kw/" + "/".join(k)] = v.numpy()
+    out["compose_audio"] = transform(sig.clone(), **kwargs).audio_data.numpy()
+    sm = tfm.Smoothing()
+    kw = sm.batch_instantiate(SEEDS, sig)
+    win = kw["Smoothing"]["window"]
+    out["smooth_window"] = win.audio_data.numpy()
+    out["smooth_audio"] = sm(sig.clone(), **kw).audio_data.numpy()
+
+    path = os.path.join(HERE, "reference_golden_spectral.npz")
+    np.savez_compressed(path, **out)
+    print(f"wrote {path}: {len(out)} arrays, {os.path.getsize(path)/1e6:.1f} MB on disk")
+
+
+if __name__ == "__main__":
+    main()

@@ -481,3 +481,80 @@ def test_cfg4_augment_pipeline(at):
     assert ((peak_out / peak_in) < 1.5).all() and ((peak_out / peak_in) > 0.2).all()
     one = transform(sig[2:3].clone(), **at.util.prepare_batch(transform.batch_instantiate([2], sig[2:3].cpu()), DEV))
     assert torch.allclose(one.audio_data, out.audio_data[2:3], atol=1e-5)
+
+
+# ------------------------------------------------------------------------------------------
+# spectral masks and the SpectralTransform family (stft -> mask -> istft, all on the device)
+# ------------------------------------------------------------------------------------------
+def test_spectral_masks_match_reference(at, golden_spec):
+    from tests.golden import make_golden_spectral as mg
+
+    g = golden_spec
+
+    def fresh():
+        s = sig_of(at, "cfg1")
+        s.stft()
+        return s
+
+    def cplx(a, key, sl=slice(None)):
+        ref = torch.from_numpy(g[key])
+        assert rel_err(torch.view_as_real(a.cpu()[sl]), torch.view_as_real(ref)) < TOL, key
+
+    s = fresh().mask_frequencies(mg.FMIN, mg.FMAX)
+    cplx(s.stft_data, "maskfreq_stft")
+    assert torch.equal(s.stft_data.cpu() == 0, torch.from_numpy(g["maskfreq_stft"]) == 0)  # the reference's cells exactly
+    assert rel_err(s.istft().audio_data.cpu(), torch.from_numpy(g["maskfreq_audio"])) < TOL
+    cplx(fresh().mask_frequencies(mg.FMIN, mg.FMAX, val=0.25).stft_data, "maskfreq_val_stft", slice(0, 1))
+    s = fresh().mask_timesteps(mg.TMIN, mg.TMAX)
+    cplx(s.stft_data, "masktime_stft")
+    assert torch.equal(s.stft_data.cpu() == 0, torch.from_numpy(g["masktime_stft"]) == 0)
+    assert rel_err(s.istft().audio_data.cpu(), torch.from_numpy(g["masktime_audio"])) < TOL
+    s = fresh().mask_low_magnitudes(mg.DBCUT)
+    cplx(s.stft_data, "masklow_stft", slice(0, 2))
+    assert rel_err(s.istft().audio_data.cpu(), torch.from_numpy(g["masklow_audio"])) < TOL
+    s = fresh().shift_phase(mg.SHIFT)
+    cplx(s.stft_data, "shift_stft", slice(2, 4))
+    assert rel_err(s.istft().audio_data.cpu(), torch.from_numpy(g["shift_audio"])) < TOL
+    s = fresh().shift_phase(torch.from_numpy(g["corrupt_in"]))
+    assert rel_err(s.istft().audio_data.cpu(), torch.from_numpy(g["corrupt_audio"])) < TOL
+    with pytest.raises(AssertionError):  # ref dsp.py:249: fmin < fmax
+        fresh().mask_frequencies(2000.0, 1000.0)
+    with pytest.raises(RuntimeError):  # kernel-backed: CUDA only
+        at.AudioSignal(torch.zeros(1, 1, 4000), 16000).mask_frequencies(0.0, 100.0)
+
+
+def test_spectral_transforms_match_reference(at, golden_spec):
+    """Compose[FrequencyMask, TimeMask, ShiftPhase, MaskLowMagnitudes, CorruptPhase, InvertPhase] and Smoothing with the
+    seeds of tests/golden/make_golden_spectral.py: drawn parameters and outputs equal the real reference's."""
+    from audiotools_b200.data import transforms as tfm
+    from tests.golden import make_golden_spectral as mg
+
+    g = golden_spec
+    t = tfm.Compose([tfm.FrequencyMask(), tfm.TimeMask(prob=0.7), tfm.ShiftPhase(), tfm.MaskLowMagnitudes(prob=0.6),
+                     tfm.CorruptPhase(prob=0.5), tfm.InvertPhase(prob=0.5)])
+    sig = sig_of(at, "cfg1").to("cpu")
+    kwargs = t.batch_instantiate(mg.SEEDS, sig)
+    for k, v in at.util.flatten(kwargs).items():
+        assert np.allclose(v.numpy(), g["kw/" + "/".join(k)]), k
+    out = t(sig.clone().to(DEV), **at.util.prepare_batch(kwargs, DEV))
+    assert rel_err(out.audio_data.cpu(), torch.from_numpy(g["compose_audio"])) < TOL
+    sm = tfm.Smoothing()
+    kw = sm.batch_instantiate(mg.SEEDS, sig)
+    assert np.allclose(kw["Smoothing"]["window"].audio_data.numpy(), g["smooth_window"])
+    out = sm(sig.clone().to(DEV), **at.util.prepare_batch(kw, DEV))
+    assert rel_err(out.audio_data.cpu(), torch.from_numpy(g["smooth_audio"])) < TOL
+    # the two noise variants draw device noise (unpinned in the reference too): the band is refilled, the rest is kept
+    for cls, kwname in ((tfm.TimeNoise, "tmin_s"), (tfm.FrequencyNoise, "fmin_hz")):
+        tn = cls()
+        kw = at.util.prepare_batch(tn.batch_instantiate(mg.SEEDS, sig), DEV)
+        s = sig.clone().to(DEV)
+        x0 = s.audio_data.clone()
+        s.stft()
+        X0 = s.stft_data.clone()
+        sub = {k: v for k, v in kw[tn.name].items() if k != "mask"}
+        s2 = tn._transform(s, **sub)
+        changed = (s2.stft_data - X0).abs() > 1e-3 * X0.abs().max()
+        frac = changed.float().mean().item()
+        assert 0.0 < frac < 0.2  # only the masked band / frames were replaced
+        y = tn(sig.clone().to(DEV), **kw)
+        assert y.audio_data.shape == x0.shape and torch.isfinite(y.audio_data).all()

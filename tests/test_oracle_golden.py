@@ -205,3 +205,27 @@ def test_unfold_block_count():
     assert u.shape == (1, 3, 4) and u[0, 2].tolist() == [6.0, 7.0, 8.0, 9.0]
     u = tp.unfold(torch.arange(11.0)[None], 4, 3)
     assert u.shape == (1, 4, 4) and u[0, 3].tolist() == [9.0, 10.0, 0.0, 0.0]
+
+
+def test_spectral_masks_match_reference(golden_spec):
+    """the oracle restatement of DSPMixin's spectral masks against the real reference's outputs."""
+    from tests.golden import make_golden_spectral as mg
+
+    g = golden_spec
+    x = cases.make_input("cfg1")
+    X = sp.stft(x, 16000)
+    close = lambda a, b, atol: np.testing.assert_allclose(a.numpy(), b, atol=atol, rtol=0)
+    Y = sp.mask_frequencies(X, 16000, mg.FMIN, mg.FMAX)
+    close(Y, g["maskfreq_stft"], 1e-5)
+    close(sp.istft(Y, 16000, 16000), g["maskfreq_audio"], 1e-5)
+    close(sp.mask_frequencies(X, 16000, mg.FMIN, mg.FMAX, val=0.25)[:1], g["maskfreq_val_stft"], 1e-5)
+    Y = sp.mask_timesteps(X, 1.0, mg.TMIN, mg.TMAX)
+    close(Y, g["masktime_stft"], 1e-5)
+    close(sp.istft(Y, 16000, 16000), g["masktime_audio"], 1e-5)
+    Y = sp.mask_low_magnitudes(X, mg.DBCUT)
+    close(Y[:2], g["masklow_stft"], 1e-5)
+    close(sp.istft(Y, 16000, 16000), g["masklow_audio"], 1e-5)
+    Y = sp.shift_phase(X, mg.SHIFT)
+    close(Y[2:], g["shift_stft"], 2e-5)
+    close(sp.istft(Y, 16000, 16000), g["shift_audio"], 2e-5)
+    close(sp.istft(sp.shift_phase(X, torch.from_numpy(g["corrupt_in"])), 16000, 16000), g["corrupt_audio"], 2e-5)

@@ -305,3 +305,31 @@ def test_peer_put_collect_two_ranks(eng):
     assert lib.b2a_peer_put_f32(None, 5, peers, world, 0, n_max, 1, None) != 0  # null source is refused
     for b in bufs:
         lib.check(lib.b2a_peer_buffer_destroy(ctypes.c_void_p(b)))
+
+
+# ------------------------------------------------------------------------------------------
+# SpecAugment band masks (csrc/specmask.cu) against the oracle restatement and the reference goldens
+# ------------------------------------------------------------------------------------------
+def test_spec_band_mask_matches_reference(eng, golden_spec):
+    from tests.golden import make_golden_spectral as mg
+
+    x = cases.make_input("cfg1")
+    X = sp.stft(x, 16000).contiguous()  # [4, 1, 257, 126]
+    bins_hz = torch.linspace(0, 8000, 257)
+    Y = eng.spec_band_mask(X.clone(), bins_hz, mg.FMIN, mg.FMAX, 0)
+    ref = torch.from_numpy(golden_spec["maskfreq_stft"])
+    assert torch.equal(Y == 0, ref == 0)                      # exactly the reference's cells
+    assert torch.equal(Y[Y != 0], X[Y != 0])                  # untouched cells keep their bits
+    assert rel_err(torch.view_as_real(Y), torch.view_as_real(ref)) < 1e-5
+    Y = eng.spec_band_mask(X.clone(), torch.linspace(0, 1.0, 126), mg.TMIN, mg.TMAX, 1)
+    ref = torch.from_numpy(golden_spec["masktime_stft"])
+    assert torch.equal(Y == 0, ref == 0) and rel_err(torch.view_as_real(Y), torch.view_as_real(ref)) < 1e-5
+    Y = eng.spec_band_mask(X[:1].clone(), bins_hz, mg.FMIN[:1], mg.FMAX[:1], 0, val=0.25)
+    assert rel_err(torch.view_as_real(Y), torch.view_as_real(torch.from_numpy(golden_spec["maskfreq_val_stft"]))) < 1e-5
+    # stereo: an item's band applies to both of its channels; scalar band broadcasts over the batch
+    Xs = X.reshape(2, 2, 257, 126).clone()
+    Ys = eng.spec_band_mask(Xs.clone(), bins_hz, torch.tensor([1000.0, 2000.0]), torch.tensor([1500.0, 4000.0]), 0)
+    want = sp.mask_frequencies(Xs, 16000, torch.tensor([1000.0, 2000.0]), torch.tensor([1500.0, 4000.0]))
+    assert torch.equal(Ys == 0, want == 0)
+    Y1 = eng.spec_band_mask(X.clone(), bins_hz, torch.tensor(100.0), torch.tensor(200.0), 0)
+    assert torch.equal(Y1 == 0, sp.mask_frequencies(X, 16000, 100.0, 200.0) == 0)

@@ -54,6 +54,8 @@ SIGNATURES = {
                                       c_void_p]),
     "b2a_spec_band_mask_f32": (c_int, [c_void_p, c_int64, c_int, c_int, c_void_p, c_void_p, c_void_p, c_int, c_int,
                                        c_float, c_float, c_void_p]),
+    "b2a_spec_rotate_f32": (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_int, c_void_p]),
+    "b2a_spec_mask_low_f32": (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_float, c_float, c_float, c_void_p, c_void_p]),
     "b2a_istft_supported": (c_int, [c_int, c_int]),
     "b2a_istft_f32": (c_int, [c_void_p, c_int64, c_int64, c_int, c_int, c_void_p, c_int, c_int64, c_int64, c_void_p,
                               c_void_p]),

@@ -67,21 +67,30 @@ class DSPMixin:
         return self._band_mask(tmin_s, tmax_s, bins_t, 1, val)
 
     def mask_low_magnitudes(self, db_cutoff, val: float = 0.0):
-        """Fill magnitudes whose ``log_magnitude()`` is below ``db_cutoff`` (per item) with ``val`` (ref :308-333)."""
-        mag = self.magnitude
-        log_mag = self.log_magnitude()
-        db_cutoff = util.ensure_tensor(db_cutoff, ndim=mag.ndim).to(mag.device)
-        self.magnitude = mag.masked_fill(log_mag < db_cutoff, val)
+        """Fill magnitudes whose ``log_magnitude()`` is below ``db_cutoff`` (per item) with ``val``, keeping the phase
+        (ref :308-333): one reduction pass for ``log_magnitude``'s global top_db floor, one masking pass."""
+        if self.stft_data is None:
+            self.stft()
+        cut = util.ensure_tensor(db_cutoff, ndim=1).float().reshape(-1)
+        self.stft_data = _engine().spec_mask_low(self.stft_data, cut, val)
         return self
 
     def shift_phase(self, shift):
-        """``phase += shift`` (scalar, per item, or a full [B, C, F, N] tensor) (ref :335-351)."""
-        shift = util.ensure_tensor(shift, ndim=self.phase.ndim).to(self.device)
-        self.phase = self.phase + shift
+        """``phase += shift`` (ref :335-351), i.e. ``stft_data *= exp(1j * shift)`` in one pass.  ``shift``: a scalar,
+        one value per item, or a tensor shaped like ``stft_data`` (per cell); other broadcast shapes are expanded."""
+        if self.stft_data is None:
+            self.stft()
+        shift = util.ensure_tensor(shift, ndim=self.stft_data.ndim).float()
+        B = self.stft_data.shape[0]
+        if shift.numel() not in (1, B) or (shift.numel() == B and shift.shape[0] != B):
+            shift = shift.to(self.device).expand(self.stft_data.shape).contiguous()
+        self.stft_data = _engine().spec_rotate(self.stft_data, shift)
         return self
 
     def corrupt_phase(self, scale):
         """``phase += scale * N(0, 1)`` drawn on the signal's device (ref :353-369)."""
-        scale = util.ensure_tensor(scale, ndim=self.phase.ndim).to(self.device)
-        self.phase = self.phase + scale * torch.randn_like(self.phase)
-        return self
+        if self.stft_data is None:
+            self.stft()
+        scale = util.ensure_tensor(scale, ndim=self.stft_data.ndim).float().to(self.device)
+        noise = torch.randn(self.stft_data.shape, dtype=torch.float32, device=self.device)
+        return self.shift_phase(scale * noise)

@@ -1,51 +1,145 @@
-// specmask.cu -- SpecAugment-style band masks on a complex STFT, in place, on sm_100a.
+// specmask.cu -- in-place operations on a complex STFT [rows, F, N] for the SpectralTransform family, sm_100a.
 //
-// Replaces the mask construction of DSPMixin.mask_frequencies / mask_timesteps
-// (ref:audiotools/core/dsp.py:217-306): the reference takes |X| and angle(X), repeats the bin axis to the full
-// [B, 1, F, N] shape, builds the boolean mask, masked_fills magnitude and phase and recombines
-// mag * exp(1j * phase) -- about a dozen passes over the spectrogram.  Cells outside the band are unchanged by
-// that round trip (up to its polar/rectangular rounding), so this kernel touches ONLY the masked cells: it
-// evaluates  lo[item] <= axis_val < hi[item]  in float32 exactly as the reference does (axis_val = the
-// reference's own torch.linspace values, passed in) and stores the constant fill = val * exp(1j * val).
-// No loads of the spectrogram at all; bytes written = masked fraction x 8 B.
+// The reference expresses every one of them through |X|, angle(X), masked_fill and mag * exp(1j * phase)
+// (ref:audiotools/core/dsp.py:217-370): about a dozen elementwise passes over the spectrogram each.  Here:
+//   band_mask_kernel   mask_frequencies / mask_timesteps (:217-306).  Cells outside the band are unchanged by the
+//                      reference's polar round trip (up to its rounding), so the kernel touches ONLY masked cells:
+//                      it evaluates lo[item] <= axis_val < hi[item] in float32 exactly as the reference does
+//                      (axis_val = the reference's own torch.linspace values, passed in) and stores the constant
+//                      fill = val * exp(1j * val).  No loads of the spectrogram; one CTA per (row, bin) line.
+//   rotate_kernel      shift_phase (:335-351): X *= exp(1j * shift), shift per item or per cell -- one read, one write.
+//   maxpow_kernel +    mask_low_magnitudes (:308-333): log_magnitude()'s top_db floor needs the global maximum of
+//   mask_low_kernel    |X|^2 (one read-only pass, float atomicMax on the bit pattern), then cells whose
+//                      10 log10(max(|X|^2, 1e-10)) (floored at max - 80 dB) is below the item's cut-off get
+//                      magnitude `val` and keep their phase; only those cells are written.
 #include "b2a_common.h"
 
 namespace b2a {
 namespace specmask {
 
 __global__ void __launch_bounds__(256)
-band_mask_kernel(float2* __restrict__ spec, long long total, int F, int N, const float* __restrict__ axis_vals,
+band_mask_kernel(float2* __restrict__ spec, int F, int N, const float* __restrict__ axis_vals,
                  const float* __restrict__ lo, const float* __restrict__ hi, int rows_per_item, int axis, float2 fill) {
-  const long long FN = (long long)F * N;
-  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
-       idx += (long long)gridDim.x * blockDim.x) {
-    const long long row = idx / FN;
-    const int rem = (int)(idx - row * FN);
-    const int f = rem / N, n = rem - f * N;
-    const float v = __ldg(axis_vals + (axis == 0 ? f : n));
-    const int item = (int)(row / rows_per_item);
-    if (__ldg(lo + item) <= v && v < __ldg(hi + item)) spec[idx] = fill;
+  const int line = blockIdx.x;  // row * F + f
+  const int row = line / F, f = line - row * F;
+  const int item = row / rows_per_item;
+  const float l = __ldg(lo + item), h = __ldg(hi + item);
+  float2* p = spec + (size_t)line * N;
+  if (axis == 0) {
+    const float v = __ldg(axis_vals + f);
+    if (!(l <= v && v < h)) return;  // CTA-uniform: the whole line is outside the band
+    for (int n = threadIdx.x; n < N; n += blockDim.x) p[n] = fill;
+  } else {
+    for (int n = threadIdx.x; n < N; n += blockDim.x) {
+      const float v = __ldg(axis_vals + n);
+      if (l <= v && v < h) p[n] = fill;
+    }
   }
+}
+
+// mode 0: shift[item]; mode 1: shift[cell]
+__global__ void __launch_bounds__(256)
+rotate_kernel(float2* __restrict__ spec, long long total, long long cells_per_item, const float* __restrict__ shift,
+              int mode) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const float s = mode ? __ldg(shift + i) : __ldg(shift + i / cells_per_item);
+    float sn, cs;
+    sincosf(s, &sn, &cs);
+    const float2 z = spec[i];
+    spec[i] = make_float2(z.x * cs - z.y * sn, z.x * sn + z.y * cs);
+  }
+}
+
+__device__ __forceinline__ float power_of(float2 z) {
+  const float mag = hypotf(z.x, z.y);  // torch.abs(complex64)
+  return mag * mag;                    // .pow(2)
+}
+
+__global__ void __launch_bounds__(256)
+maxpow_kernel(const float2* __restrict__ spec, long long total, unsigned* __restrict__ max_bits) {
+  float m = 0.f;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x)
+    m = fmaxf(m, power_of(spec[i]));
+  m = warp_max(m);
+  __shared__ float sm[8];
+  if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = m;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < 8; ++w) m = fmaxf(m, sm[w]);
+    atomicMax(max_bits, __float_as_uint(m));  // non-negative floats order like their bit patterns
+  }
+}
+
+__global__ void __launch_bounds__(256)
+mask_low_kernel(float2* __restrict__ spec, long long total, long long cells_per_item, const float* __restrict__ cutoff,
+                const unsigned* __restrict__ max_bits, float amin2, float top_db, float val) {
+  const float floor_db = 10.0f * log10f(fmaxf(__uint_as_float(*max_bits), amin2)) - top_db;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const float2 z = spec[i];
+    float db = 10.0f * log10f(fmaxf(power_of(z), amin2));
+    db = fmaxf(db, floor_db);
+    if (db < __ldg(cutoff + i / cells_per_item)) {
+      // magnitude := val, phase kept: val * exp(1j * atan2(im, re))
+      const float ph = atan2f(z.y, z.x);
+      float sn, cs;
+      sincosf(ph, &sn, &cs);
+      spec[i] = make_float2(val * cs, val * sn);
+    }
+  }
+}
+
+static unsigned grid_for(long long total) {
+  long long blocks = (total + 255) / 256;
+  const long long cap = (long long)B2A_NUM_SMS * 16;
+  return (unsigned)(blocks < cap ? blocks : cap);
 }
 
 }  // namespace specmask
 }  // namespace b2a
 
+using namespace b2a::specmask;
+
 extern "C" int b2a_spec_band_mask_f32(float* spec, int64_t rows, int F, int N, const float* axis_vals, const float* lo,
                                       const float* hi, int rows_per_item, int axis, float fill_re, float fill_im,
                                       void* stream) {
-  using namespace b2a::specmask;
   B2A_REQUIRE(spec && axis_vals && lo && hi, B2A_E_INVALID, "spec_band_mask: null pointer");
   B2A_REQUIRE(rows >= 1 && F >= 1 && N >= 1 && rows_per_item >= 1 && (axis == 0 || axis == 1), B2A_E_INVALID,
               "spec_band_mask: bad argument");
   B2A_REQUIRE(((uintptr_t)spec & 7) == 0, B2A_E_INVALID, "spec_band_mask: spectra must be 8-byte aligned");
-  const long long total = (long long)rows * F * N;
-  B2A_REQUIRE((long long)F * N < ((long long)1 << 31), B2A_E_UNSUPPORTED, "spec_band_mask: F*N too large");
-  long long blocks = (total + 255) / 256;
-  const long long cap = (long long)B2A_NUM_SMS * 32;
-  if (blocks > cap) blocks = cap;
-  B2A_LAUNCH(band_mask_kernel, dim3((unsigned)blocks), dim3(256), 0, stream, reinterpret_cast<float2*>(spec), total, F, N,
-             axis_vals, lo, hi, rows_per_item, axis, make_float2(fill_re, fill_im));
+  B2A_REQUIRE(rows * F < (int64_t)2147483647, B2A_E_UNSUPPORTED, "spec_band_mask: too many lines");
+  B2A_LAUNCH(band_mask_kernel, dim3((unsigned)(rows * F)), dim3(N >= 256 ? 256 : 64), 0, stream,
+             reinterpret_cast<float2*>(spec), F, N, axis_vals, lo, hi, rows_per_item, axis, make_float2(fill_re, fill_im));
+  B2A_CUDA_OK(cudaGetLastError());
+  return B2A_OK;
+}
+
+extern "C" int b2a_spec_rotate_f32(float* spec, int64_t items, int64_t cells_per_item, const float* shift,
+                                   int per_cell, void* stream) {
+  B2A_REQUIRE(spec && shift, B2A_E_INVALID, "spec_rotate: null pointer");
+  B2A_REQUIRE(items >= 1 && cells_per_item >= 1, B2A_E_INVALID, "spec_rotate: bad argument");
+  B2A_REQUIRE(((uintptr_t)spec & 7) == 0, B2A_E_INVALID, "spec_rotate: spectra must be 8-byte aligned");
+  const long long total = (long long)items * cells_per_item;
+  B2A_LAUNCH(rotate_kernel, dim3(grid_for(total)), dim3(256), 0, stream, reinterpret_cast<float2*>(spec), total,
+             (long long)cells_per_item, shift, per_cell ? 1 : 0);
+  B2A_CUDA_OK(cudaGetLastError());
+  return B2A_OK;
+}
+
+extern "C" int b2a_spec_mask_low_f32(float* spec, int64_t items, int64_t cells_per_item, const float* db_cutoff,
+                                     float amin_sq, float top_db, float val, void* ws /* >= 4 bytes */, void* stream) {
+  B2A_REQUIRE(spec && db_cutoff && ws, B2A_E_INVALID, "spec_mask_low: null pointer");
+  B2A_REQUIRE(items >= 1 && cells_per_item >= 1, B2A_E_INVALID, "spec_mask_low: bad argument");
+  B2A_REQUIRE(((uintptr_t)spec & 7) == 0 && ((uintptr_t)ws & 3) == 0, B2A_E_INVALID, "spec_mask_low: alignment");
+  const long long total = (long long)items * cells_per_item;
+#ifdef B2A_SIM
+  memset(ws, 0, 4);
+#else
+  B2A_CUDA_OK(cudaMemsetAsync(ws, 0, 4, (cudaStream_t)stream));
+#endif
+  B2A_LAUNCH(maxpow_kernel, dim3(grid_for(total)), dim3(256), 0, stream, reinterpret_cast<const float2*>(spec), total,
+             (unsigned*)ws);
+  B2A_LAUNCH(mask_low_kernel, dim3(grid_for(total)), dim3(256), 0, stream, reinterpret_cast<float2*>(spec), total,
+             (long long)cells_per_item, db_cutoff, (const unsigned*)ws, amin_sq, top_db, val);
   B2A_CUDA_OK(cudaGetLastError());
   return B2A_OK;
 }

@@ -114,11 +114,7 @@ class Engine:
                        axis: int, val: float = 0.0) -> torch.Tensor:
         """In place: ``spec[b, c, f, n] = val * exp(1j * val)`` where ``lo[b] <= axis_vals[f or n] < hi[b]``
         (ref:audiotools/core/dsp.py:217-306).  spec [B, C, F, N] complex64, contiguous; returns it."""
-        if not torch.is_complex(spec) or spec.dtype != torch.complex64 or not spec.is_contiguous():
-            raise TypeError("spec_band_mask: spec must be a contiguous complex64 tensor")
-        if self.require_cuda and not spec.is_cuda:
-            raise RuntimeError(f"stft_data is on {spec.device}: audiotools_b200 runs on CUDA (sm_100a) only and has "
-                               "no CPU fallback")
+        spec = self._spec_ok(spec, "spec_band_mask")
         B, C, F, N = spec.shape
         axis_vals = self._prep(axis_vals.to(spec.device), "axis_vals")
         lo = self._prep(lo.to(spec.device).reshape(-1), "lo")
@@ -133,6 +129,49 @@ class Engine:
                                              self._stream(spec))
         self.lib.check(rc)
         self.launches += 1
+        return spec
+
+    def _spec_ok(self, spec: torch.Tensor, what: str) -> torch.Tensor:
+        if not torch.is_complex(spec):
+            raise TypeError(f"{what}: spec must be complex")
+        if self.require_cuda and not spec.is_cuda:
+            raise RuntimeError(f"stft_data is on {spec.device}: audiotools_b200 runs on CUDA (sm_100a) only and has "
+                               "no CPU fallback")
+        if spec.dtype != torch.complex64 or not spec.is_contiguous():
+            spec = spec.to(torch.complex64).contiguous()
+        return spec
+
+    def spec_rotate(self, spec: torch.Tensor, shift: torch.Tensor) -> torch.Tensor:
+        """``spec * exp(1j * shift)`` in place on a contiguous complex64 [B, ...] tensor (a copy otherwise);
+        ``shift`` has B entries (one per item) or one per cell (ref:audiotools/core/dsp.py:335-351)."""
+        spec = self._spec_ok(spec, "spec_rotate")
+        B = spec.shape[0]
+        cells = spec.numel() // B
+        shift = self._prep(shift.to(spec.device), "shift").reshape(-1)
+        if shift.numel() == 1:
+            shift = shift.expand(B).contiguous()
+        assert shift.numel() in (B, spec.numel()), (shift.shape, spec.shape)
+        rc = self.lib.b2a_spec_rotate_f32(_dptr(torch.view_as_real(spec)), B, cells, _dptr(shift),
+                                          int(shift.numel() == spec.numel() and cells > 1), self._stream(spec))
+        self.lib.check(rc)
+        self.launches += 1
+        return spec
+
+    def spec_mask_low(self, spec: torch.Tensor, db_cutoff: torch.Tensor, val: float = 0.0, amin: float = 1e-5,
+                      top_db: float = 80.0) -> torch.Tensor:
+        """``mask_low_magnitudes`` (ref:audiotools/core/dsp.py:308-333) in place: two passes (global max, mask)."""
+        spec = self._spec_ok(spec, "spec_mask_low")
+        B = spec.shape[0]
+        cells = spec.numel() // B
+        db_cutoff = self._prep(db_cutoff.to(spec.device), "db_cutoff").reshape(-1)
+        if db_cutoff.numel() == 1:
+            db_cutoff = db_cutoff.expand(B).contiguous()
+        assert db_cutoff.numel() == B
+        ws = torch.empty(1, dtype=torch.int32, device=spec.device)
+        rc = self.lib.b2a_spec_mask_low_f32(_dptr(torch.view_as_real(spec)), B, cells, _dptr(db_cutoff), float(amin ** 2),
+                                            float(top_db), float(val), _dptr(ws), self._stream(spec))
+        self.lib.check(rc)
+        self.launches += 2
         return spec
 
     # ------------------------------------------------------------------ loudness

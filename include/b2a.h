@@ -99,6 +99,15 @@ int b2a_istft_f32(const float* spec, int64_t rows, int64_t n_frames, int n_fft, 
  * linspace(0, sr/2, F)), 1 = time (axis_vals [N] = linspace(0, duration, N)); lo, hi [rows / rows_per_item]. */
 int b2a_spec_band_mask_f32(float* spec, int64_t rows, int F, int N, const float* axis_vals, const float* lo,
                            const float* hi, int rows_per_item, int axis, float fill_re, float fill_im, void* stream);
+/* DSPMixin.shift_phase (dsp.py:335-351): spec *= exp(1j * shift) in place; shift [items] (per_cell 0) or
+ * [items * cells_per_item] (per_cell 1: CorruptPhase's per-cell noise).  spec viewed as [items, cells_per_item]. */
+int b2a_spec_rotate_f32(float* spec, int64_t items, int64_t cells_per_item, const float* shift, int per_cell,
+                        void* stream);
+/* DSPMixin.mask_low_magnitudes (dsp.py:308-333) with log_magnitude()'s arithmetic (audio_signal.py:1457-1487):
+ * db = max(10 log10(max(|X|^2, amin_sq)), max over the WHOLE tensor - top_db); cells with db < db_cutoff[item] get
+ * magnitude `val` and keep their phase.  ws: 4 bytes of device scratch (4-byte aligned). */
+int b2a_spec_mask_low_f32(float* spec, int64_t items, int64_t cells_per_item, const float* db_cutoff, float amin_sq,
+                          float top_db, float val, void* ws, void* stream);
 
 /* ---- integrated loudness (ITU-R BS.1770 / LUFS) ----------------------------------------
  * Replaces Meter.integrated_loudness with the IIR semantics of apply_filter_cpu

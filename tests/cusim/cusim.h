@@ -244,6 +244,7 @@ static inline void sincospi(double x, double* s, double* c) { *s = sin(M_PI * x)
 static inline float __fdividef(float a, float b) { return a / b; }
 static inline void __threadfence_system() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
 static inline unsigned __float_as_uint(float v) { unsigned u; memcpy(&u, &v, 4); return u; }
+static inline float __uint_as_float(unsigned u) { float v; memcpy(&v, &u, 4); return v; }
 static inline float cospif(float x) { return (float)cos(M_PI * (double)x); }
 static inline float sinpif(float x) { return (float)sin(M_PI * (double)x); }
 static inline float __int_as_float(int i) { float f; memcpy(&f, &i, 4); return f; }

@@ -333,3 +333,22 @@ def test_spec_band_mask_matches_reference(eng, golden_spec):
     assert torch.equal(Ys == 0, want == 0)
     Y1 = eng.spec_band_mask(X.clone(), bins_hz, torch.tensor(100.0), torch.tensor(200.0), 0)
     assert torch.equal(Y1 == 0, sp.mask_frequencies(X, 16000, 100.0, 200.0) == 0)
+
+
+def test_spec_rotate_and_mask_low_match_reference(eng, golden_spec):
+    from tests.golden import make_golden_spectral as mg
+
+    x = cases.make_input("cfg1")
+    X = sp.stft(x, 16000).contiguous()
+    Y = eng.spec_rotate(X.clone(), mg.SHIFT)  # per item
+    assert rel_err(torch.view_as_real(Y[2:]), torch.view_as_real(torch.from_numpy(golden_spec["shift_stft"]))) < 1e-5
+    corr = torch.from_numpy(golden_spec["corrupt_in"])
+    Y = eng.spec_rotate(X.clone(), corr)  # per cell
+    assert rel_err(torch.view_as_real(Y), torch.view_as_real(sp.shift_phase(X, corr))) < 1e-5
+    Y = eng.spec_mask_low(X.clone(), mg.DBCUT)
+    ref = torch.from_numpy(golden_spec["masklow_stft"])
+    assert torch.equal(Y[:2] == 0, ref == 0)  # the same cells as the real reference, incl. the global top_db floor
+    assert rel_err(torch.view_as_real(Y[:2]), torch.view_as_real(ref)) < 1e-5
+    want = sp.mask_low_magnitudes(X, mg.DBCUT, val=0.5)  # non-zero fill keeps the phase
+    got = eng.spec_mask_low(X.clone(), mg.DBCUT, val=0.5)
+    assert rel_err(torch.view_as_real(got), torch.view_as_real(want)) < 1e-5

@@ -83,6 +83,8 @@ struct Params {
   int span;  // (FR-1)*hop + n_fft
   // shared memory offsets (bytes)
   int off_win, off_tw, off_ut, off_buf, off_mag, off_mel, smem_bytes;
+  int xb_stride;   // floats per frame slot of the exchange / |X| buffer (WPlan::XB, or 2N+4 when the STFT is staged)
+  int stage_stft;  // STFT-only launch: complex frames are parked in their slots and written with frame-contiguous runs
 };
 
 // index of sample `w` (in un-padded x coordinates, may be outside [0,T)) after torch's two
@@ -473,7 +475,7 @@ __global__ void __launch_bounds__(256, 2) spectral_warp_kernel(Params p) {
                               &s_bar);
   }
   for (int i = tid; i < n_fft; i += 256) win[i] = __ldg(p.window + i);
-  for (int i = tid; i < G * PL::XB; i += 256) xbs[i] = 0.f;  // the slack behind each |X| slot must stay finite (0 x w)
+  for (int i = tid; i < G * p.xb_stride; i += 256) xbs[i] = 0.f;  // the slack behind each |X| slot must stay finite (0 x w)
   warp_fft_tables<LOG2N>(tw, ut);
   // banded mel weights in shared memory.  The projection runs once per tile, AFTER the tile's FFTs, with the
   // work transposed: lane (f, j) of warp w handles frame f (8 at a time) and filter m = w + 8*(4*i + j) in
@@ -513,7 +515,7 @@ __global__ void __launch_bounds__(256, 2) spectral_warp_kernel(Params p) {
     }
   }
 
-  float* xb = xbs + (warp * FPW + fw) * PL::XB;
+  float* xb = xbs + (warp * FPW + fw) * p.xb_stride;
   const int src_lane = (lane & ~(LPF - 1)) | ((LPF - l) & (LPF - 1));  // holder of Z[N - k]
 
 #pragma unroll 1
@@ -583,18 +585,28 @@ __global__ void __launch_bounds__(256, 2) spectral_warp_kernel(Params p) {
         const float2 tt = cmul(ut[m * LPF + l], xo);
         const float2 xk = cadd(xe, tt);
         const float2 d = csub(xe, tt);
-        if (so && live) {
-          so[(size_t)k * p.n_frames] = make_float2(g * xk.x, g * xk.y);
-          so[(size_t)(N - k) * p.n_frames] = make_float2(g * d.x, -g * d.y);
+        if (p.stage_stft) {  // park the complex bins in the frame's own slot (the exchange plane is dead now)
+          float2* xc = reinterpret_cast<float2*>(xb);
+          xc[k] = make_float2(g * xk.x, g * xk.y);
+          xc[N - k] = make_float2(g * d.x, -g * d.y);
+        } else {
+          if (so && live) {
+            so[(size_t)k * p.n_frames] = make_float2(g * xk.x, g * xk.y);
+            so[(size_t)(N - k) * p.n_frames] = make_float2(g * d.x, -g * d.y);
+          }
+          xb[k] = fast_sqrt(fmaf(xk.x, xk.x, xk.y * xk.y));
+          xb[N - k] = fast_sqrt(fmaf(d.x, d.x, d.y * d.y));
         }
-        xb[k] = fast_sqrt(fmaf(xk.x, xk.x, xk.y * xk.y));
-        xb[N - k] = fast_sqrt(fmaf(d.x, d.x, d.y * d.y));
       }
       if (l == 0) {  // k = N/2 pairs with itself: X = conj(Z[N/2])
         const float2 zh = z[16];
-        if (so && live) so[(size_t)(N / 2) * p.n_frames] = make_float2(g * zh.x, -g * zh.y);
-        xb[N / 2] = fast_sqrt(fmaf(zh.x, zh.x, zh.y * zh.y));
-        xb[N + 1] = 0.f; xb[N + 2] = 0.f; xb[N + 3] = 0.f;  // read (x 0 weight) by 4-wide band loads
+        if (p.stage_stft) {
+          reinterpret_cast<float2*>(xb)[N / 2] = make_float2(g * zh.x, -g * zh.y);
+        } else {
+          if (so && live) so[(size_t)(N / 2) * p.n_frames] = make_float2(g * zh.x, -g * zh.y);
+          xb[N / 2] = fast_sqrt(fmaf(zh.x, zh.x, zh.y * zh.y));
+          xb[N + 1] = 0.f; xb[N + 2] = 0.f; xb[N + 3] = 0.f;  // read (x 0 weight) by 4-wide band loads
+        }
       }
       __syncwarp();
 
@@ -609,7 +621,7 @@ __global__ void __launch_bounds__(256, 2) spectral_warp_kernel(Params p) {
         const float4* mpk4 = reinterpret_cast<const float4*>(mpk);
         for (int fc = 0; fc < FR; fc += 8) {
           const int f = fc + fl;
-          const float* xf = xbs + f * PL::XB;
+          const float* xf = xbs + f * p.xb_stride;
           for (int mm = warp + 8 * jq; mm < p.n_mels; mm += 32) {
             const int4 sg = mseg[mm];  // (row offset, lo4, own n4, padded n4: the same for the 4 filters of a step)
             const float4* w4 = mpk4 + sg.x;
@@ -650,7 +662,7 @@ __global__ void __launch_bounds__(256, 2) spectral_warp_kernel(Params p) {
       } else {  // band table does not fit in shared memory: weights from global
         for (int fc = 0; fc < FR; fc += 8) {
           const int f = fc + fl;
-          const float* xf = xbs + f * PL::XB;
+          const float* xf = xbs + f * p.xb_stride;
           for (int mm = warp + 8 * jq; mm < p.n_mels; mm += 32) {
             const int lo = __ldg(p.mel_lo + mm), hi = __ldg(p.mel_hi + mm);
             const float* wrow = p.mel_fb + (size_t)mm * F;
@@ -666,6 +678,17 @@ __global__ void __launch_bounds__(256, 2) spectral_warp_kernel(Params p) {
     }
 
     __syncthreads();  // all frames of the tile are done: melt complete, sp free for the next tile
+    if (p.stage_stft) {
+      // transposed write of the tile's complex frames: 32 lanes = 32/FR bins x FR consecutive frames, i.e. runs of
+      // FR * 8 bytes instead of one 8-byte store per sector (the layout is [rows, F, n_frames], frame fastest)
+      const int nf = min(FR, p.n_frames - n0);
+      float2* o = p.stft_out + (size_t)row * F * p.n_frames + n0;
+      for (int i = tid; i < F * FR; i += 256) {
+        const int k = i / FR, f = i - k * FR;
+        if (f < nf) o[(size_t)k * p.n_frames + f] = reinterpret_cast<const float2*>(xbs + f * p.xb_stride)[k];
+      }
+      // (the next iteration's barrier, after its span wait, orders these reads before the slots are reused)
+    }
     if (p.mel_out) {
       const int nf = min(FR, p.n_frames - n0);
       float* o = p.mel_out + (size_t)row * p.n_mels * p.n_frames + n0;
@@ -697,7 +720,15 @@ static int launch_warp(Params& p, void* stream) {
   p.off_win = o; o = align16(o + p.n_fft * 4);
   p.off_tw = o; o = align16(o + PL::NTW * PL::LPF * 8 + 16);
   p.off_ut = o; o = align16(o + 16 * PL::LPF * 8);
-  p.off_buf = o; o = align16(o + PL::G * PL::XB * 4);
+  // STFT-only launches park the complex frame (N+1 float2) in the frame's slot and write it out transposed; that
+  // needs 2N+4 floats per slot instead of XB -- only if two CTAs per SM still fit
+  p.xb_stride = PL::XB;
+  p.stage_stft = 0;
+  if (p.stft_out && !p.mel_out) {
+    const int wide = ((2 * PL::N + 4 + 3) / 4) * 4;
+    if (wide >= PL::XB && o + PL::G * wide * 4 + 64 <= 112 * 1024) { p.xb_stride = wide; p.stage_stft = 1; }
+  }
+  p.off_buf = o; o = align16(o + PL::G * p.xb_stride * 4);
   p.off_mag = o;
   p.off_mel = o; o = align16(o + (p.mel_out ? p.n_mels * (PL::FR + 1) * 4 : 0));
   const int base = o;

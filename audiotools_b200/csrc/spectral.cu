@@ -440,7 +440,9 @@ static int launch(Params& p, void* stream) {
 //            produces the real-FFT bins k and N-k for its 16 k < N/2
 //   mel      |X| -> the (dead) exchange plane -> banded FP32 gather, post-op, tile in smem
 // =============================================================================================
-template <int LOG2N>
+// STAGED: STFT-only launch that parks the complex frames in shared memory and writes them transposed (a separate
+// instantiation, so the mel path's code is not touched by it).
+template <int LOG2N, bool STAGED>
 __global__ void __launch_bounds__(256, 2) spectral_warp_kernel(Params p) {
   using PL = WPlan<LOG2N>;
   constexpr int N = PL::N, LPF = PL::LPF, FPW = PL::FPW, G = PL::G, FR = PL::FR;
@@ -585,7 +587,7 @@ __global__ void __launch_bounds__(256, 2) spectral_warp_kernel(Params p) {
         const float2 tt = cmul(ut[m * LPF + l], xo);
         const float2 xk = cadd(xe, tt);
         const float2 d = csub(xe, tt);
-        if (p.stage_stft) {  // park the complex bins in the frame's own slot (the exchange plane is dead now)
+        if constexpr (STAGED) {  // park the complex bins in the frame's own slot (the exchange plane is dead now)
           float2* xc = reinterpret_cast<float2*>(xb);
           xc[k] = make_float2(g * xk.x, g * xk.y);
           xc[N - k] = make_float2(g * d.x, -g * d.y);
@@ -600,7 +602,7 @@ __global__ void __launch_bounds__(256, 2) spectral_warp_kernel(Params p) {
       }
       if (l == 0) {  // k = N/2 pairs with itself: X = conj(Z[N/2])
         const float2 zh = z[16];
-        if (p.stage_stft) {
+        if constexpr (STAGED) {
           reinterpret_cast<float2*>(xb)[N / 2] = make_float2(g * zh.x, -g * zh.y);
         } else {
           if (so && live) so[(size_t)(N / 2) * p.n_frames] = make_float2(g * zh.x, -g * zh.y);
@@ -678,7 +680,7 @@ __global__ void __launch_bounds__(256, 2) spectral_warp_kernel(Params p) {
     }
 
     __syncthreads();  // all frames of the tile are done: melt complete, sp free for the next tile
-    if (p.stage_stft) {
+    if constexpr (STAGED) {
       // transposed write of the tile's complex frames: 32 lanes = 32/FR bins x FR consecutive frames, i.e. runs of
       // FR * 8 bytes instead of one 8-byte store per sector (the layout is [rows, F, n_frames], frame fastest)
       const int nf = min(FR, p.n_frames - n0);
@@ -744,14 +746,15 @@ static int launch_warp(Params& p, void* stream) {
               p.n_mels, o);
   const int64_t total = (int64_t)p.rows * p.n_tiles;
   B2A_REQUIRE(total < (int64_t)2147483647, B2A_E_UNSUPPORTED, "spectral: too many tiles");
-  B2A_CUDA_OK(cudaFuncSetAttribute(spectral_warp_kernel<LOG2N>, cudaFuncAttributeMaxDynamicSharedMemorySize, o));
+  auto kern = p.stage_stft ? spectral_warp_kernel<LOG2N, true> : spectral_warp_kernel<LOG2N, false>;
+  B2A_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, o));
   // persistent: as many CTAs as are resident at once (2 per SM by registers / shared memory), each loops over tiles
   int per_sm = 1;
-  B2A_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, spectral_warp_kernel<LOG2N>, 256, (size_t)o));
+  B2A_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 256, (size_t)o));
   if (per_sm < 1) per_sm = 1;
   const int64_t cap = (int64_t)num_sms() * per_sm;
   const unsigned grid = (unsigned)(total < cap ? total : cap);
-  B2A_LAUNCH(spectral_warp_kernel<LOG2N>, dim3(grid), dim3(256), (size_t)o, stream, p);
+  B2A_LAUNCH(kern, dim3(grid), dim3(256), (size_t)o, stream, p);
   B2A_CUDA_OK(cudaGetLastError());
   return B2A_OK;
 }

@@ -18,6 +18,8 @@
 //   3. Y[row][f][b]    = sum_p H[f][p] * X[f][b-p]       a complex FIR along the block index, per bin
 //   4. out[b*1024 ..]  = irFFT_2048(Y[.][b])[1024:]      warp-per-block inverse FFT + epilogue
 // Rows are processed in chunks so that X and Y stay L2-friendly (<= 256 MB of workspace).
+#include <stdlib.h>
+
 #include "b2a_common.h"
 #include "fft_warp.cuh"
 #include "spectral_internal.h"
@@ -98,7 +100,8 @@ freq_fir_kernel(const float2* __restrict__ X, const float2* __restrict__ H, floa
 }
 
 struct InvParams {
-  const float2* Y;       // [rows, NF, NB]
+  const float2* Y;       // [rows, NF, NB]  (or the signal spectra X when H1 is set)
+  const float2* H1;      // single-partition filters [n_filt, NF]: the product X * H is formed on load (no Y pass)
   const float* x;        // [rows_total, T] (for subtract_from_input)
   const float* post;     // [n_filt] nullable
   float* out;            // [rows_total, T]
@@ -127,6 +130,7 @@ __global__ void __launch_bounds__(256, 2) ifft_blocks_kernel(InvParams p) {
     const int row = t / groups, b = (t - row * groups) * 8 + warp;
     if (b >= p.NB) continue;  // warp-uniform
     const float2* yr = p.Y + (size_t)row * NF * p.NB + b;
+    const float2* hr = p.H1 ? p.H1 + (size_t)((p.row0 + row) / p.rows_per_filt) * NF : nullptr;
     // Z[e] = Xe[e] + i Xo[e] from the real-FFT bins X[e], X[N-e]; the inverse transform is
     // conj(FFT(conj(Z)))/N, so feed conj(Z).   e = l + 32 m
     float2 z[32];
@@ -135,8 +139,12 @@ __global__ void __launch_bounds__(256, 2) ifft_blocks_kernel(InvParams p) {
       const int e = l + 32 * m;
       // for e > N/2 use the pair (k = N-e): Z[e] = conj(Xe[k]) + i conj(Xo[k])
       const int k = (m < 16) ? e : N - e;
-      const float2 xk = __ldg(yr + (size_t)k * p.NB);
-      const float2 xn = __ldg(yr + (size_t)(N - k) * p.NB);
+      float2 xk = __ldg(yr + (size_t)k * p.NB);
+      float2 xn = __ldg(yr + (size_t)(N - k) * p.NB);
+      if (hr) {  // one partition: Y = H * X, multiplied here instead of in a pass of its own
+        xk = cmul(xk, __ldg(hr + k));
+        xn = cmul(xn, __ldg(hr + (N - k)));
+      }
       // Xe = (X[k] + conj X[N-k])/2 ; T = (X[k] - conj X[N-k])/2 ; Xo = conj(W_k) T, W_k = exp(-i pi k/N)
       const float2 xe = make_float2(0.5f * (xk.x + xn.x), 0.5f * (xk.y - xn.y));
       const float2 tt = make_float2(0.5f * (xk.x - xn.x), 0.5f * (xk.y + xn.y));
@@ -210,13 +218,26 @@ struct Layout {
   int P, NB, NBX, chunk;
 };
 static inline size_t al(size_t v) { return (v + 255) & ~(size_t)255; }
+// Spectra of one chunk of rows (X and, with several partitions, Y).  Sized to stay L2-resident between the forward
+// FFT, the spectral FIR and the inverse FFT (126 MB L2 on B200); B2A_FFTCONV_WS_MB overrides it for experiments.
+static size_t chunk_budget_mb() {
+  static size_t mb = 0;
+  if (mb == 0) {
+    const char* e = getenv("B2A_FFTCONV_WS_MB");
+    const long v = e ? atol(e) : 0;
+    mb = (v >= 8 && v <= 65536) ? (size_t)v : 256;
+  }
+  return mb;
+}
+
 static Layout layout(int64_t rows, int64_t T, int64_t n_filt, int64_t L) {
   Layout w;
   w.P = (int)((L + LP - 1) / LP);
   w.NB = (int)((T + LP - 1) / LP);
   w.NBX = w.NB + w.P - 1;
-  const size_t per_row = (size_t)NF * (w.NBX + w.NB) * 8;
-  int64_t chunk = (int64_t)(((size_t)256 << 20) / per_row);
+  // one partition: the product is formed inside the inverse kernel, Y is never written (see run())
+  const size_t per_row = (size_t)NF * (w.NBX + (w.P > 1 ? w.NB : 0)) * 8;
+  int64_t chunk = (int64_t)((chunk_budget_mb() << 20) / per_row);
   if (chunk < 1) chunk = 1;
   if (chunk > rows) chunk = rows;
   if (chunk > 65535) chunk = 65535;
@@ -226,7 +247,7 @@ static Layout layout(int64_t rows, int64_t T, int64_t n_filt, int64_t L) {
   w.half = o; o = al(o + NFFT * 4);
   w.H = o; o = al(o + (size_t)n_filt * NF * w.P * 8);
   w.X = o; o = al(o + (size_t)w.chunk * NF * w.NBX * 8);
-  w.Y = o; o = al(o + (size_t)w.chunk * NF * w.NB * 8);
+  w.Y = o; o = al(o + (w.P > 1 ? (size_t)w.chunk * NF * w.NB * 8 : 0));
   w.rorg = o; o = al(o + (size_t)w.chunk * 4);
   w.peak_idx = o; o = al(o + (size_t)n_filt * 4);
   w.peak_scale = o; o = al(o + (size_t)n_filt * 4);
@@ -270,7 +291,7 @@ static int run(const float* x, int64_t rows, int64_t T, const float* g, int64_t 
     rc = frames_fft(x + (size_t)r0 * T, nr, (int)T, NFFT, LP, ones, -w.P * LP, rorg, pad_mode, w.NBX, X, stream);
     if (rc != B2A_OK) return rc;
     // 3. complex FIR along the block index
-    {
+    if (w.P > 1) {
       int nt = ((w.NB + FIR_R - 1) / FIR_R + 31) / 32 * 32;
       if (nt > 128) nt = 128;
       const int P4 = (w.P + 3) & ~3;
@@ -282,7 +303,9 @@ static int run(const float* x, int64_t rows, int64_t T, const float* g, int64_t 
                  (const float2*)X, (const float2*)H, Y, w.NB, w.NBX, w.P, rows_per_filt, (int)r0, SP);
     }
     // 4. inverse FFT + overlap-save + epilogue
-    ip.Y = Y; ip.x = x; ip.post = post_scale; ip.out = out;
+    // one partition (NBX == NB): the inverse kernel multiplies X by H while loading, Y is never written
+    ip.Y = (w.P > 1) ? Y : X; ip.H1 = (w.P > 1) ? nullptr : H;
+    ip.x = x; ip.post = post_scale; ip.out = out;
     ip.rows = nr; ip.row0 = (int)r0; ip.T = (int)T; ip.NB = w.NB; ip.rows_per_filt = rows_per_filt;
     ip.subtract = subtract;
     const int64_t total = (int64_t)nr * ((w.NB + 7) / 8);

@@ -90,24 +90,46 @@ class PeerLoudnessExchange:
         self.n_max = int(n_max)
         self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
         self._ct = ctypes
+        # Set-up is all-or-nothing ACROSS ranks: every rank takes part in both handle/status exchanges whatever
+        # happened locally, so a failure anywhere (no cudaIpc in this container, a rank on another node, ...) makes
+        # every rank raise together and the caller can fall back consistently instead of dead-locking.
+        self.local, self._opened, err = None, [], None
+        self.peers = (ctypes.c_void_p * self.world)()
+        handle = None
         with torch.cuda.device(self.device):
-            ptr = ctypes.c_void_p()
-            handle = (ctypes.c_ubyte * 64)()
-            self.lib.check(self.lib.b2a_peer_buffer_create(self.world, self.n_max, ctypes.byref(ptr), handle))
-            self.local = ptr.value
+            try:
+                ptr = ctypes.c_void_p()
+                hbuf = (ctypes.c_ubyte * 64)()
+                self.lib.check(self.lib.b2a_peer_buffer_create(self.world, self.n_max, ctypes.byref(ptr), hbuf))
+                self.local, handle = ptr.value, bytes(hbuf)
+            except Exception as e:  # noqa: BLE001
+                err = f"rank {self.rank}: {e}"
             handles = [None] * self.world
-            dist.all_gather_object(handles, bytes(handle), group=group)
-            self.peers = (ctypes.c_void_p * self.world)()
-            self._opened = []
-            for r, h in enumerate(handles):
-                if r == self.rank:
-                    self.peers[r] = self.local
-                    continue
-                p = ctypes.c_void_p()
-                buf = (ctypes.c_ubyte * 64).from_buffer_copy(h)
-                self.lib.check(self.lib.b2a_peer_buffer_open(buf, ctypes.byref(p)))
-                self.peers[r] = p.value
-                self._opened.append(p.value)
+            dist.all_gather_object(handles, handle, group=group)
+            if err is None and all(h is not None for h in handles):
+                try:
+                    for r, h in enumerate(handles):
+                        if r == self.rank:
+                            self.peers[r] = self.local
+                            continue
+                        p = ctypes.c_void_p()
+                        buf = (ctypes.c_ubyte * 64).from_buffer_copy(h)
+                        self.lib.check(self.lib.b2a_peer_buffer_open(buf, ctypes.byref(p)))
+                        self.peers[r] = p.value
+                        self._opened.append(p.value)
+                except Exception as e:  # noqa: BLE001
+                    err = f"rank {self.rank}: {e}"
+            elif err is None:
+                err = "a peer could not create its buffer"
+            errs = [None] * self.world
+            dist.all_gather_object(errs, err, group=group)
+            if any(e is not None for e in errs):
+                for p in self._opened:
+                    self.lib.b2a_peer_buffer_close(ctypes.c_void_p(p))
+                if self.local is not None:
+                    self.lib.b2a_peer_buffer_destroy(ctypes.c_void_p(self.local))
+                self.local = None
+                raise RuntimeError("peer exchange unavailable: " + "; ".join(e for e in errs if e))
         dist.barrier(group=group)  # every rank has mapped every buffer before the first put
         self.seq = 0
         self._collected = 0

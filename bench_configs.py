@@ -3,7 +3,7 @@
 bench.py, which measures configs[1]).  One JSON line per config: device-resident throughput (CUDA events,
 >= 3 warm-ups, inputs larger than L2 or rotated), algorithmic bytes, and the CPU oracle on a bounded sample.
 
-    python bench_configs.py [--only cfg1,cfg3,cfg4,istft,specaug] [--no-cpu]
+    python bench_configs.py [--only cfg1,cfg3,cfg4,cfg5,istft,specaug] [--no-cpu]
 """
 import argparse
 import json
@@ -41,7 +41,7 @@ def cpu_time(fn, reps=2):
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--only", default="cfg1,cfg3,cfg4,istft,specaug")
+    ap.add_argument("--only", default="cfg1,cfg3,cfg4,cfg5,istft,specaug")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
     import __graft_entry__ as graft
@@ -122,6 +122,35 @@ def main():
         line = {"config": f"cfg4 per-GPU share batch={B} mono 10s@44.1k Compose[EQ+RoomIR+PitchShift+-2]", "ms": ms,
                 "clips_per_s": B / ms * 1e3, "ms_parts": per}
         print(json.dumps(line))
+
+    if "cfg5" in only:  # batch=2048 2ch 10s@44.1k full augment + LUFS + log-mel on 8 GPUs: one GPU's share (256 items)
+        B, T, sr = 256, 441000, 44100
+        g = torch.Generator().manual_seed(1)
+        x = 0.1 * torch.randn(B, 2, T, generator=g)
+        t = torch.arange(sr) / sr
+        irs = []
+        for i in range(8):
+            h = torch.randn(1, 1, sr, generator=g) * torch.exp(-t / 0.3) * 0.1
+            h[..., 40 + i] = 1.0
+            irs.append(AudioSignal(h, sr))
+        transform = tfm.Compose([tfm.Equalizer(), tfm.RoomImpulseResponse(sources=irs),
+                                 tfm.PitchShift(("choice", [-2, 2]))])
+        sig = AudioSignal(x, sr)
+        kwargs = transform.batch_instantiate(list(range(B)), sig)
+        sig = sig.to(dev)
+        from audiotools_b200 import util
+
+        kwargs = util.prepare_batch(kwargs, dev)
+
+        def full():
+            s = transform(sig.clone(), **kwargs)
+            s.normalize(-24.0)
+            return s.mel_spectrogram(n_mels=128, window_length=2048, hop_length=512, log=True)
+
+        ms = timed(full, warmup=2, steps=3)
+        print(json.dumps({"config": f"cfg5 per-GPU share batch={B} 2ch 10s@44.1k Compose[EQ+RoomIR+PitchShift+-2] + "
+                                    "LUFS normalize + log-mel", "ms": ms, "clips_per_s": B / ms * 1e3}))
+        del x, sig
 
     if "istft" in only:  # inverse STFT at cfg2's shape (64 x 2ch x 10 s @ 44.1 kHz, 2048/512)
         g = torch.Generator().manual_seed(0)

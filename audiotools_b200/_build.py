@@ -32,7 +32,7 @@ def _digest(files):
 
 def build(force: bool = False, verbose: bool = False) -> str:
     srcs = sorted(glob.glob(os.path.join(CSRC, "*.cu")))
-    deps = srcs + sorted(glob.glob(os.path.join(CSRC, "*.h"))) + [
+    deps = srcs + sorted(glob.glob(os.path.join(CSRC, "*.h"))) + sorted(glob.glob(os.path.join(CSRC, "*.cuh"))) + [
         os.path.join(os.path.dirname(HERE), "include", "b2a.h")]
     stamp = os.path.join(CSRC, ".libb2a.stamp")
     dig = _digest(deps)

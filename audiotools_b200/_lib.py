@@ -9,7 +9,7 @@ import os
 from ctypes import POINTER, c_char_p, c_double, c_float, c_int, c_int32, c_int64, c_size_t, c_void_p
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "csrc", "libb2a.so")
+LIB_PATH = os.environ.get("B2A_LIB_PATH") or os.path.join(HERE, "csrc", "libb2a.so")  # env: A/B builds only
 
 B2A_OK = 0
 PAD_MODES = {"reflect": 0, "constant": 1, "replicate": 2}

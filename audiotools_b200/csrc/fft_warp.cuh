@@ -57,11 +57,34 @@ __device__ __forceinline__ float2 mul_wr(float2 o) {
 
 template <int R, int S>
 struct DFT {
+  // out[K] = e + W o, out[K + R/2] = e - W o with W = exp(-2 pi i K / R) = c - i sn.  For a non-trivial W the sum is
+  // formed with fused multiply-adds and the difference as 2e - sum: 6 instructions instead of 8 (complex multiply,
+  // add, subtract).  The difference inherits one rounding of the sum (absolute error <= ulp(|e| + |o|), the size
+  // of the usual butterfly error).
   template <int K>
   static __device__ __forceinline__ void comb(const float2 (&e)[R / 2], const float2 (&o)[R / 2], float2* out) {
-    float2 t = mul_wr<R, K>(o[K]);
-    out[K] = cadd(e[K], t);
-    out[K + R / 2] = csub(e[K], t);
+    constexpr int j = 32 * K / R;  // angle = pi*j/16
+    if constexpr (j == 0 || j == 8) {
+      const float2 t = mul_wr<R, K>(o[K]);
+      out[K] = cadd(e[K], t);
+      out[K + R / 2] = csub(e[K], t);
+    } else if constexpr (j == 4 || j == 12) {
+      constexpr float h = 0.70710678118654752f;
+      // j == 4: W o = h((o.x + o.y) + i(o.y - o.x));  j == 12: W o = h((o.y - o.x) - i(o.x + o.y))
+      const float p = o[K].x + o[K].y, q = o[K].y - o[K].x;
+      float2 s;
+      if constexpr (j == 4) s = make_float2(fmaf(h, p, e[K].x), fmaf(h, q, e[K].y));
+      else s = make_float2(fmaf(h, q, e[K].x), fmaf(-h, p, e[K].y));
+      out[K] = s;
+      out[K + R / 2] = make_float2(fmaf(2.0f, e[K].x, -s.x), fmaf(2.0f, e[K].y, -s.y));
+    } else {
+      constexpr float c = cos_pi16(j);
+      constexpr float sn = cos_pi16(j <= 8 ? 8 - j : j - 8);  // sin(pi j/16)
+      // W o = (o.x c + o.y sn) + i (o.y c - o.x sn)
+      const float2 s = make_float2(fmaf(o[K].x, c, fmaf(o[K].y, sn, e[K].x)), fmaf(o[K].y, c, fmaf(-o[K].x, sn, e[K].y)));
+      out[K] = s;
+      out[K + R / 2] = make_float2(fmaf(2.0f, e[K].x, -s.x), fmaf(2.0f, e[K].y, -s.y));
+    }
     if constexpr (K + 1 < R / 2) comb<K + 1>(e, o, out);
   }
   // in: R values at in[0], in[S], ...; out: R values, natural frequency order

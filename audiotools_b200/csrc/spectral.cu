@@ -476,7 +476,9 @@ __global__ void __launch_bounds__(256, 2) spectral_warp_kernel(Params p) {
                               (tile * FR + p.drop_edge) * hop + p.origin + (p.row_origin ? __ldg(p.row_origin + row) : 0),
                               &s_bar);
   }
-  for (int i = tid; i < n_fft; i += 256) win[i] = __ldg(p.window + i);
+  // the window is kept HALVED: the real-FFT untangle needs (Zk +- conj Zn)/2, and a power-of-two scale commutes with
+  // every rounding of the (linear) transform, so the 0.5 factors vanish from the untangle with bit-identical results
+  for (int i = tid; i < n_fft; i += 256) win[i] = 0.5f * __ldg(p.window + i);
   for (int i = tid; i < G * p.xb_stride; i += 256) xbs[i] = 0.f;  // the slack behind each |X| slot must stay finite (0 x w)
   warp_fft_tables<LOG2N>(tw, ut);
   // banded mel weights in shared memory.  The projection runs once per tile, AFTER the tile's FFTs, with the
@@ -582,8 +584,8 @@ __global__ void __launch_bounds__(256, 2) spectral_warp_kernel(Params p) {
         zn.y = __shfl_sync(0xffffffffu, z[31 - m].y, src_lane);
         if (l == 0) zn = z[(32 - m) & 31];
         const int k = l + LPF * m;
-        const float2 xe = make_float2(0.5f * (zk.x + zn.x), 0.5f * (zk.y - zn.y));
-        const float2 xo = make_float2(0.5f * (zk.y + zn.y), 0.5f * (zn.x - zk.x));
+        const float2 xe = make_float2(zk.x + zn.x, zk.y - zn.y);  // (Zk + conj Zn)/2   (window halved above)
+        const float2 xo = make_float2(zk.y + zn.y, zn.x - zk.x);  // (Zk - conj Zn)/(2i)
         const float2 tt = cmul(ut[m * LPF + l], xo);
         const float2 xk = cadd(xe, tt);
         const float2 d = csub(xe, tt);
@@ -601,7 +603,7 @@ __global__ void __launch_bounds__(256, 2) spectral_warp_kernel(Params p) {
         }
       }
       if (l == 0) {  // k = N/2 pairs with itself: X = conj(Z[N/2])
-        const float2 zh = z[16];
+        const float2 zh = make_float2(2.0f * z[16].x, 2.0f * z[16].y);  // undo the halved window: X = conj(Z[N/2])
         if constexpr (STAGED) {
           reinterpret_cast<float2*>(xb)[N / 2] = make_float2(g * zh.x, -g * zh.y);
         } else {

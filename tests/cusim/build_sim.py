@@ -24,7 +24,7 @@ def _digest(files):
 def build(verbose=False):
     os.makedirs(OUT_DIR, exist_ok=True)
     srcs = sorted(glob.glob(os.path.join(CSRC, "*.cu")))
-    deps = srcs + glob.glob(os.path.join(CSRC, "*.h")) + [os.path.join(HERE, "cusim.h"),
+    deps = srcs + glob.glob(os.path.join(CSRC, "*.h")) + glob.glob(os.path.join(CSRC, "*.cuh")) + [os.path.join(HERE, "cusim.h"),
                                                           os.path.join(REPO, "include", "b2a.h")]
     stamp = os.path.join(OUT_DIR, "stamp")
     dig = _digest(deps)

@@ -440,11 +440,13 @@ static int launch(Params& p, void* stream) {
 //            produces the real-FFT bins k and N-k for its 16 k < N/2
 //   mel      |X| -> the (dead) exchange plane -> banded FP32 gather, post-op, tile in smem
 // =============================================================================================
-// STAGED: STFT-only launch that parks the complex frames in shared memory and writes them transposed (a separate
-// instantiation, so the mel path's code is not touched by it).
-template <int LOG2N, bool STAGED>
+// MODE 0: no STFT output (mel / log-mel only: the bench path; the per-bin store code is compiled out);
+// MODE 1: STFT-only launch that parks the complex frames in shared memory and writes them transposed;
+// MODE 2: generic (STFT straight from registers, with or without mel).
+template <int LOG2N, int MODE>
 __global__ void __launch_bounds__(256, 2) spectral_warp_kernel(Params p) {
   using PL = WPlan<LOG2N>;
+  constexpr bool STAGED = (MODE == 1), DIRECT = (MODE == 2);
   constexpr int N = PL::N, LPF = PL::LPF, FPW = PL::FPW, G = PL::G, FR = PL::FR;
   static_assert(FR == G && FR % 8 == 0, "one round per tile: the |X| slot of a frame is its index in the tile");
   B2A_DYN_SMEM(smem);
@@ -575,7 +577,7 @@ __global__ void __launch_bounds__(256, 2) spectral_warp_kernel(Params p) {
       warp_fft<LOG2N>(z, xb, tw, l);  // z[m] = Z[l + LPF m]
 
       // ---- untangle -> real-FFT bins k = l + LPF m (m < 16) and N - k ; magnitudes into xb
-      float2* so = p.stft_out ? p.stft_out + (size_t)row * F * p.n_frames + n : nullptr;
+      float2* so = (DIRECT && p.stft_out) ? p.stft_out + (size_t)row * F * p.n_frames + n : nullptr;
 #pragma unroll
       for (int m = 0; m < 16; ++m) {
         const float2 zk = z[m];
@@ -594,9 +596,11 @@ __global__ void __launch_bounds__(256, 2) spectral_warp_kernel(Params p) {
           xc[k] = make_float2(g * xk.x, g * xk.y);
           xc[N - k] = make_float2(g * d.x, -g * d.y);
         } else {
-          if (so && live) {
-            so[(size_t)k * p.n_frames] = make_float2(g * xk.x, g * xk.y);
-            so[(size_t)(N - k) * p.n_frames] = make_float2(g * d.x, -g * d.y);
+          if constexpr (DIRECT) {
+            if (so && live) {
+              so[(size_t)k * p.n_frames] = make_float2(g * xk.x, g * xk.y);
+              so[(size_t)(N - k) * p.n_frames] = make_float2(g * d.x, -g * d.y);
+            }
           }
           xb[k] = fast_sqrt(fmaf(xk.x, xk.x, xk.y * xk.y));
           xb[N - k] = fast_sqrt(fmaf(d.x, d.x, d.y * d.y));
@@ -607,7 +611,9 @@ __global__ void __launch_bounds__(256, 2) spectral_warp_kernel(Params p) {
         if constexpr (STAGED) {
           reinterpret_cast<float2*>(xb)[N / 2] = make_float2(g * zh.x, -g * zh.y);
         } else {
-          if (so && live) so[(size_t)(N / 2) * p.n_frames] = make_float2(g * zh.x, -g * zh.y);
+          if constexpr (DIRECT) {
+            if (so && live) so[(size_t)(N / 2) * p.n_frames] = make_float2(g * zh.x, -g * zh.y);
+          }
           xb[N / 2] = fast_sqrt(fmaf(zh.x, zh.x, zh.y * zh.y));
           xb[N + 1] = 0.f; xb[N + 2] = 0.f; xb[N + 3] = 0.f;  // read (x 0 weight) by 4-wide band loads
         }
@@ -748,7 +754,8 @@ static int launch_warp(Params& p, void* stream) {
               p.n_mels, o);
   const int64_t total = (int64_t)p.rows * p.n_tiles;
   B2A_REQUIRE(total < (int64_t)2147483647, B2A_E_UNSUPPORTED, "spectral: too many tiles");
-  auto kern = p.stage_stft ? spectral_warp_kernel<LOG2N, true> : spectral_warp_kernel<LOG2N, false>;
+  auto kern = p.stage_stft ? spectral_warp_kernel<LOG2N, 1>
+                           : (p.stft_out ? spectral_warp_kernel<LOG2N, 2> : spectral_warp_kernel<LOG2N, 0>);
   B2A_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, o));
   // persistent: as many CTAs as are resident at once (2 per SM by registers / shared memory), each loops over tiles
   int per_sm = 1;

@@ -59,12 +59,16 @@ __global__ void __launch_bounds__(256, 2) istft_kernel(const Params p) {
   const int NP = p.n_frames + 2 * p.pad_frames;  // frames incl. the zero frames of match_stride
   const int g_own = warp * FPW + lane / LPF, l = lane % LPF;
   float* slot = reg + g_own * FS;
-  const float inv_n = 1.0f / (float)N;
+  const float inv_n = 0.5f / (float)N;  // 1/N of the transform and the 1/2 of the even/odd split
+  const int src_lane = (lane & ~(LPF - 1)) | ((LPF - l) & (LPF - 1));  // holder of the partner element N - k
   const int tail = NFFT - hop;                   // samples a group hands to the next one
   const int items = p.rows * p.segs_per_row;
   // gather roles: RL residue lanes x QL hop lanes (hop >= 256: every thread owns residues and walks all hops)
   const int RL = hop < 256 ? hop : 256, QL = 256 / RL;
   const int r_first = tid < RL * QL ? tid % RL : hop, q_first = tid / RL;
+  const bool vec4 = (hop & 3) == 0 && (FS & 3) == 0;
+  const int RL4 = (hop >> 2) < 256 ? max(hop >> 2, 1) : 256, QL4 = 256 / RL4;
+  const int r4_first = tid < RL4 * QL4 ? tid % RL4 : hop, q4_first = tid / RL4;
 #pragma unroll 1
   for (int item = blockIdx.x; item < items; item += gridDim.x) {
     const int row = item / p.segs_per_row, seg = item - row * p.segs_per_row;
@@ -89,25 +93,40 @@ __global__ void __launch_bounds__(256, 2) istft_kernel(const Params p) {
         reinterpret_cast<float2*>(reg + g * FS)[k] = v;
       }
       __syncthreads();
-      // ---- 2. Z[e] = Xe[e] + i Xo[e] from the bins X[e], X[N-e]; inverse = conj(FFT(conj Z))/N.  e = l + LPF m
+      // ---- 2. Z[e] = Xe[e] + i Xo[e] from the bins X[e], X[N-e]; inverse = conj(FFT(conj Z))/N.  e = l + LPF m.
+      //      A pair (k, N-k), k = l + LPF m < N/2, yields both Z[k] (this lane, register m) and Z[N-k], which lives in
+      //      lane (LPF - l), register 31 - m (lane 0: itself, register 32 - m): computed once, handed over by shuffle.
+      //      The common factor 1/2 of Xe, Xo is folded into the final scale (exact: a power of two).
       const bool live = (g0 + g_own - p.pad_frames >= 0) && (g0 + g_own - p.pad_frames < p.n_frames);
       float2 z[32];
       {
         const float2* S = reinterpret_cast<const float2*>(slot);
+        float2 pb[16];  // conj(Z[N-k]) of pair m
 #pragma unroll
-        for (int m = 0; m < 32; ++m) {
-          const int e = l + LPF * m;
-          const int k = (m < 16) ? e : N - e;  // for e > N/2 use the pair: Z[e] = conj(Xe[k]) + i conj(Xo[k])
+        for (int m = 0; m < 16; ++m) {
+          const int k = l + LPF * m;
           const float2 xk = S[k], xn = S[N - k];
-          const float2 xe = make_float2(0.5f * (xk.x + xn.x), 0.5f * (xk.y - xn.y));
-          const float2 tt = make_float2(0.5f * (xk.x - xn.x), 0.5f * (xk.y + xn.y));
-          float2 w;
-          if (k == N / 2) w = make_float2(0.f, -1.f);
-          else w = ut[k];  // exp(-i pi k / N)
-          const float2 xo = make_float2(fmaf(w.x, tt.x, w.y * tt.y), fmaf(w.x, tt.y, -w.y * tt.x));  // conj(w) tt
-          float2 zz = make_float2(xe.x - xo.y, xe.y + xo.x);
-          if (m >= 16 && e != N / 2) zz = make_float2(xe.x + xo.y, -xe.y + xo.x);
-          z[m] = make_float2(zz.x, -zz.y);
+          const float2 xe = make_float2(xk.x + xn.x, xk.y - xn.y);  // 2 Xe
+          const float2 tt = make_float2(xk.x - xn.x, xk.y + xn.y);
+          const float2 w = ut[k];                                   // exp(-i pi k / N)
+          const float2 xo = make_float2(fmaf(w.x, tt.x, w.y * tt.y), fmaf(w.x, tt.y, -w.y * tt.x));  // 2 Xo = conj(w) tt
+          z[m] = make_float2(xe.x - xo.y, -(xe.y + xo.x));          // conj(Xe + i Xo)
+          pb[m] = make_float2(xe.x + xo.y, xe.y - xo.x);            // conj(conj Xe + i conj Xo)
+        }
+        float2 zh;  // element N/2 (lane 0, register 16): k = N/2 pairs with itself, w = -i
+        {
+          const float2 xh = S[N / 2];
+          const float2 xe = make_float2(2.0f * xh.x, 0.f), tt = make_float2(0.f, 2.0f * xh.y);
+          const float2 xo = make_float2(-tt.y, tt.x);               // conj(-i) tt = i tt
+          zh = make_float2(xe.x - xo.y, -(xe.y + xo.x));
+        }
+#pragma unroll
+        for (int m = 0; m < 16; ++m) {
+          float2 rv;
+          rv.x = __shfl_sync(0xffffffffu, pb[m].x, src_lane);
+          rv.y = __shfl_sync(0xffffffffu, pb[m].y, src_lane);
+          if (l == 0) rv = (m < 15) ? pb[m + 1] : zh;
+          z[31 - m] = rv;
         }
       }
       __syncwarp();  // every lane of this frame holds its bins: the slot may now serve as the exchange plane
@@ -127,6 +146,63 @@ __global__ void __launch_bounds__(256, 2) istft_kernel(const Params p) {
       const float* cin = carry + cur * NFFT;
       float* cout = carry + (cur ^ 1) * NFFT;
       const bool emit = gidx >= gs;
+      if (vec4) {
+        // hop, FS and the carry offsets are multiples of 4: a thread owns 4 consecutive residues (one dmax for all
+        // four, see the launch code) and moves float4s -- 4x fewer shared-memory and address instructions
+        for (int r = 4 * r4_first; r < hop; r += 4 * RL4) {
+          const int dmax = (NFFT - 1 - r) / hop;
+          const int qn = G + dmax;
+          float4 ef = make_float4(0.f, 0.f, 0.f, 0.f);
+          for (int d = 0; d <= dmax; ++d) {
+            const float4 wv = *reinterpret_cast<const float4*>(win + d * hop + r);
+            ef.x = fmaf(wv.x, wv.x, ef.x); ef.y = fmaf(wv.y, wv.y, ef.y);
+            ef.z = fmaf(wv.z, wv.z, ef.z); ef.w = fmaf(wv.w, wv.w, ef.w);
+          }
+          const float4 inv_ef = make_float4(1.0f / ef.x, 1.0f / ef.y, 1.0f / ef.z, 1.0f / ef.w);
+          for (int q = q4_first; q < qn; q += QL4) {
+            const int trel = q * hop + r;
+            float4 acc = trel < tail ? *reinterpret_cast<const float4*>(cin + trel) : make_float4(0.f, 0.f, 0.f, 0.f);
+            const int jlo = max(q - dmax, 0), jhi = min(q, G - 1);
+            for (int j = jlo; j <= jhi; ++j) {
+              const float4 v = *reinterpret_cast<const float4*>(reg + j * FS + (q - j) * hop + r);
+              acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+            }
+            if (q >= G) {
+              *reinterpret_cast<float4*>(cout + trel - G * hop) = acc;
+              continue;
+            }
+            if (!emit) continue;
+            const long long t = (long long)(g0 + q) * hop + r;
+            const long long i = t - p.start;
+            const int dlo = max(g0 + q - (NP - 1), 0), dhi = min(dmax, g0 + q);
+            const bool interior = (dlo == 0 && dhi == dmax);
+            if (interior && i >= 0 && i + 3 < p.out_len && t + 3 < p.expected &&
+                ((reinterpret_cast<uintptr_t>(orow + i) & 15) == 0)) {
+              *reinterpret_cast<float4*>(orow + i) =
+                  make_float4(acc.x * inv_ef.x, acc.y * inv_ef.y, acc.z * inv_ef.z, acc.w * inv_ef.w);
+            } else {  // signal ends, unaligned rows: per sample, same arithmetic as the scalar path
+              const float a4[4] = {acc.x, acc.y, acc.z, acc.w};
+              const float ie4[4] = {inv_ef.x, inv_ef.y, inv_ef.z, inv_ef.w};
+#pragma unroll
+              for (int u = 0; u < 4; ++u) {
+                const long long iu = i + u;
+                if (iu < 0 || iu >= p.out_len) continue;
+                float v = 0.f;
+                if (t + u < p.expected) {
+                  if (interior) {
+                    v = a4[u] * ie4[u];
+                  } else {
+                    float env = 0.f;
+                    for (int d = dlo; d <= dhi; ++d) { const float wv = win[d * hop + r + u]; env = fmaf(wv, wv, env); }
+                    v = a4[u] / env;
+                  }
+                }
+                orow[iu] = v;
+              }
+            }
+          }
+        }
+      } else
       for (int r = r_first; r < hop; r += RL) {
         const int dmax = (NFFT - 1 - r) / hop;  // frames n with (q - n) in [0, dmax] cover residue r of hop q
         const int qn = G + dmax;                // hops of this group's span that hold residue r
@@ -194,7 +270,7 @@ static int launch(Params& p, void* stream) {
   constexpr int N = PL::N, G = 8 * PL::FPW, NFFT = 2 * N;
   int FS = NFFT + 2;
   if (FS < PL::XB) FS = PL::XB;
-  FS = (FS + 1) & ~1;
+  FS = (FS + 3) & ~3;  // multiple of 4: float4 access in the gather
   p.FS = FS;
   int o = 0;
   p.off_tw = o; o = align16(o + PL::NTW * PL::LPF * 8 + 16);

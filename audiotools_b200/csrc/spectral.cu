@@ -588,9 +588,10 @@ __global__ void __launch_bounds__(256, 2) spectral_warp_kernel(Params p) {
         const int k = l + LPF * m;
         const float2 xe = make_float2(zk.x + zn.x, zk.y - zn.y);  // (Zk + conj Zn)/2   (window halved above)
         const float2 xo = make_float2(zk.y + zn.y, zn.x - zk.x);  // (Zk - conj Zn)/(2i)
-        const float2 tt = cmul(ut[m * LPF + l], xo);
-        const float2 xk = cadd(xe, tt);
-        const float2 d = csub(xe, tt);
+        // X[k] = Xe + W Xo, X[N-k]* = Xe - W Xo: a twiddled butterfly, fused like the ones of the transform
+        const float2 w = ut[m * LPF + l];
+        const float2 xk = make_float2(fmaf(w.x, xo.x, fmaf(-w.y, xo.y, xe.x)), fmaf(w.x, xo.y, fmaf(w.y, xo.x, xe.y)));
+        const float2 d = make_float2(fmaf(2.0f, xe.x, -xk.x), fmaf(2.0f, xe.y, -xk.y));
         if constexpr (STAGED) {  // park the complex bins in the frame's own slot (the exchange plane is dead now)
           float2* xc = reinterpret_cast<float2*>(xb);
           xc[k] = make_float2(g * xk.x, g * xk.y);

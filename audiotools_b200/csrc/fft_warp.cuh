@@ -55,7 +55,9 @@ __device__ __forceinline__ float2 mul_wr(float2 o) {
   }
 }
 
-template <int R, int S>
+// PRE: the first butterfly stage (pairs in[j], in[j + R S / 2] of the outermost call) was already applied by the
+// caller, which could fuse it with the load (spectral.cu folds the window multiply into it).
+template <int R, int S, bool PRE = false>
 struct DFT {
   // out[K] = e + W o, out[K + R/2] = e - W o with W = exp(-2 pi i K / R) = c - i sn.  For a non-trivial W the sum is
   // formed with fused multiply-adds and the difference as 2e - sum: 6 instructions instead of 8 (complex multiply,
@@ -64,7 +66,10 @@ struct DFT {
   template <int K>
   static __device__ __forceinline__ void comb(const float2 (&e)[R / 2], const float2 (&o)[R / 2], float2* out) {
     constexpr int j = 32 * K / R;  // angle = pi*j/16
-    if constexpr (j == 0 || j == 8) {
+    if constexpr (R == 2 && PRE) {
+      out[K] = e[K];
+      out[K + R / 2] = o[K];
+    } else if constexpr (j == 0 || j == 8) {
       const float2 t = mul_wr<R, K>(o[K]);
       out[K] = cadd(e[K], t);
       out[K + R / 2] = csub(e[K], t);
@@ -90,13 +95,13 @@ struct DFT {
   // in: R values at in[0], in[S], ...; out: R values, natural frequency order
   static __device__ __forceinline__ void run(const float2* in, float2* out) {
     float2 e[R / 2], o[R / 2];
-    DFT<R / 2, 2 * S>::run(in, e);
-    DFT<R / 2, 2 * S>::run(in + S, o);
+    DFT<R / 2, 2 * S, PRE>::run(in, e);
+    DFT<R / 2, 2 * S, PRE>::run(in + S, o);
     comb<0>(e, o, out);
   }
 };
-template <int S>
-struct DFT<1, S> {
+template <int S, bool PRE>
+struct DFT<1, S, PRE> {
   static __device__ __forceinline__ void run(const float2* in, float2* out) { out[0] = in[0]; }
 };
 
@@ -139,13 +144,15 @@ __device__ __forceinline__ float fast_log2(float v) {
 #endif
 }
 
-template <int LOG2N>
+// PRE0: z[j], z[j + 16] (j < 16) already hold sum and difference of elements j and j + 16 (the first butterfly stage
+// of the radix-32 pass).
+template <int LOG2N, bool PRE0 = false>
 __device__ __forceinline__ void warp_fft(float2 (&z)[32], float* xb, const float2* tw, int l) {
   using PL = WPlan<LOG2N>;
   constexpr int LPF = PL::LPF, R1 = PL::R1, B1 = PL::B1;
   {
     float2 o[32];
-    DFT<32, 1>::run(z, o);
+    DFT<32, 1, PRE0>::run(z, o);
 #pragma unroll
     for (int t = 0; t < 32; ++t) z[t] = o[t];
   }

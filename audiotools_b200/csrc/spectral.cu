@@ -544,21 +544,30 @@ __global__ void __launch_bounds__(256, 2) spectral_warp_kernel(Params p) {
       const bool live = n < p.n_frames;
       const float* fs = sp + f * hop;
 
-      // ---- windowed frame, element e = l + LPF m
+      // ---- windowed frame, element e = l + LPF m; the first butterfly stage of the radix-32 pass (elements m and
+      //      m + 16) is formed right here with the window multiply fused in: a = s_m w_m, sum = fma(s_n, w_n, a),
+      //      difference = fma(-s_n, w_n, a)  (3 instead of 4 instructions per component pair)
       float2 z[32];
       if ((hop & 1) == 0) {
 #pragma unroll
-        for (int m = 0; m < 32; ++m) {
-          const int e = l + LPF * m;
-          const float2 s2 = *reinterpret_cast<const float2*>(fs + 2 * e);
-          const float2 w2 = *reinterpret_cast<const float2*>(win + 2 * e);
-          z[m] = make_float2(s2.x * w2.x, s2.y * w2.y);
+        for (int m = 0; m < 16; ++m) {
+          const int e0 = l + LPF * m, e1 = e0 + LPF * 16;
+          const float2 s0 = *reinterpret_cast<const float2*>(fs + 2 * e0);
+          const float2 w0 = *reinterpret_cast<const float2*>(win + 2 * e0);
+          const float2 s1 = *reinterpret_cast<const float2*>(fs + 2 * e1);
+          const float2 w1 = *reinterpret_cast<const float2*>(win + 2 * e1);
+          const float ax = s0.x * w0.x, ay = s0.y * w0.y;
+          z[m] = make_float2(fmaf(s1.x, w1.x, ax), fmaf(s1.y, w1.y, ay));
+          z[m + 16] = make_float2(fmaf(-s1.x, w1.x, ax), fmaf(-s1.y, w1.y, ay));
         }
       } else {
 #pragma unroll
-        for (int m = 0; m < 32; ++m) {
-          const int e = l + LPF * m;
-          z[m] = make_float2(fs[2 * e] * win[2 * e], fs[2 * e + 1] * win[2 * e + 1]);
+        for (int m = 0; m < 16; ++m) {
+          const int e0 = l + LPF * m, e1 = e0 + LPF * 16;
+          const float ax = fs[2 * e0] * win[2 * e0], ay = fs[2 * e0 + 1] * win[2 * e0 + 1];
+          const float sx = fs[2 * e1], sy = fs[2 * e1 + 1], wx = win[2 * e1], wy = win[2 * e1 + 1];
+          z[m] = make_float2(fmaf(sx, wx, ax), fmaf(sy, wy, ay));
+          z[m + 16] = make_float2(fmaf(-sx, wx, ax), fmaf(-sy, wy, ay));
         }
       }
       if (rd == FR / G - 1) {
@@ -574,7 +583,7 @@ __global__ void __launch_bounds__(256, 2) spectral_warp_kernel(Params p) {
               &s_bar);
         }
       }
-      warp_fft<LOG2N>(z, xb, tw, l);  // z[m] = Z[l + LPF m]
+      warp_fft<LOG2N, true>(z, xb, tw, l);  // z[m] = Z[l + LPF m]
 
       // ---- untangle -> real-FFT bins k = l + LPF m (m < 16) and N - k ; magnitudes into xb
       float2* so = (DIRECT && p.stft_out) ? p.stft_out + (size_t)row * F * p.n_frames + n : nullptr;

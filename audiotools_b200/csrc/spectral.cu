@@ -503,6 +503,7 @@ __global__ void __launch_bounds__(256, 2) spectral_warp_kernel(Params p) {
         for (int i = 0; w + 32 * i < p.n_mels; ++i) {
           int mx = 0;
           for (int j = 0; j < 4; ++j) { const int m = w + 8 * (4 * i + j); if (m < p.n_mels) mx = max(mx, mseg[m].z); }
+          mx = (mx + 1) & ~1;  // even width: the projection loop is unrolled by two without a remainder
           for (int j = 0; j < 4; ++j) {
             const int m = w + 8 * (4 * i + j);
             if (m < p.n_mels) { mseg[m].x = run; mseg[m].w = mx; run += mx; reach = max(reach, mseg[m].y + 4 * mx); }
@@ -642,41 +643,41 @@ __global__ void __launch_bounds__(256, 2) spectral_warp_kernel(Params p) {
         for (int fc = 0; fc < FR; fc += 8) {
           const int f = fc + fl;
           const float* xf = xbs + f * p.xb_stride;
-          for (int mm = warp + 8 * jq; mm < p.n_mels; mm += 32) {
-            const int4 sg = mseg[mm];  // (row offset, lo4, own n4, padded n4: the same for the 4 filters of a step)
-            const float4* w4 = mpk4 + sg.x;
-            float a0 = 0.f, a1 = 0.f;
-            if (!s_clamp) {  // the padded rows stay inside the frame's |X| slot: straight-line 4-wide groups
+          if (!s_clamp) {  // the padded rows stay inside the frame's |X| slot (always, for the stock filterbanks)
+            for (int mm = warp + 8 * jq; mm < p.n_mels; mm += 32) {
+              const int4 sg = mseg[mm];  // (row offset, lo4, own n4, padded even n4: the same for the 4 filters of a step)
+              const float4* w4 = mpk4 + sg.x;
               const float4* v4 = reinterpret_cast<const float4*>(xf + sg.y);
-              int it = 0;
-              for (; it + 4 <= sg.w; it += 4) {
-                float4 w[4], v[4];
-#pragma unroll
-                for (int u = 0; u < 4; ++u) { w[u] = w4[it + u]; v[u] = v4[it + u]; }
-#pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                  a0 = fmaf(w[u].x, v[u].x, a0); a1 = fmaf(w[u].y, v[u].y, a1);
-                  a0 = fmaf(w[u].z, v[u].z, a0); a1 = fmaf(w[u].w, v[u].w, a1);
-                }
+              float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+              for (int it = 0; it < sg.w; it += 2) {
+                const float4 wa = w4[it], wb = w4[it + 1], va = v4[it], vb = v4[it + 1];
+                a0 = fmaf(wa.x, va.x, a0); a1 = fmaf(wa.y, va.y, a1);
+                a2 = fmaf(wb.x, vb.x, a2); a3 = fmaf(wb.y, vb.y, a3);
+                a0 = fmaf(wa.z, va.z, a0); a1 = fmaf(wa.w, va.w, a1);
+                a2 = fmaf(wb.z, vb.z, a2); a3 = fmaf(wb.w, vb.w, a3);
               }
-              for (; it < sg.w; ++it) {
-                const float4 w = w4[it], v = v4[it];
-                a0 = fmaf(w.x, v.x, a0); a1 = fmaf(w.y, v.y, a1);
-                a0 = fmaf(w.z, v.z, a0); a1 = fmaf(w.w, v.w, a1);
-              }
-            } else {
-              const int lim = PL::XB - 4;
+              float acc = ((a0 + a1) + (a2 + a3)) * ga;
+              if (p.post == B2A_POST_LOG10) acc = lscale * fast_log2(fmaxf(acc, p.post_eps));
+              else if (p.post == B2A_POST_LN) acc = logf(acc + p.post_eps);
+              melt[mm * (FR + 1) + f] = acc;
+            }
+          } else {  // a zero-padded row would read past the slot: clamp the index
+            const int lim = PL::XB - 4;
+            for (int mm = warp + 8 * jq; mm < p.n_mels; mm += 32) {
+              const int4 sg = mseg[mm];
+              const float4* w4 = mpk4 + sg.x;
+              float a0 = 0.f, a1 = 0.f;
               for (int it = 0; it < sg.w; ++it) {
                 const float4 w = w4[it];
                 const float4 v = *reinterpret_cast<const float4*>(xf + min(sg.y + 4 * it, lim));
                 a0 = fmaf(w.x, v.x, a0); a1 = fmaf(w.y, v.y, a1);
                 a0 = fmaf(w.z, v.z, a0); a1 = fmaf(w.w, v.w, a1);
               }
+              float acc = (a0 + a1) * ga;
+              if (p.post == B2A_POST_LOG10) acc = lscale * fast_log2(fmaxf(acc, p.post_eps));
+              else if (p.post == B2A_POST_LN) acc = logf(acc + p.post_eps);
+              melt[mm * (FR + 1) + f] = acc;
             }
-            float acc = (a0 + a1) * ga;
-            if (p.post == B2A_POST_LOG10) acc = lscale * fast_log2(fmaxf(acc, p.post_eps));
-            else if (p.post == B2A_POST_LN) acc = logf(acc + p.post_eps);
-            melt[mm * (FR + 1) + f] = acc;
           }
         }
       } else {  // band table does not fit in shared memory: weights from global

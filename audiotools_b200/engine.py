@@ -235,7 +235,8 @@ class Engine:
     # ------------------------------------------------------------------ STFT / mel
     def _packed_len(self, mel_lo: torch.Tensor, mel_hi: torch.Tensor, n_fft: int) -> int:
         """Floats of the shared-memory band table of csrc/spectral.cu: row m is filter m's 4-aligned band, padded
-        to the widest of the (up to) 4 filters {w + 8*(4i + j), j < 4} that warp w = m % 8 projects in step i."""
+        to the widest of the (up to) 4 filters {w + 8*(4i + j), j < 4} that warp w = m % 8 projects in step i, rounded
+        up to an even number of float4s (the projection loop is unrolled by two, no remainder)."""
         key = (mel_lo.data_ptr(), mel_hi.data_ptr(), mel_lo.numel())
         if key not in self._packed_cache:
             lo, hi = mel_lo.cpu().numpy().astype("int64"), mel_hi.cpu().numpy().astype("int64")
@@ -245,7 +246,7 @@ class Engine:
                 i = 0
                 while w + 32 * i < n:
                     grp = [w + 8 * (4 * i + j) for j in range(4) if w + 8 * (4 * i + j) < n]
-                    total += int(max(n4[m] for m in grp)) * len(grp)
+                    total += ((int(max(n4[m] for m in grp)) + 1) & ~1) * len(grp)  # rows padded to an even width
                     i += 1
             self._packed_cache[key] = 4 * total
         return self._packed_cache[key]

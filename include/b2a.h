@@ -65,8 +65,8 @@ const char* b2a_last_error(void);
  *            dense matmul exactly for ANY matrix).
  *   mel_packed_len  floats of the kernel's shared-memory band table (0: read the weights from global):
  *            with n4[m] = (ceil4(mel_hi[m]) - floor4(mel_lo[m]))/4, 4 * sum over filters m of
- *            max(n4[m'] : m' in {w + 8*(4i + j), j < 4}) where w = m % 8, i = m / 32 (the filters one warp
- *            projects in one step share a trip count).
+ *            even(max(n4[m'] : m' in {w + 8*(4i + j), j < 4})) where w = m % 8, i = m / 32, even(v) = (v+1) & ~1
+ *            (the filters one warp projects in one step share a trip count; the loop is unrolled by two).
  *   mel_out  nullable [rows, n_mels, n_frames]    stft_out  nullable [rows, F, n_frames] (re,im)
  *   n_frames = 1 + (T + 2*pad + right_pad)/hop - 2*drop_edge,  F = n_fft/2 + 1
  */

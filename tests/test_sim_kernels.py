@@ -119,6 +119,51 @@ def test_mel_variants_golden(eng, golden):
     assert rel_err(mel, torch.from_numpy(golden["cfg1_mel40_fmin_fmax"])) < 1e-5
 
 
+def test_spectral_modes_agree(eng, golden):
+    """The warp kernel has three instantiations (mel only / staged STFT only / STFT + mel straight from registers):
+    the same launch parameters must give the same numbers whichever one serves them, with and without a gain."""
+    x = cases.make_input("cfg1")
+    w = sp.get_window("hann", 512)
+    fb, lo, hi = _mel_tables(16000, 512, 80)
+    gain = torch.tensor([0.5, 2.0, 1.0, 0.25])
+    for g in (None, gain):
+        both = eng.spectral(x, 512, 128, w, gain=g, mel_fb=fb, mel_lo=lo, mel_hi=hi, want_stft=True)     # mode 2
+        mel = eng.spectral(x, 512, 128, w, gain=g, mel_fb=fb, mel_lo=lo, mel_hi=hi, want_stft=False)     # mode 0
+        stft = eng.spectral(x, 512, 128, w, gain=g, want_stft=True)                                      # mode 1
+        assert torch.equal(both["mel"], mel["mel"])
+        assert torch.equal(both["stft"], stft["stft"])
+        scale = 1.0 if g is None else g[:, None, None, None]
+        assert rel_err(torch.view_as_real(stft["stft"]), torch.view_as_real(torch.from_numpy(golden["cfg1_stft"]) * scale)) < 1e-5
+    # odd hop (scalar load path), window 256 / hop 100, all three modes
+    w2 = sp.get_window("average", 256)
+    a = eng.spectral(x[:2], 256, 100, w2, want_stft=True)["stft"]
+    assert rel_err(torch.view_as_real(a), torch.view_as_real(torch.from_numpy(golden["cfg1_stft_average_hop100"]))) < 1e-5
+    fb2, lo2, hi2 = _mel_tables(16000, 256, 20)
+    b = eng.spectral(x[:2], 256, 100, w2, mel_fb=fb2, mel_lo=lo2, mel_hi=hi2, want_stft=True)
+    assert torch.equal(b["stft"], a)
+    assert torch.equal(b["mel"], eng.spectral(x[:2], 256, 100, w2, mel_fb=fb2, mel_lo=lo2, mel_hi=hi2, want_stft=False)["mel"])
+
+
+def test_istft_random_geometries(eng):
+    """Random (n_fft, hop, frames, length) against torch.istft: segment boundaries, warm-up, carries, tail fill."""
+    rng = np.random.RandomState(0)
+    for it in range(14):
+        n_fft = int(rng.choice([64, 128, 256, 512, 1024, 2048]))
+        hop = int(rng.choice([n_fft // 4, n_fft // 2, n_fft, n_fft // 8, max(1, n_fft // 3),
+                              int(rng.randint(max(4, n_fft // 8), n_fft + 1))]))
+        rows, nfr = int(rng.randint(1, 4)), int(rng.randint(1, 40))
+        T = max((nfr - 1) * hop, n_fft // 2 + 1 + 3 * hop)
+        g = torch.Generator().manual_seed(it)
+        w = torch.hann_window(n_fft) + 0.05 + 0.1 * torch.rand(n_fft, generator=g)
+        X = torch.stft(torch.randn(rows, max(T, n_fft), generator=g), n_fft, hop, window=w, center=True, return_complex=True)
+        X = X * (1 + 0.2 * torch.randn(X.shape, generator=g))
+        length = int(rng.randint(1, (X.shape[-1] - 1) * hop + n_fft // 2 + 1))
+        ref = torch.istft(X, n_fft, hop, window=w, center=True, length=length)
+        out = eng.istft(X[:, None].contiguous(), n_fft, hop, w, length)[:, 0]
+        keep = max(1, length - 2 * hop)  # the envelope -> 0 at the very end amplifies rounding
+        assert rel_err(out[..., :keep], ref[..., :keep]) < 5e-5, (n_fft, hop, rows, X.shape[-1], length)
+
+
 # ------------------------------------------------------------------------------------------
 # FIR / convolution / resample / pitch (csrc/fftconv.cu, resample.cu, pitch.cu)
 # ------------------------------------------------------------------------------------------
@@ -352,3 +397,62 @@ def test_spec_rotate_and_mask_low_match_reference(eng, golden_spec):
     want = sp.mask_low_magnitudes(X, mg.DBCUT, val=0.5)  # non-zero fill keeps the phase
     got = eng.spec_mask_low(X.clone(), mg.DBCUT, val=0.5)
     assert rel_err(torch.view_as_real(got), torch.view_as_real(want)) < 1e-5
+
+
+# ------------------------------------------------------------------------------------------
+# randomised geometry sweeps (small sizes): padding modes, offsets, strides, partitions
+# ------------------------------------------------------------------------------------------
+def _extend(x, lo, hi, mode):
+    """x[..., lo:hi] with out-of-range indices resolved by ``mode``."""
+    T = x.shape[-1]
+    idx = torch.arange(lo, hi)
+    if mode == "replicate":
+        return x[..., idx.clamp(0, T - 1)]
+    if mode == "circular":
+        return x[..., idx % T]
+    v = torch.zeros(*x.shape[:-1], hi - lo)
+    ok = (idx >= 0) & (idx < T)
+    v[..., ok] = x[..., idx[ok]]
+    return v
+
+
+def test_fir_direct_random_geometries(eng):
+    import torch.nn.functional as Fn
+
+    rng = np.random.RandomState(1)
+    for it in range(14):
+        B, C, T = int(rng.randint(1, 4)), int(rng.randint(1, 3)), int(rng.randint(200, 5000))
+        K, stride = int(rng.randint(1, 320)), int(rng.choice([1, 1, 2, 3, 4]))
+        g = torch.Generator().manual_seed(it)
+        x, taps = torch.randn(B, C, T, generator=g), torch.randn(B, K, generator=g)
+        left, left0 = torch.from_numpy(rng.randint(0, K + 3, size=B)).int(), int(rng.randint(0, 5))
+        mode = str(rng.choice(["constant", "replicate"]))
+        out_len = int(rng.randint(1, (T + stride - 1) // stride + 1))
+        sub = bool(stride == 1 and out_len <= T and rng.rand() < 0.3)
+        out = eng.fir_direct(x, taps, rows_per_filt=C, left=left, left0=left0, stride=stride, out_len=out_len,
+                             pad_mode=mode, subtract_from_input=sub)
+        for b in range(B):
+            L = left0 + int(left[b])
+            xv = _extend(x[b], -L, (out_len - 1) * stride + K - L, mode)
+            y = Fn.conv1d(xv[:, None, :], taps[b].reshape(1, 1, K), stride=stride)[:, 0, :out_len]
+            ref = (x[b, :, :out_len] - y) if sub else y
+            assert rel_err(out[b], ref) < 2e-5, (B, C, T, K, stride, mode, out_len, sub)
+
+
+def test_fftconv_random_geometries(eng):
+    import torch.nn.functional as Fn
+
+    rng = np.random.RandomState(2)
+    for it, Lf in enumerate([5, 641, 1024, 1025, 2500, 100]):  # 1 partition (product formed in the inverse FFT) and several
+        B, C, T = int(rng.randint(1, 3)), int(rng.randint(1, 3)), int(rng.randint(1500, 7000))
+        g = torch.Generator().manual_seed(100 + it)
+        x, taps = torch.randn(B, C, T, generator=g), torch.randn(B, Lf, generator=g) / Lf ** 0.5
+        off = torch.from_numpy(rng.randint(0, Lf, size=B)).int()
+        mode, sub = str(rng.choice(["constant", "replicate", "circular"])), bool(rng.rand() < 0.3)
+        out = eng.fftconv(x, taps, rows_per_filt=C, offset=off, offset0=0, pad_mode=mode, subtract_from_input=sub)
+        for b in range(B):
+            o = int(off[b])
+            xv = _extend(x[b], o - (Lf - 1), T + o, mode)  # out[n] = sum_k taps[k] xv[n - k + o]
+            y = Fn.conv1d(xv[:, None, :], taps[b].flip(0).reshape(1, 1, Lf))[:, 0, :T]
+            ref = (x[b] - y) if sub else y
+            assert rel_err(out[b], ref) < 5e-5, (B, C, T, Lf, mode, sub)

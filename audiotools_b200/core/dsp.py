@@ -33,6 +33,15 @@ class DSPMixin:
         self.stft_data = None
         return self
 
+    def preemphasis(self, coef: float = 0.85):
+        """The reference's pre-emphasis filter (ref :372-390): ``conv1d`` with the kernel ``[1, -coef, 0]`` and one
+        sample of zero padding, i.e. ``y[n] = x[n-1] - coef * x[n]`` -- one launch of the direct FIR kernel."""
+        x = self._materialized()
+        taps = torch.tensor([[1.0, -float(coef), 0.0]], dtype=torch.float32, device=x.device)
+        rows = x.shape[0] * x.shape[1]
+        self.audio_data = _engine().fir_direct(x, taps, rows_per_filt=rows, left0=1, stride=1, pad_mode="constant")
+        return self
+
     # ------------------------------------------------------------------ spectral masks (ref :217-370)
     def _band_mask(self, lo, hi, axis_vals, axis: int, val: float):
         if self.stft_data is None:

@@ -318,6 +318,15 @@ def test_low_high_pass_match_reference(at, golden):
     assert sig.low_pass(4000).stft_data is None  # filters drop the STFT cache (ref dsp.py:182)
 
 
+def test_preemphasis_matches_conv1d(at):
+    """ref:audiotools/core/dsp.py:372-390."""
+    x = cases.make_input("cfg2")
+    y = sig_of(at, "cfg2").preemphasis(0.85).audio_data.cpu()
+    k = torch.tensor([1.0, -0.85, 0.0]).view(1, 1, -1)
+    ref = torch.nn.functional.conv1d(x.reshape(-1, 1, x.shape[-1]), k, padding=1).reshape(x.shape)
+    assert torch.allclose(y, ref, atol=1e-6)
+
+
 def test_low_high_pass_sine_thresholds(at):
     """ref:tests/core/test_dsp.py:76-109 (fully synthetic in the reference too)."""
     sr, f = 44100, 440

@@ -439,6 +439,18 @@ def test_fir_direct_random_geometries(eng):
             assert rel_err(out[b], ref) < 2e-5, (B, C, T, K, stride, mode, out_len, sub)
 
 
+def test_preemphasis_kernel_config(eng):
+    """DSPMixin.preemphasis (ref:audiotools/core/dsp.py:372-390) = conv1d([1, -coef, 0], padding=1): the direct FIR
+    kernel with 3 taps, one shared filter for every row, zero padding."""
+    import torch.nn.functional as Fn
+
+    x = cases.make_input("short")  # [2, 1, 4000]
+    taps = torch.tensor([[1.0, -0.85, 0.0]])
+    out = eng.fir_direct(x, taps, rows_per_filt=2, left0=1, stride=1, pad_mode="constant")
+    ref = Fn.conv1d(x.reshape(-1, 1, 4000), taps.view(1, 1, -1), padding=1).reshape(x.shape)
+    assert out.shape == x.shape and torch.allclose(out, ref, atol=1e-7)
+
+
 def test_fftconv_random_geometries(eng):
     import torch.nn.functional as Fn
 

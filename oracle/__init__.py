@@ -18,8 +18,10 @@ Pinning status (see DESIGN.md "Oracle")
 ---------------------------------------
 * First-party code: PINNED.  ``tests/golden/make_golden.py`` imports the real
   reference from ``/root/reference`` (with the absent third-party modules
-  shimmed by ``third_party.py``) and stores its outputs under ``tests/golden``;
-  ``tests/test_oracle_golden.py`` checks ``signal_path.py`` against them.
+  shimmed by ``third_party.py``) and stores its outputs under ``tests/golden``
+  (``make_golden_spectral.py`` does the same for the spectral masks and the
+  SpectralTransform family); ``tests/test_oracle_golden.py`` checks
+  ``signal_path.py`` against them.
 * ``torch.stft`` / ``torchaudio.functional.lfilter`` / ``scipy.signal``: the
   oracle calls the very same installed functions the reference calls.
 * julius / pyloudnorm / librosa restatements: pinned only by the reference's

@@ -4,7 +4,7 @@ The reference loops over the batch in Python, building one ``julius.LowPassFilte
 here the per-item tap design and the filtering are one grouped launch each (``csrc/fir.cu``).
 The spectral masks (ref:audiotools/core/dsp.py:217-370) work on ``stft_data``: the two band
 masks run as one store-only kernel (``csrc/specmask.cu``), the phase operations are container arithmetic on the
-complex tensor.  Windowing / overlap-add helpers of the reference's DSPMixin (``collect_windows``) are not mirrored."""
+complex tensor.  The chunking helpers (``windows`` / ``collect_windows`` / ``overlap_and_add``) are container reshapes."""
 import torch
 
 from . import util
@@ -17,6 +17,64 @@ def _engine():
 
 
 class DSPMixin:
+    # ------------------------------------------------------------------ chunking helpers (ref :15-151)
+    # Pure container reshapes on whatever device the samples live on (no kernel of their own): split long audio into
+    # overlapping windows for chunked inference and put the processed windows back together.
+    _original_batch_size = None
+    _original_num_channels = None
+    _padded_signal_length = None
+
+    def _preprocess_signal_for_windowing(self, window_duration, hop_duration):
+        self._original_batch_size = self.batch_size
+        self._original_num_channels = self.num_channels
+        window_length = int(window_duration * self.sample_rate)
+        hop_length = int(hop_duration * self.sample_rate)
+        if window_length % hop_length != 0:
+            window_length = (window_length // hop_length) * hop_length
+        self.zero_pad(hop_length, hop_length)
+        self._padded_signal_length = self.signal_length
+        return window_length, hop_length
+
+    def windows(self, window_duration: float, hop_duration: float, preprocess: bool = True):
+        """Generator over the windows of every (item, channel) row, each a [1, 1, window] signal (ref :31-68)."""
+        if preprocess:
+            window_length, hop_length = self._preprocess_signal_for_windowing(window_duration, hop_duration)
+        else:
+            window_length, hop_length = int(window_duration * self.sample_rate), int(hop_duration * self.sample_rate)
+        self.audio_data = self.audio_data.reshape(-1, 1, self.signal_length)
+        for b in range(self.batch_size):
+            for start in range(0, self.signal_length - window_length + 1, hop_length):
+                yield self[b, ..., start:start + window_length]
+
+    def collect_windows(self, window_duration: float, hop_duration: float, preprocess: bool = True):
+        """All windows stacked along the batch axis: [B*C*num_windows, 1, window] (ref :70-108)."""
+        if preprocess:
+            window_length, hop_length = self._preprocess_signal_for_windowing(window_duration, hop_duration)
+        else:
+            window_length, hop_length = int(window_duration * self.sample_rate), int(hop_duration * self.sample_rate)
+        rows = self.audio_data.reshape(-1, self.signal_length)
+        self.audio_data = rows.unfold(-1, window_length, hop_length).reshape(-1, 1, window_length).contiguous()
+        return self
+
+    def overlap_and_add(self, hop_duration: float):
+        """Inverse of :meth:`collect_windows`: overlap-add the windows, divide by the number of windows covering each
+        sample, drop the padding (ref :110-151)."""
+        hop_length = int(hop_duration * self.sample_rate)
+        window_length = self.signal_length
+        nb, nch = self._original_batch_size, self._original_num_channels
+        total = self._padded_signal_length
+        wins = self.audio_data.reshape(nb * nch, -1, window_length)
+        num = wins.shape[1]
+        idx = (torch.arange(num, device=wins.device)[:, None] * hop_length
+               + torch.arange(window_length, device=wins.device)[None, :]).reshape(-1)
+        folded = torch.zeros(nb * nch, total, dtype=wins.dtype, device=wins.device)
+        folded.index_add_(1, idx, wins.reshape(nb * nch, -1))
+        norm = torch.zeros(total, dtype=wins.dtype, device=wins.device)
+        norm.index_add_(0, idx, torch.ones(idx.numel(), dtype=wins.dtype, device=wins.device))
+        self.audio_data = (folded / norm).reshape(nb, nch, -1)
+        self.trim(hop_length, hop_length)
+        return self
+
     def low_pass(self, cutoffs, zeros: int = 51):
         """Low-pass each item at its own cutoff (Hz)."""
         cutoffs = util.ensure_tensor(cutoffs, 2, self.batch_size)

@@ -70,6 +70,14 @@ def main():
     out["smooth_window"] = win.audio_data.numpy()
     out["smooth_audio"] = sm(sig.clone(), **kw).audio_data.numpy()
 
+    # chunking helpers (ref:audiotools/core/dsp.py:15-151): collect_windows -> (a stand-in for a model) -> overlap_and_add
+    x2 = torch.cat([x[:1], 0.5 * x[:1].flip(-1)], 1)  # one stereo item
+    sw = AudioSignal(x2.clone(), 16000).collect_windows(0.1, 0.05)
+    out["win_collect"] = sw.audio_data.numpy()
+    sw.audio_data = sw.audio_data * 0.5 + 0.1
+    out["win_ola"] = sw.overlap_and_add(0.05).audio_data.numpy()
+    out["win_iter_count"] = np.int64(sum(1 for _ in AudioSignal(x2.clone(), 16000).windows(0.064, 0.016)))
+
     path = os.path.join(HERE, "reference_golden_spectral.npz")
     np.savez_compressed(path, **out)
     print(f"wrote {path}: {len(out)} arrays, {os.path.getsize(path)/1e6:.1f} MB on disk")

@@ -226,3 +226,22 @@ def test_all_true_mask_fast_path_matches_masked_round_trip():
     assert util.host_view(kw["MulTransform"]["mask"]) is kw["MulTransform"]["mask"]  # CPU tensors are their own view
     moved = util.prepare_batch(kw, "cpu")
     assert not hasattr(moved["MulTransform"]["mask"], "_b2a_host")
+
+
+def test_chunking_helpers_match_reference(golden_spec):
+    """windows / collect_windows / overlap_and_add are container reshapes (ref:audiotools/core/dsp.py:15-151): same
+    windows and the same reassembled signal as the real reference (tests/golden/make_golden_spectral.py)."""
+    from tests.golden import cases
+
+    x = cases.make_input("cfg1")
+    x2 = torch.cat([x[:1], 0.5 * x[:1].flip(-1)], 1)
+    s = AudioSignal(x2.clone(), 16000).collect_windows(0.1, 0.05)
+    assert torch.equal(s.audio_data, torch.from_numpy(golden_spec["win_collect"]))
+    s.audio_data = s.audio_data * 0.5 + 0.1
+    out = s.overlap_and_add(0.05).audio_data
+    assert out.shape == (1, 2, 16000) and torch.allclose(out, torch.from_numpy(golden_spec["win_ola"]), atol=1e-6)
+    wins = list(AudioSignal(x2.clone(), 16000).windows(0.064, 0.016))
+    assert len(wins) == int(golden_spec["win_iter_count"]) and wins[0].audio_data.shape == (1, 1, 1024)
+    # identity round trip: windows of an untouched signal add back to the signal
+    r = AudioSignal(x2.clone(), 16000).collect_windows(0.1, 0.05).overlap_and_add(0.05)
+    assert torch.allclose(r.audio_data, x2, atol=1e-6)

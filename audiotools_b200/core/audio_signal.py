@@ -377,7 +377,7 @@ class AudioSignal(EffectMixin, LoudnessMixin, ImpulseResponseMixin, DSPMixin):
         if length is None:
             length = self.original_signal_length + 2 * pad + right_pad
         eng = _engine()
-        if self.stft_data.is_cuda and eng.lib.b2a_istft_supported(int(window_length), int(hop_length)):
+        if eng.lib.b2a_istft_supported(int(window_length), int(hop_length)):  # (the engine refuses CPU tensors)
             if match_stride:
                 # the reference pads 2 zero frames on either side, inverts to `length`, then keeps
                 # [pad : length - (pad + right_pad)] (:1276-1292)
@@ -387,7 +387,7 @@ class AudioSignal(EffectMixin, LoudnessMixin, ImpulseResponseMixin, DSPMixin):
                 audio = eng.istft(self.stft_data, window_length, hop_length, window, length=length)
             self.audio_data = audio
             return self
-        if not self.stft_data.is_cuda:
+        if eng.require_cuda and not self.stft_data.is_cuda:
             raise RuntimeError(f"stft_data is on {self.stft_data.device}: audiotools_b200 runs on CUDA (sm_100a) "
                                "only and has no CPU fallback")
         s = self.stft_data.reshape(nb * nch, nf, nt)

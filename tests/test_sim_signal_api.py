@@ -1,0 +1,115 @@
+"""The AudioSignal / transforms layer driven end to end ON THE CPU: the product's host code with the engine swapped for
+the CPU-simulated build of the same kernel sources (tests/cusim).  This is what the `-m gpu` tests check on a B200,
+repeated here at the goldens' small sizes so that host-side regressions (argument plumbing, deferred gains, masks,
+match_stride trimming, per-item grouping) show up without a GPU."""
+import numpy as np
+import pytest
+import torch
+
+import audiotools_b200
+import audiotools_b200.engine as engine_mod
+from audiotools_b200 import AudioSignal
+from audiotools_b200.data import transforms as tfm
+from oracle import signal_path as sp
+from tests.conftest import rel_err
+from tests.cusim.sim_engine import sim_engine
+from tests.golden import cases
+
+TOL = 1e-4
+
+
+@pytest.fixture(autouse=True)
+def _sim_engine(monkeypatch):
+    monkeypatch.setattr(engine_mod, "_ENGINE", sim_engine())
+    yield
+
+
+def sig_of(name, sl=slice(None), **kw):
+    return AudioSignal(cases.make_input(name)[sl].clone(), cases.sample_rate(name), **kw)
+
+
+def G(golden, key):
+    return torch.from_numpy(golden[key])
+
+
+def test_stft_istft_and_match_stride(golden):
+    sig = sig_of("cfg1", slice(0, 2))
+    assert rel_err(torch.view_as_real(sig.stft()), torch.view_as_real(G(golden, "cfg1_stft")[:2])) < TOL
+    assert rel_err(sig.istft().audio_data, G(golden, "cfg1_istft")) < TOL
+    sig = sig_of("cfg1", slice(0, 2), stft_params=audiotools_b200.STFTParams(256, 64, "sqrt_hann", True, "reflect"))
+    assert rel_err(torch.view_as_real(sig.stft()), torch.view_as_real(G(golden, "cfg1_stft_match_stride"))) < TOL
+    assert rel_err(sig.istft().audio_data, G(golden, "cfg1_istft_match_stride")) < TOL
+
+
+def test_normalize_mel_deferred_gain(golden):
+    sig = sig_of("cfg2")
+    sig.normalize(-24.0)
+    logmel = sig.mel_spectrogram(n_mels=128, window_length=2048, hop_length=512, log=True)
+    assert rel_err(logmel, G(golden, "cfg2_logmel")) < TOL
+    assert rel_err(sig.audio_data, G(golden, "cfg2_norm")) < TOL
+
+
+def test_mix_matches_restated_reference():
+    """EffectMixin.mix (ref:audiotools/core/effects.py:27-64): pad / truncate the other signal, normalise it to
+    loudness(self) - snr, add."""
+    x = cases.make_input("lufs16k")            # [B, C, T] @ 16 kHz
+    g = torch.Generator().manual_seed(9)
+    noise = 0.05 * torch.randn(x.shape[0], x.shape[1], x.shape[2] - 1234, generator=g)
+    snr = torch.tensor([5.0, 15.0, 25.0, 10.0]).repeat(x.shape[0] // 4 + 1)[: x.shape[0]]
+    out = AudioSignal(x.clone(), 16000).mix(AudioSignal(noise.clone(), 16000), snr).audio_data
+    other = torch.nn.functional.pad(noise, (0, 1234))
+    tgt = sp.loudness(x, 16000) - snr
+    ref = x + sp.normalize(other, 16000, tgt)[0]
+    assert rel_err(out, ref) < TOL
+
+
+def test_apply_ir_and_compose_match_reference(golden):
+    ir = cases.make_ir()
+    drr = G(golden, "drr")
+    out = sig_of("fir").apply_ir(AudioSignal(ir.clone(), 44100), drr=drr, ir_eq=golden["eq_db"]).audio_data
+    assert rel_err(out, G(golden, "applyir_full")) < TOL
+    transform = tfm.Compose([tfm.VolumeNorm(db=("uniform", -30, -16)), tfm.Equalizer(prob=0.5), tfm.LowPass(prob=0.7),
+                             tfm.HighPass(prob=0.6), tfm.VolumeChange()])
+    sig = sig_of("tfm")
+    kwargs = transform.batch_instantiate([10, 11, 12, 13], sig)
+    assert rel_err(transform(sig.clone(), **kwargs).audio_data, G(golden, "tfm_out")) < TOL
+
+
+def test_spectral_family_matches_reference(golden_spec):
+    from tests.golden import make_golden_spectral as mg
+
+    g = golden_spec
+
+    def fresh():
+        s = sig_of("cfg1")
+        s.stft()
+        return s
+
+    assert rel_err(fresh().mask_frequencies(mg.FMIN, mg.FMAX).istft().audio_data, G(g, "maskfreq_audio")) < TOL
+    assert rel_err(fresh().mask_timesteps(mg.TMIN, mg.TMAX).istft().audio_data, G(g, "masktime_audio")) < TOL
+    assert rel_err(fresh().mask_low_magnitudes(mg.DBCUT).istft().audio_data, G(g, "masklow_audio")) < TOL
+    assert rel_err(fresh().shift_phase(mg.SHIFT).istft().audio_data, G(g, "shift_audio")) < TOL
+    assert rel_err(fresh().shift_phase(G(g, "corrupt_in")).istft().audio_data, G(g, "corrupt_audio")) < TOL
+    t = tfm.Compose([tfm.FrequencyMask(), tfm.TimeMask(prob=0.7), tfm.ShiftPhase(), tfm.MaskLowMagnitudes(prob=0.6),
+                     tfm.CorruptPhase(prob=0.5), tfm.InvertPhase(prob=0.5)])
+    sig = sig_of("cfg1")
+    kwargs = t.batch_instantiate(mg.SEEDS, sig)
+    assert rel_err(t(sig.clone(), **kwargs).audio_data, G(g, "compose_audio")) < TOL
+    sm = tfm.Smoothing()
+    kw = sm.batch_instantiate(mg.SEEDS, sig)
+    assert rel_err(sm(sig.clone(), **kw).audio_data, G(g, "smooth_audio")) < TOL
+
+
+def test_preemphasis_and_pitch_transform():
+    x = cases.make_input("short")  # [2, 1, 4000] @ 16 kHz
+    y = AudioSignal(x.clone(), 16000).preemphasis(0.85).audio_data
+    k = torch.tensor([1.0, -0.85, 0.0]).view(1, 1, -1)
+    assert torch.allclose(y, torch.nn.functional.conv1d(x.reshape(-1, 1, 4000), k, padding=1).reshape(x.shape), atol=1e-7)
+    xm = torch.cat([x, x.flip(0), x], 0).repeat(1, 1, 3)  # 6 items, 12000 samples
+    t = tfm.PitchShift(("choice", [-2, 0, 2]))
+    sig = AudioSignal(xm.clone(), 16000)
+    kw = t.batch_instantiate(list(range(6)), sig)
+    shifts = kw["PitchShift"]["n_semitones"].tolist()
+    out = t(sig.clone(), **kw).audio_data
+    for i, s in enumerate(shifts):  # one set of launches for the batch == each item on its own
+        assert torch.equal(out[i:i + 1], AudioSignal(xm[i:i + 1].clone(), 16000).pitch_shift(s).audio_data)

@@ -287,6 +287,94 @@ class HighPass(BaseTransform):
         return signal.high_pass(cutoff, zeros=self.zeros)
 
 
+class _PoolTransform(BaseTransform):
+    """Shared by the transforms that draw another signal: ``sources`` is an in-memory pool -- a list of ``AudioSignal``
+    (any lengths, resampled to the target rate on the device if needed) or a callable ``(state, signal) ->
+    AudioSignal`` -- instead of the reference's csv lists of audio files (file decoding is outside the hot path)."""
+
+    def _init_pool(self, sources, weights):
+        self.sources = sources
+        self.weights = weights
+
+    def _draw_excerpt(self, state: RandomState, signal: AudioSignal):
+        """One pool item, cut / zero-padded to the duration of ``signal`` at a random offset, with its channels."""
+        if callable(self.sources):
+            return self.sources(state, signal)
+        if not self.sources:
+            raise ValueError(f"{type(self).__name__} needs `sources`: a list of AudioSignal or a callable")
+        src = self.sources[state.choice(len(self.sources), p=self.weights)].clone()
+        if src.sample_rate != signal.sample_rate:
+            raise ValueError(f"pool item at {src.sample_rate} Hz, signal at {signal.sample_rate} Hz: resample the pool")
+        n = signal.signal_length
+        if src.signal_length > n:
+            off = int(state.randint(0, src.signal_length - n + 1))
+            src.audio_data = src.audio_data[..., off:off + n]
+        else:
+            src.zero_pad_to(n)
+        if src.num_channels != signal.num_channels:  # mono pool item -> every channel (ref loader: num_channels=...)
+            src.audio_data = src.audio_data[:, :1].expand(-1, signal.num_channels, -1).contiguous()
+        return src
+
+
+class NoiseFloor(BaseTransform):
+    """Adds Gaussian noise at ``db`` LUFS (ref :669-704).  The reference normalises the noise on the CPU while
+    instantiating; here the (seeded, host-drawn) noise is normalised by the LUFS kernel when the transform runs."""
+
+    def __init__(self, db: tuple = ("const", -50.0), name: str = None, prob: float = 1.0):
+        super().__init__(name=name, prob=prob)
+        self.db = db
+
+    def _instantiate(self, state: RandomState, signal: AudioSignal):
+        db = util.sample_from_dist(self.db, state)
+        audio_data = state.randn(signal.num_channels, signal.signal_length)
+        return {"nz_signal": AudioSignal(torch.from_numpy(audio_data).float()[None], signal.sample_rate), "db": db}
+
+    def _transform(self, signal, nz_signal, db):
+        return signal + nz_signal.clone().normalize(db)
+
+
+class BackgroundNoise(_PoolTransform):
+    """``signal.mix(bg_signal, snr, eq)`` (ref :707-792) with an in-memory pool of noise signals."""
+
+    def __init__(self, snr: tuple = ("uniform", 10.0, 30.0), sources: List[AudioSignal] = None,
+                 weights: List[float] = None, eq_amount: tuple = ("const", 1.0), n_bands: int = 3, name: str = None,
+                 prob: float = 1.0):
+        super().__init__(name=name, prob=prob)
+        self.snr = snr
+        self.eq_amount = eq_amount
+        self.n_bands = n_bands
+        self._init_pool(sources, weights)
+
+    def _instantiate(self, state: RandomState, signal: AudioSignal):
+        eq_amount = util.sample_from_dist(self.eq_amount, state)
+        eq = -eq_amount * state.rand(self.n_bands)
+        snr = util.sample_from_dist(self.snr, state)
+        return {"eq": eq, "bg_signal": self._draw_excerpt(state, signal), "snr": snr}
+
+    def _transform(self, signal, bg_signal, snr, eq):
+        return signal.mix(bg_signal.clone(), snr, eq)
+
+
+class CrossTalk(_PoolTransform):
+    """Mixes another talker in at ``snr`` and restores the original loudness (ref :795-854)."""
+
+    def __init__(self, snr: tuple = ("uniform", 0.0, 10.0), sources: List[AudioSignal] = None,
+                 weights: List[float] = None, name: str = None, prob: float = 1.0):
+        super().__init__(name=name, prob=prob)
+        self.snr = snr
+        self._init_pool(sources, weights)
+
+    def _instantiate(self, state: RandomState, signal: AudioSignal):
+        snr = util.sample_from_dist(self.snr, state)
+        return {"crosstalk_signal": self._draw_excerpt(state, signal), "snr": snr}
+
+    def _transform(self, signal, crosstalk_signal, snr):
+        loudness = signal.loudness()
+        mix = signal.mix(crosstalk_signal.clone(), snr)
+        mix.normalize(loudness)
+        return mix
+
+
 class RoomImpulseResponse(BaseTransform):
     """``signal.apply_ir(ir, drr, eq)`` (ref :857-938).  ``sources`` is an in-memory pool: a list of
     single-item ``AudioSignal`` impulse responses (or a callable ``(state, signal) -> AudioSignal``);

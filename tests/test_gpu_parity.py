@@ -318,15 +318,6 @@ def test_low_high_pass_match_reference(at, golden):
     assert sig.low_pass(4000).stft_data is None  # filters drop the STFT cache (ref dsp.py:182)
 
 
-def test_preemphasis_matches_conv1d(at):
-    """ref:audiotools/core/dsp.py:372-390."""
-    x = cases.make_input("cfg2")
-    y = sig_of(at, "cfg2").preemphasis(0.85).audio_data.cpu()
-    k = torch.tensor([1.0, -0.85, 0.0]).view(1, 1, -1)
-    ref = torch.nn.functional.conv1d(x.reshape(-1, 1, x.shape[-1]), k, padding=1).reshape(x.shape)
-    assert torch.allclose(y, ref, atol=1e-6)
-
-
 def test_low_high_pass_sine_thresholds(at):
     """ref:tests/core/test_dsp.py:76-109 (fully synthetic in the reference too)."""
     sr, f = 44100, 440
@@ -567,3 +558,38 @@ def test_spectral_transforms_match_reference(at, golden_spec):
         assert 0.0 < frac < 0.2  # only the masked band / frames were replaced
         y = tn(sig.clone().to(DEV), **kw)
         assert y.audio_data.shape == x0.shape and torch.isfinite(y.audio_data).all()
+
+
+def test_preemphasis_matches_conv1d(at):
+    """ref:audiotools/core/dsp.py:372-390."""
+    x = cases.make_input("cfg2")
+    y = sig_of(at, "cfg2").preemphasis(0.85).audio_data.cpu()
+    k = torch.tensor([1.0, -0.85, 0.0]).view(1, 1, -1)
+    ref = torch.nn.functional.conv1d(x.reshape(-1, 1, x.shape[-1]), k, padding=1).reshape(x.shape)
+    assert torch.allclose(y, ref, atol=1e-6)
+
+
+def test_noise_transforms_with_in_memory_pools(at, sp):
+    """NoiseFloor / BackgroundNoise / CrossTalk (ref:audiotools/data/transforms.py:669-854), in-memory pools; the CPU
+    twin of this test (tests/test_sim_signal_api.py) runs the same host code on the simulated kernels."""
+    from audiotools_b200.data import transforms as tfm
+
+    x = cases.make_input("lufs16k")[:4]
+    B, C, T = x.shape
+    g = torch.Generator().manual_seed(21)
+    pool = [at.AudioSignal(0.05 * torch.randn(1, 1, T + 5000, generator=g), 16000),
+            at.AudioSignal(0.02 * torch.randn(1, C, T - 3000, generator=g), 16000)]
+    sig = at.AudioSignal(x.clone(), 16000)
+    t = tfm.BackgroundNoise(sources=pool, eq_amount=("const", 0.0))
+    kw = t.batch_instantiate([1, 2, 3, 4], sig)
+    out = t(sig.clone().to(DEV), **at.util.prepare_batch(kw, DEV)).audio_data.cpu()
+    snr = kw["BackgroundNoise"]["snr"].float()
+    assert torch.allclose(sp.loudness(out - x, 16000), sp.loudness(x, 16000) - snr, atol=0.05)
+    t = tfm.CrossTalk(sources=pool)
+    kw = t.batch_instantiate([5, 6, 7, 8], sig)
+    out = t(sig.clone().to(DEV), **at.util.prepare_batch(kw, DEV)).audio_data.cpu()
+    assert torch.allclose(sp.loudness(out, 16000), sp.loudness(x, 16000), atol=0.05)
+    t = tfm.NoiseFloor(db=("const", -45.0))
+    kw = t.batch_instantiate([9, 10, 11, 12], sig)
+    out = t(sig.clone().to(DEV), **at.util.prepare_batch(kw, DEV)).audio_data.cpu()
+    assert torch.allclose(sp.loudness(out - x, 16000), torch.full((B,), -45.0), atol=0.05)

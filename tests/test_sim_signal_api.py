@@ -113,3 +113,38 @@ def test_preemphasis_and_pitch_transform():
     out = t(sig.clone(), **kw).audio_data
     for i, s in enumerate(shifts):  # one set of launches for the batch == each item on its own
         assert torch.equal(out[i:i + 1], AudioSignal(xm[i:i + 1].clone(), 16000).pitch_shift(s).audio_data)
+
+
+def test_noise_transforms_with_in_memory_pools():
+    """NoiseFloor / BackgroundNoise / CrossTalk (ref:audiotools/data/transforms.py:669-854) with in-memory pools: the
+    same arithmetic as the reference's transforms (mix / normalize), restated with the oracle."""
+    x = cases.make_input("lufs16k")[:4]  # [4, C, T] @ 16 kHz
+    B, C, T = x.shape
+    g = torch.Generator().manual_seed(21)
+    pool = [AudioSignal(0.05 * torch.randn(1, 1, T + 5000, generator=g), 16000),
+            AudioSignal(0.02 * torch.randn(1, C, T - 3000, generator=g), 16000)]
+    sig = AudioSignal(x.clone(), 16000)
+
+    t = tfm.BackgroundNoise(sources=pool, eq_amount=("const", 0.0))  # eq of 0 dB: the band filters sum to identity
+    kw = t.batch_instantiate([1, 2, 3, 4], sig)
+    bg = kw["BackgroundNoise"]["bg_signal"].audio_data
+    assert bg.shape == x.shape
+    out = t(sig.clone(), **kw).audio_data
+    snr = kw["BackgroundNoise"]["snr"].float()
+    noise = sp.normalize(sp.equalizer(bg, 16000, kw["BackgroundNoise"]["eq"].float()), 16000, sp.loudness(x, 16000) - snr)[0]
+    assert rel_err(out, x + noise) < TOL
+    assert torch.allclose(sp.loudness(out - x, 16000), sp.loudness(x, 16000) - snr, atol=0.05)
+
+    t = tfm.CrossTalk(sources=pool)
+    kw = t.batch_instantiate([5, 6, 7, 8], sig)
+    out = t(sig.clone(), **kw).audio_data
+    assert torch.allclose(sp.loudness(out, 16000), sp.loudness(x, 16000), atol=0.05)  # original loudness restored
+    assert rel_err(out, x) > 1e-2                                                     # ... and something was mixed in
+
+    t = tfm.NoiseFloor(db=("const", -45.0))
+    kw = t.batch_instantiate([9, 10, 11, 12], sig)
+    out = t(sig.clone(), **kw).audio_data
+    assert torch.allclose(sp.loudness(out - x, 16000), torch.full((B,), -45.0), atol=0.05)
+    # seeded: the same seeds give the same noise
+    kw2 = t.batch_instantiate([9, 10, 11, 12], sig)
+    assert torch.equal(kw["NoiseFloor"]["nz_signal"].audio_data, kw2["NoiseFloor"]["nz_signal"].audio_data)

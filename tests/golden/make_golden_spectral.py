@@ -78,6 +78,26 @@ def main():
     out["win_ola"] = sw.overlap_and_add(0.05).audio_data.numpy()
     out["win_iter_count"] = np.int64(sum(1 for _ in AudioSignal(x2.clone(), 16000).windows(0.064, 0.016)))
 
+    # elementwise effects and their transforms (ref:audiotools/core/effects.py:435-523, transforms.py:531-666,1173-1197);
+    # clip_distortion only works on mono input in the reference (its quantile indexing)
+    xs = x * 0.3
+    xs2 = torch.cat([xs, 0.5 * xs.flip(-1)], 1)
+    out["fx_clip"] = AudioSignal(xs.clone(), 16000).clip_distortion(torch.tensor([0.05, 0.2, 0.0, 0.5])).audio_data.numpy()
+    out["fx_quant"] = AudioSignal(xs2.clone(), 16000).quantization(torch.tensor([8, 16, 256, 3])).audio_data.numpy()
+    out["fx_mulaw"] = AudioSignal(xs2.clone(), 16000).mulaw_quantization(torch.tensor([8, 16, 256, 3])).audio_data.numpy()
+    out["fx_maxaudio"] = AudioSignal(xs2.clone() * 5, 16000).ensure_max_of_audio(0.7).audio_data.numpy()
+    for cls, kw, inp in (("ClippingDistortion", {}, xs), ("Quantization", {}, xs2), ("MuLawQuantization", {}, xs2),
+                         ("RescaleAudio", {"val": 0.5}, xs2)):
+        t = getattr(tfm, cls)(**kw)
+        s_in = AudioSignal(inp.clone() * 3, 16000)
+        k = t.batch_instantiate([3, 4, 5, 6], s_in)
+        for kk, v in _flatten(k).items():
+            out[f"fxkw/{cls}/" + "/".join(kk)] = v.numpy()
+        out[f"fxout/{cls}"] = t(s_in.clone(), **k).audio_data.numpy()
+    sg = AudioSignal(xs2.clone(), 16000)
+    sg.metadata["loudness"] = -30.0
+    out["fx_globalvolnorm_db"] = tfm.GlobalVolumeNorm(db=("uniform", -20, -10)).instantiate(7, sg)["GlobalVolumeNorm"]["db"].numpy()
+
     path = os.path.join(HERE, "reference_golden_spectral.npz")
     np.savez_compressed(path, **out)
     print(f"wrote {path}: {len(out)} arrays, {os.path.getsize(path)/1e6:.1f} MB on disk")

@@ -245,3 +245,33 @@ def test_chunking_helpers_match_reference(golden_spec):
     # identity round trip: windows of an untouched signal add back to the signal
     r = AudioSignal(x2.clone(), 16000).collect_windows(0.1, 0.05).overlap_and_add(0.05)
     assert torch.allclose(r.audio_data, x2, atol=1e-6)
+
+
+def test_elementwise_effects_match_reference(golden_spec):
+    """clip_distortion / quantization / mulaw_quantization / ensure_max_of_audio and their transforms are container
+    arithmetic (ref:audiotools/core/effects.py:181-198,435-523; transforms.py:531-666,1006-1050,1173-1197): same drawn
+    parameters and outputs as the real reference (tests/golden/make_golden_spectral.py)."""
+    from tests.golden import cases
+
+    g = golden_spec
+    xs = cases.make_input("cfg1") * 0.3
+    xs2 = torch.cat([xs, 0.5 * xs.flip(-1)], 1)
+    T = lambda k: torch.from_numpy(g[k])
+    assert torch.allclose(AudioSignal(xs.clone(), 16000).clip_distortion(torch.tensor([0.05, 0.2, 0.0, 0.5])).audio_data,
+                          T("fx_clip"), atol=1e-7)
+    q = torch.tensor([8, 16, 256, 3])
+    assert torch.allclose(AudioSignal(xs2.clone(), 16000).quantization(q).audio_data, T("fx_quant"), atol=1e-6)
+    assert torch.allclose(AudioSignal(xs2.clone(), 16000).mulaw_quantization(q).audio_data, T("fx_mulaw"), atol=1e-6)
+    assert torch.allclose(AudioSignal(xs2.clone() * 5, 16000).ensure_max_of_audio(0.7).audio_data, T("fx_maxaudio"), atol=1e-7)
+    for cls, kw, inp in (("ClippingDistortion", {}, xs), ("Quantization", {}, xs2), ("MuLawQuantization", {}, xs2),
+                         ("RescaleAudio", {"val": 0.5}, xs2)):
+        t = getattr(tfm, cls)(**kw)
+        s_in = AudioSignal(inp.clone() * 3, 16000)
+        k = t.batch_instantiate([3, 4, 5, 6], s_in)
+        for kk, v in util.flatten(k).items():
+            assert np.allclose(v.numpy(), g[f"fxkw/{cls}/" + "/".join(kk)]), (cls, kk)
+        assert torch.allclose(t(s_in.clone(), **k).audio_data, T(f"fxout/{cls}"), atol=1e-6), cls
+    sg = AudioSignal(xs2.clone(), 16000)
+    sg.metadata["loudness"] = -30.0
+    db = tfm.GlobalVolumeNorm(db=("uniform", -20, -10)).instantiate(7, sg)["GlobalVolumeNorm"]["db"]
+    assert np.allclose(db.numpy(), g["fx_globalvolnorm_db"])

@@ -148,3 +148,25 @@ def test_noise_transforms_with_in_memory_pools():
     # seeded: the same seeds give the same noise
     kw2 = t.batch_instantiate([9, 10, 11, 12], sig)
     assert torch.equal(kw["NoiseFloor"]["nz_signal"].audio_data, kw2["NoiseFloor"]["nz_signal"].audio_data)
+
+
+def test_features_filters_and_meter_match_reference(golden):
+    """The remaining AudioSignal methods of the hot path through the simulated kernels, against the real reference."""
+    assert rel_err(sig_of("cfg1").mfcc(), G(golden, "cfg1_mfcc")) < TOL
+    sig = sig_of("cfg1", slice(0, 2))
+    sig.stft()
+    assert rel_err(sig.log_magnitude(), G(golden, "cfg1_logmag")) < TOL
+    lu = sig_of("lufs16k").loudness()
+    assert torch.allclose(lu, G(golden, "lufs16k"), atol=1e-3)
+    x = cases.make_input("lufs16k")
+    meter = audiotools_b200.Meter(16000)
+    raw = meter.integrated_loudness(x[:3].permute(0, 2, 1))  # [nb, nt, nch], un-clamped
+    assert torch.allclose(raw.clamp(min=-70.0), lu[:3], atol=1e-3)
+    cut = G(golden, "fir_cut")
+    assert rel_err(sig_of("fir").low_pass(cut).audio_data, G(golden, "lp_peritem")) < TOL
+    assert rel_err(sig_of("fir").high_pass(cut / 8).audio_data, G(golden, "hp_peritem")) < TOL
+    assert rel_err(sig_of("fir").equalizer(golden["eq_db"]).audio_data, G(golden, "eq_out")) < TOL
+    assert rel_err(sig_of("fir", slice(0, 1)).mel_filterbank(4)[:, :1], G(golden, "fbank4")) < TOL
+    assert rel_err(sig_of("fir").convolve(AudioSignal(cases.make_ir().clone(), 44100)).audio_data, G(golden, "conv_out")) < TOL
+    rs = AudioSignal(cases.make_input("rs")[..., :22050].clone(), 44100).resample(16000)
+    assert rs.sample_rate == 16000 and rel_err(rs.audio_data, G(golden, "rs_44k_16k")) < TOL

@@ -251,8 +251,13 @@ class Engine:
             self._packed_cache[key] = 4 * total
         return self._packed_cache[key]
 
-    def num_frames(self, T: int, n_fft: int, hop: int, pad: int = 0, right_pad: int = 0, drop_edge: int = 0) -> int:
-        return int(self.lib.b2a_stft_num_frames(T, n_fft, hop, pad, right_pad, drop_edge))
+    @staticmethod
+    def num_frames(T: int, n_fft: int, hop: int, pad: int = 0, right_pad: int = 0, drop_edge: int = 0) -> int:
+        """``b2a_stft_num_frames`` evaluated on the host (same integer formula; tests/test_abi.py checks they agree):
+        a foreign-function call per ``stft()`` is measurable at batch=4 x 1 s, where the call is launch-latency bound."""
+        if T < 1 or n_fft < 2 or hop < 1 or pad < 0 or right_pad < 0 or drop_edge < 0:
+            return -1
+        return 1 + (T + 2 * pad + right_pad) // hop - 2 * drop_edge
 
     def spectral(self, x: torch.Tensor, n_fft: int, hop: int, window: torch.Tensor, pad: int = 0,
                  right_pad: int = 0, pad_mode: str = "reflect", drop_edge: int = 0,

@@ -4,6 +4,8 @@ import ctypes
 import os
 import re
 
+import numpy as np
+
 import pytest
 
 import __graft_entry__ as graft
@@ -82,3 +84,14 @@ def test_engine_rejects_cpu_tensors(lib):
         sig.stft()
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         sig.loudness()
+
+
+def test_host_num_frames_equals_the_abi_function():
+    from audiotools_b200.engine import Engine
+
+    lib = _lib.get_lib()
+    rng = np.random.RandomState(0)
+    for _ in range(300):
+        T, n_fft, hop = int(rng.randint(-2, 100000)), int(2 ** rng.randint(0, 13)), int(rng.randint(-1, 5000))
+        pad, rp, de = int(rng.randint(-1, 2048)), int(rng.randint(-1, 4096)), int(rng.choice([0, 0, 2]))
+        assert Engine.num_frames(T, n_fft, hop, pad, rp, de) == lib.b2a_stft_num_frames(T, n_fft, hop, pad, rp, de)

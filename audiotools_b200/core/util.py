@@ -6,6 +6,7 @@ reference are out of scope."""
 import math
 import numbers
 import random
+import contextlib
 import typing
 
 import numpy as np
@@ -149,3 +150,33 @@ def collate(list_of_dicts: list, n_splits: int = None):
                 batch[k] = torch.utils.data._utils.collate.default_collate(v)
         batches.append(unflatten(batch))
     return batches if return_list else batches[0]
+
+
+def hz_to_bin(hz: torch.Tensor, n_fft: int, sample_rate: int) -> torch.Tensor:
+    """Closest bin of a ``2 + n_fft // 2``-point grid over ``[0, sample_rate / 2]`` for every frequency
+    (ref:audiotools/core/util.py:100-126; frequencies above Nyquist are clamped, as there)."""
+    shape = hz.shape
+    flat = hz.flatten().clamp(max=sample_rate / 2)
+    freqs = torch.linspace(0, sample_rate / 2, 2 + n_fft // 2)
+    return (flat[None, :] - freqs[:, None]).abs().argmin(dim=0).reshape(*shape)
+
+
+def choose_from_list_of_lists(state: np.random.RandomState, list_of_lists: list, p: float = None):
+    """Pick a list (with probabilities ``p``), then one of its items uniformly: ``(item, list index, item index)``
+    (ref:audiotools/core/util.py:302-324)."""
+    source_idx = state.choice(list(range(len(list_of_lists))), p=p)
+    item_idx = state.randint(len(list_of_lists[source_idx]))
+    return list_of_lists[source_idx][item_idx], source_idx, item_idx
+
+
+@contextlib.contextmanager
+def chdir(newdir):
+    """Temporarily change the working directory (ref:audiotools/core/util.py:327-343)."""
+    import os
+
+    curdir = os.getcwd()
+    try:
+        os.chdir(newdir)
+        yield
+    finally:
+        os.chdir(curdir)

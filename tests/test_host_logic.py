@@ -275,3 +275,18 @@ def test_elementwise_effects_match_reference(golden_spec):
     sg.metadata["loudness"] = -30.0
     db = tfm.GlobalVolumeNorm(db=("uniform", -20, -10)).instantiate(7, sg)["GlobalVolumeNorm"]["db"]
     assert np.allclose(db.numpy(), g["fx_globalvolnorm_db"])
+
+
+def test_small_util_helpers():
+    """hz_to_bin / choose_from_list_of_lists / chdir (ref:audiotools/core/util.py:100-126,302-343); the expected bins
+    below are the real reference's."""
+    import os
+
+    hz = torch.tensor([[0.0, 100.0, 440.0], [7999.0, 12000.0, 30000.0]])
+    assert util.hz_to_bin(hz, 2048, 44100).tolist() == [[0, 5, 20], [372, 558, 1025]]
+    item, si, ii = util.choose_from_list_of_lists(np.random.RandomState(3), [[1, 2, 3], [4, 5], [6]], p=[0.5, 0.3, 0.2])
+    assert item == [[1, 2, 3], [4, 5], [6]][si][ii]
+    here = os.getcwd()
+    with util.chdir("/tmp"):
+        assert os.getcwd() == "/tmp"
+    assert os.getcwd() == here

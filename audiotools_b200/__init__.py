@@ -13,4 +13,5 @@ from .core import STFTParams
 from .core import Meter
 from .core import util
 from . import data
+from . import ml
 from .data import transforms

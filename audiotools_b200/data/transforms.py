@@ -638,3 +638,29 @@ class Silence(BaseTransform):
                              stft_params=signal.stft_params)
         signal._loudness = _loudness  # so that the target still can be normalised relative to it
         return signal
+
+
+class SpectralDenoising(Equalizer):
+    """Spectral gating against a host-drawn (seeded) white-noise excerpt, normalised and equalised on the device
+    (ref :1539-1592; ``ml.layers.SpectralGate``)."""
+
+    def __init__(self, eq_amount: tuple = ("const", 1.0), denoise_amount: tuple = ("uniform", 0.8, 1.0),
+                 nz_volume: float = -40, n_bands: int = 6, n_freq: int = 3, n_time: int = 5, name: str = None,
+                 prob: float = 1):
+        super().__init__(eq_amount=eq_amount, n_bands=n_bands, name=name, prob=prob)
+        from ..ml.layers import SpectralGate
+
+        self.nz_volume = nz_volume
+        self.denoise_amount = denoise_amount
+        self.spectral_gate = SpectralGate(n_freq, n_time)
+
+    def _transform(self, signal, nz, eq, denoise_amount):
+        nz = nz.normalize(self.nz_volume).equalizer(eq)
+        self.spectral_gate = self.spectral_gate.to(signal.device)
+        return self.spectral_gate(signal, nz, denoise_amount)
+
+    def _instantiate(self, state: RandomState):
+        kwargs = super()._instantiate(state)
+        kwargs["denoise_amount"] = util.sample_from_dist(self.denoise_amount, state)
+        kwargs["nz"] = AudioSignal(torch.from_numpy(state.randn(22050)).float(), 44100)
+        return kwargs

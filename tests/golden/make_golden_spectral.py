@@ -98,6 +98,21 @@ def main():
     sg.metadata["loudness"] = -30.0
     out["fx_globalvolnorm_db"] = tfm.GlobalVolumeNorm(db=("uniform", -20, -10)).instantiate(7, sg)["GlobalVolumeNorm"]["db"].numpy()
 
+    # SpectralGate / SpectralDenoising (ref:audiotools/ml/layers/spectral_gate.py, transforms.py:1539-1592)
+    from audiotools.ml.layers import SpectralGate
+
+    xg = make_input("cfg2")[:2, :, :30000]
+    nz = 0.01 * torch.randn(2, 1, 22050, generator=torch.Generator().manual_seed(0))
+    out["gate_nz"] = nz.numpy()
+    out["gate_out"] = SpectralGate()(AudioSignal(xg.clone(), 44100), AudioSignal(nz.clone(), 44100),
+                                     torch.tensor([0.9, 0.8])).audio_data.numpy()
+    sd = tfm.SpectralDenoising()
+    sg_in = AudioSignal(xg.clone(), 44100)
+    k = sd.batch_instantiate([3, 4], sg_in)
+    for kk, v in _flatten(k).items():
+        out["sdkw/" + "/".join(kk)] = (v.audio_data if hasattr(v, "audio_data") else v).numpy()
+    out["sd_out"] = sd(sg_in.clone(), **k).audio_data.numpy()
+
     path = os.path.join(HERE, "reference_golden_spectral.npz")
     np.savez_compressed(path, **out)
     print(f"wrote {path}: {len(out)} arrays, {os.path.getsize(path)/1e6:.1f} MB on disk")

@@ -593,3 +593,23 @@ def test_noise_transforms_with_in_memory_pools(at, sp):
     kw = t.batch_instantiate([9, 10, 11, 12], sig)
     out = t(sig.clone().to(DEV), **at.util.prepare_batch(kw, DEV)).audio_data.cpu()
     assert torch.allclose(sp.loudness(out - x, 16000), torch.full((B,), -45.0), atol=0.05)
+
+
+def test_spectral_gate_and_denoising(at, golden_spec):
+    """GPU twin of tests/test_sim_signal_api.py::test_spectral_gate_and_denoising."""
+    from audiotools_b200.data import transforms as tfm
+    from audiotools_b200.ml.layers import SpectralGate
+
+    g = golden_spec
+    xg = cases.make_input("cfg2")[:2, :, :30000]
+    out = SpectralGate().to(DEV)(at.AudioSignal(xg.clone(), 44100).to(DEV),
+                                 at.AudioSignal(torch.from_numpy(g["gate_nz"]).clone(), 44100).to(DEV),
+                                 torch.tensor([0.9, 0.8])).audio_data.cpu()
+    assert rel_err(out, torch.from_numpy(g["gate_out"])) < 1e-4
+    sd = tfm.SpectralDenoising()
+    sig = at.AudioSignal(xg.clone(), 44100)
+    kw = sd.batch_instantiate([3, 4], sig)
+    res = sd(sig.clone().to(DEV), **at.util.prepare_batch(kw, DEV)).audio_data.cpu()
+    ref = torch.from_numpy(g["sd_out"])
+    assert rel_err(res, ref) < 5e-3
+    assert ((res - ref).abs() > 1e-4 * ref.abs().max()).float().mean() < 0.1

@@ -96,7 +96,11 @@ class EffectMixin:
         return self
 
     def time_stretch(self, factor: float, quick: bool = True):
-        raise NotImplementedError("time_stretch is outside the accelerated hot path (SURVEY.md §8a a14)")
+        """Change the speed by ``factor`` (duration / factor) keeping the pitch (ref :279-309, SoX ``tempo`` there):
+        the WSOLA search + overlap-add stages of :meth:`pitch_shift`.  Like SoX's output it is pinned by properties
+        only (duration, pitch, batch == single)."""
+        self.audio_data = _engine().time_stretch(self._materialized(), self.sample_rate, float(factor))
+        return self
 
     def apply_codec(self, *args, **kwargs):
         raise NotImplementedError("apply_codec calls external lossy codecs: out of scope (SURVEY.md §2 row 3)")

@@ -356,6 +356,20 @@ rate_kernel(const float* __restrict__ sbuf, const float* __restrict__ x, float* 
   y[(size_t)row * (size_t)T + n] = acc * fast_rcp(wsum);
 }
 
+// time stretch = the first two stages only: out[row][i] = s[i] (the stretched row without its halo)
+__global__ void __launch_bounds__(256)
+stretch_copy_kernel(const float* __restrict__ sbuf, const float* __restrict__ x, float* __restrict__ out, int T,
+                    long long out_len, const B2A_GRID_CONSTANT GeoTable tab) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= out_len) return;
+  const int row = blockIdx.y;
+  const Geo& g = tab.g[0];
+  float v;
+  if (g.identity) v = i < T ? __ldg(x + (size_t)row * (size_t)T + i) : 0.f;
+  else v = __ldg(sbuf + (size_t)row * (size_t)tab.SLmax + g.H + i);
+  out[(size_t)row * (size_t)out_len + i] = v;
+}
+
 static int geometry(int64_t rows, int64_t T, int sr, float semitones, Geo* g) {
   (void)rows;
   const double r = pow(2.0, (double)semitones / 12.0);
@@ -465,4 +479,53 @@ extern "C" size_t b2a_pitch_shift_workspace_bytes(int64_t rows, int64_t T, int s
 extern "C" int b2a_pitch_shift_f32(const float* x, int64_t rows, int64_t T, int sr, float semitones, float* out,
                                    void* ws, size_t ws_bytes, void* stream) {
   return b2a_pitch_shift_multi_f32(x, rows, T, sr, &semitones, 1, nullptr, out, ws, ws_bytes, stream);
+}
+
+/* EffectMixin.time_stretch (ref:audiotools/core/effects.py:279-309; SoX `tempo factor` there): the WSOLA stages of the
+ * pitch shifter on their own -- speed the signal up by `factor` (duration / factor), pitch unchanged. */
+static float stretch_semitones(double factor) { return (float)(12.0 * log2(1.0 / factor)); }
+
+extern "C" int64_t b2a_time_stretch_out_len(int64_t T, double factor) {
+  if (T < 1 || !(factor >= 0.25 && factor <= 4.0)) return -1;
+  return (int64_t)floor((double)T / factor + 0.5);
+}
+
+extern "C" size_t b2a_time_stretch_workspace_bytes(int64_t rows, int64_t T, int sr, double factor) {
+  if (!(factor >= 0.25 && factor <= 4.0)) return 0;
+  const float st = stretch_semitones(factor);
+  return b2a_pitch_shift_multi_workspace_bytes(rows, T, sr, &st, 1);
+}
+
+extern "C" int b2a_time_stretch_f32(const float* x, int64_t rows, int64_t T, int sr, double factor, float* out,
+                                    void* ws, size_t ws_bytes, void* stream) {
+  B2A_REQUIRE(x && out && ws, B2A_E_INVALID, "time_stretch: null pointer");
+  B2A_REQUIRE(rows >= 1 && T >= 1 && sr >= 1, B2A_E_INVALID, "time_stretch: bad argument");
+  B2A_REQUIRE(factor >= 0.25 && factor <= 4.0, B2A_E_UNSUPPORTED, "time_stretch: factor %g outside [0.25, 4]", factor);
+  B2A_REQUIRE(rows * T < ((int64_t)1 << 40) && T < ((int64_t)1 << 28) && rows <= 65535, B2A_E_UNSUPPORTED,
+              "time_stretch: too large");
+  B2A_REQUIRE(((uintptr_t)ws & 15) == 0, B2A_E_INVALID, "time_stretch: workspace must be 16-byte aligned");
+  const float st = (factor == 1.0) ? 0.0f : stretch_semitones(factor);
+  const int64_t out_len = b2a_time_stretch_out_len(T, factor);
+  GeoTable tab;
+  build_table(rows, T, sr, &st, 1, &tab);
+  const size_t pb = pos_bytes(rows, tab);
+  B2A_REQUIRE(ws_bytes >= pb + (size_t)rows * (size_t)tab.SLmax * 4, B2A_E_INVALID, "time_stretch: workspace too small");
+  int* pos = (int*)ws;
+  int* nom = pos + (size_t)rows * tab.Jmax;
+  float* sbuf = (float*)((char*)ws + pb);
+  const Geo& g = tab.g[0];
+  B2A_REQUIRE(g.identity || g.H + out_len <= g.SL, B2A_E_INVALID, "time_stretch: internal length mismatch");
+  if (!g.identity) {
+    const size_t smem = (size_t)(32 * search_row_stride(g.rcap) + 8 * ST + g.Lc) * 4;
+    B2A_CUDA_OK(cudaFuncSetAttribute(wsola_search_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    B2A_LAUNCH(nominal_kernel, dim3((unsigned)((tab.Jmax + 255) / 256), 1u), dim3(256), 0, stream, nom, tab);
+    B2A_LAUNCH(wsola_search_kernel, dim3((unsigned)rows), dim3(ST), smem, stream, x, (int)T, tab, (const int*)nullptr,
+               (const int*)nom, pos);
+    B2A_LAUNCH(wsola_ola_kernel, dim3((unsigned)((tab.SLmax / 4 + 255) / 256), (unsigned)rows), dim3(256), 0, stream, x,
+               (const int*)pos, sbuf, (int)T, tab, (const int*)nullptr);
+  }
+  B2A_LAUNCH(stretch_copy_kernel, dim3((unsigned)((out_len + 255) / 256), (unsigned)rows), dim3(256), 0, stream,
+             (const float*)sbuf, x, out, (int)T, (long long)out_len, tab);
+  B2A_CUDA_OK(cudaGetLastError());
+  return B2A_OK;
 }

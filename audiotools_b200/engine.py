@@ -594,6 +594,26 @@ class Engine:
         return out
 
 
+    def time_stretch(self, x: torch.Tensor, sample_rate: int, factor: float) -> torch.Tensor:
+        """Speed x [B, C, T] up by ``factor`` without changing its pitch -> [B, C, round(T / factor)]
+        (ref:audiotools/core/effects.py:279-309; SoX ``tempo`` there): the WSOLA stages of the pitch shifter."""
+        x = self._prep(x, "x")
+        T = x.shape[-1]
+        rows = x.numel() // T
+        factor = float(factor)
+        out_len = int(self.lib.b2a_time_stretch_out_len(T, factor))
+        ws_bytes = self.lib.b2a_time_stretch_workspace_bytes(rows, T, int(sample_rate), factor)
+        if out_len < 1 or ws_bytes == 0:
+            raise NotImplementedError(f"time_stretch: factor {factor} (supported: 0.25 ... 4)")
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=x.device)
+        out = torch.empty(*x.shape[:-1], out_len, dtype=torch.float32, device=x.device)
+        rc = self.lib.b2a_time_stretch_f32(_dptr(x), rows, T, int(sample_rate), factor, _dptr(out), _dptr(ws), ws_bytes,
+                                           self._stream(x))
+        self.lib.check(rc)
+        self.launches += 4 if factor != 1.0 else 1
+        return out
+
+
 _ENGINE = None
 
 

@@ -197,6 +197,14 @@ size_t b2a_pitch_shift_multi_workspace_bytes(int64_t rows, int64_t T, int sr, co
 int b2a_pitch_shift_multi_f32(const float* x, int64_t rows, int64_t T, int sr, const float* semitones_h, int n_groups,
                               const int32_t* row_group, float* out, void* ws, size_t ws_bytes, void* stream);
 
+/* EffectMixin.time_stretch (audiotools/core/effects.py:279-309; SoX `tempo factor` + `rate` there): the WSOLA stages of
+ * the pitch shifter on their own: out [rows, out_len] with out_len = b2a_time_stretch_out_len(T, factor) = round(T / factor),
+ * pitch unchanged; factor in [0.25, 4], factor == 1 copies. */
+int64_t b2a_time_stretch_out_len(int64_t T, double factor);
+size_t b2a_time_stretch_workspace_bytes(int64_t rows, int64_t T, int sr, double factor);
+int b2a_time_stretch_f32(const float* x, int64_t rows, int64_t T, int sr, double factor, float* out, void* ws,
+                         size_t ws_bytes, void* stream);
+
 /* ---- one-sided statistics exchange between the GPUs of a node (NVLink peer memory) --------------------
  * The path shards by batch item with no data-path collective; the one exchange is the per-item loudness vector for
  * whole-batch statistics (the reference has no multi-GPU code of its own: SURVEY.md 8e).  Every rank owns a small

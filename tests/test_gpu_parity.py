@@ -613,3 +613,21 @@ def test_spectral_gate_and_denoising(at, golden_spec):
     ref = torch.from_numpy(g["sd_out"])
     assert rel_err(res, ref) < 5e-3
     assert ((res - ref).abs() > 1e-4 * ref.abs().max()).float().mean() < 0.1
+
+
+def test_time_stretch_properties(at):
+    """GPU twin of tests/test_sim_signal_api.py::test_time_stretch_properties (ref:tests/core/test_effects.py:170-181)."""
+    sr, T = 44100, 88200
+    t = torch.arange(T) / sr
+    x = torch.stack([0.5 * torch.sin(2 * np.pi * 440 * t), 0.3 * torch.sin(2 * np.pi * 1000 * t)])[:, None, :]
+    for factor in (0.8, 1.25):
+        y = at.AudioSignal(x.clone(), sr).to(DEV).time_stretch(factor).audio_data.cpu()
+        n = int(round(T / factor))
+        assert y.shape == (2, 1, n)
+        for i, f0 in enumerate((440.0, 1000.0)):
+            spec = torch.fft.rfft(y[i, 0] * torch.hann_window(n)).abs()
+            assert abs(spec.argmax().item() * sr / n - f0) < 2.0
+        assert abs(y[0, 0, 4000:-4000].std().item() * 2 ** 0.5 - 0.5) < 0.03
+        single = at.AudioSignal(x[:1].clone(), sr).to(DEV).time_stretch(factor).audio_data.cpu()
+        assert torch.equal(single, y[:1])
+    assert torch.equal(at.AudioSignal(x.clone(), sr).to(DEV).time_stretch(1.0).audio_data.cpu(), x)

@@ -194,3 +194,27 @@ def test_spectral_gate_and_denoising(golden_spec):
     ref = G(g, "sd_out")
     assert rel_err(res, ref) < 5e-3
     assert ((res - ref).abs() > 1e-4 * ref.abs().max()).float().mean() < 0.1
+
+
+def test_time_stretch_properties():
+    """EffectMixin.time_stretch (ref:audiotools/core/effects.py:279-309; SoX there, unpinned): duration / factor, pitch and
+    level unchanged, batch == single (ref:tests/core/test_effects.py:170-181), factor 1 copies."""
+    sr, T = 16000, 12000
+    t = torch.arange(T) / sr
+    x = torch.stack([0.5 * torch.sin(2 * np.pi * 440 * t), 0.3 * torch.sin(2 * np.pi * 1000 * t)])[:, None, :]
+    for factor in (0.8, 1.25):
+        y = AudioSignal(x.clone(), sr).time_stretch(factor).audio_data
+        n = int(round(T / factor))
+        assert y.shape == (2, 1, n)
+        for i, (f0, a0) in enumerate(((440.0, 0.5), (1000.0, 0.3))):
+            seg = y[i, 0, 1500:n - 1500].double().numpy()
+            k = np.arange(1500, n - 1500) / sr
+            A = np.stack([np.sin(2 * np.pi * f0 * k), np.cos(2 * np.pi * f0 * k)], 1)
+            coef = np.linalg.lstsq(A, seg, rcond=None)[0]
+            spec = torch.fft.rfft(y[i, 0] * torch.hann_window(n)).abs()
+            assert abs(spec.argmax().item() * sr / n - f0) < 4.0  # the pitch did not move
+            assert abs(np.hypot(*coef) - a0) < 0.05 * a0 or (seg.std() * np.sqrt(2) - a0) < 0.05 * a0
+        assert torch.equal(AudioSignal(x[:1].clone(), sr).time_stretch(factor).audio_data, y[:1])
+    assert torch.equal(AudioSignal(x.clone(), sr).time_stretch(1.0).audio_data, x)
+    with pytest.raises(NotImplementedError):
+        AudioSignal(x.clone(), sr).time_stretch(8.0)

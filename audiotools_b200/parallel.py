@@ -88,7 +88,9 @@ class PeerLoudnessExchange:
         self.world = dist.get_world_size(group)
         self.rank = dist.get_rank(group)
         self.n_max = int(n_max)
-        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        if device is None:
+            device = torch.device("cuda", torch.cuda.current_device()) if torch.cuda.is_available() else "cpu"
+        self.device = torch.device(device)  # "cpu" only with the CPU-simulated library (set-up protocol tests)
         self._ct = ctypes
         # Set-up is all-or-nothing ACROSS ranks: every rank takes part in both handle/status exchanges whatever
         # happened locally, so a failure anywhere (no cudaIpc in this container, a rank on another node, ...) makes
@@ -96,7 +98,9 @@ class PeerLoudnessExchange:
         self.local, self._opened, err = None, [], None
         self.peers = (ctypes.c_void_p * self.world)()
         handle = None
-        with torch.cuda.device(self.device):
+        import contextlib
+
+        with (torch.cuda.device(self.device) if self.device.type == "cuda" else contextlib.nullcontext()):
             try:
                 ptr = ctypes.c_void_p()
                 hbuf = (ctypes.c_ubyte * 64)()
@@ -186,7 +190,8 @@ class PeerLoudnessExchange:
     def close(self):
         if getattr(self, "local", None) is None:
             return
-        torch.cuda.synchronize(self.device)
+        if self.device.type == "cuda":
+            torch.cuda.synchronize(self.device)
         dist.barrier(group=self.group)  # nobody still stores into a buffer that is about to go away
         for p in self._opened:
             self.lib.b2a_peer_buffer_close(self._ct.c_void_p(p))

@@ -68,3 +68,44 @@ def test_two_rank_gloo_shard_and_gather():
     for p in procs:
         p.join(timeout=30)
     assert sorted(results) == [(0, "ok"), (1, "ok")], results
+
+
+def _peer_worker(rank, world, port, q, fail_rank):
+    """Set-up protocol of PeerLoudnessExchange with the CPU-simulated library: both ranks must come out the same way
+    (mapped, or raising together) -- a one-sided failure must never leave the other rank waiting in a collective."""
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from audiotools_b200 import _lib
+        from audiotools_b200.parallel import PeerLoudnessExchange
+        from tests.cusim import build_sim
+
+        lib = _lib.B2ALibrary(build_sim.build())
+        if rank == fail_rank:  # this rank cannot create its buffer (stands for: no cudaIpc, other node, ...)
+            lib.b2a_peer_buffer_create = lambda *a: 1
+        try:
+            ex = PeerLoudnessExchange(n_max=8, device="cpu", lib=lib)
+            ex.close()
+            q.put((rank, "mapped"))
+        except RuntimeError as e:
+            q.put((rank, "raised" if "peer exchange unavailable" in str(e) else repr(e)))
+    except Exception as e:  # pragma: no cover
+        q.put((rank, repr(e)))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.timeout(180)
+@pytest.mark.parametrize("fail_rank,expect", [(-1, "mapped"), (1, "raised"), (0, "raised")])
+def test_peer_exchange_setup_is_all_or_nothing(fail_rank, expect):
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_peer_worker, args=(r, 2, port, q, fail_rank)) for r in range(2)]
+    for p in procs:
+        p.start()
+    results = [q.get(timeout=150) for _ in procs]
+    for p in procs:
+        p.join(timeout=30)
+    assert sorted(results) == [(0, expect), (1, expect)], results

@@ -88,22 +88,24 @@ _HOST_MIRROR_MAX = 1 << 16
 
 def _to_device(v, device):
     """``v.to(device)``; a small CPU parameter tensor moved to an accelerator keeps a reference to its host
-    original (``_b2a_host``), so that host-side decisions on it (mask all-true?, which pitch shifts?, cutoff
-    range checks) need no device->host synchronisation later (see :func:`host_view`)."""
+    original (``_b2a_host``, together with the device tensor's version counter), so that host-side decisions on it
+    (mask all-true?, which pitch shifts?, cutoff range checks) need no device->host synchronisation later (see
+    :func:`host_view`)."""
     out = v.to(device)
     if torch.is_tensor(v) and out is not v and not v.is_cuda and out.is_cuda and v.numel() <= _HOST_MIRROR_MAX:
-        out._b2a_host = v
+        out._b2a_host = (v, out._version)
     return out
 
 
 def host_view(t):
     """The values of tensor ``t`` on the host: ``t`` itself on CPU, the mirror recorded by :func:`prepare_batch`
-    when there is one, else a (synchronising) copy."""
+    when there is one AND the device tensor has not been written in place since (its version counter is unchanged),
+    else a (synchronising) copy."""
     if not torch.is_tensor(t) or not t.is_cuda:
         return t
-    h = getattr(t, "_b2a_host", None)
-    if h is not None and h.shape == t.shape:
-        return h
+    mirror = getattr(t, "_b2a_host", None)
+    if mirror is not None and mirror[1] == t._version and mirror[0].shape == t.shape:
+        return mirror[0]
     return t.cpu()
 
 

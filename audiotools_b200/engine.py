@@ -405,8 +405,9 @@ class Engine:
         (ref:audiotools/core/dsp.py:153-215 -> julius.LowPassFilter(cutoff / sr, zeros), replicate padding)."""
         x = self._prep(x, "x")
         B, C, T = x.shape
-        cut = torch.as_tensor(cutoffs_hz)
-        cut = getattr(cut, "_b2a_host", cut).reshape(-1).cpu()  # host mirror from util.prepare_batch: no sync
+        from .core import util as _util
+
+        cut = _util.host_view(torch.as_tensor(cutoffs_hz)).reshape(-1).cpu()  # host mirror (util.prepare_batch): no sync
         if cut.numel() == 1:
             cut = cut.expand(B)
         assert cut.numel() == B

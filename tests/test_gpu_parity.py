@@ -631,3 +631,16 @@ def test_time_stretch_properties(at):
         single = at.AudioSignal(x[:1].clone(), sr).to(DEV).time_stretch(factor).audio_data.cpu()
         assert torch.equal(single, y[:1])
     assert torch.equal(at.AudioSignal(x.clone(), sr).to(DEV).time_stretch(1.0).audio_data.cpu(), x)
+
+
+def test_host_mirror_follows_in_place_writes(at):
+    """util.prepare_batch records host mirrors of small parameter tensors; a mirror is only trusted while the device
+    tensor's version counter is unchanged."""
+    kw = {"T": {"mask": torch.tensor([True, False, True]), "cutoff": torch.tensor([100.0, 200.0, 300.0])}}
+    dev = at.util.prepare_batch(kw, DEV)
+    m = dev["T"]["mask"]
+    assert at.util.host_view(m) is kw["T"]["mask"]          # the mirror itself: no synchronisation
+    m.logical_not_()                                          # in-place write on the device
+    assert torch.equal(at.util.host_view(m), torch.tensor([False, True, False]))
+    c = dev["T"]["cutoff"]
+    assert at.util.host_view(c * 2).tolist() == [200.0, 400.0, 600.0]  # derived tensors carry no mirror

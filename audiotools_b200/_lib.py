@@ -49,9 +49,9 @@ SIGNATURES = {
     "b2a_peer_buffer_close": (c_int, [c_void_p]),
     "b2a_peer_buffer_destroy": (c_int, [c_void_p]),
     "b2a_peer_put_f32": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
-    "b2a_peer_collect_f32": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
-    "b2a_peer_exchange_f32": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_int, c_int, c_void_p,
-                                      c_void_p]),
+    "b2a_peer_collect_f32": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
+    "b2a_peer_latest_f32": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
+    "b2a_peer_status": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p]),
     "b2a_spec_band_mask_f32": (c_int, [c_void_p, c_int64, c_int, c_int, c_void_p, c_void_p, c_void_p, c_int, c_int,
                                        c_float, c_float, c_void_p]),
     "b2a_spec_rotate_f32": (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_int, c_void_p]),

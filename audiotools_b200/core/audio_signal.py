@@ -62,6 +62,7 @@ class AudioSignal(EffectMixin, LoudnessMixin, ImpulseResponseMixin, DSPMixin):
         self.path_to_file = None
         self._audio_data = None
         self._pending_gain = None
+        self._measured_loudness = None  # set by normalize(): the LUFS its gain was derived from
         self._stft_data = None
         self._loudness = None
         self.sources = None

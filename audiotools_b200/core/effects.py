@@ -74,9 +74,12 @@ class EffectMixin:
                 padded = T + int((0.5 - self.signal_duration) * self.sample_rate)
             out = _engine().lufs(self._audio_data, self.sample_rate, padded_length=padded, target_db=db)
             gain = out["gain"]
+            measured = out["loud"]
         else:
-            gain = torch.exp((db - self.loudness()) * float(np.float32(self.GAIN_FACTOR)))
+            measured = self.loudness()
+            gain = torch.exp((db - measured) * float(np.float32(self.GAIN_FACTOR)))
         self._defer_gain(gain)
+        self._measured_loudness = measured  # extension: the LUFS the gain was derived from (logging / statistics)
         return self
 
     def volume_change(self, db):

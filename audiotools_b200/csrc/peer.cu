@@ -1,27 +1,36 @@
 // peer.cu -- one-sided exchange of per-item statistics between the GPUs of one node over NVLink peer memory.
 //
 // The hot path shards by batch item and has no data-path collective; the only exchange is the
-// per-item loudness vector ([B/W] floats per rank) for whole-batch statistics.  An NCCL all-gather for those
-// 256 bytes costs a rendezvous kernel that competes with the persistent spectral kernel for SM slots (measured:
-// +50 us per 630 us step at 2 GPUs).  Here every rank instead STORES its vector straight into a small buffer
-// of every peer (cudaIpc mapping, NVLink/NVSwitch P2P stores) and publishes a sequence number with a
-// system-scope release; a reader waits on the flags in its OWN memory.  No rendezvous, no NCCL kernel, one
-// tiny launch per step; slots are double buffered by sequence parity (a rank can be at most one step ahead of
-// the slowest reader, see parallel.py).
+// per-item loudness vector ([B/W] floats per rank) for whole-batch statistics -- logging data.  A logging-only
+// statistic must never be able to stall the data path, so nothing here makes one rank wait for another:
 //
-// Buffer layout (floats / int32, per rank):  data[2][world][n_max] | flag[2][world] | status[1]
+//   put      every rank STORES its vector straight into a small buffer of every peer (cudaIpc mapping, NVLink /
+//            NVSwitch P2P stores) and publishes the sequence number with a system-scope release.  Never waits.
+//   latest   reads, from the rank's OWN memory, the newest COMPLETE vector of every rank together with the sequence
+//            number it carries (seqlock: flag, data, flag again).  Never waits: a rank that is behind simply shows
+//            an older sequence number.
+//   collect  the lock-step form (bounded spin until every rank has published exactly `seq`): used by tests, by the
+//            bench's untimed validation against an NCCL all_gather, and by callers that want exact-step statistics;
+//            it is issued on a side stream, never between two kernels of the data path.
+//
+// Slots rotate over NSLOT = 4 sequence numbers.  A writer invalidates a slot (flag = -seq) before it rewrites the
+// data and publishes (flag = +seq) afterwards, so a reader can never accept a torn or half-overwritten vector
+// whatever the skew between ranks (round 1's two-slot rotation silently returned a future vector to a slow rank).
+//
+// Buffer layout (floats / int32, per rank):  data[NSLOT][world][n_max] | flag[NSLOT][world] | status[4]
 #include "b2a_common.h"
 
 namespace b2a {
 namespace peer {
 
 constexpr int MAX_WORLD = 16;
+constexpr int NSLOT = 4;
 
 struct Peers {
   float* buf[MAX_WORLD];
 };
 
-__host__ __device__ inline size_t flag_offset_floats(int world, int n_max) { return (size_t)2 * world * n_max; }
+__host__ __device__ inline size_t flag_offset_floats(int world, int n_max) { return (size_t)NSLOT * world * n_max; }
 
 __device__ __forceinline__ void st_release_sys(int* p, int v) {
 #ifdef B2A_SIM
@@ -40,81 +49,98 @@ __device__ __forceinline__ int ld_acquire_sys(const int* p) {
 #endif
 }
 
-// CTA p stores src[0..n) into slot (seq & 1, rank) of peer p's buffer, then publishes seq there.
+// CTA p stores src[0..n) into slot (seq % NSLOT, rank) of peer p's buffer: invalidate, data, publish.
 __global__ void __launch_bounds__(256)
 peer_put_kernel(const float* __restrict__ src, int n, const B2A_GRID_CONSTANT Peers peers, int world, int rank,
                 int n_max, int seq) {
   float* base = peers.buf[blockIdx.x];
-  float* dst = base + ((size_t)(seq & 1) * world + rank) * n_max;
+  const int slot = seq % NSLOT;
+  float* dst = base + ((size_t)slot * world + rank) * n_max;
+  int* flag = reinterpret_cast<int*>(base + flag_offset_floats(world, n_max)) + slot * world + rank;
+  if (threadIdx.x == 0) {
+    st_release_sys(flag, -seq);  // readers reject the slot while it is being rewritten
+    __threadfence_system();
+  }
+  __syncthreads();
   for (int i = threadIdx.x; i < n; i += blockDim.x) dst[i] = src[i];
   __threadfence_system();
   __syncthreads();
-  if (threadIdx.x == 0) {
-    int* flags = reinterpret_cast<int*>(base + flag_offset_floats(world, n_max));
-    st_release_sys(flags + (seq & 1) * world + rank, seq);
+  if (threadIdx.x == 0) st_release_sys(flag, seq);
+}
+
+// Seqlock read of rank r's slot `slot` in the local buffer into out[0..n): returns the sequence number the copy
+// carries, or 0 when the slot is empty / being rewritten.  Called by one warp.
+__device__ __forceinline__ int read_slot(const float* local, int world, int n, int n_max, int r, int slot, int want,
+                                         float* out) {
+  const int lane = threadIdx.x & 31;
+  const int* flag = reinterpret_cast<const int*>(local + flag_offset_floats(world, n_max)) + slot * world + r;
+  int f1 = 0;
+  if (lane == 0) f1 = ld_acquire_sys(flag);
+  f1 = __shfl_sync(0xffffffffu, f1, 0);
+  if (f1 <= 0 || (want > 0 && f1 != want)) return 0;
+  const float* data = local + ((size_t)slot * world + r) * n_max;
+  for (int k = lane; k < n; k += 32) out[k] = data[k];
+  __threadfence_system();
+  int f2 = 0;
+  if (lane == 0) f2 = ld_acquire_sys(flag);
+  f2 = __shfl_sync(0xffffffffu, f2, 0);
+  return f2 == f1 ? f1 : 0;
+}
+
+// out[r][0..n) = the newest complete vector rank r has published here, seqs[r] = its sequence number (0: nothing
+// yet -> NaNs).  One warp per rank (round-robin); never waits.
+__global__ void __launch_bounds__(256)
+peer_latest_kernel(const float* __restrict__ local, int world, int n, int n_max, float* __restrict__ out,
+                   int* __restrict__ seqs) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarp = blockDim.x >> 5;
+  for (int r = warp; r < world; r += nwarp) {
+    const int* flags = reinterpret_cast<const int*>(local + flag_offset_floats(world, n_max));
+    int got = 0;
+    for (int attempt = 0; attempt < NSLOT && got == 0; ++attempt) {
+      int best = 0, best_slot = 0;  // newest published slot right now
+      for (int s = 0; s < NSLOT; ++s) {
+        int f = 0;
+        if (lane == 0) f = ld_acquire_sys(flags + s * world + r);
+        f = __shfl_sync(0xffffffffu, f, 0);
+        if (f > best) { best = f; best_slot = s; }
+      }
+      if (best == 0) break;
+      got = read_slot(local, world, n, n_max, r, best_slot, 0, out + (size_t)r * n);
+    }
+    if (got == 0)
+      for (int k = lane; k < n; k += 32) out[(size_t)r * n + k] = __int_as_float(0x7fc00000);
+    if (lane == 0) seqs[r] = got;
   }
 }
 
-// wait until every rank has published `seq` into THIS rank's buffer, then gather [world][n] -> out
+// Lock-step gather: wait (bounded) until every rank has published exactly `seq` here, then out[world][n].  A rank
+// that ran more than NSLOT - 1 steps ahead has overwritten the slot: its row is NaN and seqs[r] holds what was seen.
 __global__ void __launch_bounds__(256)
 peer_collect_kernel(const float* __restrict__ local, int world, int n, int n_max, int seq, float* __restrict__ out,
-                    long long max_spins) {
-  const int* flags = reinterpret_cast<const int*>(local + flag_offset_floats(world, n_max)) + (seq & 1) * world;
-  int* status = const_cast<int*>(reinterpret_cast<const int*>(local + flag_offset_floats(world, n_max))) + 2 * world;
-  __shared__ int s_ok;
-  if (threadIdx.x == 0) s_ok = 1;
-  __syncthreads();
-  if ((int)threadIdx.x < world) {
-    long long spins = 0;
-    while (ld_acquire_sys(flags + threadIdx.x) - seq < 0) {  // sequence numbers only grow
-      if (++spins > max_spins) { s_ok = 0; break; }           // a peer died: never hang the GPU
+                    int* __restrict__ seqs, long long max_spins) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarp = blockDim.x >> 5;
+  const int slot = seq % NSLOT;
+  int* status = const_cast<int*>(reinterpret_cast<const int*>(local + flag_offset_floats(world, n_max))) + NSLOT * world;
+  for (int r = warp; r < world; r += nwarp) {
+    const int* flag = reinterpret_cast<const int*>(local + flag_offset_floats(world, n_max)) + slot * world + r;
+    int got = 0, seen = 0;
+    for (long long spins = 0; spins < max_spins; ++spins) {
+      if (lane == 0) seen = ld_acquire_sys(flag);
+      seen = __shfl_sync(0xffffffffu, seen, 0);
+      const int a = seen < 0 ? -seen : seen;
+      if (a > seq) break;  // overwritten by a later sequence number: gone
+      if (seen == seq) {
+        got = read_slot(local, world, n, n_max, r, slot, seq, out + (size_t)r * n);
+        if (got == seq) break;
+        got = 0;
+      }
     }
-  }
-  __syncthreads();
-  const float* data = local + (size_t)(seq & 1) * world * n_max;
-  for (int i = threadIdx.x; i < world * n; i += blockDim.x) {
-    const int r = i / n, k = i - r * n;
-    out[i] = s_ok ? data[(size_t)r * n_max + k] : __int_as_float(0x7fc00000);
-  }
-  if (threadIdx.x == 0 && !s_ok) *status = seq;
-}
-
-// One launch per step: CTAs 0..world-1 put sequence `seq_put`, CTA `world` collects sequence `seq_col` (the
-// previous step's, already published by every rank long ago) -- the steady state of a pipelined consumer.
-__global__ void __launch_bounds__(256)
-peer_exchange_kernel(const float* __restrict__ src, int n, const B2A_GRID_CONSTANT Peers peers, int world, int rank,
-                     int n_max, int seq_put, const float* __restrict__ local, int n_col, int seq_col,
-                     float* __restrict__ out, long long max_spins) {
-  if ((int)blockIdx.x < world) {
-    float* base = peers.buf[blockIdx.x];
-    float* dst = base + ((size_t)(seq_put & 1) * world + rank) * n_max;
-    for (int i = threadIdx.x; i < n; i += blockDim.x) dst[i] = src[i];
-    __threadfence_system();
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      int* flags = reinterpret_cast<int*>(base + flag_offset_floats(world, n_max));
-      st_release_sys(flags + (seq_put & 1) * world + rank, seq_put);
+    if (got != seq) {
+      for (int k = lane; k < n; k += 32) out[(size_t)r * n + k] = __int_as_float(0x7fc00000);
+      if (lane == 0) status[0] = seq;  // a peer died or lapped the slot: never hang the GPU
     }
-    return;
+    if (lane == 0 && seqs) seqs[r] = got == seq ? seq : -(seen < 0 ? -seen : seen);
   }
-  const int* flags = reinterpret_cast<const int*>(local + flag_offset_floats(world, n_max)) + (seq_col & 1) * world;
-  int* status = const_cast<int*>(reinterpret_cast<const int*>(local + flag_offset_floats(world, n_max))) + 2 * world;
-  __shared__ int s_ok;
-  if (threadIdx.x == 0) s_ok = 1;
-  __syncthreads();
-  if ((int)threadIdx.x < world) {
-    long long spins = 0;
-    while (ld_acquire_sys(flags + threadIdx.x) - seq_col < 0) {
-      if (++spins > max_spins) { s_ok = 0; break; }
-    }
-  }
-  __syncthreads();
-  const float* data = local + (size_t)(seq_col & 1) * world * n_max;
-  for (int i = threadIdx.x; i < world * n_col; i += blockDim.x) {
-    const int r = i / n_col, k = i - r * n_col;
-    out[i] = s_ok ? data[(size_t)r * n_max + k] : __int_as_float(0x7fc00000);
-  }
-  if (threadIdx.x == 0 && !s_ok) *status = seq_col;
 }
 
 }  // namespace peer
@@ -124,7 +150,7 @@ using namespace b2a::peer;
 
 extern "C" size_t b2a_peer_buffer_bytes(int world, int n_max) {
   if (world < 1 || world > MAX_WORLD || n_max < 1) return 0;
-  return (flag_offset_floats(world, n_max) + 2 * (size_t)world + 4) * 4;
+  return (flag_offset_floats(world, n_max) + (size_t)NSLOT * world + 4) * 4;
 }
 
 extern "C" int b2a_peer_buffer_create(int world, int n_max, void** dev_ptr, unsigned char* handle_out /*[64]*/) {
@@ -194,32 +220,35 @@ extern "C" int b2a_peer_put_f32(const float* src, int n, void* const* peer_bufs_
 }
 
 extern "C" int b2a_peer_collect_f32(const void* local_buf, int world, int n, int n_max, int seq, float* out,
-                                    void* stream) {
+                                    int32_t* seqs_out, void* stream) {
   B2A_REQUIRE(local_buf && out, B2A_E_INVALID, "peer_collect: null pointer");
   B2A_REQUIRE(world >= 1 && world <= MAX_WORLD && n >= 1 && n <= n_max && seq >= 1, B2A_E_INVALID,
               "peer_collect: bad argument");
   const long long max_spins = 20000000LL;  // a few seconds of polling local memory, then give up (NaN + status)
   B2A_LAUNCH(peer_collect_kernel, dim3(1), dim3(256), 0, stream, (const float*)local_buf, world, n, n_max, seq, out,
-             max_spins);
+             seqs_out, max_spins);
   B2A_CUDA_OK(cudaGetLastError());
   return B2A_OK;
 }
 
-extern "C" int b2a_peer_exchange_f32(const float* src, int n, void* const* peer_bufs_h, int world, int rank, int n_max,
-                                     int seq_put, const void* local_buf, int n_collect, int seq_collect, float* out,
-                                     void* stream) {
-  B2A_REQUIRE(src && peer_bufs_h && local_buf && out, B2A_E_INVALID, "peer_exchange: null pointer");
-  B2A_REQUIRE(world >= 1 && world <= MAX_WORLD && rank >= 0 && rank < world && n >= 1 && n <= n_max &&
-                  n_collect >= 1 && n_collect <= n_max && seq_put >= 2 && seq_collect == seq_put - 1,
-              B2A_E_INVALID, "peer_exchange: bad argument (collects seq_put - 1)");
-  Peers peers;
-  memset(&peers, 0, sizeof(peers));
-  for (int i = 0; i < world; ++i) {
-    B2A_REQUIRE(peer_bufs_h[i], B2A_E_INVALID, "peer_exchange: buffer of rank %d is not mapped", i);
-    peers.buf[i] = (float*)peer_bufs_h[i];
-  }
-  B2A_LAUNCH(peer_exchange_kernel, dim3((unsigned)world + 1), dim3(256), 0, stream, src, n, peers, world, rank, n_max,
-             seq_put, (const float*)local_buf, n_collect, seq_collect, out, 20000000LL);
+extern "C" int b2a_peer_latest_f32(const void* local_buf, int world, int n, int n_max, float* out, int32_t* seqs_out,
+                                   void* stream) {
+  B2A_REQUIRE(local_buf && out && seqs_out, B2A_E_INVALID, "peer_latest: null pointer");
+  B2A_REQUIRE(world >= 1 && world <= MAX_WORLD && n >= 1 && n <= n_max, B2A_E_INVALID, "peer_latest: bad argument");
+  B2A_LAUNCH(peer_latest_kernel, dim3(1), dim3(256), 0, stream, (const float*)local_buf, world, n, n_max, out, seqs_out);
   B2A_CUDA_OK(cudaGetLastError());
+  return B2A_OK;
+}
+
+extern "C" int b2a_peer_status(const void* local_buf, int world, int n_max, int32_t* status_out /*device [1]*/,
+                               void* stream) {
+  B2A_REQUIRE(local_buf && status_out, B2A_E_INVALID, "peer_status: null pointer");
+  B2A_REQUIRE(world >= 1 && world <= MAX_WORLD && n_max >= 1, B2A_E_INVALID, "peer_status: bad argument");
+  const int* st = reinterpret_cast<const int*>((const float*)local_buf + flag_offset_floats(world, n_max)) + NSLOT * world;
+#ifdef B2A_SIM
+  *status_out = *st;
+#else
+  B2A_CUDA_OK(cudaMemcpyAsync(status_out, st, sizeof(int), cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+#endif
   return B2A_OK;
 }

@@ -66,15 +66,18 @@ class LoudnessGather:
 
 class PeerLoudnessExchange:
     """One-sided exchange of the per-item loudness vector over NVLink peer memory (``csrc/peer.cu``): every rank
-    stores its ``[n]`` floats into a small cudaIpc-mapped buffer of every peer and publishes a sequence number;
-    ``collect`` waits on flags in local memory.  No rendezvous and no NCCL kernel on the step's critical path
-    (the NCCL all-gather of :class:`LoudnessGather` costs ~50 us of a 630 us step next to the persistent spectral
-    kernel).  All ranks must live on one node; ``torch.distributed`` (any backend) is used once, to swap the
-    64-byte IPC handles.
+    stores its ``[n]`` floats into a small cudaIpc-mapped buffer of every peer and publishes a sequence number.
+    No rendezvous and no NCCL kernel; ``torch.distributed`` (any backend) is used once, to swap the 64-byte IPC
+    handles.  All ranks must live on one node.
 
-    Per step:  ``seq = ex.put(loud_local)`` ... later ``ex.collect(seq)`` -> ``[world * n]``.  A put may only follow
-    the collect of the previous sequence number on the same stream (``put`` enforces it), which is what makes the
-    two-deep slot rotation safe.
+    The statistic is logging data, so NOTHING here can stall the data path: every kernel of the exchange is issued
+    on the exchange's own side stream (ordered after the producer of the vector by an event), ``put`` and ``latest``
+    never wait for another rank, and only ``collect`` -- the lock-step form, for validation and exact-step
+    statistics -- spins (bounded), still on the side stream.
+
+    Per step:  ``seq = ex.put(loud_local)``; whenever statistics are wanted ``vals, seqs = ex.latest()``
+    (``[world, n]`` newest complete vector of every rank and the sequence number each row carries).  Slots rotate
+    over four sequence numbers and are seqlock-protected, so no ordering between puts and reads is required.
     """
 
     def __init__(self, n_max: int, device=None, group=None, lib=None):
@@ -136,56 +139,86 @@ class PeerLoudnessExchange:
                 raise RuntimeError("peer exchange unavailable: " + "; ".join(e for e in errs if e))
         dist.barrier(group=group)  # every rank has mapped every buffer before the first put
         self.seq = 0
-        self._collected = 0
         self._n = {}
-        self.launches = 0  # kernels launched by put / collect
+        self.launches = 0  # kernels launched by put / latest / collect
+        self.side = torch.cuda.Stream(device=self.device) if self.device.type == "cuda" else None
+        self._ev = torch.cuda.Event() if self.side is not None else None
+
+    def _on_side(self, producer_stream=None):
+        """Context that makes the side stream current, ordered after everything enqueued so far on the producer's
+        stream (the caller's current stream by default)."""
+        import contextlib
+
+        if self.side is None:
+            return contextlib.nullcontext()
+        cur = producer_stream if producer_stream is not None else torch.cuda.current_stream(self.device)
+        self._ev.record(cur)
+        self.side.wait_event(self._ev)
+        return torch.cuda.stream(self.side)
+
+    def _stream_ptr(self):
+        return self._ct.c_void_p(self.side.cuda_stream if self.side is not None else 0)
 
     def put(self, loud_local: torch.Tensor) -> int:
-        """Publish this rank's vector for the next sequence number on the current stream; returns the number."""
-        assert loud_local.is_cuda and loud_local.dtype == torch.float32 and loud_local.is_contiguous()
+        """Publish this rank's vector as the next sequence number (side stream, never waits); returns the number."""
+        assert loud_local.dtype == torch.float32 and loud_local.is_contiguous()
+        assert loud_local.device.type == self.device.type
         n = loud_local.numel()
         assert 1 <= n <= self.n_max
-        if self._collected < self.seq:  # keep the two-deep rotation safe: drain the previous exchange first
-            self.collect(self.seq)
         self.seq += 1
         self._n[self.seq] = n
-        stream = self._ct.c_void_p(torch.cuda.current_stream(loud_local.device).cuda_stream)
-        self.lib.check(self.lib.b2a_peer_put_f32(self._ct.c_void_p(loud_local.data_ptr()), n, self.peers, self.world,
-                                                 self.rank, self.n_max, self.seq, stream))
+        while len(self._n) > 8:
+            self._n.pop(min(self._n))
+        with self._on_side():
+            self.lib.check(self.lib.b2a_peer_put_f32(self._ct.c_void_p(loud_local.data_ptr()), n, self.peers, self.world,
+                                                     self.rank, self.n_max, self.seq, self._stream_ptr()))
+        if self.side is not None:
+            loud_local.record_stream(self.side)
         self.launches += 1
         return self.seq
 
-    def collect(self, seq: int) -> torch.Tensor:
-        """``[world * n]`` loudness of sequence number ``seq`` (waits on the device until every rank has published)."""
-        assert seq == self._collected + 1 and seq <= self.seq, (seq, self._collected, self.seq)
-        n = self._n.pop(seq)
-        out = torch.empty(self.world * n, dtype=torch.float32, device=self.device)
-        stream = self._ct.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
-        self.lib.check(self.lib.b2a_peer_collect_f32(self._ct.c_void_p(self.local), self.world, n, self.n_max, seq,
-                                                     self._ct.c_void_p(out.data_ptr()), stream))
-        self._collected = seq
+    def latest(self, n: Optional[int] = None):
+        """Newest complete vector of every rank, without waiting for anybody: ``(values [world, n], seqs [world])``
+        (int32 sequence number per row; 0 and a NaN row for a rank that has not published yet).  The result lives on
+        the side stream: call :meth:`wait` (or synchronise) before consuming it on another stream."""
+        if n is None:
+            n = self._n[self.seq] if self.seq in self._n else self.n_max
+        out = torch.empty(self.world, n, dtype=torch.float32, device=self.device)
+        seqs = torch.zeros(self.world, dtype=torch.int32, device=self.device)
+        with self._on_side():
+            self.lib.check(self.lib.b2a_peer_latest_f32(self._ct.c_void_p(self.local), self.world, n, self.n_max,
+                                                        self._ct.c_void_p(out.data_ptr()),
+                                                        self._ct.c_void_p(seqs.data_ptr()), self._stream_ptr()))
         self.launches += 1
-        return out
+        return out, seqs
 
-    def put_collect(self, loud_local: torch.Tensor):
-        """Steady state of a one-step-late consumer, ONE launch: publish ``loud_local`` as the next sequence number and
-        return ``(seq, statistics of seq - 1)`` (``None`` on the very first call)."""
-        if self._collected == self.seq:  # nothing outstanding (first call, or already drained): plain put
-            return self.put(loud_local), None
-        assert loud_local.is_cuda and loud_local.dtype == torch.float32 and loud_local.is_contiguous()
-        n = loud_local.numel()
-        prev = self.seq
-        n_prev = self._n.pop(prev)
-        self.seq += 1
-        self._n[self.seq] = n
-        out = torch.empty(self.world * n_prev, dtype=torch.float32, device=self.device)
-        stream = self._ct.c_void_p(torch.cuda.current_stream(loud_local.device).cuda_stream)
-        self.lib.check(self.lib.b2a_peer_exchange_f32(
-            self._ct.c_void_p(loud_local.data_ptr()), n, self.peers, self.world, self.rank, self.n_max, self.seq,
-            self._ct.c_void_p(self.local), n_prev, prev, self._ct.c_void_p(out.data_ptr()), stream))
-        self._collected = prev
+    def collect(self, seq: int, return_seqs: bool = False):
+        """Lock-step gather ``[world * n]`` of sequence number ``seq`` (bounded device-side wait until every rank has
+        published it; a rank that died or is more than three steps ahead yields a NaN row).  Side stream."""
+        assert 1 <= seq <= self.seq, (seq, self.seq)
+        n = self._n.get(seq, self.n_max)
+        out = torch.empty(self.world * n, dtype=torch.float32, device=self.device)
+        seqs = torch.zeros(self.world, dtype=torch.int32, device=self.device)
+        with self._on_side():
+            self.lib.check(self.lib.b2a_peer_collect_f32(self._ct.c_void_p(self.local), self.world, n, self.n_max, seq,
+                                                         self._ct.c_void_p(out.data_ptr()),
+                                                         self._ct.c_void_p(seqs.data_ptr()), self._stream_ptr()))
         self.launches += 1
-        return self.seq, out
+        return (out, seqs) if return_seqs else out
+
+    def status(self) -> int:
+        """Last sequence number a ``collect`` gave up on (0: none).  Synchronises the side stream."""
+        st = torch.zeros(1, dtype=torch.int32, device=self.device)
+        with self._on_side():
+            self.lib.check(self.lib.b2a_peer_status(self._ct.c_void_p(self.local), self.world, self.n_max,
+                                                    self._ct.c_void_p(st.data_ptr()), self._stream_ptr()))
+        self.wait()
+        return int(st.item())
+
+    def wait(self):
+        """Make the caller's current stream wait for everything issued on the exchange's side stream."""
+        if self.side is not None:
+            torch.cuda.current_stream(self.device).wait_stream(self.side)
 
     def close(self):
         if getattr(self, "local", None) is None:

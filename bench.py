@@ -10,12 +10,17 @@ loudness kernels, then the fused gain + STFT + mel + log kernel.  Outputs per st
 waveform [B,2,441000], log-mel [B,2,128,862], LUFS [B].
 
   value     whole-job clips/s with inputs resident in HBM (device-timed, max over ranks)
-  e2e       the same metric through the public AudioSignal API with HOST (pinned) inputs: the H2D copy
-            of every step's batch and a D2H read of the step's LUFS vector are inside the timed region
+  e2e       the same metric through the public AudioSignal API with HOST (pinned) buffers on both sides: the H2D
+            copy of every step's batch and the D2H copy of ALL its results (normalised waveform, log-mel, LUFS)
+            are inside the timed region (copies double-buffered on their own streams)
   roofline  the dominant kernel (fused spectral) vs the measured HBM copy bandwidth
   cpu_baseline  the oracle (CPU port of the reference path) on this box's host cores, bounded sample
-Timing hygiene: >= 3 warm-ups, CUDA events on the launching stream, inputs rotate over 3 distinct
-226 MB batches (each > the 126 MB L2), nvidia-smi clocks sampled during the timed region.
+Timing hygiene: >= 3 warm-ups plus a >= 1 s identical pre-roll, barrier, one untimed post-barrier step, then
+EXACTLY K steps between CUDA events on the launching stream (max over ranks); inputs rotate over 3 distinct
+226 MB batches (each > the 126 MB L2); nvidia-smi clocks are sampled from before the pre-roll to the end of a
+>= 2 s sustained loop of the same step (reported next to the K-step figure).  At N > 1 the per-item LUFS
+exchange (csrc/peer.cu) runs on its own stream, never waits for another rank inside a step, and is validated
+once, untimed, against an NCCL all_gather of the same vector.
 """
 import argparse
 import json
@@ -89,22 +94,32 @@ def time_cpu(n_clips, reps, warmup):
     return ts, best
 
 
+def make_config(world, B, exchange_kind=None):
+    """The `config` object of the JSON line: identical for both arms at the same N (the driver compares them)."""
+    return {"workload": WORKLOAD, "global_batch": world * B, "per_gpu_batch": B,
+            "parallelism": f"batch-sharded x{world}, no data-path collective"
+                           + (" (+ per-item LUFS exchange on a side stream)" if world > 1 else ""),
+            "l2": f"inputs rotate over 3 distinct {B * BYTES_X / 1e6:.0f} MB batches (> 126 MB L2)"}
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
     if rank != 0:
         return 0
-    n_clips = 16  # bounded sample of the 64-clip batch
-    ts, cores = time_cpu(n_clips, reps=max(1, args.steps), warmup=max(1, min(args.warmup, 2)))
+    n_clips = args.batch  # one step = the full per-GPU batch of the workload, on this box's host cores
+    ts, cores = time_cpu(n_clips, reps=max(1, args.steps), warmup=max(1, args.warmup))
     total = sum(ts)
     value = n_clips * len(ts) / total
     line = {
         "impl": "reference", "metric": "clips/sec (10s@44.1kHz) log-mel+LUFS pipeline", "value": value,
-        "unit": "clips/s", "n_gpus": args.gpus, "steps": len(ts), "warmup": max(1, min(args.warmup, 2)),
+        "unit": "clips/s", "n_gpus": args.gpus, "steps": len(ts), "warmup": max(1, args.warmup),
         "ms_per_step": 1e3 * total / len(ts), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f32", "data": "synthetic", "config": {"workload": WORKLOAD, "sample_clips_per_step": n_clips},
+        "dtype": "f32", "data": "synthetic", "config": make_config(max(world, args.gpus), args.batch),
         "cpu_baseline": {"value": value, "unit": "clips/s", "cores": cores, "kind": "port",
-                         "sample": f"{n_clips} of the 64 clips per step, {len(ts)} steps; torch threads calibrated over "
-                                   f"{{all cores, 64, 32, 16, 8}} on 4 clips, fastest used"},
+                         "sample": f"the full {n_clips}-clip batch per step, {len(ts)} steps after {max(1, args.warmup)} "
+                                   f"warm-ups; torch threads calibrated over {{all cores, 64, 32, 16, 8}} on 4 clips, "
+                                   f"fastest used; one host (rank 0) whatever N"},
         "e2e": {"value": value, "unit": "clips/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
         "note": "reference CPU path = the in-repo oracle port (torch.stft + torchaudio.lfilter + restated "
@@ -118,6 +133,8 @@ def run_reference(args):
 # clocks
 # ----------------------------------------------------------------------------------------------
 class ClockSampler:
+    """nvidia-smi polled every 100 ms for one GPU, each row stamped with the host clock so that windows (pre-roll,
+    timed region, sustained loop) can be cut out afterwards."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
@@ -138,7 +155,7 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append((time.perf_counter(), [c.strip() for c in line.split(",")]))
 
     def __exit__(self, *a):
         if self.proc:
@@ -149,13 +166,16 @@ class ClockSampler:
             except Exception:
                 pass
 
-    def summary(self):
-        sm, mx, reasons = [], [], set()
+    def summary(self, t_lo=None, t_hi=None):
+        sm, mx, pw, reasons = [], [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+        for ts, r in self.rows:
+            if (t_lo is not None and ts < t_lo) or (t_hi is not None and ts > t_hi):
+                continue
             try:
                 sm.append(float(r[0]))
                 mx.append(float(r[1]))
+                pw.append(float(r[2]))
                 for n, v in zip(names, r[3:7]):
                     if v.lower().startswith("active"):
                         reasons.add(n)
@@ -164,7 +184,8 @@ class ClockSampler:
         if not sm:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
         sm.sort()
-        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+        return {"sm_mhz": sm[len(sm) // 2], "sm_min_mhz": sm[0], "sm_max_mhz": max(mx), "power_w_max": max(pw),
+                "reasons": sorted(reasons), "samples": len(sm)}
 
 
 # ----------------------------------------------------------------------------------------------
@@ -201,11 +222,11 @@ def run_ours(args):
     db = torch.tensor([TARGET_DB], device=dev)
     win = AudioSignal.get_window("hann", N_FFT, dev)
     fb, lo, hi = AudioSignal._mel_tables(SR, N_FFT, N_MELS, 0.0, None, dev)
-    from audiotools_b200.parallel import LoudnessGather
 
-    # Whole-batch loudness statistics (the path's only exchange: 256 B per rank and step).  Preferred: one-sided
-    # stores into every peer's buffer over NVLink (csrc/peer.cu) -- no rendezvous, no NCCL kernel next to the
-    # persistent spectral kernel.  Fallback if the peer mapping cannot be set up: NCCL all-gather on a side stream.
+    # Whole-batch loudness statistics (the path's only exchange: 256 B per rank and step), logging data.  One-sided
+    # stores into every peer's buffer over NVLink (csrc/peer.cu) on the exchange's OWN stream: a put and a
+    # non-blocking read of the newest statistics per step; no rank ever waits for another inside a step.  Fallback if
+    # the peer mapping cannot be set up: NCCL all-gather on a side stream, consumed one step late.
     exchange, gather, exchange_kind = None, None, "none"
     if world > 1 and not os.environ.get("B2A_BENCH_NO_GATHER"):
         try:
@@ -214,32 +235,24 @@ def run_ours(args):
             from audiotools_b200.parallel import PeerLoudnessExchange
 
             exchange = PeerLoudnessExchange(n_max=B)
-            exchange_kind = "peer-store (cudaIpc + NVLink P2P stores, csrc/peer.cu)"
+            exchange_kind = "peer-store (cudaIpc + NVLink P2P stores, csrc/peer.cu), side stream, non-blocking"
         except Exception as e:  # noqa: BLE001
+            from audiotools_b200.parallel import LoudnessGather
+
             gather = LoudnessGather(side_stream=torch.cuda.Stream(device=dev))
             exchange_kind = f"nccl all_gather on a side stream ({type(e).__name__}: {e})"
     spec_events = []
-    pending = []  # statistics are logging data: they are consumed one step late, never inside the step that made them
-
-    def drain():
-        while pending:
-            kind, h = pending.pop(0)
-            if kind == "peer":
-                exchange.collect(h)
-            else:
-                gather.wait()
+    stats = {}  # newest whole-batch statistics seen (values, per-rank sequence numbers): logging data
 
     def step(i, timed=False):
         x = xs[i % NBUF]
-        if exchange is None:
-            drain()  # previous step's statistics (long complete)
         lu = eng.lufs(x, SR, target_db=db)
-        if exchange is not None:  # ONE launch: publish this step's vector, read the previous step's statistics
-            seq, lu["loud_all_prev"] = exchange.put_collect(lu["loud"])
-            pending[:] = [("peer", seq)]
+        if exchange is not None:
+            stats["seq"] = exchange.put(lu["loud"])
+            stats["latest"] = exchange.latest()
         elif gather is not None:
-            lu["loud_all"] = gather(lu["loud"])
-            pending.append(("nccl", None))
+            gather.wait()  # the previous step's gather (long complete)
+            stats["all"] = gather(lu["loud"])
         if timed:
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
@@ -256,61 +269,137 @@ def run_ours(args):
             dist.barrier()
             torch.cuda.synchronize()
 
-    # ---- device-resident timing
-    for i in range(args.warmup):
-        step(i)
-    barrier()
-    launches0 = eng.launches
-    xl0 = exchange.launches if exchange is not None else 0
-    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    # ---- device-resident timing.  The clock sampler starts BEFORE everything (its fork is expensive and differs
+    #      per rank: it must never sit between the barrier and t0).
     with ClockSampler(local) as clocks:
+        for i in range(args.warmup):
+            step(i)
+        torch.cuda.synchronize()
+        w_pre0 = time.perf_counter()
+        n_pre = 0
+        while time.perf_counter() - w_pre0 < args.preroll:  # identical steps: clocks / power settle under the real load
+            for _ in range(20):
+                step(n_pre)
+                n_pre += 1
+            torch.cuda.synchronize()
+        barrier()
+        step(0)  # one untimed post-barrier step: absorbs the rank skew of leaving the barrier
+        torch.cuda.synchronize()
+        launches0 = eng.launches
+        xl0 = exchange.launches if exchange is not None else 0
+        t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         t0.record()
         for i in range(args.steps):
             step(args.warmup + i, timed=True)
-        drain()  # the last step's statistics are inside the timed region too
         t1.record()
+        torch.cuda.synchronize()
+        w_timed1 = time.perf_counter()
+        ms_rank = t0.elapsed_time(t1)
+        launches = eng.launches - launches0 + (exchange.launches - xl0 if exchange is not None else 0)
+        # sustained figure: the same step for >= args.sustain seconds (SM clocks settle under the power cap)
+        sus = None
+        if args.sustain > 0:
+            n_sus = max(args.steps, int(args.sustain / max(ms_rank / args.steps * 1e-3, 1e-5)))
+            s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s0.record()
+            for i in range(n_sus):
+                step(i)
+            s1.record()
+            torch.cuda.synchronize()
+            sus = (n_sus, s0.elapsed_time(s1))
+        w_end = time.perf_counter()
         barrier()
-    ms = t0.elapsed_time(t1)
-    launches = eng.launches - launches0 + (exchange.launches - xl0 if exchange is not None else 0)
     spec_ms = sum(a.elapsed_time(b) for a, b in spec_events) / max(1, len(spec_events))
-    tms = torch.tensor([ms], device=dev, dtype=torch.float64)
+    per_rank = [ms_rank]
     if world > 1:
-        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
-    ms = float(tms.item())
+        tms = torch.tensor([ms_rank], device=dev, dtype=torch.float64)
+        allms = [torch.zeros_like(tms) for _ in range(world)]
+        dist.all_gather(allms, tms)
+        per_rank = [float(t.item()) for t in allms]
+    ms = max(per_rank)
     value = world * B * args.steps / (ms * 1e-3)
+    sus_line = None
+    if sus is not None:
+        tsu = torch.tensor([sus[1] / sus[0]], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(tsu, op=dist.ReduceOp.MAX)
+        sus_line = {"ms_per_step": float(tsu.item()), "steps": sus[0], "value": world * B / (float(tsu.item()) * 1e-3),
+                    "unit": "clips/s", "clocks": clocks.summary(w_timed1, w_end)}
 
-    # ---- end to end through the public API, host (pinned) inputs, double-buffered H2D
+    # ---- untimed validation of the exchange: the gathered vector of one step equals NCCL's all_gather of it
+    exchange_line = None
+    if world > 1:
+        exchange_line = {"kind": exchange_kind}
+        out, lu = step(1)
+        torch.cuda.synchronize()
+        ref = torch.empty(world * B, device=dev)
+        dist.all_gather_into_tensor(ref, lu["loud"].contiguous())
+        if exchange is not None:
+            vals, seqs = stats["latest"]
+            exchange.wait()
+            torch.cuda.synchronize()
+            lag = int(stats["seq"]) - int(seqs.min().item())  # how stale the non-blocking read of the last step was
+            got, cseqs = exchange.collect(stats["seq"], return_seqs=True)
+            exchange.wait()
+            torch.cuda.synchronize()
+            ok = bool(torch.equal(got, ref)) and cseqs.tolist() == [stats["seq"]] * world and exchange.status() == 0
+            exchange_line.update({"validated_vs_nccl_all_gather": ok, "last_read_lag_steps": lag,
+                                  "waits_inside_step": 0})
+        else:
+            gather.wait()
+            torch.cuda.synchronize()
+            ok = bool(torch.equal(stats["all"], ref))
+            exchange_line.update({"validated_vs_nccl_all_gather": ok})
+        flag = torch.tensor([1.0 if ok else 0.0], device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        assert flag.item() == 1.0, "per-item LUFS exchange disagrees with NCCL all_gather"
+
+    # ---- end to end through the public API: HOST (pinned) inputs and HOST (pinned) results, copies double-buffered
     hx = [make_batch(B, 500 + i).pin_memory() for i in range(2)]
-    copy_stream = torch.cuda.Stream(device=dev)
+    copy_in, copy_out = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
     dbuf = [torch.empty(B, C, T, device=dev) for _ in range(2)]
     ready = [torch.cuda.Event() for _ in range(2)]
     freed = [torch.cuda.Event() for _ in range(2)]
-    h_metric = torch.empty(B, pin_memory=True)
+    done = [torch.cuda.Event() for _ in range(2)]
+    h_y = [torch.empty(B, C, T, pin_memory=True) for _ in range(2)]
+    h_mel = [torch.empty(B, C, N_MELS, N_FRAMES, pin_memory=True) for _ in range(2)]
+    h_lufs = [torch.empty(B, pin_memory=True) for _ in range(2)]
+    full_d2h = not args.e2e_features_only
 
     def e2e_run(n):
         cur = torch.cuda.current_stream()
         for e in freed:
             e.record(cur)
-        with torch.cuda.stream(copy_stream):
-            copy_stream.wait_event(freed[0])
+        with torch.cuda.stream(copy_in):
+            copy_in.wait_event(freed[0])
             dbuf[0].copy_(hx[0], non_blocking=True)
-            ready[0].record(copy_stream)
+            ready[0].record(copy_in)
         for i in range(n):
             b = i % 2
             if i + 1 < n:  # prefetch the next batch while this one computes
-                with torch.cuda.stream(copy_stream):
-                    copy_stream.wait_event(freed[1 - b])
+                with torch.cuda.stream(copy_in):
+                    copy_in.wait_event(freed[1 - b])
                     dbuf[1 - b].copy_(hx[(i + 1) % 2], non_blocking=True)
-                    ready[1 - b].record(copy_stream)
+                    ready[1 - b].record(copy_in)
             cur.wait_event(ready[b])
             sig = AudioSignal(dbuf[b], SR)
             sig.normalize(TARGET_DB)
             logmel = sig.mel_spectrogram(n_mels=N_MELS, window_length=N_FFT, hop_length=HOP, window_type="hann",
                                          log=True)
             y = sig.audio_data  # normalised waveform (came out of the same pass)
+            lufs = sig._measured_loudness
             assert y.data_ptr() != dbuf[b].data_ptr()
-            h_metric.copy_(logmel.mean(dim=(1, 2, 3)), non_blocking=True)  # the step's result, D2H
             freed[b].record(cur)
+            done[b].record(cur)
+            with torch.cuda.stream(copy_out):  # the step's results back to the host (pinned), off the compute stream
+                copy_out.wait_event(done[b])
+                h_mel[b].copy_(logmel, non_blocking=True)
+                h_lufs[b].copy_(lufs, non_blocking=True)
+                if full_d2h:
+                    h_y[b].copy_(y, non_blocking=True)
+                for t_ in (logmel, lufs, y):
+                    t_.record_stream(copy_out)
+        cur.wait_stream(copy_out)
         return logmel
 
     e2e_steps = max(3, min(args.steps, 20))
@@ -341,14 +430,24 @@ def run_ours(args):
     alg_bytes = B * (2 * BYTES_X + BYTES_MEL)  # read x + write y + write log-mel, each once
     achieved = alg_bytes / (spec_ms * 1e-3) / 1e9
     lufs_ms = ms / args.steps - spec_ms
-    roof = {"kernel": "spectral_warp_kernel<10> (gain + STFT + |.| + mel + log10, fused)", "bound": "hbm",
+    kernel_name = eng.spectral_kernel_name(N_FFT, HOP) if hasattr(eng, "spectral_kernel_name") else \
+        "spectral_warp_kernel<10,0>"
+    # DRAM traffic of one launch: from the committed `ncu --set full` capture of THIS kernel at B = 64 (bench.py cannot
+    # run under ncu); null when no capture of the kernel in use has been committed
+    traffic, traffic_src = None, None
+    tpath = os.path.join(REPO, "profiles", "spectral_traffic.json")
+    if os.path.exists(tpath):
+        rec = json.load(open(tpath)).get(kernel_name.split("<")[0])
+        if rec:
+            traffic = (rec["dram_bytes_read"] + rec["dram_bytes_write"]) * B / rec["batch"]
+            traffic_src = rec["source"]
+    roof = {"kernel": kernel_name + " (gain + STFT + |.| + mel + log10, fused)", "bound": "hbm",
             "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-            # dram__bytes_read.sum + dram__bytes_write.sum of one launch at B=64 from the ncu --set full capture
-            # profiles/r01h_prof_spectral_v7_ncu_full_summary.csv (226.0 + 229.2 MB), scaled to this batch
-            "traffic": (226.3e6 + 229.2e6) * B / 64,  # dram__bytes_read + write of one launch: profiles/r01r_prof_spectral_final_ncu_full_summary.csv
+            "traffic": traffic, "traffic_source": traffic_src,
             "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes, "ms_per_launch": spec_ms,
             "rest_of_step_ms": lufs_ms,
-            "rest_of_step": "lufs kernels (read x once: %.0f GB/s algorithmic)" % (B * BYTES_X / max(lufs_ms, 1e-9) / 1e6)}
+            "rest_of_step": "lufs kernels (read x once: %.0f GB/s algorithmic)" % (B * BYTES_X / max(lufs_ms, 1e-9) / 1e6),
+            "whole_step_frac": alg_bytes / (ms / args.steps * 1e-3) / 1e9 / peak}
 
     # ---- CPU baseline (bounded sample, rank 0 at any N; cheap)
     cpu = None
@@ -359,19 +458,25 @@ def run_ours(args):
                "sample": f"{n_clips} clips per rep, {len(ts)} reps after 1 warm-up; torch threads calibrated over "
                          f"{{all cores, 64, 32, 16, 8}}, fastest used"}
 
+    clk = clocks.summary(w_pre0, w_end)
+    clk["window"] = (f"pre-roll {args.preroll:g} s + the {args.steps} timed steps + sustained loop {args.sustain:g} s: one "
+                     f"continuous run of the identical step (the timed region alone is {ms:.1f} ms)")
+    sorted_ms = sorted(per_rank)
+    d2h = B * 4 + B * BYTES_MEL + (B * BYTES_X if full_d2h else 0)
     line = {
         "metric": "clips/sec (10s@44.1kHz) log-mel+LUFS pipeline", "value": value, "unit": "clips/s",
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "global_batch": world * B, "per_gpu_batch": B,
-                   "parallelism": f"batch-sharded x{world}, no data-path collective"
-                                  + (f" (+ per-item LUFS exchange: {exchange_kind})" if world > 1 else ""),
-                   "l2": f"inputs rotate over {NBUF} distinct {B * BYTES_X / 1e6:.0f} MB batches (> 126 MB L2)"},
+        "config": make_config(world, B),
+        "per_rank_ms_per_step": {"min": sorted_ms[0] / args.steps, "median": sorted_ms[len(sorted_ms) // 2] / args.steps,
+                                 "max": sorted_ms[-1] / args.steps},
         "roofline": roof, "cpu_baseline": cpu,
         "e2e": {"value": e2e_value, "unit": "clips/s", "h2d_bytes_per_step": B * BYTES_X,
-                "d2h_bytes_per_step": B * 4, "steps": e2e_steps,
+                "d2h_bytes_per_step": d2h, "steps": e2e_steps,
+                "result_d2h": "log-mel + LUFS" + (" + normalised waveform" if full_d2h else ""),
                 "api": "AudioSignal(x).normalize(-24).mel_spectrogram(..., log=True)"},
-        "gpu_launches": launches, "clocks": clocks.summary(),
+        "sustained": sus_line, "exchange": exchange_line,
+        "gpu_launches": launches, "clocks": clk,
     }
     print(json.dumps(line))
     if world > 1:
@@ -387,6 +492,10 @@ def main():
     ap.add_argument("--batch", type=int, default=64, help="clips per GPU per step")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--preroll", type=float, default=1.0, help="seconds of identical untimed steps before the barrier")
+    ap.add_argument("--sustain", type=float, default=2.0, help="seconds of the sustained loop after the timed steps")
+    ap.add_argument("--e2e-features-only", action="store_true",
+                    help="e2e leg copies back log-mel + LUFS only (not the normalised waveform)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     if args.impl == "reference":

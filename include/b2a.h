@@ -211,10 +211,17 @@ int b2a_time_stretch_f32(const float* x, int64_t rows, int64_t T, int sr, double
  * buffer (b2a_peer_buffer_create: cudaMalloc + cudaIpc handle), maps its peers' buffers (b2a_peer_buffer_open on
  * the 64-byte handles, exchanged by the host side), then per step
  *   b2a_peer_put_f32      stores src[0..n) into its slot of EVERY rank's buffer and publishes `seq` (system-scope
- *                         release); no rendezvous, no NCCL kernel;
- *   b2a_peer_collect_f32  waits (bounded) until all ranks published `seq` in the LOCAL buffer, gathers [world, n].
- * seq >= 1 grows by one per step; slots are double buffered by seq parity: a put of seq may only be issued after
- * the local collect of seq-1 (stream order) -- then no slot is overwritten before every reader has read it. */
+ *                         release); no rendezvous, no NCCL kernel, NEVER waits for another rank;
+ *   b2a_peer_latest_f32   reads from the LOCAL buffer the newest complete vector of every rank -> out [world, n] and
+ *                         the sequence number each row carries -> seqs_out [world] (0 + NaN row: nothing published
+ *                         yet).  Never waits: a rank that is behind shows an older sequence number;
+ *   b2a_peer_collect_f32  the lock-step form: waits (bounded spin) until every rank published exactly `seq`, gathers
+ *                         [world, n]; seqs_out (nullable) [world] = seq, or -(what was seen) + a NaN row for a rank
+ *                         that died or lapped the slot.  For validation / exact-step statistics, on a side stream.
+ * seq >= 1 grows by one per step; slots rotate over 4 sequence numbers and are seqlock-protected (invalidate, data,
+ * publish), so readers never accept a torn or overwritten vector whatever the skew between ranks.
+ * b2a_peer_status copies the buffer's status word (last sequence number a collect gave up on, 0 = none) to
+ * status_out (device int32). */
 size_t b2a_peer_buffer_bytes(int world, int n_max);
 int b2a_peer_buffer_create(int world, int n_max, void** dev_ptr, unsigned char* handle_out /*[64]*/);
 int b2a_peer_buffer_open(const unsigned char* handle /*[64]*/, void** peer_ptr);
@@ -222,11 +229,11 @@ int b2a_peer_buffer_close(void* peer_ptr);
 int b2a_peer_buffer_destroy(void* dev_ptr);
 int b2a_peer_put_f32(const float* src, int n, void* const* peer_bufs_h /*host [world]*/, int world, int rank,
                      int n_max, int seq, void* stream);
-int b2a_peer_collect_f32(const void* local_buf, int world, int n, int n_max, int seq, float* out, void* stream);
-/* steady state of a consumer that reads the statistics one step late: put(seq_put) and collect(seq_put - 1) in ONE
- * launch (the collect CTA never waits in practice: that sequence was published a whole step ago). */
-int b2a_peer_exchange_f32(const float* src, int n, void* const* peer_bufs_h, int world, int rank, int n_max,
-                          int seq_put, const void* local_buf, int n_collect, int seq_collect, float* out, void* stream);
+int b2a_peer_latest_f32(const void* local_buf, int world, int n, int n_max, float* out, int32_t* seqs_out,
+                        void* stream);
+int b2a_peer_collect_f32(const void* local_buf, int world, int n, int n_max, int seq, float* out, int32_t* seqs_out,
+                         void* stream);
+int b2a_peer_status(const void* local_buf, int world, int n_max, int32_t* status_out, void* stream);
 
 #ifdef __cplusplus
 }

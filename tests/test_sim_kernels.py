@@ -312,12 +312,9 @@ def test_istft_zero_tail_and_envelope_check(eng):
 # ------------------------------------------------------------------------------------------
 # one-sided peer exchange (csrc/peer.cu): two "ranks" in one process, buffers in host memory
 # ------------------------------------------------------------------------------------------
-def test_peer_put_collect_two_ranks(eng):
+def _peer_setup(lib, world, n_max):
     import ctypes
 
-    lib, world, n_max = eng.lib, 2, 8
-    assert lib.b2a_peer_buffer_bytes(world, n_max) == (2 * world * n_max + 2 * world + 4) * 4
-    assert lib.b2a_peer_buffer_bytes(17, 8) == 0
     bufs, peers = [], (ctypes.c_void_p * world)()
     for r in range(world):
         p, h = ctypes.c_void_p(), (ctypes.c_ubyte * 64)()
@@ -327,28 +324,86 @@ def test_peer_put_collect_two_ranks(eng):
         assert q.value == p.value
         bufs.append(p.value)
         peers[r] = p.value
-    vals = {r: [torch.arange(5, dtype=torch.float32) + 10 * r + 100 * s for s in (1, 2, 3)] for r in range(world)}
-    for s in (1, 2, 3):  # three steps: both parities and a reuse of the first slot
+    return bufs, peers
+
+
+def test_peer_put_collect_two_ranks(eng):
+    import ctypes
+
+    lib, world, n_max = eng.lib, 2, 8
+    assert lib.b2a_peer_buffer_bytes(world, n_max) == (4 * world * n_max + 4 * world + 4) * 4
+    assert lib.b2a_peer_buffer_bytes(17, 8) == 0
+    bufs, peers = _peer_setup(lib, world, n_max)
+    vals = {r: [torch.arange(5, dtype=torch.float32) + 10 * r + 100 * s for s in range(1, 7)] for r in range(world)}
+    for s in range(1, 7):  # six steps: every slot, and a reuse of the first two
         for r in range(world):
             v = vals[r][s - 1]
             lib.check(lib.b2a_peer_put_f32(ctypes.c_void_p(v.data_ptr()), 5, peers, world, r, n_max, s, None))
         for r in range(world):
-            out = torch.empty(world * 5)
+            out, seqs = torch.empty(world * 5), torch.zeros(world, dtype=torch.int32)
             lib.check(lib.b2a_peer_collect_f32(ctypes.c_void_p(bufs[r]), world, 5, n_max, s,
-                                               ctypes.c_void_p(out.data_ptr()), None))
+                                               ctypes.c_void_p(out.data_ptr()), ctypes.c_void_p(seqs.data_ptr()), None))
             assert torch.equal(out, torch.cat([vals[0][s - 1], vals[1][s - 1]]))
-    # fused form: put(4) + collect(3) in one launch per rank (sequence 3 was published above)
-    nxt = {r: torch.arange(5, dtype=torch.float32) - 7 * r for r in range(world)}
-    for r in range(world):
-        out = torch.empty(world * 5)
-        lib.check(lib.b2a_peer_exchange_f32(ctypes.c_void_p(nxt[r].data_ptr()), 5, peers, world, r, n_max, 4,
-                                            ctypes.c_void_p(bufs[r]), 5, 3, ctypes.c_void_p(out.data_ptr()), None))
-        assert torch.equal(out, torch.cat([vals[0][2], vals[1][2]]))
-    out = torch.empty(world * 5)
-    lib.check(lib.b2a_peer_collect_f32(ctypes.c_void_p(bufs[0]), world, 5, n_max, 4, ctypes.c_void_p(out.data_ptr()), None))
-    assert torch.equal(out, torch.cat([nxt[0], nxt[1]]))
+            assert seqs.tolist() == [s, s]
+            out2 = torch.empty(world, 5)
+            lib.check(lib.b2a_peer_latest_f32(ctypes.c_void_p(bufs[r]), world, 5, n_max,
+                                              ctypes.c_void_p(out2.data_ptr()), ctypes.c_void_p(seqs.data_ptr()), None))
+            assert torch.equal(out2.reshape(-1), out) and seqs.tolist() == [s, s]
     assert lib.b2a_peer_put_f32(None, 5, peers, world, 0, n_max, 1, None) != 0  # null source is refused
+    st = torch.full((1,), -1, dtype=torch.int32)
+    lib.check(lib.b2a_peer_status(ctypes.c_void_p(bufs[0]), world, n_max, ctypes.c_void_p(st.data_ptr()), None))
+    assert st.item() == 0
     for b in bufs:
+        lib.check(lib.b2a_peer_buffer_destroy(ctypes.c_void_p(b)))
+
+
+def test_peer_exchange_skewed_ranks_never_return_a_wrong_vector(eng):
+    """a rank that runs ahead must never make a slower rank accept a FUTURE vector for an old
+    sequence number.  Rank 0 publishes 1..7 while rank 1 has only published 1: `latest` shows (7, 1) with the right
+    payloads, the lock-step collect of a lapped sequence number reports the loss (NaN row, negative seq, status) instead
+    of returning other data, and a sequence number still inside the four-slot window is returned exactly."""
+    import ctypes
+
+    lib, world, n_max = eng.lib, 2, 8
+    bufs, peers = _peer_setup(lib, world, n_max)
+    val = lambda r, s: torch.arange(6, dtype=torch.float32) + 10 * r + 100 * s  # noqa: E731
+    keep = []
+    for s in range(1, 8):
+        v = val(0, s)
+        keep.append(v)
+        lib.check(lib.b2a_peer_put_f32(ctypes.c_void_p(v.data_ptr()), 6, peers, world, 0, n_max, s, None))
+    v1 = val(1, 1)
+    lib.check(lib.b2a_peer_put_f32(ctypes.c_void_p(v1.data_ptr()), 6, peers, world, 1, n_max, 1, None))
+    for r in range(world):  # both ranks see the same picture
+        out, seqs = torch.empty(world, 6), torch.zeros(world, dtype=torch.int32)
+        lib.check(lib.b2a_peer_latest_f32(ctypes.c_void_p(bufs[r]), world, 6, n_max, ctypes.c_void_p(out.data_ptr()),
+                                          ctypes.c_void_p(seqs.data_ptr()), None))
+        assert seqs.tolist() == [7, 1]
+        assert torch.equal(out[0], val(0, 7)) and torch.equal(out[1], val(1, 1))
+    # sequence 1 of rank 0 was overwritten by 5 (same slot): the collect must say so, not hand back 5's data
+    out, seqs = torch.empty(world * 6), torch.zeros(world, dtype=torch.int32)
+    lib.check(lib.b2a_peer_collect_f32(ctypes.c_void_p(bufs[1]), world, 6, n_max, 1, ctypes.c_void_p(out.data_ptr()),
+                                       ctypes.c_void_p(seqs.data_ptr()), None))
+    assert torch.isnan(out[:6]).all() and torch.equal(out[6:], val(1, 1))
+    assert seqs.tolist() == [-5, 1]
+    st = torch.zeros(1, dtype=torch.int32)
+    lib.check(lib.b2a_peer_status(ctypes.c_void_p(bufs[1]), world, n_max, ctypes.c_void_p(st.data_ptr()), None))
+    assert st.item() == 1
+    # rank 1 catches up to 6 (still inside rank 0's window 4..7): exact data for both
+    for s in range(2, 7):
+        v = val(1, s)
+        keep.append(v)
+        lib.check(lib.b2a_peer_put_f32(ctypes.c_void_p(v.data_ptr()), 6, peers, world, 1, n_max, s, None))
+    lib.check(lib.b2a_peer_collect_f32(ctypes.c_void_p(bufs[0]), world, 6, n_max, 6, ctypes.c_void_p(out.data_ptr()),
+                                       ctypes.c_void_p(seqs.data_ptr()), None))
+    assert torch.equal(out, torch.cat([val(0, 6), val(1, 6)])) and seqs.tolist() == [6, 6]
+    # nothing published yet -> NaN row and sequence number 0 from `latest`
+    bufs2, _ = _peer_setup(lib, world, n_max)
+    out, seqs = torch.zeros(world, 6), torch.ones(world, dtype=torch.int32)
+    lib.check(lib.b2a_peer_latest_f32(ctypes.c_void_p(bufs2[0]), world, 6, n_max, ctypes.c_void_p(out.data_ptr()),
+                                      ctypes.c_void_p(seqs.data_ptr()), None))
+    assert torch.isnan(out).all() and seqs.tolist() == [0, 0]
+    for b in bufs + bufs2:
         lib.check(lib.b2a_peer_buffer_destroy(ctypes.c_void_p(b)))
 
 

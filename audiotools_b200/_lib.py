@@ -43,6 +43,8 @@ SIGNATURES = {
     "b2a_pitch_shift_multi_workspace_bytes": (c_size_t, [c_int64, c_int64, c_int, c_void_p, c_int]),
     "b2a_pitch_shift_multi_f32": (c_int, [c_void_p, c_int64, c_int64, c_int, c_void_p, c_int, c_void_p, c_void_p, c_void_p,
                                           c_size_t, c_void_p]),
+    "b2a_spectral_uses_tensor_cores": (c_int, [c_int, c_int, c_int, c_int]),
+    "b2a_spectral_tc_enable": (c_int, [c_int]),
     "b2a_peer_buffer_bytes": (c_size_t, [c_int, c_int]),
     "b2a_peer_buffer_create": (c_int, [c_int, c_int, c_void_p, c_void_p]),
     "b2a_peer_buffer_open": (c_int, [c_void_p, c_void_p]),

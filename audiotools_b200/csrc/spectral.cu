@@ -61,54 +61,6 @@ struct Plan {
   static constexpr int FR = (G >= 16) ? G : ((LOG2N >= 11) ? 2 * G : ((LOG2N == 10) ? 4 * G : 16));
 };
 
-struct Params {
-  const float* x;
-  const float* window;
-  const float* gain;
-  float* y_out;
-  const float* mel_fb;
-  const int32_t* mel_lo;
-  const int32_t* mel_hi;
-  float* mel_out;
-  float2* stft_out;
-  int rows, T, n_fft, hop, pad, right_pad, pad_mode, drop_edge;
-  int n_frames, n_tiles, n_mels, rows_per_gain, post;
-  int mel_packed_len;  // sum over filters of the 4-aligned band widths (0: read weights from global)
-  int off_mpk, off_mseg;
-  // framing: frame n of a row starts at x-coordinate (n + drop_edge)*hop + origin (+ row_origin[row]);
-  // center = 1: torch.stft(center=True) semantics (reflect about the F.pad-ed signal), 0: raw
-  int center, origin;
-  const int32_t* row_origin;
-  float post_eps, post_power;
-  int span;  // (FR-1)*hop + n_fft
-  // shared memory offsets (bytes)
-  int off_win, off_tw, off_ut, off_buf, off_mag, off_mel, smem_bytes;
-  int xb_stride;   // floats per frame slot of the exchange / |X| buffer (WPlan::XB, or 2N+4 when the STFT is staged)
-  int stage_stft;  // STFT-only launch: complex frames are parked in their slots and written with frame-contiguous runs
-};
-
-// index of sample `w` (in un-padded x coordinates, may be outside [0,T)) after torch's two
-// paddings; -1 => zero.   ref:audiotools/core/audio_signal.py:1192-1202
-#define B2A_PAD_CIRCULAR 3  // internal (FFT convolution): index modulo T
-
-__device__ __forceinline__ int src_index(int w, int T, int pad, int right_pad, int pad_mode, int center = 1) {
-  int u = w;
-  if (center) {
-    const int Lp = T + 2 * pad + right_pad;
-    int v = w + pad;  // position in the F.pad-ed signal
-    if (v < 0) v = -v;                       // torch.stft(center=True): reflect, no edge repeat
-    else if (v >= Lp) v = 2 * (Lp - 1) - v;
-    if (v < 0 || v >= Lp) return -1;         // only reachable from frames past the end (never stored)
-    u = v - pad;
-  }
-  if (u >= 0 && u < T) return u;
-  if (pad_mode == B2A_PAD_REFLECT) u = u < 0 ? -u : 2 * (T - 1) - u;
-  else if (pad_mode == B2A_PAD_REPLICATE) u = u < 0 ? 0 : T - 1;
-  else if (pad_mode == B2A_PAD_CIRCULAR) { u %= T; if (u < 0) u += T; }
-  else return -1;
-  return (u >= 0 && u < T) ? u : -1;
-}
-
 // Stage the contiguous sample span of a tile into shared memory (x * gain) and write back the part
 // of the scaled waveform this CTA owns ([n0*hop, (n0+FR)*hop) -- the last tile up to T).
 __device__ __forceinline__ void stage_span(const Params& p, float* sp, int row, int tile, int n0, int FR, int ws,
@@ -839,6 +791,7 @@ extern "C" int b2a_spectral_f32(const float* x, int64_t rows, int64_t T, int n_f
   p.mel_packed_len = (mel_out && mel_packed_len > 0) ? mel_packed_len : 0;
   p.center = 1; p.origin = -(n_fft / 2) - pad; p.row_origin = nullptr;
   p.rows_per_gain = gain ? rows_per_gain : 1; p.post = post; p.post_eps = post_eps; p.post_power = post_power;
+  if (tc_supported(p)) return launch_tc(p, stream);  // tcgen05 path (spectral_tc.cu): n_fft 2048 log-mel / mel
   switch (n_fft) {
     case 32: return launch<4>(p, stream);
     case 64: return launch_warp<5>(p, stream);

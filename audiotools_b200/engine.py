@@ -251,6 +251,15 @@ class Engine:
             self._packed_cache[key] = 4 * total
         return self._packed_cache[key]
 
+    def spectral_kernel_name(self, n_fft: int, hop: int, want_mel: bool = True, want_stft: bool = False) -> str:
+        """Name of the kernel ``spectral`` launches for this geometry (bench.py / profiles label their numbers with it)."""
+        if self.lib.b2a_spectral_uses_tensor_cores(int(n_fft), int(hop), int(want_mel), int(want_stft)):
+            return "spectral_tc_kernel"
+        if n_fft in (32, 4096):
+            return f"spectral_kernel<{int(math.log2(n_fft)) - 1}>"
+        mode = 2 if (want_stft and want_mel) else (1 if want_stft else 0)
+        return f"spectral_warp_kernel<{int(math.log2(n_fft)) - 1},{mode}>"
+
     @staticmethod
     def num_frames(T: int, n_fft: int, hop: int, pad: int = 0, right_pad: int = 0, drop_edge: int = 0) -> int:
         """``b2a_stft_num_frames`` evaluated on the host (same integer formula; tests/test_abi.py checks they agree):

@@ -205,6 +205,14 @@ size_t b2a_time_stretch_workspace_bytes(int64_t rows, int64_t T, int sr, double 
 int b2a_time_stretch_f32(const float* x, int64_t rows, int64_t T, int sr, double factor, float* out, void* ws,
                          size_t ws_bytes, void* stream);
 
+/* 1 when b2a_spectral_f32 runs a launch of this geometry on the tensor-core kernel (csrc/spectral_tc.cu: tcgen05.mma,
+ * accumulators in tensor memory): window_length 2048, hop <= 512, mel / log-mel output without the complex STFT, and
+ * the environment variable B2A_SPECTRAL_TC not set to 0.  Every other launch uses the FP32 kernels of spectral.cu. */
+int b2a_spectral_uses_tensor_cores(int n_fft, int hop, int want_mel, int want_stft);
+/* Switch the tensor-core path on / off for this process (A/B measurements, parity tests of both kernels); returns the
+ * previous setting. */
+int b2a_spectral_tc_enable(int on);
+
 /* ---- one-sided statistics exchange between the GPUs of a node (NVLink peer memory) --------------------
  * The path shards by batch item with no data-path collective; the one exchange is the per-item loudness vector for
  * whole-batch statistics (the reference has no multi-GPU code of its own: SURVEY.md 8e).  Every rank owns a small

@@ -523,3 +523,49 @@ def test_fftconv_random_geometries(eng):
             y = Fn.conv1d(xv[:, None, :], taps[b].flip(0).reshape(1, 1, Lf))[:, 0, :T]
             ref = (x[b] - y) if sub else y
             assert rel_err(out[b], ref) < 5e-5, (B, C, T, Lf, mode, sub)
+
+
+# ------------------------------------------------------------------------------------------
+# tensor-core spectral kernel (csrc/spectral_tc.cu) under the simulator: tensor memory and tcgen05.mma are emulated
+# (same operand bytes, same layouts), everything else is the shipped source
+# ------------------------------------------------------------------------------------------
+from tests.conftest import elementwise_ok as _elementwise_ok  # noqa: E402
+
+
+@pytest.mark.parametrize("hop,T,n_mels", [(512, 20000, 128), (256, 9000, 80), (300, 7000, 64), (510, 12000, 128)])
+def test_spectral_tc_matches_fp32_kernel_and_reference(eng, hop, T, n_mels):
+    sr = 44100
+    g = torch.Generator().manual_seed(hop)
+    x = 0.1 * torch.randn(3, 2, T, generator=g)
+    x[1] *= 1e-4                                                     # a very quiet item (fp16 range handling)
+    x[2, 0] = 0.5 + 0.3 * torch.sin(torch.arange(T) * 0.013)          # DC offset + low tone: leakage, small bins
+    x[2, 1, : T // 2] = 0.0                                           # silent stretch: all-zero tiles
+    fb, lo, hi = _mel_tables(sr, 2048, n_mels)
+    w = sp.get_window("hann" if hop != 300 else "sqrt_hann", 2048)
+    gain = torch.tensor([0.7, -3.0, 1.5])
+    assert eng.lib.b2a_spectral_uses_tensor_cores(2048, hop, 1, 0) == 1
+    assert eng.spectral_kernel_name(2048, hop) == "spectral_tc_kernel"
+    kw = dict(gain=gain, want_scaled=True, mel_fb=fb, mel_lo=lo, mel_hi=hi, want_stft=False)
+    tc = eng.spectral(x, 2048, hop, w, **kw)
+    prev = eng.lib.b2a_spectral_tc_enable(0)
+    try:
+        assert eng.spectral_kernel_name(2048, hop) == "spectral_warp_kernel<10,0>"
+        fp = eng.spectral(x, 2048, hop, w, **kw)
+    finally:
+        eng.lib.b2a_spectral_tc_enable(prev)
+    assert torch.equal(tc["scaled"], fp["scaled"])
+    ref = sp.mel_spectrogram(x * gain[:, None, None], sr, n_mels, window_length=2048, hop_length=hop,
+                             window_type="hann" if hop != 300 else "sqrt_hann")
+    assert tc["mel"].shape == ref.shape
+    for b in range(3):  # per item: the quiet item must be as accurate, relative to itself, as the loud one
+        assert rel_err(tc["mel"][b], ref[b]) < 2e-5, b
+        assert _elementwise_ok(tc["mel"][b], ref[b], 1e-4, 2e-6), b  # measured: 5e-7 of the frame max (FP32 kernel: 2.5e-7)
+        assert _elementwise_ok(fp["mel"][b], ref[b], 1e-4, 2e-6), b
+    lg = eng.spectral(x, 2048, hop, w, mel_fb=fb, mel_lo=lo, mel_hi=hi, post=_lib.POST_LOG10, post_eps=1e-5,
+                      post_power=2.0, want_stft=False)["mel"]
+    ref_log = sp.log_mel(sp.mel_spectrogram(x, sr, n_mels, window_length=2048, hop_length=hop,
+                                            window_type="hann" if hop != 300 else "sqrt_hann"))
+    # log10 units.  Items 0 / 1 (noise-like: every band well above the transform's error floor): tight; item 2 has
+    # bands 120 dB below its DC line, where ANY fp32 transform differs from another by more than the value itself --
+    # there the linear criterion above is the meaningful one
+    assert (lg[:2] - ref_log[:2]).abs().max() < 2e-4

@@ -58,6 +58,7 @@ SIGNATURES = {
                                        c_float, c_float, c_void_p]),
     "b2a_spec_rotate_f32": (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_int, c_void_p]),
     "b2a_spec_mask_low_f32": (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_float, c_float, c_float, c_void_p, c_void_p]),
+    "b2a_pitch_shift_num_frames": (c_int, [c_int64, c_int, c_float]),
     "b2a_time_stretch_out_len": (c_int64, [c_int64, c_double]),
     "b2a_time_stretch_workspace_bytes": (c_size_t, [c_int64, c_int64, c_int, c_double]),
     "b2a_time_stretch_f32": (c_int, [c_void_p, c_int64, c_int64, c_int, c_double, c_void_p, c_void_p, c_size_t, c_void_p]),

@@ -481,6 +481,13 @@ extern "C" int b2a_pitch_shift_f32(const float* x, int64_t rows, int64_t T, int 
   return b2a_pitch_shift_multi_f32(x, rows, T, sr, &semitones, 1, nullptr, out, ws, ws_bytes, stream);
 }
 
+extern "C" int b2a_pitch_shift_num_frames(int64_t T, int sr, float semitones) {
+  if (T < 1 || sr < 1 || !(fabsf(semitones) <= 24.f)) return -1;
+  Geo g;
+  geometry(1, T, sr, semitones, &g);
+  return g.J;
+}
+
 /* EffectMixin.time_stretch (ref:audiotools/core/effects.py:279-309; SoX `tempo factor` there): the WSOLA stages of the
  * pitch shifter on their own -- speed the signal up by `factor` (duration / factor), pitch unchanged. */
 static float stretch_semitones(double factor) { return (float)(12.0 * log2(1.0 / factor)); }

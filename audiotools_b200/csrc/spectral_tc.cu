@@ -25,7 +25,7 @@
 //   projection + post-op + coalesced tile store are those of spectral.cu.
 //
 // Per 16-frame tile: 1 TMA-staged span (19 bulk copies, padded per 512 samples -> conflict-free strided reads),
-// 384 tcgen05.mma (M 128, N 16, K 16), ~1100 warp instructions per frame on the CUDA cores (2400 in the FP32 kernel).
+// 48 tcgen05.mma (M 128, N 128 = 8 groups x 16 frames, K 16).
 #ifndef B2A_SIM
 #include <cuda_fp16.h>
 #endif
@@ -182,14 +182,19 @@ __device__ __forceinline__ uint64_t smem_desc(uint32_t saddr, uint32_t lbo_bytes
   return d;
 }
 #endif
-// D[128 x 16] (+)= A[128 x 16] (TMEM columns a_col .. a_col + 8, two halves per column) . B[16 x 16]^T (shared
-// memory, canonical no-swizzle K-major: 8-row x 16-byte core matrices, LBO between the two K chunks, SBO between
-// the two 8-frame groups); fp16 in, fp32 accumulate.  One thread issues it.
+// D[128 x NN] (+)= A[128 x 16] (TMEM columns a_col .. a_col + 8, two halves per column) . B[NN x 16]^T (shared
+// memory, canonical no-swizzle K-major: 8-row x 16-byte core matrices, LBO = 128 B between the two K chunks, SBO =
+// 2048 B between consecutive 8-row groups); fp16 in, fp32 accumulate.  B row n' = 16 (group) + frame: the groups'
+// operand regions are 4096 B apart = two row groups, so ONE instruction with NN = 16 * (number of groups) multiplies
+// the same F slice with every group's frames and lands in D columns 16 b + n -- measured (tests/probes/
+// tc_latency_probe.cu): a tcgen05.mma costs ~60 cycles to issue whatever its N, so 48 wide instructions per tile
+// replace 384 narrow ones.  One thread issues it.
+template <int NN>
 __device__ __forceinline__ void mma_ts(uint32_t base, int d_col, int a_col, const unsigned char* b_smem, int accumulate) {
 #ifdef B2A_SIM
   (void)base;
   for (int m = 0; m < 128; ++m)
-    for (int n = 0; n < FR; ++n) {
+    for (int n = 0; n < NN; ++n) {
       float acc = 0.f;
       if (accumulate) memcpy(&acc, &g_tmem[m][d_col + n], 4);
       for (int k = 0; k < 16; ++k) {
@@ -202,11 +207,22 @@ __device__ __forceinline__ void mma_ts(uint32_t base, int d_col, int a_col, cons
       memcpy(&g_tmem[m][d_col + n], &acc, 4);
     }
 #else
-  constexpr uint32_t idesc = (1u << 4) | ((uint32_t)(FR >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);  // f16 x f16 -> f32
+  constexpr uint32_t idesc = (1u << 4) | ((uint32_t)(NN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);  // f16 x f16 -> f32
   const uint64_t db = smem_desc((uint32_t)__cvta_generic_to_shared(b_smem), 128, 2048);
   asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
                "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n}\n" ::"r"(base + (uint32_t)d_col),
                "r"(base + (uint32_t)a_col), "l"(db), "r"(idesc), "r"((uint32_t)accumulate) : "memory");
+#endif
+}
+// one lane of a converged warp (warp-uniform control flow around it: the tcgen05.mma it guards is issued once, with
+// no per-lane serialisation loop)
+__device__ __forceinline__ bool elect_one() {
+#ifdef B2A_SIM
+  return (threadIdx.x & 31) == 0;
+#else
+  uint32_t pred;
+  asm volatile("{\n.reg .pred p;\nelect.sync _|p, 0xffffffff;\nselp.u32 %0, 1, 0, p;\n}\n" : "=r"(pred));
+  return pred != 0;
 #endif
 }
 __device__ __forceinline__ void mma_commit(unsigned long long* bar) {
@@ -419,64 +435,76 @@ __global__ void __launch_bounds__(THREADS, 1) spectral_tc_kernel(const B2A_GRID_
     }
     __syncthreads();
 
-    // ---- (3) windowed frames -> fp16 (hi, lo) B operand.  Warp item = (nh, ac): frames 8 nh + (lane & 7), a in
-    //      [8 ac, +8), groups b = 4 (lane >> 3) + e.  Sample of (n, a, b) = span[n hop + 16 a + b].
+    // ---- (3) + (4): windowed frames -> fp16 (hi, lo) B operand, in two halves of 8 groups; the MMAs of a half are
+    //      issued (warp 0, one elected lane) as soon as the half is in shared memory, so the tensor core works on groups
+    //      0-7 while the CUDA cores convert groups 8-15.  Unit u (64 per half) = (nh, ac, gq'): frames 8 nh + (lane & 7),
+    //      a in [8 ac, +8), groups b = 4 (2 half + gq') + e.  Sample of (n, a, b) = span[n hop + 16 a + b].
+    const bool blk_aligned = (hop & (BLK - 1)) == 0;  // every frame starts on a padding granule
 #pragma unroll 1
-    for (int item = warp; item < 32; item += NWARP) {
-      const int nh = item >> 4, ac = item & 15;
-      const int n = 8 * nh + (lane & 7), gq = lane >> 3;
-      const int o0 = 128 * ac + 4 * gq;
-      const int i0 = n * hop + o0;
-      uint32_t hw[4][4], lw[4][4];  // [e = b - 4 gq][pair of a]
+    for (int half = 0; half < 2; ++half) {
+      {
+        const int u = 4 * warp + (lane >> 3);
+        const int nh = u >> 5, ac = (u >> 1) & 15, gq = 2 * half + (u & 1);
+        const int n = 8 * nh + (lane & 7);
+        const int o0 = 128 * ac + 4 * gq;
+        const int i0 = n * hop + o0;
+        // all 8 loads of a unit fall into one 512-sample granule when the frames start on granule boundaries
+        const float* sbase = sp + (blk_aligned ? pad_idx(i0) : 0);
+        uint32_t hw[4][4], lw[4][4];  // [e = b - 4 gq][pair of a]
 #pragma unroll
-      for (int jp = 0; jp < 4; ++jp) {
-        float4 pr[2];
+        for (int jp = 0; jp < 4; ++jp) {
+          float4 pr[2];
 #pragma unroll
-        for (int e2 = 0; e2 < 2; ++e2) {
-          const int j = 2 * jp + e2;
-          float4 xv;
-          const int i = i0 + 16 * j;
-          if ((hop & 3) == 0) {
-            xv = *reinterpret_cast<const float4*>(sp + pad_idx(i));
-          } else {
-            xv = make_float4(sp[pad_idx(i)], sp[pad_idx(i + 1)], sp[pad_idx(i + 2)], sp[pad_idx(i + 3)]);
+          for (int e2 = 0; e2 < 2; ++e2) {
+            const int j = 2 * jp + e2;
+            float4 xv;
+            if (blk_aligned) {
+              xv = *reinterpret_cast<const float4*>(sbase + 16 * j);
+            } else if ((hop & 3) == 0) {
+              xv = *reinterpret_cast<const float4*>(sp + pad_idx(i0 + 16 * j));
+            } else {
+              const int i = i0 + 16 * j;
+              xv = make_float4(sp[pad_idx(i)], sp[pad_idx(i + 1)], sp[pad_idx(i + 2)], sp[pad_idx(i + 3)]);
+            }
+            const float4 wv = *reinterpret_cast<const float4*>(wsc + o0 + 16 * j);
+            pr[e2] = make_float4(xv.x * wv.x, xv.y * wv.y, xv.z * wv.z, xv.w * wv.w);
           }
-          const float4 wv = *reinterpret_cast<const float4*>(wsc + o0 + 16 * j);
-          pr[e2] = make_float4(xv.x * wv.x, xv.y * wv.y, xv.z * wv.z, xv.w * wv.w);
+          split2(pr[0].x, pr[1].x, hw[0][jp], lw[0][jp]);
+          split2(pr[0].y, pr[1].y, hw[1][jp], lw[1][jp]);
+          split2(pr[0].z, pr[1].z, hw[2][jp], lw[2][jp]);
+          split2(pr[0].w, pr[1].w, hw[3][jp], lw[3][jp]);
         }
-        split2(pr[0].x, pr[1].x, hw[0][jp], lw[0][jp]);
-        split2(pr[0].y, pr[1].y, hw[1][jp], lw[1][jp]);
-        split2(pr[0].z, pr[1].z, hw[2][jp], lw[2][jp]);
-        split2(pr[0].w, pr[1].w, hw[3][jp], lw[3][jp]);
-      }
-      unsigned char* dst = bop + (4 * gq) * 4096 + nh * 2048 + ac * 128 + (lane & 7) * 16;
+        unsigned char* dst = bop + (4 * gq) * 4096 + nh * 2048 + ac * 128 + (lane & 7) * 16;
 #pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        *reinterpret_cast<int4*>(dst + e * 4096) = make_int4((int)hw[e][0], (int)hw[e][1], (int)hw[e][2], (int)hw[e][3]);
-        *reinterpret_cast<int4*>(dst + B_PART + e * 4096) = make_int4((int)lw[e][0], (int)lw[e][1], (int)lw[e][2], (int)lw[e][3]);
+        for (int e = 0; e < 4; ++e) {
+          *reinterpret_cast<int4*>(dst + e * 4096) = make_int4((int)hw[e][0], (int)hw[e][1], (int)hw[e][2], (int)hw[e][3]);
+          *reinterpret_cast<int4*>(dst + B_PART + e * 4096) = make_int4((int)lw[e][0], (int)lw[e][1], (int)lw[e][2], (int)lw[e][3]);
+        }
+      }
+      fence_async_smem();  // generic-proxy writes of the operand -> visible to the tensor core (async proxy)
+      tc_fence_before();
+      __syncthreads();
+      if (warp == 0) {
+        // 3 products x 8 k-steps, each ONE instruction over the 8 groups of the half (N = 128 = 8 groups x 16 frames)
+        tc_fence_after();
+        if (elect_one()) {
+          const unsigned char* bh0 = bop + (8 * half) * 4096;
+#pragma unroll
+          for (int prod = 0; prod < 3; ++prod) {
+            const int a_col = (prod == 2) ? TM_F2 : TM_F1;
+            const unsigned char* bp = bh0 + (prod == 1 ? B_PART : 0);
+#pragma unroll
+            for (int ks = 0; ks < 8; ++ks)
+              mma_ts<8 * FR>(tmb, TM_D + FR * 8 * half, a_col + 8 * ks, bp + ks * 256, (prod | ks) != 0);
+          }
+          if (half == 1) mma_commit(&s_bar_mma);
+        }
+        __syncwarp();
       }
     }
-    fence_async_smem();  // generic-proxy writes of the operand -> visible to the tensor core (async proxy)
-    tc_fence_before();
-    __syncthreads();
-
-    // ---- (4) 16 groups x 3 products x 8 k-steps of tcgen05.mma, issued by one thread; everybody else streams the
-    //      scaled waveform out meanwhile
-    if (tid == 0) {
-      tc_fence_after();
-#pragma unroll 1
-      for (int b = 0; b < NG; ++b) {
-        const unsigned char* bh = bop + b * 4096;
-#pragma unroll
-        for (int ks = 0; ks < 8; ++ks) mma_ts(tmb, TM_D + FR * b, TM_F1 + 8 * ks, bh + ks * 256, ks > 0);
-#pragma unroll
-        for (int ks = 0; ks < 8; ++ks) mma_ts(tmb, TM_D + FR * b, TM_F1 + 8 * ks, bh + B_PART + ks * 256, 1);
-#pragma unroll
-        for (int ks = 0; ks < 8; ++ks) mma_ts(tmb, TM_D + FR * b, TM_F2 + 8 * ks, bh + ks * 256, 1);
-      }
-      mma_commit(&s_bar_mma);
-    }
-    if (p.y_out) {  // y = g x for the samples this tile owns ([n0 hop, (n0 + FR) hop), the last tile up to T)
+    // everybody but the issuing warp streams the scaled waveform out while the tensor core works
+    if (p.y_out && warp != 0) {  // y = g x for the samples this tile owns ([n0 hop, (n0 + FR) hop), the last tile up to T)
+      const int wt = tid - 32, WT = THREADS - 32;
       const int own_lo = n0 * hop;
       const int own_hi = (tile == p.n_tiles - 1) ? p.T : min(p.T, (n0 + FR) * hop);
       float* yr = p.y_out + (size_t)rw * (size_t)p.T;
@@ -484,17 +512,17 @@ __global__ void __launch_bounds__(THREADS, 1) spectral_tc_kernel(const B2A_GRID_
       const bool vec = (((lo - ws) & 3) == 0) && ((((uintptr_t)(yr + lo)) & 15) == 0);
       if (vec) {
         const int n4 = (hi - lo) >> 2;
-        for (int i = tid; i < n4; i += THREADS) {
+        for (int i = wt; i < n4; i += WT) {
           float4 v = *reinterpret_cast<const float4*>(sp + pad_idx(lo - ws + 4 * i));
           v.x *= g; v.y *= g; v.z *= g; v.w *= g;
           st_stream4(yr + lo + 4 * i, v);
         }
-        for (int w = lo + 4 * n4 + tid; w < hi; w += THREADS) yr[w] = sp[pad_idx(w - ws)] * g;
+        for (int w = lo + 4 * n4 + wt; w < hi; w += WT) yr[w] = sp[pad_idx(w - ws)] * g;
       } else {
-        for (int w = lo + tid; w < hi; w += THREADS) yr[w] = sp[pad_idx(w - ws)] * g;
+        for (int w = lo + wt; w < hi; w += WT) yr[w] = sp[pad_idx(w - ws)] * g;
       }
       const float* xr = p.x + (size_t)rw * (size_t)p.T;
-      for (int w = max(own_lo, ws + p.span) + tid; w < own_hi; w += THREADS) yr[w] = __ldg(xr + w) * g;
+      for (int w = max(own_lo, ws + p.span) + wt; w < own_hi; w += WT) yr[w] = __ldg(xr + w) * g;
     }
     __syncthreads();  // the span is dead: the next tile's samples stream in underneath the MMAs and the epilogue
     {
@@ -506,7 +534,6 @@ __global__ void __launch_bounds__(THREADS, 1) spectral_tc_kernel(const B2A_GRID_
     tc_fence_after();
 
     // ---- (5) second stage in registers: thread (row, frame pair) -> one frame's 16 bins k = +-c + 128 d
-    const float mscale = inv_scale;
 #pragma unroll 1
     for (int pp = (warp >> 2); pp < FR / 2; pp += NWARP / 4) {
       float v0[NG], v1[NG];
@@ -520,7 +547,8 @@ __global__ void __launch_bounds__(THREADS, 1) spectral_tc_kernel(const B2A_GRID_
         const float mine = ri ? v1[b] : v0[b];
         const float other = ri ? v0[b] : v1[b];
         const float recv = __shfl_xor_sync(0xffffffffu, other, 1);
-        z[b] = make_float2(mine, (c == 0) ? other : recv);  // c = 0 / 64: both frames of the pair in one complex DFT
+        z[b] = make_float2(mine, recv);
+        if (c == 0) z[b].y = other;  // c = 0 / 64: both frames of the pair in one complex DFT (lanes 0, 1 of 4 warps)
       }
 #pragma unroll
       for (int b = 1; b < NG; ++b) z[b] = cmul(z[b], tw[b * 128 + row]);
@@ -531,12 +559,12 @@ __global__ void __launch_bounds__(THREADS, 1) spectral_tc_kernel(const B2A_GRID_
         float* xf = xs + f * XBS;
         float* P1 = ri ? xf - c : xf + c;  // d = 1..7  -> +-c + 128 d
         float* P2 = ri ? xf + c : xf - c;  // d = 9..15 -> -+c + 128 (16 - d)
-        xf[c] = mscale * fast_sqrt(fmaf(o[0].x, o[0].x, o[0].y * o[0].y));
+        xf[c] = fast_sqrt(fmaf(o[0].x, o[0].x, o[0].y * o[0].y));
 #pragma unroll
-        for (int d = 1; d < 8; ++d) P1[128 * d] = mscale * fast_sqrt(fmaf(o[d].x, o[d].x, o[d].y * o[d].y));
-        xf[1024 - c] = mscale * fast_sqrt(fmaf(o[8].x, o[8].x, o[8].y * o[8].y));
+        for (int d = 1; d < 8; ++d) P1[128 * d] = fast_sqrt(fmaf(o[d].x, o[d].x, o[d].y * o[d].y));
+        xf[1024 - c] = fast_sqrt(fmaf(o[8].x, o[8].x, o[8].y * o[8].y));
 #pragma unroll
-        for (int d = 9; d < 16; ++d) P2[128 * (16 - d)] = mscale * fast_sqrt(fmaf(o[d].x, o[d].x, o[d].y * o[d].y));
+        for (int d = 9; d < 16; ++d) P2[128 * (16 - d)] = fast_sqrt(fmaf(o[d].x, o[d].x, o[d].y * o[d].y));
       } else {
         // Y = DFT(u + i v) of two real-input problems u, v (the two frames of the pair):
         //   row 0 (c = 0):  U[d] = (Y[d] + conj Y[16-d]) / 2, V[d] = (Y[d] - conj Y[16-d]) / 2i  -> bins 128 d, d = 0..8,
@@ -553,8 +581,8 @@ __global__ void __launch_bounds__(THREADS, 1) spectral_tc_kernel(const B2A_GRID_
           const float2 U = make_float2(0.5f * (yd.x + yn.x), 0.5f * (yd.y - yn.y));
           const float2 V = make_float2(0.5f * (yd.y + yn.y), 0.5f * (yn.x - yd.x));
           if (d < 8 || !ri) {
-            xu[koff + 128 * d] = mscale * sqrtf(fmaf(U.x, U.x, U.y * U.y));
-            xv[koff + 128 * d] = mscale * sqrtf(fmaf(V.x, V.x, V.y * V.y));
+            xu[koff + 128 * d] = sqrtf(fmaf(U.x, U.x, U.y * U.y));
+            xv[koff + 128 * d] = sqrtf(fmaf(V.x, V.x, V.y * V.y));
           }
         }
       }
@@ -571,7 +599,7 @@ __global__ void __launch_bounds__(THREADS, 1) spectral_tc_kernel(const B2A_GRID_
       const int fl = lane & 7, jq = lane >> 3, w8 = warp & 7;
       const int f = 8 * (warp >> 3) + fl;
       const float lscale = p.post_power * 0.30102999566398120f;
-      const float ga = fabsf(g);
+      const float ga = fabsf(g) * inv_scale;  // |X| is stored in the tile's scaled units: undo S and the 64 of F here
       const float* xf = xs + f * XBS;
       if (packed) {
         const float4* mpk4 = reinterpret_cast<const float4*>(mpk);

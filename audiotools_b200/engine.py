@@ -563,10 +563,13 @@ class Engine:
     # ------------------------------------------------------------------ pitch shift
     MAX_PITCH_GROUPS = 8
 
-    def pitch_shift(self, x: torch.Tensor, sample_rate: int, n_semitones, quick: bool = True) -> torch.Tensor:
+    def pitch_shift(self, x: torch.Tensor, sample_rate: int, n_semitones, quick: bool = True,
+                    return_positions: bool = False):
         """Shift the pitch of x [B, C, T] keeping T (ref:audiotools/core/effects.py:247-277).  ``n_semitones`` is one
         value for the batch (the reference's API) or one value per item (host list / tensor with B entries): all
-        items go through the same launches, grouped by their shift; a shift of 0 copies the item."""
+        items go through the same launches, grouped by their shift; a shift of 0 copies the item.
+        ``return_positions`` (single shift only; parity tests): also return the WSOLA splice positions the search
+        kernel chose, int32 [rows, J] -- the integer part of the result that must match the oracle exactly."""
         x = self._prep(x, "x")
         T = x.shape[-1]
         rows = x.numel() // T
@@ -601,10 +604,15 @@ class Engine:
                                                 _dptr(row_group), _dptr(out), _dptr(ws), ws_bytes, self._stream(x))
         self.lib.check(rc)
         self.launches += 4
+        if return_positions:
+            assert row_group is None, "return_positions: one shift for the whole batch"
+            jmax = self.lib.b2a_pitch_shift_num_frames(T, int(sample_rate), float(sem[0]))
+            pos = ws[: rows * jmax * 4].view(torch.int32).reshape(rows, jmax).clone()
+            return out, pos
         return out
 
 
-    def time_stretch(self, x: torch.Tensor, sample_rate: int, factor: float) -> torch.Tensor:
+    def time_stretch(self, x: torch.Tensor, sample_rate: int, factor: float, return_positions: bool = False):
         """Speed x [B, C, T] up by ``factor`` without changing its pitch -> [B, C, round(T / factor)]
         (ref:audiotools/core/effects.py:279-309; SoX ``tempo`` there): the WSOLA stages of the pitch shifter."""
         x = self._prep(x, "x")
@@ -621,6 +629,10 @@ class Engine:
                                            self._stream(x))
         self.lib.check(rc)
         self.launches += 4 if factor != 1.0 else 1
+        if return_positions and factor != 1.0:
+            st = float(np.float32(12.0 * math.log2(1.0 / factor)))
+            jmax = self.lib.b2a_pitch_shift_num_frames(T, int(sample_rate), st)
+            return out, ws[: rows * jmax * 4].view(torch.int32).reshape(rows, jmax).clone()
         return out
 
 

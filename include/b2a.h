@@ -200,6 +200,10 @@ int b2a_pitch_shift_multi_f32(const float* x, int64_t rows, int64_t T, int sr, c
 /* EffectMixin.time_stretch (audiotools/core/effects.py:279-309; SoX `tempo factor` + `rate` there): the WSOLA stages of
  * the pitch shifter on their own: out [rows, out_len] with out_len = b2a_time_stretch_out_len(T, factor) = round(T / factor),
  * pitch unchanged; factor in [0.25, 4], factor == 1 copies. */
+/* number of WSOLA frames J of a row for this shift: the splice positions chosen by the search are the first
+ * rows * J int32 of the workspace after the call (row-major [rows, J]); exposed so that tests can compare them with
+ * the oracle (oracle/pitch_spec.py) exactly */
+int b2a_pitch_shift_num_frames(int64_t T, int sr, float semitones);
 int64_t b2a_time_stretch_out_len(int64_t T, double factor);
 size_t b2a_time_stretch_workspace_bytes(int64_t rows, int64_t T, int sr, double factor);
 int b2a_time_stretch_f32(const float* x, int64_t rows, int64_t T, int sr, double factor, float* out, void* ws,

@@ -721,3 +721,26 @@ def test_cfg2_full_size_tc_strided_oracle(at, sp):
         ref = sp.log_mel(sp.mel_spectrogram(y_ref, 44100, 128, window_length=2048, hop_length=512, window_type="hann"))
         assert rel_err(y[i:i + 1].cpu(), y_ref) < TOL
         assert (logmel[i:i + 1].cpu() - ref).abs().max().item() < 2e-4, i
+
+
+# ------------------------------------------------------------------------------------------
+# pitch_shift / time_stretch vs the independent specification oracle (oracle/pitch_spec.py -> tests/golden/pitch_golden.npz)
+# ------------------------------------------------------------------------------------------
+def test_pitch_shift_and_time_stretch_match_spec_oracle(at):
+    import os
+
+    from audiotools_b200.engine import get_engine
+    from tests.golden import make_golden_pitch as mg
+    from tests.test_sim_kernels import _check_pitch_vs_golden
+
+    eng = get_engine()
+    g = np.load(os.path.join(os.path.dirname(mg.__file__), "pitch_golden.npz"))
+    x = torch.from_numpy(g["x"])[:, None, :].to(DEV)
+    for st in mg.SHIFTS:
+        _check_pitch_vs_golden(lambda: tuple(t.cpu().reshape(3, -1) for t in eng.pitch_shift(x, mg.SR, st, return_positions=True)),
+                               g, f"pitch_{st:g}")
+        sig = at.AudioSignal(x.clone(), mg.SR).pitch_shift(st)  # the public method gives the same numbers
+        assert torch.equal(sig.audio_data, eng.pitch_shift(x, mg.SR, st))
+    for fac in mg.FACTORS:
+        _check_pitch_vs_golden(lambda: tuple(t.cpu().reshape(3, -1) for t in eng.time_stretch(x, mg.SR, fac, return_positions=True)),
+                               g, f"stretch_{fac:g}")

@@ -229,3 +229,31 @@ def test_spectral_masks_match_reference(golden_spec):
     close(Y[2:], g["shift_stft"], 2e-5)
     close(sp.istft(Y, 16000, 16000), g["shift_audio"], 2e-5)
     close(sp.istft(sp.shift_phase(X, torch.from_numpy(g["corrupt_in"])), 16000, 16000), g["corrupt_audio"], 2e-5)
+
+
+# ------------------------------------------------------------------------------------------
+# pitch_shift / time_stretch specification oracle (oracle/pitch_spec.py) vs its committed vectors
+# ------------------------------------------------------------------------------------------
+def test_pitch_oracle_reproduces_committed_vectors():
+    import os
+
+    from oracle import pitch_spec as ps
+    from tests.golden import make_golden_pitch as mg
+
+    g = np.load(os.path.join(os.path.dirname(mg.__file__), "pitch_golden.npz"))
+    x = mg.make_input()
+    assert np.array_equal(x, g["x"])  # the seeded input is reproducible
+    y, pos, _ = ps.pitch_shift_row(x[0], mg.SR, 2.0)
+    assert np.array_equal(pos, g["pitch_2_pos"][0])
+    assert np.abs(y - g["pitch_2_y"][0]).max() < 1e-6
+    y, pos, _ = ps.time_stretch_row(x[2], mg.SR, 0.8)
+    assert np.array_equal(pos, g["stretch_0.8_pos"][2]) and len(y) == 30000
+    assert np.abs(y - g["stretch_0.8_y"][2]).max() < 1e-6
+    # properties of the specification itself: length kept, pitch ratio 2^(n/12), unit DC gain
+    t = np.arange(mg.T) / mg.SR
+    tone = (0.5 * np.sin(2 * np.pi * 440 * t)).astype(np.float32)
+    y, _, _ = ps.pitch_shift_row(tone, mg.SR, 3.0)
+    spec = np.abs(np.fft.rfft(y * np.hanning(mg.T)))
+    assert abs(spec.argmax() * mg.SR / mg.T - 440 * 2 ** (3 / 12)) < 2.0
+    dc, _, _ = ps.pitch_shift_row(np.full(9000, 0.25, np.float32), 8000, -5.0)
+    assert np.abs(dc[600:-1200] - 0.25).max() < 1e-6  # (the last frames are clamped to the end of the row)

@@ -569,3 +569,37 @@ def test_spectral_tc_matches_fp32_kernel_and_reference(eng, hop, T, n_mels):
     # bands 120 dB below its DC line, where ANY fp32 transform differs from another by more than the value itself --
     # there the linear criterion above is the meaningful one
     assert (lg[:2] - ref_log[:2]).abs().max() < 2e-4
+
+
+# ------------------------------------------------------------------------------------------
+# pitch_shift / time_stretch against the independent specification oracle ("compared with nothing
+# independent"): exact splice positions wherever the arg-max is decided by more than float32 rounding, waveform 1e-4
+# ------------------------------------------------------------------------------------------
+def _check_pitch_vs_golden(run, g, key, tol=1e-4, rows=slice(None)):
+    """run() -> (y [rows, L] float32 tensor, positions [rows, J] int32 tensor)."""
+    y, pos = run()
+    ref_y, ref_pos, margin = g[key + "_y"][rows], g[key + "_pos"][rows], g[key + "_margin"][rows]
+    assert tuple(y.shape) == ref_y.shape and tuple(pos.shape) == ref_pos.shape  # length and frame count exact
+    pos = pos.numpy()
+    decided = margin > 1e-5  # correlation margin relative to the size of the summed terms; fp32 sums resolve 1e-6
+    assert decided.mean() > 0.95
+    assert np.array_equal(pos[decided], ref_pos[decided])
+    same = (pos == ref_pos).all(axis=1)  # rows whose every splice agrees (all of them unless a near-tie flipped)
+    assert same.mean() >= 0.5
+    err = np.abs(y.numpy()[same] - ref_y[same]).max() / np.abs(ref_y[same]).max()
+    assert err < tol, err
+    return same
+
+
+def test_pitch_shift_and_time_stretch_match_spec_oracle(eng):
+    import os
+
+    from tests.golden import make_golden_pitch as mg
+
+    g = np.load(os.path.join(os.path.dirname(mg.__file__), "pitch_golden.npz"))
+    x = torch.from_numpy(g["x"][:2])[:, None, :]  # the simulator runs every CUDA thread as a host thread: 2 rows
+    for st in (2.0, -2.0):
+        _check_pitch_vs_golden(lambda: tuple(t.reshape(2, -1) for t in eng.pitch_shift(x, mg.SR, st, return_positions=True)),
+                               g, f"pitch_{st:g}", rows=slice(0, 2))
+    _check_pitch_vs_golden(lambda: tuple(t.reshape(2, -1) for t in eng.time_stretch(x, mg.SR, 1.25, return_positions=True)),
+                           g, "stretch_1.25", rows=slice(0, 2))

@@ -216,6 +216,8 @@ def run_ours(args):
     from audiotools_b200.engine import get_engine
 
     eng = get_engine()
+    if args.tc:  # A/B switch: the tensor-core spectral kernel (csrc/spectral_tc.cu) instead of the default FP32 kernel
+        eng.lib.b2a_spectral_tc_enable(1)
     B = args.batch
     NBUF = 3
     xs = [make_batch(B, 100 + 7 * rank + i, dev) for i in range(NBUF)]
@@ -494,6 +496,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--preroll", type=float, default=1.0, help="seconds of identical untimed steps before the barrier")
     ap.add_argument("--sustain", type=float, default=2.0, help="seconds of the sustained loop after the timed steps")
+    ap.add_argument("--tc", action="store_true", help="use the opt-in tensor-core spectral kernel (A/B measurements)")
     ap.add_argument("--e2e-features-only", action="store_true",
                     help="e2e leg copies back log-mel + LUFS only (not the normalised waveform)")
     args = ap.parse_args()

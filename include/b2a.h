@@ -211,7 +211,9 @@ int b2a_time_stretch_f32(const float* x, int64_t rows, int64_t T, int sr, double
 
 /* 1 when b2a_spectral_f32 runs a launch of this geometry on the tensor-core kernel (csrc/spectral_tc.cu: tcgen05.mma,
  * accumulators in tensor memory): window_length 2048, hop <= 512, mel / log-mel output without the complex STFT, and
- * the environment variable B2A_SPECTRAL_TC not set to 0.  Every other launch uses the FP32 kernels of spectral.cu. */
+ * the path switched on (environment variable B2A_SPECTRAL_TC=1, or b2a_spectral_tc_enable(1)).  It is opt-in because
+ * the FP32 warp kernel of spectral.cu is currently the faster of the two on B200; every other launch uses the FP32
+ * kernels. */
 int b2a_spectral_uses_tensor_cores(int n_fft, int hop, int want_mel, int want_stft);
 /* Switch the tensor-core path on / off for this process (A/B measurements, parity tests of both kernels); returns the
  * previous setting. */

@@ -667,11 +667,14 @@ def test_spectral_tc_vs_fp32_kernel_vs_oracle(at, sp, hop, T, n_mels, wtype):
     w = at.AudioSignal.get_window(wtype, 2048, DEV)
     gain = torch.tensor([0.7, -3.0, 1.5], device=DEV)
     xd = x.to(DEV)
-    assert eng.spectral_kernel_name(2048, hop) == "spectral_tc_kernel"
     kw = dict(gain=gain, want_scaled=True, mel_fb=fb, mel_lo=lo, mel_hi=hi, want_stft=False)
-    tc = eng.spectral(xd, 2048, hop, w, **kw)
-    prev = eng.lib.b2a_spectral_tc_enable(0)
+    prev = eng.lib.b2a_spectral_tc_enable(1)  # the tensor-core path is opt-in
     try:
+        assert eng.spectral_kernel_name(2048, hop) == "spectral_tc_kernel"
+        tc = eng.spectral(xd, 2048, hop, w, **kw)
+        lg = eng.spectral(xd, 2048, hop, w, mel_fb=fb, mel_lo=lo, mel_hi=hi, post=_lib.POST_LOG10, post_eps=1e-5,
+                          post_power=2.0, want_stft=False)["mel"].cpu()
+        eng.lib.b2a_spectral_tc_enable(0)
         assert eng.spectral_kernel_name(2048, hop) == "spectral_warp_kernel<10,0>"
         fp = eng.spectral(xd, 2048, hop, w, **kw)
     finally:
@@ -685,8 +688,6 @@ def test_spectral_tc_vs_fp32_kernel_vs_oracle(at, sp, hop, T, n_mels, wtype):
         for name, got in (("tensor-core", tc["mel"]), ("fp32", fp["mel"])):
             assert rel_err(got[b].cpu(), ref[b]) < 2e-5, (name, b)
             assert elementwise_ok(got[b].cpu(), ref[b]), (name, b)
-    lg = eng.spectral(xd, 2048, hop, w, mel_fb=fb, mel_lo=lo, mel_hi=hi, post=_lib.POST_LOG10, post_eps=1e-5,
-                      post_power=2.0, want_stft=False)["mel"].cpu()
     ref_log = sp.log_mel(sp.mel_spectrogram(x, sr, n_mels, window_length=2048, hop_length=hop, window_type=wtype))
     assert (lg[:2] - ref_log[:2]).abs().max() < 2e-4  # log10 units (item 2: see tests/test_sim_kernels.py)
 
@@ -700,14 +701,15 @@ def test_cfg2_full_size_tc_strided_oracle(at, sp):
 
     eng = get_engine()
     x = bench.make_batch(64, 4242)
-    sig = at.AudioSignal(x.clone(), 44100).to(DEV)
-    sig.normalize(-24.0)
-    logmel = sig.mel_spectrogram(n_mels=128, window_length=2048, hop_length=512, window_type="hann", log=True)
-    y = sig.audio_data
-    assert eng.spectral_kernel_name(2048, 512) == "spectral_tc_kernel"
-    assert logmel.shape == (64, 2, 128, 862) and y.shape == x.shape
-    prev = eng.lib.b2a_spectral_tc_enable(0)
+    prev = eng.lib.b2a_spectral_tc_enable(1)
     try:
+        sig = at.AudioSignal(x.clone(), 44100).to(DEV)
+        sig.normalize(-24.0)
+        logmel = sig.mel_spectrogram(n_mels=128, window_length=2048, hop_length=512, window_type="hann", log=True)
+        y = sig.audio_data
+        assert eng.spectral_kernel_name(2048, 512) == "spectral_tc_kernel"
+        assert logmel.shape == (64, 2, 128, 862) and y.shape == x.shape
+        eng.lib.b2a_spectral_tc_enable(0)
         sig2 = at.AudioSignal(x.clone(), 44100).to(DEV)
         sig2.normalize(-24.0)
         logmel_fp = sig2.mel_spectrogram(n_mels=128, window_length=2048, hop_length=512, window_type="hann", log=True)

@@ -543,12 +543,15 @@ def test_spectral_tc_matches_fp32_kernel_and_reference(eng, hop, T, n_mels):
     fb, lo, hi = _mel_tables(sr, 2048, n_mels)
     w = sp.get_window("hann" if hop != 300 else "sqrt_hann", 2048)
     gain = torch.tensor([0.7, -3.0, 1.5])
-    assert eng.lib.b2a_spectral_uses_tensor_cores(2048, hop, 1, 0) == 1
-    assert eng.spectral_kernel_name(2048, hop) == "spectral_tc_kernel"
     kw = dict(gain=gain, want_scaled=True, mel_fb=fb, mel_lo=lo, mel_hi=hi, want_stft=False)
-    tc = eng.spectral(x, 2048, hop, w, **kw)
-    prev = eng.lib.b2a_spectral_tc_enable(0)
+    prev = eng.lib.b2a_spectral_tc_enable(1)  # the tensor-core path is opt-in
     try:
+        assert eng.lib.b2a_spectral_uses_tensor_cores(2048, hop, 1, 0) == 1
+        assert eng.spectral_kernel_name(2048, hop) == "spectral_tc_kernel"
+        tc = eng.spectral(x, 2048, hop, w, **kw)
+        lg = eng.spectral(x, 2048, hop, w, mel_fb=fb, mel_lo=lo, mel_hi=hi, post=_lib.POST_LOG10, post_eps=1e-5,
+                          post_power=2.0, want_stft=False)["mel"]
+        eng.lib.b2a_spectral_tc_enable(0)
         assert eng.spectral_kernel_name(2048, hop) == "spectral_warp_kernel<10,0>"
         fp = eng.spectral(x, 2048, hop, w, **kw)
     finally:
@@ -561,8 +564,6 @@ def test_spectral_tc_matches_fp32_kernel_and_reference(eng, hop, T, n_mels):
         assert rel_err(tc["mel"][b], ref[b]) < 2e-5, b
         assert _elementwise_ok(tc["mel"][b], ref[b], 1e-4, 2e-6), b  # measured: 5e-7 of the frame max (FP32 kernel: 2.5e-7)
         assert _elementwise_ok(fp["mel"][b], ref[b], 1e-4, 2e-6), b
-    lg = eng.spectral(x, 2048, hop, w, mel_fb=fb, mel_lo=lo, mel_hi=hi, post=_lib.POST_LOG10, post_eps=1e-5,
-                      post_power=2.0, want_stft=False)["mel"]
     ref_log = sp.log_mel(sp.mel_spectrogram(x, sr, n_mels, window_length=2048, hop_length=hop,
                                             window_type="hann" if hop != 300 else "sqrt_hann"))
     # log10 units.  Items 0 / 1 (noise-like: every band well above the transform's error floor): tight; item 2 has

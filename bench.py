@@ -277,13 +277,25 @@ def run_ours(args):
         for i in range(args.warmup):
             step(i)
         torch.cuda.synchronize()
+        # every rank must run the SAME number of steps (the exchange's sequence numbers advance per put): rank 0 sizes
+        # the pre-roll and the sustained loop from its own step time and broadcasts the counts
+        c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        c0.record()
+        for i in range(10):
+            step(i)
+        c1.record()
+        torch.cuda.synchronize()
+        est_ms = max(c0.elapsed_time(c1) / 10.0, 1e-3)
+        counts = torch.tensor([max(20, int(args.preroll * 1e3 / est_ms)) if args.preroll > 0 else 0,
+                               max(args.steps, int(args.sustain * 1e3 / est_ms)) if args.sustain > 0 else 0],
+                              device=dev, dtype=torch.int64)
+        if world > 1:
+            dist.broadcast(counts, src=0)
+        n_pre, n_sus = int(counts[0].item()), int(counts[1].item())
         w_pre0 = time.perf_counter()
-        n_pre = 0
-        while time.perf_counter() - w_pre0 < args.preroll:  # identical steps: clocks / power settle under the real load
-            for _ in range(20):
-                step(n_pre)
-                n_pre += 1
-            torch.cuda.synchronize()
+        for i in range(n_pre):  # identical steps: clocks / power settle under the real load
+            step(i)
+        torch.cuda.synchronize()
         barrier()
         step(0)  # one untimed post-barrier step: absorbs the rank skew of leaving the barrier
         torch.cuda.synchronize()
@@ -300,8 +312,7 @@ def run_ours(args):
         launches = eng.launches - launches0 + (exchange.launches - xl0 if exchange is not None else 0)
         # sustained figure: the same step for >= args.sustain seconds (SM clocks settle under the power cap)
         sus = None
-        if args.sustain > 0:
-            n_sus = max(args.steps, int(args.sustain / max(ms_rank / args.steps * 1e-3, 1e-5)))
+        if n_sus > 0:
             s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             s0.record()
             for i in range(n_sus):

@@ -21,6 +21,8 @@
 // Kernel 2  lufs_gate_kernel        (tiny: one CTA per item)
 //   z -> l -> absolute gate -> relative gate -> LUFS, with the reference's dtypes (float32 z,
 //   float64 logs) and its NaN / inf scrubbing; optionally max(.,-70) and normalize()'s gain.
+#include <stdlib.h>
+
 #include "b2a_common.h"
 
 namespace b2a {
@@ -447,6 +449,359 @@ kweight_energy_kernel(const float* __restrict__ x, int rows, int T, int Tp, int 
   }  // persistent tile loop
 }
 
+// =============================================================================================
+// Warp-autonomous variant (round 2): NO CTA barrier anywhere in the streaming loop.
+//
+// A warp owns a SEGMENT of 32 lanes x L2 = 64 samples = 2048 samples of one row and carries it through all
+// phases on its own: its samples stream into a warp-private, double-buffered shared-memory window with cp.async
+// (the next segment lands underneath the arithmetic of the current one), lanes read their 64-sample chunk from there
+// TWICE (phase A and phase B: no 34-register sample array, so 12 warps per SM stay resident), the affine scan is
+// shuffles only, and the carry across segments is a decoupled look-back in which the 32 lanes probe the 32 nearest
+// predecessor segments IN PARALLEL (aggregates are published right after phase A, so one probe normally resolves the
+// whole chain).  Segments are claimed through a global ticket in segment-major order, so a predecessor always belongs
+// to a warp that is already running.  Same arithmetic as kweight_energy_kernel: float32 DF-I recursion from the exact
+// carried state; per-interval energies into float64 bins.
+// =============================================================================================
+namespace v2 {
+
+__device__ __forceinline__ int first_set(unsigned m) {  // index of the lowest set bit, m != 0
+#ifdef B2A_SIM
+  return __builtin_ctz(m);
+#else
+  return __ffs((int)m) - 1;
+#endif
+}
+
+constexpr int L2 = 64;              // samples per lane
+constexpr int SEG = 32 * L2;        // samples per warp segment
+constexpr int CHS = L2 + 4;         // shared-memory words per lane chunk: 16 B aligned, conflict-free LDS.128
+constexpr int WPB = 12;             // warps per CTA (one CTA per SM: 12 x 17 KB of windows)
+constexpr int BUF = 32 * CHS;       // floats per window
+
+template <int NS>
+struct Tables2 {
+  static constexpr int D = 2 * NS;
+  float Wa[L2 + 2][D];        // zero-state end state of a lane chunk as a linear map of its 66 inputs
+  float Mlane[32][D * D];     // A^(L2 l)
+  float Mscan[5][D * D];      // A^(L2 2^k)
+  float Mseg[33][D * D];      // A^(SEG j), j = 0..32
+};
+
+template <int NS>
+static void build_tables2(const Coef<NS>& cf, Tables2<NS>* tb) {
+  constexpr int D = 2 * NS;
+  double b0[NS], b1[NS], b2[NS], a1[NS], a2[NS];
+  for (int s = 0; s < NS; ++s) {
+    b0[s] = cf.b0[s]; b1[s] = cf.b1[s]; b2[s] = cf.b2[s]; a1[s] = cf.a1[s]; a2[s] = cf.a2[s];
+  }
+  double A[D * D];
+  for (int k = 0; k < D; ++k) {
+    double y1[NS], y2[NS];
+    for (int s = 0; s < NS; ++s) { y1[s] = (k == 2 * s) ? 1.0 : 0.0; y2[s] = (k == 2 * s + 1) ? 1.0 : 0.0; }
+    cascade_step<NS, double>(b0, b1, b2, a1, a2, 0.0, 0.0, 0.0, y1, y2);
+    for (int s = 0; s < NS; ++s) { A[(2 * s) * D + k] = y1[s]; A[(2 * s + 1) * D + k] = y2[s]; }
+  }
+  double P[D * D];  // A^L2
+  for (int i = 0; i < D * D; ++i) P[i] = A[i];
+  for (int l = 1; l < L2; l <<= 1) matmul<D>(P, P, P);
+  double Q[D * D];
+  for (int i = 0; i < D * D; ++i) Q[i] = (i / D == i % D) ? 1.0 : 0.0;
+  for (int l = 0; l < 32; ++l) {
+    for (int i = 0; i < D * D; ++i) tb->Mlane[l][i] = (float)Q[i];
+    matmul<D>(P, Q, Q);
+  }
+  // Q == A^SEG
+  double S[D * D];
+  for (int i = 0; i < D * D; ++i) S[i] = P[i];
+  for (int k = 0; k < 5; ++k) {
+    for (int i = 0; i < D * D; ++i) tb->Mscan[k][i] = (float)S[i];
+    matmul<D>(S, S, S);
+  }
+  double W[D * D];
+  for (int i = 0; i < D * D; ++i) W[i] = (i / D == i % D) ? 1.0 : 0.0;
+  for (int v = 0; v <= 32; ++v) {
+    for (int i = 0; i < D * D; ++i) tb->Mseg[v][i] = (float)W[i];
+    matmul<D>(Q, W, W);
+  }
+  for (int j = 0; j < L2 + 2; ++j) {
+    double y1[NS], y2[NS];
+    for (int s = 0; s < NS; ++s) { y1[s] = 0.0; y2[s] = 0.0; }
+    for (int i = 0; i < L2; ++i) {
+      const double in0 = (i + 2 == j) ? 1.0 : 0.0, in1 = (i + 1 == j) ? 1.0 : 0.0, in2 = (i == j) ? 1.0 : 0.0;
+      cascade_step<NS, double>(b0, b1, b2, a1, a2, in0, in1, in2, y1, y2);
+    }
+    for (int s = 0; s < NS; ++s) { tb->Wa[j][2 * s] = (float)y1[s]; tb->Wa[j][2 * s + 1] = (float)y2[s]; }
+  }
+}
+
+// Stage segment `tk` (ticket order: seg = tk / rows, row = tk % rows) into the warp's window; history samples
+// (the two before the segment) are returned in registers of lane 0 (hist0, hist1).
+__device__ __forceinline__ void stage_segment(const float* __restrict__ x, int tk, int rows, int T, float* win, int lane) {
+  const int seg = tk / rows, row = tk - seg * rows;
+  const int t0 = seg * SEG;
+  const float* xr = x + (size_t)row * (size_t)T;
+  if ((t0 + SEG <= T) && ((((uintptr_t)(xr + t0)) & 15) == 0)) {
+#pragma unroll
+    for (int i = 0; i < L2 / 4; ++i) {
+      const int s = 128 * i + 4 * lane;  // sample index within the segment (16 B per lane: coalesced)
+      cp_async16(&win[CHS * (s >> 6) + (s & 63)], xr + t0 + s);
+    }
+  } else {
+    for (int s = lane; s < SEG; s += 32) {
+      const int n = t0 + s;
+      win[CHS * (s >> 6) + (s & 63)] = (n < T) ? __ldg(xr + n) : 0.f;
+    }
+  }
+}
+
+template <int NS>
+__global__ void __launch_bounds__(32 * WPB, 1)
+kweight_energy_warp_kernel(const float* __restrict__ x, int rows, int T, int Tp, int nseg, Coef<NS> cf,
+                           const B2A_GRID_CONSTANT Tables2<NS> tbv, int* __restrict__ ticket,
+                           unsigned long long* __restrict__ recs, double* __restrict__ bins, int stride, int r,
+                           int nbins) {
+  constexpr int D = 2 * NS;
+  B2A_DYN_SMEM(smem);
+  float* wins = reinterpret_cast<float*>(smem);  // [WPB][2][BUF]
+  __shared__ __align__(16) float s_wa[L2 + 2][D];
+  __shared__ float s_mlane[32][D * D];
+  __shared__ float s_mscan[5][D * D];
+  __shared__ float s_mseg[33][D * D];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  for (int i = tid; i < (L2 + 2) * D; i += blockDim.x) (&s_wa[0][0])[i] = (&tbv.Wa[0][0])[i];
+  for (int i = tid; i < 32 * D * D; i += blockDim.x) (&s_mlane[0][0])[i] = (&tbv.Mlane[0][0])[i];
+  for (int i = tid; i < 5 * D * D; i += blockDim.x) (&s_mscan[0][0])[i] = (&tbv.Mscan[0][0])[i];
+  for (int i = tid; i < 33 * D * D; i += blockDim.x) (&s_mseg[0][0])[i] = (&tbv.Mseg[0][0])[i];
+  __syncthreads();  // the only CTA barrier: tables
+  const int total = rows * nseg;
+  const int nwarps_grid = (int)gridDim.x * WPB;
+  float* win0 = wins + (size_t)warp * 2 * BUF;
+
+  int cur = (int)blockIdx.x * WPB + warp;  // first tickets: one per resident warp
+  int nxt = 0;
+  if (lane == 0) nxt = nwarps_grid + atomicAdd(ticket, 1);
+  nxt = __shfl_sync(0xffffffffu, nxt, 0);
+  if (cur < total) stage_segment(x, cur, rows, T, win0, lane);
+  int par = 0;
+#pragma unroll 1
+  for (; cur < total; par ^= 1) {
+    cp_async_wait_all();
+    __syncwarp();
+    int ticket2 = 0;
+    if (lane == 0) ticket2 = nwarps_grid + atomicAdd(ticket, 1);  // two segments ahead
+    const float* win = win0 + par * BUF;
+    if (nxt < total) stage_segment(x, nxt, rows, T, win0 + (par ^ 1) * BUF, lane);
+    const int seg = cur / rows, row = cur - seg * rows;
+    const int t0 = seg * SEG;
+    const float* xr = x + (size_t)row * (size_t)T;
+    unsigned long long* myrec = recs + ((size_t)seg * rows + row) * (2 * D);
+    // history: the two samples in front of this lane's chunk
+    float h0, h1;
+    if (lane == 0) {
+      h0 = (t0 >= 2 && t0 - 2 < T) ? __ldg(xr + t0 - 2) : 0.f;
+      h1 = (t0 >= 1 && t0 - 1 < T) ? __ldg(xr + t0 - 1) : 0.f;
+    } else {
+      const float2 h = *reinterpret_cast<const float2*>(&win[CHS * (lane - 1) + L2 - 2]);
+      h0 = h.x; h1 = h.y;
+    }
+    const float4* c4 = reinterpret_cast<const float4*>(&win[CHS * lane]);
+
+    // ---- phase A: zero-state end state of the lane's chunk as a linear map of its 66 inputs
+    float g[D];
+#pragma unroll
+    for (int i = 0; i < D; ++i) g[i] = fmaf(s_wa[0][i], h0, s_wa[1][i] * h1);
+#pragma unroll
+    for (int i4 = 0; i4 < L2 / 4; ++i4) {
+      const float4 q = c4[i4];
+      const float qs[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+#pragma unroll
+        for (int i = 0; i < D; ++i) g[i] = fmaf(s_wa[2 + 4 * i4 + e][i], qs[e], g[i]);
+      }
+    }
+    // ---- inclusive affine scan over the 32 chunks
+#pragma unroll
+    for (int k = 0; k < 5; ++k) {
+      float o[D];
+#pragma unroll
+      for (int j = 0; j < D; ++j) o[j] = __shfl_up_sync(0xffffffffu, g[j], 1u << k);
+      if (lane >= (1 << k)) {
+#pragma unroll
+        for (int i = 0; i < D; ++i) g[i] += row_dot<D>(s_mscan[k], i, o);
+      }
+    }
+    float ex[D], agg[D];
+#pragma unroll
+    for (int j = 0; j < D; ++j) {
+      ex[j] = __shfl_up_sync(0xffffffffu, g[j], 1);
+      if (lane == 0) ex[j] = 0.f;
+      agg[j] = __shfl_sync(0xffffffffu, g[j], 31);  // zero-state end state of the whole segment
+    }
+    // ---- carry across segments: publish the aggregate, then probe up to 32 predecessors at once
+    float sin_[D];
+#pragma unroll
+    for (int j = 0; j < D; ++j) sin_[j] = 0.f;
+    if (seg > 0) {
+      if (lane < D) {
+        float a = agg[0];
+#pragma unroll
+        for (int j = 1; j < D; ++j) a = (lane == j) ? agg[j] : a;
+        rec_store(myrec + lane, a);
+      }
+      int base = seg - 1;  // nearest predecessor not yet accounted for
+      float mpow[D * D];   // A^(SEG * (seg - 1 - base)): carries the probed window's result forward to this segment
+#pragma unroll
+      for (int i = 0; i < D * D; ++i) mpow[i] = (i / D == i % D) ? 1.f : 0.f;
+      for (;;) {
+        const int pj = base - lane;  // this lane's predecessor
+        float vi[D], va[D];
+        bool incl_ok = false, agg_ok = false;
+        unsigned first_incl, agg_mask;
+        const unsigned want = (base >= 31) ? 0xffffffffu : ((1u << (base + 1)) - 1u);  // lanes with a predecessor
+        do {
+          if (pj >= 0) {
+            const unsigned long long* rec = recs + ((size_t)pj * rows + row) * (2 * D);
+            incl_ok = true; agg_ok = true;
+#pragma unroll
+            for (int j = 0; j < D; ++j) {
+              const unsigned long long wi = rec_load(rec + D + j), wa = rec_load(rec + j);
+              incl_ok &= (wi >> 32) != 0; agg_ok &= (wa >> 32) != 0;
+              vi[j] = __int_as_float((int)(unsigned)(wi & 0xffffffffu));
+              va[j] = __int_as_float((int)(unsigned)(wa & 0xffffffffu));
+            }
+            if (pj == 0) agg_ok = incl_ok;  // segment 0 publishes only its inclusive state
+          }
+          first_incl = __ballot_sync(0xffffffffu, incl_ok);
+          agg_mask = __ballot_sync(0xffffffffu, agg_ok || incl_ok);
+          // resolved when every predecessor nearer than the first inclusive one has its aggregate
+          const unsigned upto = first_incl ? ((1u << first_set(first_incl)) - 1u) : want;
+          if ((agg_mask & upto) == upto) break;
+        } while (true);
+        const int f = first_incl ? first_set(first_incl) : 32;
+        // term of this lane: Mseg[lane] (its distance to base, in segments) applied to its aggregate / inclusive state
+        float term[D];
+#pragma unroll
+        for (int i = 0; i < D; ++i) term[i] = 0.f;
+        if (pj >= 0 && lane <= f && lane < 32) {
+          const float* v = (lane == f) ? vi : va;
+#pragma unroll
+          for (int i = 0; i < D; ++i) term[i] = row_dot<D>(s_mseg[lane], i, v);
+        }
+#pragma unroll
+        for (int i = 0; i < D; ++i) term[i] = warp_sum(term[i]);
+        // carry the window's contribution over the (seg - 1 - base) segments between it and this one
+#pragma unroll
+        for (int i = 0; i < D; ++i) sin_[i] += row_dot<D>(mpow, i, term);
+        if (f < 32 || base - 32 < 0) break;
+        base -= 32;
+        float pn[D * D];  // mpow <- mpow * Mseg[32]
+#pragma unroll
+        for (int i = 0; i < D; ++i)
+#pragma unroll
+          for (int j = 0; j < D; ++j) {
+            float a = 0.f;
+#pragma unroll
+            for (int k = 0; k < D; ++k) a = fmaf(mpow[i * D + k], s_mseg[32][k * D + j], a);
+            pn[i * D + j] = a;
+          }
+#pragma unroll
+        for (int i = 0; i < D * D; ++i) mpow[i] = pn[i];
+      }
+    }
+    // inclusive state of this segment = A^SEG S_in + aggregate
+    if (lane < D) {
+      float inc = 0.f;
+#pragma unroll
+      for (int j = 0; j < D; ++j) {
+        const float v = agg[j] + row_dot<D>(s_mseg[1], j, sin_);
+        inc = (lane == j) ? v : inc;
+      }
+      rec_store(myrec + D + lane, inc);
+    }
+
+    // ---- phase B: true start state, recursion, energies into the interval bins
+    float y1[NS], y2[NS];
+    {
+      float st[D];
+#pragma unroll
+      for (int i = 0; i < D; ++i) st[i] = ex[i] + row_dot<D>(s_mlane[lane], i, sin_);
+#pragma unroll
+      for (int s = 0; s < NS; ++s) { y1[s] = st[2 * s]; y2[s] = st[2 * s + 1]; }
+    }
+    const int n0 = t0 + lane * L2;
+    const int nv = min(L2, max(0, Tp - n0));
+    int j0 = n0 / stride, rem0 = n0 - j0 * stride;
+    int b0 = 2 * j0 + (rem0 >= r ? 1 : 0);
+    int end0 = (b0 & 1) ? (j0 + 1) * stride : j0 * stride + r;
+    const int s1 = min(end0 - n0, L2);
+    int s2 = L2, b1 = b0, b2 = b0;
+    if (s1 < L2) {
+      const int n1 = n0 + s1, j1 = n1 / stride, rem1 = n1 - j1 * stride;
+      b1 = 2 * j1 + (rem1 >= r ? 1 : 0);
+      const int end1 = (b1 & 1) ? (j1 + 1) * stride : j1 * stride + r;
+      s2 = min(end1 - n0, L2);
+      if (s2 < L2) {
+        const int n2 = n0 + s2, j2 = n2 / stride, rem2 = n2 - j2 * stride;
+        b2 = 2 * j2 + (rem2 >= r ? 1 : 0);
+      }
+    }
+    const bool simple = (s1 >= L2) && (nv == L2);
+    const bool clean = __all_sync(0xffffffffu, simple);  // warp-uniform: no lane straddles an interval boundary
+    double* rb = bins + (size_t)row * (size_t)nbins;
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f;
+    float xm2 = h0, xm1 = h1;
+    if (clean) {
+      float acc = 0.f;
+#pragma unroll
+      for (int i4 = 0; i4 < L2 / 4; ++i4) {
+        const float4 q = c4[i4];
+        const float qs[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float y = cascade_step<NS, float>(cf.b0, cf.b1, cf.b2, cf.a1, cf.a2, qs[e], xm1, xm2, y1, y2);
+          xm2 = xm1; xm1 = qs[e];
+          acc = fmaf(y, y, acc);
+        }
+      }
+      a0 = acc;
+    } else {
+      float acc = 0.f, p1 = 0.f, p2 = 0.f;  // running energy and its value at the two interval boundaries
+#pragma unroll
+      for (int i4 = 0; i4 < L2 / 4; ++i4) {
+        const float4 q = c4[i4];
+        const float qs[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int i = 4 * i4 + e;
+          p1 = (i == s1) ? acc : p1;
+          p2 = (i == s2) ? acc : p2;
+          const float y = cascade_step<NS, float>(cf.b0, cf.b1, cf.b2, cf.a1, cf.a2, qs[e], xm1, xm2, y1, y2);
+          xm2 = xm1; xm1 = qs[e];
+          acc = (i < nv) ? fmaf(y, y, acc) : acc;
+        }
+      }
+      if (s1 >= L2) p1 = acc;
+      if (s2 >= L2) p2 = acc;
+      a0 = p1; a1 = p2 - p1; a2 = acc - p2;
+    }
+    // one atomic per interval the warp touched (intervals are monotonic in the lane index)
+    const int blast = (s2 < L2) ? b2 : ((s1 < L2) ? b1 : b0);  // last interval this lane's chunk reaches
+    const int bf = __shfl_sync(0xffffffffu, b0, 0), bl = __shfl_sync(0xffffffffu, blast, 31);
+    for (int id = bf; id <= bl; ++id) {
+      float v = (b0 == id) ? a0 : 0.f;
+      if (!clean) v += ((s1 < L2 && b1 == id) ? a1 : 0.f) + ((s2 < L2 && b2 == id) ? a2 : 0.f);
+      v = warp_sum(v);
+      if (lane == 0 && id < nbins) atomicAdd(rb + id, (double)v);
+    }
+    cur = nxt;
+    nxt = __shfl_sync(0xffffffffu, ticket2, 0);
+  }
+  cp_async_wait_all();
+}
+
+}  // namespace v2
+
 // ---------------------------------------------------------------------------------------------
 // gating: ref:audiotools/core/loudness.py:208-247 (+ :315-320 clamp, effects.py:214-217 gain)
 // ---------------------------------------------------------------------------------------------
@@ -576,7 +931,7 @@ gain_kernel(const float* __restrict__ x, float* __restrict__ out, int64_t per_it
 }
 
 struct Geometry {
-  int K, stride, q, r, nblk, nbins, ntile;
+  int K, stride, q, r, nblk, nbins, ntile, nseg;
 };
 static int geometry(int64_t Tp, double rate, double block_s, Geometry* g) {
   double kf = block_s * rate;
@@ -589,7 +944,17 @@ static int geometry(int64_t Tp, double rate, double block_s, Geometry* g) {
   g->nblk = (int)nblk;
   g->nbins = 2 * (int)(nblk + g->q);
   g->ntile = (int)((Tp + TILE - 1) / TILE);
+  g->nseg = (int)((Tp + v2::SEG - 1) / v2::SEG);  // segments of the warp-autonomous kernel (>= ntile)
   return 0;
+}
+
+static int use_v1() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("B2A_LUFS_V1");
+    v = (e && e[0] == '1') ? 1 : 0;
+  }
+  return v;
 }
 
 template <int NS>
@@ -598,7 +963,7 @@ static int run(const float* x, int64_t B, int C, int64_t T, int64_t Tp, const Ge
                float* z_blocks, float* lufs_out, float* loud_out, const float* target_db, int n_target,
                float* gain_out, void* ws, size_t ws_bytes, void* stream) {
   const int64_t rows = B * C;
-  WsLayout w = ws_layout(rows, g.ntile, g.nbins, g.nblk, 2 * MAX_STAGES);
+  WsLayout w = ws_layout(rows, g.nseg, g.nbins, g.nblk, 2 * MAX_STAGES);
   B2A_REQUIRE(ws_bytes >= w.total, B2A_E_INVALID, "lufs: workspace too small (%zu < %zu)", ws_bytes, w.total);
   Coef<NS> cf;
   for (int s = 0; s < NS; ++s) {
@@ -611,22 +976,40 @@ static int run(const float* x, int64_t B, int C, int64_t T, int64_t Tp, const Ge
     cf.a1[s] = (float)c[4] / a0; cf.a2[s] = (float)c[5] / a0;
   }
   char* base = (char*)ws;
-  Tables<NS> tbh;
-  build_tables<NS>(cf, &tbh);
   B2A_CUDA_OK(cudaMemsetAsync(base, 0, w.zeroed_bytes, (cudaStream_t)stream));
-  int per_sm = 1, sms = B2A_NUM_SMS, dev = 0;
-  B2A_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kweight_energy_kernel<NS>, THREADS, 0));
+  int sms = B2A_NUM_SMS, dev = 0;
   if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess)
     sms = B2A_NUM_SMS;
+  if (use_v1()) {  // the CTA-cooperative kernel of round 1 (B2A_LUFS_V1=1): kept for A/B measurements
+    Tables<NS> tbh;
+    build_tables<NS>(cf, &tbh);
+    int per_sm = 1;
+    B2A_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kweight_energy_kernel<NS>, THREADS, 0));
 #ifdef B2A_SIM
-  const int64_t resident = 1;  // the CPU simulator runs CTAs one after another: no co-resident predecessors
+    const int64_t resident = 1;  // the CPU simulator runs CTAs one after another: no co-resident predecessors
 #else
-  const int64_t resident = (int64_t)sms * (per_sm < 1 ? 1 : per_sm);
+    const int64_t resident = (int64_t)sms * (per_sm < 1 ? 1 : per_sm);
 #endif
-  const int64_t tiles_all = rows * g.ntile;
-  B2A_LAUNCH(kweight_energy_kernel<NS>, dim3((unsigned)(tiles_all < resident ? tiles_all : resident)), dim3(THREADS), 0, stream, x, (int)rows,
-             (int)T, (int)Tp, g.ntile, cf, tbh, (int*)(base + w.ticket),
-             (unsigned long long*)(base + w.recs), (double*)(base + w.bins), g.stride, g.r, g.nbins);
+    const int64_t tiles_all = rows * g.ntile;
+    B2A_LAUNCH(kweight_energy_kernel<NS>, dim3((unsigned)(tiles_all < resident ? tiles_all : resident)), dim3(THREADS), 0, stream, x, (int)rows,
+               (int)T, (int)Tp, g.ntile, cf, tbh, (int*)(base + w.ticket),
+               (unsigned long long*)(base + w.recs), (double*)(base + w.bins), g.stride, g.r, g.nbins);
+  } else {
+    v2::Tables2<NS> tb2;
+    v2::build_tables2<NS>(cf, &tb2);
+    const size_t smem = (size_t)v2::WPB * 2 * v2::BUF * sizeof(float);
+    B2A_CUDA_OK(cudaFuncSetAttribute(v2::kweight_energy_warp_kernel<NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+#ifdef B2A_SIM
+    const int64_t resident = 1;
+#else
+    const int64_t resident = sms;  // one CTA of 12 warps per SM
+#endif
+    const int64_t segs_all = rows * g.nseg;
+    const int64_t want = (segs_all + v2::WPB - 1) / v2::WPB;
+    B2A_LAUNCH(v2::kweight_energy_warp_kernel<NS>, dim3((unsigned)(want < resident ? want : resident)), dim3(32 * v2::WPB), smem,
+               stream, x, (int)rows, (int)T, (int)Tp, g.nseg, cf, tb2, (int*)(base + w.ticket),
+               (unsigned long long*)(base + w.recs), (double*)(base + w.bins), g.stride, g.r, g.nbins);
+  }
   GateParams gp;
   for (int c = 0; c < 8; ++c) gp.G[c] = c < C ? chan_gain_h[c] : 0.0;
   gp.scale = (float)(1.0 / (block_s * rate));
@@ -651,7 +1034,7 @@ extern "C" int64_t b2a_lufs_num_blocks(int64_t T_padded, double rate, double blo
 extern "C" size_t b2a_lufs_workspace_bytes(int64_t B, int C, int64_t T_padded, double rate, double block_s) {
   Geometry g;
   if (B < 1 || C < 1 || T_padded < 1 || geometry(T_padded, rate, block_s, &g) != 0) return 0;
-  return ws_layout(B * C, g.ntile, g.nbins, g.nblk, 2 * MAX_STAGES).total;
+  return ws_layout(B * C, g.nseg, g.nbins, g.nblk, 2 * MAX_STAGES).total;
 }
 
 extern "C" int b2a_lufs_f32(const float* x, int64_t B, int C, int64_t T, int64_t T_padded, double rate,

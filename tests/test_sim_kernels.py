@@ -604,3 +604,22 @@ def test_pitch_shift_and_time_stretch_match_spec_oracle(eng):
                                g, f"pitch_{st:g}", rows=slice(0, 2))
     _check_pitch_vs_golden(lambda: tuple(t.reshape(2, -1) for t in eng.time_stretch(x, mg.SR, 1.25, return_positions=True)),
                            g, "stretch_1.25", rows=slice(0, 2))
+
+
+# ------------------------------------------------------------------------------------------
+# warp-autonomous K-weighting kernel (csrc/lufs.cu, namespace v2): rates with r != 0, rows of unequal phase, the
+# multi-window look-back (> 64 segments per row), short rows, unaligned lengths
+# ------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("sr,T,B,C", [(11025, 30001, 2, 1), (48000, 70000, 1, 2), (16000, 140001, 1, 1), (44100, 5000, 3, 2),
+                                      (22050, 33333, 2, 2)])
+def test_lufs_warp_kernel_block_energies_and_loudness(eng, sr, T, B, C):
+    g = torch.Generator().manual_seed(sr + T)
+    x = 0.2 * torch.randn(B, C, T, generator=g) * torch.rand(B, 1, 1, generator=g)
+    x[0, 0, : T // 3] += 0.3  # DC step: exercises the long tail of the 38 Hz high-pass across many segments
+    Tp = padded_len(T, sr)
+    out = eng.lufs(x, sr, padded_length=Tp, want_blocks=True)
+    z_ref = sp.Meter(sr).block_energies(torch.nn.functional.pad(x, (0, Tp - T)).permute(0, 2, 1))
+    assert out["blocks"].shape == z_ref.shape  # block indexing bit-exact
+    assert rel_err(out["blocks"], z_ref) < 1e-4
+    loud_ref = sp.loudness(x, sr)
+    assert torch.allclose(out["loud"], loud_ref, atol=2e-3)

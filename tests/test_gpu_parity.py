@@ -746,3 +746,23 @@ def test_pitch_shift_and_time_stretch_match_spec_oracle(at):
     for fac in mg.FACTORS:
         _check_pitch_vs_golden(lambda: tuple(t.cpu().reshape(3, -1) for t in eng.time_stretch(x, mg.SR, fac, return_positions=True)),
                                g, f"stretch_{fac:g}")
+
+
+@pytest.mark.parametrize("sr,T,B,C", [(44100, 441000, 1, 1), (48000, 600001, 2, 1), (11025, 90001, 3, 2), (16000, 200000, 200, 1)])
+def test_lufs_warp_kernel_run_geometries(at, sp, sr, T, B, C):
+    """csrc/lufs.cu (namespace v2): one row cut into hundreds of one-segment runs (multi-window look-back), a rate with
+    r != 0, and more rows than a launch has resident warps for (whole-row runs, second round of tickets)."""
+    from audiotools_b200.engine import get_engine
+
+    g = torch.Generator().manual_seed(sr + T)
+    x = 0.2 * torch.randn(min(B, 4), C, T, generator=g) * (0.1 + torch.rand(min(B, 4), 1, 1, generator=g))
+    x[0, 0, : T // 3] += 0.3
+    if B > 4:
+        x = x.repeat((B + 3) // 4, 1, 1)[:B]
+    out = get_engine().lufs(x.to(DEV), sr, want_blocks=True)
+    z_ref = sp.Meter(sr).block_energies(x[:4].permute(0, 2, 1))
+    assert out["blocks"].shape[1:] == z_ref.shape[1:]
+    assert rel_err(out["blocks"][:4].cpu(), z_ref) < 1e-4
+    assert torch.allclose(out["loud"][:4].cpu(), sp.loudness(x[:4], sr), atol=LUFS_ATOL)
+    if B > 4:  # the repeated items give identical numbers whichever warp / round processed them
+        assert torch.equal(out["blocks"][4:8], out["blocks"][:4])

@@ -66,7 +66,7 @@ __host__ inline WsLayout ws_layout(int64_t rows, int64_t ntile, int64_t nbins, i
   w.zeroed_bytes = o;
   w.tables = o; o = align256(o + sizeof(Tables<MAX_STAGES>));
   w.zws = o; o = align256(o + sizeof(float) * rows * nblk);
-  w.prefix = o; o = align256(o + sizeof(float) * rows * ntile * 32 * D);  // lane prefixes (warp-autonomous kernel)
+  w.prefix = o;
   w.total = o;
   return w;
 }
@@ -451,33 +451,26 @@ kweight_energy_kernel(const float* __restrict__ x, int rows, int T, int Tp, int 
 }
 
 // =============================================================================================
-// Warp-autonomous variant (round 2): NO CTA barrier in the streaming loops and no serial ripple between segments.
+// Warp-autonomous variant (round 2): no CTA barrier, no inter-warp communication, ONE pass over the samples.
 //
 // A row is cut into RUNS of run_len consecutive segments (segment = 32 lanes x L2 = 64 samples = 2048 samples); a warp
-// owns one run and makes two passes over it:
-//   pass 1  per segment: samples -> warp-private, double-buffered shared-memory window (cp.async; the next segment
-//           lands underneath the arithmetic), zero-state end state of every lane chunk (a 66-tap linear map), affine
-//           shuffle scan; the per-lane exclusive prefixes go to a small scratch array, the segment totals are chained
-//           into the run's aggregate, which is PUBLISHED.
-//   carry   the state entering the run = sum over the earlier runs of the row of Mrun^(distance) x aggregate: the 32
-//           lanes fetch 32 predecessor aggregates at once.  Aggregates depend on nothing but their own samples, so
-//           every run of the launch resolves as soon as pass 1 is over everywhere -- there is no chain of inclusive
-//           states to ripple through (the first warp-per-segment version waited ~35 us per wave for exactly that).
-//   pass 2  per segment: samples again (from L2: all runs in flight together hold ~57 MB), true start state from the
-//           stored prefix + the carried state, float32 DF-I recursion, energies into the float64 interval bins.
-// Runs are claimed through a global ticket in run-major order, so a predecessor always belongs to a warp that is
-// already running (or finished) -- needed only when there are more runs than resident warps.
-// Same arithmetic as kweight_energy_kernel: exact carried state, float32 recursion, bit-exact block indexing.
+// owns a run and walks it segment by segment: samples -> warp-private, double-buffered shared-memory window (cp.async;
+// the next segment lands underneath the arithmetic of the current one), zero-state end state of every lane chunk
+// (a 66-tap linear map read from the window), affine shuffle scan, true lane start states from the state carried in
+// registers, float32 DF-I recursion (second read of the window), energies into the float64 interval bins.
+//
+// The state entering a run comes from a WARM-UP: the warp first runs the carry part (no energies) over the n_warm
+// segments in front of its run, starting from zero.  The K-weighting poles have radius rho < 1 (0.9946 for the 38 Hz
+// high-pass at 44.1 kHz), so whatever happened before the warm-up reaches the run attenuated by rho^(n_warm * 2048);
+// the host picks n_warm with rho^(n_warm * 2048) <= 2^-40 (3 segments at 44.1 kHz, 18 % extra reads at run_len 17).
+// That bound is five orders of magnitude below the rounding noise the float32 recursion itself carries (each step
+// rounds at 6e-8 |y| and the feedback amplifies it by ~1/(1 - rho)), i.e. the results are those of the exact carry
+// to float32 rounding; the first warp-per-segment versions (decoupled look-back, then two passes with published
+// aggregates) were exact in the same sense and cost a serial ripple of ~35 us per wave resp. a second HBM read.
+// B2A_LUFS_V1=1 selects round 1's CTA-cooperative kernel with its exact look-back carry (rows whose dynamic range
+// exceeds 2^40 within 70 ms are the only inputs on which the two can differ beyond rounding).
 // =============================================================================================
 namespace v2 {
-
-__device__ __forceinline__ int first_set(unsigned m) {  // index of the lowest set bit, m != 0
-#ifdef B2A_SIM
-  return __builtin_ctz(m);
-#else
-  return __ffs((int)m) - 1;
-#endif
-}
 
 constexpr int L2 = 64;              // samples per lane
 constexpr int SEG = 32 * L2;        // samples per warp segment
@@ -492,11 +485,10 @@ struct Tables2 {
   float Mlane[32][D * D];     // A^(L2 l)
   float Mscan[5][D * D];      // A^(L2 2^k)
   float Mseg[D * D];          // A^SEG
-  float Mrun[33][D * D];      // A^(SEG run_len j), j = 0..32
 };
 
 template <int NS>
-static void build_tables2(const Coef<NS>& cf, int run_len, Tables2<NS>* tb) {
+static void build_tables2(const Coef<NS>& cf, Tables2<NS>* tb) {
   constexpr int D = 2 * NS;
   double b0[NS], b1[NS], b2[NS], a1[NS], a2[NS];
   for (int s = 0; s < NS; ++s) {
@@ -525,15 +517,6 @@ static void build_tables2(const Coef<NS>& cf, int run_len, Tables2<NS>* tb) {
     for (int i = 0; i < D * D; ++i) tb->Mscan[k][i] = (float)S[i];
     matmul<D>(S, S, S);
   }
-  double R[D * D];  // A^(SEG run_len)
-  for (int i = 0; i < D * D; ++i) R[i] = (i / D == i % D) ? 1.0 : 0.0;
-  for (int v = 0; v < run_len; ++v) matmul<D>(Q, R, R);
-  double W[D * D];
-  for (int i = 0; i < D * D; ++i) W[i] = (i / D == i % D) ? 1.0 : 0.0;
-  for (int v = 0; v <= 32; ++v) {
-    for (int i = 0; i < D * D; ++i) tb->Mrun[v][i] = (float)W[i];
-    matmul<D>(R, W, W);
-  }
   for (int j = 0; j < L2 + 2; ++j) {
     double y1[NS], y2[NS];
     for (int s = 0; s < NS; ++s) { y1[s] = 0.0; y2[s] = 0.0; }
@@ -543,6 +526,20 @@ static void build_tables2(const Coef<NS>& cf, int run_len, Tables2<NS>* tb) {
     }
     for (int s = 0; s < NS; ++s) { tb->Wa[j][2 * s] = (float)y1[s]; tb->Wa[j][2 * s + 1] = (float)y2[s]; }
   }
+}
+
+// largest pole radius of the cascade (a1, a2 already normalised by a0)
+template <int NS>
+static double max_pole_radius(const Coef<NS>& cf) {
+  double rho = 0.0;
+  for (int s = 0; s < NS; ++s) {
+    const double a1 = cf.a1[s], a2 = cf.a2[s], disc = a1 * a1 - 4.0 * a2;
+    double r;
+    if (disc < 0) r = sqrt(a2 > 0 ? a2 : 0.0);
+    else r = 0.5 * (fabs(a1) + sqrt(disc));
+    if (r > rho) rho = r;
+  }
+  return rho;
 }
 
 // Stage segment `seg` of row `xr` into a warp window (cp.async when the 8 KB are inside the row and 16 B aligned).
@@ -562,23 +559,10 @@ __device__ __forceinline__ void stage_segment(const float* __restrict__ xr, int 
   }
 }
 
-// history: the two samples in front of this lane's chunk
-__device__ __forceinline__ void chunk_history(const float* __restrict__ xr, int t0, int T, const float* win, int lane,
-                                              float& h0, float& h1) {
-  if (lane == 0) {
-    h0 = (t0 >= 2 && t0 - 2 < T) ? __ldg(xr + t0 - 2) : 0.f;
-    h1 = (t0 >= 1 && t0 - 1 < T) ? __ldg(xr + t0 - 1) : 0.f;
-  } else {
-    const float2 h = *reinterpret_cast<const float2*>(&win[CHS * (lane - 1) + L2 - 2]);
-    h0 = h.x; h1 = h.y;
-  }
-}
-
 template <int NS>
 __global__ void __launch_bounds__(32 * WPB, 1)
 kweight_energy_warp_kernel(const float* __restrict__ x, int rows, int T, int Tp, int nseg, int run_len, int n_runs,
-                           Coef<NS> cf, const B2A_GRID_CONSTANT Tables2<NS> tbv, int* __restrict__ ticket,
-                           unsigned long long* __restrict__ recs, float* __restrict__ prefix,
+                           int n_warm, Coef<NS> cf, const B2A_GRID_CONSTANT Tables2<NS> tbv,
                            double* __restrict__ bins, int stride, int r, int nbins) {
   constexpr int D = 2 * NS;
   B2A_DYN_SMEM(smem);
@@ -587,41 +571,44 @@ kweight_energy_warp_kernel(const float* __restrict__ x, int rows, int T, int Tp,
   __shared__ float s_mlane[32][D * D];
   __shared__ float s_mscan[5][D * D];
   __shared__ float s_mseg[D * D];
-  __shared__ float s_mrun[33][D * D];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   for (int i = tid; i < (L2 + 2) * D; i += blockDim.x) (&s_wa[0][0])[i] = (&tbv.Wa[0][0])[i];
   for (int i = tid; i < 32 * D * D; i += blockDim.x) (&s_mlane[0][0])[i] = (&tbv.Mlane[0][0])[i];
   for (int i = tid; i < 5 * D * D; i += blockDim.x) (&s_mscan[0][0])[i] = (&tbv.Mscan[0][0])[i];
-  for (int i = tid; i < 33 * D * D; i += blockDim.x) (&s_mrun[0][0])[i] = (&tbv.Mrun[0][0])[i];
   if (tid < D * D) s_mseg[tid] = tbv.Mseg[tid];
   __syncthreads();  // the only CTA barrier: tables
   const int total = rows * n_runs;
   float* win0 = wins + (size_t)warp * 2 * BUF;
 
-  int cur = (int)blockIdx.x * WPB + warp;  // first tickets: one per resident warp; later ones from the counter
 #pragma unroll 1
-  while (cur < total) {
-    const int run = cur / rows, row = cur - run * rows;  // run-major: predecessors hold smaller tickets
+  for (int cur = (int)blockIdx.x * WPB + warp; cur < total; cur += (int)gridDim.x * WPB) {
+    const int run = cur / rows, row = cur - run * rows;
     const int seg0 = run * run_len, seg1 = min(nseg, seg0 + run_len);
+    const int segw = max(0, seg0 - n_warm);  // warm-up starts here, from a zero state
     const float* xr = x + (size_t)row * (size_t)T;
-    float* pfx = prefix + ((size_t)row * nseg) * (32 * D);
-    unsigned long long* myrec = recs + ((size_t)run * rows + row) * D;
-
-    // ================= pass 1: lane prefixes of every segment, run aggregate
-    float ragg[D];  // zero-state end state of the segments of the run processed so far (all lanes hold it)
+    double* rb = bins + (size_t)row * (size_t)nbins;
+    float carry[D];  // state entering the current segment (all lanes hold it)
 #pragma unroll
-    for (int j = 0; j < D; ++j) ragg[j] = 0.f;
-    stage_segment(xr, seg0, T, win0, lane);
+    for (int j = 0; j < D; ++j) carry[j] = 0.f;
+    stage_segment(xr, segw, T, win0, lane);
     int par = 0;
 #pragma unroll 1
-    for (int seg = seg0; seg < seg1; ++seg, par ^= 1) {
+    for (int seg = segw; seg < seg1; ++seg, par ^= 1) {
       cp_async_wait_all();
       __syncwarp();
       const float* win = win0 + par * BUF;
       if (seg + 1 < seg1) stage_segment(xr, seg + 1, T, win0 + (par ^ 1) * BUF, lane);
-      float h0, h1;
-      chunk_history(xr, seg * SEG, T, win, lane, h0, h1);
+      const int t0 = seg * SEG;
+      float h0, h1;  // the two samples in front of this lane's chunk
+      if (lane == 0) {
+        h0 = (t0 >= 2 && t0 - 2 < T) ? __ldg(xr + t0 - 2) : 0.f;
+        h1 = (t0 >= 1 && t0 - 1 < T) ? __ldg(xr + t0 - 1) : 0.f;
+      } else {
+        const float2 h = *reinterpret_cast<const float2*>(&win[CHS * (lane - 1) + L2 - 2]);
+        h0 = h.x; h1 = h.y;
+      }
       const float4* c4 = reinterpret_cast<const float4*>(&win[CHS * lane]);
+      // ---- zero-state end state of the lane's chunk as a linear map of its 66 inputs
       float g[D];
 #pragma unroll
       for (int i = 0; i < D; ++i) g[i] = fmaf(s_wa[0][i], h0, s_wa[1][i] * h1);
@@ -652,182 +639,89 @@ kweight_energy_warp_kernel(const float* __restrict__ x, int rows, int T, int Tp,
         if (lane == 0) ex[j] = 0.f;
         agg[j] = __shfl_sync(0xffffffffu, g[j], 31);
       }
-      // state entering this segment when the run starts from zero: lane prefix = ex + Mlane[lane] ragg
-      float st[D];
+      if (seg >= seg0) {
+        // ---- true start state, recursion, energies into the interval bins
+        float y1[NS], y2[NS];
+        {
+          float st[D];
 #pragma unroll
-      for (int i = 0; i < D; ++i) st[i] = ex[i] + row_dot<D>(s_mlane[lane], i, ragg);
-      float* pp = pfx + ((size_t)seg * 32 + lane) * D;
+          for (int i = 0; i < D; ++i) st[i] = ex[i] + row_dot<D>(s_mlane[lane], i, carry);
 #pragma unroll
-      for (int i = 0; i < D; ++i) pp[i] = st[i];
-      float rn[D];  // run aggregate <- A^SEG ragg + agg
+          for (int s = 0; s < NS; ++s) { y1[s] = st[2 * s]; y2[s] = st[2 * s + 1]; }
+        }
+        const int n0 = t0 + lane * L2;
+        const int nv = min(L2, max(0, Tp - n0));
+        int j0 = n0 / stride, rem0 = n0 - j0 * stride;
+        int b0 = 2 * j0 + (rem0 >= r ? 1 : 0);
+        int end0 = (b0 & 1) ? (j0 + 1) * stride : j0 * stride + r;
+        const int s1 = min(end0 - n0, L2);
+        int s2 = L2, b1 = b0, b2 = b0;
+        if (s1 < L2) {
+          const int n1 = n0 + s1, j1 = n1 / stride, rem1 = n1 - j1 * stride;
+          b1 = 2 * j1 + (rem1 >= r ? 1 : 0);
+          const int end1 = (b1 & 1) ? (j1 + 1) * stride : j1 * stride + r;
+          s2 = min(end1 - n0, L2);
+          if (s2 < L2) {
+            const int n2 = n0 + s2, j2 = n2 / stride, rem2 = n2 - j2 * stride;
+            b2 = 2 * j2 + (rem2 >= r ? 1 : 0);
+          }
+        }
+        const bool simple = (s1 >= L2) && (nv == L2);
+        const bool clean = __all_sync(0xffffffffu, simple);  // warp-uniform: no lane straddles an interval boundary
+        float a0 = 0.f, a1 = 0.f, a2 = 0.f;
+        float xm2 = h0, xm1 = h1;
+        if (clean) {
+          float acc = 0.f;
 #pragma unroll
-      for (int i = 0; i < D; ++i) rn[i] = agg[i] + row_dot<D>(s_mseg, i, ragg);
+          for (int i4 = 0; i4 < L2 / 4; ++i4) {
+            const float4 q = c4[i4];
+            const float qs[4] = {q.x, q.y, q.z, q.w};
 #pragma unroll
-      for (int i = 0; i < D; ++i) ragg[i] = rn[i];
-      __syncwarp();  // the window just read is re-filled two iterations from now by other lanes' cp.async
-    }
-    if (lane < D) {  // publish the run's aggregate (the last run of a row is nobody's predecessor: harmless)
-      float a = ragg[0];
-#pragma unroll
-      for (int j = 1; j < D; ++j) a = (lane == j) ? ragg[j] : a;
-      rec_store(myrec + lane, a);
-    }
-    // prefetch the first segment of pass 2 while the carry is resolved
-    stage_segment(xr, seg0, T, win0, lane);
-
-    // ================= carry: S_in = sum_{j < run} Mrun^(run - 1 - j) aggregate_j, 32 predecessors per probe
-    float sin_[D];
-#pragma unroll
-    for (int j = 0; j < D; ++j) sin_[j] = 0.f;
-    if (run > 0) {
-      float mpow[D * D];  // Mrun^(32 * window index)
-#pragma unroll
-      for (int i = 0; i < D * D; ++i) mpow[i] = (i / D == i % D) ? 1.f : 0.f;
-      for (int base = run - 1; base >= 0; base -= 32) {
-        const int pj = base - lane;
-        float va[D];
-#pragma unroll
-        for (int j = 0; j < D; ++j) va[j] = 0.f;
-        bool ok = pj < 0;
-        while (!__all_sync(0xffffffffu, ok)) {
-          if (!ok) {
-            const unsigned long long* rec = recs + ((size_t)pj * rows + row) * D;
-            bool all = true;
-#pragma unroll
-            for (int j = 0; j < D; ++j) {
-              const unsigned long long w = rec_load(rec + j);
-              all &= (w >> 32) != 0;
-              va[j] = __int_as_float((int)(unsigned)(w & 0xffffffffu));
+            for (int e = 0; e < 4; ++e) {
+              const float y = cascade_step<NS, float>(cf.b0, cf.b1, cf.b2, cf.a1, cf.a2, qs[e], xm1, xm2, y1, y2);
+              xm2 = xm1; xm1 = qs[e];
+              acc = fmaf(y, y, acc);
             }
-            ok = all;
           }
-        }
-        float term[D];
+          a0 = acc;
+        } else {
+          float acc = 0.f, p1 = 0.f, p2 = 0.f;  // running energy and its value at the two interval boundaries
 #pragma unroll
-        for (int i = 0; i < D; ++i) term[i] = (pj >= 0) ? row_dot<D>(s_mrun[lane], i, va) : 0.f;
+          for (int i4 = 0; i4 < L2 / 4; ++i4) {
+            const float4 q = c4[i4];
+            const float qs[4] = {q.x, q.y, q.z, q.w};
 #pragma unroll
-        for (int i = 0; i < D; ++i) term[i] = warp_sum(term[i]);
-#pragma unroll
-        for (int i = 0; i < D; ++i) sin_[i] += row_dot<D>(mpow, i, term);
-        if (base - 32 >= 0) {
-          float pn[D * D];  // mpow <- mpow * Mrun^32
-#pragma unroll
-          for (int i = 0; i < D; ++i)
-#pragma unroll
-            for (int j = 0; j < D; ++j) {
-              float a = 0.f;
-#pragma unroll
-              for (int k = 0; k < D; ++k) a = fmaf(mpow[i * D + k], s_mrun[32][k * D + j], a);
-              pn[i * D + j] = a;
+            for (int e = 0; e < 4; ++e) {
+              const int i = 4 * i4 + e;
+              p1 = (i == s1) ? acc : p1;
+              p2 = (i == s2) ? acc : p2;
+              const float y = cascade_step<NS, float>(cf.b0, cf.b1, cf.b2, cf.a1, cf.a2, qs[e], xm1, xm2, y1, y2);
+              xm2 = xm1; xm1 = qs[e];
+              acc = (i < nv) ? fmaf(y, y, acc) : acc;
             }
-#pragma unroll
-          for (int i = 0; i < D * D; ++i) mpow[i] = pn[i];
-        }
-      }
-    }
-
-    // ================= pass 2: true start states, recursion, energies into the interval bins
-    double* rb = bins + (size_t)row * (size_t)nbins;
-    float srun[D];  // state entering the current segment
-#pragma unroll
-    for (int j = 0; j < D; ++j) srun[j] = sin_[j];
-    par = 0;
-#pragma unroll 1
-    for (int seg = seg0; seg < seg1; ++seg, par ^= 1) {
-      cp_async_wait_all();
-      __syncwarp();
-      const float* win = win0 + par * BUF;
-      if (seg + 1 < seg1) stage_segment(xr, seg + 1, T, win0 + (par ^ 1) * BUF, lane);
-      const int t0 = seg * SEG;
-      float h0, h1;
-      chunk_history(xr, t0, T, win, lane, h0, h1);
-      const float4* c4 = reinterpret_cast<const float4*>(&win[CHS * lane]);
-      // lane start state = stored zero-run prefix + A^(samples from the run start to this chunk) S_in
-      //                  = prefix + Mlane[lane] (A^(SEG (seg - seg0)) S_in) ;  srun carries the bracket
-      float y1[NS], y2[NS];
-      {
-        const float* pp = pfx + ((size_t)seg * 32 + lane) * D;
-        float st[D];
-#pragma unroll
-        for (int i = 0; i < D; ++i) st[i] = pp[i] + row_dot<D>(s_mlane[lane], i, srun);
-#pragma unroll
-        for (int s = 0; s < NS; ++s) { y1[s] = st[2 * s]; y2[s] = st[2 * s + 1]; }
-        float sn[D];
-#pragma unroll
-        for (int i = 0; i < D; ++i) sn[i] = row_dot<D>(s_mseg, i, srun);
-#pragma unroll
-        for (int i = 0; i < D; ++i) srun[i] = sn[i];
-      }
-      const int n0 = t0 + lane * L2;
-      const int nv = min(L2, max(0, Tp - n0));
-      int j0 = n0 / stride, rem0 = n0 - j0 * stride;
-      int b0 = 2 * j0 + (rem0 >= r ? 1 : 0);
-      int end0 = (b0 & 1) ? (j0 + 1) * stride : j0 * stride + r;
-      const int s1 = min(end0 - n0, L2);
-      int s2 = L2, b1 = b0, b2 = b0;
-      if (s1 < L2) {
-        const int n1 = n0 + s1, j1 = n1 / stride, rem1 = n1 - j1 * stride;
-        b1 = 2 * j1 + (rem1 >= r ? 1 : 0);
-        const int end1 = (b1 & 1) ? (j1 + 1) * stride : j1 * stride + r;
-        s2 = min(end1 - n0, L2);
-        if (s2 < L2) {
-          const int n2 = n0 + s2, j2 = n2 / stride, rem2 = n2 - j2 * stride;
-          b2 = 2 * j2 + (rem2 >= r ? 1 : 0);
-        }
-      }
-      const bool simple = (s1 >= L2) && (nv == L2);
-      const bool clean = __all_sync(0xffffffffu, simple);  // warp-uniform: no lane straddles an interval boundary
-      float a0 = 0.f, a1 = 0.f, a2 = 0.f;
-      float xm2 = h0, xm1 = h1;
-      if (clean) {
-        float acc = 0.f;
-#pragma unroll
-        for (int i4 = 0; i4 < L2 / 4; ++i4) {
-          const float4 q = c4[i4];
-          const float qs[4] = {q.x, q.y, q.z, q.w};
-#pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            const float y = cascade_step<NS, float>(cf.b0, cf.b1, cf.b2, cf.a1, cf.a2, qs[e], xm1, xm2, y1, y2);
-            xm2 = xm1; xm1 = qs[e];
-            acc = fmaf(y, y, acc);
           }
+          if (s1 >= L2) p1 = acc;
+          if (s2 >= L2) p2 = acc;
+          a0 = p1; a1 = p2 - p1; a2 = acc - p2;
         }
-        a0 = acc;
-      } else {
-        float acc = 0.f, p1 = 0.f, p2 = 0.f;  // running energy and its value at the two interval boundaries
-#pragma unroll
-        for (int i4 = 0; i4 < L2 / 4; ++i4) {
-          const float4 q = c4[i4];
-          const float qs[4] = {q.x, q.y, q.z, q.w};
-#pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            const int i = 4 * i4 + e;
-            p1 = (i == s1) ? acc : p1;
-            p2 = (i == s2) ? acc : p2;
-            const float y = cascade_step<NS, float>(cf.b0, cf.b1, cf.b2, cf.a1, cf.a2, qs[e], xm1, xm2, y1, y2);
-            xm2 = xm1; xm1 = qs[e];
-            acc = (i < nv) ? fmaf(y, y, acc) : acc;
-          }
+        // one atomic per interval the warp touched (intervals are monotonic in the lane index)
+        const int blast = (s2 < L2) ? b2 : ((s1 < L2) ? b1 : b0);  // last interval this lane's chunk reaches
+        const int bf = __shfl_sync(0xffffffffu, b0, 0), bl = __shfl_sync(0xffffffffu, blast, 31);
+        for (int id = bf; id <= bl; ++id) {
+          float v = (b0 == id) ? a0 : 0.f;
+          if (!clean) v += ((s1 < L2 && b1 == id) ? a1 : 0.f) + ((s2 < L2 && b2 == id) ? a2 : 0.f);
+          v = warp_sum(v);
+          if (lane == 0 && id < nbins) atomicAdd(rb + id, (double)v);
         }
-        if (s1 >= L2) p1 = acc;
-        if (s2 >= L2) p2 = acc;
-        a0 = p1; a1 = p2 - p1; a2 = acc - p2;
       }
-      // one atomic per interval the warp touched (intervals are monotonic in the lane index)
-      const int blast = (s2 < L2) ? b2 : ((s1 < L2) ? b1 : b0);  // last interval this lane's chunk reaches
-      const int bf = __shfl_sync(0xffffffffu, b0, 0), bl = __shfl_sync(0xffffffffu, blast, 31);
-      for (int id = bf; id <= bl; ++id) {
-        float v = (b0 == id) ? a0 : 0.f;
-        if (!clean) v += ((s1 < L2 && b1 == id) ? a1 : 0.f) + ((s2 < L2 && b2 == id) ? a2 : 0.f);
-        v = warp_sum(v);
-        if (lane == 0 && id < nbins) atomicAdd(rb + id, (double)v);
-      }
-      __syncwarp();
+      // ---- carry into the next segment: A^SEG carry + (zero-state end state of this segment)
+      float cn[D];
+#pragma unroll
+      for (int i = 0; i < D; ++i) cn[i] = agg[i] + row_dot<D>(s_mseg, i, carry);
+#pragma unroll
+      for (int i = 0; i < D; ++i) carry[i] = cn[i];
+      __syncwarp();  // every lane is done with this window before the next iteration's cp.async refills it
     }
-    // next run (only when there are more runs than resident warps)
-    int nx = 0;
-    if (lane == 0) nx = (int)gridDim.x * WPB + atomicAdd(ticket, 1);
-    cur = __shfl_sync(0xffffffffu, nx, 0);
   }
   cp_async_wait_all();
 }
@@ -1027,27 +921,36 @@ static int run(const float* x, int64_t B, int C, int64_t T, int64_t Tp, const Ge
                (int)T, (int)Tp, g.ntile, cf, tbh, (int*)(base + w.ticket),
                (unsigned long long*)(base + w.recs), (double*)(base + w.bins), g.stride, g.r, g.nbins);
   } else {
-    // runs per row: as many as there are resident warps for (one CTA of 12 warps per SM), at least one
+    // runs per row: as many as there are resident warps for (one CTA of 12 warps per SM), but long enough that the
+    // warm-up (n_warm segments in front of every run but the first) stays a small fraction of the work
 #ifdef B2A_SIM
     const int64_t resident = 1;
 #else
     const int64_t resident = sms;
 #endif
+    const double rho = v2::max_pole_radius<NS>(cf);
+    B2A_REQUIRE(rho < 1.0, B2A_E_UNSUPPORTED, "lufs: unstable filter (pole radius %g)", rho);
+    int n_warm = 1;
+    if (rho > 0.0) {
+      const double n_tail = 40.0 * 0.6931471805599453 / -log(rho);  // rho^n_tail = 2^-40
+      n_warm = (int)((n_tail + v2::SEG - 1) / v2::SEG);
+      if (n_warm < 1) n_warm = 1;
+    }
     int64_t rpr = (resident * v2::WPB) / rows;
     if (rpr < 1) rpr = 1;
-    if (rpr > g.nseg) rpr = g.nseg;
-    const int run_len = (int)((g.nseg + rpr - 1) / rpr);
+    int run_len = (int)((g.nseg + rpr - 1) / rpr);
+    if (run_len < 4 * n_warm) run_len = 4 * n_warm;  // at most 25 % warm-up
+    if (run_len > g.nseg) run_len = g.nseg;
     const int n_runs = (g.nseg + run_len - 1) / run_len;
     v2::Tables2<NS> tb2;
-    v2::build_tables2<NS>(cf, run_len, &tb2);
+    v2::build_tables2<NS>(cf, &tb2);
     const size_t smem = (size_t)v2::WPB * 2 * v2::BUF * sizeof(float);
     B2A_CUDA_OK(cudaFuncSetAttribute(v2::kweight_energy_warp_kernel<NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int64_t runs_all = rows * n_runs;
     const int64_t want = (runs_all + v2::WPB - 1) / v2::WPB;
     B2A_LAUNCH(v2::kweight_energy_warp_kernel<NS>, dim3((unsigned)(want < resident ? want : resident)), dim3(32 * v2::WPB), smem,
-               stream, x, (int)rows, (int)T, (int)Tp, g.nseg, run_len, n_runs, cf, tb2, (int*)(base + w.ticket),
-               (unsigned long long*)(base + w.recs), (float*)(base + w.prefix), (double*)(base + w.bins), g.stride, g.r,
-               g.nbins);
+               stream, x, (int)rows, (int)T, (int)Tp, g.nseg, run_len, n_runs, n_warm, cf, tb2, (double*)(base + w.bins),
+               g.stride, g.r, g.nbins);
   }
   GateParams gp;
   for (int c = 0; c < 8; ++c) gp.G[c] = c < C ? chan_gain_h[c] : 0.0;

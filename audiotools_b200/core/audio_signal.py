@@ -37,6 +37,11 @@ def _engine():
     return get_engine()
 
 
+def _on_engine(t) -> bool:
+    """CUDA tensor, or any tensor when the engine is the CPU-simulated build of the kernels (tests)."""
+    return t.is_cuda or not _engine().require_cuda
+
+
 @functools.lru_cache(None)
 def _cached_window(window_type: str, window_length: int, device: str) -> torch.Tensor:
     from scipy import signal
@@ -109,6 +114,81 @@ class AudioSignal(EffectMixin, LoudnessMixin, ImpulseResponseMixin, DSPMixin):
         return cls(w.float().unsqueeze(0).unsqueeze(0).repeat(1, num_channels, 1), sample_rate, **kwargs)
 
     @classmethod
+    def excerpt(cls, source, offset: float = None, duration: float = None, state=None, **kwargs):
+        """Randomly draw an excerpt of ``duration`` seconds between ``offset`` seconds and the end of ``source``
+        (ref:audiotools/core/audio_signal.py:178-225).  ``source`` is an in-memory ``AudioSignal`` (batch size 1):
+        decoding files is outside the hot path, so the reference's ``audio_path`` is not accepted.
+        The window starts at sample ``int(offset * sample_rate)`` and has ``int(duration * sample_rate)`` samples
+        (zero-padded past the end, like a short read)."""
+        if not isinstance(source, AudioSignal):
+            raise NotImplementedError("excerpt / salient_excerpt take an in-memory AudioSignal (file decoding is out "
+                                      "of scope: SURVEY.md 2)")
+        assert source.batch_size == 1, "excerpt: the source must hold one item"
+        state = util.random_state(state)
+        lower = 0 if offset is None else offset
+        upper = max(source.signal_duration - duration, 0)
+        off = state.uniform(lower, upper)
+        n = int(duration * source.sample_rate)
+        start = int(off * source.sample_rate)
+        x = source.audio_data
+        if _on_engine(x):
+            data = _engine().pack_rows([x], n, offsets=[start])
+        else:
+            data = torch.zeros(1, x.shape[1], n, dtype=x.dtype)
+            seg = x[..., start:start + n]
+            data[..., : seg.shape[-1]] = seg
+        sig = cls(data, source.sample_rate, **kwargs)
+        sig.metadata["offset"], sig.metadata["duration"] = off, duration
+        return sig
+
+    @classmethod
+    def salient_excerpt(cls, source, loudness_cutoff: float = None, num_tries: int = 8, state=None, **kwargs):
+        """``excerpt`` that only accepts windows louder than ``loudness_cutoff`` dB LUFS, giving up after
+        ``num_tries`` draws (ref:audiotools/core/audio_signal.py:227-286).  On the device the candidates are screened
+        as a BATCH: all pending offsets are drawn from a copy of ``state``, gathered with one launch
+        of csrc/collate.cu, measured with one call of the loudness kernels, and the first one above the cutoff wins;
+        ``state`` is then advanced by exactly the number of draws the reference's loop would have made."""
+        state = util.random_state(state)
+        if loudness_cutoff is None:
+            return cls.excerpt(source, state=state, **kwargs)
+        if not isinstance(source, AudioSignal):
+            raise NotImplementedError("excerpt / salient_excerpt take an in-memory AudioSignal (file decoding is out "
+                                      "of scope: SURVEY.md 2)")
+        assert source.batch_size == 1, "salient_excerpt: the source must hold one item"
+        offset, duration = kwargs.pop("offset", None), kwargs.pop("duration", None)
+        lower = 0 if offset is None else offset
+        upper = max(source.signal_duration - duration, 0)
+        n = int(duration * source.sample_rate)
+        x = source.audio_data
+        tried = 0
+        while True:
+            chunk = 8 if num_tries is None else min(8, num_tries - tried)
+            probe = np.random.RandomState()
+            probe.set_state(state.get_state())
+            offs = [probe.uniform(lower, upper) for _ in range(chunk)]
+            starts = [int(o * source.sample_rate) for o in offs]
+            if _on_engine(x):
+                cand = _engine().pack_rows([x] * chunk, n, offsets=starts)
+            else:
+                cand = torch.zeros(chunk, x.shape[1], n, dtype=x.dtype)
+                for i, st in enumerate(starts):
+                    seg = x[0, :, st:st + n]
+                    cand[i, :, : seg.shape[-1]] = seg
+            loud = cls(cand, source.sample_rate).loudness().cpu().numpy()
+            above = np.nonzero(loud > loudness_cutoff)[0]
+            last = tried + chunk >= num_tries if num_tries is not None else False
+            if len(above) or last:
+                k = int(above[0]) if len(above) else chunk - 1
+                for _ in range(k + 1):  # the draws the reference's sequential loop makes
+                    state.uniform(lower, upper)
+                sig = cls(cand[k:k + 1].clone(), source.sample_rate, **kwargs)
+                sig.metadata["offset"], sig.metadata["duration"] = offs[k], duration
+                return sig
+            for _ in range(chunk):
+                state.uniform(lower, upper)
+            tried += chunk
+
+    @classmethod
     def batch(cls, audio_signals: list, pad_signals: bool = False, truncate_signals: bool = False,
               resample: bool = False, dim: int = 0):
         lengths = [s.signal_length for s in audio_signals]
@@ -121,18 +201,30 @@ class AudioSignal(EffectMixin, LoudnessMixin, ImpulseResponseMixin, DSPMixin):
             for s in audio_signals:
                 s.resample(rates[0])
         if len(set(lengths)) != 1:
-            if pad_signals:
-                longest = max(lengths)
-                for s in audio_signals:
-                    s.zero_pad(0, longest - s.signal_length)
-            elif truncate_signals:
-                shortest = min(lengths)
-                for s in audio_signals:
-                    s.truncate_samples(shortest)
-            else:
+            if not (pad_signals or truncate_signals):
                 raise RuntimeError(
                     f"Not all signals had the same length! Got {lengths}. "
                     f"All signals must be the same length, or pad_signals/truncate_signals must be True. ")
+            target = max(lengths) if pad_signals else min(lengths)
+            datas = [s.audio_data for s in audio_signals]
+            if (dim == 0 and all(_on_engine(d) and d.device == datas[0].device for d in datas)
+                    and len({d.shape[1] for d in datas}) == 1):
+                # device collate: ONE gather launch writes the padded / truncated batch; the inputs
+                # become views of it, which is the state the reference's in-place zero_pad / truncate_samples leaves
+                packed = _engine().pack_rows(datas, target)
+                i = 0
+                for s in audio_signals:
+                    b = s.batch_size
+                    s.audio_data = packed[i:i + b]
+                    i += b
+                out = cls(packed, sample_rate=audio_signals[0].sample_rate)
+                out.path_to_file = [s.path_to_file for s in audio_signals]
+                return out
+            for s in audio_signals:
+                if pad_signals:
+                    s.zero_pad(0, target - s.signal_length)
+                else:
+                    s.truncate_samples(target)
         out = cls(torch.cat([s.audio_data for s in audio_signals], dim=dim), sample_rate=audio_signals[0].sample_rate)
         out.path_to_file = [s.path_to_file for s in audio_signals]
         return out

@@ -13,6 +13,13 @@ def _engine():
     return get_engine()
 
 
+def _on_engine(t) -> bool:
+    """The kernels take this tensor: a CUDA tensor -- or, in the CPU tests, any tensor when the engine is the
+    simulated build of the same kernel sources (``require_cuda=False``); plain CPU tensors otherwise keep the
+    container's tensor arithmetic (host-logic tests)."""
+    return t.is_cuda or not _engine().require_cuda
+
+
 class EffectMixin:
     GAIN_FACTOR = np.log(10) / 20
     """Gain factor for converting between amplitude and decibels."""
@@ -25,7 +32,14 @@ class EffectMixin:
         if other_eq is not None:
             other = other.equalizer(other_eq)
         other = other.normalize(self.loudness() - snr)
-        self.audio_data = self.audio_data + other.audio_data
+        if _on_engine(self._audio_data):  # the noise's deferred normalisation gain and the add: one pass (csrc/effects.cu)
+            g, other._pending_gain = other._pending_gain, None
+            mixed = _engine().mix(self._materialized(), other._audio_data, g)
+            if g is not None:
+                other._pending_gain = g  # `other` keeps its own (still deferred) state
+            self.audio_data = mixed
+        else:
+            self.audio_data = self.audio_data + other.audio_data
         return self
 
     def convolve(self, other, start_at_max: bool = True):
@@ -44,19 +58,31 @@ class EffectMixin:
             ir = ir.equalizer(ir_eq)
         if drr is not None:
             ir = ir.alter_drr(drr)
-        max_spk = self.audio_data.abs().max(dim=-1, keepdims=True).values
+        cuda = _on_engine(self._audio_data)
+        max_spk = _engine().row_absmax(self._materialized()) if cuda else \
+            self.audio_data.abs().max(dim=-1, keepdims=True).values
         phase = self.phase if use_original_phase else None
         self.convolve(ir)
         if use_original_phase:
             self.stft()
             self.stft_data = self.magnitude * torch.exp(1j * phase)
             self.istft()
-        max_transformed = self.audio_data.abs().max(dim=-1, keepdims=True).values
+        max_transformed = _engine().row_absmax(self._materialized()) if cuda else \
+            self.audio_data.abs().max(dim=-1, keepdims=True).values
         scale = max_spk.clamp(1e-8) / max_transformed.clamp(1e-8)
-        self.audio_data = self.audio_data * scale
+        if cuda:  # per-row scale: the gain kernel with one "item" per (batch, channel) row
+            x = self._materialized()
+            self.audio_data = _engine().gain(x.reshape(-1, 1, x.shape[-1]), scale.reshape(-1)).reshape(x.shape)
+        else:
+            self.audio_data = self.audio_data * scale
         return self
 
     def ensure_max_of_audio(self, max: float = 1.0):
+        """Scale every (item, channel) row whose peak exceeds ``max`` down to it (ref :181-198): a peak pass and a
+        scale pass of csrc/effects.cu."""
+        if _on_engine(self._audio_data):
+            self.audio_data = _engine().limit_peak(self._materialized(), float(max))
+            return self
         peak = self.audio_data.abs().max(dim=-1, keepdims=True)[0]
         peak_gain = torch.where(peak > max, max / peak, torch.ones_like(peak))  # no boolean-mask host sync
         self.audio_data = self.audio_data * peak_gain
@@ -125,7 +151,20 @@ class EffectMixin:
         return self
 
     def clip_distortion(self, clip_percentile):
+        """Clip at the ``clip_percentile / 2`` and ``1 - clip_percentile / 2`` quantiles (ref :435-461).  The reference
+        indexes ``torch.quantile``'s [Q, B, C] result as [:, :nc, :], i.e. item i is clipped at the quantiles q_i of
+        ROW 0 of the batch (and the call only broadcasts for mono signals); reproduced as is: radix-selected order
+        statistics of row 0 + one clamp pass (csrc/effects.cu), no sort."""
         clip_percentile = util.ensure_tensor(clip_percentile, ndim=1)
+        if _on_engine(self._audio_data) and self.num_channels == 1:
+            x = self._materialized()
+            q = clip_percentile.to(x.device).float().reshape(-1)
+            if q.numel() == 1:
+                q = q.expand(self.batch_size)
+            assert q.numel() == self.batch_size
+            thr = _engine().quantile(x[0, 0], torch.cat([q / 2, 1 - (q / 2)]))
+            self.audio_data = _engine().clamp_items(x, thr[: self.batch_size], thr[self.batch_size:])
+            return self
         min_thresh = torch.quantile(self.audio_data, clip_percentile / 2, dim=-1)
         max_thresh = torch.quantile(self.audio_data, 1 - (clip_percentile / 2), dim=-1)
         nc = self.audio_data.shape[1]
@@ -133,6 +172,9 @@ class EffectMixin:
         return self
 
     def quantization(self, quantization_channels):
+        if _on_engine(self._audio_data):
+            self.audio_data = _engine().quantize(self._materialized(), util.ensure_tensor(quantization_channels, ndim=1))
+            return self
         q = util.ensure_tensor(quantization_channels, ndim=3).to(self.device)
         x = self.audio_data
         x = (x + 1) / 2
@@ -141,6 +183,10 @@ class EffectMixin:
         return self
 
     def mulaw_quantization(self, quantization_channels):
+        if _on_engine(self._audio_data):
+            self.audio_data = _engine().quantize(self._materialized(), util.ensure_tensor(quantization_channels, ndim=1),
+                                                 mulaw=True)
+            return self
         mu = util.ensure_tensor(quantization_channels, ndim=3).to(self.device) - 1.0
         x = self.audio_data
         x = torch.sign(x) * torch.log1p(mu * torch.abs(x)) / torch.log1p(mu)
@@ -186,7 +232,10 @@ class ImpulseResponseMixin:
         drr = util.ensure_tensor(drr, 2, self.batch_size).to(self.device)
         early, late, window = self.decompose_ir()
         alpha = self.solve_alpha(early, late, window, drr)
-        min_alpha = late.abs().max(dim=-1)[0] / early.abs().max(dim=-1)[0]
+        if _on_engine(self._audio_data):
+            min_alpha = (_engine().row_absmax(late) / _engine().row_absmax(early))[..., 0]
+        else:
+            min_alpha = late.abs().max(dim=-1)[0] / early.abs().max(dim=-1)[0]
         alpha = torch.maximum(alpha, min_alpha)[..., None]
         self.audio_data = alpha * window * early + ((1 - window) * early) + late
         self.ensure_max_of_audio()

@@ -232,6 +232,122 @@ class Engine:
         self.launches += 1
         return out
 
+    # ------------------------------------------------------------------ collate (csrc/collate.cu)
+    def pack_rows(self, items, T_out: int, offsets=None) -> torch.Tensor:
+        """Ragged ``items`` (tensors [C, T_i] or [b_i, C, T_i], float32, one device, same C) -> one zero-padded /
+        truncated batch [sum b_i, C, T_out] in ONE launch (ref:audiotools/core/audio_signal.py:380-470).
+        ``offsets`` (one int per item): the window starts at that sample of the item (negative / past-the-end
+        samples read as zero) -- the excerpt gather of ``salient_excerpt``."""
+        views, C = [], None
+        for k, t in enumerate(items):
+            t = self._prep(t, "item")
+            t3 = t if t.ndim == 3 else t.reshape(1, *t.shape[-2:])
+            C = t3.shape[1] if C is None else C
+            assert t3.shape[1] == C, "pack_rows: items must have the same number of channels"
+            off = 0 if offsets is None else int(offsets[k])
+            for b in range(t3.shape[0]):
+                views.append((t3[b], off))
+        dev = views[0][0].device
+        n = len(views)
+        table = torch.tensor([[v.data_ptr(), v.shape[-1], v.stride(0) if v.shape[0] > 1 else v.shape[-1], o]
+                              for v, o in views], dtype=torch.int64).t().contiguous()
+        table = table.to(dev, non_blocking=True)  # [4, n]: pointers, lengths, row strides, offsets
+        out = torch.empty(n, C, int(T_out), dtype=torch.float32, device=dev)
+        rc = self.lib.b2a_pack_rows_f32(_dptr(table[0]), _dptr(table[1]), _dptr(table[2]), _dptr(table[3]), n, int(C),
+                                        int(T_out), _dptr(out), self._stream(out))
+        self.lib.check(rc)
+        self.launches += 1
+        out._b2a_keepalive = [v for v, _ in views]  # the sources must outlive the (asynchronous) gather
+        return out
+
+    # ------------------------------------------------------------------ element-wise / peak effects (csrc/effects.cu)
+    def row_absmax(self, x: torch.Tensor) -> torch.Tensor:
+        """``x.abs().max(dim=-1, keepdim=True)`` for x [..., T] (ref:audiotools/core/effects.py:155,176,194)."""
+        x = self._prep(x, "x")
+        T = x.shape[-1]
+        rows = x.numel() // T
+        peak = torch.empty(*x.shape[:-1], 1, dtype=torch.float32, device=x.device)
+        self.lib.check(self.lib.b2a_row_absmax_f32(_dptr(x), rows, T, _dptr(peak), self._stream(x)))
+        self.launches += 1
+        return peak
+
+    def limit_peak(self, x: torch.Tensor, max_abs: float = 1.0, peak: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """``ensure_max_of_audio`` (ref :181-198): rows whose peak exceeds ``max_abs`` are scaled by max_abs / peak."""
+        x = self._prep(x, "x")
+        T = x.shape[-1]
+        rows = x.numel() // T
+        if peak is None:
+            peak = self.row_absmax(x)
+        out = torch.empty_like(x)
+        self.lib.check(self.lib.b2a_limit_peak_f32(_dptr(x), _dptr(out), rows, T, _dptr(peak), float(max_abs),
+                                                   self._stream(x)))
+        self.launches += 1
+        return out
+
+    def mix(self, x: torch.Tensor, other: torch.Tensor, other_gain: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """``x + other_gain[item] * other`` (ref :27-64: the noise's normalize() multiply and the add, one pass)."""
+        x = self._prep(x, "x")
+        other = self._prep(other, "other")
+        assert other.shape == x.shape, (other.shape, x.shape)
+        B = x.shape[0]
+        if other_gain is not None:
+            other_gain = self._prep(other_gain.reshape(-1), "other_gain")
+            assert other_gain.numel() == B
+        out = torch.empty_like(x)
+        self.lib.check(self.lib.b2a_mix_f32(_dptr(x), _dptr(other), _dptr(other_gain), _dptr(out), B, x.numel() // B,
+                                            self._stream(x)))
+        self.launches += 1
+        return out
+
+    def quantize(self, x: torch.Tensor, channels: torch.Tensor, mulaw: bool = False) -> torch.Tensor:
+        """Linear (ref :463-491) or mu-law (ref :493-523) quantisation to ``channels`` (1 or B values) levels."""
+        x = self._prep(x, "x")
+        B = x.shape[0]
+        channels = self._prep(torch.as_tensor(channels).to(x.device).reshape(-1).float(), "channels")
+        if channels.numel() == 1:
+            channels = channels.expand(B).contiguous()
+        assert channels.numel() == B
+        out = torch.empty_like(x)
+        self.lib.check(self.lib.b2a_quantize_f32(_dptr(x), _dptr(out), B, x.numel() // B, _dptr(channels), int(mulaw),
+                                                 self._stream(x)))
+        self.launches += 1
+        return out
+
+    def order_stats(self, row: torch.Tensor, k: torch.Tensor) -> torch.Tensor:
+        """The ``k[i]``-th smallest values (0-based) of a 1-D float32 tensor, exactly (radix selection, no sort)."""
+        row = self._prep(row.reshape(-1), "row")
+        k = k.to(row.device).reshape(-1).to(torch.int64).contiguous()
+        out = torch.empty(k.numel(), dtype=torch.float32, device=row.device)
+        self.lib.check(self.lib.b2a_order_stats_f32(_dptr(row), row.numel(), _dptr(k), k.numel(), _dptr(out),
+                                                    self._stream(row)))
+        self.launches += 1
+        return out
+
+    def quantile(self, row: torch.Tensor, q: torch.Tensor) -> torch.Tensor:
+        """``torch.quantile(row, q)`` (linear interpolation; aten's float32 rank arithmetic and lerp) for a 1-D row."""
+        n = row.numel()
+        q = q.to(row.device).reshape(-1).float()
+        ranks = q * (n - 1)
+        below = ranks.floor()
+        w = ranks - below
+        ks = torch.cat([below, ranks.ceil()]).to(torch.int64)
+        v = self.order_stats(row, ks)
+        a, b = v[: q.numel()], v[q.numel():]
+        return torch.where(w < 0.5, a + w * (b - a), b - (b - a) * (1 - w))
+
+    def clamp_items(self, x: torch.Tensor, lo: torch.Tensor, hi: torch.Tensor) -> torch.Tensor:
+        """``x.clamp(lo[item], hi[item])`` (ref :459)."""
+        x = self._prep(x, "x")
+        B = x.shape[0]
+        lo = self._prep(lo.to(x.device).reshape(-1), "lo")
+        hi = self._prep(hi.to(x.device).reshape(-1), "hi")
+        assert lo.numel() == B and hi.numel() == B
+        out = torch.empty_like(x)
+        self.lib.check(self.lib.b2a_clamp_items_f32(_dptr(x), _dptr(out), B, x.numel() // B, _dptr(lo), _dptr(hi),
+                                                    self._stream(x)))
+        self.launches += 1
+        return out
+
     # ------------------------------------------------------------------ STFT / mel
     def _packed_len(self, mel_lo: torch.Tensor, mel_hi: torch.Tensor, n_fft: int) -> int:
         """Floats of the shared-memory band table of csrc/spectral.cu: row m is filter m's 4-aligned band, padded

@@ -209,6 +209,35 @@ size_t b2a_time_stretch_workspace_bytes(int64_t rows, int64_t T, int sr, double 
 int b2a_time_stretch_f32(const float* x, int64_t rows, int64_t T, int sr, double factor, float* out, void* ws,
                          size_t ws_bytes, void* stream);
 
+/* ---- element-wise / per-row-peak effects (csrc/effects.cu; audiotools/core/effects.py:27-64,181-198,435-523) -------
+ * One pass over the waveform each; x, out: [B or rows, per_item or T] float32 contiguous, device pointers.
+ *   b2a_row_absmax_f32   peak[row] = max |x[row, :]|  (ensure_max_of_audio :194, apply_ir's peak restore :155,176)
+ *   b2a_limit_peak_f32   out = x * (peak[row] > max_abs ? max_abs / peak[row] : 1)          (:181-198)
+ *   b2a_mix_f32          out = x + other_gain[item] * other   (other_gain nullable = 1)       (:27-64: the
+ *                        normalize() multiply of the noise and the addition, in one pass)
+ *   b2a_quantize_f32     mulaw = 0: linear quantisation to channels[item] levels (:463-491); 1: mu-law (:493-523);
+ *                        the reference's float32 operation order, including out = x - (x - q)
+ *   b2a_order_stats_f32  out[i] = the k[i]-th smallest value (0-based) of row[0..T): exact 4-pass radix selection;
+ *                        k: device int64 [nk].  torch.quantile's sorted gather for clip_distortion (:452-453)
+ *   b2a_clamp_items_f32  out = min(max(x, lo[item]), hi[item])                                 (:459) */
+int b2a_row_absmax_f32(const float* x, int64_t rows, int64_t T, float* peak, void* stream);
+int b2a_limit_peak_f32(const float* x, float* out, int64_t rows, int64_t T, const float* peak, float max_abs, void* stream);
+int b2a_clamp_items_f32(const float* x, float* out, int64_t B, int64_t per_item, const float* lo, const float* hi,
+                        void* stream);
+int b2a_mix_f32(const float* x, const float* other, const float* other_gain, float* out, int64_t B, int64_t per_item,
+                void* stream);
+int b2a_quantize_f32(const float* x, float* out, int64_t B, int64_t per_item, const float* channels, int mulaw,
+                     void* stream);
+int b2a_order_stats_f32(const float* row, int64_t T, const int64_t* k, int nk, float* out, void* stream);
+
+/* ---- ragged signals -> one padded / truncated batch (csrc/collate.cu; AudioSignal.batch, audiotools/core/audio_signal.py:
+ * 380-470, called by util.collate, core/util.py:426-479; excerpt gathering of salient_excerpt, audio_signal.py:227-286)
+ * item i = C rows of src_len[i] samples at src_ptrs[i], consecutive rows src_stride[i] samples apart;
+ * out[i, c, t] = row c's sample t + src_off[i] when that index is inside [0, src_len[i]), else 0 (zero padding,
+ * truncation at T_out).  src_ptrs / src_len / src_stride / src_off (nullable = 0) are DEVICE arrays of n_items entries. */
+int b2a_pack_rows_f32(const float* const* src_ptrs, const int64_t* src_len, const int64_t* src_stride,
+                      const int64_t* src_off, int64_t n_items, int C, int64_t T_out, float* out, void* stream);
+
 /* 1 when b2a_spectral_f32 runs a launch of this geometry on the tensor-core kernel (csrc/spectral_tc.cu: tcgen05.mma,
  * accumulators in tensor memory): window_length 2048, hop <= 512, mel / log-mel output without the complex STFT, and
  * the path switched on (environment variable B2A_SPECTRAL_TC=1, or b2a_spectral_tc_enable(1)).  It is opt-in because

@@ -235,6 +235,7 @@ template <class T> static inline T __ldg(const T* p) { return *p; }
 static inline float __fmaf_rn(float a, float b, float c) { return fmaf(a, b, c); }
 static inline float __fmul_rn(float a, float b) { return a * b; }
 static inline float __fadd_rn(float a, float b) { return a + b; }
+static inline float __fdiv_rn(float a, float b) { return a / b; }
 static inline float rsqrtf(float x) { return 1.0f / sqrtf(x); }
 static inline void sincospif(float x, float* s, float* c) {
   *s = (float)sin(M_PI * (double)x);

@@ -766,3 +766,80 @@ def test_lufs_warp_kernel_run_geometries(at, sp, sr, T, B, C):
     assert torch.allclose(out["loud"][:4].cpu(), sp.loudness(x[:4], sr), atol=LUFS_ATOL)
     if B > 4:  # the repeated items give identical numbers whichever warp / round processed them
         assert torch.equal(out["blocks"][4:8], out["blocks"][:4])
+
+
+# ------------------------------------------------------------------------------------------
+# element-wise / peak effects as kernels (csrc/effects.cu), through the AudioSignal methods, against
+# the REAL reference's outputs (fx_* goldens of tests/golden/make_golden_spectral.py)
+# ------------------------------------------------------------------------------------------
+def test_elementwise_effects_on_gpu_match_reference(at, golden_spec):
+    from audiotools_b200.engine import get_engine
+
+    g = golden_spec
+    eng = get_engine()
+    xs = cases.make_input("cfg1") * 0.3
+    xs2 = torch.cat([xs, 0.5 * xs.flip(-1)], 1)
+    GS = lambda k: torch.from_numpy(g[k])  # noqa: E731
+    n0 = eng.launches
+    q = torch.tensor([8, 16, 256, 3])
+    assert torch.allclose(at.AudioSignal(xs2.clone(), 16000).to(DEV).quantization(q).audio_data.cpu(), GS("fx_quant"), atol=1e-6)
+    assert torch.allclose(at.AudioSignal(xs2.clone(), 16000).to(DEV).mulaw_quantization(q).audio_data.cpu(), GS("fx_mulaw"),
+                          atol=1e-6)
+    assert torch.allclose(at.AudioSignal(xs2.clone() * 5, 16000).to(DEV).ensure_max_of_audio(0.7).audio_data.cpu(),
+                          GS("fx_maxaudio"), atol=1e-7)
+    clip = at.AudioSignal(xs.clone(), 16000).to(DEV).clip_distortion(torch.tensor([0.05, 0.2, 0.0, 0.5]))
+    assert torch.allclose(clip.audio_data.cpu(), GS("fx_clip"), atol=1e-7)
+    assert eng.launches - n0 >= 6  # the methods ran on the library's kernels, not on tensor arithmetic
+    # mix: the noise's normalisation gain rides along the add (one kernel), same numbers as the two-step arithmetic
+    sig = at.AudioSignal(xs2.clone(), 16000).to(DEV)
+    noise = at.AudioSignal(0.05 * torch.randn(xs2.shape, generator=torch.Generator().manual_seed(3)), 16000).to(DEV)
+    ref_noise = noise.clone().normalize(sig.clone().loudness() - 12.0).audio_data
+    mixed = sig.clone().mix(noise.clone(), snr=12.0).audio_data
+    assert torch.equal(mixed, sig.audio_data + ref_noise)
+    # full-size row peak / limiter (64 x 2ch x 10 s)
+    big = torch.randn(64, 2, 441000, device=DEV)
+    assert torch.equal(eng.row_absmax(big), big.abs().amax(dim=-1, keepdim=True))
+    lim = eng.limit_peak(big, 1.0)
+    assert lim.abs().amax().item() <= 1.0 + 1e-6 and torch.equal(lim[0, 0] * big[0, 0].abs().max(), big[0, 0]) is not None
+
+
+# ------------------------------------------------------------------------------------------
+# device collate (csrc/collate.cu) and loudness-screened excerpts batched through the LUFS kernels
+# ------------------------------------------------------------------------------------------
+def test_device_collate_and_salient_excerpt(at):
+    from audiotools_b200.core import util
+    from audiotools_b200.engine import get_engine
+
+    eng = get_engine()
+    g = torch.Generator().manual_seed(2)
+    lens = [44100 * 3 + 17, 44100 * 5, 44100 * 2 + 1, 44100 * 4 + 3]
+    raw = [0.1 * torch.randn(1, 2, T, generator=g) for T in lens]
+    items = [{"signal": at.AudioSignal(r.clone().to(DEV), 44100), "idx": i} for i, r in enumerate(raw)]
+    n0 = eng.launches
+    batch = util.collate(items)  # list of dataset samples -> dict with one batched AudioSignal
+    sig = batch["signal"]
+    assert eng.launches - n0 == 1  # one gather launch for the whole ragged list
+    assert sig.shape == (4, 2, max(lens)) and sig.audio_data.is_cuda
+    ref = torch.zeros(4, 2, max(lens))
+    for i, r in enumerate(raw):
+        ref[i, :, : lens[i]] = r[0]
+    assert torch.equal(sig.audio_data.cpu(), ref)
+    # salient excerpt: quiet source with one loud stretch; candidates are screened as one batch on the device
+    sr = 44100
+    x = 1e-4 * torch.randn(1, 1, 30 * sr, generator=g)
+    x[..., 20 * sr: 24 * sr] = 0.3 * torch.randn(4 * sr, generator=g)
+    src = at.AudioSignal(x.to(DEV), sr)
+    for seed in range(4):
+        st = np.random.RandomState(seed)
+        got = at.AudioSignal.salient_excerpt(src, loudness_cutoff=-40.0, num_tries=8, state=st, duration=2.0)
+        ref_state = np.random.RandomState(seed)
+        tries = 0
+        while True:  # the reference's sequential loop (audio_signal.py:276-285), one excerpt at a time
+            off = ref_state.uniform(0, 28.0)
+            seg = at.AudioSignal(x[..., int(off * sr): int(off * sr) + 2 * sr].clone().to(DEV), sr)
+            tries += 1
+            if seg.loudness().item() > -40.0 or tries >= 8:
+                break
+        assert abs(got.metadata["offset"] - off) < 1e-12 and got.signal_length == 2 * sr
+        assert torch.equal(got.audio_data.cpu(), x[..., int(off * sr): int(off * sr) + 2 * sr])
+        assert st.uniform() == ref_state.uniform()

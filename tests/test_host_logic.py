@@ -290,3 +290,4 @@ def test_small_util_helpers():
     with util.chdir("/tmp"):
         assert os.getcwd() == "/tmp"
     assert os.getcwd() == here
+

@@ -623,3 +623,61 @@ def test_lufs_warp_kernel_block_energies_and_loudness(eng, sr, T, B, C):
     assert rel_err(out["blocks"], z_ref) < 1e-4
     loud_ref = sp.loudness(x, sr)
     assert torch.allclose(out["loud"], loud_ref, atol=2e-3)
+
+
+# ------------------------------------------------------------------------------------------
+# element-wise / peak effects (csrc/effects.cu) against the REAL reference's outputs (fx_* goldens) and torch
+# ------------------------------------------------------------------------------------------
+def test_effect_kernels_match_reference(eng, golden_spec):
+    g = golden_spec
+    xs = cases.make_input("cfg1") * 0.3
+    xs2 = torch.cat([xs, 0.5 * xs.flip(-1)], 1)
+    G = lambda k: torch.from_numpy(g[k])  # noqa: E731
+    q = torch.tensor([8, 16, 256, 3])
+    assert torch.allclose(eng.quantize(xs2, q), G("fx_quant"), atol=1e-6)
+    assert torch.allclose(eng.quantize(xs2, q, mulaw=True), G("fx_mulaw"), atol=1e-6)
+    x5 = xs2 * 5
+    assert torch.equal(eng.row_absmax(x5), x5.abs().max(dim=-1, keepdim=True).values)
+    assert torch.allclose(eng.limit_peak(x5, 0.7), G("fx_maxaudio"), atol=1e-7)
+    # clip_distortion: the reference's quantiles of row 0 (see EffectMixin.clip_distortion), then the clamp
+    perc = torch.tensor([0.05, 0.2, 0.0, 0.5])
+    qs = torch.cat([perc / 2, 1 - perc / 2])
+    thr = eng.quantile(xs[0, 0], qs)
+    assert torch.allclose(thr, torch.quantile(xs[0, 0], qs), atol=0, rtol=1e-6)
+    assert torch.allclose(eng.clamp_items(xs, thr[:4], thr[4:]), G("fx_clip"), atol=1e-7)
+    # order statistics are exact whatever the data (negative values, ties, odd length)
+    rng = torch.Generator().manual_seed(5)
+    row = torch.randn(10007, generator=rng).round(decimals=2)
+    ks = torch.tensor([0, 1, 5003, 10005, 10006, 777])
+    assert torch.equal(eng.order_stats(row, ks), row.sort().values[ks])
+    # mix: x + g * other with the reference's two roundings
+    other = torch.randn(xs2.shape, generator=rng) * 0.1
+    gain = torch.tensor([0.5, 2.0, 0.0, 1.25])
+    assert torch.equal(eng.mix(xs2, other, gain), xs2 + other * gain[:, None, None])
+    assert torch.equal(eng.mix(xs2, other), xs2 + other)
+
+
+# ------------------------------------------------------------------------------------------
+# device collate (csrc/collate.cu): ragged items -> padded / truncated batch, excerpt windows with offsets
+# ------------------------------------------------------------------------------------------
+def test_pack_rows_pad_truncate_and_windows(eng):
+    g = torch.Generator().manual_seed(11)
+    items = [torch.randn(2, 1001, generator=g), torch.randn(3, 2, 1500, generator=g), torch.randn(2, 640, generator=g)]
+    for T_out in (1500, 640, 1000, 2048):  # pad to the longest, truncate to the shortest, in between, beyond
+        out = eng.pack_rows(items, T_out)
+        ref = torch.zeros(5, 2, T_out)
+        rows = [items[0][None], items[1], items[2][None]]
+        i = 0
+        for r in rows:
+            n = min(T_out, r.shape[-1])
+            ref[i:i + r.shape[0], :, :n] = r[..., :n]
+            i += r.shape[0]
+        assert torch.equal(out, ref), T_out
+    long = torch.randn(1, 2, 5000, generator=g)
+    offs = [0, 13, 4096, 4990, -7]
+    win = eng.pack_rows([long] * len(offs), 512, offsets=offs)
+    for k, o in enumerate(offs):
+        ref = torch.zeros(2, 512)
+        lo, hi = max(o, 0), min(o + 512, 5000)
+        ref[:, lo - o: hi - o] = long[0, :, lo:hi]
+        assert torch.equal(win[k], ref), o

@@ -218,3 +218,57 @@ def test_time_stretch_properties():
     assert torch.equal(AudioSignal(x.clone(), sr).time_stretch(1.0).audio_data, x)
     with pytest.raises(NotImplementedError):
         AudioSignal(x.clone(), sr).time_stretch(8.0)
+
+
+def test_excerpt_and_salient_excerpt_semantics():
+    """ref:audiotools/core/audio_signal.py:178-286 on an in-memory source: the offset is ONE uniform draw from the
+    caller's state, the loudness screen keeps drawing until a window is above the cut-off (at most num_tries), and the
+    state ends up where the reference's sequential loop would leave it."""
+    sr = 16000
+    x = torch.zeros(1, 1, 10 * sr)
+    x[..., 6 * sr: 8 * sr] = 0.3 * torch.randn(2 * sr, generator=torch.Generator().manual_seed(0))  # loud only in [6 s, 8 s)
+    src = AudioSignal(x, sr)
+    st = np.random.RandomState(5)
+    expect_off = np.random.RandomState(5).uniform(0, 10 - 1.0)
+    e = AudioSignal.excerpt(src, duration=1.0, state=st)
+    assert e.signal_length == sr and abs(e.metadata["offset"] - expect_off) < 1e-12
+    assert torch.equal(e.audio_data[0, 0], x[0, 0, int(expect_off * sr): int(expect_off * sr) + sr])
+    # sequential reference loop, re-stated: draw, measure, stop at the first window above the cut-off
+    for seed in range(6):
+        ref_state = np.random.RandomState(seed)
+        tries, off = 0, None
+        while True:
+            off = ref_state.uniform(0, 9.0)
+            seg = AudioSignal(x[..., int(off * sr): int(off * sr) + sr].clone(), sr)
+            tries += 1
+            if seg.loudness().item() > -40.0 or tries >= 8:
+                break
+        st = np.random.RandomState(seed)
+        got = AudioSignal.salient_excerpt(src, loudness_cutoff=-40.0, num_tries=8, state=st, duration=1.0)
+        assert abs(got.metadata["offset"] - off) < 1e-12, seed
+        assert st.uniform() == ref_state.uniform(), seed  # both states advanced by the same number of draws
+    with pytest.raises(NotImplementedError):
+        AudioSignal.salient_excerpt("some/file.wav", loudness_cutoff=-40, duration=1.0)
+
+
+def test_batch_collates_ragged_signals_in_one_launch():
+    """AudioSignal.batch (ref:audiotools/core/audio_signal.py:380-470) on the engine: pad / truncate + concatenate is
+    one gather launch, and the inputs end up padded / truncated like after the reference's in-place calls."""
+    g = torch.Generator().manual_seed(2)
+    mk = lambda b, T: AudioSignal(torch.randn(b, 2, T, generator=g), 16000)  # noqa: E731
+    sigs = [mk(1, 900), mk(2, 1200), mk(1, 640)]
+    raw = [s.audio_data.clone() for s in sigs]
+    eng = engine_mod.get_engine()
+    n0 = eng.launches
+    out = AudioSignal.batch(sigs, pad_signals=True)
+    assert eng.launches - n0 == 1 and out.shape == (4, 2, 1200)
+    ref = torch.zeros(4, 2, 1200)
+    ref[0, :, :900], ref[1:3], ref[3, :, :640] = raw[0][0], raw[1], raw[2][0]
+    assert torch.equal(out.audio_data, ref)
+    assert [s.signal_length for s in sigs] == [1200, 1200, 1200] and torch.equal(sigs[2].audio_data[0], ref[3])
+    sigs = [mk(1, 900), mk(1, 640)]
+    raw = [s.audio_data.clone() for s in sigs]
+    out = AudioSignal.batch(sigs, truncate_signals=True)
+    assert out.shape == (2, 2, 640) and torch.equal(out.audio_data, torch.cat([raw[0][..., :640], raw[1]]))
+    with pytest.raises(RuntimeError):
+        AudioSignal.batch([mk(1, 900), mk(1, 640)])

@@ -57,6 +57,8 @@ def _get_value(other):
 
 
 def random_state(seed: typing.Union[int, np.random.RandomState, None]):
+    if isinstance(seed, np.random.RandomState):  # the hot case (every transform of a Compose passes its state on)
+        return seed
     if seed is None or seed is np.random:
         return np.random.mtrand._rand
     if isinstance(seed, (numbers.Integral, np.integer, int)):

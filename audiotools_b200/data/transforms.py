@@ -28,6 +28,44 @@ tt = torch.tensor
 """Shorthand for converting things to torch.tensor."""
 
 
+# ------------------------------------------------------------------------------------------
+# Parameter tables.  A transform draws its parameters as PLAIN host values (python / numpy scalars, small arrays,
+# AudioSignals) -- the RNG calls and their order are the reference's, so a seed reproduces them -- and they only become
+# tensors once per batch: ``batch_instantiate`` stacks the B draws of every parameter into ONE tensor per key
+# (the reference builds B x n_keys zero-dim tensors and collates them: 250 ms per 512 items for a seven-transform
+# Compose on this host, 30 ms here), ``instantiate`` tensorises a single draw.  ``util.prepare_batch`` then uploads each
+# table once and keeps its host mirror, so mask / cutoff / shift decisions never synchronise with the device.
+# ------------------------------------------------------------------------------------------
+def _tensorize(value):
+    """One draw -> the reference's ``instantiate`` output: every leaf a tensor (``torch.tensor(v)``)."""
+    if isinstance(value, dict):
+        return {k: _tensorize(v) for k, v in value.items()}
+    if isinstance(value, (list, tuple)):
+        return [_tensorize(v) for v in value]
+    if isinstance(value, (AudioSignal, torch.Tensor)):
+        return value
+    return tt(value)
+
+
+def _stack_leaf(vals: list):
+    """B draws of one parameter -> one [B, ...] tensor with the dtype ``default_collate([torch.tensor(v) ...])`` gives."""
+    v0 = vals[0]
+    if isinstance(v0, AudioSignal):
+        return AudioSignal.batch(list(vals), pad_signals=True)
+    if isinstance(v0, torch.Tensor):
+        return torch.stack(list(vals))
+    if isinstance(v0, (list, tuple)):  # e.g. Choose's one_hot: a list of per-child flags -> a list of [B] tensors
+        return [_stack_leaf([v[i] for v in vals]) for i in range(len(v0))]
+    dtype = tt(v0).dtype  # python float -> float32, python int -> int64, bool -> bool, numpy scalars / arrays keep theirs
+    arr = np.asarray(vals)
+    return torch.as_tensor(arr).to(dtype) if arr.dtype != object else torch.stack([tt(v) for v in vals])
+
+
+def _collate_draws(draws: list):
+    flats = [util.flatten(d) for d in draws]
+    return util.unflatten({k: _stack_leaf([f[k] for f in flats]) for k in flats[0]})
+
+
 class BaseTransform:
     def __init__(self, keys: list = [], name: str = None, prob: float = 1.0):
         # parameter names come from the _transform signature (everything but signal / kwargs)
@@ -35,6 +73,7 @@ class BaseTransform:
         self.keys = keys + tfm_keys + ["mask"]
         self.prob = prob
         self.name = self.__class__.__name__ if name is None else name
+        self._needs_signal = "signal" in signature(self._instantiate).parameters  # inspected once, not per item
 
     def _prepare(self, batch: dict):
         sub_batch = batch[self.name]
@@ -83,19 +122,19 @@ class BaseTransform:
     def __call__(self, *args, **kwargs):
         return self.transform(*args, **kwargs)
 
-    def instantiate(self, state: RandomState = None, signal: AudioSignal = None):
-        state = util.random_state(state)
-        needs_signal = "signal" in set(signature(self._instantiate).parameters.keys())
-        params = self._instantiate(state, **({"signal": signal} if needs_signal else {}))
-        for k in list(params.keys()):
-            v = params[k]
-            if not isinstance(v, (AudioSignal, torch.Tensor, dict)):
-                params[k] = tt(v)
-        params["mask"] = tt(state.rand() <= self.prob)
+    def _draw(self, state: RandomState, signal: AudioSignal = None) -> dict:
+        """One item's parameters as plain host values, keyed by the transform's name (mask last, as in the reference:
+        ``state.rand() <= prob`` is drawn AFTER the parameters, ref :228-240)."""
+        params = self._instantiate(state, signal) if self._needs_signal else self._instantiate(state)
+        params["mask"] = bool(state.rand() <= self.prob)
         return {self.name: params}
 
+    def instantiate(self, state: RandomState = None, signal: AudioSignal = None):
+        return _tensorize(self._draw(util.random_state(state), signal))
+
     def batch_instantiate(self, states: list = None, signal: AudioSignal = None):
-        return util.collate([self.instantiate(state, signal) for state in states])
+        """Parameters for a batch, one seed / state per item (ref :242-265): B draws, ONE tensor per parameter."""
+        return _collate_draws([self._draw(util.random_state(state), signal) for state in states])
 
 
 class Identity(BaseTransform):
@@ -139,7 +178,7 @@ class Compose(BaseTransform):
     def _instantiate(self, state: RandomState, signal: AudioSignal = None):
         parameters = {}
         for transform in self.transforms:
-            parameters.update(transform.instantiate(state, signal=signal))
+            parameters.update(transform._draw(state, signal))
         return parameters
 
     def __getitem__(self, idx):
@@ -166,9 +205,8 @@ class Choose(Compose):
         tfm_idx = state.choice(list(range(len(self.transforms))), p=self.weights)
         one_hot = []
         for i, t in enumerate(self.transforms):
-            mask = kwargs[t.name]["mask"]
-            if mask.item():
-                kwargs[t.name]["mask"] = tt(i == tfm_idx)
+            if kwargs[t.name]["mask"]:
+                kwargs[t.name]["mask"] = bool(i == tfm_idx)
             one_hot.append(kwargs[t.name]["mask"])
         kwargs["one_hot"] = one_hot
         return kwargs

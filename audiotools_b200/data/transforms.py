@@ -429,7 +429,7 @@ class RoomImpulseResponse(BaseTransform):
         self.sources = sources
         self.weights = weights
 
-    def _draw(self, state, signal):
+    def _draw_ir(self, state, signal):
         if callable(self.sources):
             return self.sources(state, signal)
         if not self.sources:
@@ -441,7 +441,7 @@ class RoomImpulseResponse(BaseTransform):
         eq_amount = util.sample_from_dist(self.eq_amount, state)
         eq = -eq_amount * state.rand(self.n_bands)
         drr = util.sample_from_dist(self.drr, state)
-        ir_signal = self._draw(state, signal)
+        ir_signal = self._draw_ir(state, signal)
         ir_signal.zero_pad_to(signal.sample_rate)
         return {"eq": eq, "ir_signal": ir_signal, "drr": drr}
 

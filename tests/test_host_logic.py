@@ -119,6 +119,24 @@ def test_keys_come_from_transform_signature():
     assert np.allclose(p["eq"].numpy(), expected)  # same draw order as the reference (ref :594-597)
 
 
+def test_pool_transforms_instantiate_inside_compose():
+    """Every concrete transform must draw through BaseTransform._draw when it is a child of Compose (a pool transform
+    that shadowed `_draw` broke cfg4's Compose[Equalizer + RoomImpulseResponse + PitchShift])."""
+    irs = [noise(B=1, T=500) for _ in range(3)]
+    pool = [noise(B=1, T=4000) for _ in range(2)]
+    transform = tfm.Compose([tfm.Equalizer(), tfm.RoomImpulseResponse(sources=irs),
+                             tfm.PitchShift(("choice", [-2, -1, 1, 2])), tfm.BackgroundNoise(sources=pool),
+                             tfm.CrossTalk(sources=pool)])
+    sig = noise(B=4, T=4000)
+    kwargs = transform.batch_instantiate(list(range(4)), sig)
+    flat = util.flatten(kwargs)
+    assert flat[("Compose", "1.RoomImpulseResponse", "ir_signal")].shape == (4, 1, sig.sample_rate)
+    assert flat[("Compose", "2.PitchShift", "n_semitones")].shape == (4,)
+    assert all(v.shape[0] == 4 for v in flat.values())
+    for cls in (c for c in vars(tfm).values() if isinstance(c, type) and issubclass(c, tfm.BaseTransform)):
+        assert cls._draw is tfm.BaseTransform._draw, f"{cls.__name__} shadows BaseTransform._draw"
+
+
 def test_sample_from_dist_and_ensure_tensor():
     assert util.sample_from_dist(("const", 3)) == 3
     v = util.sample_from_dist(("uniform", 1.0, 2.0), 0)

@@ -74,6 +74,54 @@ __device__ __forceinline__ float warp_max(float v) {
   return v;
 }
 
+// Packed FP32 pairs.  sm_100a issues fma / add / mul on a register PAIR as one instruction (SASS FFMA2 / FADD2 / FMUL2:
+// PTX fma.rn.f32x2 ...), each half rounded exactly like the scalar instruction, and its operands take free half swaps,
+// per-half negation and scalar broadcast (R4.F32x2.LO_HI.NP, R7.F32 ...).  The FFT kernels are bound by instruction
+// issue, not by the FP32 pipe (tests/probes/f32x2_probe.cu: FFMA2 = 2 pipe cycles, 1 issue slot), so a complex
+// butterfly written on (re, im) pairs costs half the issue slots with bit-identical results.  Under the CPU
+// simulator the same functions are two scalar operations.
+__device__ __forceinline__ float2 fma2(float2 a, float2 b, float2 c) {
+#ifdef B2A_SIM
+  return make_float2(fmaf(a.x, b.x, c.x), fmaf(a.y, b.y, c.y));
+#else
+  unsigned long long A, B, C, R;
+  float2 r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(A) : "f"(a.x), "f"(a.y));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(B) : "f"(b.x), "f"(b.y));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(C) : "f"(c.x), "f"(c.y));
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(R) : "l"(A), "l"(B), "l"(C));
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(r.x), "=f"(r.y) : "l"(R));
+  return r;
+#endif
+}
+__device__ __forceinline__ float2 add2(float2 a, float2 b) {
+#ifdef B2A_SIM
+  return make_float2(a.x + b.x, a.y + b.y);
+#else
+  unsigned long long A, B, R;
+  float2 r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(A) : "f"(a.x), "f"(a.y));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(B) : "f"(b.x), "f"(b.y));
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(R) : "l"(A), "l"(B));
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(r.x), "=f"(r.y) : "l"(R));
+  return r;
+#endif
+}
+__device__ __forceinline__ float2 mul2(float2 a, float2 b) {
+#ifdef B2A_SIM
+  return make_float2(a.x * b.x, a.y * b.y);
+#else
+  unsigned long long A, B, R;
+  float2 r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(A) : "f"(a.x), "f"(a.y));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(B) : "f"(b.x), "f"(b.y));
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(R) : "l"(A), "l"(B));
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(r.x), "=f"(r.y) : "l"(R));
+  return r;
+#endif
+}
+__device__ __forceinline__ float2 neg2(float2 a) { return make_float2(-a.x, -a.y); }
+__device__ __forceinline__ float2 bcast2(float v) { return make_float2(v, v); }
 // acquire / release on a 32-bit flag in global memory (decoupled look-back)
 __device__ __forceinline__ void st_release(int* p, int v) {
 #ifdef B2A_SIM

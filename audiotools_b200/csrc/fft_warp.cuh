@@ -14,10 +14,13 @@ namespace spectral {
 // ---------------------------------------------------------------------------------------------
 // small DFTs in registers
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
-__device__ __forceinline__ float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
+__device__ __forceinline__ float2 rot_mi(float2 a) { return make_float2(a.y, -a.x); }  // a * (-i)
+
+__device__ __forceinline__ float2 cadd(float2 a, float2 b) { return add2(a, b); }
+__device__ __forceinline__ float2 csub(float2 a, float2 b) { return add2(a, neg2(b)); }
+// a * b = (a.x b.x - a.y b.y, a.x b.y + a.y b.x): the same two roundings per component as the scalar form
 __device__ __forceinline__ float2 cmul(float2 a, float2 b) {
-  return make_float2(fmaf(a.x, b.x, -a.y * b.y), fmaf(a.x, b.y, a.y * b.x));
+  return fma2(bcast2(a.x), b, mul2(bcast2(a.y), make_float2(-b.y, b.x)));
 }
 
 // cos(pi*j/16), j = 0..16
@@ -69,26 +72,28 @@ struct DFT {
     if constexpr (R == 2 && PRE) {
       out[K] = e[K];
       out[K + R / 2] = o[K];
-    } else if constexpr (j == 0 || j == 8) {
-      const float2 t = mul_wr<R, K>(o[K]);
-      out[K] = cadd(e[K], t);
-      out[K + R / 2] = csub(e[K], t);
+    } else if constexpr (j == 0) {
+      out[K] = add2(e[K], o[K]);
+      out[K + R / 2] = add2(e[K], neg2(o[K]));
+    } else if constexpr (j == 8) {  // W = -i
+      out[K] = add2(e[K], rot_mi(o[K]));
+      out[K + R / 2] = add2(e[K], neg2(rot_mi(o[K])));
     } else if constexpr (j == 4 || j == 12) {
       constexpr float h = 0.70710678118654752f;
       // j == 4: W o = h((o.x + o.y) + i(o.y - o.x));  j == 12: W o = h((o.y - o.x) - i(o.x + o.y))
-      const float p = o[K].x + o[K].y, q = o[K].y - o[K].x;
+      const float2 pq = add2(o[K], rot_mi(o[K]));  // (p, q) = (o.x + o.y, o.y - o.x)
       float2 s;
-      if constexpr (j == 4) s = make_float2(fmaf(h, p, e[K].x), fmaf(h, q, e[K].y));
-      else s = make_float2(fmaf(h, q, e[K].x), fmaf(-h, p, e[K].y));
+      if constexpr (j == 4) s = fma2(bcast2(h), pq, e[K]);
+      else s = fma2(make_float2(h, -h), make_float2(pq.y, pq.x), e[K]);
       out[K] = s;
-      out[K + R / 2] = make_float2(fmaf(2.0f, e[K].x, -s.x), fmaf(2.0f, e[K].y, -s.y));
+      out[K + R / 2] = fma2(bcast2(2.0f), e[K], neg2(s));
     } else {
       constexpr float c = cos_pi16(j);
       constexpr float sn = cos_pi16(j <= 8 ? 8 - j : j - 8);  // sin(pi j/16)
       // W o = (o.x c + o.y sn) + i (o.y c - o.x sn)
-      const float2 s = make_float2(fmaf(o[K].x, c, fmaf(o[K].y, sn, e[K].x)), fmaf(o[K].y, c, fmaf(-o[K].x, sn, e[K].y)));
+      const float2 s = fma2(o[K], bcast2(c), fma2(rot_mi(o[K]), bcast2(sn), e[K]));
       out[K] = s;
-      out[K + R / 2] = make_float2(fmaf(2.0f, e[K].x, -s.x), fmaf(2.0f, e[K].y, -s.y));
+      out[K + R / 2] = fma2(bcast2(2.0f), e[K], neg2(s));
     }
     if constexpr (K + 1 < R / 2) comb<K + 1>(e, o, out);
   }

@@ -732,6 +732,289 @@ kweight_energy_warp_kernel(const float* __restrict__ x, int rows, int T, int Tp,
 
 }  // namespace v2
 
+// =============================================================================================
+// Row-pair variant (round 2, second half): the v2 algorithm with TWO rows per warp in the halves of packed FP32
+// registers.  Rows 2p and 2p+1 (the two channels of a stereo item; any two rows of the batch otherwise) have the same
+// length, segment grid, interval boundaries and filter, so every arithmetic instruction of v2 -- the 66-tap end-state
+// map, the affine scan, the DF-I recursion, the energy accumulation -- becomes ONE FFMA2 / FMUL2 / FADD2 on an
+// (row A, row B) pair with the coefficient broadcast, and all the per-lane bookkeeping (interval indices, split
+// points, staging addresses, loop control) is shared by the two rows.  v2 executed 24.8 warp instructions per sample
+// at 57 % issue utilisation (profiles/r02j): instruction issue, not HBM, is the limit, and this halves it.
+// The windows hold the two rows INTERLEAVED sample by sample (4-byte cp.async, coalesced 128 B per warp instruction),
+// so a 128-bit shared load delivers two ready-made register pairs.  An unpaired last row is processed against itself
+// with the second half's results dropped.
+// =============================================================================================
+namespace v3 {
+
+constexpr int L2 = v2::L2;             // samples per lane and row
+constexpr int SEG = v2::SEG;           // samples per warp segment and row
+constexpr int CHS = 2 * L2 + 4;        // words per lane chunk (both rows interleaved): 16 B aligned, conflict-free LDS.128
+constexpr int WPB = 6;                 // warps per CTA (one CTA per SM: 6 x 2 x 16.5 KB of windows)
+constexpr int NBUF = 2;
+constexpr int BUF = 32 * CHS;          // floats per window
+
+__device__ __forceinline__ void cp_async4(float* smem_dst, const float* gmem_src) {
+#ifdef B2A_SIM
+  *smem_dst = *gmem_src;
+#else
+  const unsigned sa = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(sa), "l"(gmem_src) : "memory");
+#endif
+}
+
+// Stage segment `seg` of rows xa / xb into a warp window, interleaved: win[CHS * chunk + 2 * i + {0: A, 1: B}].
+__device__ __forceinline__ void stage_pair(const float* __restrict__ xa, const float* __restrict__ xb, int seg, int T,
+                                           float* win, int lane) {
+  const int t0 = seg * SEG;
+  if (t0 + SEG <= T) {
+#pragma unroll
+    for (int e = 0; e < SEG / 32; ++e) {  // sample s = 32 e + lane: 128 contiguous bytes per warp instruction
+      float* d = &win[CHS * (e >> 1) + 2 * (32 * (e & 1) + lane)];
+      cp_async4(d, xa + t0 + 32 * e + lane);
+      cp_async4(d + 1, xb + t0 + 32 * e + lane);
+    }
+  } else {
+    for (int e = 0; e < SEG / 32; ++e) {
+      const int n = t0 + 32 * e + lane;
+      float* d = &win[CHS * (e >> 1) + 2 * (32 * (e & 1) + lane)];
+      d[0] = (n < T) ? __ldg(xa + n) : 0.f;
+      d[1] = (n < T) ? __ldg(xb + n) : 0.f;
+    }
+  }
+}
+
+template <int D>
+__device__ __forceinline__ float2 row_dot2(const float* M, int i, const float2* v) {
+  float2 a = make_float2(0.f, 0.f);
+#pragma unroll
+  for (int j = 0; j < D; ++j) a = fma2(bcast2(M[i * D + j]), v[j], a);
+  return a;
+}
+
+// one step of the cascade on a pair of rows: the operation order of cascade_step, every product fused
+template <int NS>
+__device__ __forceinline__ float2 cascade_step2(const Coef<NS>& cf, float2 in0, float2 in1, float2 in2, float2 (&y1)[NS],
+                                                float2 (&y2)[NS]) {
+#pragma unroll
+  for (int s = 0; s < NS; ++s) {
+    const float2 f = fma2(bcast2(cf.b0[s]), in0, fma2(bcast2(cf.b1[s]), in1, mul2(bcast2(cf.b2[s]), in2)));
+    const float2 y0 = fma2(bcast2(-cf.a1[s]), y1[s], fma2(bcast2(-cf.a2[s]), y2[s], f));
+    in0 = y0; in1 = y1[s]; in2 = y2[s];
+    y2[s] = y1[s]; y1[s] = y0;
+  }
+  return in0;
+}
+
+template <int NS>
+__global__ void __launch_bounds__(32 * WPB, 1)
+kweight_energy_pair_kernel(const float* __restrict__ x, int rows, int T, int Tp, int nseg, int run_len, int n_runs,
+                           int n_warm, Coef<NS> cf, const B2A_GRID_CONSTANT v2::Tables2<NS> tbv,
+                           double* __restrict__ bins, int stride, int r, int nbins) {
+  constexpr int D = 2 * NS;
+  B2A_DYN_SMEM(smem);
+  float* wins = reinterpret_cast<float*>(smem);  // [WPB][NBUF][BUF]
+  __shared__ __align__(16) float s_wa[L2 + 2][D];
+  __shared__ float s_mlane[32][D * D];
+  __shared__ float s_mscan[5][D * D];
+  __shared__ float s_mseg[D * D];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  for (int i = tid; i < (L2 + 2) * D; i += blockDim.x) (&s_wa[0][0])[i] = (&tbv.Wa[0][0])[i];
+  for (int i = tid; i < 32 * D * D; i += blockDim.x) (&s_mlane[0][0])[i] = (&tbv.Mlane[0][0])[i];
+  for (int i = tid; i < 5 * D * D; i += blockDim.x) (&s_mscan[0][0])[i] = (&tbv.Mscan[0][0])[i];
+  if (tid < D * D) s_mseg[tid] = tbv.Mseg[tid];
+  __syncthreads();  // the only CTA barrier: tables
+  const int npairs = (rows + 1) >> 1;
+  const int total = npairs * n_runs;
+  float* win0 = wins + (size_t)warp * NBUF * BUF;
+
+#pragma unroll 1
+  for (int cur = (int)blockIdx.x * WPB + warp; cur < total; cur += (int)gridDim.x * WPB) {
+    const int run = cur / npairs, pr = cur - run * npairs;
+    const int rowa = 2 * pr;
+    const bool has_b = rowa + 1 < rows;
+    const int rowb = has_b ? rowa + 1 : rowa;
+    const int seg0 = run * run_len, seg1 = min(nseg, seg0 + run_len);
+    const int segw = max(0, seg0 - n_warm);  // warm-up starts here, from a zero state
+    const float* xa = x + (size_t)rowa * (size_t)T;
+    const float* xb = x + (size_t)rowb * (size_t)T;
+    double* rba = bins + (size_t)rowa * (size_t)nbins;
+    double* rbb = bins + (size_t)rowb * (size_t)nbins;
+    float2 carry[D];  // state entering the current segment (all lanes hold it), (row A, row B)
+#pragma unroll
+    for (int j = 0; j < D; ++j) carry[j] = make_float2(0.f, 0.f);
+    stage_pair(xa, xb, segw, T, win0, lane);
+    int par = 0;
+#pragma unroll 1
+    for (int seg = segw; seg < seg1; ++seg, par ^= (NBUF - 1)) {
+      cp_async_wait_all();
+      __syncwarp();
+      const float* win = win0 + par * BUF;
+      if (seg + 1 < seg1) stage_pair(xa, xb, seg + 1, T, win0 + (par ^ 1) * BUF, lane);
+      const int t0 = seg * SEG;
+      float2 h0, h1;  // the two samples in front of this lane's chunk
+      if (lane == 0) {
+        const bool in0 = (t0 >= 2 && t0 - 2 < T), in1 = (t0 >= 1 && t0 - 1 < T);
+        h0 = make_float2(in0 ? __ldg(xa + t0 - 2) : 0.f, in0 ? __ldg(xb + t0 - 2) : 0.f);
+        h1 = make_float2(in1 ? __ldg(xa + t0 - 1) : 0.f, in1 ? __ldg(xb + t0 - 1) : 0.f);
+      } else {
+        const float4 h = *reinterpret_cast<const float4*>(&win[CHS * (lane - 1) + 2 * (L2 - 2)]);
+        h0 = make_float2(h.x, h.y); h1 = make_float2(h.z, h.w);
+      }
+      const float4* c4 = reinterpret_cast<const float4*>(&win[CHS * lane]);
+      const float4* wa4 = reinterpret_cast<const float4*>(&s_wa[0][0]);  // D == 4: one 128-bit broadcast load per tap
+      // ---- zero-state end state of the lane's chunk as a linear map of its 66 inputs (two partial sums: ILP)
+      float2 g[D], ge[D];
+#pragma unroll
+      for (int i = 0; i < D; ++i) {
+        g[i] = mul2(bcast2(s_wa[0][i]), h0);
+        ge[i] = mul2(bcast2(s_wa[1][i]), h1);
+      }
+#pragma unroll
+      for (int i4 = 0; i4 < L2 / 2; ++i4) {
+        const float4 q = c4[i4];  // (A[2 i4], B[2 i4], A[2 i4 + 1], B[2 i4 + 1])
+        if constexpr (D == 4) {
+          const float4 w0 = wa4[2 + 2 * i4], w1 = wa4[3 + 2 * i4];
+          const float2 q0 = make_float2(q.x, q.y), q1 = make_float2(q.z, q.w);
+          g[0] = fma2(bcast2(w0.x), q0, g[0]); g[1] = fma2(bcast2(w0.y), q0, g[1]);
+          g[2] = fma2(bcast2(w0.z), q0, g[2]); g[3] = fma2(bcast2(w0.w), q0, g[3]);
+          ge[0] = fma2(bcast2(w1.x), q1, ge[0]); ge[1] = fma2(bcast2(w1.y), q1, ge[1]);
+          ge[2] = fma2(bcast2(w1.z), q1, ge[2]); ge[3] = fma2(bcast2(w1.w), q1, ge[3]);
+        } else {
+          const float2 q0 = make_float2(q.x, q.y), q1 = make_float2(q.z, q.w);
+#pragma unroll
+          for (int i = 0; i < D; ++i) {
+            g[i] = fma2(bcast2(s_wa[2 + 2 * i4][i]), q0, g[i]);
+            ge[i] = fma2(bcast2(s_wa[3 + 2 * i4][i]), q1, ge[i]);
+          }
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < D; ++i) g[i] = add2(g[i], ge[i]);
+#pragma unroll
+      for (int k = 0; k < 5; ++k) {  // inclusive affine scan over the 32 chunks
+        float2 o[D];
+#pragma unroll
+        for (int j = 0; j < D; ++j) {
+          o[j].x = __shfl_up_sync(0xffffffffu, g[j].x, 1u << k);
+          o[j].y = __shfl_up_sync(0xffffffffu, g[j].y, 1u << k);
+        }
+        if (lane >= (1 << k)) {
+#pragma unroll
+          for (int i = 0; i < D; ++i) g[i] = add2(g[i], row_dot2<D>(s_mscan[k], i, o));
+        }
+      }
+      float2 ex[D], agg[D];
+#pragma unroll
+      for (int j = 0; j < D; ++j) {
+        ex[j].x = __shfl_up_sync(0xffffffffu, g[j].x, 1);
+        ex[j].y = __shfl_up_sync(0xffffffffu, g[j].y, 1);
+        if (lane == 0) ex[j] = make_float2(0.f, 0.f);
+        agg[j].x = __shfl_sync(0xffffffffu, g[j].x, 31);
+        agg[j].y = __shfl_sync(0xffffffffu, g[j].y, 31);
+      }
+      if (seg >= seg0) {
+        // ---- true start state, recursion, energies into the interval bins
+        float2 y1[NS], y2[NS];
+        {
+#pragma unroll
+          for (int s = 0; s < NS; ++s) {
+            y1[s] = add2(ex[2 * s], row_dot2<D>(s_mlane[lane], 2 * s, carry));
+            y2[s] = add2(ex[2 * s + 1], row_dot2<D>(s_mlane[lane], 2 * s + 1, carry));
+          }
+        }
+        const int n0 = t0 + lane * L2;
+        const int nv = min(L2, max(0, Tp - n0));
+        int j0 = n0 / stride, rem0 = n0 - j0 * stride;
+        int b0 = 2 * j0 + (rem0 >= r ? 1 : 0);
+        int end0 = (b0 & 1) ? (j0 + 1) * stride : j0 * stride + r;
+        const int s1 = min(end0 - n0, L2);
+        int s2 = L2, b1 = b0, b2 = b0;
+        if (s1 < L2) {
+          const int n1 = n0 + s1, j1 = n1 / stride, rem1 = n1 - j1 * stride;
+          b1 = 2 * j1 + (rem1 >= r ? 1 : 0);
+          const int end1 = (b1 & 1) ? (j1 + 1) * stride : j1 * stride + r;
+          s2 = min(end1 - n0, L2);
+          if (s2 < L2) {
+            const int n2 = n0 + s2, j2 = n2 / stride, rem2 = n2 - j2 * stride;
+            b2 = 2 * j2 + (rem2 >= r ? 1 : 0);
+          }
+        }
+        const bool simple = (s1 >= L2) && (nv == L2);
+        const bool clean = __all_sync(0xffffffffu, simple);  // warp-uniform: no lane straddles an interval boundary
+        const float2 zero2 = make_float2(0.f, 0.f);
+        float2 a0 = zero2, a1 = zero2, a2 = zero2;
+        float2 xm2 = h0, xm1 = h1;
+        if (clean) {
+          float2 acc = zero2;
+#pragma unroll
+          for (int i4 = 0; i4 < L2 / 2; ++i4) {
+            const float4 q = c4[i4];
+            const float2 qs[2] = {make_float2(q.x, q.y), make_float2(q.z, q.w)};
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+              const float2 y = cascade_step2<NS>(cf, qs[e], xm1, xm2, y1, y2);
+              xm2 = xm1; xm1 = qs[e];
+              acc = fma2(y, y, acc);
+            }
+          }
+          a0 = acc;
+        } else {
+          float2 acc = zero2, p1 = zero2, p2 = zero2;  // running energy and its value at the two interval boundaries
+#pragma unroll
+          for (int i4 = 0; i4 < L2 / 2; ++i4) {
+            const float4 q = c4[i4];
+            const float2 qs[2] = {make_float2(q.x, q.y), make_float2(q.z, q.w)};
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+              const int i = 2 * i4 + e;
+              if (i == s1) p1 = acc;
+              if (i == s2) p2 = acc;
+              const float2 y = cascade_step2<NS>(cf, qs[e], xm1, xm2, y1, y2);
+              xm2 = xm1; xm1 = qs[e];
+              const float2 an = fma2(y, y, acc);
+              if (i < nv) acc = an;
+            }
+          }
+          if (s1 >= L2) p1 = acc;
+          if (s2 >= L2) p2 = acc;
+          a0 = p1; a1 = add2(p2, neg2(p1)); a2 = add2(acc, neg2(p2));
+        }
+        // one atomic per row and interval the warp touched (intervals are monotonic in the lane index)
+        const int blast = (s2 < L2) ? b2 : ((s1 < L2) ? b1 : b0);  // last interval this lane's chunk reaches
+        const int bf = __shfl_sync(0xffffffffu, b0, 0), bl = __shfl_sync(0xffffffffu, blast, 31);
+        for (int id = bf; id <= bl; ++id) {
+          float2 v = (b0 == id) ? a0 : zero2;
+          if (!clean) {
+            if (s1 < L2 && b1 == id) v = add2(v, a1);
+            if (s2 < L2 && b2 == id) v = add2(v, a2);
+          }
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) {
+            float2 t;
+            t.x = __shfl_xor_sync(0xffffffffu, v.x, o);
+            t.y = __shfl_xor_sync(0xffffffffu, v.y, o);
+            v = add2(v, t);
+          }
+          if (lane == 0 && id < nbins) {
+            atomicAdd(rba + id, (double)v.x);
+            if (has_b) atomicAdd(rbb + id, (double)v.y);
+          }
+        }
+      }
+      // ---- carry into the next segment: A^SEG carry + (zero-state end state of this segment)
+      float2 cn[D];
+#pragma unroll
+      for (int i = 0; i < D; ++i) cn[i] = add2(agg[i], row_dot2<D>(s_mseg, i, carry));
+#pragma unroll
+      for (int i = 0; i < D; ++i) carry[i] = cn[i];
+      __syncwarp();  // every lane is done with this window before it is refilled
+    }
+  }
+  cp_async_wait_all();
+}
+
+}  // namespace v3
+
 // ---------------------------------------------------------------------------------------------
 // gating: ref:audiotools/core/loudness.py:208-247 (+ :315-320 clamp, effects.py:214-217 gain)
 // ---------------------------------------------------------------------------------------------
@@ -887,6 +1170,15 @@ static int use_v1() {
   return v;
 }
 
+static int use_v2() {  // B2A_LUFS_V2=1: one row per warp, scalar FP32 (the kernel the pair kernel was derived from)
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("B2A_LUFS_V2");
+    v = (e && e[0] == '1') ? 1 : 0;
+  }
+  return v;
+}
+
 template <int NS>
 static int run(const float* x, int64_t B, int C, int64_t T, int64_t Tp, const Geometry& g, const double* sos_h,
                const double* stage_gain_h, double rate, double block_s, const double* chan_gain_h,
@@ -940,7 +1232,10 @@ static int run(const float* x, int64_t B, int C, int64_t T, int64_t Tp, const Ge
       n_warm = (int)((n_tail + v2::SEG - 1) / v2::SEG);
       if (n_warm < 1) n_warm = 1;
     }
-    int64_t rpr = (resident * v2::WPB) / rows;
+    const bool pairs = !use_v2();
+    const int64_t units = pairs ? (rows + 1) / 2 : rows;  // independent streams: row pairs (v3) or rows (v2)
+    const int wpb = pairs ? v3::WPB : v2::WPB;
+    int64_t rpr = (resident * wpb) / units;
     if (rpr < 1) rpr = 1;
     int run_len = (int)((g.nseg + rpr - 1) / rpr);
     if (run_len < 4 * n_warm) run_len = 4 * n_warm;  // at most 25 % warm-up
@@ -948,13 +1243,20 @@ static int run(const float* x, int64_t B, int C, int64_t T, int64_t Tp, const Ge
     const int n_runs = (g.nseg + run_len - 1) / run_len;
     v2::Tables2<NS> tb2;
     v2::build_tables2<NS>(cf, &tb2);
-    const size_t smem = (size_t)v2::WPB * v2::NBUF * v2::BUF * sizeof(float);
-    B2A_CUDA_OK(cudaFuncSetAttribute(v2::kweight_energy_warp_kernel<NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    const int64_t runs_all = rows * n_runs;
-    const int64_t want = (runs_all + v2::WPB - 1) / v2::WPB;
-    B2A_LAUNCH(v2::kweight_energy_warp_kernel<NS>, dim3((unsigned)(want < resident ? want : resident)), dim3(32 * v2::WPB), smem,
-               stream, x, (int)rows, (int)T, (int)Tp, g.nseg, run_len, n_runs, n_warm, cf, tb2, (double*)(base + w.bins),
-               g.stride, g.r, g.nbins);
+    const int64_t runs_all = units * n_runs;
+    const int64_t want = (runs_all + wpb - 1) / wpb;
+    const unsigned grid = (unsigned)(want < resident ? want : resident);
+    if (pairs) {
+      const size_t smem = (size_t)v3::WPB * v3::NBUF * v3::BUF * sizeof(float);
+      B2A_CUDA_OK(cudaFuncSetAttribute(v3::kweight_energy_pair_kernel<NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      B2A_LAUNCH(v3::kweight_energy_pair_kernel<NS>, dim3(grid), dim3(32 * v3::WPB), smem, stream, x, (int)rows, (int)T,
+                 (int)Tp, g.nseg, run_len, n_runs, n_warm, cf, tb2, (double*)(base + w.bins), g.stride, g.r, g.nbins);
+    } else {
+      const size_t smem = (size_t)v2::WPB * v2::NBUF * v2::BUF * sizeof(float);
+      B2A_CUDA_OK(cudaFuncSetAttribute(v2::kweight_energy_warp_kernel<NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      B2A_LAUNCH(v2::kweight_energy_warp_kernel<NS>, dim3(grid), dim3(32 * v2::WPB), smem, stream, x, (int)rows, (int)T,
+                 (int)Tp, g.nseg, run_len, n_runs, n_warm, cf, tb2, (double*)(base + w.bins), g.stride, g.r, g.nbins);
+    }
   }
   GateParams gp;
   for (int c = 0; c < 8; ++c) gp.G[c] = c < C ? chan_gain_h[c] : 0.0;

@@ -509,9 +509,9 @@ __global__ void __launch_bounds__(256, 2) spectral_warp_kernel(Params p) {
           const float2 w0 = *reinterpret_cast<const float2*>(win + 2 * e0);
           const float2 s1 = *reinterpret_cast<const float2*>(fs + 2 * e1);
           const float2 w1 = *reinterpret_cast<const float2*>(win + 2 * e1);
-          const float ax = s0.x * w0.x, ay = s0.y * w0.y;
-          z[m] = make_float2(fmaf(s1.x, w1.x, ax), fmaf(s1.y, w1.y, ay));
-          z[m + 16] = make_float2(fmaf(-s1.x, w1.x, ax), fmaf(-s1.y, w1.y, ay));
+          const float2 a = mul2(s0, w0);
+          z[m] = fma2(s1, w1, a);
+          z[m + 16] = fma2(neg2(s1), w1, a);
         }
       } else {
 #pragma unroll
@@ -548,12 +548,12 @@ __global__ void __launch_bounds__(256, 2) spectral_warp_kernel(Params p) {
         zn.y = __shfl_sync(0xffffffffu, z[31 - m].y, src_lane);
         if (l == 0) zn = z[(32 - m) & 31];
         const int k = l + LPF * m;
-        const float2 xe = make_float2(zk.x + zn.x, zk.y - zn.y);  // (Zk + conj Zn)/2   (window halved above)
-        const float2 xo = make_float2(zk.y + zn.y, zn.x - zk.x);  // (Zk - conj Zn)/(2i)
+        const float2 xe = add2(zk, make_float2(zn.x, -zn.y));               // (Zk + conj Zn)/2   (window halved above)
+        const float2 xo = add2(make_float2(zk.y, -zk.x), make_float2(zn.y, zn.x));  // (Zk - conj Zn)/(2i)
         // X[k] = Xe + W Xo, X[N-k]* = Xe - W Xo: a twiddled butterfly, fused like the ones of the transform
         const float2 w = ut[m * LPF + l];
-        const float2 xk = make_float2(fmaf(w.x, xo.x, fmaf(-w.y, xo.y, xe.x)), fmaf(w.x, xo.y, fmaf(w.y, xo.x, xe.y)));
-        const float2 d = make_float2(fmaf(2.0f, xe.x, -xk.x), fmaf(2.0f, xe.y, -xk.y));
+        const float2 xk = fma2(bcast2(w.x), xo, fma2(make_float2(-w.y, w.y), make_float2(xo.y, xo.x), xe));
+        const float2 d = fma2(bcast2(2.0f), xe, neg2(xk));
         if constexpr (STAGED) {  // park the complex bins in the frame's own slot (the exchange plane is dead now)
           float2* xc = reinterpret_cast<float2*>(xb);
           xc[k] = make_float2(g * xk.x, g * xk.y);
@@ -600,15 +600,15 @@ __global__ void __launch_bounds__(256, 2) spectral_warp_kernel(Params p) {
               const int4 sg = mseg[mm];  // (row offset, lo4, own n4, padded even n4: the same for the 4 filters of a step)
               const float4* w4 = mpk4 + sg.x;
               const float4* v4 = reinterpret_cast<const float4*>(xf + sg.y);
-              float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+              float2 a01 = make_float2(0.f, 0.f), a23 = a01;  // packed accumulator pairs (FFMA2)
               for (int it = 0; it < sg.w; it += 2) {
                 const float4 wa = w4[it], wb = w4[it + 1], va = v4[it], vb = v4[it + 1];
-                a0 = fmaf(wa.x, va.x, a0); a1 = fmaf(wa.y, va.y, a1);
-                a2 = fmaf(wb.x, vb.x, a2); a3 = fmaf(wb.y, vb.y, a3);
-                a0 = fmaf(wa.z, va.z, a0); a1 = fmaf(wa.w, va.w, a1);
-                a2 = fmaf(wb.z, vb.z, a2); a3 = fmaf(wb.w, vb.w, a3);
+                a01 = fma2(make_float2(wa.x, wa.y), make_float2(va.x, va.y), a01);
+                a23 = fma2(make_float2(wb.x, wb.y), make_float2(vb.x, vb.y), a23);
+                a01 = fma2(make_float2(wa.z, wa.w), make_float2(va.z, va.w), a01);
+                a23 = fma2(make_float2(wb.z, wb.w), make_float2(vb.z, vb.w), a23);
               }
-              float acc = ((a0 + a1) + (a2 + a3)) * ga;
+              float acc = ((a01.x + a01.y) + (a23.x + a23.y)) * ga;
               if (p.post == B2A_POST_LOG10) acc = lscale * fast_log2(fmaxf(acc, p.post_eps));
               else if (p.post == B2A_POST_LN) acc = logf(acc + p.post_eps);
               melt[mm * (FR + 1) + f] = acc;

@@ -490,8 +490,10 @@ struct Tables2 {
   float Mseg[D * D];          // A^SEG
 };
 
+// L = samples per lane chunk (<= L2): Wa = end-state map of a chunk, Mlane[l] = A^(L l), Mscan[k] = A^(L 2^k),
+// Mseg = A^(32 L)
 template <int NS>
-static void build_tables2(const Coef<NS>& cf, Tables2<NS>* tb) {
+static void build_tables2(const Coef<NS>& cf, Tables2<NS>* tb, int L = L2) {
   constexpr int D = 2 * NS;
   double b0[NS], b1[NS], b2[NS], a1[NS], a2[NS];
   for (int s = 0; s < NS; ++s) {
@@ -506,24 +508,24 @@ static void build_tables2(const Coef<NS>& cf, Tables2<NS>* tb) {
   }
   double P[D * D];  // A^L2
   for (int i = 0; i < D * D; ++i) P[i] = A[i];
-  for (int l = 1; l < L2; l <<= 1) matmul<D>(P, P, P);
+  for (int l = 1; l < L; l <<= 1) matmul<D>(P, P, P);
   double Q[D * D];
   for (int i = 0; i < D * D; ++i) Q[i] = (i / D == i % D) ? 1.0 : 0.0;
   for (int l = 0; l < 32; ++l) {
     for (int i = 0; i < D * D; ++i) tb->Mlane[l][i] = (float)Q[i];
     matmul<D>(P, Q, Q);
   }
-  for (int i = 0; i < D * D; ++i) tb->Mseg[i] = (float)Q[i];  // Q == A^SEG
+  for (int i = 0; i < D * D; ++i) tb->Mseg[i] = (float)Q[i];  // Q == A^(32 L)
   double S[D * D];
   for (int i = 0; i < D * D; ++i) S[i] = P[i];
   for (int k = 0; k < 5; ++k) {
     for (int i = 0; i < D * D; ++i) tb->Mscan[k][i] = (float)S[i];
     matmul<D>(S, S, S);
   }
-  for (int j = 0; j < L2 + 2; ++j) {
+  for (int j = 0; j < L + 2; ++j) {
     double y1[NS], y2[NS];
     for (int s = 0; s < NS; ++s) { y1[s] = 0.0; y2[s] = 0.0; }
-    for (int i = 0; i < L2; ++i) {
+    for (int i = 0; i < L; ++i) {
       const double in0 = (i + 2 == j) ? 1.0 : 0.0, in1 = (i + 1 == j) ? 1.0 : 0.0, in2 = (i == j) ? 1.0 : 0.0;
       cascade_step<NS, double>(b0, b1, b2, a1, a2, in0, in1, in2, y1, y2);
     }
@@ -733,25 +735,28 @@ kweight_energy_warp_kernel(const float* __restrict__ x, int rows, int T, int Tp,
 }  // namespace v2
 
 // =============================================================================================
-// Row-pair variant (round 2, second half): the v2 algorithm with TWO rows per warp in the halves of packed FP32
-// registers.  Rows 2p and 2p+1 (the two channels of a stereo item; any two rows of the batch otherwise) have the same
-// length, segment grid, interval boundaries and filter, so every arithmetic instruction of v2 -- the 66-tap end-state
-// map, the affine scan, the DF-I recursion, the energy accumulation -- becomes ONE FFMA2 / FMUL2 / FADD2 on an
-// (row A, row B) pair with the coefficient broadcast, and all the per-lane bookkeeping (interval indices, split
-// points, staging addresses, loop control) is shared by the two rows.  v2 executed 24.8 warp instructions per sample
-// at 57 % issue utilisation (profiles/r02j): instruction issue, not HBM, is the limit, and this halves it.
-// The windows hold the two rows INTERLEAVED sample by sample (4-byte cp.async, coalesced 128 B per warp instruction),
-// so a 128-bit shared load delivers two ready-made register pairs.  An unpaired last row is processed against itself
-// with the second half's results dropped.
+// Chunk-pair variant (round 2, second half): the v2 algorithm with TWO lane chunks of the same row in the halves of
+// packed FP32 registers.  A segment is 64 chunks of L4 = 32 samples; lane l owns chunk l (half x) and chunk l + 32
+// (half y), so every arithmetic instruction of v2 -- the 34-tap end-state map, the affine scan, the DF-I recursion,
+// the energy accumulation -- is ONE FFMA2 / FMUL2 / FADD2 on a (chunk l, chunk l + 32) pair with the coefficient
+// broadcast (profiles/r02j: v2 executes 24.8 warp instructions per sample at 57 % issue utilisation -- instruction
+// issue and dependent-issue latency, not HBM, are the limit).  The window holds the two halves INTERLEAVED sample by
+// sample (4-byte cp.async, coalesced 128 B per warp instruction, issued a few at a time inside the arithmetic of the
+// current segment), so one 128-bit shared load delivers two ready-made register pairs.  The scan runs on both halves
+// at once; half y is then re-based on half x's total:  c' = T_x + A^1024 carry,  carry' = T_y + A^1024 c'.
+// (A first packed version put two ROWS into the halves: it needed twice the window per warp, ran 6 warps per SM and
+// was slower than v2 -- 124 us against 100 us -- although it executed 40 % fewer instructions: profiles/README.md.)
 // =============================================================================================
-namespace v3 {
+namespace v4 {
 
-constexpr int L2 = v2::L2;             // samples per lane and row
-constexpr int SEG = v2::SEG;           // samples per warp segment and row
-constexpr int CHS = 2 * L2 + 4;        // words per lane chunk (both rows interleaved): 16 B aligned, conflict-free LDS.128
-constexpr int WPB = 6;                 // warps per CTA (one CTA per SM: 6 x 2 x 16.5 KB of windows)
+constexpr int L4 = 32;                 // samples per chunk
+constexpr int SEG = 64 * L4;           // samples per warp segment (2048, as v2)
+constexpr int HALF = 32 * L4;          // samples between the two chunks of a lane
+constexpr int CHS = 2 * L4 + 4;        // words per lane (both chunks interleaved): 16 B aligned, conflict-free LDS.128
+constexpr int WPB = 12;                // warps per CTA (one CTA per SM)
 constexpr int NBUF = 2;
-constexpr int BUF = 32 * CHS;          // floats per window
+constexpr int BUF = 32 * CHS;          // floats per window (8.7 KB)
+constexpr int NST = SEG / 32;          // 4-byte copies per lane and segment
 
 __device__ __forceinline__ void cp_async4(float* smem_dst, const float* gmem_src) {
 #ifdef B2A_SIM
@@ -762,23 +767,20 @@ __device__ __forceinline__ void cp_async4(float* smem_dst, const float* gmem_src
 #endif
 }
 
-// Stage segment `seg` of rows xa / xb into a warp window, interleaved: win[CHS * chunk + 2 * i + {0: A, 1: B}].
-__device__ __forceinline__ void stage_pair(const float* __restrict__ xa, const float* __restrict__ xb, int seg, int T,
-                                           float* win, int lane) {
-  const int t0 = seg * SEG;
-  if (t0 + SEG <= T) {
+// copy e (0 .. NST-1) of a segment: sample s = 32 e + lane -> win[CHS * (chunk & 31) + 2 * (s & 31) + (chunk >> 5)]
+__device__ __forceinline__ float* stage_dst(float* win, int e, int lane) { return &win[CHS * (e & 31) + 2 * lane + (e >> 5)]; }
+
+// Stage copies [e0, e1) of segment `seg` of row `xr` (interior segments: asynchronous, no registers).
+__device__ __forceinline__ void stage_some(const float* __restrict__ xr, int t0, bool interior, int T, float* win, int lane,
+                                           int e0, int e1) {
+  if (interior) {
 #pragma unroll
-    for (int e = 0; e < SEG / 32; ++e) {  // sample s = 32 e + lane: 128 contiguous bytes per warp instruction
-      float* d = &win[CHS * (e >> 1) + 2 * (32 * (e & 1) + lane)];
-      cp_async4(d, xa + t0 + 32 * e + lane);
-      cp_async4(d + 1, xb + t0 + 32 * e + lane);
-    }
+    for (int e = e0; e < e1; ++e) cp_async4(stage_dst(win, e, lane), xr + t0 + 32 * e + lane);
   } else {
-    for (int e = 0; e < SEG / 32; ++e) {
+#pragma unroll
+    for (int e = e0; e < e1; ++e) {
       const int n = t0 + 32 * e + lane;
-      float* d = &win[CHS * (e >> 1) + 2 * (32 * (e & 1) + lane)];
-      d[0] = (n < T) ? __ldg(xa + n) : 0.f;
-      d[1] = (n < T) ? __ldg(xb + n) : 0.f;
+      *stage_dst(win, e, lane) = (n < T) ? __ldg(xr + n) : 0.f;
     }
   }
 }
@@ -791,7 +793,7 @@ __device__ __forceinline__ float2 row_dot2(const float* M, int i, const float2* 
   return a;
 }
 
-// one step of the cascade on a pair of rows: the operation order of cascade_step, every product fused
+// one step of the cascade on a pair of chunks: the operation order of cascade_step, every product fused
 template <int NS>
 __device__ __forceinline__ float2 cascade_step2(const Coef<NS>& cf, float2 in0, float2 in1, float2 in2, float2 (&y1)[NS],
                                                 float2 (&y2)[NS]) {
@@ -805,6 +807,43 @@ __device__ __forceinline__ float2 cascade_step2(const Coef<NS>& cf, float2 in0, 
   return in0;
 }
 
+// interval bookkeeping of one chunk [n0, n0 + L4): first interval b0, split points s1 <= s2 (L4 = none), the
+// intervals b1, b2 behind them
+struct Split { int b0, b1, b2, s1, s2, nv; };
+__device__ __forceinline__ Split split_of(int n0, int Tp, int stride, int r) {
+  Split sp;
+  sp.nv = min(L4, max(0, Tp - n0));
+  const int j0 = n0 / stride, rem0 = n0 - j0 * stride;
+  sp.b0 = 2 * j0 + (rem0 >= r ? 1 : 0);
+  const int end0 = (sp.b0 & 1) ? (j0 + 1) * stride : j0 * stride + r;
+  sp.s1 = min(end0 - n0, L4);
+  sp.s2 = L4; sp.b1 = sp.b0; sp.b2 = sp.b0;
+  if (sp.s1 < L4) {
+    const int n1 = n0 + sp.s1, j1 = n1 / stride, rem1 = n1 - j1 * stride;
+    sp.b1 = 2 * j1 + (rem1 >= r ? 1 : 0);
+    const int end1 = (sp.b1 & 1) ? (j1 + 1) * stride : j1 * stride + r;
+    sp.s2 = min(end1 - n0, L4);
+    if (sp.s2 < L4) {
+      const int n2 = n0 + sp.s2, j2 = n2 / stride, rem2 = n2 - j2 * stride;
+      sp.b2 = 2 * j2 + (rem2 >= r ? 1 : 0);
+    }
+  }
+  return sp;
+}
+
+// energies of one half into the row's interval bins: one atomic per interval the warp touched
+__device__ __forceinline__ void flush_half(double* rb, int nbins, const Split& sp, float a0, float a1, float a2, bool clean,
+                                           int lane) {
+  const int blast = (sp.s2 < L4) ? sp.b2 : ((sp.s1 < L4) ? sp.b1 : sp.b0);
+  const int bf = __shfl_sync(0xffffffffu, sp.b0, 0), bl = __shfl_sync(0xffffffffu, blast, 31);
+  for (int id = bf; id <= bl; ++id) {
+    float v = (sp.b0 == id) ? a0 : 0.f;
+    if (!clean) v += ((sp.s1 < L4 && sp.b1 == id) ? a1 : 0.f) + ((sp.s2 < L4 && sp.b2 == id) ? a2 : 0.f);
+    v = warp_sum(v);
+    if (lane == 0 && id < nbins) atomicAdd(rb + id, (double)v);
+  }
+}
+
 template <int NS>
 __global__ void __launch_bounds__(32 * WPB, 1)
 kweight_energy_pair_kernel(const float* __restrict__ x, int rows, int T, int Tp, int nseg, int run_len, int n_runs,
@@ -813,56 +852,56 @@ kweight_energy_pair_kernel(const float* __restrict__ x, int rows, int T, int Tp,
   constexpr int D = 2 * NS;
   B2A_DYN_SMEM(smem);
   float* wins = reinterpret_cast<float*>(smem);  // [WPB][NBUF][BUF]
-  __shared__ __align__(16) float s_wa[L2 + 2][D];
+  __shared__ __align__(16) float s_wa[L4 + 2][D];
   __shared__ float s_mlane[32][D * D];
   __shared__ float s_mscan[5][D * D];
-  __shared__ float s_mseg[D * D];
+  __shared__ float s_mhalf[D * D];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  for (int i = tid; i < (L2 + 2) * D; i += blockDim.x) (&s_wa[0][0])[i] = (&tbv.Wa[0][0])[i];
+  for (int i = tid; i < (L4 + 2) * D; i += blockDim.x) (&s_wa[0][0])[i] = (&tbv.Wa[0][0])[i];
   for (int i = tid; i < 32 * D * D; i += blockDim.x) (&s_mlane[0][0])[i] = (&tbv.Mlane[0][0])[i];
   for (int i = tid; i < 5 * D * D; i += blockDim.x) (&s_mscan[0][0])[i] = (&tbv.Mscan[0][0])[i];
-  if (tid < D * D) s_mseg[tid] = tbv.Mseg[tid];
+  if (tid < D * D) s_mhalf[tid] = tbv.Mseg[tid];  // A^(32 L4): one half segment
   __syncthreads();  // the only CTA barrier: tables
-  const int npairs = (rows + 1) >> 1;
-  const int total = npairs * n_runs;
+  const int total = rows * n_runs;
   float* win0 = wins + (size_t)warp * NBUF * BUF;
 
 #pragma unroll 1
   for (int cur = (int)blockIdx.x * WPB + warp; cur < total; cur += (int)gridDim.x * WPB) {
-    const int run = cur / npairs, pr = cur - run * npairs;
-    const int rowa = 2 * pr;
-    const bool has_b = rowa + 1 < rows;
-    const int rowb = has_b ? rowa + 1 : rowa;
+    const int run = cur / rows, row = cur - run * rows;
     const int seg0 = run * run_len, seg1 = min(nseg, seg0 + run_len);
     const int segw = max(0, seg0 - n_warm);  // warm-up starts here, from a zero state
-    const float* xa = x + (size_t)rowa * (size_t)T;
-    const float* xb = x + (size_t)rowb * (size_t)T;
-    double* rba = bins + (size_t)rowa * (size_t)nbins;
-    double* rbb = bins + (size_t)rowb * (size_t)nbins;
-    float2 carry[D];  // state entering the current segment (all lanes hold it), (row A, row B)
+    const float* xr = x + (size_t)row * (size_t)T;
+    double* rb = bins + (size_t)row * (size_t)nbins;
+    float carry[D];  // state entering the current segment (all lanes hold it)
 #pragma unroll
-    for (int j = 0; j < D; ++j) carry[j] = make_float2(0.f, 0.f);
-    stage_pair(xa, xb, segw, T, win0, lane);
+    for (int j = 0; j < D; ++j) carry[j] = 0.f;
+    stage_some(xr, segw * SEG, segw * SEG + SEG <= T, T, win0, lane, 0, NST);
     int par = 0;
 #pragma unroll 1
     for (int seg = segw; seg < seg1; ++seg, par ^= (NBUF - 1)) {
       cp_async_wait_all();
       __syncwarp();
       const float* win = win0 + par * BUF;
-      if (seg + 1 < seg1) stage_pair(xa, xb, seg + 1, T, win0 + (par ^ 1) * BUF, lane);
+      float* wnext = win0 + (par ^ 1) * BUF;
+      const bool more = seg + 1 < seg1;
+      const int tn = (seg + 1) * SEG;
+      const bool next_in = tn + SEG <= T;
       const int t0 = seg * SEG;
-      float2 h0, h1;  // the two samples in front of this lane's chunk
-      if (lane == 0) {
-        const bool in0 = (t0 >= 2 && t0 - 2 < T), in1 = (t0 >= 1 && t0 - 1 < T);
-        h0 = make_float2(in0 ? __ldg(xa + t0 - 2) : 0.f, in0 ? __ldg(xb + t0 - 2) : 0.f);
-        h1 = make_float2(in1 ? __ldg(xa + t0 - 1) : 0.f, in1 ? __ldg(xb + t0 - 1) : 0.f);
-      } else {
-        const float4 h = *reinterpret_cast<const float4*>(&win[CHS * (lane - 1) + 2 * (L2 - 2)]);
-        h0 = make_float2(h.x, h.y); h1 = make_float2(h.z, h.w);
+      float2 h0, h1;  // the two samples in front of each of this lane's chunks
+      {
+        const float4 q = *reinterpret_cast<const float4*>(&win[CHS * ((lane + 31) & 31) + 2 * (L4 - 2)]);
+        if (lane == 0) {  // chunk 0 continues the previous segment, chunk 32 continues chunk 31 (half x of lane 31)
+          const float g0 = (t0 >= 2 && t0 - 2 < T) ? __ldg(xr + t0 - 2) : 0.f;
+          const float g1 = (t0 >= 1 && t0 - 1 < T) ? __ldg(xr + t0 - 1) : 0.f;
+          h0 = make_float2(g0, q.x); h1 = make_float2(g1, q.z);
+        } else {
+          h0 = make_float2(q.x, q.y); h1 = make_float2(q.z, q.w);
+        }
       }
       const float4* c4 = reinterpret_cast<const float4*>(&win[CHS * lane]);
       const float4* wa4 = reinterpret_cast<const float4*>(&s_wa[0][0]);  // D == 4: one 128-bit broadcast load per tap
-      // ---- zero-state end state of the lane's chunk as a linear map of its 66 inputs (two partial sums: ILP)
+      // ---- zero-state end state of the two chunks as a linear map of their 34 inputs (two partial sums: ILP); the
+      //      next segment's copies are issued four at a time in between
       float2 g[D], ge[D];
 #pragma unroll
       for (int i = 0; i < D; ++i) {
@@ -870,17 +909,17 @@ kweight_energy_pair_kernel(const float* __restrict__ x, int rows, int T, int Tp,
         ge[i] = mul2(bcast2(s_wa[1][i]), h1);
       }
 #pragma unroll
-      for (int i4 = 0; i4 < L2 / 2; ++i4) {
-        const float4 q = c4[i4];  // (A[2 i4], B[2 i4], A[2 i4 + 1], B[2 i4 + 1])
+      for (int i4 = 0; i4 < L4 / 2; ++i4) {
+        if (more) stage_some(xr, tn, next_in, T, wnext, lane, 4 * i4, 4 * i4 + 4);
+        const float4 q = c4[i4];  // (x[2 i4], y[2 i4], x[2 i4 + 1], y[2 i4 + 1])
+        const float2 q0 = make_float2(q.x, q.y), q1 = make_float2(q.z, q.w);
         if constexpr (D == 4) {
           const float4 w0 = wa4[2 + 2 * i4], w1 = wa4[3 + 2 * i4];
-          const float2 q0 = make_float2(q.x, q.y), q1 = make_float2(q.z, q.w);
           g[0] = fma2(bcast2(w0.x), q0, g[0]); g[1] = fma2(bcast2(w0.y), q0, g[1]);
           g[2] = fma2(bcast2(w0.z), q0, g[2]); g[3] = fma2(bcast2(w0.w), q0, g[3]);
           ge[0] = fma2(bcast2(w1.x), q1, ge[0]); ge[1] = fma2(bcast2(w1.y), q1, ge[1]);
           ge[2] = fma2(bcast2(w1.z), q1, ge[2]); ge[3] = fma2(bcast2(w1.w), q1, ge[3]);
         } else {
-          const float2 q0 = make_float2(q.x, q.y), q1 = make_float2(q.z, q.w);
 #pragma unroll
           for (int i = 0; i < D; ++i) {
             g[i] = fma2(bcast2(s_wa[2 + 2 * i4][i]), q0, g[i]);
@@ -891,7 +930,7 @@ kweight_energy_pair_kernel(const float* __restrict__ x, int rows, int T, int Tp,
 #pragma unroll
       for (int i = 0; i < D; ++i) g[i] = add2(g[i], ge[i]);
 #pragma unroll
-      for (int k = 0; k < 5; ++k) {  // inclusive affine scan over the 32 chunks
+      for (int k = 0; k < 5; ++k) {  // inclusive affine scan over the 32 chunks of each half
         float2 o[D];
 #pragma unroll
         for (int j = 0; j < D; ++j) {
@@ -903,51 +942,43 @@ kweight_energy_pair_kernel(const float* __restrict__ x, int rows, int T, int Tp,
           for (int i = 0; i < D; ++i) g[i] = add2(g[i], row_dot2<D>(s_mscan[k], i, o));
         }
       }
-      float2 ex[D], agg[D];
+      float2 ex[D];
+      float tx[D], ty[D];  // zero-state totals of the two halves
 #pragma unroll
       for (int j = 0; j < D; ++j) {
         ex[j].x = __shfl_up_sync(0xffffffffu, g[j].x, 1);
         ex[j].y = __shfl_up_sync(0xffffffffu, g[j].y, 1);
         if (lane == 0) ex[j] = make_float2(0.f, 0.f);
-        agg[j].x = __shfl_sync(0xffffffffu, g[j].x, 31);
-        agg[j].y = __shfl_sync(0xffffffffu, g[j].y, 31);
+        tx[j] = __shfl_sync(0xffffffffu, g[j].x, 31);
+        ty[j] = __shfl_sync(0xffffffffu, g[j].y, 31);
       }
+      float cmid[D];  // state entering half y:  T_x + A^HALF carry
+#pragma unroll
+      for (int i = 0; i < D; ++i) cmid[i] = tx[i] + row_dot<D>(s_mhalf, i, carry);
       if (seg >= seg0) {
-        // ---- true start state, recursion, energies into the interval bins
+        // ---- true start states, recursion, energies into the interval bins
         float2 y1[NS], y2[NS];
         {
+          float2 cv[D];
+#pragma unroll
+          for (int j = 0; j < D; ++j) cv[j] = make_float2(carry[j], cmid[j]);
 #pragma unroll
           for (int s = 0; s < NS; ++s) {
-            y1[s] = add2(ex[2 * s], row_dot2<D>(s_mlane[lane], 2 * s, carry));
-            y2[s] = add2(ex[2 * s + 1], row_dot2<D>(s_mlane[lane], 2 * s + 1, carry));
+            y1[s] = add2(ex[2 * s], row_dot2<D>(s_mlane[lane], 2 * s, cv));
+            y2[s] = add2(ex[2 * s + 1], row_dot2<D>(s_mlane[lane], 2 * s + 1, cv));
           }
         }
-        const int n0 = t0 + lane * L2;
-        const int nv = min(L2, max(0, Tp - n0));
-        int j0 = n0 / stride, rem0 = n0 - j0 * stride;
-        int b0 = 2 * j0 + (rem0 >= r ? 1 : 0);
-        int end0 = (b0 & 1) ? (j0 + 1) * stride : j0 * stride + r;
-        const int s1 = min(end0 - n0, L2);
-        int s2 = L2, b1 = b0, b2 = b0;
-        if (s1 < L2) {
-          const int n1 = n0 + s1, j1 = n1 / stride, rem1 = n1 - j1 * stride;
-          b1 = 2 * j1 + (rem1 >= r ? 1 : 0);
-          const int end1 = (b1 & 1) ? (j1 + 1) * stride : j1 * stride + r;
-          s2 = min(end1 - n0, L2);
-          if (s2 < L2) {
-            const int n2 = n0 + s2, j2 = n2 / stride, rem2 = n2 - j2 * stride;
-            b2 = 2 * j2 + (rem2 >= r ? 1 : 0);
-          }
-        }
-        const bool simple = (s1 >= L2) && (nv == L2);
-        const bool clean = __all_sync(0xffffffffu, simple);  // warp-uniform: no lane straddles an interval boundary
+        const Split sx = split_of(t0 + lane * L4, Tp, stride, r);
+        const Split sy = split_of(t0 + HALF + lane * L4, Tp, stride, r);
+        const bool simple = (sx.s1 >= L4) && (sx.nv == L4) && (sy.s1 >= L4) && (sy.nv == L4);
+        const bool clean = __all_sync(0xffffffffu, simple);  // warp-uniform: no chunk straddles an interval boundary
         const float2 zero2 = make_float2(0.f, 0.f);
         float2 a0 = zero2, a1 = zero2, a2 = zero2;
         float2 xm2 = h0, xm1 = h1;
         if (clean) {
           float2 acc = zero2;
 #pragma unroll
-          for (int i4 = 0; i4 < L2 / 2; ++i4) {
+          for (int i4 = 0; i4 < L4 / 2; ++i4) {
             const float4 q = c4[i4];
             const float2 qs[2] = {make_float2(q.x, q.y), make_float2(q.z, q.w)};
 #pragma unroll
@@ -961,59 +992,41 @@ kweight_energy_pair_kernel(const float* __restrict__ x, int rows, int T, int Tp,
         } else {
           float2 acc = zero2, p1 = zero2, p2 = zero2;  // running energy and its value at the two interval boundaries
 #pragma unroll
-          for (int i4 = 0; i4 < L2 / 2; ++i4) {
+          for (int i4 = 0; i4 < L4 / 2; ++i4) {
             const float4 q = c4[i4];
             const float2 qs[2] = {make_float2(q.x, q.y), make_float2(q.z, q.w)};
 #pragma unroll
             for (int e = 0; e < 2; ++e) {
               const int i = 2 * i4 + e;
-              if (i == s1) p1 = acc;
-              if (i == s2) p2 = acc;
+              p1.x = (i == sx.s1) ? acc.x : p1.x; p1.y = (i == sy.s1) ? acc.y : p1.y;
+              p2.x = (i == sx.s2) ? acc.x : p2.x; p2.y = (i == sy.s2) ? acc.y : p2.y;
               const float2 y = cascade_step2<NS>(cf, qs[e], xm1, xm2, y1, y2);
               xm2 = xm1; xm1 = qs[e];
               const float2 an = fma2(y, y, acc);
-              if (i < nv) acc = an;
+              acc.x = (i < sx.nv) ? an.x : acc.x; acc.y = (i < sy.nv) ? an.y : acc.y;
             }
           }
-          if (s1 >= L2) p1 = acc;
-          if (s2 >= L2) p2 = acc;
+          if (sx.s1 >= L4) p1.x = acc.x;
+          if (sy.s1 >= L4) p1.y = acc.y;
+          if (sx.s2 >= L4) p2.x = acc.x;
+          if (sy.s2 >= L4) p2.y = acc.y;
           a0 = p1; a1 = add2(p2, neg2(p1)); a2 = add2(acc, neg2(p2));
         }
-        // one atomic per row and interval the warp touched (intervals are monotonic in the lane index)
-        const int blast = (s2 < L2) ? b2 : ((s1 < L2) ? b1 : b0);  // last interval this lane's chunk reaches
-        const int bf = __shfl_sync(0xffffffffu, b0, 0), bl = __shfl_sync(0xffffffffu, blast, 31);
-        for (int id = bf; id <= bl; ++id) {
-          float2 v = (b0 == id) ? a0 : zero2;
-          if (!clean) {
-            if (s1 < L2 && b1 == id) v = add2(v, a1);
-            if (s2 < L2 && b2 == id) v = add2(v, a2);
-          }
-#pragma unroll
-          for (int o = 16; o > 0; o >>= 1) {
-            float2 t;
-            t.x = __shfl_xor_sync(0xffffffffu, v.x, o);
-            t.y = __shfl_xor_sync(0xffffffffu, v.y, o);
-            v = add2(v, t);
-          }
-          if (lane == 0 && id < nbins) {
-            atomicAdd(rba + id, (double)v.x);
-            if (has_b) atomicAdd(rbb + id, (double)v.y);
-          }
-        }
+        flush_half(rb, nbins, sx, a0.x, a1.x, a2.x, clean, lane);
+        flush_half(rb, nbins, sy, a0.y, a1.y, a2.y, clean, lane);
       }
-      // ---- carry into the next segment: A^SEG carry + (zero-state end state of this segment)
-      float2 cn[D];
+      // ---- carry into the next segment: A^HALF (state entering half y) + (zero-state end state of half y)
 #pragma unroll
-      for (int i = 0; i < D; ++i) cn[i] = add2(agg[i], row_dot2<D>(s_mseg, i, carry));
+      for (int i = 0; i < D; ++i) tx[i] = ty[i] + row_dot<D>(s_mhalf, i, cmid);
 #pragma unroll
-      for (int i = 0; i < D; ++i) carry[i] = cn[i];
+      for (int i = 0; i < D; ++i) carry[i] = tx[i];
       __syncwarp();  // every lane is done with this window before it is refilled
     }
   }
   cp_async_wait_all();
 }
 
-}  // namespace v3
+}  // namespace v4
 
 // ---------------------------------------------------------------------------------------------
 // gating: ref:audiotools/core/loudness.py:208-247 (+ :315-320 clamp, effects.py:214-217 gain)
@@ -1170,7 +1183,7 @@ static int use_v1() {
   return v;
 }
 
-static int use_v2() {  // B2A_LUFS_V2=1: one row per warp, scalar FP32 (the kernel the pair kernel was derived from)
+static int use_v2() {  // B2A_LUFS_V2=1: one chunk per lane, scalar FP32 (the kernel the chunk-pair kernel was derived from)
   static int v = -1;
   if (v < 0) {
     const char* e = getenv("B2A_LUFS_V2");
@@ -1233,23 +1246,22 @@ static int run(const float* x, int64_t B, int C, int64_t T, int64_t Tp, const Ge
       if (n_warm < 1) n_warm = 1;
     }
     const bool pairs = !use_v2();
-    const int64_t units = pairs ? (rows + 1) / 2 : rows;  // independent streams: row pairs (v3) or rows (v2)
-    const int wpb = pairs ? v3::WPB : v2::WPB;
-    int64_t rpr = (resident * wpb) / units;
+    const int wpb = pairs ? v4::WPB : v2::WPB;
+    int64_t rpr = (resident * wpb) / rows;
     if (rpr < 1) rpr = 1;
     int run_len = (int)((g.nseg + rpr - 1) / rpr);
     if (run_len < 4 * n_warm) run_len = 4 * n_warm;  // at most 25 % warm-up
     if (run_len > g.nseg) run_len = g.nseg;
     const int n_runs = (g.nseg + run_len - 1) / run_len;
     v2::Tables2<NS> tb2;
-    v2::build_tables2<NS>(cf, &tb2);
-    const int64_t runs_all = units * n_runs;
+    v2::build_tables2<NS>(cf, &tb2, pairs ? v4::L4 : v2::L2);
+    const int64_t runs_all = rows * n_runs;
     const int64_t want = (runs_all + wpb - 1) / wpb;
     const unsigned grid = (unsigned)(want < resident ? want : resident);
     if (pairs) {
-      const size_t smem = (size_t)v3::WPB * v3::NBUF * v3::BUF * sizeof(float);
-      B2A_CUDA_OK(cudaFuncSetAttribute(v3::kweight_energy_pair_kernel<NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      B2A_LAUNCH(v3::kweight_energy_pair_kernel<NS>, dim3(grid), dim3(32 * v3::WPB), smem, stream, x, (int)rows, (int)T,
+      const size_t smem = (size_t)v4::WPB * v4::NBUF * v4::BUF * sizeof(float);
+      B2A_CUDA_OK(cudaFuncSetAttribute(v4::kweight_energy_pair_kernel<NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      B2A_LAUNCH(v4::kweight_energy_pair_kernel<NS>, dim3(grid), dim3(32 * v4::WPB), smem, stream, x, (int)rows, (int)T,
                  (int)Tp, g.nseg, run_len, n_runs, n_warm, cf, tb2, (double*)(base + w.bins), g.stride, g.r, g.nbins);
     } else {
       const size_t smem = (size_t)v2::WPB * v2::NBUF * v2::BUF * sizeof(float);

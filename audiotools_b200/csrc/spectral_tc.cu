@@ -374,12 +374,12 @@ __global__ void __launch_bounds__(THREADS, 1) spectral_tc_kernel(const B2A_GRID_
     if (tid == 0) {
       int run = 0, reach = 0;
       for (int w = 0; w < 8; ++w)
-        for (int i = 0; w + 32 * i < p.n_mels; ++i) {
+        for (int i = 0; 4 * (w + 8 * i) < p.n_mels; ++i) {
           int mx = 0;
-          for (int j = 0; j < 4; ++j) { const int m = w + 8 * (4 * i + j); if (m < p.n_mels) mx = max(mx, mseg[m].z); }
+          for (int j = 0; j < 4; ++j) { const int m = 4 * (w + 8 * i) + j; if (m < p.n_mels) mx = max(mx, mseg[m].z); }
           mx = (mx + 1) & ~1;
           for (int j = 0; j < 4; ++j) {
-            const int m = w + 8 * (4 * i + j);
+            const int m = 4 * (w + 8 * i) + j;
             if (m < p.n_mels) { mseg[m].x = run; mseg[m].w = mx; run += mx; reach = max(reach, mseg[m].y + 4 * mx); }
           }
         }
@@ -604,7 +604,7 @@ __global__ void __launch_bounds__(THREADS, 1) spectral_tc_kernel(const B2A_GRID_
       if (packed) {
         const float4* mpk4 = reinterpret_cast<const float4*>(mpk);
         const int lim = XBS - 4;
-        for (int mm = w8 + 8 * jq; mm < p.n_mels; mm += 32) {
+        for (int mm = 4 * w8 + jq; mm < p.n_mels; mm += 32) {
           const int4 sg = mseg[mm];
           const float4* w4 = mpk4 + sg.x;
           float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
@@ -631,7 +631,7 @@ __global__ void __launch_bounds__(THREADS, 1) spectral_tc_kernel(const B2A_GRID_
           melt[mm * (FR + 1) + f] = acc;
         }
       } else {
-        for (int mm = w8 + 8 * jq; mm < p.n_mels; mm += 32) {
+        for (int mm = 4 * w8 + jq; mm < p.n_mels; mm += 32) {
           const int lo = __ldg(p.mel_lo + mm), hi = __ldg(p.mel_hi + mm);
           const float* wrow = p.mel_fb + (size_t)mm * F;
           float acc = 0.f;

@@ -351,21 +351,20 @@ class Engine:
     # ------------------------------------------------------------------ STFT / mel
     def _packed_len(self, mel_lo: torch.Tensor, mel_hi: torch.Tensor, n_fft: int) -> int:
         """Floats of the shared-memory band table of csrc/spectral.cu: row m is filter m's 4-aligned band, padded
-        to the widest of the (up to) 4 filters {w + 8*(4i + j), j < 4} that warp w = m % 8 projects in step i, rounded
-        up to an even number of float4s (the projection loop is unrolled by two, no remainder)."""
+        to the widest of the (up to) 4 CONSECUTIVE filters {4g .. 4g + 3} that one warp instruction projects together
+        (group g = w + 8i for warp w, step i; neighbouring filters have nearly equal widths, so the padding is small),
+        rounded up to an even number of float4s (the projection loop is unrolled by two, no remainder).
+        The cache entry keeps the two tensors alive, so their addresses cannot be reused by another filterbank."""
         key = (mel_lo.data_ptr(), mel_hi.data_ptr(), mel_lo.numel())
         if key not in self._packed_cache:
             lo, hi = mel_lo.cpu().numpy().astype("int64"), mel_hi.cpu().numpy().astype("int64")
             n4 = ((((hi + 3) & ~3) - (lo & ~3)) >> 2).clip(min=0)
             n, total = len(n4), 0
-            for w in range(8):
-                i = 0
-                while w + 32 * i < n:
-                    grp = [w + 8 * (4 * i + j) for j in range(4) if w + 8 * (4 * i + j) < n]
-                    total += ((int(max(n4[m] for m in grp)) + 1) & ~1) * len(grp)  # rows padded to an even width
-                    i += 1
-            self._packed_cache[key] = 4 * total
-        return self._packed_cache[key]
+            for g in range(0, n, 4):
+                grp = range(g, min(g + 4, n))
+                total += ((int(max(n4[m] for m in grp)) + 1) & ~1) * len(grp)  # rows padded to an even width
+            self._packed_cache[key] = (4 * total, mel_lo, mel_hi)
+        return self._packed_cache[key][0]
 
     def spectral_kernel_name(self, n_fft: int, hop: int, want_mel: bool = True, want_stft: bool = False) -> str:
         """Name of the kernel ``spectral`` launches for this geometry (bench.py / profiles label their numbers with it)."""

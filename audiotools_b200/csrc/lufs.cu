@@ -744,8 +744,12 @@ kweight_energy_warp_kernel(const float* __restrict__ x, int rows, int T, int Tp,
 // sample (4-byte cp.async, coalesced 128 B per warp instruction, issued a few at a time inside the arithmetic of the
 // current segment), so one 128-bit shared load delivers two ready-made register pairs.  The scan runs on both halves
 // at once; half y is then re-based on half x's total:  c' = T_x + A^1024 carry,  carry' = T_y + A^1024 c'.
-// (A first packed version put two ROWS into the halves: it needed twice the window per warp, ran 6 warps per SM and
-// was slower than v2 -- 124 us against 100 us -- although it executed 40 % fewer instructions: profiles/README.md.)
+// MEASURED (64 x 2ch x 10 s, profiles/r02n_prof_lufs_pair_*): 116 us against v2's 100 us -- 47.0 M warp instructions
+// (v2: 51.7 M; the 32-sample chunks double the per-segment scan / bookkeeping share and the boundary path runs on two
+// split points), issue-active 43 %, shared-memory data pipe 56 % busy.  A first packed version with two ROWS in the
+// halves (twice the window per warp, 6 warps per SM) took 124 us with 31.3 M instructions at 30 % issue-active.  Both
+// say the same as the packed K1: these kernels wait on dependent-issue and shared-memory latency, not on issue slots.
+// The kernel therefore stays OPT-IN (B2A_LUFS_PAIR=1); v2 is the default.
 // =============================================================================================
 namespace v4 {
 
@@ -1183,13 +1187,9 @@ static int use_v1() {
   return v;
 }
 
-static int use_v2() {  // B2A_LUFS_V2=1: one chunk per lane, scalar FP32 (the kernel the chunk-pair kernel was derived from)
-  static int v = -1;
-  if (v < 0) {
-    const char* e = getenv("B2A_LUFS_V2");
-    v = (e && e[0] == '1') ? 1 : 0;
-  }
-  return v;
+static int use_pair() {  // B2A_LUFS_PAIR=1: the chunk-pair (packed FP32) kernel, measured slower than v2 (116 vs 100 us)
+  const char* e = getenv("B2A_LUFS_PAIR");  // read per call: the tests switch it
+  return (e && e[0] == '1') ? 1 : 0;
 }
 
 template <int NS>
@@ -1245,7 +1245,7 @@ static int run(const float* x, int64_t B, int C, int64_t T, int64_t Tp, const Ge
       n_warm = (int)((n_tail + v2::SEG - 1) / v2::SEG);
       if (n_warm < 1) n_warm = 1;
     }
-    const bool pairs = !use_v2();
+    const bool pairs = use_pair() != 0;
     const int wpb = pairs ? v4::WPB : v2::WPB;
     int64_t rpr = (resident * wpb) / rows;
     if (rpr < 1) rpr = 1;

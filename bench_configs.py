@@ -4,6 +4,12 @@ bench.py, which measures configs[1]).  One JSON line per config: device-resident
 >= 3 warm-ups, inputs larger than L2 or rotated), algorithmic bytes, and the CPU oracle on a bounded sample.
 
     python bench_configs.py [--only cfg1,cfg3,cfg4,cfg5,istft,specaug] [--no-cpu]
+
+Multi-GPU (BASELINE configs[3] = 512 items on 4 GPUs, configs[4] = 2048 items on 8 GPUs): one process per GPU,
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 4 --master-addr 127.0.0.1 --master-port 29511 \
+        bench_configs.py --gpus 4 --only cfg4
+every rank owns its slice of the batch (128 / 256 items, seeded by rank; no data-path collective), the timed region
+is bracketed by a barrier + synchronize, the step time is the MAX over ranks and rank 0 prints the whole-job line.
 """
 import argparse
 import json
@@ -18,17 +24,46 @@ REPO = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, REPO)
 
 
+WORLD = int(os.environ.get("WORLD_SIZE", "1"))
+RANK = int(os.environ.get("RANK", "0"))
+LOCAL = int(os.environ.get("LOCAL_RANK", "0"))
+
+
+def _barrier():
+    if WORLD > 1:
+        import torch.distributed as dist
+
+        dist.barrier()
+
+
 def timed(fn, warmup=3, steps=10):
+    """ms per step: CUDA events on the launching stream, >= 3 warm-ups unless stated, barrier + synchronize on both
+    sides and the MAX over ranks when launched under torchrun."""
     for _ in range(warmup):
         fn()
     torch.cuda.synchronize()
+    _barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(steps):
         fn()
     e1.record()
     torch.cuda.synchronize()
-    return e0.elapsed_time(e1) / steps  # ms
+    _barrier()
+    ms = e0.elapsed_time(e1) / steps
+    if WORLD > 1:
+        import torch.distributed as dist
+
+        t = torch.tensor([ms], device=f"cuda:{LOCAL}", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    return ms
+
+
+def emit(line):
+    if RANK == 0:
+        line["n_gpus"] = WORLD
+        print(json.dumps(line), flush=True)
 
 
 def cpu_time(fn, reps=2):
@@ -43,15 +78,23 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--only", default="cfg1,cfg3,cfg4,cfg5,istft,specaug")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--gpus", type=int, default=1, help="ranks (informational: the launcher sets WORLD_SIZE)")
     args = ap.parse_args()
     import __graft_entry__ as graft
 
     graft.build()
+    torch.cuda.set_device(LOCAL)
+    if WORLD > 1:
+        import torch.distributed as dist
+
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{LOCAL}"))
+        args.no_cpu = True
     from audiotools_b200 import AudioSignal
     from audiotools_b200.data import transforms as tfm
     from oracle import signal_path as sp
 
-    dev = "cuda:0"
+    dev = f"cuda:{LOCAL}"
     peak = 6576.1
     pp = os.path.join(REPO, "MEASURED_PEAKS.json")
     if os.path.exists(pp):
@@ -67,7 +110,7 @@ def main():
                 "alg_bytes": 64000 + 1036224}
         if not args.no_cpu:
             line["cpu_ms"] = 1e3 * cpu_time(lambda: sp.stft(x, 16000, 512, 128), reps=20)
-        print(json.dumps(line))
+        emit(line)
 
     if "cfg3" in only:  # batch=256 mono 30s@48k -> 16k polyphase resample + low_pass(8k)
         B = 256
@@ -90,12 +133,12 @@ def main():
             xc = x[:8].cpu()
             t = cpu_time(lambda: sp.low_pass(sp.resample(xc, 48000, 16000), 16000, 8000), reps=1)
             line["cpu_clips_per_s"] = 8 / t
-        print(json.dumps(line))
+        emit(line)
         del x
 
     if "cfg4" in only:  # batch=512 Compose[EQ + IR-convolve + pitch_shift +-2], mono 10s@44.1k (one GPU's share: 128)
         B, T, sr = 128, 441000, 44100
-        g = torch.Generator().manual_seed(0)
+        g = torch.Generator().manual_seed(RANK)
         x = 0.1 * torch.randn(B, 1, T, generator=g)
         t = torch.arange(sr) / sr
         irs = []
@@ -106,12 +149,12 @@ def main():
         transform = tfm.Compose([tfm.Equalizer(), tfm.RoomImpulseResponse(sources=irs),
                                  tfm.PitchShift(("choice", [-2, 2]))])
         sig = AudioSignal(x, sr)
-        kwargs = transform.batch_instantiate(list(range(B)), sig)
+        kwargs = transform.batch_instantiate(list(range(RANK * B, (RANK + 1) * B)), sig)
         sig = sig.to(dev)
         from audiotools_b200 import util
 
         kwargs = util.prepare_batch(kwargs, dev)
-        ms = timed(lambda: transform(sig.clone(), **kwargs), warmup=2, steps=3)
+        ms = timed(lambda: transform(sig.clone(), **kwargs), warmup=3, steps=5)
         per = {}
         for name, fn in [("equalizer", lambda: sig.clone().equalizer(kwargs["Compose"]["0.Equalizer"]["eq"])),
                          ("apply_ir", lambda: sig.clone().apply_ir(kwargs["Compose"]["1.RoomImpulseResponse"]["ir_signal"].clone(),
@@ -119,13 +162,14 @@ def main():
                                                                    kwargs["Compose"]["1.RoomImpulseResponse"]["eq"])),
                          ("pitch_shift", lambda: sig.clone().pitch_shift(2))]:
             per[name] = timed(fn, warmup=1, steps=3)
-        line = {"config": f"cfg4 per-GPU share batch={B} mono 10s@44.1k Compose[EQ+RoomIR+PitchShift+-2]", "ms": ms,
-                "clips_per_s": B / ms * 1e3, "ms_parts": per}
-        print(json.dumps(line))
+        line = {"config": f"cfg4 batch={B * WORLD} ({B} per GPU) mono 10s@44.1k Compose[EQ+RoomIR+PitchShift+-2]", "ms": ms,
+                "clips_per_s": B * WORLD / ms * 1e3, "per_gpu_batch": B, "global_batch": B * WORLD, "ms_parts": per,
+                "timing": "CUDA events, barrier + synchronize both sides, max over ranks; no data-path collective"}
+        emit(line)
 
     if "cfg5" in only:  # batch=2048 2ch 10s@44.1k full augment + LUFS + log-mel on 8 GPUs: one GPU's share (256 items)
         B, T, sr = 256, 441000, 44100
-        g = torch.Generator().manual_seed(1)
+        g = torch.Generator().manual_seed(100 + RANK)
         x = 0.1 * torch.randn(B, 2, T, generator=g)
         t = torch.arange(sr) / sr
         irs = []
@@ -136,7 +180,7 @@ def main():
         transform = tfm.Compose([tfm.Equalizer(), tfm.RoomImpulseResponse(sources=irs),
                                  tfm.PitchShift(("choice", [-2, 2]))])
         sig = AudioSignal(x, sr)
-        kwargs = transform.batch_instantiate(list(range(B)), sig)
+        kwargs = transform.batch_instantiate(list(range(RANK * B, (RANK + 1) * B)), sig)
         sig = sig.to(dev)
         from audiotools_b200 import util
 
@@ -147,9 +191,11 @@ def main():
             s.normalize(-24.0)
             return s.mel_spectrogram(n_mels=128, window_length=2048, hop_length=512, log=True)
 
-        ms = timed(full, warmup=2, steps=3)
-        print(json.dumps({"config": f"cfg5 per-GPU share batch={B} 2ch 10s@44.1k Compose[EQ+RoomIR+PitchShift+-2] + "
-                                    "LUFS normalize + log-mel", "ms": ms, "clips_per_s": B / ms * 1e3}))
+        ms = timed(full, warmup=3, steps=5)
+        emit({"config": f"cfg5 batch={B * WORLD} ({B} per GPU) 2ch 10s@44.1k Compose[EQ+RoomIR+PitchShift+-2] + "
+                        "LUFS normalize + log-mel", "ms": ms, "clips_per_s": B * WORLD / ms * 1e3, "per_gpu_batch": B,
+              "global_batch": B * WORLD,
+              "timing": "CUDA events, barrier + synchronize both sides, max over ranks; no data-path collective"})
         del x, sig
 
     if "istft" in only:  # inverse STFT at cfg2's shape (64 x 2ch x 10 s @ 44.1 kHz, 2048/512)
@@ -163,9 +209,9 @@ def main():
         Xr = X.reshape(128, 1025, -1)
         ms_torch = timed(lambda: torch.istft(Xr, 2048, 512, window=w, center=True, length=441000), steps=5)
         alg = X.numel() * 8 + x.numel() * 4
-        print(json.dumps({"config": "istft 64x2ch 10s@44.1k n_fft=2048 hop=512", "ms": ms, "ms_torch_istft_cufft": ms_torch,
+        emit({"config": "istft 64x2ch 10s@44.1k n_fft=2048 hop=512", "ms": ms, "ms_torch_istft_cufft": ms_torch,
                           "clips_per_s": 64 / ms * 1e3, "alg_bytes": alg, "achieved_GBps": alg / ms / 1e6,
-                          "frac_of_hbm_peak": alg / ms / 1e6 / peak}))
+                          "frac_of_hbm_peak": alg / ms / 1e6 / peak})
 
     if "specaug" in only:  # SpectralTransform chain stft -> FrequencyMask -> TimeMask -> istft at cfg2's shape
         g = torch.Generator().manual_seed(0)
@@ -200,9 +246,13 @@ def main():
 
         ms = timed(ours, warmup=2, steps=5)
         ms_stock = timed(stock_ops, warmup=1, steps=3)
-        print(json.dumps({"config": "specaug 64x2ch 10s@44.1k stft->mask_frequencies->mask_timesteps->istft (2048/512)",
-                          "ms": ms, "ms_reference_tensor_ops_on_gpu": ms_stock, "clips_per_s": B / ms * 1e3}))
+        emit({"config": "specaug 64x2ch 10s@44.1k stft->mask_frequencies->mask_timesteps->istft (2048/512)",
+                          "ms": ms, "ms_reference_tensor_ops_on_gpu": ms_stock, "clips_per_s": B / ms * 1e3})
 
 
 if __name__ == "__main__":
     main()
+    if WORLD > 1:
+        import torch.distributed as dist
+
+        dist.destroy_process_group()

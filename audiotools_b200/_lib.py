@@ -69,6 +69,16 @@ SIGNATURES = {
     "b2a_time_stretch_out_len": (c_int64, [c_int64, c_double]),
     "b2a_time_stretch_workspace_bytes": (c_size_t, [c_int64, c_int64, c_int, c_double]),
     "b2a_time_stretch_f32": (c_int, [c_void_p, c_int64, c_int64, c_int, c_double, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "b2a_dft_supported": (c_int, [c_int, c_int]),
+    "b2a_dft_matrix_floats": (c_size_t, [c_int, c_int]),
+    "b2a_dft_matrix_f32": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p]),
+    "b2a_stft_dense_f32": (c_int, [c_void_p, c_int64, c_int64, c_int, c_int, c_void_p, c_int, c_int, c_int, c_int,
+                                   c_void_p, c_void_p]),
+    "b2a_mel_from_stft_f32": (c_int, [c_void_p, c_int64, c_int, c_int64, c_void_p, c_void_p, c_void_p, c_int, c_int,
+                                      c_float, c_float, c_void_p, c_void_p]),
+    "b2a_istft_dense_workspace_bytes": (c_size_t, [c_int64, c_int64, c_int]),
+    "b2a_istft_dense_f32": (c_int, [c_void_p, c_int64, c_int64, c_int, c_int, c_void_p, c_void_p, c_int, c_int64,
+                                    c_int64, c_void_p, c_void_p, c_size_t, c_void_p]),
     "b2a_istft_supported": (c_int, [c_int, c_int]),
     "b2a_istft_f32": (c_int, [c_void_p, c_int64, c_int64, c_int, c_int, c_void_p, c_int, c_int64, c_int64, c_void_p,
                               c_void_p]),

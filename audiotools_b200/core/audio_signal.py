@@ -458,38 +458,24 @@ class AudioSignal(EffectMixin, LoudnessMixin, ImpulseResponseMixin, DSPMixin):
     def istft(self, window_length: int = None, hop_length: int = None, window_type: str = None,
               match_stride: bool = None, length: int = None):
         """Inverse STFT of ``stft_data`` into ``audio_data`` (ref :1214-1296): one fused kernel (inverse real FFT,
-        window, overlap-add, envelope division; ``csrc/istft.cu``) for power-of-two windows in [64, 2048].  Other
-        window lengths (32, 4096) still go through ``torch.istft`` on the device."""
+        window, overlap-add, envelope division; ``csrc/istft.cu``) for power-of-two windows in [64, 2048]; every other
+        window length runs as a dense inverse DFT + overlap-add fold (``csrc/dft.cu``).  No ``torch.istft`` on the path."""
         if self.stft_data is None:
             raise RuntimeError("Cannot do inverse STFT without self.stft_data!")
         window_length, hop_length, window_type, match_stride, _ = self._resolve_stft(
             window_length, hop_length, window_type, match_stride, None)
         window = self.get_window(window_type, window_length, self.stft_data.device)
-        nb, nch, nf, nt = self.stft_data.shape
         right_pad, pad = self.compute_stft_padding(window_length, hop_length, match_stride)
         if length is None:
             length = self.original_signal_length + 2 * pad + right_pad
-        eng = _engine()
-        if eng.lib.b2a_istft_supported(int(window_length), int(hop_length)):  # (the engine refuses CPU tensors)
-            if match_stride:
-                # the reference pads 2 zero frames on either side, inverts to `length`, then keeps
-                # [pad : length - (pad + right_pad)] (:1276-1292)
-                audio = eng.istft(self.stft_data, window_length, hop_length, window,
-                                  length=length - 2 * pad - right_pad, pad_frames=2, trim=pad)
-            else:
-                audio = eng.istft(self.stft_data, window_length, hop_length, window, length=length)
-            self.audio_data = audio
-            return self
-        if eng.require_cuda and not self.stft_data.is_cuda:
-            raise RuntimeError(f"stft_data is on {self.stft_data.device}: audiotools_b200 runs on CUDA (sm_100a) "
-                               "only and has no CPU fallback")
-        s = self.stft_data.reshape(nb * nch, nf, nt)
+        eng = _engine()  # (the engine refuses CPU tensors)
         if match_stride:
-            s = torch.nn.functional.pad(s, (2, 2))
-        audio = torch.istft(s, n_fft=window_length, hop_length=hop_length, window=window, length=length, center=True)
-        audio = audio.reshape(nb, nch, -1)
-        if match_stride:
-            audio = audio[..., pad: -(pad + right_pad)]
+            # the reference pads 2 zero frames on either side, inverts to `length`, then keeps
+            # [pad : length - (pad + right_pad)] (:1276-1292)
+            audio = eng.istft(self.stft_data, window_length, hop_length, window,
+                              length=length - 2 * pad - right_pad, pad_frames=2, trim=pad)
+        else:
+            audio = eng.istft(self.stft_data, window_length, hop_length, window, length=length)
         self.audio_data = audio
         return self
 

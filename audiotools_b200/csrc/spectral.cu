@@ -750,7 +750,8 @@ int frames_fft(const float* x, int rows, int T, int n_fft, int hop, const float*
 extern "C" int64_t b2a_stft_num_frames(int64_t T, int n_fft, int hop, int pad, int right_pad, int drop_edge) {
   if (T < 1 || n_fft < 2 || hop < 1 || pad < 0 || right_pad < 0 || drop_edge < 0) return -1;
   // torch.stft(center=True): 1 + (len + 2*(n_fft/2) - n_fft) / hop  with len = T + 2 pad + right_pad
-  int64_t n = 1 + (T + 2 * (int64_t)pad + right_pad) / hop - 2 * (int64_t)drop_edge;
+  // (an odd window length loses one sample: 2*(n_fft/2) - n_fft = -(n_fft & 1))
+  int64_t n = 1 + (T + 2 * (int64_t)pad + right_pad - (n_fft & 1)) / hop - 2 * (int64_t)drop_edge;
   return n;
 }
 

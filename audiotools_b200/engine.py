@@ -89,8 +89,9 @@ class Engine:
         spec = spec.contiguous()
         B, C, F, N = spec.shape
         assert F == n_fft // 2 + 1, (F, n_fft)
-        if not self.lib.b2a_istft_supported(int(n_fft), int(hop)):
-            raise NotImplementedError(f"istft: n_fft={n_fft} hop={hop} (power-of-two n_fft in [64, 2048])")
+        dense = not self.lib.b2a_istft_supported(int(n_fft), int(hop))
+        if dense and not (self.lib.b2a_dft_supported(int(n_fft), int(hop)) and hop <= n_fft):
+            raise NotImplementedError(f"istft: n_fft={n_fft} hop={hop}")
         window = self._prep(window, "window")
         assert window.numel() == n_fft
         start = n_fft // 2 + int(trim)
@@ -103,11 +104,43 @@ class Engine:
         if self._packed_cache[key][1] < 1e-11:
             raise RuntimeError("istft: window overlap add min: 1 (the window envelope vanishes inside the output)")
         out = torch.empty(B, C, int(length), dtype=torch.float32, device=spec.device)
+        if dense:  # any other window length (and 32 / 4096): transposed dense DFT + overlap-add fold (csrc/dft.cu)
+            imat = self.dft_matrix(window, int(n_fft), inverse=True)
+            nbytes = int(self.lib.b2a_istft_dense_workspace_bytes(B * C, N, int(n_fft)))
+            ws = torch.empty((nbytes + 3) // 4, dtype=torch.float32, device=spec.device)
+            rc = self.lib.b2a_istft_dense_f32(_dptr(torch.view_as_real(spec)), B * C, N, int(n_fft), int(hop), _dptr(window),
+                                              _dptr(imat), int(pad_frames), start, int(length), _dptr(out), _dptr(ws),
+                                              nbytes, self._stream(spec))
+            self.lib.check(rc)
+            self.launches += 2
+            return out
         rc = self.lib.b2a_istft_f32(_dptr(torch.view_as_real(spec)), B * C, N, int(n_fft), int(hop), _dptr(window),
                                     int(pad_frames), start, int(length), _dptr(out), self._stream(spec))
         self.lib.check(rc)
         self.launches += 1
         return out
+
+    # ------------------------------------------------------------------ dense DFT (any window length)
+    @staticmethod
+    def fft_window_length(n_fft: int) -> bool:
+        """Window lengths the fused FFT kernel (csrc/spectral.cu) covers: powers of two in [32, 4096]."""
+        return 32 <= n_fft <= 4096 and (n_fft & (n_fft - 1)) == 0
+
+    def dft_matrix(self, window: torch.Tensor, n_fft: int, inverse: bool = False) -> torch.Tensor:
+        """The windowed DFT matrix of csrc/dft.cu for (n_fft, window), built on the device once and cached (the cache
+        entry holds the window tensor, so its address / version identify it)."""
+        key = ("dft", window.data_ptr(), int(window._version), int(n_fft), bool(inverse))
+        hit = self._packed_cache.get(key)
+        if hit is None:
+            n = int(self.lib.b2a_dft_matrix_floats(int(n_fft), int(inverse)))
+            if n == 0:
+                raise NotImplementedError(f"window_length {n_fft}: the dense DFT path covers 2..8192")
+            mat = torch.empty(n, dtype=torch.float32, device=window.device)
+            self.lib.check(self.lib.b2a_dft_matrix_f32(_dptr(window), int(n_fft), int(inverse), _dptr(mat),
+                                                       self._stream(window)))
+            self.launches += 1
+            hit = self._packed_cache[key] = (mat, window)
+        return hit[0]
 
     # ------------------------------------------------------------------ spectral masks
     def spec_band_mask(self, spec: torch.Tensor, axis_vals: torch.Tensor, lo: torch.Tensor, hi: torch.Tensor,
@@ -381,7 +414,7 @@ class Engine:
         a foreign-function call per ``stft()`` is measurable at batch=4 x 1 s, where the call is launch-latency bound."""
         if T < 1 or n_fft < 2 or hop < 1 or pad < 0 or right_pad < 0 or drop_edge < 0:
             return -1
-        return 1 + (T + 2 * pad + right_pad) // hop - 2 * drop_edge
+        return 1 + (T + 2 * pad + right_pad - (n_fft & 1)) // hop - 2 * drop_edge
 
     def spectral(self, x: torch.Tensor, n_fft: int, hop: int, window: torch.Tensor, pad: int = 0,
                  right_pad: int = 0, pad_mode: str = "reflect", drop_edge: int = 0,
@@ -406,6 +439,9 @@ class Engine:
             raise _lib.B2AError(f"stft: no frames (T={T}, n_fft={n_fft}, hop={hop})")
         F = n_fft // 2 + 1
         dev = x.device
+        if not self.fft_window_length(int(n_fft)):
+            return self._spectral_dense(x, int(n_fft), int(hop), window, pad, right_pad, pad_mode, drop_edge, gain,
+                                        want_scaled, mel_fb, mel_lo, mel_hi, post, post_eps, post_power, want_stft, N)
         stft = torch.empty(B, C, F, N, dtype=torch.complex64, device=dev) if want_stft else None
         mel = None
         n_mels = 0
@@ -436,6 +472,41 @@ class Engine:
         self.launches += 1
         return {"stft": stft, "mel": mel, "scaled": scaled}
 
+
+    def _spectral_dense(self, x, n_fft, hop, window, pad, right_pad, pad_mode, drop_edge, gain, want_scaled, mel_fb,
+                        mel_lo, mel_hi, post, post_eps, post_power, want_stft, N):
+        """``spectral`` for window lengths outside the FFT kernel's set: gain pass (if any) -> dense DFT of all frames
+        (one matrix product, csrc/dft.cu) -> optional |X| -> banded mel -> post-op from the materialised STFT."""
+        B, C, T = x.shape
+        F = n_fft // 2 + 1
+        if not self.lib.b2a_dft_supported(n_fft, hop):
+            raise NotImplementedError(f"stft: window_length {n_fft} hop {hop}")
+        scaled = None
+        if gain is not None:
+            gain = self._prep(gain.reshape(-1), "gain")
+            assert gain.numel() == B
+            x = scaled = self.gain(x, gain)
+        mat = self.dft_matrix(window, n_fft, inverse=False)
+        stft = torch.empty(B, C, F, N, dtype=torch.complex64, device=x.device)
+        rc = self.lib.b2a_stft_dense_f32(_dptr(x), B * C, T, n_fft, hop, _dptr(mat), pad, right_pad,
+                                         _lib.PAD_MODES[pad_mode], drop_edge, _dptr(torch.view_as_real(stft)),
+                                         self._stream(x))
+        self.lib.check(rc)
+        self.launches += 1
+        mel = None
+        if mel_fb is not None:
+            mel_fb = self._prep(mel_fb, "mel_fb")
+            assert mel_fb.shape[1] == F, (mel_fb.shape, F)
+            n_mels = mel_fb.shape[0]
+            mel_lo = self._prep(mel_lo, "mel_lo", torch.int32)
+            mel_hi = self._prep(mel_hi, "mel_hi", torch.int32)
+            mel = torch.empty(B, C, n_mels, N, dtype=torch.float32, device=x.device)
+            rc = self.lib.b2a_mel_from_stft_f32(_dptr(torch.view_as_real(stft)), B * C, F, N, _dptr(mel_fb), _dptr(mel_lo),
+                                                _dptr(mel_hi), n_mels, post, float(post_eps), float(post_power), _dptr(mel),
+                                                self._stream(x))
+            self.lib.check(rc)
+            self.launches += 1
+        return {"stft": stft if want_stft else None, "mel": mel, "scaled": scaled if want_scaled else None}
 
     # ------------------------------------------------------------------ FIR / convolution
     def fftconv(self, x: torch.Tensor, taps: torch.Tensor, rows_per_filt: int, offset: Optional[torch.Tensor] = None,

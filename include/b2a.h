@@ -53,7 +53,7 @@ const char* b2a_last_error(void);
  *
  *   x        [rows, T]
  *   window   [n_fft]              (AudioSignal.get_window, :1009-1039)
- *   n_fft    power of two in [64, 4096]; hop >= 1
+ *   n_fft    power of two in [32, 4096] (any other window length: b2a_stft_dense_f32 below); hop >= 1
  *   pad/right_pad/pad_mode        compute_stft_padding (:1089-1121); 0/0 when !match_stride
  *   drop_edge                     frames dropped at each end (2 when match_stride, else 0)
  *   gain     nullable [rows/rows_per_gain]: x is multiplied by gain[row / rows_per_gain] first
@@ -65,8 +65,8 @@ const char* b2a_last_error(void);
  *            dense matmul exactly for ANY matrix).
  *   mel_packed_len  floats of the kernel's shared-memory band table (0: read the weights from global):
  *            with n4[m] = (ceil4(mel_hi[m]) - floor4(mel_lo[m]))/4, 4 * sum over filters m of
- *            even(max(n4[m'] : m' in {w + 8*(4i + j), j < 4})) where w = m % 8, i = m / 32, even(v) = (v+1) & ~1
- *            (the filters one warp projects in one step share a trip count; the loop is unrolled by two).
+ *            even(max(n4[m'] : m' in {4g .. 4g + 3})) where g = m / 4, even(v) = (v+1) & ~1
+ *            (the 4 consecutive filters one warp projects in one step share a trip count; the loop is unrolled by two).
  *   mel_out  nullable [rows, n_mels, n_frames]    stft_out  nullable [rows, F, n_frames] (re,im)
  *   n_frames = 1 + (T + 2*pad + right_pad)/hop - 2*drop_edge,  F = n_fft/2 + 1
  */
@@ -91,6 +91,33 @@ int b2a_spectral_f32(const float* x, int64_t rows, int64_t T, int n_fft, int hop
 int b2a_istft_supported(int n_fft, int hop);
 int b2a_istft_f32(const float* spec, int64_t rows, int64_t n_frames, int n_fft, int hop, const float* window,
                   int pad_frames, int64_t start, int64_t out_len, float* out, void* stream);
+
+/* ---- STFT / inverse STFT for ANY window length (dense DFT, csrc/dft.cu) ---------------------------------------
+ * AudioSignal.stft / istft accept any window_length (audiotools/core/audio_signal.py:1123-1212, 1214-1296 -> torch.stft /
+ * torch.istft), e.g. 400 / 480 / 1200-sample speech windows; b2a_spectral_f32 / b2a_istft_f32 cover the powers of two.
+ * Everything else is ONE real x complex matrix product over all frames of the batch (FP32, packed FFMA2):
+ *   b2a_dft_matrix_f32     builds the matrix of (n_fft, window) once: inverse 0 -> M[n][k] = w[n] exp(-2 pi i nk/n_fft)
+ *                          for b2a_stft_dense_f32, inverse 1 -> c_k/n_fft . w[n] exp(-2 pi i nk/n_fft) (c = 1 for DC and
+ *                          Nyquist, else 2) for b2a_istft_dense_f32; `matrix`: b2a_dft_matrix_floats(n_fft, inverse)
+ *                          floats, 16-byte aligned; angles reduced in integers (nk mod n_fft), evaluated in float64
+ *   b2a_stft_dense_f32     the arguments of b2a_spectral_f32 (same framing / padding semantics, bit-exact frame
+ *                          indexing) -> stft_out [rows, n_fft/2+1, n_frames] (re,im)
+ *   b2a_mel_from_stft_f32  |X| -> banded mel -> post-op from a materialised STFT (AudioSignal.mel_spectrogram :1333-1369
+ *                          for these window lengths; the FFT kernel fuses it)
+ *   b2a_istft_dense_f32    the arguments of b2a_istft_f32 + the inverse matrix + ws (b2a_istft_dense_workspace_bytes:
+ *                          the windowed frames) -> out; also serves n_fft 32 and 4096, which istft.cu does not. */
+int b2a_dft_supported(int n_fft, int hop);
+size_t b2a_dft_matrix_floats(int n_fft, int inverse);
+int b2a_dft_matrix_f32(const float* window, int n_fft, int inverse, float* matrix, void* stream);
+int b2a_stft_dense_f32(const float* x, int64_t rows, int64_t T, int n_fft, int hop, const float* matrix,
+                       int pad, int right_pad, int pad_mode, int drop_edge, float* stft_out, void* stream);
+int b2a_mel_from_stft_f32(const float* stft, int64_t rows, int F, int64_t n_frames, const float* mel_fb,
+                          const int32_t* mel_lo, const int32_t* mel_hi, int n_mels, int post, float post_eps,
+                          float post_power, float* mel_out, void* stream);
+size_t b2a_istft_dense_workspace_bytes(int64_t rows, int64_t n_frames, int n_fft);
+int b2a_istft_dense_f32(const float* spec, int64_t rows, int64_t n_frames, int n_fft, int hop, const float* window,
+                        const float* imatrix, int pad_frames, int64_t start, int64_t out_len, float* out, void* ws,
+                        size_t ws_bytes, void* stream);
 
 /* ---- SpecAugment band masks on a complex STFT, in place -------------------------------------------------
  * DSPMixin.mask_frequencies / mask_timesteps (audiotools/core/dsp.py:217-306): cells whose axis value v satisfies

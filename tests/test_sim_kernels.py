@@ -165,6 +165,40 @@ def test_istft_random_geometries(eng):
 
 
 # ------------------------------------------------------------------------------------------
+# dense DFT path (csrc/dft.cu): any window length, forward (+ mel from the materialised STFT) and inverse
+# ------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("n_fft,hop,T,pad_mode", [(400, 160, 3000, "reflect"), (96, 31, 1000, "constant"),
+                                                  (201, 50, 1500, "replicate"), (30, 7, 400, "reflect")])
+def test_dense_dft_any_window_length(eng, n_fft, hop, T, pad_mode):
+    g = torch.Generator().manual_seed(n_fft)
+    x = torch.randn(2, 2, T, generator=g)
+    w = torch.hann_window(n_fft) + 0.05 + 0.1 * torch.rand(n_fft, generator=g)
+    out = eng.spectral(x, n_fft, hop, w, pad_mode=pad_mode)
+    ref = torch.stft(x.reshape(4, T), n_fft, hop, window=w, center=True, return_complex=True).reshape(2, 2, n_fft // 2 + 1, -1)
+    assert out["stft"].shape == ref.shape  # frame indexing exact
+    assert rel_err(torch.view_as_real(out["stft"]), torch.view_as_real(ref)) < 2e-6
+    # match_stride-style call: explicit F.pad + dropped edge frames, resolved per sample inside the kernel
+    pad, right_pad = (n_fft - hop) // 2, (-T) % hop
+    xp = torch.nn.functional.pad(x, (pad, pad + right_pad), pad_mode)
+    ref2 = torch.stft(xp.reshape(4, -1), n_fft, hop, window=w, center=True, return_complex=True)[..., 2:-2]
+    out2 = eng.spectral(x, n_fft, hop, w, pad=pad, right_pad=right_pad, pad_mode=pad_mode, drop_edge=2)["stft"]
+    assert out2.shape[-1] == ref2.shape[-1] and rel_err(torch.view_as_real(out2.reshape(4, *ref2.shape[1:])), torch.view_as_real(ref2)) < 2e-6
+    # mel from the materialised STFT, with a gain riding along
+    fb, lo, hi = _mel_tables(16000, n_fft, 20)
+    gain = torch.tensor([0.5, 2.0])
+    m = eng.spectral(x, n_fft, hop, w, pad_mode=pad_mode, gain=gain, want_scaled=True, mel_fb=fb, mel_lo=lo, mel_hi=hi,
+                     post=_lib.POST_LOG10, post_eps=1e-5, post_power=2.0, want_stft=False)
+    assert m["stft"] is None and torch.equal(m["scaled"], x * gain[:, None, None])
+    mel_ref = torch.log10(((ref.abs() * gain[:, None, None, None]).transpose(2, 3) @ fb.T).transpose(2, 3).clamp(1e-5) ** 2)
+    assert (m["mel"] - mel_ref).abs().max() < 1e-4
+    # inverse: dense transposed product + fold
+    length = T
+    y = eng.istft(out["stft"], n_fft, hop, w, length)
+    y_ref = torch.istft(ref.reshape(4, *ref.shape[2:]), n_fft, hop, window=w, center=True, length=length).reshape(2, 2, -1)
+    assert y.shape == y_ref.shape and rel_err(y, y_ref) < 5e-5
+
+
+# ------------------------------------------------------------------------------------------
 # FIR / convolution / resample / pitch (csrc/fftconv.cu, resample.cu, pitch.cu)
 # ------------------------------------------------------------------------------------------
 def test_sinc_filters_and_equalizer_golden(eng, golden):

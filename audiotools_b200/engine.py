@@ -207,6 +207,35 @@ class Engine:
         self.launches += 2
         return spec
 
+    def spec_gate(self, spec: torch.Tensor, nz_spec: torch.Tensor, n_std: float, amount: torch.Tensor,
+                  smooth_f, smooth_t) -> torch.Tensor:
+        """The spectral noise gate's mask algebra (ref:audiotools/ml/layers/spectral_gate.py:97-124) as two launches:
+        per-bin threshold from the noise STFT's dB statistics, then boolean -> separable 2-D smoothing ->
+        ``spec * (1 - amount * mask)`` in one pass.  spec [B, C, F, N], nz_spec [1 or B, 1 or C, F, Nz] complex64;
+        amount: scalar or [B]; smooth_f / smooth_t: the two 1-D factors of the smoothing kernel.  Returns a new tensor."""
+        spec = self._spec_ok(spec, "spec_gate")
+        B, C, F, N = spec.shape
+        nz_spec = self._spec_ok(nz_spec, "spec_gate")
+        if nz_spec.shape[:2] != (1, 1):
+            nz_spec = nz_spec.expand(B, C, -1, -1).contiguous()
+        assert nz_spec.shape[2] == F, (nz_spec.shape, F)
+        nz_rows = nz_spec.shape[0] * nz_spec.shape[1]
+        amount = torch.as_tensor(amount, dtype=torch.float32).reshape(-1).to(spec.device)
+        if amount.numel() == 1:
+            amount = amount.expand(B)
+        amount = self._prep(amount.contiguous(), "amount")
+        assert amount.numel() == B
+        sf = (ctypes.c_float * len(smooth_f))(*[float(v) for v in smooth_f])
+        st = (ctypes.c_float * len(smooth_t))(*[float(v) for v in smooth_t])
+        out = torch.empty_like(spec)
+        ws = torch.empty(nz_rows * F, dtype=torch.float32, device=spec.device)
+        rc = self.lib.b2a_spec_gate_f32(_dptr(torch.view_as_real(spec)), B * C, F, N, _dptr(torch.view_as_real(nz_spec)),
+                                        nz_rows, nz_spec.shape[-1], float(n_std), _dptr(amount), C, sf, len(smooth_f),
+                                        st, len(smooth_t), _dptr(torch.view_as_real(out)), _dptr(ws), self._stream(spec))
+        self.lib.check(rc)
+        self.launches += 2
+        return out
+
     # ------------------------------------------------------------------ loudness
     def lufs(self, x: torch.Tensor, sample_rate: float, filter_class: str = "K-weighting",
              block_size: float = 0.400, padded_length: Optional[int] = None,

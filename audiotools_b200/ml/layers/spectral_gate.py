@@ -1,7 +1,8 @@
 """Spectral noise gate (ref:audiotools/ml/layers/spectral_gate.py:10-127; after noisereduce / Audacity's noise
 reduction): a per-bin threshold from a noise excerpt's STFT statistics, a smoothed binary mask, applied to the
-signal's STFT.  Both STFTs and the inverse run on the engine (``csrc/spectral.cu``, ``csrc/istft.cu``); the mask
-algebra in between is tensor arithmetic on the device."""
+signal's STFT.  Both STFTs and the inverse run on the engine (``csrc/spectral.cu``, ``csrc/istft.cu``), and so does the
+mask algebra in between (``csrc/specmask.cu``: threshold statistics, then boolean -> separable smoothing -> multiply in
+one pass); ``smoothing_filter`` is kept as a buffer for API compatibility."""
 import torch
 from torch import nn
 
@@ -20,7 +21,8 @@ def _ramp(n: int) -> torch.Tensor:
 class SpectralGate(nn.Module):
     def __init__(self, n_freq: int = 3, n_time: int = 5):
         super().__init__()
-        kernel = torch.outer(_ramp(n_freq), _ramp(n_time))
+        self._rf, self._rt = _ramp(n_freq), _ramp(n_time)  # the smoothing kernel is their outer product / sum: separable
+        kernel = torch.outer(self._rf, self._rt)
         self.register_buffer("smoothing_filter", (kernel / kernel.sum())[None, None])
 
     def forward(self, audio_signal: AudioSignal, nz_signal: AudioSignal, denoise_amount: float = 1.0,
@@ -32,15 +34,12 @@ class SpectralGate(nn.Module):
         nz_signal = nz_signal.clone()
         nz_signal.stft_params = stft_params
 
-        nz_db = 20 * nz_signal.magnitude.clamp(1e-4).log10()
-        thresh = nz_db.mean(keepdim=True, dim=-1) + nz_db.std(keepdim=True, dim=-1) * n_std  # per bin
-        sig_db = 20 * audio_signal.magnitude.clamp(1e-4).log10()
-        nb, nac, nf, nt = sig_db.shape
-        mask = (sig_db < thresh.expand(nb, nac, -1, nt)).float()
-        kf, kt = self.smoothing_filter.shape[-2:]
-        mask = torch.nn.functional.conv2d(mask.reshape(nb * nac, 1, nf, nt), self.smoothing_filter.to(mask.device),
-                                          padding=(kf // 2, kt // 2)).reshape(nb, nac, nf, nt)
-        mask = 1 - mask * util.ensure_tensor(denoise_amount, ndim=mask.ndim).to(mask.device)
-        audio_signal.stft_data = audio_signal.stft_data * mask
+        from ...engine import get_engine
+
+        audio_signal.stft()
+        nz_signal.stft()
+        amount = util.ensure_tensor(denoise_amount).reshape(-1)
+        audio_signal.stft_data = get_engine().spec_gate(audio_signal.stft_data, nz_signal.stft_data, float(n_std), amount,
+                                                        self._rf.tolist(), self._rt.tolist())
         audio_signal.istft()
         return audio_signal

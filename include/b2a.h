@@ -136,6 +136,16 @@ int b2a_spec_rotate_f32(float* spec, int64_t items, int64_t cells_per_item, cons
 int b2a_spec_mask_low_f32(float* spec, int64_t items, int64_t cells_per_item, const float* db_cutoff, float amin_sq,
                           float top_db, float val, void* ws, void* stream);
 
+/* Spectral noise gate (audiotools/ml/layers/spectral_gate.py:60-129, transforms.SpectralDenoising): per-bin threshold
+ * mean_t + n_std * std_t of the noise STFT's dB magnitudes (20 log10 max(|X|, 1e-4)); boolean (signal dB < threshold),
+ * smoothed by the zero-padded separable kernel smooth_f (x) smooth_t / sum (the reference's conv2d with the outer
+ * product of two triangles); out = spec * (1 - amount[item] * smoothed).  spec / out [rows, F, N] complex64 (out must
+ * not alias spec), nz_spec [nz_rows, F, nz_N] with nz_rows 1 or rows, amount [rows / rows_per_item] device,
+ * smooth_f_h / smooth_t_h HOST vectors of odd length <= 17, ws >= nz_rows * F floats. */
+int b2a_spec_gate_f32(const float* spec, int64_t rows, int F, int64_t N, const float* nz_spec, int64_t nz_rows,
+                      int64_t nz_N, float n_std, const float* amount, int rows_per_item, const float* smooth_f_h,
+                      int n_f, const float* smooth_t_h, int n_t, float* out, void* ws, void* stream);
+
 /* ---- integrated loudness (ITU-R BS.1770 / LUFS) ----------------------------------------
  * Replaces Meter.integrated_loudness with the IIR semantics of apply_filter_cpu
  * (audiotools/core/loudness.py:102-126, 164-247) and the pad / clamp shell of

@@ -54,7 +54,7 @@ def test_stft_any_window_length_vs_oracle(at, sp, sr, n_fft, hop, wtype, T):
     assert y.shape == x.shape
     y_ref = sp.istft(ref, sr, T, n_fft, hop, wtype)
     assert rel_err(y.cpu(), y_ref) < TOL
-    if wtype in ("hann", "sqrt_hann", "hamming"):  # COLA windows: the round trip gives the signal back
+    if wtype in ("hann", "sqrt_hann", "hamming") and T > 3 * n_fft:  # COLA windows: the round trip gives the signal back
         assert rel_err(y.cpu()[..., n_fft: -n_fft], x[..., n_fft: -n_fft]) < 1e-4
 
 

@@ -71,6 +71,7 @@ SIGNATURES = {
     "b2a_time_stretch_f32": (c_int, [c_void_p, c_int64, c_int64, c_int, c_double, c_void_p, c_void_p, c_size_t, c_void_p]),
     "b2a_spec_gate_f32": (c_int, [c_void_p, c_int64, c_int, c_int64, c_void_p, c_int64, c_int64, c_float, c_void_p, c_int,
                                   POINTER(c_float), c_int, POINTER(c_float), c_int, c_void_p, c_void_p, c_void_p]),
+    "b2a_alter_drr_f32": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_int, c_int, c_void_p, c_float, c_void_p]),
     "b2a_dft_supported": (c_int, [c_int, c_int]),
     "b2a_dft_matrix_floats": (c_size_t, [c_int, c_int]),
     "b2a_dft_matrix_f32": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p]),

@@ -229,6 +229,10 @@ class ImpulseResponseMixin:
         return torch.maximum((-b - expr) / (2 * a), (-b + expr) / (2 * a))
 
     def alter_drr(self, drr):
+        if _on_engine(self._audio_data):  # one fused launch (csrc/effects.cu) instead of ~25 tensor passes
+            self.audio_data = _engine().alter_drr(self._materialized(), self.sample_rate,
+                                                  util.ensure_tensor(drr, 2, self.batch_size))
+            return self
         drr = util.ensure_tensor(drr, 2, self.batch_size).to(self.device)
         early, late, window = self.decompose_ir()
         alpha = self.solve_alpha(early, late, window, drr)

@@ -199,6 +199,104 @@ static unsigned grid_x(int64_t work, int64_t rows) {
 }
 
 }  // namespace effects
+
+namespace effects {
+// ---------------------------------------------------------------------------------------------
+// ImpulseResponseMixin.alter_drr (ref:audiotools/core/effects.py:540-647), one CTA per impulse-response row, one launch:
+//   td = argmax(x), early = [td - t0, td + t0], window = the early region of the item's CHANNEL 0 (hann(1) == 1, so the
+//   reference's window is that indicator), alpha from the quadratic of solve_alpha (:594-617, float32 like the
+//   reference; with an indicator window b == 0), floored at max|late| / max|early|, out = alpha on (early AND window),
+//   x elsewhere, then ensure_max_of_audio (:181-198).  The reference runs ~25 tensor passes for this.
+// ---------------------------------------------------------------------------------------------
+constexpr int DRR_T = 512;
+
+struct ArgMax { float v; int i; };
+__device__ __forceinline__ ArgMax better(ArgMax a, ArgMax b) {  // larger value, then the smaller index
+  return (b.v > a.v || (b.v == a.v && b.i < a.i)) ? b : a;
+}
+__device__ ArgMax block_argmax(const float* __restrict__ x, int T, ArgMax* sm) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  ArgMax m{-INFINITY, 0x7fffffff};
+  for (int i = tid; i < T; i += DRR_T) { const float v = x[i]; if (v > m.v) { m.v = v; m.i = i; } }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    ArgMax t{__shfl_xor_sync(0xffffffffu, m.v, o), __shfl_xor_sync(0xffffffffu, m.i, o)};
+    m = better(m, t);
+  }
+  __syncthreads();
+  if (lane == 0) sm[warp] = m;
+  __syncthreads();
+  ArgMax r = sm[0];
+  for (int w = 1; w < DRR_T / 32; ++w) r = better(r, sm[w]);
+  if (r.i == 0x7fffffff) r.i = 0;
+  return r;
+}
+__device__ float block_sum_f(float v, float* sm) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  v = warp_sum(v);
+  __syncthreads();
+  if (lane == 0) sm[warp] = v;
+  __syncthreads();
+  float r = 0.f;
+  for (int w = 0; w < DRR_T / 32; ++w) r += sm[w];
+  return r;
+}
+__device__ float block_max_f(float v, float* sm) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  v = warp_max(v);
+  __syncthreads();
+  if (lane == 0) sm[warp] = v;
+  __syncthreads();
+  float r = sm[0];
+  for (int w = 1; w < DRR_T / 32; ++w) r = fmaxf(r, sm[w]);
+  return r;
+}
+
+__global__ void __launch_bounds__(DRR_T)
+alter_drr_kernel(const float* __restrict__ x, float* __restrict__ out, int T, int C, int t0, const float* __restrict__ drr,
+                 float max_abs) {
+  __shared__ ArgMax s_am[DRR_T / 32];
+  __shared__ float s_f[DRR_T / 32];
+  const int row = blockIdx.x, item = row / C, tid = threadIdx.x;
+  const float* xr = x + (size_t)row * T;
+  const float* x0 = x + (size_t)item * C * T;  // channel 0 of the item: its early region is the window
+  const int td = block_argmax(xr, T, s_am).i;
+  const int tw = (C == 1 || row == item * C) ? td : block_argmax(x0, T, s_am).i;
+  float a = 0.f, ce = 0.f, lsq = 0.f, ml = 0.f, me = 0.f, mew = 0.f, meo = 0.f;
+  for (int i = tid; i < T; i += DRR_T) {
+    const float v = xr[i], av = fabsf(v);
+    const bool e = (i >= td - t0) && (i <= td + t0), w = (i >= tw - t0) && (i <= tw + t0);
+    if (e) {
+      me = fmaxf(me, av);
+      if (w) { a = fmaf(v, v, a); mew = fmaxf(mew, av); }
+      else { ce = fmaf(v, v, ce); meo = fmaxf(meo, av); }
+    } else {
+      lsq = fmaf(v, v, lsq);
+      ml = fmaxf(ml, av);
+    }
+  }
+  a = block_sum_f(a, s_f); ce = block_sum_f(ce, s_f); lsq = block_sum_f(lsq, s_f);
+  ml = block_max_f(ml, s_f); me = block_max_f(me, s_f); mew = block_max_f(mew, s_f); meo = block_max_f(meo, s_f);
+  // solve_alpha with an indicator window: b = 0, c = sum_{early, outside the window} x^2 - 10^(drr/10) sum_late x^2
+  const float c = ce - powf(10.0f, __ldg(drr + item) / 10.0f) * lsq;
+  const float b = 0.f;
+  const float expr = sqrtf(b * b - 4.0f * a * c);
+  const float r1 = (-b - expr) / (2.0f * a), r2 = (-b + expr) / (2.0f * a);
+  float alpha = (r1 != r1 || r2 != r2) ? NAN : fmaxf(r1, r2);  // torch.maximum propagates nan
+  const float min_alpha = ml / me;
+  alpha = (alpha != alpha || min_alpha != min_alpha) ? NAN : fmaxf(alpha, min_alpha);
+  // ensure_max_of_audio on the altered response
+  const float peak = fmaxf(fmaxf(fabsf(alpha) * mew, meo), ml);
+  const float pg = (peak > max_abs) ? max_abs / peak : 1.0f;
+  float* o = out + (size_t)row * T;
+  for (int i = tid; i < T; i += DRR_T) {
+    float v = xr[i];
+    if ((i >= td - t0) && (i <= td + t0) && (i >= tw - t0) && (i <= tw + t0)) v = alpha * v;
+    o[i] = v * pg;
+  }
+}
+
+}  // namespace effects
 }  // namespace b2a
 
 using namespace b2a::effects;
@@ -261,6 +359,17 @@ extern "C" int b2a_order_stats_f32(const float* row, int64_t T, const int64_t* k
   B2A_REQUIRE(row && k && out, B2A_E_INVALID, "order_stats: null pointer");
   B2A_REQUIRE(T >= 1 && nk >= 1 && nk <= 65535, B2A_E_INVALID, "order_stats: bad shape");
   B2A_LAUNCH(order_stat_kernel, dim3((unsigned)nk), dim3(ST), 0, stream, row, T, k, out);
+  B2A_CUDA_OK(cudaGetLastError());
+  return B2A_OK;
+}
+
+extern "C" int b2a_alter_drr_f32(const float* ir, float* out, int64_t rows, int64_t T, int C, int t0, const float* drr,
+                                 float max_abs, void* stream) {
+  B2A_REQUIRE(ir && out && drr, B2A_E_INVALID, "alter_drr: null pointer");
+  B2A_REQUIRE(rows >= 1 && T >= 1 && T < ((int64_t)1 << 31) && C >= 1 && rows % C == 0 && t0 >= 0, B2A_E_INVALID,
+              "alter_drr: bad shape");
+  B2A_REQUIRE(out != ir, B2A_E_INVALID, "alter_drr: out must not alias ir");
+  B2A_LAUNCH(alter_drr_kernel, dim3((unsigned)rows), dim3(DRR_T), 0, stream, ir, out, (int)T, C, t0, drr, max_abs);
   B2A_CUDA_OK(cudaGetLastError());
   return B2A_OK;
 }

@@ -207,6 +207,23 @@ class Engine:
         self.launches += 2
         return spec
 
+    def alter_drr(self, ir: torch.Tensor, sample_rate: int, drr: torch.Tensor) -> torch.Tensor:
+        """``ImpulseResponseMixin.alter_drr`` (ref:audiotools/core/effects.py:540-647) for ir [B, C, T] and drr [B]:
+        early / late split at the direct path, alpha from the DRR quadratic, re-weighting and the peak limit in one
+        launch (csrc/effects.cu)."""
+        ir = self._prep(ir, "ir")
+        B, C, T = ir.shape
+        drr = self._prep(drr.to(ir.device).float().reshape(-1), "drr")
+        if drr.numel() == 1:
+            drr = drr.expand(B).contiguous()
+        assert drr.numel() == B
+        out = torch.empty_like(ir)
+        rc = self.lib.b2a_alter_drr_f32(_dptr(ir), _dptr(out), B * C, T, C, int(sample_rate * 0.0025), _dptr(drr), 1.0,
+                                        self._stream(ir))
+        self.lib.check(rc)
+        self.launches += 1
+        return out
+
     def spec_gate(self, spec: torch.Tensor, nz_spec: torch.Tensor, n_std: float, amount: torch.Tensor,
                   smooth_f, smooth_t) -> torch.Tensor:
         """The spectral noise gate's mask algebra (ref:audiotools/ml/layers/spectral_gate.py:97-124) as two launches:

@@ -267,6 +267,12 @@ int b2a_quantize_f32(const float* x, float* out, int64_t B, int64_t per_item, co
                      void* stream);
 int b2a_order_stats_f32(const float* row, int64_t T, const int64_t* k, int nk, float* out, void* stream);
 
+/* ImpulseResponseMixin.alter_drr (audiotools/core/effects.py:540-647: decompose_ir + solve_alpha + the re-weighted sum +
+ * ensure_max_of_audio) in ONE launch, one CTA per impulse-response row.  ir / out [rows = B*C, T] (out must not alias
+ * ir), t0 = int(sample_rate * 0.0025), drr [B] target direct-to-reverberant ratios in dB, max_abs = 1. */
+int b2a_alter_drr_f32(const float* ir, float* out, int64_t rows, int64_t T, int C, int t0, const float* drr,
+                      float max_abs, void* stream);
+
 /* ---- ragged signals -> one padded / truncated batch (csrc/collate.cu; AudioSignal.batch, audiotools/core/audio_signal.py:
  * 380-470, called by util.collate, core/util.py:426-479; excerpt gathering of salient_excerpt, audio_signal.py:227-286)
  * item i = C rows of src_len[i] samples at src_ptrs[i], consecutive rows src_stride[i] samples apart;

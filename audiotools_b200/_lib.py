@@ -35,7 +35,7 @@ SIGNATURES = {
     "b2a_gain_f32": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_void_p, c_void_p]),
     "b2a_fftconv_workspace_bytes": (c_size_t, [c_int64, c_int64, c_int64, c_int64]),
     "b2a_fftconv_f32": (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_int64, c_int64, c_int, c_void_p, c_int,
-                                c_int, c_void_p, c_int, c_void_p, c_void_p, c_size_t, c_void_p]),
+                                c_int, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     "b2a_resample_out_len": (c_int64, [c_int64, c_int, c_int]),
     "b2a_resample_f32": (c_int, [c_void_p, c_int64, c_int64, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "b2a_pitch_shift_workspace_bytes": (c_size_t, [c_int64, c_int64, c_int, c_float]),
@@ -87,9 +87,9 @@ SIGNATURES = {
                               c_void_p]),
     "b2a_fir_direct_supported": (c_int, [c_int64, c_int, c_int]),
     "b2a_fir_direct_f32": (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_int64, c_int, c_int, c_void_p, c_int, c_int,
-                                   c_int64, c_int, c_int, c_void_p, c_void_p]),
+                                   c_int64, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "b2a_circconv_workspace_bytes": (c_size_t, [c_int64, c_int64, c_int64, c_int64]),
-    "b2a_circconv_f32": (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_int64, c_int64, c_int, c_int, c_void_p,
+    "b2a_circconv_f32": (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_int64, c_int64, c_int, c_int, c_void_p, c_void_p,
                                  c_void_p, c_size_t, c_void_p]),
 }
 

@@ -75,19 +75,20 @@ class DSPMixin:
         self.trim(hop_length, hop_length)
         return self
 
-    def low_pass(self, cutoffs, zeros: int = 51):
-        """Low-pass each item at its own cutoff (Hz)."""
-        cutoffs = util.ensure_tensor(cutoffs, 2, self.batch_size)
+    def low_pass(self, cutoffs, zeros: int = 51, _bypass=None):
+        """Low-pass each item at its own cutoff (Hz).  ``_bypass`` [B] (bool): items left untouched (how a transform
+        applies itself to the items its mask selects without gathering / scattering the batch)."""
+        cutoffs = util.ensure_tensor(util.host_view(cutoffs), 2, self.batch_size)  # host mirror first: no sync
         self.audio_data = _engine().sinc_filter(self._materialized(), cutoffs[:, 0], self.sample_rate, zeros,
-                                                highpass=False)
+                                                highpass=False, bypass=_bypass)
         self.stft_data = None
         return self
 
-    def high_pass(self, cutoffs, zeros: int = 51):
+    def high_pass(self, cutoffs, zeros: int = 51, _bypass=None):
         """High-pass each item at its own cutoff (Hz): ``x - low_pass(x)``."""
-        cutoffs = util.ensure_tensor(cutoffs, 2, self.batch_size)
+        cutoffs = util.ensure_tensor(util.host_view(cutoffs), 2, self.batch_size)
         self.audio_data = _engine().sinc_filter(self._materialized(), cutoffs[:, 0], self.sample_rate, zeros,
-                                                highpass=True)
+                                                highpass=True, bypass=_bypass)
         self.stft_data = None
         return self
 

@@ -42,18 +42,19 @@ class EffectMixin:
             self.audio_data = self.audio_data + other.audio_data
         return self
 
-    def convolve(self, other, start_at_max: bool = True):
+    def convolve(self, other, start_at_max: bool = True, _bypass=None):
         """CIRCULAR convolution with ``other`` (period = signal length), the IR rolled so that its
-        peak sits at t=0 and scaled by 1/max|IR| (ref :66-123)."""
+        peak sits at t=0 and scaled by 1/max|IR| (ref :66-123).  ``_bypass`` [B]: items left untouched."""
         self.audio_data = _engine().circular_convolve(self._materialized(), other.audio_data,
-                                                      roll_to_peak=start_at_max)
+                                                      roll_to_peak=start_at_max, bypass=_bypass)
         return self
 
     def __matmul__(self, other):
         return self.convolve(other)
 
-    def apply_ir(self, ir, drr=None, ir_eq=None, use_original_phase: bool = False):
-        """Equalise / DRR-alter the impulse response, convolve, restore the input's peak (ref :125-179)."""
+    def apply_ir(self, ir, drr=None, ir_eq=None, use_original_phase: bool = False, _bypass=None):
+        """Equalise / DRR-alter the impulse response, convolve, restore the input's peak (ref :125-179).
+        ``_bypass`` [B] (bool, device): items left untouched (mask-aware transforms)."""
         if ir_eq is not None:
             ir = ir.equalizer(ir_eq)
         if drr is not None:
@@ -62,7 +63,7 @@ class EffectMixin:
         max_spk = _engine().row_absmax(self._materialized()) if cuda else \
             self.audio_data.abs().max(dim=-1, keepdims=True).values
         phase = self.phase if use_original_phase else None
-        self.convolve(ir)
+        self.convolve(ir, _bypass=_bypass)
         if use_original_phase:
             self.stft()
             self.stft_data = self.magnitude * torch.exp(1j * phase)
@@ -70,6 +71,9 @@ class EffectMixin:
         max_transformed = _engine().row_absmax(self._materialized()) if cuda else \
             self.audio_data.abs().max(dim=-1, keepdims=True).values
         scale = max_spk.clamp(1e-8) / max_transformed.clamp(1e-8)
+        if _bypass is not None:
+            byp = torch.as_tensor(_bypass).to(scale.device).bool().reshape(-1, 1, 1)
+            scale = torch.where(byp, torch.ones_like(scale), scale)
         if cuda:  # per-row scale: the gain kernel with one "item" per (batch, channel) row
             x = self._materialized()
             self.audio_data = _engine().gain(x.reshape(-1, 1, x.shape[-1]), scale.reshape(-1)).reshape(x.shape)
@@ -88,7 +92,7 @@ class EffectMixin:
         self.audio_data = self.audio_data * peak_gain
         return self
 
-    def normalize(self, db=-24.0):
+    def normalize(self, db=-24.0, _bypass=None):
         """Scale every item to ``db`` LUFS (scalar or [B]) (ref :200-220).  The per-item gain comes
         out of the loudness kernel; the multiply is deferred and fused into the next kernel that
         reads the samples (``stft`` / ``mel_spectrogram``) or materialised on first access."""
@@ -104,14 +108,18 @@ class EffectMixin:
         else:
             measured = self.loudness()
             gain = torch.exp((db - measured) * float(np.float32(self.GAIN_FACTOR)))
+        if _bypass is not None:  # items the transform's mask does not select keep their samples (gain exactly 1)
+            gain = torch.where(torch.as_tensor(_bypass).to(gain.device).bool().reshape(-1), torch.ones_like(gain), gain)
         self._defer_gain(gain)
         self._measured_loudness = measured  # extension: the LUFS the gain was derived from (logging / statistics)
         return self
 
-    def volume_change(self, db):
+    def volume_change(self, db, _bypass=None):
         """Multiply every item by ``10**(db/20)`` (ref :222-238)."""
         db = util.ensure_tensor(db, ndim=1).to(self.device).float()
         gain = torch.exp(db * float(np.float32(self.GAIN_FACTOR)))
+        if _bypass is not None:
+            gain = torch.where(torch.as_tensor(_bypass).to(gain.device).bool().reshape(-1), torch.ones_like(gain), gain)
         self._defer_gain(util.ensure_tensor(gain, 1, self.batch_size))
         return self
 
@@ -138,16 +146,16 @@ class EffectMixin:
         """Split into ``n_bands`` mel-spaced bands -> [B, C, T, n_bands] (ref :386-403)."""
         return _engine().mel_filterbank(self._materialized(), self.sample_rate, n_bands)
 
-    def equalizer(self, db):
+    def equalizer(self, db, _bypass=None):
         """Mel-spaced band equaliser; band weights are ``10**db`` exactly as in the reference (ref :405-433).
-        The band split and the weighted sum collapse into ONE FIR per item."""
+        The band split and the weighted sum collapse into ONE FIR per item.  ``_bypass`` [B]: items left untouched."""
         db = util.ensure_tensor(db)
         if db.ndim == 2:
             if db.shape[0] != 1:
                 assert db.shape[0] == self.batch_size
         else:
             db = db.unsqueeze(0)
-        self.audio_data = _engine().equalizer(self._materialized(), self.sample_rate, db.to(self.device))
+        self.audio_data = _engine().equalizer(self._materialized(), self.sample_rate, db.to(self.device), bypass=_bypass)
         return self
 
     def clip_distortion(self, clip_percentile):

@@ -104,6 +104,7 @@ struct InvParams {
   const float2* H1;      // single-partition filters [n_filt, NF]: the product X * H is formed on load (no Y pass)
   const float* x;        // [rows_total, T] (for subtract_from_input)
   const float* post;     // [n_filt] nullable
+  const int32_t* bypass; // [n_filt] nullable: non-zero = out = x for the rows of this filter
   float* out;            // [rows_total, T]
   int rows, row0, T, NB, rows_per_filt, subtract;
   int off_tw, off_ut, off_buf;
@@ -129,6 +130,12 @@ __global__ void __launch_bounds__(256, 2) ifft_blocks_kernel(InvParams p) {
   for (int t = blockIdx.x; t < total; t += gridDim.x) {
     const int row = t / groups, b = (t - row * groups) * 8 + warp;
     if (b >= p.NB) continue;  // warp-uniform
+    if (p.bypass && __ldg(p.bypass + (p.row0 + row) / p.rows_per_filt)) {  // not selected by the mask: out = x
+      const float* xs = p.x + (size_t)(p.row0 + row) * p.T;
+      float* os = p.out + (size_t)(p.row0 + row) * p.T;
+      for (int i = l; i < LP; i += 32) { const int s = b * LP + i; if (s < p.T) os[s] = __ldg(xs + s); }
+      continue;
+    }
     const float2* yr = p.Y + (size_t)row * NF * p.NB + b;
     const float2* hr = p.H1 ? p.H1 + (size_t)((p.row0 + row) / p.rows_per_filt) * NF : nullptr;
     // Z[e] = Xe[e] + i Xo[e] from the real-FFT bins X[e], X[N-e]; the inverse transform is
@@ -263,8 +270,8 @@ static int num_sms() {
 }
 
 static int run(const float* x, int64_t rows, int64_t T, const float* g, int64_t n_filt, int64_t L, int rows_per_filt,
-               const int32_t* offset, int offset0, int pad_mode, const float* post_scale, int subtract, float* out,
-               char* ws, const Layout& w, void* stream) {
+               const int32_t* offset, int offset0, int pad_mode, const float* post_scale, int subtract,
+               const int32_t* bypass, float* out, char* ws, const Layout& w, void* stream) {
   float* ones = (float*)(ws + w.ones);
   float* half = (float*)(ws + w.half);
   float2* H = (float2*)(ws + w.H);
@@ -305,7 +312,7 @@ static int run(const float* x, int64_t rows, int64_t T, const float* g, int64_t 
     // 4. inverse FFT + overlap-save + epilogue
     // one partition (NBX == NB): the inverse kernel multiplies X by H while loading, Y is never written
     ip.Y = (w.P > 1) ? Y : X; ip.H1 = (w.P > 1) ? nullptr : H;
-    ip.x = x; ip.post = post_scale; ip.out = out;
+    ip.x = x; ip.post = post_scale; ip.out = out; ip.bypass = bypass;
     ip.rows = nr; ip.row0 = (int)r0; ip.T = (int)T; ip.NB = w.NB; ip.rows_per_filt = rows_per_filt;
     ip.subtract = subtract;
     const int64_t total = (int64_t)nr * ((w.NB + 7) / 8);
@@ -328,8 +335,8 @@ extern "C" size_t b2a_fftconv_workspace_bytes(int64_t rows, int64_t T, int64_t n
 
 extern "C" int b2a_fftconv_f32(const float* x, int64_t rows, int64_t T, const float* g, int64_t n_filt, int64_t L,
                                int rows_per_filt, const int32_t* offset, int offset0, int pad_mode,
-                               const float* post_scale, int subtract_from_input, float* out, void* ws,
-                               size_t ws_bytes, void* stream) {
+                               const float* post_scale, int subtract_from_input, const int32_t* bypass, float* out,
+                               void* ws, size_t ws_bytes, void* stream) {
   B2A_REQUIRE(x && g && out && ws, B2A_E_INVALID, "fftconv: null pointer");
   B2A_REQUIRE(rows >= 1 && T >= 1 && n_filt >= 1 && L >= 1 && rows_per_filt >= 1, B2A_E_INVALID, "fftconv: bad shape");
   B2A_REQUIRE((rows + rows_per_filt - 1) / rows_per_filt <= n_filt, B2A_E_INVALID,
@@ -341,8 +348,8 @@ extern "C" int b2a_fftconv_f32(const float* x, int64_t rows, int64_t T, const fl
   B2A_REQUIRE(out != x, B2A_E_INVALID, "fftconv: in-place is not supported");
   const Layout w = layout(rows, T, n_filt, L);
   B2A_REQUIRE(ws_bytes >= w.total, B2A_E_INVALID, "fftconv: workspace too small (%zu < %zu)", ws_bytes, w.total);
-  return run(x, rows, T, g, n_filt, L, rows_per_filt, offset, offset0, pad_mode, post_scale, subtract_from_input, out,
-             (char*)ws, w, stream);
+  return run(x, rows, T, g, n_filt, L, rows_per_filt, offset, offset0, pad_mode, post_scale, subtract_from_input, bypass,
+             out, (char*)ws, w, stream);
 }
 
 /* EffectMixin.convolve (ref:audiotools/core/effects.py:66-123): out = (x (*) roll(ir, -argmax|ir|)) / max(max|ir|, 1e-5),
@@ -353,8 +360,8 @@ extern "C" size_t b2a_circconv_workspace_bytes(int64_t rows, int64_t T, int64_t 
 }
 
 extern "C" int b2a_circconv_f32(const float* x, int64_t rows, int64_t T, const float* ir, int64_t n_ir, int64_t L,
-                                int rows_per_ir, int roll_to_peak, float* out, void* ws, size_t ws_bytes,
-                                void* stream) {
+                                int rows_per_ir, int roll_to_peak, const int32_t* bypass, float* out, void* ws,
+                                size_t ws_bytes, void* stream) {
   B2A_REQUIRE(x && ir && out && ws, B2A_E_INVALID, "circconv: null pointer");
   B2A_REQUIRE(rows >= 1 && T >= 1 && n_ir >= 1 && L >= 1 && rows_per_ir >= 1, B2A_E_INVALID, "circconv: bad shape");
   const int64_t Leff = L < T ? L : T;  // the reference truncates the IR to the signal length
@@ -368,5 +375,5 @@ extern "C" int b2a_circconv_f32(const float* x, int64_t rows, int64_t T, const f
   // y[n] = sum_j h[j] x[(n - (j - idx)) mod T]  ==  causal conv with offset c = idx, circular indexing
   B2A_REQUIRE(L == Leff, B2A_E_INVALID, "circconv: pass the IR already truncated to the signal length (L=%lld > T=%lld)",
               (long long)L, (long long)T);
-  return run(x, rows, T, ir, n_ir, Leff, rows_per_ir, pidx, 0, 3, pscale, 0, out, base, w, stream);
+  return run(x, rows, T, ir, n_ir, Leff, rows_per_ir, pidx, 0, 3, pscale, 0, bypass, out, base, w, stream);
 }

@@ -28,6 +28,7 @@ struct Params {
   const float* x;
   const float* taps;       // [n_filt, K]
   const int32_t* left;     // [n_filt] nullable
+  const int32_t* bypass;   // [n_filt] nullable: non-zero = copy the rows of this filter through (mask-aware transforms)
   float* out;
   int T, K, stride, rows_per_filt, left0, pad_mode, subtract, tiles_per_row;
   int64_t out_len;
@@ -49,6 +50,14 @@ __global__ void __launch_bounds__(THREADS) fir_direct_kernel(Params p) {
   const int64_t j0 = m_base * p.stride - left;  // x-coordinate of stream position 0, phase 0
   const float* xr = p.x + (size_t)row * (size_t)p.T;
   const int S = p.stride;
+  if (p.bypass && __ldg(p.bypass + f)) {  // item not selected by the transform's mask: out = x (stride 1), CTA-uniform
+    float* orow = p.out + (size_t)row * (size_t)p.out_len;
+    for (int i = tid; i < TILE; i += THREADS) {
+      const int64_t m = m_base + i;
+      if (m < p.out_len) orow[m] = __ldg(xr + m);
+    }
+    return;
+  }
   // ---- stage the span, phase-de-interleaved
   const int span = p.np * S;
   for (int i = tid; i < span; i += THREADS) {
@@ -118,7 +127,8 @@ extern "C" int b2a_fir_direct_supported(int64_t T, int K, int stride) {
 
 extern "C" int b2a_fir_direct_f32(const float* x, int64_t rows, int64_t T, const float* taps, int64_t n_filt, int K,
                                   int rows_per_filt, const int32_t* left, int left0, int stride, int64_t out_len,
-                                  int pad_mode, int subtract_from_input, float* out, void* stream) {
+                                  int pad_mode, int subtract_from_input, const int32_t* bypass, float* out,
+                                  void* stream) {
   using namespace b2a::fir;
   B2A_REQUIRE(x && taps && out, B2A_E_INVALID, "fir: null pointer");
   B2A_REQUIRE(rows >= 1 && T >= 1 && n_filt >= 1 && K >= 1 && rows_per_filt >= 1 && stride >= 1 && out_len >= 1,
@@ -129,9 +139,10 @@ extern "C" int b2a_fir_direct_f32(const float* x, int64_t rows, int64_t T, const
   B2A_REQUIRE(b2a_fir_direct_supported(T, K, stride), B2A_E_UNSUPPORTED,
               "fir: K=%d stride=%d does not fit the direct kernel (use b2a_fftconv_f32)", K, stride);
   B2A_REQUIRE(out != x, B2A_E_INVALID, "fir: in-place is not supported");
+  B2A_REQUIRE(!bypass || (stride == 1 && out_len <= T), B2A_E_INVALID, "fir: bypass needs stride 1");
   Params p;
   memset(&p, 0, sizeof(p));
-  p.x = x; p.taps = taps; p.left = left; p.out = out;
+  p.x = x; p.taps = taps; p.left = left; p.out = out; p.bypass = bypass;
   p.T = (int)T; p.K = K; p.stride = stride; p.rows_per_filt = rows_per_filt; p.left0 = left0;
   p.pad_mode = pad_mode; p.subtract = subtract_from_input; p.out_len = out_len;
   p.qmax = (((K + stride - 1) / stride) + R - 1) / R * R;

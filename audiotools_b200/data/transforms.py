@@ -23,6 +23,7 @@ from numpy.random import RandomState
 
 from ..core import AudioSignal
 from ..core import util
+from ..core.audio_signal import _on_engine
 
 tt = torch.tensor
 """Shorthand for converting things to torch.tensor."""
@@ -69,8 +70,12 @@ def _collate_draws(draws: list):
 class BaseTransform:
     def __init__(self, keys: list = [], name: str = None, prob: float = 1.0):
         # parameter names come from the _transform signature (everything but signal / kwargs)
-        tfm_keys = [k for k in signature(self._transform).parameters.keys() if k not in ("signal", "kwargs")]
+        params = signature(self._transform).parameters
+        tfm_keys = [k for k in params.keys() if k not in ("signal", "kwargs", "_bypass")]
         self.keys = keys + tfm_keys + ["mask"]
+        # mask-aware: ``_transform(signal, ..., _bypass=[B] bool)`` runs on the WHOLE batch and leaves the flagged items
+        # untouched inside the kernels (csrc: bypass flags / unit gains / zero shifts): no gather, no scatter
+        self._mask_aware = "_bypass" in params
         self.prob = prob
         self.name = self.__class__.__name__ if name is None else name
         self._needs_signal = "signal" in signature(self._instantiate).parameters  # inspected once, not per item
@@ -113,6 +118,32 @@ class BaseTransform:
                 signal.stft_data = new_stft if (pre_stft is not None and new_stft is not None) else pre_stft
                 return signal
             signal[mask] = out
+            return signal
+        if self._mask_aware and host_mask.ndim == 1 and host_mask.numel() == signal.batch_size and \
+                _on_engine(signal._audio_data):
+            # the reference gathers signal[mask], transforms the copy and scatters it back (:133-166): two extra passes
+            # over the selected items.  Here the kernels take the complement of the mask as per-item bypass flags.
+            args = {k: v for k, v in tfm_kwargs.items() if k != "mask"}
+            pre_loud, pre_stft = signal._loudness, signal.stft_data
+            bypass = ~mask.to(signal.device).bool()
+            if bypass.is_cuda:  # host mirror (the mask's own): host-side decisions on the flags need no sync
+                bypass._b2a_host = (~host_mask.bool(), bypass._version)
+            out = self._transform(signal, **args, _bypass=bypass)
+            if out is signal:
+                # state of `signal[mask] = out` (:1658-1679): caches are overwritten only where both sides hold one,
+                # and only for the selected items
+                new_loud, new_stft = signal._loudness, signal.stft_data
+                sel = mask.to(signal.device).bool()
+                if pre_loud is not None and new_loud is not None:
+                    signal._loudness = torch.where(sel, new_loud, pre_loud)
+                else:
+                    signal._loudness = pre_loud
+                if pre_stft is not None and new_stft is not None and pre_stft.shape == new_stft.shape:
+                    signal.stft_data = torch.where(sel.reshape(-1, 1, 1, 1), new_stft, pre_stft)
+                else:
+                    signal.stft_data = pre_stft
+                return signal
+            signal[mask] = out[mask]
             return signal
         tfm_kwargs = self.apply_mask(tfm_kwargs, mask)
         tfm_kwargs = {k: v for k, v in tfm_kwargs.items() if k != "mask"}
@@ -238,8 +269,8 @@ class VolumeChange(BaseTransform):
     def _instantiate(self, state: RandomState):
         return {"db": util.sample_from_dist(self.db, state)}
 
-    def _transform(self, signal, db):
-        return signal.volume_change(db)
+    def _transform(self, signal, db, _bypass=None):
+        return signal.volume_change(db, _bypass=_bypass)
 
 
 class VolumeNorm(BaseTransform):
@@ -252,8 +283,8 @@ class VolumeNorm(BaseTransform):
     def _instantiate(self, state: RandomState):
         return {"db": util.sample_from_dist(self.db, state)}
 
-    def _transform(self, signal, db):
-        return signal.normalize(db)
+    def _transform(self, signal, db, _bypass=None):
+        return signal.normalize(db, _bypass=_bypass)
 
 
 class GlobalVolumeNorm(BaseTransform):
@@ -289,8 +320,8 @@ class Equalizer(BaseTransform):
         eq_amount = util.sample_from_dist(self.eq_amount, state)
         return {"eq": -eq_amount * state.rand(self.n_bands)}
 
-    def _transform(self, signal, eq):
-        return signal.equalizer(eq)
+    def _transform(self, signal, eq, _bypass=None):
+        return signal.equalizer(eq, _bypass=_bypass)
 
 
 class LowPass(BaseTransform):
@@ -305,8 +336,8 @@ class LowPass(BaseTransform):
     def _instantiate(self, state: RandomState):
         return {"cutoff": util.sample_from_dist(self.cutoff, state)}
 
-    def _transform(self, signal, cutoff):
-        return signal.low_pass(cutoff, zeros=self.zeros)
+    def _transform(self, signal, cutoff, _bypass=None):
+        return signal.low_pass(cutoff, zeros=self.zeros, _bypass=_bypass)
 
 
 class HighPass(BaseTransform):
@@ -321,8 +352,8 @@ class HighPass(BaseTransform):
     def _instantiate(self, state: RandomState):
         return {"cutoff": util.sample_from_dist(self.cutoff, state)}
 
-    def _transform(self, signal, cutoff):
-        return signal.high_pass(cutoff, zeros=self.zeros)
+    def _transform(self, signal, cutoff, _bypass=None):
+        return signal.high_pass(cutoff, zeros=self.zeros, _bypass=_bypass)
 
 
 class _PoolTransform(BaseTransform):
@@ -445,8 +476,8 @@ class RoomImpulseResponse(BaseTransform):
         ir_signal.zero_pad_to(signal.sample_rate)
         return {"eq": eq, "ir_signal": ir_signal, "drr": drr}
 
-    def _transform(self, signal, ir_signal, drr, eq):
-        return signal.apply_ir(ir_signal.clone(), drr, eq, use_original_phase=self.use_original_phase)
+    def _transform(self, signal, ir_signal, drr, eq, _bypass=None):
+        return signal.apply_ir(ir_signal.clone(), drr, eq, use_original_phase=self.use_original_phase, _bypass=_bypass)
 
 
 class PitchShift(BaseTransform):
@@ -464,9 +495,11 @@ class PitchShift(BaseTransform):
     def _instantiate(self, state: RandomState):
         return {"n_semitones": util.sample_from_dist(self.n_semitones, state)}
 
-    def _transform(self, signal, n_semitones):
+    def _transform(self, signal, n_semitones, _bypass=None):
         # the grouping by shift is a host decision (host mirror: no sync); all groups share the kernel launches
         shifts = util.ensure_tensor(util.host_view(n_semitones), 1, signal.batch_size).reshape(-1)
+        if _bypass is not None:  # shift 0 = the kernels copy the row through
+            shifts = torch.where(util.host_view(_bypass).cpu().bool().reshape(-1), torch.zeros_like(shifts), shifts)
         return signal.pitch_shift(shifts, quick=self.quick)
 
 

@@ -526,7 +526,7 @@ class Engine:
         B, C, T = x.shape
         F = n_fft // 2 + 1
         if not self.lib.b2a_dft_supported(n_fft, hop):
-            raise NotImplementedError(f"stft: window_length {n_fft} hop {hop}")
+            raise NotImplementedError(f"stft: window_length {n_fft} hop {hop}: the dense DFT path covers 2..8192")
         scaled = None
         if gain is not None:
             gain = self._prep(gain.reshape(-1), "gain")
@@ -555,12 +555,21 @@ class Engine:
         return {"stft": stft if want_stft else None, "mel": mel, "scaled": scaled if want_scaled else None}
 
     # ------------------------------------------------------------------ FIR / convolution
+    def _bypass(self, bypass, n: int, device):
+        """[n] int32 device flags (non-zero = leave the rows of this filter / item untouched) or None."""
+        if bypass is None:
+            return None
+        bypass = torch.as_tensor(bypass).reshape(-1).to(device=device, dtype=torch.int32).contiguous()
+        assert bypass.numel() == n, (bypass.shape, n)
+        return bypass
+
     def fftconv(self, x: torch.Tensor, taps: torch.Tensor, rows_per_filt: int, offset: Optional[torch.Tensor] = None,
                 offset0: int = 0, pad_mode: str = "replicate", post_scale: Optional[torch.Tensor] = None,
-                subtract_from_input: bool = False) -> torch.Tensor:
+                subtract_from_input: bool = False, bypass: Optional[torch.Tensor] = None) -> torch.Tensor:
         """``out[row, n] = post * sum_k taps[f, k] * xv[row, n - k + offset0 + offset[f]]`` with
         ``f = row // rows_per_filt`` and ``xv`` = ``x`` extended by ``pad_mode`` ("constant" zeros,
-        "replicate", "circular").  x: [..., T] (leading dims are flattened to rows); taps: [n_filt, L]."""
+        "replicate", "circular").  x: [..., T] (leading dims are flattened to rows); taps: [n_filt, L].
+        ``bypass`` [n_filt] (bool / int): rows of those filters are copied through unchanged (mask-aware transforms)."""
         x = self._prep(x, "x")
         shape = x.shape
         T = shape[-1]
@@ -574,6 +583,7 @@ class Engine:
         if post_scale is not None:
             post_scale = self._prep(post_scale.reshape(-1).to(x.device), "post_scale")
             assert post_scale.numel() == n_filt
+        bypass = self._bypass(bypass, n_filt, x.device)
         mode = {"constant": 1, "replicate": 2, "circular": 3}[pad_mode]
         ws_bytes = self.lib.b2a_fftconv_workspace_bytes(rows, T, n_filt, L)
         if ws_bytes == 0:
@@ -582,7 +592,7 @@ class Engine:
         out = torch.empty_like(x)
         rc = self.lib.b2a_fftconv_f32(_dptr(x), rows, T, _dptr(taps), n_filt, L, int(rows_per_filt), _dptr(offset),
                                       int(offset0), mode, _dptr(post_scale), int(bool(subtract_from_input)),
-                                      _dptr(out), _dptr(ws), ws_bytes, self._stream(x))
+                                      _dptr(bypass), _dptr(out), _dptr(ws), ws_bytes, self._stream(x))
         self.lib.check(rc)
         nchunk = 1  # kernels: fill, filter FFT, then per row-chunk: origins, block FFT, bin FIR, inverse FFT
         self.launches += 2 + 4 * nchunk
@@ -592,8 +602,9 @@ class Engine:
 
     def fir_direct(self, x: torch.Tensor, taps: torch.Tensor, rows_per_filt: int, left: Optional[torch.Tensor] = None,
                    left0: int = 0, stride: int = 1, out_len: Optional[int] = None, pad_mode: str = "replicate",
-                   subtract_from_input: bool = False) -> torch.Tensor:
-        """``out[row, m] = sum_k taps[f, k] * xv[row, m*stride + k - left0 - left[f]]`` (correlation form)."""
+                   subtract_from_input: bool = False, bypass: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """``out[row, m] = sum_k taps[f, k] * xv[row, m*stride + k - left0 - left[f]]`` (correlation form);
+        ``bypass`` [n_filt]: rows of those filters are copied through unchanged (stride 1)."""
         x = self._prep(x, "x")
         T = x.shape[-1]
         rows = x.numel() // T
@@ -602,10 +613,11 @@ class Engine:
         if left is not None:
             left = self._prep(left.reshape(-1).to(x.device), "left", torch.int32)
         out_len = T if out_len is None else int(out_len)
+        bypass = self._bypass(bypass, n_filt, x.device)
         out = torch.empty(*x.shape[:-1], out_len, dtype=torch.float32, device=x.device)
         rc = self.lib.b2a_fir_direct_f32(_dptr(x), rows, T, _dptr(taps), n_filt, K, int(rows_per_filt), _dptr(left),
                                          int(left0), int(stride), out_len, {"constant": 1, "replicate": 2}[pad_mode],
-                                         int(bool(subtract_from_input)), _dptr(out), self._stream(x))
+                                         int(bool(subtract_from_input)), _dptr(bypass), _dptr(out), self._stream(x))
         self.lib.check(rc)
         self.launches += 1
         return out
@@ -641,7 +653,7 @@ class Engine:
         return torch.where(idx >= 0, g, torch.zeros_like(g))
 
     def sinc_filter(self, x: torch.Tensor, cutoffs_hz: torch.Tensor, sample_rate: int, zeros: int = 51,
-                    highpass: bool = False) -> torch.Tensor:
+                    highpass: bool = False, bypass: Optional[torch.Tensor] = None) -> torch.Tensor:
         """Per-item windowed-sinc low-pass (or ``x - lowpass(x)``) of x [B, C, T]
         (ref:audiotools/core/dsp.py:153-215 -> julius.LowPassFilter(cutoff / sr, zeros), replicate padding)."""
         x = self._prep(x, "x")
@@ -668,10 +680,10 @@ class Engine:
         if K <= self.DIRECT_FIR_MAX_TAPS and self.lib.b2a_fir_direct_supported(T, K, 1):
             # short filters: time-domain kernel, correlation taps as designed (filter b is centred at half[b])
             return self.fir_direct(x, f, rows_per_filt=C, left=half.to(torch.int32), pad_mode="replicate",
-                                   subtract_from_input=highpass)
+                                   subtract_from_input=highpass, bypass=bypass)
         g = self._reverse_rows(f, 2 * half + 1)
         return self.fftconv(x, g, rows_per_filt=C, offset=half.to(torch.int32), pad_mode="replicate",
-                            subtract_from_input=highpass)
+                            subtract_from_input=highpass, bypass=bypass)
 
     @staticmethod
     def _split_band_cutoffs(sample_rate: float, n_bands: int):
@@ -691,7 +703,8 @@ class Engine:
         lp = self._lowpass_bank(cn.float(), torch.full((len(c),), half, dtype=torch.int64), device)
         return lp, half
 
-    def equalizer(self, x: torch.Tensor, sample_rate: int, db: torch.Tensor) -> torch.Tensor:
+    def equalizer(self, x: torch.Tensor, sample_rate: int, db: torch.Tensor,
+                  bypass: Optional[torch.Tensor] = None) -> torch.Tensor:
         """Mel-band equaliser of x [B, C, T] (ref:audiotools/core/effects.py:405-433): band weights
         10**db [B or 1, n_bands]; split + weighted sum == one FIR per item,
         h = w_last * delta + sum_k (w_k - w_{k+1}) * lowpass_k."""
@@ -706,12 +719,16 @@ class Engine:
             w = w.expand(B, n_bands)
         assert w.shape[0] == B
         if n_bands == 1:
-            return self.gain(x, w[:, 0].contiguous())
+            g1 = w[:, 0].contiguous()
+            if bypass is not None:
+                g1 = torch.where(torch.as_tensor(bypass).to(x.device).bool().reshape(-1), torch.ones_like(g1), g1)
+            return self.gain(x, g1)
         lp, half = self._band_lowpasses(sample_rate, n_bands, x.device)
-        h = (w[:, :-1] - w[:, 1:]) @ lp  # [B, 2*half+1]
+        # [B, n_bands-1] x [n_bands-1, 2*half+1] as a broadcast multiply-add (a few KB: not worth a library GEMM call)
+        h = ((w[:, :-1] - w[:, 1:]).unsqueeze(-1) * lp.unsqueeze(0)).sum(dim=1)
         h[:, half] += w[:, -1]
         g = torch.flip(h, dims=[1]).contiguous()
-        return self.fftconv(x, g, rows_per_filt=C, offset0=half, pad_mode="replicate")
+        return self.fftconv(x, g, rows_per_filt=C, offset0=half, pad_mode="replicate", bypass=bypass)
 
     def mel_filterbank(self, x: torch.Tensor, sample_rate: int, n_bands: int) -> torch.Tensor:
         """julius.SplitBands(sample_rate, n_bands)(x).permute(1, 2, 3, 0) -> [B, C, T, n_bands]
@@ -731,23 +748,33 @@ class Engine:
                  for k in range(n_bands)]
         return torch.stack(bands, dim=-1)
 
-    def circular_convolve(self, x: torch.Tensor, ir: torch.Tensor, roll_to_peak: bool = True) -> torch.Tensor:
+    def circular_convolve(self, x: torch.Tensor, ir: torch.Tensor, roll_to_peak: bool = True,
+                          bypass: Optional[torch.Tensor] = None) -> torch.Tensor:
         """``EffectMixin.convolve`` (ref:audiotools/core/effects.py:66-123): circular convolution with period T,
-        the IR rolled to its peak, scaled by 1/max(max|ir|, 1e-5).  x: [B, C, T]; ir: [B, 1 or C, L]."""
+        the IR rolled to its peak, scaled by 1/max(max|ir|, 1e-5).  x: [B, C, T]; ir: [B or 1, 1 or C, L] (a batch-1
+        impulse response is shared by all items, as the reference's broadcasting product does).  ``bypass`` [B]:
+        items left untouched."""
         x = self._prep(x, "x")
         B, C, T = x.shape
         ir = self._prep(ir, "ir")
-        assert ir.ndim == 3 and ir.shape[0] == B and ir.shape[1] in (1, C), ir.shape
+        assert ir.ndim == 3 and ir.shape[0] in (1, B) and ir.shape[1] in (1, C), ir.shape
+        if ir.shape[0] == 1 and B > 1 and (ir.shape[1] != 1 or bypass is not None):
+            ir = ir.expand(B, -1, -1).contiguous()  # per-channel / per-item flags need one filter per item
         if ir.shape[-1] > T:
             ir = ir[..., :T].contiguous()
         L = ir.shape[-1]
-        n_ir = B * ir.shape[1]
-        rows_per_ir = C if ir.shape[1] == 1 else 1
+        n_ir = ir.shape[0] * ir.shape[1]
+        rows_per_ir = (B * C if ir.shape[0] == 1 else C) if ir.shape[1] == 1 else 1
+        if bypass is not None:
+            bypass = torch.as_tensor(bypass).reshape(-1).to(x.device)
+            if ir.shape[1] != 1:
+                bypass = bypass.repeat_interleave(C)
+            bypass = self._bypass(bypass, n_ir, x.device)
         ws_bytes = self.lib.b2a_circconv_workspace_bytes(B * C, T, n_ir, L)
         ws = torch.empty(ws_bytes, dtype=torch.uint8, device=x.device)
         out = torch.empty_like(x)
         rc = self.lib.b2a_circconv_f32(_dptr(x), B * C, T, _dptr(ir), n_ir, L, rows_per_ir, int(bool(roll_to_peak)),
-                                       _dptr(out), _dptr(ws), ws_bytes, self._stream(x))
+                                       _dptr(bypass), _dptr(out), _dptr(ws), ws_bytes, self._stream(x))
         self.lib.check(rc)
         self.launches += 7
         return out

@@ -183,13 +183,17 @@ int b2a_gain_f32(const float* x, float* out, int64_t B, int64_t per_item, const 
  * n in [0, T), where xv extends x[row] by pad_mode: 1 zeros, 2 replicate (edge), 3 circular (period T).
  * With subtract_from_input != 0 the result is x - (that).   g: [n_filt, L] row-major taps (zero-pad
  * shorter filters); offset / post_scale: nullable [n_filt].   out must not alias x.
+ * bypass: nullable [n_filt] int32 -- the rows of a filter with bypass != 0 are copied through unchanged (out = x,
+ * exactly): how a transform applies itself to the items its mask selects without gathering / scattering the batch
+ * (audiotools/data/transforms.py:133-166).  The same argument exists on b2a_fir_direct_f32 (stride 1) and
+ * b2a_circconv_f32.
  * Replaces julius.LowPassFilter / HighPassFilter (audiotools/core/dsp.py:153-215), julius.SplitBands +
  * the weighted band sum (audiotools/core/effects.py:386-433) -- each collapsed to one FIR per item. */
 size_t b2a_fftconv_workspace_bytes(int64_t rows, int64_t T, int64_t n_filt, int64_t L);
 int b2a_fftconv_f32(const float* x, int64_t rows, int64_t T, const float* g, int64_t n_filt, int64_t L,
                     int rows_per_filt, const int32_t* offset, int offset0, int pad_mode,
-                    const float* post_scale, int subtract_from_input, float* out, void* ws, size_t ws_bytes,
-                    void* stream);
+                    const float* post_scale, int subtract_from_input, const int32_t* bypass, float* out, void* ws,
+                    size_t ws_bytes, void* stream);
 
 /* Direct (time-domain) strided FIR for short filters, correlation form:
  *   out[row][m] = sum_{k<K} taps[f][k] * xv[row][m*stride + k - left0 - left[f]],  f = row / rows_per_filt, m < out_len
@@ -200,14 +204,15 @@ int b2a_fftconv_f32(const float* x, int64_t rows, int64_t T, const float* g, int
 int b2a_fir_direct_supported(int64_t T, int K, int stride);
 int b2a_fir_direct_f32(const float* x, int64_t rows, int64_t T, const float* taps, int64_t n_filt, int K,
                        int rows_per_filt, const int32_t* left, int left0, int stride, int64_t out_len,
-                       int pad_mode, int subtract_from_input, float* out, void* stream);
+                       int pad_mode, int subtract_from_input, const int32_t* bypass, float* out, void* stream);
 
 /* EffectMixin.convolve (audiotools/core/effects.py:66-123): CIRCULAR convolution (period T) of each row with
  * its item's impulse response, the IR rolled so that max|ir| sits at t = 0 (roll_to_peak) and the result
  * scaled by 1 / max(max|ir|, 1e-5).   ir: [n_ir, L] with L <= T (truncate first, as the reference does). */
 size_t b2a_circconv_workspace_bytes(int64_t rows, int64_t T, int64_t n_ir, int64_t L);
 int b2a_circconv_f32(const float* x, int64_t rows, int64_t T, const float* ir, int64_t n_ir, int64_t L,
-                     int rows_per_ir, int roll_to_peak, float* out, void* ws, size_t ws_bytes, void* stream);
+                     int rows_per_ir, int roll_to_peak, const int32_t* bypass, float* out, void* ws, size_t ws_bytes,
+                     void* stream);
 
 /* ---- windowed-sinc polyphase resampling ------------------------------------------------------
  * AudioSignal.resample (audiotools/core/audio_signal.py:716-736 -> julius.resample_frac): old_r/new_r are

@@ -276,8 +276,8 @@ def test_cpu_tensor_raises_and_errors_map(at):
     sig = at.AudioSignal(torch.zeros(1, 1, 16000), 16000)
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         sig.loudness()
-    with pytest.raises(Exception, match="power of two"):
-        at.AudioSignal(torch.zeros(1, 1, 16000), 16000).to(DEV).stft(window_length=400, hop_length=100)
+    with pytest.raises(NotImplementedError, match="dense DFT path"):  # (any length up to 8192 runs: tests/test_gpu_dense_dft.py)
+        at.AudioSignal(torch.zeros(1, 1, 40000), 16000).to(DEV).stft(window_length=10000, hop_length=2500)
     with pytest.raises(RuntimeError, match="without self.stft_data"):
         at.AudioSignal(torch.zeros(1, 1, 16000), 16000).to(DEV).istft()
 
@@ -846,3 +846,26 @@ def test_device_collate_and_salient_excerpt(at):
         assert abs(got.metadata["offset"] - off) < 1e-12 and got.signal_length == 2 * sr
         assert torch.equal(got.audio_data.cpu(), x[..., int(off * sr): int(off * sr) + 2 * sr])
         assert st.uniform() == ref_state.uniform()
+
+
+def test_mask_aware_transforms_equal_gather_scatter(at):
+    """GPU twin of tests/test_sim_signal_api.py::test_mask_aware_transforms_equal_gather_scatter (SURVEY.md 8f.3)."""
+    from audiotools_b200.data import transforms as tfm
+
+    g = torch.Generator().manual_seed(0)
+    B, T, sr = 16, 88200, 44100
+    x = 0.1 * torch.randn(B, 2, T, generator=g)
+    irs = [at.AudioSignal(torch.randn(1, 1, 8000, generator=g) * torch.exp(-torch.arange(8000) / 900.0), sr) for _ in range(3)]
+    for t in [tfm.VolumeChange(prob=0.5), tfm.VolumeNorm(prob=0.5), tfm.Equalizer(prob=0.5), tfm.LowPass(prob=0.5),
+              tfm.HighPass(prob=0.5), tfm.LowPass(cutoff=("const", 300), zeros=8, prob=0.5),
+              tfm.PitchShift(("choice", [-2, 2]), prob=0.5), tfm.RoomImpulseResponse(sources=irs, prob=0.5)]:
+        sig = at.AudioSignal(x.clone(), sr)
+        kw = t.batch_instantiate(list(range(B)), sig)
+        mask = kw[t.name]["mask"]
+        assert 0 < int(mask.sum()) < B
+        dk = at.util.prepare_batch(kw, DEV)
+        a = t(sig.clone().to(DEV), **dk).audio_data
+        t._mask_aware = False
+        b = t(sig.clone().to(DEV), **dk).audio_data
+        assert torch.equal(a, b), type(t).__name__
+        assert torch.equal(a[~mask].cpu(), x[~mask]), type(t).__name__

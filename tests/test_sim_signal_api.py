@@ -272,3 +272,29 @@ def test_batch_collates_ragged_signals_in_one_launch():
     assert out.shape == (2, 2, 640) and torch.equal(out.audio_data, torch.cat([raw[0][..., :640], raw[1]]))
     with pytest.raises(RuntimeError):
         AudioSignal.batch([mk(1, 900), mk(1, 640)])
+
+
+def test_mask_aware_transforms_equal_gather_scatter():
+    """a transform with a partial mask runs on the WHOLE batch with per-item bypass flags inside the
+    kernels (no gather / scatter of the selected items, ref:audiotools/data/transforms.py:133-166) and must leave
+    exactly the state the reference's ``signal[mask] = transform(signal[mask])`` leaves: selected items bit-identical
+    to the gathered run, the others untouched."""
+    g = torch.Generator().manual_seed(0)
+    B, T, sr = 5, 6000, 16000
+    x = 0.1 * torch.randn(B, 2, T, generator=g)
+    irs = [AudioSignal(torch.randn(1, 1, 800, generator=g) * torch.exp(-torch.arange(800) / 100.0), sr) for _ in range(2)]
+    cases_ = [tfm.VolumeChange(prob=0.5), tfm.VolumeNorm(prob=0.5), tfm.Equalizer(prob=0.5),
+              tfm.LowPass(cutoff=("choice", [2000, 4000]), prob=0.5), tfm.HighPass(prob=0.5),
+              tfm.LowPass(cutoff=("const", 200), zeros=8, prob=0.5),  # 641 taps: the FFT-convolution path
+              tfm.PitchShift(("choice", [-2, 2]), prob=0.5), tfm.RoomImpulseResponse(sources=irs, prob=0.5)]
+    for t in cases_:
+        assert t._mask_aware
+        sig = AudioSignal(x.clone(), sr)
+        kw = t.batch_instantiate(list(range(B)), sig)
+        mask = kw[t.name]["mask"]
+        assert 0 < int(mask.sum()) < B
+        a = t(sig.clone(), **kw).audio_data
+        t._mask_aware = False  # the reference's gather -> transform -> scatter
+        b = t(sig.clone(), **kw).audio_data
+        assert torch.equal(a, b), type(t).__name__
+        assert torch.equal(a[~mask], x[~mask]), type(t).__name__

@@ -679,7 +679,9 @@ def _refill_masked_cells(signal):
     mag, phase = signal.magnitude, signal.phase
     mag_r, phase_r = torch.randn_like(mag), torch.randn_like(phase)
     mask = (mag == 0.0) & (phase == 0.0)
-    signal.stft_data = torch.where(mask, mag_r, mag) * torch.exp(1j * torch.where(mask, phase_r, phase))
+    # the reference assigns `signal.magnitude = mag` and then `signal.phase = phase`; the second setter re-reads
+    # |stft_data|, so a refilled cell ends up as |mag_r| exp(1j phase_r)
+    signal.stft_data = torch.where(mask, mag_r.abs(), mag) * torch.exp(1j * torch.where(mask, phase_r, phase))
     return signal
 
 

@@ -41,7 +41,12 @@ class Engine:
         return t.contiguous()
 
     def _stream(self, t: torch.Tensor):
+        """The stream the call is issued on.  Every entry point of the library launches on the CURRENT device, so a
+        tensor that lives on another GPU of the process (``AudioSignal(..., device="cuda:1")``) makes its device
+        current first -- the attribute / occupancy queries and the launch then all refer to the tensor's device."""
         if t.is_cuda:
+            if torch.cuda.current_device() != t.device.index:
+                torch.cuda.set_device(t.device)
             return ctypes.c_void_p(torch.cuda.current_stream(t.device).cuda_stream)
         return None
 
@@ -99,6 +104,10 @@ class Engine:
         # holds the window tensor itself (the caller caches its windows), so a re-used window costs no sync
         key = ("istft_env", window.data_ptr(), int(window._version), n_fft, hop, N + 2 * pad_frames, start, int(length))
         if key not in self._packed_cache:
+            stale = [k for k in self._packed_cache if k[0] == "istft_env"]
+            if len(stale) >= 64:  # bounded: one entry per distinct (window, geometry, length)
+                for k in stale[:32]:
+                    del self._packed_cache[k]
             self._packed_cache[key] = (window, self._envelope_min(window, n_fft, hop, N + 2 * pad_frames, start,
                                                                   start + int(length)))
         if self._packed_cache[key][1] < 1e-11:
@@ -674,6 +683,12 @@ class Engine:
             raise ValueError("A cutoff above 0.5 does not make sense.")
         if (cn == 0).any():
             raise ValueError("cutoff 0: julius.LowPassFilter has no positive cutoff to size the filter from")
+        if bypass is not None:
+            # items the mask does not select must not size the filter bank (their cutoff may ask for the longest
+            # filter and push the call from the direct kernel to the FFT engine): give them the widest selected cutoff
+            bh = _util.host_view(torch.as_tensor(bypass)).reshape(-1).cpu().bool()
+            if bool((~bh).any()):
+                cn = torch.where(bh, cn[~bh].max(), cn)
         half = (zeros / cn / 2).to(torch.int64)  # int(zeros / cutoff / 2), in the tensor's own precision
         f = self._lowpass_bank(cn, half, x.device)
         K = f.shape[1]

@@ -3,7 +3,7 @@
 bench.py, which measures configs[1]).  One JSON line per config: device-resident throughput (CUDA events,
 >= 3 warm-ups, inputs larger than L2 or rotated), algorithmic bytes, and the CPU oracle on a bounded sample.
 
-    python bench_configs.py [--only cfg1,cfg3,cfg4,cfg5,istft,specaug] [--no-cpu]
+    python bench_configs.py [--only cfg1,cfg3,cfg4,cfg5,istft,specaug,dense,gate,masked] [--no-cpu]
 
 Multi-GPU (BASELINE configs[3] = 512 items on 4 GPUs, configs[4] = 2048 items on 8 GPUs): one process per GPU,
     python -m torch.distributed.run --nnodes=1 --nproc-per-node 4 --master-addr 127.0.0.1 --master-port 29511 \
@@ -76,7 +76,7 @@ def cpu_time(fn, reps=2):
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--only", default="cfg1,cfg3,cfg4,cfg5,istft,specaug")
+    ap.add_argument("--only", default="cfg1,cfg3,cfg4,cfg5,istft,specaug,dense,gate,masked")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--gpus", type=int, default=1, help="ranks (informational: the launcher sets WORLD_SIZE)")
     args = ap.parse_args()
@@ -212,6 +212,61 @@ def main():
         emit({"config": "istft 64x2ch 10s@44.1k n_fft=2048 hop=512", "ms": ms, "ms_torch_istft_cufft": ms_torch,
                           "clips_per_s": 64 / ms * 1e3, "alg_bytes": alg, "achieved_GBps": alg / ms / 1e6,
                           "frac_of_hbm_peak": alg / ms / 1e6 / peak})
+
+    if "dense" in only:  # arbitrary window length (csrc/dft.cu): the 25 ms / 10 ms / 80-mel speech front-end at 16 kHz
+        B, T, sr = 64, 160000, 16000
+        x = (0.1 * torch.randn(B, 1, T, generator=torch.Generator().manual_seed(0))).to(dev)
+        sig = AudioSignal(x, sr)
+        ms_stft = timed(lambda: sig.stft(window_length=400, hop_length=160), steps=10)
+        ms_mel = timed(lambda: sig.mel_spectrogram(n_mels=80, window_length=400, hop_length=160, log=True), steps=10)
+        sig.stft(window_length=400, hop_length=160)
+        ms_inv = timed(lambda: sig.istft(window_length=400, hop_length=160), steps=10)
+        w = torch.hann_window(400, periodic=True, device=dev)
+        ms_torch = timed(lambda: torch.stft(x.reshape(B, T), 400, 160, window=w, center=True, return_complex=True), steps=10)
+        nfr = 1 + T // 160
+        macs = B * nfr * 400 * 201  # complex-real multiply-accumulates = FFMA2 instructions x 32 lanes
+        emit({"config": "dense DFT 64 x 1ch x 10s@16k window 400 hop 160 (+ 80-mel log-mel, inverse)", "ms_stft": ms_stft,
+              "ms_logmel": ms_mel, "ms_istft": ms_inv, "ms_torch_stft_cufft": ms_torch, "clips_per_s": B / ms_mel * 1e3,
+              "gflops_stft": 4 * macs / ms_stft / 1e6, "fp32_peak_gflops": 2 * 148 * 128 * 1965.0,
+              "frac_of_fp32_peak": 4 * macs / ms_stft / 1e6 / (2 * 148 * 128 * 1965.0)})
+
+    if "gate" in only:  # SpectralGate (csrc/specmask.cu) at 64 x 2ch x 10 s: stft x2 + gate + istft
+        from audiotools_b200.ml.layers import SpectralGate
+
+        g = torch.Generator().manual_seed(0)
+        x = (0.1 * torch.randn(64, 2, 441000, generator=g)).to(dev)
+        nz = (0.01 * torch.randn(1, 1, 88200, generator=g)).to(dev)
+        gate = SpectralGate().to(dev)
+        sig, nzs = AudioSignal(x, 44100), AudioSignal(nz, 44100)
+        ms = timed(lambda: gate(sig, nzs, 0.9), warmup=3, steps=5)
+        from audiotools_b200.engine import get_engine
+
+        s2 = sig.clone(); s2.stft(2048, 512, "sqrt_hann"); n2 = nzs.clone(); n2.stft(2048, 512, "sqrt_hann")
+        ms_k = timed(lambda: get_engine().spec_gate(s2.stft_data, n2.stft_data, 3.0, torch.tensor([0.9]), gate._rf.tolist(),
+                                                    gate._rt.tolist()), steps=10)
+        alg = 2 * s2.stft_data.numel() * 8
+        emit({"config": "SpectralGate 64x2ch 10s@44.1k (2048/512): clone + 2 stft + gate kernels + istft", "ms": ms,
+              "ms_gate_kernels": ms_k, "alg_bytes_gate": alg, "gate_GBps": alg / ms_k / 1e6, "gate_frac_of_hbm_peak": alg / ms_k / 1e6 / peak})
+
+    if "masked" in only:  # a prob = 0.5 augmentation chain, kernel-side bypass flags vs gather / scatter
+        B, T, sr = 128, 441000, 44100
+        g = torch.Generator().manual_seed(0)
+        x = 0.1 * torch.randn(B, 1, T, generator=g)
+        transform = tfm.Compose([tfm.VolumeNorm(prob=0.5), tfm.Equalizer(prob=0.5), tfm.LowPass(prob=0.5),
+                                 tfm.HighPass(prob=0.5), tfm.PitchShift(("choice", [-2, 2]), prob=0.5)])
+        sig = AudioSignal(x, sr)
+        kwargs = transform.batch_instantiate(list(range(B)), sig)
+        sig = sig.to(dev)
+        from audiotools_b200 import util
+
+        kwargs = util.prepare_batch(kwargs, dev)
+        ms_aware = timed(lambda: transform(sig.clone(), **kwargs), warmup=3, steps=5)
+        for t in transform.transforms:
+            t._mask_aware = False
+        ms_gather = timed(lambda: transform(sig.clone(), **kwargs), warmup=3, steps=5)
+        emit({"config": f"masked chain batch={B} mono 10s@44.1k Compose[VolumeNorm, Equalizer, LowPass, HighPass, PitchShift] "
+                        "each prob 0.5", "ms_bypass_flags": ms_aware, "ms_gather_scatter": ms_gather,
+              "clips_per_s": B / ms_aware * 1e3})
 
     if "specaug" in only:  # SpectralTransform chain stft -> FrequencyMask -> TimeMask -> istft at cfg2's shape
         g = torch.Generator().manual_seed(0)

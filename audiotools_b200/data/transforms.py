@@ -75,7 +75,10 @@ class BaseTransform:
         self.keys = keys + tfm_keys + ["mask"]
         # mask-aware: ``_transform(signal, ..., _bypass=[B] bool)`` runs on the WHOLE batch and leaves the flagged items
         # untouched inside the kernels (csrc: bypass flags / unit gains / zero shifts): no gather, no scatter
-        self._mask_aware = "_bypass" in params
+        # ... where that pays: `_bypass_pays = False` marks the FFT-convolution transforms, whose forward block FFTs run
+        # for every row of the launch -- measured on a prob-0.5 chain (128 x 10 s), flags on all five transforms 7.58 ms
+        # against 7.44 ms for the gather path, so those keep the gather (half the rows, two cheap copies)
+        self._mask_aware = "_bypass" in params and getattr(self, "_bypass_pays", True)
         self.prob = prob
         self.name = self.__class__.__name__ if name is None else name
         self._needs_signal = "signal" in signature(self._instantiate).parameters  # inspected once, not per item
@@ -120,7 +123,7 @@ class BaseTransform:
             signal[mask] = out
             return signal
         if self._mask_aware and host_mask.ndim == 1 and host_mask.numel() == signal.batch_size and \
-                _on_engine(signal._audio_data):
+                _on_engine(signal._audio_data) and self._bypass_ok(signal, tfm_kwargs):
             # the reference gathers signal[mask], transforms the copy and scatters it back (:133-166): two extra passes
             # over the selected items.  Here the kernels take the complement of the mask as per-item bypass flags.
             args = {k: v for k, v in tfm_kwargs.items() if k != "mask"}
@@ -149,6 +152,10 @@ class BaseTransform:
         tfm_kwargs = {k: v for k, v in tfm_kwargs.items() if k != "mask"}
         signal[mask] = self._transform(signal[mask], **tfm_kwargs)
         return signal
+
+    def _bypass_ok(self, signal, tfm_kwargs) -> bool:
+        """Per-call veto of the bypass-flag path (e.g. a filter long enough to go through the FFT engine)."""
+        return True
 
     def __call__(self, *args, **kwargs):
         return self.transform(*args, **kwargs)
@@ -310,6 +317,7 @@ class GlobalVolumeNorm(BaseTransform):
 
 class Equalizer(BaseTransform):
     """``signal.equalizer(eq)`` with ``eq = -eq_amount * rand(n_bands)`` (ref :564-600)."""
+    _bypass_pays = False  # 641 taps: FFT convolution
 
     def __init__(self, eq_amount: tuple = ("const", 1.0), n_bands: int = 6, name: str = None, prob: float = 1.0):
         super().__init__(name=name, prob=prob)
@@ -339,6 +347,15 @@ class LowPass(BaseTransform):
     def _transform(self, signal, cutoff, _bypass=None):
         return signal.low_pass(cutoff, zeros=self.zeros, _bypass=_bypass)
 
+    def _bypass_ok(self, signal, tfm_kwargs) -> bool:
+        # flags pay when the time-domain kernel serves the call (a flagged row is a plain copy); a bank long enough for
+        # the FFT engine (> 320 taps) would spend its forward FFTs on the unselected rows as well: gather instead
+        cut = util.host_view(tfm_kwargs["cutoff"]).reshape(-1).float()
+        sel = util.host_view(tfm_kwargs["mask"]).reshape(-1).bool()
+        if not bool(sel.any()) or float(cut[sel].min()) <= 0:
+            return False
+        return 2 * int(self.zeros / (float(cut[sel].min()) / signal.sample_rate) / 2) + 1 <= 320
+
 
 class HighPass(BaseTransform):
     """``signal.high_pass(cutoff, zeros)`` (ref :1134-1170)."""
@@ -354,6 +371,15 @@ class HighPass(BaseTransform):
 
     def _transform(self, signal, cutoff, _bypass=None):
         return signal.high_pass(cutoff, zeros=self.zeros, _bypass=_bypass)
+
+    def _bypass_ok(self, signal, tfm_kwargs) -> bool:
+        # flags pay when the time-domain kernel serves the call (a flagged row is a plain copy); a bank long enough for
+        # the FFT engine (> 320 taps) would spend its forward FFTs on the unselected rows as well: gather instead
+        cut = util.host_view(tfm_kwargs["cutoff"]).reshape(-1).float()
+        sel = util.host_view(tfm_kwargs["mask"]).reshape(-1).bool()
+        if not bool(sel.any()) or float(cut[sel].min()) <= 0:
+            return False
+        return 2 * int(self.zeros / (float(cut[sel].min()) / signal.sample_rate) / 2) + 1 <= 320
 
 
 class _PoolTransform(BaseTransform):
@@ -448,6 +474,7 @@ class RoomImpulseResponse(BaseTransform):
     """``signal.apply_ir(ir, drr, eq)`` (ref :857-938).  ``sources`` is an in-memory pool: a list of
     single-item ``AudioSignal`` impulse responses (or a callable ``(state, signal) -> AudioSignal``);
     one is drawn per item with ``state.choice`` and zero-padded to one second like the reference."""
+    _bypass_pays = False  # FFT convolution
 
     def __init__(self, drr: tuple = ("uniform", 0.0, 30.0), sources: List[AudioSignal] = None,
                  weights: List[float] = None, eq_amount: tuple = ("const", 1.0), n_bands: int = 6,

@@ -864,8 +864,11 @@ def test_mask_aware_transforms_equal_gather_scatter(at):
         mask = kw[t.name]["mask"]
         assert 0 < int(mask.sum()) < B
         dk = at.util.prepare_batch(kw, DEV)
+        t._mask_aware, t._bypass_ok = True, (lambda *a: True)  # force the flag path (some default to gather: _bypass_pays)
         a = t(sig.clone().to(DEV), **dk).audio_data
         t._mask_aware = False
         b = t(sig.clone().to(DEV), **dk).audio_data
-        assert torch.equal(a, b), type(t).__name__
-        assert torch.equal(a[~mask].cpu(), x[~mask]), type(t).__name__
+        # selected items: the same kernels on the same samples; the tap DESIGN (a float32 row sum on the device) may
+        # round differently for a bank of B and of n_selected filters, hence 2e-6 instead of bit equality on the GPU
+        assert (a - b).abs().max().item() <= 2e-6 * b.abs().max().item(), type(t).__name__
+        assert torch.equal(a[~mask].cpu(), x[~mask]), type(t).__name__  # unselected items: untouched, exactly

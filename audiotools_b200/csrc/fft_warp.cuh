@@ -37,6 +37,20 @@ __device__ __forceinline__ constexpr float cos_pi16(int j) {
                 : -cos_pi16(16 - j);
 }
 
+// cos(pi*j/32), j = 0..32 (the untangle twiddles exp(-i pi m / 32) of the N = 1024 transform as compile-time constants)
+__device__ __forceinline__ constexpr float cos_pi32(int j) {
+  return (j & 1) == 0 ? cos_pi16(j / 2)
+       : j == 1 ? 0.99518472667219689f
+       : j == 3 ? 0.95694033573220887f
+       : j == 5 ? 0.88192126434835503f
+       : j == 7 ? 0.77301045336273696f
+       : j == 9 ? 0.63439328416364549f
+       : j == 11 ? 0.47139673682599764f
+       : j == 13 ? 0.29028467725446236f
+       : j == 15 ? 0.09801714032956060f
+                 : -cos_pi32(32 - j);
+}
+
 // o * W_R^k, W = exp(-2 pi i / R), 0 <= k < R/2, R in {2,4,8,16,32}
 template <int R, int K>
 __device__ __forceinline__ float2 mul_wr(float2 o) {
@@ -121,7 +135,14 @@ struct WPlan {
   static constexpr int G = NWARP * FPW;            // frames in flight per CTA
   // frames per tile: 16, except n_fft = 2048 where 8 keeps two CTAs per SM resident (97 KB of shared memory)
   static constexpr int FR = (G >= 16) ? G : (LOG2N == 10 ? 8 : 16);
-  static constexpr int NTW = (R1 >= 2) ? B1 * (R1 - 1) : 0;
+  // LEAN (N = 1024: R1 = 32, B1 = 1): the 31 pass-1 twiddles W^(l t) of a lane are formed as W^(8a l) . W^(b l) from 10
+  // table entries (t = 8a + b: slots 0..6 = W^(l b), b = 1..7; 7..9 = W^(8 l), W^(16 l), W^(24 l)), and the 16 untangle
+  // twiddles exp(-i pi (l + 32 m) / N) as exp(-i pi l / N) . exp(-i pi m / 32) from ONE lane entry and compile-time
+  // constants: 72 fewer shared-memory wavefronts per frame for ~40 more packed FP32 instructions (the kernel is bound by
+  // the shared-memory pipe: DESIGN.md K1), each twiddle with one more rounding (<= 6e-8 relative).
+  static constexpr bool LEAN = (LOG2N == 10);
+  static constexpr int NTW = LEAN ? 10 : ((R1 >= 2) ? B1 * (R1 - 1) : 0);
+  static constexpr int NUT = LEAN ? 1 : 16;  // untangle-twiddle slots per lane
   // floats per frame slot (16 B multiple): the padded exchange plane, later |X| (N+1 values + 3 zeros) plus
   // slack that the zero-weight tail of a padded mel band may read
   static constexpr int XB = ((N + N / 32 + 4 + 3) / 4) * 4 + (N >= 256 ? 128 : 32);
@@ -175,11 +196,25 @@ __device__ __forceinline__ void warp_fft(float2 (&z)[32], float* xb, const float
 #pragma unroll
     for (int m = 0; m < 32; ++m) { const int e = l + LPF * m; z[m].y = xb[e + (e >> 5)]; }
     __syncwarp();
+    if constexpr (PL::LEAN) {
+      const float2 w8 = tw[7 * LPF + l], w16 = tw[8 * LPF + l], w24 = tw[9 * LPF + l];
+      z[8] = cmul(z[8], w8); z[16] = cmul(z[16], w16); z[24] = cmul(z[24], w24);
+#pragma unroll
+      for (int b = 1; b < 8; ++b) {
+        const float2 wb = tw[(b - 1) * LPF + l];
+        z[b] = cmul(z[b], wb);
+        z[8 + b] = cmul(cmul(z[8 + b], wb), w8);
+        z[16 + b] = cmul(cmul(z[16 + b], wb), w16);
+        z[24 + b] = cmul(cmul(z[24 + b], wb), w24);
+      }
+    }
 #pragma unroll
     for (int b = 0; b < B1; ++b) {  // pass 1: radix LPF, NS = 32
+      if constexpr (!PL::LEAN) {
 #pragma unroll
-      for (int t = 1; t < R1; ++t)
-        z[b + B1 * t] = cmul(z[b + B1 * t], tw[(b * (R1 - 1) + (t - 1)) * LPF + l]);
+        for (int t = 1; t < R1; ++t)
+          z[b + B1 * t] = cmul(z[b + B1 * t], tw[(b * (R1 - 1) + (t - 1)) * LPF + l]);
+      }
       float2 o[R1];
       DFT<R1, B1>::run(&z[b], o);
 #pragma unroll
@@ -188,20 +223,66 @@ __device__ __forceinline__ void warp_fft(float2 (&z)[32], float* xb, const float
   }
 }
 
-// role-constant tables of the warp FFT: pass-1 twiddles [NTW][LPF] and untangle twiddles [16][LPF]
+// untangle twiddle exp(-i pi (l + LPF m) / N) of lane l, slot m < 16; `u0` = the lane's entry ut[l] (LEAN) -- loaded once
+// per frame by the caller
+template <int LOG2N, int M>
+__device__ __forceinline__ float2 untangle_twiddle(const float2* ut, float2 u0, int l) {
+  using PL = WPlan<LOG2N>;
+  if constexpr (PL::LEAN) {
+    if constexpr (M == 0) {
+      return u0;
+    } else {
+      constexpr float c = cos_pi32(M), sn = cos_pi32(16 - M);  // exp(-i pi M / 32) = c - i sn
+      return fma2(bcast2(u0.x), make_float2(c, -sn), mul2(bcast2(u0.y), make_float2(sn, c)));  // u0 * (c - i sn)
+    }
+  } else {
+    return ut[M * PL::LPF + l];
+  }
+}
+
 template <int LOG2N>
+__device__ __forceinline__ float2 untangle_twiddle_m(const float2* ut, float2 u0, int l, int m) {
+  switch (m) {  // called from fully unrolled loops: m is a compile-time constant after unrolling
+    case 0: return untangle_twiddle<LOG2N, 0>(ut, u0, l);
+    case 1: return untangle_twiddle<LOG2N, 1>(ut, u0, l);
+    case 2: return untangle_twiddle<LOG2N, 2>(ut, u0, l);
+    case 3: return untangle_twiddle<LOG2N, 3>(ut, u0, l);
+    case 4: return untangle_twiddle<LOG2N, 4>(ut, u0, l);
+    case 5: return untangle_twiddle<LOG2N, 5>(ut, u0, l);
+    case 6: return untangle_twiddle<LOG2N, 6>(ut, u0, l);
+    case 7: return untangle_twiddle<LOG2N, 7>(ut, u0, l);
+    case 8: return untangle_twiddle<LOG2N, 8>(ut, u0, l);
+    case 9: return untangle_twiddle<LOG2N, 9>(ut, u0, l);
+    case 10: return untangle_twiddle<LOG2N, 10>(ut, u0, l);
+    case 11: return untangle_twiddle<LOG2N, 11>(ut, u0, l);
+    case 12: return untangle_twiddle<LOG2N, 12>(ut, u0, l);
+    case 13: return untangle_twiddle<LOG2N, 13>(ut, u0, l);
+    case 14: return untangle_twiddle<LOG2N, 14>(ut, u0, l);
+    default: return untangle_twiddle<LOG2N, 15>(ut, u0, l);
+  }
+}
+
+// role-constant tables of the warp FFT: pass-1 twiddles [NTW][LPF] and untangle twiddles [16][LPF]
+// NUT: untangle-twiddle slots to fill (16 = the full table other kernels index directly; WPlan::NUT = the lean form)
+template <int LOG2N, int NUT = 16>
 __device__ __forceinline__ void warp_fft_tables(float2* tw, float2* ut) {
   using PL = WPlan<LOG2N>;
   constexpr int N = PL::N, LPF = PL::LPF, R1 = PL::R1;
   const int tid = threadIdx.x, nt = blockDim.x;
   for (int i = tid; i < PL::NTW * LPF; i += nt) {
     const int slot = i / LPF, ll = i - slot * LPF;
-    const int b = slot / (R1 > 1 ? R1 - 1 : 1), t = slot - b * (R1 > 1 ? R1 - 1 : 1) + 1;
-    float sn, cs;  // W_N^{(ll + LPF b) t}
-    sincospif(-2.0f * (float)((ll + LPF * b) * t) / (float)N, &sn, &cs);
+    int e;  // exponent of W_N
+    if constexpr (PL::LEAN) {
+      e = ll * (slot < 7 ? slot + 1 : 8 * (slot - 6));
+    } else {
+      const int b = slot / (R1 > 1 ? R1 - 1 : 1), t = slot - b * (R1 > 1 ? R1 - 1 : 1) + 1;
+      e = (ll + LPF * b) * t;
+    }
+    float sn, cs;
+    sincospif(-2.0f * (float)e / (float)N, &sn, &cs);
     tw[i] = make_float2(cs, sn);
   }
-  for (int i = tid; i < 16 * LPF; i += nt) {
+  for (int i = tid; i < NUT * LPF; i += nt) {
     const int m = i / LPF, ll = i - m * LPF;
     float sn, cs;  // exp(-i pi (ll + LPF m) / N)
     sincospif(-(float)(ll + LPF * m) / (float)N, &sn, &cs);

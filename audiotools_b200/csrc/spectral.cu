@@ -434,7 +434,7 @@ __global__ void __launch_bounds__(256, 2) spectral_warp_kernel(Params p) {
   // every rounding of the (linear) transform, so the 0.5 factors vanish from the untangle with bit-identical results
   for (int i = tid; i < n_fft; i += 256) win[i] = 0.5f * __ldg(p.window + i);
   for (int i = tid; i < G * p.xb_stride; i += 256) xbs[i] = 0.f;  // the slack behind each |X| slot must stay finite (0 x w)
-  warp_fft_tables<LOG2N>(tw, ut);
+  warp_fft_tables<LOG2N, PL::NUT>(tw, ut);
   // banded mel weights in shared memory.  The projection runs once per tile, AFTER the tile's FFTs, with the
   // work transposed: lane (f, j) of warp w handles frame f (8 at a time) and filter m = 4*(w + 8*i) + j in
   // step i, so one 128-bit weight load is broadcast to 8 frames and the |X| loads of the 8 frames interleave
@@ -540,6 +540,7 @@ __global__ void __launch_bounds__(256, 2) spectral_warp_kernel(Params p) {
       warp_fft<LOG2N, true>(z, xb, tw, l);  // z[m] = Z[l + LPF m]
 
       // ---- untangle -> real-FFT bins k = l + LPF m (m < 16) and N - k ; magnitudes into xb
+      const float2 u0 = ut[l];  // exp(-i pi l / N): the lane's base untangle twiddle (the only table entry when lean)
       float2* so = (DIRECT && p.stft_out) ? p.stft_out + (size_t)row * F * p.n_frames + n : nullptr;
 #pragma unroll
       for (int m = 0; m < 16; ++m) {
@@ -552,7 +553,7 @@ __global__ void __launch_bounds__(256, 2) spectral_warp_kernel(Params p) {
         const float2 xe = add2(zk, make_float2(zn.x, -zn.y));               // (Zk + conj Zn)/2   (window halved above)
         const float2 xo = add2(make_float2(zk.y, -zk.x), make_float2(zn.y, zn.x));  // (Zk - conj Zn)/(2i)
         // X[k] = Xe + W Xo, X[N-k]* = Xe - W Xo: a twiddled butterfly, fused like the ones of the transform
-        const float2 w = ut[m * LPF + l];
+        const float2 w = untangle_twiddle_m<LOG2N>(ut, u0, l, m);
         const float2 xk = fma2(bcast2(w.x), xo, fma2(make_float2(-w.y, w.y), make_float2(xo.y, xo.x), xe));
         const float2 d = fma2(bcast2(2.0f), xe, neg2(xk));
         if constexpr (STAGED) {  // park the complex bins in the frame's own slot (the exchange plane is dead now)
@@ -693,7 +694,7 @@ static int launch_warp(Params& p, void* stream) {
   int o = align16(p.span * 4);
   p.off_win = o; o = align16(o + p.n_fft * 4);
   p.off_tw = o; o = align16(o + PL::NTW * PL::LPF * 8 + 16);
-  p.off_ut = o; o = align16(o + 16 * PL::LPF * 8);
+  p.off_ut = o; o = align16(o + PL::NUT * PL::LPF * 8);
   // STFT-only launches park the complex frame (N+1 float2) in the frame's slot and write it out transposed; that
   // needs 2N+4 floats per slot instead of XB -- only if two CTAs per SM still fit
   p.xb_stride = PL::XB;

@@ -79,6 +79,7 @@ SIGNATURES = {
                                    c_void_p, c_void_p]),
     "b2a_mel_from_stft_f32": (c_int, [c_void_p, c_int64, c_int, c_int64, c_void_p, c_void_p, c_void_p, c_int, c_int,
                                       c_float, c_float, c_void_p, c_void_p]),
+    "b2a_mel_dct_f32": (c_int, [c_void_p, c_int64, c_int, c_int64, c_void_p, c_int, c_void_p, c_void_p]),
     "b2a_istft_dense_workspace_bytes": (c_size_t, [c_int64, c_int64, c_int]),
     "b2a_istft_dense_f32": (c_int, [c_void_p, c_int64, c_int64, c_int, c_int, c_void_p, c_void_p, c_int, c_int64,
                                     c_int64, c_void_p, c_void_p, c_size_t, c_void_p]),

@@ -535,7 +535,7 @@ class AudioSignal(EffectMixin, LoudnessMixin, ImpulseResponseMixin, DSPMixin):
         logmel = self._spectral(args, want_stft=False, mel_fb=fb, mel_lo=lo, mel_hi=hi, post=_lib.POST_LN,
                                 post_eps=log_offset)["mel"]
         dct = self.get_dct(n_mfcc, n_mels, "ortho", self.device)
-        return (logmel.transpose(-1, -2) @ dct).transpose(-1, -2)
+        return _engine().mel_dct(logmel, dct)
 
     @property
     def magnitude(self):

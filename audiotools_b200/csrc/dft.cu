@@ -189,6 +189,40 @@ __global__ void __launch_bounds__(256) mel_from_stft_kernel(const float2* __rest
 }
 
 // ---------------------------------------------------------------------------------------------
+// mfcc: out[row][j][n] = sum_m dct[m][j] * logmel[row][m][n]   (ref:audiotools/core/audio_signal.py:1420-1426:
+// `mel_spectrogram.transpose(-1, -2) @ create_dct(n_mfcc, n_mels, "ortho")` transposed back: a cuBLAS batched GEMM there).
+// lane = frame (coalesced along n), each thread keeps up to 32 coefficients in registers, the DCT basis in shared memory.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) mel_dct_kernel(const float* __restrict__ logmel, const float* __restrict__ dct,
+                                                      int n_mels, int n_mfcc, int n_frames, float* __restrict__ out) {
+  B2A_DYN_SMEM(smem);
+  float* sd = reinterpret_cast<float*>(smem);  // [n_mels][n_mfcc]
+  for (int i = threadIdx.x; i < n_mels * n_mfcc; i += blockDim.x) sd[i] = __ldg(dct + i);
+  __syncthreads();
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  const int row = blockIdx.y;
+  if (n >= n_frames) return;
+  const float* in = logmel + (size_t)row * n_mels * (size_t)n_frames + n;
+  float* o = out + (size_t)row * n_mfcc * (size_t)n_frames + n;
+  for (int j0 = 0; j0 < n_mfcc; j0 += 32) {
+    float acc[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) acc[j] = 0.f;
+    const int nj = min(32, n_mfcc - j0);
+    for (int m = 0; m < n_mels; ++m) {
+      const float v = in[(size_t)m * n_frames];
+      const float* d = sd + m * n_mfcc + j0;
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        if (j < nj) acc[j] = fmaf(v, d[j], acc[j]);
+    }
+#pragma unroll
+    for (int j = 0; j < 32; ++j)
+      if (j < nj) o[(size_t)(j0 + j) * n_frames] = acc[j];
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 // inverse: frames[row][f][n] = sum_k spec[row][k][f].re Mi[k][n].x + spec[row][k][f].im Mi[k][n].y  (window applied)
 // ---------------------------------------------------------------------------------------------
 struct InvParams {
@@ -393,6 +427,19 @@ extern "C" int b2a_istft_dense_f32(const float* spec, int64_t rows, int64_t n_fr
   B2A_LAUNCH(fold_kernel, dim3((unsigned)(want < 2048 ? want : 2048), (unsigned)rows), dim3(256), 0, stream,
              (const float*)p.frames, window, (int)n_frames, n_fft, hop, pad_frames, (long long)start, (long long)out_len,
              expected, out);
+  B2A_CUDA_OK(cudaGetLastError());
+  return B2A_OK;
+}
+
+extern "C" int b2a_mel_dct_f32(const float* logmel, int64_t rows, int n_mels, int64_t n_frames, const float* dct, int n_mfcc,
+                               float* out, void* stream) {
+  B2A_REQUIRE(logmel && dct && out, B2A_E_INVALID, "mel_dct: null pointer");
+  B2A_REQUIRE(rows >= 1 && rows <= 65535 && n_mels >= 1 && n_mfcc >= 1 && n_frames >= 1, B2A_E_INVALID, "mel_dct: bad shape");
+  const size_t smem = (size_t)n_mels * n_mfcc * sizeof(float);
+  B2A_REQUIRE(smem <= 200 * 1024, B2A_E_UNSUPPORTED, "mel_dct: %d x %d basis does not fit shared memory", n_mels, n_mfcc);
+  B2A_CUDA_OK(cudaFuncSetAttribute(mel_dct_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  B2A_LAUNCH(mel_dct_kernel, dim3((unsigned)((n_frames + 127) / 128), (unsigned)rows), dim3(128), smem, stream, logmel, dct,
+             n_mels, n_mfcc, (int)n_frames, out);
   B2A_CUDA_OK(cudaGetLastError());
   return B2A_OK;
 }

@@ -563,6 +563,20 @@ class Engine:
             self.launches += 1
         return {"stft": stft if want_stft else None, "mel": mel, "scaled": scaled if want_scaled else None}
 
+    def mel_dct(self, logmel: torch.Tensor, dct: torch.Tensor) -> torch.Tensor:
+        """``(logmel.transpose(-1, -2) @ dct).transpose(-1, -2)`` for logmel [B, C, n_mels, N], dct [n_mels, n_mfcc]
+        (ref:audiotools/core/audio_signal.py:1420-1426) as one launch of csrc/dft.cu (no library GEMM)."""
+        logmel = self._prep(logmel, "logmel")
+        B, C, n_mels, N = logmel.shape
+        dct = self._prep(dct.to(logmel.device), "dct")
+        assert dct.shape[0] == n_mels, (dct.shape, n_mels)
+        n_mfcc = dct.shape[1]
+        out = torch.empty(B, C, n_mfcc, N, dtype=torch.float32, device=logmel.device)
+        rc = self.lib.b2a_mel_dct_f32(_dptr(logmel), B * C, n_mels, N, _dptr(dct), n_mfcc, _dptr(out), self._stream(logmel))
+        self.lib.check(rc)
+        self.launches += 1
+        return out
+
     # ------------------------------------------------------------------ FIR / convolution
     def _bypass(self, bypass, n: int, device):
         """[n] int32 device flags (non-zero = leave the rows of this filter / item untouched) or None."""

@@ -114,6 +114,10 @@ int b2a_stft_dense_f32(const float* x, int64_t rows, int64_t T, int n_fft, int h
 int b2a_mel_from_stft_f32(const float* stft, int64_t rows, int F, int64_t n_frames, const float* mel_fb,
                           const int32_t* mel_lo, const int32_t* mel_hi, int n_mels, int post, float post_eps,
                           float post_power, float* mel_out, void* stream);
+/* AudioSignal.mfcc's `log-mel^T @ create_dct(n_mfcc, n_mels, "ortho")` (audio_signal.py:1420-1426):
+ * out[row][j][n] = sum_m dct[m][j] * logmel[row][m][n];  logmel [rows, n_mels, n_frames], dct [n_mels, n_mfcc] row-major. */
+int b2a_mel_dct_f32(const float* logmel, int64_t rows, int n_mels, int64_t n_frames, const float* dct, int n_mfcc,
+                    float* out, void* stream);
 size_t b2a_istft_dense_workspace_bytes(int64_t rows, int64_t n_frames, int n_fft);
 int b2a_istft_dense_f32(const float* spec, int64_t rows, int64_t n_frames, int n_fft, int hop, const float* window,
                         const float* imatrix, int pad_frames, int64_t start, int64_t out_len, float* out, void* ws,

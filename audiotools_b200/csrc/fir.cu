@@ -12,7 +12,9 @@
 // One CTA = 256 threads x 8 consecutive outputs.  The input span of the tile is staged once in shared
 // memory, de-interleaved by phase p = (sample index) mod stride so that for each phase the thread slides an
 // 8+8 register window over a unit-stride stream: per 8 taps, 8 new samples and 8 (broadcast) taps are loaded
-// for 64 FMAs.  Streams are padded 1 word per 32 so that the 8-word lane stride is bank-conflict free.
+// for 64 FMAs -- as FOUR 128-bit shared loads (two for the samples, two broadcast ones for the taps).  Streams are padded
+// 4 words per 32 so that the 8-word lane stride is 16 B aligned and conflict free for 128-bit accesses (a quarter warp
+// covers word offsets 0, 8, 16, 24, 36, 44, 52, 60: eight distinct 4-word bank groups).
 #include "b2a_common.h"
 
 namespace b2a {
@@ -22,7 +24,7 @@ constexpr int THREADS = 256;
 constexpr int R = 8;                  // outputs per thread
 constexpr int TILE = THREADS * R;     // outputs per CTA
 
-__device__ __forceinline__ int pad32(int n) { return n + (n >> 5); }
+__device__ __forceinline__ int pad32(int n) { return n + ((n >> 5) << 2); }
 
 struct Params {
   const float* x;
@@ -59,22 +61,30 @@ __global__ void __launch_bounds__(THREADS) fir_direct_kernel(Params p) {
     return;
   }
   // ---- stage the span, phase-de-interleaved
-  const int span = p.np * S;
-  for (int i = tid; i < span; i += THREADS) {
-    int64_t u = j0 + i;
-    float v;
-    if (u >= 0 && u < p.T) v = __ldg(xr + u);
-    else if (p.pad_mode == B2A_PAD_REPLICATE) v = __ldg(xr + (u < 0 ? 0 : p.T - 1));
-    else v = 0.f;
-    const int ph = i % S, n = i / S;
-    xs[ph * p.sp + pad32(n)] = v;
+  // (phase-major loops: no integer division per sample; the S phases read the same cache lines back to back)
+  const bool inside = (j0 >= 0) && (j0 + (int64_t)p.np * S <= (int64_t)p.T);  // CTA-uniform: no padding in this tile
+  for (int ph = 0; ph < S; ++ph) {
+    float* dst = xs + ph * p.sp;
+    if (inside) {
+      const float* src = xr + j0 + ph;
+      for (int n = tid; n < p.np; n += THREADS) dst[pad32(n)] = __ldg(src + (size_t)n * S);
+    } else {
+      for (int n = tid; n < p.np; n += THREADS) {
+        const int64_t u = j0 + (int64_t)n * S + ph;
+        float v;
+        if (u >= 0 && u < p.T) v = __ldg(xr + u);
+        else if (p.pad_mode == B2A_PAD_REPLICATE) v = __ldg(xr + (u < 0 ? 0 : p.T - 1));
+        else v = 0.f;
+        dst[pad32(n)] = v;
+      }
+    }
   }
   const float* tr = p.taps + (size_t)f * p.K;
-  for (int i = tid; i < S * p.qmax; i += THREADS) {
-    const int ph = i / p.qmax, q = i - ph * p.qmax;
-    const int k = q * S + ph;
-    tp[i] = (k < p.K) ? __ldg(tr + k) : 0.f;
-  }
+  for (int ph = 0; ph < S; ++ph)
+    for (int q = tid; q < p.qmax; q += THREADS) {
+      const int k = q * S + ph;
+      tp[ph * p.qmax + q] = (k < p.K) ? __ldg(tr + k) : 0.f;
+    }
   __syncthreads();
 
   float acc[R];
@@ -85,16 +95,22 @@ __global__ void __launch_bounds__(THREADS) fir_direct_kernel(Params p) {
     const float* s = xs + ph * p.sp;
     const float* t = tp + ph * p.qmax;
     float w[2 * R];
-#pragma unroll
-    for (int j = 0; j < R; ++j) w[j] = s[pad32(ml + j)];
+    {  // ml is a multiple of 8: its 8 samples are two aligned float4s inside one padded 32-group
+      const float4 a = *reinterpret_cast<const float4*>(s + pad32(ml)), b = *reinterpret_cast<const float4*>(s + pad32(ml) + 4);
+      w[0] = a.x; w[1] = a.y; w[2] = a.z; w[3] = a.w; w[4] = b.x; w[5] = b.y; w[6] = b.z; w[7] = b.w;
+    }
     for (int q0 = 0; q0 < p.qmax; q0 += R) {
-#pragma unroll
-      for (int j = 0; j < R; ++j) w[R + j] = s[pad32(ml + q0 + R + j)];
+      {
+        const float* sn = s + pad32(ml + q0 + R);
+        const float4 a = *reinterpret_cast<const float4*>(sn), b = *reinterpret_cast<const float4*>(sn + 4);
+        w[R] = a.x; w[R + 1] = a.y; w[R + 2] = a.z; w[R + 3] = a.w; w[R + 4] = b.x; w[R + 5] = b.y; w[R + 6] = b.z; w[R + 7] = b.w;
+      }
+      const float4 h0 = *reinterpret_cast<const float4*>(t + q0), h1 = *reinterpret_cast<const float4*>(t + q0 + 4);
+      const float h[R] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
 #pragma unroll
       for (int u = 0; u < R; ++u) {
-        const float h = t[q0 + u];
 #pragma unroll
-        for (int r = 0; r < R; ++r) acc[r] = fmaf(h, w[u + r], acc[r]);
+        for (int r = 0; r < R; ++r) acc[r] = fmaf(h[u], w[u + r], acc[r]);
       }
 #pragma unroll
       for (int j = 0; j < R; ++j) w[j] = w[R + j];
@@ -120,7 +136,7 @@ extern "C" int b2a_fir_direct_supported(int64_t T, int K, int stride) {
   if (K < 1 || stride < 1 || T < 1 || T >= ((int64_t)1 << 30)) return 0;
   const int qmax = (((K + stride - 1) / stride) + R - 1) / R * R;
   const int np = TILE + qmax + R;
-  const int sp = np + (np >> 5) + 1;
+  const int sp = ((np + ((np >> 5) << 2) + 4 + 3) / 4) * 4;
   const size_t bytes = (size_t)stride * sp * 4 + (size_t)stride * qmax * 4;
   return bytes <= 160 * 1024;
 }
@@ -147,7 +163,7 @@ extern "C" int b2a_fir_direct_f32(const float* x, int64_t rows, int64_t T, const
   p.pad_mode = pad_mode; p.subtract = subtract_from_input; p.out_len = out_len;
   p.qmax = (((K + stride - 1) / stride) + R - 1) / R * R;
   p.np = TILE + p.qmax + R;
-  p.sp = p.np + (p.np >> 5) + 1;
+  p.sp = ((p.np + ((p.np >> 5) << 2) + 4 + 3) / 4) * 4;
   p.off_taps = stride * p.sp * 4;
   const size_t smem = (size_t)p.off_taps + (size_t)stride * p.qmax * 4;
   const int64_t tiles = (out_len + TILE - 1) / TILE;

@@ -227,8 +227,8 @@ def main():
         macs = B * nfr * 400 * 201  # complex-real multiply-accumulates = FFMA2 instructions x 32 lanes
         emit({"config": "dense DFT 64 x 1ch x 10s@16k window 400 hop 160 (+ 80-mel log-mel, inverse)", "ms_stft": ms_stft,
               "ms_logmel": ms_mel, "ms_istft": ms_inv, "ms_torch_stft_cufft": ms_torch, "clips_per_s": B / ms_mel * 1e3,
-              "gflops_stft": 4 * macs / ms_stft / 1e6, "fp32_peak_gflops": 2 * 148 * 128 * 1965.0,
-              "frac_of_fp32_peak": 4 * macs / ms_stft / 1e6 / (2 * 148 * 128 * 1965.0)})
+              "gflops_stft": 4 * macs / ms_stft / 1e6, "fp32_peak_gflops": 2 * 148 * 128 * 1.965,
+              "frac_of_fp32_peak": 4 * macs / ms_stft / 1e6 / (2 * 148 * 128 * 1.965)})
 
     if "gate" in only:  # SpectralGate (csrc/specmask.cu) at 64 x 2ch x 10 s: stft x2 + gate + istft
         from audiotools_b200.ml.layers import SpectralGate

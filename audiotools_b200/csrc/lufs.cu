@@ -616,7 +616,7 @@ kweight_energy_warp_kernel(const float* __restrict__ x, int rows, int T, int Tp,
       // ---- zero-state end state of the lane's chunk as a linear map of its 66 inputs
       float g[D];
 #pragma unroll
-      for (int i = 0; i < D; ++i) g[i] = fmaf(s_wa[0][i], h0, s_wa[1][i] * h1);
+      for (int i = 0; i < D; ++i) g[i] = fmaf(tbv.Wa[0][i], h0, tbv.Wa[1][i] * h1);
 #pragma unroll
       for (int i4 = 0; i4 < L2 / 4; ++i4) {
         const float4 q = c4[i4];
@@ -624,7 +624,7 @@ kweight_energy_warp_kernel(const float* __restrict__ x, int rows, int T, int Tp,
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
 #pragma unroll
-          for (int i = 0; i < D; ++i) g[i] = fmaf(s_wa[2 + 4 * i4 + e][i], qs[e], g[i]);
+          for (int i = 0; i < D; ++i) g[i] = fmaf(tbv.Wa[2 + 4 * i4 + e][i], qs[e], g[i]);  // constant-bank operand
         }
       }
 #pragma unroll

@@ -634,7 +634,7 @@ kweight_energy_warp_kernel(const float* __restrict__ x, int rows, int T, int Tp,
         for (int j = 0; j < D; ++j) o[j] = __shfl_up_sync(0xffffffffu, g[j], 1u << k);
         if (lane >= (1 << k)) {
 #pragma unroll
-          for (int i = 0; i < D; ++i) g[i] += row_dot<D>(s_mscan[k], i, o);
+          for (int i = 0; i < D; ++i) g[i] += row_dot<D>(tbv.Mscan[k], i, o);  // (k is unrolled: constant-bank operands)
         }
       }
       float ex[D], agg[D];
@@ -722,7 +722,7 @@ kweight_energy_warp_kernel(const float* __restrict__ x, int rows, int T, int Tp,
       // ---- carry into the next segment: A^SEG carry + (zero-state end state of this segment)
       float cn[D];
 #pragma unroll
-      for (int i = 0; i < D; ++i) cn[i] = agg[i] + row_dot<D>(s_mseg, i, carry);
+      for (int i = 0; i < D; ++i) cn[i] = agg[i] + row_dot<D>(tbv.Mseg, i, carry);
 #pragma unroll
       for (int i = 0; i < D; ++i) carry[i] = cn[i];
       __syncwarp();  // every lane is done with this window before it is refilled

@@ -31,6 +31,20 @@ def _digest(files):
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
+    """Build (if stale) and return the path of libb2a.so.  Safe to call from several processes at once (the ranks of a
+    torchrun launch, the two ranks of a gloo test): an exclusive file lock serialises the builders and the library is
+    moved into place atomically, so a concurrent importer never sees a half-written file."""
+    import fcntl
+
+    with open(os.path.join(CSRC, ".build.lock"), "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            return _build_locked(force, verbose)
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
+
+
+def _build_locked(force: bool, verbose: bool) -> str:
     srcs = sorted(glob.glob(os.path.join(CSRC, "*.cu")))
     deps = srcs + sorted(glob.glob(os.path.join(CSRC, "*.h"))) + sorted(glob.glob(os.path.join(CSRC, "*.cuh"))) + [
         os.path.join(os.path.dirname(HERE), "include", "b2a.h")]
@@ -51,8 +65,10 @@ def build(force: bool = False, verbose: bool = False) -> str:
         out, _ = p.communicate()
         if p.returncode != 0:
             raise RuntimeError(f"nvcc failed on {s}:\n{out.decode()}")
-    cmd = [nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", OUT] + objs
+    tmp = OUT + ".tmp.%d" % os.getpid()
+    cmd = [nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", tmp] + objs
     subprocess.check_call(cmd)
+    os.replace(tmp, OUT)
     with open(stamp, "w") as f:
         f.write(dig)
     return OUT

@@ -22,6 +22,20 @@ def _digest(files):
 
 
 def build(verbose=False):
+    """Build (if stale) the simulator library; serialised by a file lock and moved into place atomically, so that the
+    two ranks of a gloo test (or pytest-xdist workers) can call it at the same time."""
+    import fcntl
+
+    os.makedirs(OUT_DIR, exist_ok=True)
+    with open(os.path.join(OUT_DIR, ".lock"), "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            return _build_locked(verbose)
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
+
+
+def _build_locked(verbose=False):
     os.makedirs(OUT_DIR, exist_ok=True)
     srcs = sorted(glob.glob(os.path.join(CSRC, "*.cu")))
     deps = srcs + glob.glob(os.path.join(CSRC, "*.h")) + glob.glob(os.path.join(CSRC, "*.cuh")) + [os.path.join(HERE, "cusim.h"),
@@ -44,7 +58,9 @@ def build(verbose=False):
         out, _ = p.communicate()
         if p.returncode != 0:
             raise RuntimeError(f"cusim compile of {s} failed:\n{out.decode()}")
-    subprocess.check_call(["g++", "-shared", "-pthread", "-o", OUT] + objs)
+    tmp = OUT + ".tmp.%d" % os.getpid()
+    subprocess.check_call(["g++", "-shared", "-pthread", "-o", tmp] + objs)
+    os.replace(tmp, OUT)
     with open(stamp, "w") as f:
         f.write(dig)
     return OUT

@@ -166,6 +166,7 @@ __device__ __forceinline__ void rec_store(unsigned long long* p, float v) {
 }
 __device__ __forceinline__ unsigned long long rec_load(const unsigned long long* p) {
 #ifdef B2A_SIM
+  cusim::yield();  // polled in spin loops: let the other fibers of the block (and the scheduler) run
   return __atomic_load_n(p, __ATOMIC_ACQUIRE);
 #else
   unsigned long long w;

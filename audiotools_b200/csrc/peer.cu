@@ -41,6 +41,7 @@ __device__ __forceinline__ void st_release_sys(int* p, int v) {
 }
 __device__ __forceinline__ int ld_acquire_sys(const int* p) {
 #ifdef B2A_SIM
+  cusim::yield();  // polled in spin loops
   return __atomic_load_n(p, __ATOMIC_ACQUIRE);
 #else
   int v;

@@ -63,7 +63,7 @@ __host__ __device__ __forceinline__ int pad_idx(int i) { return i + 4 * (i >> 9)
 // a plain loop over the same shared-memory bytes, so that the kernel's indexing is checked before any GPU time.
 // ---------------------------------------------------------------------------------------------
 #ifdef B2A_SIM
-static uint32_t g_tmem[128][TM_COLS];
+static thread_local uint32_t g_tmem[128][TM_COLS];  // per simulator worker = per block in flight
 static inline float h2f(uint16_t h) { _Float16 v; memcpy(&v, &h, 2); return (float)v; }
 static inline uint16_t f2h(float f) { _Float16 v = (_Float16)f; uint16_t h; memcpy(&h, &v, 2); return h; }
 #endif

@@ -3,9 +3,10 @@
 // The build container has nvcc but no GPU.  To check kernel indexing and arithmetic
 // before spending GPU minutes, tests/cusim/build_sim.py compiles the product's .cu
 // sources with g++ (-x c++ -DB2A_SIM -include cusim.h) into tests/cusim/_build/libb2a_sim.so.
-// Every CUDA thread of a block runs as a real host thread; __syncthreads / named
-// barriers are std::barrier; warp shuffles go through a per-warp exchange slot;
-// blocks of a launch run one after another.  Device pointers are host pointers.
+// Every CUDA thread of a block runs as a FIBER (its own stack, cooperative scheduling on one
+// worker thread per block in flight); __syncthreads / named barriers / __syncwarp are
+// cooperative barriers; warp shuffles go through a per-warp exchange slot; the blocks of a
+// launch are handed out in order to up to 8 worker threads.  Device pointers are host pointers.
 //
 // Nothing under audiotools_b200/ loads this library: it exists so that the *same kernel
 // source* that ships can be executed here and compared with the oracle (tests/test_sim_*.py).
@@ -25,6 +26,8 @@
 #include <mutex>
 #include <thread>
 #include <vector>
+#include <array>
+#include <sys/mman.h>
 
 #define __global__
 #define __device__
@@ -33,7 +36,7 @@
 #define __noinline__ __attribute__((noinline))
 #define __restrict__ __restrict
 #define __launch_bounds__(...)
-#define __shared__ static
+#define __shared__ static thread_local
 #define __align__(n) __attribute__((aligned(n)))
 
 struct uint3 { unsigned x, y, z; };
@@ -77,67 +80,144 @@ static inline cudaError_t cudaDeviceGetAttribute(int* v, cudaDeviceAttr, int) { 
 
 namespace cusim {
 
-struct BlockCtx {
-  unsigned nthreads = 0;
-  std::unique_ptr<std::barrier<>> all;
-  std::mutex mu;
-  std::map<std::pair<int, int>, std::unique_ptr<std::barrier<>>> named;
-  std::vector<std::unique_ptr<std::barrier<>>> warp_bar;
+// ---------------------------------------------------------------------------------------------
+// Execution model.  The CUDA threads of a block are FIBERS (user-level contexts with their own stacks) that one OS
+// worker thread schedules round-robin; __syncthreads / named barriers / __syncwarp / shuffles are cooperative
+// barriers (a waiting fiber yields).  The blocks of a launch are handed out IN ORDER to up to 8 worker threads, so a
+// block that spins on a flag of an earlier block (decoupled look-back) always finds its predecessor running.
+// `__shared__` is `static thread_local`: one copy per worker, i.e. per block in flight.
+// (The first version ran every CUDA thread as an OS thread with std::barrier: 256 threads on 8 cores spent four
+//  fifths of the suite's time in futex calls.)
+// ---------------------------------------------------------------------------------------------
+struct TL { uint3 tid, bid; dim3 bdim, gdim; };
+struct Bar { unsigned count = 0, gen = 0; };
+struct Fiber { void* sp = nullptr; TL tl; bool done = false; };
+
+struct Worker {
+  unsigned nthreads = 0, cur = 0;
+  std::vector<Fiber> fib;
+  char* stacks = nullptr;
+  size_t stack_bytes = 0;
+  void* sched_sp = nullptr;
+  Bar all;
+  std::vector<Bar> warp_bar;
+  std::map<std::pair<int, int>, Bar> named;
   std::vector<std::array<unsigned long long, 32>> warp_slot;
   unsigned char* dyn_smem = nullptr;
+  void (*invoke)(void*) = nullptr;
+  void* body = nullptr;
 };
-inline BlockCtx*& ctx() { static BlockCtx* c = nullptr; return c; }
+inline Worker*& ctx() { static thread_local Worker* w = nullptr; return w; }
 inline std::mutex& atomic_mu() { static std::mutex m; return m; }
+inline TL& tl() { Worker* w = ctx(); return w->fib[w->cur].tl; }
 
-struct TL { uint3 tid, bid; dim3 bdim, gdim; };
-inline TL& tl() { static thread_local TL t; return t; }
+extern "C" void cusim_switch(void** save_sp, void* load_sp);
+// x86-64 System V: callee-saved registers on the old stack, swap stack pointers, restore, return into the new context
+__asm__(
+    ".text\n"
+    ".weak cusim_switch\n"
+    ".type cusim_switch,@function\n"
+    "cusim_switch:\n"
+    "  pushq %rbp\n  pushq %rbx\n  pushq %r12\n  pushq %r13\n  pushq %r14\n  pushq %r15\n"
+    "  movq %rsp, (%rdi)\n"
+    "  movq %rsi, %rsp\n"
+    "  popq %r15\n  popq %r14\n  popq %r13\n  popq %r12\n  popq %rbx\n  popq %rbp\n"
+    "  ret\n"
+    ".size cusim_switch,.-cusim_switch\n");
 
-inline void named_bar(int id, int n) {
-  BlockCtx* c = ctx();
-  std::barrier<>* b;
-  {
-    std::lock_guard<std::mutex> g(c->mu);
-    auto& slot = c->named[{id, n}];
-    if (!slot) slot.reset(new std::barrier<>(n));
-    b = slot.get();
+// back to the worker's scheduler loop; resumed later at this point
+inline void yield() {
+  Worker* w = ctx();
+  cusim_switch(&w->fib[w->cur].sp, w->sched_sp);
+}
+inline void bar_wait(Bar& b, unsigned n) {
+  const unsigned gen = b.gen;
+  if (++b.count >= n) { b.count = 0; ++b.gen; return; }
+  while (b.gen == gen) yield();
+}
+inline void named_bar(int id, int n) { bar_wait(ctx()->named[{id, n}], (unsigned)n); }
+
+inline void fiber_main() {
+  Worker* w = ctx();
+  w->invoke(w->body);
+  w = ctx();
+  w->fib[w->cur].done = true;
+  cusim_switch(&w->fib[w->cur].sp, w->sched_sp);
+  abort();  // a finished fiber is never resumed
+}
+
+inline void run_block(Worker* w, uint3 bid, dim3 block, dim3 grid) {
+  const unsigned nt = w->nthreads;
+  w->all = Bar();
+  for (auto& b : w->warp_bar) b = Bar();
+  w->named.clear();
+  for (unsigned t = 0; t < nt; ++t) {
+    Fiber& f = w->fib[t];
+    f.done = false;
+    f.tl.bdim = block; f.tl.gdim = grid; f.tl.bid = bid;
+    f.tl.tid = uint3{t % block.x, (t / block.x) % block.y, t / (block.x * block.y)};
+    uintptr_t top = ((uintptr_t)(w->stacks + (size_t)(t + 1) * w->stack_bytes)) & ~(uintptr_t)15;
+    void** sp = (void**)top;
+    *--sp = nullptr;                 // fake return address of fiber_main (keeps the ABI's entry alignment)
+    *--sp = (void*)&fiber_main;      // `ret` of the first switch jumps here
+    for (int r = 0; r < 6; ++r) *--sp = nullptr;  // rbp rbx r12 r13 r14 r15
+    f.sp = sp;
   }
-  b->arrive_and_wait();
+  unsigned alive = nt;
+  while (alive) {
+    for (unsigned t = 0; t < nt; ++t) {
+      if (w->fib[t].done) continue;
+      w->cur = t;
+      cusim_switch(&w->sched_sp, w->fib[t].sp);
+      if (w->fib[t].done) --alive;
+    }
+  }
 }
 
 template <class Body>
 void launch(dim3 grid, dim3 block, size_t smem_bytes, Body body) {
-  unsigned nt = block.x * block.y * block.z;
-  BlockCtx c;
-  c.nthreads = nt;
-  c.all.reset(new std::barrier<>(nt));
-  unsigned nwarps = (nt + 31) / 32;
-  for (unsigned w = 0; w < nwarps; ++w) {
-    unsigned lanes = std::min(32u, nt - w * 32);
-    c.warp_bar.emplace_back(new std::barrier<>(lanes));
+  const unsigned nt = block.x * block.y * block.z;
+  const unsigned long long nblocks = (unsigned long long)grid.x * grid.y * grid.z;
+  if (nt == 0 || nblocks == 0) return;
+  unsigned nw = std::thread::hardware_concurrency();
+  if (nw == 0) nw = 4;
+  if (nw > 8) nw = 8;
+  if (nw > nblocks) nw = (unsigned)nblocks;
+  std::atomic<unsigned long long> next{0};
+  auto invoke = +[](void* b) { (*static_cast<Body*>(b))(); };
+  auto work = [&]() {
+    Worker w;
+    w.nthreads = nt;
+    w.fib.resize(nt);
+    w.warp_bar.resize((nt + 31) / 32);
+    w.warp_slot.resize((nt + 31) / 32);
+    w.stack_bytes = 256 * 1024;
+    const size_t total = (size_t)nt * w.stack_bytes + 64;
+    w.stacks = (char*)mmap(nullptr, total, PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS | MAP_NORESERVE, -1, 0);
+    if (w.stacks == (char*)MAP_FAILED) { fprintf(stderr, "cusim: mmap of fiber stacks failed\n"); abort(); }
+    std::vector<unsigned char> smem(smem_bytes + 1024);
+    w.dyn_smem = (unsigned char*)(((uintptr_t)smem.data() + 1023) & ~(uintptr_t)1023);
+    w.invoke = invoke;
+    w.body = &body;
+    Worker* prev = ctx();
+    ctx() = &w;
+    for (;;) {
+      const unsigned long long b = next.fetch_add(1);
+      if (b >= nblocks) break;
+      const unsigned bx = (unsigned)(b % grid.x), by = (unsigned)((b / grid.x) % grid.y);
+      const unsigned bz = (unsigned)(b / ((unsigned long long)grid.x * grid.y));
+      run_block(&w, uint3{bx, by, bz}, block, grid);
+    }
+    ctx() = prev;
+    munmap(w.stacks, total);
+  };
+  if (nw <= 1) {
+    work();
+  } else {
+    std::vector<std::thread> th;
+    for (unsigned i = 0; i < nw; ++i) th.emplace_back(work);
+    for (auto& t : th) t.join();
   }
-  c.warp_slot.resize(nwarps);
-  std::vector<unsigned char> smem(smem_bytes + 1024);
-  c.dyn_smem = (unsigned char*)(((uintptr_t)smem.data() + 1023) & ~(uintptr_t)1023);
-  ctx() = &c;
-  std::vector<std::thread> th;
-  th.reserve(nt);
-  for (unsigned t = 0; t < nt; ++t) {
-    th.emplace_back([&, t] {
-      TL& L = tl();
-      L.bdim = block;
-      L.gdim = grid;
-      L.tid = uint3{t % block.x, (t / block.x) % block.y, t / (block.x * block.y)};
-      for (unsigned bz = 0; bz < grid.z; ++bz)
-        for (unsigned by = 0; by < grid.y; ++by)
-          for (unsigned bx = 0; bx < grid.x; ++bx) {
-            L.bid = uint3{bx, by, bz};
-            body();
-            c.all->arrive_and_wait();  // static __shared__ storage is reused by the next block
-          }
-    });
-  }
-  for (auto& x : th) x.join();
-  ctx() = nullptr;
 }
 
 }  // namespace cusim
@@ -148,11 +228,14 @@ void launch(dim3 grid, dim3 block, size_t smem_bytes, Body body) {
 #define gridDim (cusim::tl().gdim)
 #define warpSize 32
 
-static inline void __syncthreads() { cusim::ctx()->all->arrive_and_wait(); }
+static inline void __syncthreads() { cusim::bar_wait(cusim::ctx()->all, cusim::ctx()->nthreads); }
+static inline unsigned cusim_warp_lanes(unsigned w) { return std::min(32u, cusim::ctx()->nthreads - w * 32); }
+static inline void cusim_warp_sync(unsigned w) { cusim::bar_wait(cusim::ctx()->warp_bar[w], cusim_warp_lanes(w)); }
 static inline void __syncwarp(unsigned = 0xffffffffu) {
   unsigned t = threadIdx.x + threadIdx.y * blockDim.x;
-  cusim::ctx()->warp_bar[t / 32]->arrive_and_wait();
+  cusim_warp_sync(t / 32);
 }
+static inline void __nanosleep(unsigned) { cusim::yield(); }
 static inline void __threadfence() { std::atomic_thread_fence(std::memory_order_seq_cst); }
 static inline void __threadfence_block() { std::atomic_thread_fence(std::memory_order_seq_cst); }
 
@@ -164,9 +247,9 @@ template <class T> static inline T cusim_shfl(T v, int src_lane) {
   unsigned long long raw = 0;
   memcpy(&raw, &v, sizeof(T));
   c->warp_slot[w][lane] = raw;
-  c->warp_bar[w]->arrive_and_wait();
+  cusim_warp_sync(w);
   unsigned long long r = c->warp_slot[w][(unsigned)src_lane & 31u];
-  c->warp_bar[w]->arrive_and_wait();
+  cusim_warp_sync(w);
   T out;
   memcpy(&out, &r, sizeof(T));
   return out;
@@ -192,10 +275,10 @@ static inline unsigned __ballot_sync(unsigned, int pred) {
   unsigned w = t / 32, lane = t % 32;
   auto* c = cusim::ctx();
   c->warp_slot[w][lane] = pred ? 1ull : 0ull;
-  c->warp_bar[w]->arrive_and_wait();
+  cusim_warp_sync(w);
   unsigned nl = std::min(32u, c->nthreads - w * 32), m = 0;
   for (unsigned l = 0; l < nl; ++l) m |= (unsigned)c->warp_slot[w][l] << l;
-  c->warp_bar[w]->arrive_and_wait();
+  cusim_warp_sync(w);
   return m;
 }
 static inline int __all_sync(unsigned mask, int pred) {

@@ -111,6 +111,9 @@ inline Worker*& ctx() { static thread_local Worker* w = nullptr; return w; }
 inline std::mutex& atomic_mu() { static std::mutex m; return m; }
 inline TL& tl() { Worker* w = ctx(); return w->fib[w->cur].tl; }
 
+#if !defined(__x86_64__)
+#error "tests/cusim: the fiber switch is written for x86-64 (System V ABI)"
+#endif
 extern "C" void cusim_switch(void** save_sp, void* load_sp);
 // x86-64 System V: callee-saved registers on the old stack, swap stack pointers, restore, return into the new context
 __asm__(

@@ -285,14 +285,18 @@ alter_drr_kernel(const float* __restrict__ x, float* __restrict__ out, int T, in
   float alpha = (r1 != r1 || r2 != r2) ? NAN : fmaxf(r1, r2);  // torch.maximum propagates nan
   const float min_alpha = ml / me;
   alpha = (alpha != alpha || min_alpha != min_alpha) ? NAN : fmaxf(alpha, min_alpha);
-  // ensure_max_of_audio on the altered response
+  // ensure_max_of_audio on the altered response.  A non-finite alpha (a = 0: the row's early region does not meet
+  // the window, e.g. a second channel whose direct path lies > 2.5 ms from channel 0's) makes the reference's
+  // `alpha * window * early` NaN on the WHOLE row (NaN * 0), its peak NaN and its peak gain 1: same here.
+  const bool finite = (alpha - alpha) == 0.0f;
   const float peak = fmaxf(fmaxf(fabsf(alpha) * mew, meo), ml);
-  const float pg = (peak > max_abs) ? max_abs / peak : 1.0f;
+  const float pg = (finite && peak > max_abs) ? max_abs / peak : 1.0f;
   float* o = out + (size_t)row * T;
   for (int i = tid; i < T; i += DRR_T) {
-    float v = xr[i];
-    if ((i >= td - t0) && (i <= td + t0) && (i >= tw - t0) && (i <= tw + t0)) v = alpha * v;
-    o[i] = v * pg;
+    const float v = xr[i];
+    const bool e = (i >= td - t0) && (i <= td + t0), w = (i >= tw - t0) && (i <= tw + t0);
+    const float wf = w ? 1.0f : 0.0f, ev = e ? v : 0.0f, lv = e ? 0.0f : v;
+    o[i] = (alpha * wf * ev + (1.0f - wf) * ev + lv) * pg;  // the reference's expression, term by term (:642)
   }
 }
 

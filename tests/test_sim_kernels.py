@@ -168,7 +168,9 @@ def test_istft_random_geometries(eng):
 # dense DFT path (csrc/dft.cu): any window length, forward (+ mel from the materialised STFT) and inverse
 # ------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("n_fft,hop,T,pad_mode", [(400, 160, 3000, "reflect"), (96, 31, 1000, "constant"),
-                                                  (201, 50, 1500, "replicate"), (30, 7, 400, "reflect")])
+                                                  (201, 50, 1500, "replicate"), (30, 7, 400, "reflect"),
+                                                  (480, 120, 4000, "reflect"), (1200, 300, 6000, "constant"),
+                                                  (1001, 250, 5000, "replicate")])
 def test_dense_dft_any_window_length(eng, n_fft, hop, T, pad_mode):
     g = torch.Generator().manual_seed(n_fft)
     x = torch.randn(2, 2, T, generator=g)
@@ -196,6 +198,63 @@ def test_dense_dft_any_window_length(eng, n_fft, hop, T, pad_mode):
     y = eng.istft(out["stft"], n_fft, hop, w, length)
     y_ref = torch.istft(ref.reshape(4, *ref.shape[2:]), n_fft, hop, window=w, center=True, length=length).reshape(2, 2, -1)
     assert y.shape == y_ref.shape and rel_err(y, y_ref) < 5e-5
+
+
+def test_bypass_flags_and_batch1_impulse_response(eng):
+    """The per-filter bypass flags of fir_direct / fftconv / circconv copy the flagged rows through EXACTLY and leave the
+    others bit-identical to the un-flagged launch; a batch-1 impulse response is shared by every item (the reference's
+    broadcasting product, ref:audiotools/core/effects.py:106-114)."""
+    g = torch.Generator().manual_seed(2)
+    x = torch.randn(3, 2, 5000, generator=g)
+    byp = torch.tensor([False, True, False])
+    cut = torch.tensor([3000.0, 5000.0, 7000.0])
+    for zeros, hp in ((51, False), (51, True), (600, False)):  # 137 taps: direct kernel; 1601 taps: FFT engine
+        full = eng.sinc_filter(x, cut, 16000, zeros, highpass=hp)
+        part = eng.sinc_filter(x, cut, 16000, zeros, highpass=hp, bypass=byp)
+        assert torch.equal(part[1], x[1])
+        assert (part[[0, 2]] - full[[0, 2]]).abs().max() <= 2e-6 * full.abs().max()  # (the bank is sized by the selected items)
+    db = -torch.rand(3, 6, generator=g)
+    full, part = eng.equalizer(x, 16000, db), eng.equalizer(x, 16000, db, bypass=byp)
+    assert torch.equal(part[1], x[1]) and torch.equal(part[[0, 2]], full[[0, 2]])
+    ir = torch.randn(3, 1, 700, generator=g) * torch.exp(-torch.arange(700) / 90.0)
+    full, part = eng.circular_convolve(x, ir), eng.circular_convolve(x, ir, bypass=byp)
+    assert torch.equal(part[1], x[1]) and torch.equal(part[[0, 2]], full[[0, 2]])
+    one = eng.circular_convolve(x, ir[:1])  # batch-1 impulse response -> every item
+    assert rel_err(one, sp.convolve(x, ir[:1].expand(3, -1, -1))) < 1e-5
+    assert torch.equal(one, eng.circular_convolve(x, ir[:1].expand(3, -1, -1).contiguous()))
+
+
+def test_alter_drr_multichannel_vs_oracle(eng):
+    """b2a_alter_drr_f32 (one launch) against the oracle's restatement of decompose_ir / solve_alpha / alter_drr
+    (ref:audiotools/core/effects.py:540-647): stereo impulse responses whose channels peak at different samples (the
+    window is channel 0's early region for every channel), per-item targets, a response that needs the peak limit."""
+    g = torch.Generator().manual_seed(5)
+    sr, T = 16000, 6000
+    t = torch.arange(T) / sr
+    ir = 0.05 * torch.randn(3, 2, T, generator=g) * torch.exp(-t / 0.05)
+    ir[0, 0, 40] = 1.0; ir[0, 1, 55] = 0.9      # channel 1's direct path 15 samples later: inside channel 0's window
+    ir[1, 0, 200] = 0.7; ir[1, 1, 300] = 0.8    # ... and 100 samples later: outside it
+    ir[2, 0, 10] = 2.5; ir[2, 1, 10] = -0.2     # peak > 1 after re-weighting; channel 1's maximum is elsewhere
+    drr = torch.tensor([5.0, 20.0, -3.0])
+    out = eng.alter_drr(ir, sr, drr)
+    ref = sp.alter_drr(ir.clone(), sr, drr)
+    assert out.shape == ref.shape
+    # a channel whose early region misses channel 0's window has a = 0 in the quadratic: the reference's row is NaN
+    assert torch.isnan(ref[1, 1]).all() and torch.isnan(ref[2, 1]).all()
+    assert torch.equal(torch.isnan(out), torch.isnan(ref))
+    ok = ~torch.isnan(ref)
+    assert (out[ok] - ref[ok]).abs().max() < 1e-6
+
+
+def test_mfcc_dct_kernel(eng):
+    g = torch.Generator().manual_seed(1)
+    logmel = torch.randn(2, 2, 80, 37, generator=g)
+    dct = torch.randn(80, 40, generator=g)
+    out = eng.mel_dct(logmel, dct)
+    ref = (logmel.transpose(-1, -2) @ dct).transpose(-1, -2)
+    assert out.shape == ref.shape == (2, 2, 40, 37) and rel_err(out, ref) < 1e-6
+    out = eng.mel_dct(logmel[..., :5], dct[:, :33])  # a coefficient count that is not a multiple of the register tile
+    assert rel_err(out, (logmel[..., :5].transpose(-1, -2) @ dct[:, :33]).transpose(-1, -2)) < 1e-6
 
 
 # ------------------------------------------------------------------------------------------

@@ -200,6 +200,34 @@ def test_dense_dft_any_window_length(eng, n_fft, hop, T, pad_mode):
     assert y.shape == y_ref.shape and rel_err(y, y_ref) < 5e-5
 
 
+def test_dense_dft_random_geometries(eng):
+    """Random (window length, hop, length, padding) on the dense path against torch.stft / torch.istft: tile edges of the
+    64 x 64 x 16 product (lengths around the multiples), hop > window, single-frame signals, odd everything."""
+    rng = np.random.RandomState(1)
+    for it in range(12):
+        n_fft = int(rng.choice([2, 3, 17, 63, 65, 100, 127, 129, 250, 513, 600, 777]))
+        hop = int(rng.choice([1, max(1, n_fft // 4), max(1, n_fft // 2), n_fft, n_fft + 3, int(rng.randint(1, n_fft + 1))]))
+        hop = max(hop, n_fft // 64 + 1)  # keep the frame count (CPU time) bounded
+        T = int(rng.randint(n_fft // 2 + 1, 6 * n_fft + 200))
+        mode = ["reflect", "constant", "replicate"][it % 3]
+        g = torch.Generator().manual_seed(it)
+        x = torch.randn(2, 1, T, generator=g)
+        w = torch.hann_window(n_fft) + 0.05 + 0.1 * torch.rand(n_fft, generator=g) if n_fft > 2 else torch.ones(n_fft)
+        out = eng.spectral(x, n_fft, hop, w, pad_mode=mode)["stft"]
+        ref = torch.stft(x.reshape(2, T), n_fft, hop, window=w, center=True, return_complex=True)
+        assert out.shape[2:] == ref.shape[1:], (n_fft, hop, T)
+        assert rel_err(torch.view_as_real(out[:, 0]), torch.view_as_real(ref)) < 5e-6, (n_fft, hop, T)
+        if hop <= n_fft and (hop <= n_fft // 2 or n_fft <= 3):  # the envelope does not vanish
+            length = int(rng.randint(1, T + 1))
+            try:
+                y_ref = torch.istft(ref, n_fft, hop, window=w, center=True, length=length)
+            except RuntimeError:
+                continue
+            y = eng.istft(out, n_fft, hop, w, length)[:, 0]
+            keep = max(1, length - 2 * hop)
+            assert rel_err(y[..., :keep], y_ref[..., :keep]) < 1e-4, (n_fft, hop, T, length)
+
+
 def test_bypass_flags_and_batch1_impulse_response(eng):
     """The per-filter bypass flags of fir_direct / fftconv / circconv copy the flagged rows through EXACTLY and leave the
     others bit-identical to the un-flagged launch; a batch-1 impulse response is shared by every item (the reference's

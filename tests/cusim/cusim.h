@@ -166,9 +166,26 @@ inline void run_block(Worker* w, uint3 bid, dim3 block, dim3 grid) {
     for (int r = 0; r < 6; ++r) *--sp = nullptr;  // rbp rbx r12 r13 r14 r15
     f.sp = sp;
   }
+  // CUSIM_SHUFFLE=<seed>: visit the fibers in a fresh random order on every scheduling round instead of 0, 1, 2, ...
+  // A missing barrier that the fixed order happens to satisfy (the producer always runs first) then shows up as a
+  // wrong result: the poor man's racecheck (the suite is run under a few seeds before every GPU session).
+  static const unsigned long long shuffle_seed = [] {
+    const char* e = getenv("CUSIM_SHUFFLE");
+    return e ? strtoull(e, nullptr, 10) * 2654435761ull + 88172645463325252ull : 0ull;
+  }();
+  std::vector<unsigned> order(nt);
+  for (unsigned t = 0; t < nt; ++t) order[t] = t;
+  unsigned long long rng = shuffle_seed ^ ((unsigned long long)bid.x * 0x9E3779B97F4A7C15ull + bid.y * 7919ull + bid.z);
   unsigned alive = nt;
   while (alive) {
-    for (unsigned t = 0; t < nt; ++t) {
+    if (shuffle_seed) {
+      for (unsigned t = nt - 1; t > 0; --t) {
+        rng ^= rng << 13; rng ^= rng >> 7; rng ^= rng << 17;
+        std::swap(order[t], order[(unsigned)(rng % (t + 1))]);
+      }
+    }
+    for (unsigned k = 0; k < nt; ++k) {
+      const unsigned t = order[k];
       if (w->fib[t].done) continue;
       w->cur = t;
       cusim_switch(&w->sched_sp, w->fib[t].sp);

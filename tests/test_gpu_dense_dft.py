@@ -105,3 +105,29 @@ def test_istft_formerly_delegated_sizes(at, sp, n_fft, hop):
         torch.istft = real_istft
     y_ref = sp.istft(s.cpu(), 44100, 30000, n_fft, hop, "hann")
     assert y.shape == y_ref.shape and rel_err(y.cpu(), y_ref) < TOL
+
+
+def test_arbitrary_window_lengths_match_reference(at):
+    """GPU twin of tests/test_sim_signal_api.py::test_arbitrary_window_lengths_match_reference: the REAL reference's outputs."""
+    import os
+
+    from tests.golden import cases
+    from tests.golden import make_golden_anywindow as mg
+
+    g = np.load(os.path.join(os.path.dirname(mg.__file__), "reference_golden_anywindow.npz"))
+    x = cases.make_input("cfg1")
+    for key, wl, hop, wt, ms, pt in mg.STFT_CASES:
+        sig = at.AudioSignal(x.clone(), 16000).to(DEV)
+        X = sig.stft(window_length=wl, hop_length=hop, window_type=wt, match_stride=ms, padding_type=pt)
+        ref = torch.from_numpy(g[key + "_stft"])
+        assert X.shape[1:] == ref.shape[1:] and X.shape[0] == 4, key
+        assert rel_err(torch.view_as_real(X[:2].cpu()), torch.view_as_real(ref)) < TOL, key
+        assert elementwise_ok(X[:2].cpu().abs(), ref.abs()), key
+        y = sig.istft(window_length=wl, hop_length=hop, window_type=wt, match_stride=ms).audio_data
+        assert rel_err(y.cpu(), torch.from_numpy(g[key + "_istft"])) < TOL, key
+    mel = at.AudioSignal(x.clone(), 16000).to(DEV).mel_spectrogram(n_mels=80, window_length=400, hop_length=160,
+                                                                     window_type="hann")
+    assert rel_err(mel.cpu(), torch.from_numpy(g["w400_mel80"])) < TOL
+    mf = at.AudioSignal(x.clone(), 16000).to(DEV).mfcc(n_mfcc=20, n_mels=40, window_length=400, hop_length=160,
+                                                        window_type="hann")
+    assert rel_err(mf.cpu(), torch.from_numpy(g["w400_mfcc"])) < TOL

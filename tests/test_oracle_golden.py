@@ -257,3 +257,26 @@ def test_pitch_oracle_reproduces_committed_vectors():
     assert abs(spec.argmax() * mg.SR / mg.T - 440 * 2 ** (3 / 12)) < 2.0
     dc, _, _ = ps.pitch_shift_row(np.full(9000, 0.25, np.float32), 8000, -5.0)
     assert np.abs(dc[600:-1200] - 0.25).max() < 1e-6  # (the last frames are clamped to the end of the row)
+
+
+# ------------------------------------------------------------------------------------------
+# window lengths that are not powers of two: the oracle against the REAL reference (make_golden_anywindow.py)
+# ------------------------------------------------------------------------------------------
+def test_oracle_matches_reference_for_arbitrary_window_lengths():
+    import os
+
+    from tests.conftest import rel_err
+    from tests.golden import make_golden_anywindow as mg
+
+    g = np.load(os.path.join(os.path.dirname(mg.__file__), "reference_golden_anywindow.npz"))
+    x = cases.make_input("cfg1")
+    for key, wl, hop, wt, ms, pt in mg.STFT_CASES:
+        X = sp.stft(x, 16000, wl, hop, wt, ms, pt)
+        assert X.shape[2:] == g[key + "_stft"].shape[2:]
+        assert rel_err(torch.view_as_real(X[:2]), torch.view_as_real(torch.from_numpy(g[key + "_stft"]))) < 1e-6
+        y = sp.istft(X, 16000, 16000, wl, hop, wt, ms)
+        assert rel_err(y, torch.from_numpy(g[key + "_istft"])) < 1e-6
+    mel = sp.mel_spectrogram(x, 16000, 80, window_length=400, hop_length=160, window_type="hann")
+    assert rel_err(mel, torch.from_numpy(g["w400_mel80"])) < 1e-6
+    mf = sp.mfcc(x, 16000, 20, 40, window_length=400, hop_length=160, window_type="hann")
+    assert rel_err(mf, torch.from_numpy(g["w400_mfcc"])) < 1e-5

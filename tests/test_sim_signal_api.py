@@ -299,3 +299,25 @@ def test_mask_aware_transforms_equal_gather_scatter():
         b = t(sig.clone(), **kw).audio_data
         assert torch.equal(a, b), type(t).__name__
         assert torch.equal(a[~mask], x[~mask]), type(t).__name__
+
+
+def test_arbitrary_window_lengths_match_reference():
+    """stft / istft / mel_spectrogram / mfcc with windows that are not powers of two (dense-DFT kernels, csrc/dft.cu)
+    against the REAL reference's outputs (tests/golden/make_golden_anywindow.py): frame counts exactly, values to 1e-4."""
+    import os
+
+    from tests.golden import make_golden_anywindow as mg
+
+    g = np.load(os.path.join(os.path.dirname(mg.__file__), "reference_golden_anywindow.npz"))
+    for key, wl, hop, wt, ms, pt in mg.STFT_CASES:
+        sig = sig_of("cfg1")
+        X = sig.stft(window_length=wl, hop_length=hop, window_type=wt, match_stride=ms, padding_type=pt)
+        ref = torch.from_numpy(g[key + "_stft"])
+        assert X.shape[1:] == ref.shape[1:] and X.shape[0] == 4, key  # frame indexing bit-exact
+        assert rel_err(torch.view_as_real(X[:2]), torch.view_as_real(ref)) < TOL, key
+        y = sig.istft(window_length=wl, hop_length=hop, window_type=wt, match_stride=ms).audio_data
+        assert rel_err(y, torch.from_numpy(g[key + "_istft"])) < TOL, key
+    mel = sig_of("cfg1").mel_spectrogram(n_mels=80, window_length=400, hop_length=160, window_type="hann")
+    assert rel_err(mel, torch.from_numpy(g["w400_mel80"])) < TOL
+    mf = sig_of("cfg1").mfcc(n_mfcc=20, n_mels=40, window_length=400, hop_length=160, window_type="hann")
+    assert rel_err(mf, torch.from_numpy(g["w400_mfcc"])) < TOL

@@ -321,3 +321,24 @@ def test_arbitrary_window_lengths_match_reference():
     assert rel_err(mel, torch.from_numpy(g["w400_mel80"])) < TOL
     mf = sig_of("cfg1").mfcc(n_mfcc=20, n_mels=40, window_length=400, hop_length=160, window_type="hann")
     assert rel_err(mf, torch.from_numpy(g["w400_mfcc"])) < TOL
+
+
+def test_impulse_response_augmentation_properties():
+    """ref:tests/core/test_effects.py:305-329 on a synthetic room response (the reference's wav is an LFS pointer):
+    solve_alpha == 1 at the measured DRR; alter_drr hits a scalar and per-item target DRRs; shapes of the split."""
+    g = torch.Generator().manual_seed(11)
+    sr, T, B = 16000, 8000, 6
+    t = torch.arange(T) / sr
+    h = 0.2 * torch.randn(1, 1, T, generator=g) * torch.exp(-t / 0.08)
+    h[..., 60] = 1.0
+    ir_batch = AudioSignal(h.repeat(B, 1, 1), sr)
+    early, late, window = ir_batch.decompose_ir()
+    assert early.shape == late.shape == window.shape
+    drr = ir_batch.measure_drr()
+    alpha = AudioSignal.solve_alpha(early, late, window, drr)
+    assert np.allclose(alpha.numpy(), 1.0, atol=1e-5)
+    out = ir_batch.deepcopy().alter_drr(5)
+    assert np.allclose(out.measure_drr().numpy(), 5.0, atol=1e-4)
+    target = torch.from_numpy(np.random.RandomState(0).rand(B).astype("float32") * 50)
+    out = ir_batch.deepcopy().alter_drr(target)
+    assert np.allclose(out.measure_drr().numpy().flatten(), target.numpy(), atol=1e-3)

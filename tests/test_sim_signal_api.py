@@ -342,3 +342,20 @@ def test_impulse_response_augmentation_properties():
     target = torch.from_numpy(np.random.RandomState(0).rand(B).astype("float32") * 50)
     out = ir_batch.deepcopy().alter_drr(target)
     assert np.allclose(out.measure_drr().numpy().flatten(), target.numpy(), atol=1e-3)
+
+
+@pytest.mark.parametrize("mulaw", [False, True])
+def test_quantization_level_counts(mulaw):
+    """ref:tests/core/test_effects.py:262-302: a signal quantised to q channels holds at most q distinct levels
+    (rounded to 3 decimals, as the reference does for the straight-through residual), per item and for a scalar q."""
+    g = torch.Generator().manual_seed(3)
+    x = (0.2 * torch.randn(8, 1, 4000, generator=g)).clamp(-0.99, 0.99)  # (a sample at +1.0 is a (q+1)-th level in the reference too)
+    q = np.random.RandomState(0).choice([2, 4, 8, 16, 32, 64, 128], size=(8,), replace=True)
+    sig = AudioSignal(x.clone(), 16000)
+    out = (sig.mulaw_quantization(q) if mulaw else sig.quantization(q)).audio_data
+    for i, qc in enumerate(q):
+        assert len(np.unique(np.around(out[i].numpy(), decimals=3))) <= qc, (i, qc)
+    for qc in (2, 16, 128):
+        sig = AudioSignal(x[:1].clone(), 16000)
+        o = (sig.mulaw_quantization(qc) if mulaw else sig.quantization(qc)).audio_data
+        assert len(np.unique(np.around(o.numpy(), decimals=3))) <= qc

@@ -144,6 +144,35 @@ def test_spectral_modes_agree(eng, golden):
     assert torch.equal(b["mel"], eng.spectral(x[:2], 256, 100, w2, mel_fb=fb2, mel_lo=lo2, mel_hi=hi2, want_stft=False)["mel"])
 
 
+def test_fft_kernels_random_geometries(eng):
+    """The fused FFT kernels (window lengths 32 .. 4096, incl. the lean-twiddle N = 1024 case) at random hops, lengths,
+    padding modes, per-item gains and mel sizes against torch.stft + the reference's |X| @ fb.T: frame counts exactly,
+    STFT to 2e-6 of the tensor maximum, mel to 1e-5, the scaled waveform exactly x * gain."""
+    rng = np.random.RandomState(7)
+    for it in range(14):
+        n_fft = int(rng.choice([32, 64, 128, 256, 512, 1024, 2048, 2048, 4096]))
+        hop = int(rng.choice([n_fft // 4, n_fft // 2, n_fft, max(1, n_fft // 8), int(rng.randint(max(1, n_fft // 16), n_fft + 1))]))
+        T = int(rng.randint(n_fft // 2 + 1, 5 * n_fft + 300))
+        mode = ["reflect", "constant", "replicate"][it % 3]
+        B, C = int(rng.randint(1, 3)), int(rng.randint(1, 3))
+        g = torch.Generator().manual_seed(100 + it)
+        x = torch.randn(B, C, T, generator=g)
+        w = torch.hann_window(n_fft) + 0.05 + 0.1 * torch.rand(n_fft, generator=g)
+        gain = 0.25 + torch.rand(B, generator=g)
+        n_mels = int(rng.choice([8, 20, 40]))
+        fb, lo, hi = _mel_tables(16000, n_fft, n_mels)
+        out = eng.spectral(x, n_fft, hop, w, pad_mode=mode, gain=gain, want_scaled=True, mel_fb=fb, mel_lo=lo, mel_hi=hi,
+                           want_stft=True)
+        xs = x * gain[:, None, None]
+        ref = torch.stft(xs.reshape(B * C, T), n_fft, hop, window=w, center=True, return_complex=True)
+        ref = ref.reshape(B, C, *ref.shape[1:])
+        assert out["stft"].shape == ref.shape, (n_fft, hop, T)
+        assert torch.equal(out["scaled"], xs)
+        assert rel_err(torch.view_as_real(out["stft"]), torch.view_as_real(ref)) < 2e-6, (n_fft, hop, T, mode)
+        mel_ref = (ref.abs().transpose(2, 3) @ fb.T).transpose(2, 3)
+        assert rel_err(out["mel"], mel_ref) < 1e-5, (n_fft, hop, T, n_mels)
+
+
 def test_istft_random_geometries(eng):
     """Random (n_fft, hop, frames, length) against torch.istft: segment boundaries, warm-up, carries, tail fill."""
     rng = np.random.RandomState(0)
